@@ -1,0 +1,26 @@
+# Builds the product library (CUDA kernels + C ABI + host pipeline) and the test-only CPU oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+GENCODE := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 $(GENCODE) -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-sign-compare
+CSRC := glnexus_b200/csrc
+HOST_SRCS := $(CSRC)/glx_host.cc $(CSRC)/glx_host_c.cc $(CSRC)/glx_presets.cc $(CSRC)/glx_synth.cc
+HOST_OBJS := $(HOST_SRCS:.cc=.o)
+
+all: glnexus_b200/libglx.so oracle/libglx_oracle.so
+
+$(CSRC)/%.o: $(CSRC)/%.cc $(CSRC)/glx_host.hpp include/glx.h include/glx_host.h
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(CSRC)/glx_device.o: $(CSRC)/glx_device.cu $(wildcard $(CSRC)/*.cuh) include/glx.h
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(CSRC)/glx_device.ptxas.log || (cat $(CSRC)/glx_device.ptxas.log; false)
+
+glnexus_b200/libglx.so: $(HOST_OBJS) $(CSRC)/glx_device.o
+	$(NVCC) -shared $(GENCODE) -o $@ $^ -cudart static -lpthread
+
+oracle/libglx_oracle.so: oracle/glx_oracle.cc include/glx.h
+	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -o $@ $< -lpthread
+
+clean:
+	rm -f $(CSRC)/*.o glnexus_b200/libglx.so oracle/libglx_oracle.so $(CSRC)/*.ptxas.log

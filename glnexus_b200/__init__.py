@@ -1,0 +1,6 @@
+"""glnexus_b200 — B200-native joint genotyper behind the GLnexus genotype_site interface.
+
+Only the hot path lives here: the CUDA kernels + C ABI (csrc/, built into libglx.so) and the thin
+host-side mirror of the reference's interface (api.py). See DESIGN.md.
+"""
+from .api import Batch, Context, GlxError, Out, SynthParams, lib, preset_text  # noqa: F401

@@ -1,0 +1,301 @@
+"""ctypes binding of libglx.so (include/glx.h + include/glx_host.h).
+
+The library is the product: CUDA kernels for sm_100a behind a C ABI plus the C++ host pipeline
+(decode -> pack -> assemble). There is no CPU fallback: if the shared library is missing or a CUDA call
+fails, the calls below raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libglx.so")
+
+GLX_OK = 0
+STATUS_NAMES = {0: "OK", -1: "Failure", -2: "Invalid", -3: "NotFound", -4: "Exists", -5: "IOError",
+                -6: "NotImplemented", -7: "Aborted", -100: "CudaError", -101: "Unsupported"}
+
+
+class GlxError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        self.status = STATUS_NAMES.get(code, str(code))
+        super().__init__(f"{self.status}: {msg}" if msg else self.status)
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("n_samples", C.c_uint32), ("n_sites", C.c_uint32), ("seed", C.c_uint64),
+                ("region_beg", C.c_int32), ("region_len", C.c_int32), ("max_alt", C.c_uint32),
+                ("frac_multiallelic", C.c_float), ("frac_indel", C.c_float), ("af_max", C.c_float),
+                ("band_mean_len", C.c_float), ("frac_uncovered", C.c_float), ("frac_two_record_cells", C.c_float),
+                ("frac_lost_allele", C.c_float), ("frac_homalt", C.c_float), ("gatk_style", C.c_uint8),
+                ("_pad", C.c_uint8 * 3)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libglx.so; fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make` or __graft_entry__.build(); "
+                          "glnexus_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, sz = C.c_void_p, C.c_char_p, C.c_size_t
+    L.glxh_batch_from_text.argtypes = [cp, cp, cp, C.c_int, C.POINTER(cp), C.POINTER(cp), cp, C.c_int, C.POINTER(vp), cp, sz]
+    L.glxh_batch_from_text.restype = C.c_int
+    L.glxh_synth_batch.argtypes = [cp, C.POINTER(SynthParams), C.POINTER(vp), cp, sz]
+    L.glxh_synth_batch.restype = C.c_int
+    L.glxh_batch_free.argtypes = [vp]
+    L.glxh_batch_free.restype = None
+    for fn in ("glxh_config", "glxh_records", "glxh_sites"):
+        getattr(L, fn).argtypes = [vp]
+        getattr(L, fn).restype = vp
+    L.glxh_n_fields.argtypes = [vp]
+    L.glxh_n_fields.restype = C.c_uint32
+    L.glxh_device_supported.argtypes = [vp]
+    L.glxh_device_supported.restype = C.c_int
+    L.glxh_out_alloc.argtypes = [vp, C.c_int]
+    L.glxh_out_alloc.restype = vp
+    L.glxh_out_free.argtypes = [vp]
+    L.glxh_out_free.restype = None
+    L.glxh_out_struct.argtypes = [vp]
+    L.glxh_out_struct.restype = vp
+    L.glxh_out_array.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.glxh_out_array.restype = C.c_int
+    L.glxh_assemble_vcf.argtypes = [vp, vp, C.POINTER(vp), cp, sz]
+    L.glxh_assemble_vcf.restype = C.c_int
+    L.glxh_free_text.argtypes = [vp]
+    L.glxh_free_text.restype = None
+    L.glxh_preset_text.argtypes = [cp, C.POINTER(vp)]
+    L.glxh_preset_text.restype = C.c_int
+    L.glxh_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.glxh_batch_stats.restype = None
+    # device ABI
+    L.glx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.glx_create.restype = C.c_int
+    L.glx_destroy.argtypes = [vp]
+    L.glx_destroy.restype = None
+    L.glx_last_error.argtypes = [vp]
+    L.glx_last_error.restype = cp
+    L.glx_genotype_batch.argtypes = [vp, vp, vp, vp, vp]
+    L.glx_genotype_batch.restype = C.c_int
+    L.glx_upload.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
+    L.glx_upload.restype = C.c_int
+    L.glx_launch.argtypes = [vp, vp, vp]
+    L.glx_launch.restype = C.c_int
+    L.glx_download.argtypes = [vp, vp, vp]
+    L.glx_download.restype = C.c_int
+    L.glx_check.argtypes = [vp, vp]
+    L.glx_check.restype = C.c_int
+    L.glx_out_bytes.argtypes = [vp]
+    L.glx_out_bytes.restype = C.c_uint64
+    L.glx_in_bytes.argtypes = [vp]
+    L.glx_in_bytes.restype = C.c_uint64
+    L.glx_launch_count.argtypes = [vp]
+    L.glx_launch_count.restype = C.c_int
+    L.glx_free_batch.argtypes = [vp, vp]
+    L.glx_free_batch.restype = None
+    L.glx_synchronize.argtypes = [vp]
+    L.glx_synchronize.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _b(s):
+    return None if s is None else s.encode()
+
+
+class Out:
+    """Host output columns of one batch (glx_out)."""
+    WHICH = {"gt": (0, np.int8), "rnc": (1, np.uint8), "allele_used": (2, np.uint32), "site_flags": (3, np.uint8)}
+
+    def __init__(self, batch, pinned=False):
+        self._batch = batch
+        self.handle = lib().glxh_out_alloc(batch.handle, 1 if pinned else 0)
+        if not self.handle:
+            raise MemoryError("glxh_out_alloc")
+        self.ptr = lib().glxh_out_struct(self.handle)
+
+    def array(self, which):
+        if isinstance(which, str):
+            idx, dt = self.WHICH[which]
+        else:
+            idx, dt = 16 + int(which), np.int32
+        p, n = C.c_void_p(), C.c_uint64()
+        rc = lib().glxh_out_array(self.handle, idx, C.byref(p), C.byref(n))
+        if rc != GLX_OK:
+            raise GlxError(rc, "glxh_out_array")
+        if n.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_uint8 * n.value).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt)
+
+    def arrays(self):
+        d = {k: self.array(k) for k in self.WHICH}
+        for k in range(self._batch.n_fields):
+            d[f"fld{k}"] = self.array(k)
+        return d
+
+    def nbytes(self):
+        return sum(a.nbytes for a in self.arrays().values())
+
+    def close(self):
+        if self.handle:
+            lib().glxh_out_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """One contig-range batch: flattened config + columnar record store + unified sites."""
+
+    def __init__(self, handle):
+        self.handle = handle
+        L = lib()
+        self.config_ptr = L.glxh_config(handle)
+        self.records_ptr = L.glxh_records(handle)
+        self.sites_ptr = L.glxh_sites(handle)
+        self.n_fields = L.glxh_n_fields(handle)
+        st = (C.c_uint64 * 8)()
+        L.glxh_batch_stats(handle, st)
+        self.n_sites, self.n_samples, self.n_records, self.n_datasets = st[0], st[1], st[2], st[3]
+        self.input_bytes = st[4]
+        self.variant_records = st[5]
+
+    @classmethod
+    def from_text(cls, sites_text, datasets, preset=None, config_text=None, contig=None, test_ingest_rules=False):
+        L = lib()
+        n = len(datasets)
+        names = (C.c_char_p * max(n, 1))(*[_b(d[0]) for d in datasets])
+        texts = (C.c_char_p * max(n, 1))(*[_b(d[1]) for d in datasets])
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = L.glxh_batch_from_text(_b(preset), _b(config_text), _b(sites_text), n, names, texts, _b(contig),
+                                    1 if test_ingest_rules else 0, C.byref(h), err, len(err))
+        if rc != GLX_OK:
+            raise GlxError(rc, err.value.decode(errors="replace"))
+        return cls(h)
+
+    @classmethod
+    def synthetic(cls, params, preset="DeepVariant"):
+        L = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = L.glxh_synth_batch(_b(preset), C.byref(params), C.byref(h), err, len(err))
+        if rc != GLX_OK:
+            raise GlxError(rc, err.value.decode(errors="replace"))
+        return cls(h)
+
+    @property
+    def device_supported(self):
+        return bool(lib().glxh_device_supported(self.handle))
+
+    def alloc_out(self, pinned=False):
+        return Out(self, pinned)
+
+    def assemble_vcf(self, out):
+        t = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = lib().glxh_assemble_vcf(self.handle, out.ptr, C.byref(t), err, len(err))
+        if rc != GLX_OK:
+            raise GlxError(rc, err.value.decode(errors="replace"))
+        try:
+            return C.string_at(t.value).decode()
+        finally:
+            lib().glxh_free_text(t)
+
+    def close(self):
+        if self.handle:
+            lib().glxh_batch_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBatch:
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    def launch(self, stream=None):
+        self.ctx._check(lib().glx_launch(self.ctx.handle, self.handle, C.c_void_p(stream or 0)))
+
+    def check(self):
+        self.ctx._check(lib().glx_check(self.ctx.handle, self.handle))
+
+    def download(self, out):
+        self.ctx._check(lib().glx_download(self.ctx.handle, self.handle, out.ptr))
+
+    @property
+    def out_bytes(self):
+        return lib().glx_out_bytes(self.handle)
+
+    @property
+    def in_bytes(self):
+        return lib().glx_in_bytes(self.handle)
+
+    @property
+    def launch_count(self):
+        return lib().glx_launch_count(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib().glx_free_batch(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class Context:
+    """glx_ctx: one per process and GPU."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = lib().glx_create(C.byref(h), int(device))
+        if rc != GLX_OK:
+            raise GlxError(rc, "glx_create failed (no usable CUDA device?)")
+        self.handle = h
+
+    def _check(self, rc):
+        if rc != GLX_OK:
+            msg = lib().glx_last_error(self.handle)
+            raise GlxError(rc, msg.decode(errors="replace") if msg else "")
+
+    def genotype_batch(self, batch, out):
+        """Host buffers in, host buffers out (H2D + kernels + D2H)."""
+        self._check(lib().glx_genotype_batch(self.handle, batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr))
+
+    def upload(self, batch):
+        d = C.c_void_p()
+        self._check(lib().glx_upload(self.handle, batch.config_ptr, batch.records_ptr, batch.sites_ptr, C.byref(d)))
+        return DeviceBatch(self, d)
+
+    def synchronize(self):
+        self._check(lib().glx_synchronize(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib().glx_destroy(self.handle)
+            self.handle = None
+
+
+def preset_text(name):
+    t = C.c_void_p()
+    rc = lib().glxh_preset_text(_b(name), C.byref(t))
+    if rc != GLX_OK:
+        raise GlxError(rc, f"unknown configuration preset {name}")
+    try:
+        return C.string_at(t.value).decode()
+    finally:
+        lib().glxh_free_text(t)

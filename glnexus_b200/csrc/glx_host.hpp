@@ -1,0 +1,256 @@
+// glx_host.hpp — host side of the B200 genotyper: the reference-facing types and the
+// decode -> pack -> (device) -> assemble pipeline around the C ABI in include/glx.h.
+//
+// Mirrors (names, argument meaning, error behaviour) the pieces of GLnexus the hot path touches:
+//   Status / StatusCode            include/types.h:31-128
+//   range, allele                  include/types.h:139-264
+//   unified_allele, unified_site   include/types.h:434-506
+//   retained_format_field          include/types.h:652-698
+//   genotyper_config               include/types.h:700-776
+//   Service::genotype_sites        src/service.cc:302-428   (glx::genotype_sites below)
+// RocksDB/htslib are not available in this image; the decoded-record type GvcfRecord
+// stands in for an unpacked bcf1_t and read_vcf_text() for htslib's VCF reader.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/glx.h"
+
+namespace glx {
+
+enum class StatusCode { OK, FAILURE, INVALID, NOT_FOUND, EXISTS, IO_ERROR, NOT_IMPLEMENTED, ABORTED };
+
+class Status {
+    StatusCode code_;
+    std::string msg_;
+
+public:
+    Status(StatusCode code = StatusCode::OK, const std::string& msg = "", const std::string& noun = "")
+        : code_(code), msg_(noun.empty() ? msg : msg + " (" + noun + ")") {}
+    bool ok() const { return code_ == StatusCode::OK; }
+    bool bad() const { return !ok(); }
+    operator StatusCode() const { return code_; }
+    StatusCode code() const { return code_; }
+    int c_code() const { return -static_cast<int>(code_); }
+    static Status OK() { return Status(); }
+#define GLX_STATUS_SUGAR(nm, code) \
+    static Status nm(const std::string& msg = "", const std::string& noun = "") { return Status(code, msg, noun); }
+    GLX_STATUS_SUGAR(Failure, StatusCode::FAILURE)
+    GLX_STATUS_SUGAR(Invalid, StatusCode::INVALID)
+    GLX_STATUS_SUGAR(NotFound, StatusCode::NOT_FOUND)
+    GLX_STATUS_SUGAR(Exists, StatusCode::EXISTS)
+    GLX_STATUS_SUGAR(IOError, StatusCode::IO_ERROR)
+    GLX_STATUS_SUGAR(NotImplemented, StatusCode::NOT_IMPLEMENTED)
+    GLX_STATUS_SUGAR(Aborted, StatusCode::ABORTED)
+    std::string str() const;
+};
+#define GLX_S(st)              \
+    do {                       \
+        s = (st);              \
+        if (s.bad()) return s; \
+    } while (0)
+
+bool is_dna(const std::string& s);
+bool is_iupac_nucleotides(const std::string& s);
+bool is_symbolic_allele(const std::string& s);
+
+struct range {
+    int rid = -1, beg = -1, end = -1;
+    range() = default;
+    range(int rid_, int beg_, int end_) : rid(rid_), beg(beg_), end(end_) {}
+    size_t size() const { return end - beg; }
+    bool operator==(const range& r) const { return rid == r.rid && beg == r.beg && end == r.end; }
+    bool operator!=(const range& r) const { return !(*this == r); }
+    bool operator<(const range& r) const {
+        return rid < r.rid || (rid == r.rid && (beg < r.beg || (beg == r.beg && end < r.end)));
+    }
+    bool overlaps(const range& r) const { return rid == r.rid && end > r.beg && beg < r.end; }
+    bool within(const range& r) const { return rid == r.rid && beg >= r.beg && end <= r.end; }
+    bool contains(const range& r) const { return r.within(*this); }
+};
+
+struct allele {
+    range pos;
+    std::string dna;
+    allele(const range& pos_, const std::string& dna_) : pos(pos_), dna(dna_) {}
+    bool operator==(const allele& rhs) const { return pos == rhs.pos && dna == rhs.dna; }
+    bool operator<(const allele& rhs) const { return pos < rhs.pos || (pos == rhs.pos && dna < rhs.dna); }
+};
+
+struct unified_allele {
+    std::string dna;
+    allele normalized;
+    int quality = 0;
+    float frequency = NAN;
+    unified_allele(const range& pos, const std::string& dna_) : dna(dna_), normalized(pos, dna_) {}
+};
+
+struct unified_site {
+    range pos;
+    range in_target;
+    std::vector<unified_allele> alleles;
+    std::map<allele, int> unification;
+    float lost_allele_frequency = 0.0f;
+    int qual = 0;
+    bool monoallelic = false;
+    explicit unified_site(const range& pos_) : pos(pos_), in_target(-1, -1, -1) {}
+    void fill_implicit_unification();
+};
+
+enum class GLnexusOutputFormat { BCF, VCF };
+enum class RetainedFieldFrom { FORMAT, INFO };
+enum class RetainedFieldType { INT, FLOAT, STRING };
+enum class FieldCombinationMethod { MIN, MAX, MISSING, SEMICOLON };
+enum class RetainedFieldNumber { BASIC, ALT, GENOTYPE, ALLELES };
+enum class DefaultValueFiller { MISSING = 0, ZERO, NONE };
+
+struct retained_format_field {
+    std::vector<std::string> orig_names;
+    std::string name;
+    std::string description;
+    RetainedFieldFrom from = RetainedFieldFrom::FORMAT;
+    RetainedFieldType type = RetainedFieldType::INT;
+    RetainedFieldNumber number = RetainedFieldNumber::BASIC;
+    int count = 0;
+    DefaultValueFiller default_type = DefaultValueFiller::MISSING;
+    FieldCombinationMethod combi_method = FieldCombinationMethod::MISSING;
+    bool ignore_non_variants = false;
+};
+
+struct genotyper_config {
+    bool revise_genotypes = false;
+    float min_assumed_allele_frequency = 0.0001f;
+    float snv_prior_calibration = 1.0f, indel_prior_calibration = 1.0f;
+    size_t required_dp = 0;
+    bool allow_partial_data = false;
+    std::string allele_dp_format = "AD";
+    std::string ref_dp_format = "MIN_DP";
+    bool output_residuals = false;
+    GLnexusOutputFormat output_format = GLnexusOutputFormat::BCF;
+    std::vector<retained_format_field> liftover_fields;
+    bool more_PL = false;
+    bool squeeze = false;
+    bool trim_uncalled_alleles = false;
+    bool top_two_half_calls = false;
+
+    // line-oriented text form used by the fixtures and the CLI (see config_of_text)
+    static Status of_text(const std::string& txt, genotyper_config& ans);
+    std::string text() const;
+};
+
+// `glnexus_cli --config NAME` presets (src/cli_utils.cc:465-1188), genotyper half.
+Status load_config_preset(const std::string& name, genotyper_config& ans);
+std::vector<std::string> config_preset_names();
+
+// ---------------------------------------------------------------------------------------------
+// Decoded gVCF record: what an unpacked bcf1_t + its header give the reference through
+// bcf_get_genotypes / bcf_get_format_int32 / bcf_get_info_* (htslib 1.9).
+// ---------------------------------------------------------------------------------------------
+struct FieldValues {
+    std::string id;
+    uint8_t type = GLX_TYPE_INT;  // header Type: Integer / Float / other (STRING)
+    int per_sample = 0;           // values per sample (FORMAT) or total (INFO)
+    std::vector<int32_t> v;       // int32 or float bits; n_sample*per_sample
+};
+
+struct GvcfRecord {
+    int rid = 0, pos = 0, rlen = 0;
+    float qual = NAN;
+    bool qual_missing = true;
+    std::vector<std::string> alleles;
+    std::vector<std::string> filters;  // FILTER ids as written ("PASS" included)
+    int n_sample = 0;
+    int n_gt = 0;                      // GT values per sample (1 haploid, 2 diploid), 0 = no GT
+    std::vector<int32_t> gt;           // htslib GT ints, n_sample*n_gt
+    std::vector<FieldValues> format;
+    std::vector<FieldValues> info;
+    range rng() const { return range(rid, pos, pos + rlen); }
+};
+
+struct GvcfDataset {
+    std::string name;
+    std::vector<std::string> samples;
+    std::vector<GvcfRecord> records;
+};
+
+struct VcfHeaderInfo {
+    std::vector<std::pair<std::string, size_t>> contigs;
+    std::map<std::string, uint8_t> format_types, info_types;  // GLX_TYPE_*
+};
+
+// Minimal VCF text reader (stand-in for htslib's). `test_ingest_rules` applies what VCFData /
+// validate_bcf do at ingest in the reference's tests (test/utils.cc:75-84, src/BCF_utils.cc:54-66).
+Status read_vcf_text(const std::string& text, const std::string& dataset_name, bool test_ingest_rules,
+                     VcfHeaderInfo& hdr, GvcfDataset& ans);
+
+Status sites_of_text(const std::string& txt, const std::vector<std::pair<std::string, size_t>>& contigs,
+                     std::vector<unified_site>& ans);
+
+// ---------------------------------------------------------------------------------------------
+// Packed batch: owns every array the C ABI structs point at.
+// ---------------------------------------------------------------------------------------------
+struct PackedBatch {
+    glx_config cfg{};
+    glx_records recs{};
+    glx_sites sites{};
+    // metadata for output assembly
+    genotyper_config gcfg;
+    std::vector<unified_site> usites;
+    std::vector<std::string> sample_names;
+    std::vector<std::pair<std::string, size_t>> contigs;
+    std::vector<std::string> filter_names;
+    std::vector<const char*> filter_name_ptrs;
+    // storage
+    std::vector<uint64_t> ds_rec_off;
+    std::vector<uint32_t> ds_n_sample, ds_sample_off;
+    std::vector<int32_t> sample_out;
+    std::vector<int32_t> r_beg, r_end, r_maxend;
+    std::vector<float> r_qual;
+    std::vector<uint8_t> r_n_allele, r_flags;
+    std::vector<uint32_t> r_filt, r_gt, r_allele_off;
+    std::vector<int32_t> col_val;
+    std::vector<uint16_t> col_len;
+    std::vector<int32_t> pool, gt_pool;
+    std::vector<uint32_t> al_len, al_str;
+    std::vector<uint8_t> al_flags;
+    std::vector<uint64_t> al_prefix;
+    std::vector<char> al_pool;
+    std::vector<int32_t> s_beg, s_end, s_qbeg, s_qend;
+    std::vector<uint8_t> s_n_allele, s_mono, s_is_indel, u_to;
+    std::vector<uint32_t> s_allele_off, s_unif_off, u_len, u_str;
+    std::vector<float> s_af, s_hom_prior, s_lost_prior, s_lost_af;
+    std::vector<int32_t> u_beg, u_end;
+    std::vector<uint64_t> u_prefix;
+    std::vector<char> u_pool;
+    std::vector<uint16_t> fld_cnt[GLX_MAX_FIELDS];
+    std::vector<uint64_t> fld_off[GLX_MAX_FIELDS];
+    void rebind();  // refresh the raw pointers after the vectors are final
+};
+
+struct OutBuffers {
+    glx_out out{};
+    std::vector<int8_t> gt;
+    std::vector<uint8_t> rnc, site_flags;
+    std::vector<int32_t> fld[GLX_MAX_FIELDS];
+    std::vector<uint32_t> allele_used;
+    void allocate(const PackedBatch& b);
+};
+
+Status make_glx_config(const genotyper_config& cfg, glx_config& ans);
+Status pack_sites(const genotyper_config& cfg, const std::vector<unified_site>& sites, uint32_t n_samples,
+                  PackedBatch& b);
+// samples = sorted sample names of the sample set (Service::genotype_sites, src/service.cc:307-309)
+Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInfo& hdr,
+                    const std::vector<std::string>& samples, PackedBatch& b);
+
+// Output assembly = src/genotyper.cc:862-1003 after the per-dataset loop + the pVCF header of
+// src/service.cc:190-241, written as VCF text (htslib vcf_format value semantics).
+Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& vcf_text);
+
+}  // namespace glx

@@ -1,0 +1,218 @@
+// glx_host_c.cc — C entry points of include/glx_host.h over the C++ host pipeline.
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/glx_host.h"
+#include "glx_host.hpp"
+
+// provided by the CUDA translation unit (glx_device.cu)
+extern "C" void* glx_pinned_alloc(size_t bytes);
+extern "C" void glx_pinned_free(void* p);
+
+struct glxh_batch {
+    glx::PackedBatch b;
+};
+
+struct glxh_out {
+    glx_out out{};
+    bool pinned = false;
+    uint32_t n_fields = 0;
+    uint64_t n_gt = 0, n_sites = 0;
+    uint64_t n_fld[GLX_MAX_FIELDS] = {};
+};
+
+namespace {
+
+int fail(const glx::Status& s, char* err, size_t errlen) {
+    if (err && errlen) snprintf(err, errlen, "%s", s.str().c_str());
+    return s.c_code();
+}
+
+void* out_alloc(size_t bytes, bool pinned) {
+    if (bytes == 0) bytes = 16;
+    void* p = pinned ? glx_pinned_alloc(bytes) : malloc(bytes);
+    if (p) memset(p, 0, bytes);
+    return p;
+}
+void out_release(void* p, bool pinned) {
+    if (!p) return;
+    if (pinned) glx_pinned_free(p);
+    else free(p);
+}
+
+}  // namespace
+
+extern "C" {
+
+int glxh_batch_from_text(const char* preset, const char* config_text, const char* sites_text, int n_datasets, const char* const* dataset_names,
+                         const char* const* vcf_texts, const char* contig, int test_ingest_rules, glxh_batch** ans, char* err, size_t errlen) {
+    using namespace glx;
+    if (!ans || !sites_text || n_datasets < 0) return GLX_E_INVALID;
+    *ans = nullptr;
+    Status s;
+    genotyper_config cfg;
+    if (preset && *preset) {
+        s = load_config_preset(preset, cfg);
+        if (s.bad()) return fail(s, err, errlen);
+    }
+    if (config_text && *config_text) {
+        s = genotyper_config::of_text(config_text, cfg);
+        if (s.bad()) return fail(s, err, errlen);
+    }
+    std::vector<GvcfDataset> datasets(n_datasets);
+    VcfHeaderInfo hdr0, hdr_all;
+    for (int i = 0; i < n_datasets; i++) {
+        VcfHeaderInfo h;
+        s = read_vcf_text(vcf_texts[i], dataset_names[i], test_ingest_rules != 0, h, datasets[i]);
+        if (s.bad()) return fail(s, err, errlen);
+        if (i == 0) hdr0 = h;  // VCFData::contigs serves the first dataset's contigs (test/utils.cc:128-131)
+        for (const auto& p : h.format_types) hdr_all.format_types.insert(p);
+        for (const auto& p : h.info_types) hdr_all.info_types.insert(p);
+    }
+    hdr_all.contigs = hdr0.contigs;
+    // every dataset must number contigs the same way for rid comparisons to be meaningful
+    std::vector<unified_site> sites;
+    s = sites_of_text(sites_text, hdr_all.contigs, sites);
+    if (s.bad()) return fail(s, err, errlen);
+    int rid = -1;
+    if (contig) {
+        for (size_t i = 0; i < hdr_all.contigs.size(); i++)
+            if (hdr_all.contigs[i].first == contig) rid = (int)i;
+        if (rid < 0) return fail(Status::Invalid("glxh_batch_from_text: unknown contig", contig), err, errlen);
+        std::vector<unified_site> keep;
+        for (auto& us : sites)
+            if (us.pos.rid == rid) keep.push_back(us);
+        sites.swap(keep);
+    } else if (!sites.empty()) {
+        rid = sites[0].pos.rid;
+        for (auto& us : sites)
+            if (us.pos.rid != rid) return fail(Status::Invalid("glxh_batch_from_text: sites span several contigs; pass `contig`"), err, errlen);
+    }
+    for (int i = 0; i < n_datasets; i++) {
+        // records of other contigs are outside this range batch; contig names resolve per dataset header
+        std::vector<GvcfRecord> keep;
+        for (auto& r : datasets[i].records)
+            if (rid < 0 || r.rid == rid) keep.push_back(std::move(r));
+        datasets[i].records.swap(keep);
+    }
+    std::set<std::string> sample_set;
+    for (const auto& ds : datasets) {
+        for (const auto& sm : ds.samples) {
+            if (!sample_set.insert(sm).second) return fail(Status::Invalid("sample is duplicated", sm), err, errlen);
+        }
+    }
+    std::vector<std::string> samples(sample_set.begin(), sample_set.end());
+    auto* b = new glxh_batch();
+    s = pack_sites(cfg, sites, (uint32_t)samples.size(), b->b);
+    if (s.ok()) s = pack_records(datasets, hdr_all, samples, b->b);
+    if (s.bad()) {
+        delete b;
+        return fail(s, err, errlen);
+    }
+    *ans = b;
+    return GLX_OK;
+}
+
+void glxh_batch_free(glxh_batch* b) { delete b; }
+const glx_config* glxh_config(const glxh_batch* b) { return &b->b.cfg; }
+const glx_records* glxh_records(const glxh_batch* b) { return &b->b.recs; }
+const glx_sites* glxh_sites(const glxh_batch* b) { return &b->b.sites; }
+uint32_t glxh_n_fields(const glxh_batch* b) { return b->b.cfg.n_fields; }
+
+int glxh_device_supported(const glxh_batch* b) {
+    const glx_records& r = b->b.recs;
+    if (r.n_datasets != r.n_samples_out) return 0;
+    for (uint32_t d = 0; d < r.n_datasets; d++)
+        if (r.ds_n_sample[d] != 1 || r.sample_out[r.ds_sample_off[d]] != (int32_t)d) return 0;
+    return 1;
+}
+
+void glxh_batch_stats(const glxh_batch* hb, uint64_t st[8]) {
+    const glx::PackedBatch& b = hb->b;
+    auto bytes = [](const auto& v) { return (uint64_t)v.size() * sizeof(v[0]); };
+    st[0] = b.sites.n_sites;
+    st[1] = b.sites.n_samples;
+    st[2] = b.recs.n_records;
+    st[3] = b.recs.n_datasets;
+    uint64_t in = bytes(b.ds_rec_off) + bytes(b.r_beg) + bytes(b.r_end) + bytes(b.r_maxend) + bytes(b.r_qual) + bytes(b.r_n_allele) + bytes(b.r_flags) +
+                  bytes(b.r_filt) + bytes(b.r_gt) + bytes(b.r_allele_off) + bytes(b.col_val) + bytes(b.col_len) + bytes(b.pool) + bytes(b.gt_pool) +
+                  bytes(b.al_len) + bytes(b.al_str) + bytes(b.al_flags) + bytes(b.al_prefix) + bytes(b.al_pool) + bytes(b.s_beg) + bytes(b.s_end) +
+                  bytes(b.s_qbeg) + bytes(b.s_qend) + bytes(b.s_n_allele) + bytes(b.s_mono) + bytes(b.s_is_indel) + bytes(b.u_to) + bytes(b.s_allele_off) +
+                  bytes(b.s_unif_off) + bytes(b.u_len) + bytes(b.u_str) + bytes(b.s_hom_prior) + bytes(b.s_lost_prior) + bytes(b.u_beg) + bytes(b.u_end) +
+                  bytes(b.u_prefix) + bytes(b.u_pool);
+    for (uint32_t k = 0; k < b.cfg.n_fields; k++) in += bytes(b.fld_cnt[k]) + bytes(b.fld_off[k]);
+    st[4] = in;
+    uint64_t nv = 0;
+    for (auto f : b.r_flags) nv += !(f & GLX_RF_IS_REF);
+    st[5] = nv;
+    st[6] = st[7] = 0;
+}
+
+glxh_out* glxh_out_alloc(const glxh_batch* b, int pinned) {
+    auto* o = new glxh_out();
+    o->pinned = pinned != 0;
+    const uint64_t S = b->b.sites.n_sites, N = b->b.sites.n_samples;
+    o->n_sites = S;
+    o->n_gt = S * N * 2;
+    o->n_fields = b->b.cfg.n_fields;
+    o->out.gt = (int8_t*)out_alloc(o->n_gt, o->pinned);
+    o->out.rnc = (uint8_t*)out_alloc(o->n_gt, o->pinned);
+    o->out.allele_used = (uint32_t*)out_alloc(S * 4, o->pinned);
+    o->out.site_flags = (uint8_t*)out_alloc(S, o->pinned);
+    for (uint32_t k = 0; k < o->n_fields; k++) {
+        o->n_fld[k] = b->b.fld_off[k].empty() ? 0 : b->b.fld_off[k].back();
+        o->out.fld[k] = (int32_t*)out_alloc(o->n_fld[k] * 4, o->pinned);
+    }
+    return o;
+}
+
+void glxh_out_free(glxh_out* o) {
+    if (!o) return;
+    out_release(o->out.gt, o->pinned);
+    out_release(o->out.rnc, o->pinned);
+    out_release(o->out.allele_used, o->pinned);
+    out_release(o->out.site_flags, o->pinned);
+    for (uint32_t k = 0; k < GLX_MAX_FIELDS; k++) out_release(o->out.fld[k], o->pinned);
+    delete o;
+}
+
+glx_out* glxh_out_struct(glxh_out* o) { return &o->out; }
+
+int glxh_out_array(const glxh_out* o, int which, const void** ptr, uint64_t* nbytes) {
+    if (!o || !ptr || !nbytes) return GLX_E_INVALID;
+    switch (which) {
+        case 0: *ptr = o->out.gt; *nbytes = o->n_gt; return GLX_OK;
+        case 1: *ptr = o->out.rnc; *nbytes = o->n_gt; return GLX_OK;
+        case 2: *ptr = o->out.allele_used; *nbytes = o->n_sites * 4; return GLX_OK;
+        case 3: *ptr = o->out.site_flags; *nbytes = o->n_sites; return GLX_OK;
+        default: break;
+    }
+    int k = which - 16;
+    if (k < 0 || k >= (int)o->n_fields) return GLX_E_INVALID;
+    *ptr = o->out.fld[k];
+    *nbytes = o->n_fld[k] * 4;
+    return GLX_OK;
+}
+
+int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char* err, size_t errlen) {
+    if (!b || !out || !text) return GLX_E_INVALID;
+    std::string o;
+    glx::Status s = glx::assemble_vcf_text(b->b, *out, o);
+    if (s.bad()) return fail(s, err, errlen);
+    *text = (char*)malloc(o.size() + 1);
+    memcpy(*text, o.c_str(), o.size() + 1);
+    return GLX_OK;
+}
+
+void glxh_free_text(char* text) { free(text); }
+
+int glxh_preset_text(const char* name, char** text) {
+    glx::genotyper_config cfg;
+    glx::Status s = glx::load_config_preset(name ? name : "", cfg);
+    if (s.bad()) return s.c_code();
+    std::string o = cfg.text();
+    *text = (char*)malloc(o.size() + 1);
+    memcpy(*text, o.c_str(), o.size() + 1);
+    return GLX_OK;
+}
+}

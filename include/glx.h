@@ -1,0 +1,220 @@
+/* glx.h — C ABI of the B200-native joint genotyper (drop-in for GLnexus' genotype_site path).
+ *
+ * The reference (dnanexus-rnd/GLnexus) has no FFI layer; its seam for this path is the pair of
+ * C++ signatures
+ *     Service::genotype_sites(cfg, sampleset, sites, filename, abort)   include/service.h:67-70
+ *     genotype_site(cfg, cache, data, site, sampleset, samples, hdr, ans, ...)  include/genotyper.h:18-24
+ * fed by BCFData::sampleset_range / RangeBCFIterator::next (include/data.h:86-94,149-153).
+ * This header is what a GLnexus maintainer binds instead: the host decodes each contig range's
+ * gVCF records ONCE into the columnar record store below (glx_records), flattens genotyper_config
+ * (include/types.h:700-776) and the range's unified_site vector (include/types.h:454-506) into
+ * glx_config / glx_sites, and calls glx_genotype_batch. The kernels do everything genotype_site
+ * does per (site, sample) cell: record selection, allele translation, revise_genotypes, calling,
+ * FORMAT lifting, censoring, RNC codes; the host turns the packed FORMAT columns into bcf1_t.
+ *
+ * Plain pointers and sizes only. All arrays are caller-owned. 0 = OK, negative = error
+ * (codes mirror GLnexus::StatusCode, include/types.h:31-40).
+ */
+#ifndef GLX_H
+#define GLX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLX_ABI_VERSION 1u
+#define GLX_MAX_ALLELES 32 /* unified alleles per site and alleles per record (unifier max_alleles_per_site) */
+#define GLX_MAX_FIELDS 12  /* genotyper_config::liftover_fields */
+#define GLX_MAX_ORIG 4     /* retained_format_field::orig_names */
+#define GLX_MAX_COLS 24    /* distinct source columns of the record store */
+#define GLX_MAX_FILTERS 32 /* distinct non-PASS FILTER ids per batch (FT field) */
+
+/* ---- status codes: -(GLnexus::StatusCode), include/types.h:31-40 ---- */
+enum {
+    GLX_OK = 0,
+    GLX_E_FAILURE = -1,
+    GLX_E_INVALID = -2,
+    GLX_E_NOT_FOUND = -3,
+    GLX_E_EXISTS = -4,
+    GLX_E_IO_ERROR = -5,
+    GLX_E_NOT_IMPLEMENTED = -6,
+    GLX_E_ABORTED = -7,
+    GLX_E_CUDA = -100,       /* CUDA runtime error (message in glx_last_error) */
+    GLX_E_UNSUPPORTED = -101 /* input outside what the device path accepts (e.g. multi-sample dataset) */
+};
+
+/* ---- sentinels, exactly htslib's (htslib/vcf.h) ---- */
+#define GLX_INT_MISSING ((int32_t)0x80000000)    /* bcf_int32_missing    */
+#define GLX_INT_VECTOR_END ((int32_t)0x80000001) /* bcf_int32_vector_end */
+#define GLX_FLOAT_MISSING_BITS 0x7F800001u       /* bcf_float_missing    */
+#define GLX_FLOAT_VECTOR_END_BITS 0x7F800002u    /* bcf_float_vector_end */
+#define GLX_LEN_ABSENT 0xFFFFu                   /* column not present on this record (htslib rv -1/-3) */
+#define GLX_GT16_VECTOR_END ((int16_t)-32767)    /* inline GT slot = bcf_int32_vector_end */
+
+/* ---- retained_format_field enums (include/types.h:604-650) ---- */
+enum { GLX_TYPE_INT = 0, GLX_TYPE_FLOAT = 1, GLX_TYPE_STRING = 2 };
+enum { GLX_NUM_BASIC = 0, GLX_NUM_ALT = 1, GLX_NUM_GENOTYPE = 2, GLX_NUM_ALLELES = 3 };
+enum { GLX_COMBI_MIN = 0, GLX_COMBI_MAX = 1, GLX_COMBI_MISSING = 2, GLX_COMBI_SEMICOLON = 3 };
+/* helper class chosen by setup_format_helpers (src/genotyper_utils.h:865-931) */
+enum { GLX_FK_NUMERIC = 0, GLX_FK_DP = 1, GLX_FK_AD = 2, GLX_FK_PL = 3, GLX_FK_PL2 = 4, GLX_FK_FT = 5, GLX_FK_STRING = 6 };
+
+/* NoCallReason (include/genotyper.h:28-39); ASCII RNC codes of src/genotyper.cc:930-947 */
+enum {
+    GLX_RNC_NA = 0, GLX_RNC_MISSING = 1, GLX_RNC_PARTIAL = 2, GLX_RNC_DEPTH = 3, GLX_RNC_LOST_DELETION = 4,
+    GLX_RNC_LOST_ALLELE = 5, GLX_RNC_UNPHASED = 6, GLX_RNC_OVERLAPPING = 7, GLX_RNC_MONOALLELIC = 8,
+    GLX_RNC_INPUT_NONCALLED = 9
+};
+
+typedef struct glx_field {
+    char name[16];               /* output FORMAT id */
+    uint8_t kind;                /* GLX_FK_* */
+    uint8_t type;                /* GLX_TYPE_* */
+    uint8_t number;              /* GLX_NUM_* */
+    uint8_t combi;               /* GLX_COMBI_* */
+    uint8_t default_zero;        /* DefaultValueFiller::ZERO (else MISSING) */
+    uint8_t ignore_non_variants;
+    uint8_t n_cols;              /* #orig_names */
+    uint8_t _pad;
+    int32_t count;               /* RetainedFieldNumber::BASIC only */
+    int16_t cols[GLX_MAX_ORIG];  /* source column ids, orig_names order (first found wins) */
+} glx_field;
+
+typedef struct glx_column {
+    char name[24];     /* FORMAT/INFO id in the input gVCFs */
+    uint8_t from_info; /* RetainedFieldFrom::INFO */
+    uint8_t type;      /* GLX_TYPE_INT / GLX_TYPE_FLOAT */
+    uint8_t _pad[6];
+} glx_column;
+
+/* flattened genotyper_config (include/types.h:700-776) */
+typedef struct glx_config {
+    uint32_t abi_version;
+    uint8_t revise_genotypes, allow_partial_data, more_PL, squeeze;
+    uint8_t trim_uncalled_alleles, top_two_half_calls, xatlas_depth_mode, _pad;
+    uint32_t required_dp;
+    float min_assumed_allele_frequency, snv_prior_calibration, indel_prior_calibration;
+    /* libm constants evaluated on the host so device arithmetic is bit-identical
+       (src/diploid.cc:105-106, src/genotyper.cc:213) */
+    double neg10_log10e; /* -10.0*log10(exp(1.0)) */
+    double ln10;         /* log(10.0) */
+    int16_t col_ref_dp, col_allele_dp, col_pl, col_gq; /* ref_dp_format, allele_dp_format, "PL", "GQ" */
+    uint32_t n_cols;
+    glx_column cols[GLX_MAX_COLS];
+    uint32_t n_fields;
+    glx_field fields[GLX_MAX_FIELDS];
+} glx_config;
+
+/* Columnar record store: every gVCF record of one contig range, decoded once.
+ * Records of dataset d are [ds_rec_off[d], ds_rec_off[d+1]), sorted by (beg,end) (range::operator<).
+ * The device path requires single-sample datasets with sample_out[d]==d. */
+typedef struct glx_records {
+    uint32_t n_datasets, n_samples_out, n_cols, _pad;
+    uint64_t n_records;
+    const uint64_t* ds_rec_off;    /* [D+1] */
+    const uint32_t* ds_n_sample;   /* [D] */
+    const uint32_t* ds_sample_off; /* [D+1] into sample_out */
+    const int32_t* sample_out;     /* output sample index of each dataset sample, or -1 (not in sample set) */
+    /* per record */
+    const int32_t* beg;            /* bcf->pos */
+    const int32_t* end;            /* pos + rlen (rlen from INFO/END when present) */
+    const int32_t* maxend;         /* running max of end within the dataset (interval-join aid) */
+    const float* qual;
+    const uint8_t* n_allele;
+    const uint8_t* flags;          /* GLX_RF_* */
+    const uint32_t* filt;          /* bit i = FILTER id filter_names[i] set (non-PASS only) */
+    const uint32_t* gt;            /* single-sample dataset: int16 gt0 | int16 gt1 << 16 (htslib GT ints);
+                                      multi-sample: offset into gt_pool (2 int32 per sample) */
+    const uint32_t* allele_off;    /* first allele descriptor (non-ref records only; n_allele entries) */
+    /* per column c, record r: col_len[c*n_records+r] values per sample (GLX_LEN_ABSENT = not present);
+       col_val holds the value itself when the dataset is single-sample and len==1, else an offset into pool */
+    const int32_t* col_val;
+    const uint16_t* col_len;
+    const int32_t* pool;
+    const int32_t* gt_pool;
+    /* allele descriptors */
+    const uint32_t* al_len;
+    const uint8_t* al_flags;       /* GLX_AF_* */
+    const uint64_t* al_prefix;     /* first 8 bytes of the allele, zero padded */
+    const uint32_t* al_str;        /* offset into al_pool */
+    const char* al_pool;
+    uint64_t n_pool, n_gt_pool, n_al, n_al_pool;
+    uint32_t n_filters, _pad2;
+    const char* const* filter_names; /* sorted; host-side only */
+} glx_records;
+
+enum { GLX_RF_IS_REF = 1, GLX_RF_HAPLOID = 2, GLX_RF_SYMBOLIC_LAST = 4, GLX_RF_NO_GT = 8 };
+enum { GLX_AF_IS_DNA = 1, GLX_AF_DELETION = 2, GLX_AF_SYMBOLIC = 4 };
+
+/* One batch of unified sites (include/types.h:454-506), sorted by position. */
+typedef struct glx_sites {
+    uint32_t n_sites, n_samples;
+    const int32_t* beg;  /* site.pos */
+    const int32_t* end;
+    const int32_t* qbeg; /* hull of site.pos and all unification keys (src/genotyper.cc:700-706) */
+    const int32_t* qend;
+    const uint8_t* n_allele;
+    const uint8_t* monoallelic;
+    const uint32_t* allele_off;    /* [S+1] */
+    const uint8_t* allele_is_indel;/* alleles[a].dna.size() != alleles[0].dna.size() */
+    const float* allele_af;        /* unified_allele::frequency (NaN allowed); host/output only */
+    const float* lost_af;          /* [S] unified_site::lost_allele_frequency; host only */
+    const float* hom_log_prior;    /* logf(max(frequency, min_assumed_allele_frequency))  genotyper.cc:164 */
+    const float* lost_log_prior;   /* [S] logf(max(lost_allele_frequency, min_AF))        genotyper.cc:154 */
+    const uint32_t* unif_off;      /* [S+1] unification entries (std::map<allele,int>) */
+    const int32_t* unif_beg;
+    const int32_t* unif_end;
+    const uint8_t* unif_to;
+    const uint32_t* unif_len;
+    const uint64_t* unif_prefix;
+    const uint32_t* unif_str;
+    const char* unif_pool;
+    uint64_t n_unif, n_unif_pool, n_site_alleles;
+    /* output layout: field k of site s holds fld_cnt[k][s] values per sample starting at value index fld_off[k][s] */
+    const uint16_t* fld_cnt[GLX_MAX_FIELDS];
+    const uint64_t* fld_off[GLX_MAX_FIELDS]; /* [S+1] */
+} glx_sites;
+
+/* Packed FORMAT columns, sample-major within a site. */
+typedef struct glx_out {
+    int8_t* gt;     /* [S][N][2] unified allele index, -1 = missing */
+    uint8_t* rnc;   /* [S][N][2] ASCII RNC code */
+    int32_t* fld[GLX_MAX_FIELDS]; /* int32 / float bits / FT filter mask; see glx_sites.fld_off */
+    uint32_t* allele_used; /* [S] bit a = unified allele a appears in some GT (bcf_trim_alleles) */
+    uint8_t* site_flags;   /* [S] bit0 = some call lost (residuals rule, src/genotyper.cc:837-849) */
+} glx_out;
+
+typedef struct glx_ctx glx_ctx;
+
+/* lifecycle */
+int glx_create(glx_ctx** ctx, int device);
+void glx_destroy(glx_ctx* ctx);
+const char* glx_last_error(const glx_ctx* ctx);
+
+/* Fill hom_log_prior / lost_log_prior (host logf, src/genotyper.cc:154,164). Arrays are caller-owned. */
+int glx_compute_priors(const glx_config* cfg, uint32_t n_sites, const uint32_t* allele_off, const float* allele_af,
+                       const float* lost_af, float* hom_log_prior, float* lost_log_prior);
+
+/* Replaces the genotype_site loop of Service::genotype_sites (src/service.cc:344-381) for one batch.
+ * Host buffers in, host buffers out: H2D, kernels, D2H on the context's stream; returns after completion. */
+int glx_genotype_batch(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites,
+                       glx_out* out);
+
+/* Device-resident variant: upload once, launch many (site batches of one range share the record store). */
+typedef struct glx_dev_batch glx_dev_batch;
+int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites,
+               glx_dev_batch** dev);
+int glx_launch(glx_ctx* ctx, glx_dev_batch* dev, void* stream /* cudaStream_t or NULL = ctx stream */);
+int glx_download(glx_ctx* ctx, glx_dev_batch* dev, glx_out* out);
+int glx_check(glx_ctx* ctx, glx_dev_batch* dev); /* device-side error word -> status */
+uint64_t glx_out_bytes(const glx_dev_batch* dev);
+uint64_t glx_in_bytes(const glx_dev_batch* dev);
+int glx_launch_count(const glx_dev_batch* dev); /* kernels per glx_launch */
+void glx_free_batch(glx_ctx* ctx, glx_dev_batch* dev);
+int glx_synchronize(glx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,75 @@
+/* glx_host.h — C entry points of the host pipeline around include/glx.h: decode (VCF text stand-in for
+ * htslib), pack into the columnar record store, and assemble pVCF text from the packed FORMAT columns.
+ * These replace, for this path, what Service::genotype_sites does around the genotype_site loop
+ * (src/service.cc:302-343 header/sample set-up, 388-418 ordered output) and the tail of genotype_site
+ * (src/genotyper.cc:869-1003: alleles, INFO AF/AQ, bcf_trim_alleles, ID).
+ */
+#ifndef GLX_HOST_H
+#define GLX_HOST_H
+#include "glx.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct glxh_batch glxh_batch;
+typedef struct glxh_out glxh_out;
+
+/* Build one batch from text inputs.
+ *  config_text : genotyper_config, line format of glx::genotyper_config::of_text
+ *  preset      : if non-NULL, `glnexus_cli --config` preset name loaded first (src/cli_utils.cc:1236-1265);
+ *                config_text (may be NULL/empty) then replaces it wholesale, as genotyper_config::of_yaml does
+ *  sites_text  : unified sites, line format of glx::sites_of_text (0-based half-open)
+ *  vcf_texts   : one single- or multi-sample gVCF per dataset (dataset name = file stem)
+ *  contig      : keep only this contig's sites and records (NULL: all input must be on one contig)
+ *  test_ingest_rules : apply the ingest-time record skips of the reference's test harness
+ * The sample set is "<ALL>": every sample of every dataset, sorted by name (src/service.cc:307-309). */
+int glxh_batch_from_text(const char* preset, const char* config_text, const char* sites_text, int n_datasets,
+                         const char* const* dataset_names, const char* const* vcf_texts, const char* contig,
+                         int test_ingest_rules, glxh_batch** ans, char* err, size_t errlen);
+void glxh_batch_free(glxh_batch* b);
+const glx_config* glxh_config(const glxh_batch* b);
+const glx_records* glxh_records(const glxh_batch* b);
+const glx_sites* glxh_sites(const glxh_batch* b);
+uint32_t glxh_n_fields(const glxh_batch* b);
+int glxh_device_supported(const glxh_batch* b); /* 1 if the batch meets the device path's preconditions */
+/* st[0..5] = n_sites, n_samples, n_records, n_datasets, bytes of all input arrays, #variant (non-reference) records */
+void glxh_batch_stats(const glxh_batch* b, uint64_t st[8]);
+
+/* Host output buffers sized for the batch. `pinned` != 0 uses cudaHostAlloc. */
+glxh_out* glxh_out_alloc(const glxh_batch* b, int pinned);
+void glxh_out_free(glxh_out* o);
+glx_out* glxh_out_struct(glxh_out* o);
+/* raw access for comparisons: which = 0 gt, 1 rnc, 2 allele_used, 3 site_flags, 16+k field k */
+int glxh_out_array(const glxh_out* o, int which, const void** ptr, uint64_t* nbytes);
+
+/* pVCF text from packed columns. Caller frees with glxh_free_text. */
+int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char* err, size_t errlen);
+void glxh_free_text(char* text);
+
+/* genotyper_config preset -> text (for `--config NAME`); caller frees with glxh_free_text */
+int glxh_preset_text(const char* name, char** text);
+
+/* Seeded synthetic cohort in record-store form (BASELINE.json configs[1..4] shapes). See DESIGN.md §synthetic. */
+typedef struct glxh_synth_params {
+    uint32_t n_samples, n_sites;
+    uint64_t seed;
+    int32_t region_beg, region_len; /* sites are drawn uniformly without replacement inside [beg, beg+len) */
+    uint32_t max_alt;               /* ALT alleles per site: 1..max_alt */
+    float frac_multiallelic;        /* fraction of sites with >1 ALT (when max_alt>1) */
+    float frac_indel;               /* fraction of ALT alleles that are indels */
+    float af_max;                   /* site AF ~ 1/x on [1/(2N), af_max] */
+    float band_mean_len;            /* mean reference-band length (geometric) */
+    float frac_uncovered;           /* fraction of band starts replaced by a coverage gap */
+    float frac_two_record_cells;    /* extra overlapping/0-0 variant records (config 3 stress) */
+    float frac_lost_allele;         /* carrier records whose ALT is absent from the unified site */
+    float frac_homalt;              /* carriers called hom-ALT (forces revise_genotypes) */
+    uint8_t gatk_style;             /* <NON_REF> + SB field, no PL on bands */
+    uint8_t _pad[3];
+} glxh_synth_params;
+int glxh_synth_batch(const char* preset, const glxh_synth_params* p, glxh_batch** ans, char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
