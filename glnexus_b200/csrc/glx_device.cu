@@ -1,21 +1,406 @@
-// temporary stub
+// glx_device.cu — CUDA side of the C ABI in include/glx.h: device context, batch upload, kernels, download.
+//
+// Replaces, for one contig-range batch, the per-site task loop of Service::genotype_sites
+// (src/service.cc:344-381) and everything genotype_site does per (site, sample) cell
+// (src/genotyper.cc:682-867). sm_100a only; there is no host fallback: every entry point fails with
+// GLX_E_CUDA when no device is usable.
 #include <cuda_runtime.h>
+
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
 #include "../../include/glx.h"
-extern "C" void* glx_pinned_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
-extern "C" void glx_pinned_free(void* p) { cudaFreeHost(p); }
+#include "glx_cell_general.cuh"
+#include "glx_dev_types.cuh"
+
+using namespace glxd;
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+
+// first record of [lo,hi) whose running max end exceeds qbeg (records with maxend <= qbeg cannot overlap the query)
+__device__ __forceinline__ uint64_t first_candidate(const int32_t* __restrict__ maxend, uint64_t lo, uint64_t hi, int qbeg) {
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (maxend[mid] <= qbeg) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// General path: one thread per cell, taken from a worklist (or every cell of the batch when worklist == nullptr).
+__global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint32_t* __restrict__ worklist,
+                                                                const uint32_t* __restrict__ n_work_ptr, uint64_t n_all, uint8_t* __restrict__ cnt_scratch,
+                                                                uint32_t max_slots) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t* cnt = cnt_scratch + tid;
+    const uint64_t n_items = worklist ? (uint64_t)*n_work_ptr : n_all;
+    const uint32_t N = S.n_samples;
+    for (uint64_t it = tid; it < n_items; it += stride) {
+        const uint64_t cell = worklist ? worklist[it] : it;
+        const uint32_t s = (uint32_t)(cell / N), sample = (uint32_t)(cell % N);
+        const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
+        const uint64_t first = first_candidate(R.maxend, lo, hi, S.qbeg[s]);
+        genotype_cell_general(cfg, R, S, O, s, sample, first, hi, cnt, stride);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct glx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sm_count = 0;
+};
+
+namespace {
+
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    template <class T>
+    T* take(size_t n) {
+        used = (used + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+};
+
+int cuda_fail(glx_ctx* ctx, cudaError_t e, const char* what) {
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return GLX_E_CUDA;
+}
+#define CU(call)                                                  \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+}  // namespace
+
+struct glx_dev_batch {
+    DCfg cfg;
+    DRecs R;
+    DSites S;
+    DOut O;
+    char* in_base = nullptr;
+    char* out_base = nullptr;
+    size_t in_bytes = 0, out_bytes = 0;
+    uint32_t n_sites = 0, n_samples = 0, n_fields = 0;
+    uint64_t n_cells = 0;
+    uint64_t fld_total[GLX_MAX_FIELDS] = {};
+    uint32_t max_slots = 0;
+    uint8_t* cnt_scratch = nullptr;
+    size_t cnt_scratch_bytes = 0;
+    int general_blocks = 0;
+    int launches_per_call = 0;
+    bool force_general = false;
+};
+
 extern "C" {
-int glx_create(glx_ctx**, int) { return GLX_E_CUDA; }
-void glx_destroy(glx_ctx*) {}
-const char* glx_last_error(const glx_ctx*) { return ""; }
-int glx_genotype_batch(glx_ctx*, const glx_config*, const glx_records*, const glx_sites*, glx_out*) { return GLX_E_CUDA; }
-int glx_upload(glx_ctx*, const glx_config*, const glx_records*, const glx_sites*, glx_dev_batch**) { return GLX_E_CUDA; }
-int glx_launch(glx_ctx*, glx_dev_batch*, void*) { return GLX_E_CUDA; }
-int glx_download(glx_ctx*, glx_dev_batch*, glx_out*) { return GLX_E_CUDA; }
-int glx_check(glx_ctx*, glx_dev_batch*) { return GLX_E_CUDA; }
-uint64_t glx_out_bytes(const glx_dev_batch*) { return 0; }
-uint64_t glx_in_bytes(const glx_dev_batch*) { return 0; }
-int glx_launch_count(const glx_dev_batch*) { return 0; }
-void glx_free_batch(glx_ctx*, glx_dev_batch*) {}
-int glx_synchronize(glx_ctx*) { return GLX_E_CUDA; }
+
+void* glx_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void glx_pinned_free(void* p) { cudaFreeHost(p); }
+
+int glx_create(glx_ctx** out, int device) {
+    if (!out) return GLX_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return GLX_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return GLX_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GLX_E_CUDA;
+    if (prop.major != 10) return GLX_E_CUDA;  // sm_100a binary only
+    auto* ctx = new glx_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return GLX_E_CUDA;
+    }
+    *out = ctx;
+    return GLX_OK;
+}
+
+void glx_destroy(glx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* glx_last_error(const glx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int glx_synchronize(glx_ctx* ctx) {
+    if (!ctx) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GLX_OK;
+}
+
+void* glx_stream(glx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
+    if (!d) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (d->in_base) cudaFree(d->in_base);
+    if (d->out_base) cudaFree(d->out_base);
+    if (d->cnt_scratch) cudaFree(d->cnt_scratch);
+    delete d;
+}
+
+int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_dev_batch** out) {
+    if (!ctx) return GLX_E_INVALID;
+    if (!cfg || !recs || !sites || !out) {
+        ctx->err = "glx_upload: null argument";
+        return GLX_E_INVALID;
+    }
+    *out = nullptr;
+    if (cfg->abi_version != GLX_ABI_VERSION) {
+        ctx->err = "glx_upload: ABI version mismatch";
+        return GLX_E_INVALID;
+    }
+    // preconditions of the device path: single-sample datasets in output-sample order
+    if (recs->n_datasets != sites->n_samples || recs->n_samples_out != sites->n_samples) {
+        ctx->err = "glx_upload: device path needs one single-sample dataset per output sample";
+        return GLX_E_UNSUPPORTED;
+    }
+    for (uint32_t d = 0; d < recs->n_datasets; d++) {
+        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) {
+            ctx->err = "glx_upload: multi-sample or out-of-order dataset is outside the device path";
+            return GLX_E_UNSUPPORTED;
+        }
+    }
+    const uint64_t S = sites->n_sites, N = sites->n_samples;
+    if (S * N >= (1ull << 32)) {
+        ctx->err = "glx_upload: more than 2^32 cells in one batch; split the site range";
+        return GLX_E_UNSUPPORTED;
+    }
+    if (cfg->n_fields > GLX_MAX_FIELDS || cfg->n_cols > GLX_MAX_COLS) {
+        ctx->err = "glx_upload: config exceeds GLX_MAX_FIELDS / GLX_MAX_COLS";
+        return GLX_E_INVALID;
+    }
+    CU(cudaSetDevice(ctx->device));
+    auto* d = new glx_dev_batch();
+    d->cfg = make_dcfg(*cfg);
+    d->n_sites = (uint32_t)S;
+    d->n_samples = (uint32_t)N;
+    d->n_fields = cfg->n_fields;
+    d->n_cells = S * N;
+    const char* fg = getenv("GLX_FORCE_GENERAL");
+    d->force_general = fg && *fg && *fg != '0';
+
+    const uint64_t Rn = recs->n_records, D = recs->n_datasets, C = cfg->n_cols;
+    const uint64_t nA = sites->n_site_alleles, nU = sites->n_unif;
+    // ---- size the input arena ----
+    struct Item {
+        const void* src;
+        size_t bytes;
+        void** dst;
+    };
+    std::vector<Item> items;
+    auto add = [&](const void* src, size_t bytes, auto** dst) { items.push_back(Item{src, bytes, (void**)dst}); };
+    DRecs& R = d->R;
+    DSites& Sx = d->S;
+    memset(&R, 0, sizeof R);
+    memset(&Sx, 0, sizeof Sx);
+    R.n_records = Rn;
+    add(recs->ds_rec_off, (D + 1) * 8, &R.ds_rec_off);
+    add(recs->beg, Rn * 4, &R.beg);
+    add(recs->end, Rn * 4, &R.end);
+    add(recs->maxend, Rn * 4, &R.maxend);
+    add(recs->qual, Rn * 4, &R.qual);
+    add(recs->n_allele, Rn, &R.n_allele);
+    add(recs->flags, Rn, &R.flags);
+    add(recs->filt, Rn * 4, &R.filt);
+    add(recs->gt, Rn * 4, &R.gt);
+    add(recs->allele_off, Rn * 4, &R.allele_off);
+    add(recs->col_val, C * Rn * 4, &R.col_val);
+    add(recs->col_len, C * Rn * 2, &R.col_len);
+    add(recs->pool, recs->n_pool * 4, &R.pool);
+    add(recs->al_len, recs->n_al * 4, &R.al_len);
+    add(recs->al_flags, recs->n_al, &R.al_flags);
+    add(recs->al_prefix, recs->n_al * 8, &R.al_prefix);
+    add(recs->al_str, recs->n_al * 4, &R.al_str);
+    add(recs->al_pool, recs->n_al_pool, &R.al_pool);
+    Sx.n_sites = (uint32_t)S;
+    Sx.n_samples = (uint32_t)N;
+    add(sites->beg, S * 4, &Sx.beg);
+    add(sites->end, S * 4, &Sx.end);
+    add(sites->qbeg, S * 4, &Sx.qbeg);
+    add(sites->qend, S * 4, &Sx.qend);
+    add(sites->n_allele, S, &Sx.n_allele);
+    add(sites->monoallelic, S, &Sx.monoallelic);
+    add(sites->allele_off, (S + 1) * 4, &Sx.allele_off);
+    add(sites->allele_is_indel, nA, &Sx.allele_is_indel);
+    add(sites->hom_log_prior, nA * 4, &Sx.hom_log_prior);
+    add(sites->lost_log_prior, S * 4, &Sx.lost_log_prior);
+    add(sites->unif_off, (S + 1) * 4, &Sx.unif_off);
+    add(sites->unif_beg, nU * 4, &Sx.unif_beg);
+    add(sites->unif_end, nU * 4, &Sx.unif_end);
+    add(sites->unif_to, nU, &Sx.unif_to);
+    add(sites->unif_len, nU * 4, &Sx.unif_len);
+    add(sites->unif_prefix, nU * 8, &Sx.unif_prefix);
+    add(sites->unif_str, nU * 4, &Sx.unif_str);
+    add(sites->unif_pool, sites->n_unif_pool, &Sx.unif_pool);
+    for (uint32_t k = 0; k < cfg->n_fields; k++) {
+        add(sites->fld_cnt[k], S * 2, &Sx.fld_cnt[k]);
+        add(sites->fld_off[k], (S + 1) * 8, &Sx.fld_off[k]);
+        d->fld_total[k] = S ? sites->fld_off[k][S] : 0;
+    }
+    size_t total = 0;
+    for (auto& it : items) total += ((it.bytes + 255) & ~(size_t)255) + 256;
+    d->in_bytes = total;
+    cudaError_t e = cudaMalloc(&d->in_base, total ? total : 256);
+    if (e != cudaSuccess) {
+        glx_free_batch(ctx, d);
+        return cuda_fail(ctx, e, "cudaMalloc(input arena)");
+    }
+    Arena ar{d->in_base, total, 0};
+    for (auto& it : items) {
+        char* p = ar.take<char>(it.bytes ? it.bytes : 1);
+        *it.dst = p;
+        if (it.bytes) {
+            e = cudaMemcpyAsync(p, it.src, it.bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) {
+                glx_free_batch(ctx, d);
+                return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
+            }
+        }
+    }
+    // max output slots of any cell (scratch sizing of the general path)
+    uint32_t max_slots = 1;
+    for (uint64_t s = 0; s < S; s++) {
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < cfg->n_fields; k++) t += sites->fld_cnt[k][s];
+        if (t > max_slots) max_slots = t;
+    }
+    d->max_slots = max_slots;
+
+    // ---- output arena ----
+    size_t ob = 0;
+    auto osz = [&](size_t b) { ob += ((b + 255) & ~(size_t)255) + 256; };
+    osz(S * N * 2);
+    osz(S * N * 2);
+    osz(S * 4);
+    osz(S + 4);
+    osz(8);
+    for (uint32_t k = 0; k < cfg->n_fields; k++) osz(d->fld_total[k] * 4);
+    d->out_bytes = ob;
+    e = cudaMalloc(&d->out_base, ob);
+    if (e != cudaSuccess) {
+        glx_free_batch(ctx, d);
+        return cuda_fail(ctx, e, "cudaMalloc(output arena)");
+    }
+    Arena oa{d->out_base, ob, 0};
+    memset(&d->O, 0, sizeof d->O);
+    d->O.gt = oa.take<int8_t>(S * N * 2);
+    d->O.rnc = oa.take<uint8_t>(S * N * 2);
+    d->O.allele_used = oa.take<uint32_t>(S);
+    d->O.site_flags = oa.take<uint8_t>(S + 4);
+    d->O.error = oa.take<unsigned long long>(1);
+    for (uint32_t k = 0; k < cfg->n_fields; k++) d->O.fld[k] = oa.take<int32_t>(d->fld_total[k]);
+
+    // ---- general-path scratch ----
+    const int threads = 128;
+    uint64_t want_blocks = (d->n_cells + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 16;
+    d->general_blocks = (int)(want_blocks < cap ? (want_blocks ? want_blocks : 1) : cap);
+    d->cnt_scratch_bytes = (size_t)d->general_blocks * threads * max_slots;
+    e = cudaMalloc(&d->cnt_scratch, d->cnt_scratch_bytes);
+    if (e != cudaSuccess) {
+        glx_free_batch(ctx, d);
+        return cuda_fail(ctx, e, "cudaMalloc(scratch)");
+    }
+    e = cudaStreamSynchronize(ctx->stream);  // caller's host arrays may be released after return
+    if (e != cudaSuccess) {
+        glx_free_batch(ctx, d);
+        return cuda_fail(ctx, e, "cudaStreamSynchronize(upload)");
+    }
+    *out = d;
+    return GLX_OK;
+}
+
+int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
+    if (!ctx || !d) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    const uint64_t S = d->n_sites;
+    CU(cudaMemsetAsync(d->O.allele_used, 0, S * 4, st));
+    CU(cudaMemsetAsync(d->O.site_flags, 0, S + 4, st));
+    CU(cudaMemsetAsync(d->O.error, 0xff, 8, st));
+    d->launches_per_call = 0;
+    if (d->n_cells) {
+        glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, nullptr, d->n_cells, d->cnt_scratch, d->max_slots);
+        d->launches_per_call++;
+        CU(cudaGetLastError());
+    }
+    return GLX_OK;
+}
+
+int glx_check(glx_ctx* ctx, glx_dev_batch* d) {
+    if (!ctx || !d) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long w = 0;
+    CU(cudaMemcpyAsync(&w, d->O.error, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (w == ~0ull) return GLX_OK;
+    const int code = (int)(w & 0xff);
+    const unsigned long long site = w >> 8;
+    char buf[160];
+    snprintf(buf, sizeof buf, "genotyper: site %llu failed with status %d (first failing site of the batch)", site, -code);
+    ctx->err = buf;
+    return code == 101 ? GLX_E_UNSUPPORTED : -code;
+}
+
+int glx_download(glx_ctx* ctx, glx_dev_batch* d, glx_out* out) {
+    if (!ctx || !d || !out) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t S = d->n_sites, N = d->n_samples;
+    cudaStream_t st = ctx->stream;
+    if (S * N) {
+        CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->rnc, d->O.rnc, S * N * 2, cudaMemcpyDeviceToHost, st));
+    }
+    if (S) {
+        CU(cudaMemcpyAsync(out->allele_used, d->O.allele_used, S * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->site_flags, d->O.site_flags, S, cudaMemcpyDeviceToHost, st));
+    }
+    for (uint32_t k = 0; k < d->n_fields; k++)
+        if (d->fld_total[k]) CU(cudaMemcpyAsync(out->fld[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GLX_OK;
+}
+
+uint64_t glx_out_bytes(const glx_dev_batch* d) {
+    if (!d) return 0;
+    uint64_t b = (uint64_t)d->n_cells * 4 + (uint64_t)d->n_sites * 5;
+    for (uint32_t k = 0; k < d->n_fields; k++) b += d->fld_total[k] * 4;
+    return b;
+}
+uint64_t glx_in_bytes(const glx_dev_batch* d) { return d ? d->in_bytes : 0; }
+int glx_launch_count(const glx_dev_batch* d) { return d ? d->launches_per_call : 0; }
+
+int glx_genotype_batch(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out) {
+    glx_dev_batch* d = nullptr;
+    int rc = glx_upload(ctx, cfg, recs, sites, &d);
+    if (rc != GLX_OK) return rc;
+    rc = glx_launch(ctx, d, nullptr);
+    if (rc == GLX_OK) rc = glx_check(ctx, d);
+    if (rc == GLX_OK) rc = glx_download(ctx, d, out);
+    glx_free_batch(ctx, d);
+    return rc;
+}
 }

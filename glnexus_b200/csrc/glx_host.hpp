@@ -254,3 +254,8 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
 Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& vcf_text);
 
 }  // namespace glx
+
+// opaque handle of include/glx_host.h
+struct glxh_batch {
+    glx::PackedBatch b;
+};

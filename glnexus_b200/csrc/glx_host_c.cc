@@ -9,10 +9,6 @@
 extern "C" void* glx_pinned_alloc(size_t bytes);
 extern "C" void glx_pinned_free(void* p);
 
-struct glxh_batch {
-    glx::PackedBatch b;
-};
-
 struct glxh_out {
     glx_out out{};
     bool pinned = false;

@@ -1,0 +1,69 @@
+// glx_emu.cc — TEST INFRASTRUCTURE: the device cell logic compiled for the host (see cuda_host_shim.h) and driven
+// cell by cell over host arrays. Used by tests/test_emu_parity.py to diff the kernels' control flow against the
+// oracle without a GPU. Not part of libglx.so.
+#include "cuda_host_shim.h"
+
+#include <vector>
+
+#include "../../glnexus_b200/csrc/glx_cell_general.cuh"
+
+using namespace glxd;
+
+static void bind(const glx_config* cfg, const glx_records* r, const glx_sites* s, glx_out* o, unsigned long long* err, DCfg& C, DRecs& R, DSites& S, DOut& O) {
+    C = make_dcfg(*cfg);
+    memset(&R, 0, sizeof R);
+    R.n_records = r->n_records;
+    R.ds_rec_off = r->ds_rec_off; R.beg = r->beg; R.end = r->end; R.maxend = r->maxend; R.qual = r->qual;
+    R.n_allele = r->n_allele; R.flags = r->flags; R.filt = r->filt; R.gt = r->gt; R.allele_off = r->allele_off;
+    R.col_val = r->col_val; R.col_len = r->col_len; R.pool = r->pool;
+    R.al_len = r->al_len; R.al_flags = r->al_flags; R.al_prefix = r->al_prefix; R.al_str = r->al_str; R.al_pool = r->al_pool;
+    memset(&S, 0, sizeof S);
+    S.n_sites = s->n_sites; S.n_samples = s->n_samples;
+    S.beg = s->beg; S.end = s->end; S.qbeg = s->qbeg; S.qend = s->qend; S.n_allele = s->n_allele; S.monoallelic = s->monoallelic;
+    S.allele_off = s->allele_off; S.allele_is_indel = s->allele_is_indel; S.hom_log_prior = s->hom_log_prior; S.lost_log_prior = s->lost_log_prior;
+    S.unif_off = s->unif_off; S.unif_beg = s->unif_beg; S.unif_end = s->unif_end; S.unif_to = s->unif_to; S.unif_len = s->unif_len;
+    S.unif_prefix = s->unif_prefix; S.unif_str = s->unif_str; S.unif_pool = s->unif_pool;
+    for (int k = 0; k < GLX_MAX_FIELDS; k++) { S.fld_cnt[k] = s->fld_cnt[k]; S.fld_off[k] = s->fld_off[k]; }
+    memset(&O, 0, sizeof O);
+    O.gt = o->gt; O.rnc = o->rnc; O.allele_used = o->allele_used; O.site_flags = o->site_flags; O.error = err;
+    for (int k = 0; k < GLX_MAX_FIELDS; k++) O.fld[k] = o->fld[k];
+}
+
+static uint64_t first_candidate(const int32_t* maxend, uint64_t lo, uint64_t hi, int qbeg) {
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (maxend[mid] <= qbeg) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out) {
+    if (recs->n_datasets != sites->n_samples) return GLX_E_UNSUPPORTED;
+    for (uint32_t d = 0; d < recs->n_datasets; d++)
+        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) return GLX_E_UNSUPPORTED;
+    DCfg C; DRecs R; DSites S; DOut O;
+    unsigned long long err = ~0ull;
+    bind(cfg, recs, sites, out, &err, C, R, S, O);
+    const uint32_t Sn = sites->n_sites, N = sites->n_samples;
+    // site_flags is OR-ed through an aligned 32-bit word: give it padded storage
+    std::vector<uint8_t> flags(Sn + 8, 0);
+    O.site_flags = flags.data();
+    uint32_t max_slots = 1;
+    for (uint32_t s = 0; s < Sn; s++) {
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < cfg->n_fields; k++) t += sites->fld_cnt[k][s];
+        max_slots = std::max(max_slots, t);
+        out->allele_used[s] = 0;
+    }
+    std::vector<uint8_t> cnt(max_slots);
+    for (uint32_t s = 0; s < Sn; s++)
+        for (uint32_t n = 0; n < N; n++) {
+            const uint64_t lo = R.ds_rec_off[n], hi = R.ds_rec_off[n + 1];
+            genotype_cell_general(C, R, S, O, s, n, first_candidate(R.maxend, lo, hi, S.qbeg[s]), hi, cnt.data(), 1);
+        }
+    memcpy(out->site_flags, flags.data(), Sn);
+    if (err == ~0ull) return GLX_OK;
+    const int code = (int)(err & 0xff);
+    return code == 101 ? GLX_E_UNSUPPORTED : -code;
+}

@@ -1,0 +1,43 @@
+"""ctypes binding of tests/emu/libglx_emu.so — the device cell logic compiled for the host (TEST INFRASTRUCTURE).
+It exists so that the kernels' control flow can be diffed against the oracle on the CPU-only build box; the GPU
+tests (-m gpu) run the real CUDA build of the same headers through the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_PATH = os.path.join(EMU_DIR, "libglx_emu.so")
+_lib = None
+
+
+def build():
+    srcs = [os.path.join(EMU_DIR, "glx_emu.cc"), os.path.join(EMU_DIR, "cuda_host_shim.h")]
+    srcs += [os.path.join(ROOT, "glnexus_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "glnexus_b200", "csrc")) if f.endswith(".cuh")]
+    srcs.append(os.path.join(ROOT, "include", "glx.h"))
+    if os.path.exists(EMU_PATH) and all(os.path.getmtime(EMU_PATH) >= os.path.getmtime(s) for s in srcs):
+        return
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-sign-compare",
+                           "-o", EMU_PATH, os.path.join(EMU_DIR, "glx_emu.cc")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(EMU_PATH)
+        vp = C.c_void_p
+        for fn in ("glx_emu_general_batch", "glx_emu_tiled_batch"):
+            if hasattr(L, fn):
+                getattr(L, fn).argtypes = [vp, vp, vp, vp]
+                getattr(L, fn).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def general_batch(batch, out):
+    return lib().glx_emu_general_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr)
+
+
+def tiled_batch(batch, out):
+    return lib().glx_emu_tiled_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr)

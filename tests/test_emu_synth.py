@@ -1,0 +1,36 @@
+"""Device cell logic (host build, tests/emu) vs the oracle on seeded synthetic cohorts of the BASELINE shapes."""
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle_lib
+import synth_cases
+from test_emu_parity import compare_outs
+
+
+@pytest.mark.parametrize("shape", ["c2", "c3", "c4", "c5"])
+def test_emu_general_synth(built, shape):
+    b = synth_cases.make(shape, n_samples=96, n_sites=700, region_len=6000 if shape == "c2" else 40000)
+    ref, got = b.alloc_out(), b.alloc_out()
+    oracle_lib.genotype_batch(b, ref, threads=4)
+    assert emu_lib.general_batch(b, got) == 0
+    d = compare_outs(got, ref, b.n_fields)
+    assert not d, "\n".join(d)
+    rnc = set(ref.array("rnc").tobytes().decode())
+    assert {".", "M"} <= rnc
+
+
+@pytest.mark.parametrize("preset", ["gatk_unfiltered", "DeepVariant_unfiltered", "DeepVariantWES", "weCall", "Strelka2"])
+def test_emu_general_presets(built, preset):
+    b = synth_cases.make("c3", n_samples=40, n_sites=300, region_len=9000, preset=preset, frac_two_record_cells=0.05, frac_lost_allele=0.05,
+                         frac_homalt=0.2)
+    ref, got = b.alloc_out(), b.alloc_out()
+    try:
+        oracle_lib.genotype_batch(b, ref)
+        orc = 0
+    except oracle_lib.OracleError as e:
+        orc = e.code
+    assert emu_lib.general_batch(b, got) == orc
+    if orc == 0:
+        d = compare_outs(got, ref, b.n_fields)
+        assert not d, "\n".join(d)

@@ -1,0 +1,95 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (glx_genotype_batch / glx_upload+launch+download),
+against the oracle — bit-exact on every output column — and against the reference's truth pVCFs."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_lib
+import synth_cases
+import vcfcmp
+from test_emu_parity import compare_outs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    from glnexus_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", gu.case_names())
+def test_gpu_golden(ctx, name):
+    from glnexus_b200 import GlxError
+    case = gu.load_case(name)
+    texts = []
+    for batch in gu.batches_of_case(case):
+        ref, got = batch.alloc_out(), batch.alloc_out(pinned=True)
+        if not batch.device_supported:
+            with pytest.raises(GlxError) as ei:
+                ctx.genotype_batch(batch, got)
+            assert ei.value.code == -101  # rejected, not mis-computed (multi-sample dataset)
+            return
+        oracle_lib.genotype_batch(batch, ref)
+        ctx.genotype_batch(batch, got)
+        d = compare_outs(got, ref, batch.n_fields)
+        assert not d, "\n".join(d)
+        texts.append(batch.assemble_vcf(got))
+    diffs = vcfcmp.compare(gu.merge_vcf_texts(texts), case["truth_vcf"], case["formats"], case["infos"])
+    assert not diffs, "\n".join(diffs[:20])
+
+
+@pytest.mark.parametrize("shape,n_samples,n_sites,region_len", [
+    ("c2", 1000, 3000, 3000),
+    ("c3", 1500, 2000, 128000),
+    ("c4", 2000, 1500, 96000),
+    ("c5", 600, 2000, 60000),
+])
+def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len):
+    b = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len)
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    oracle_lib.genotype_batch(b, ref, threads=8)
+    dev = ctx.upload(b)
+    dev.launch()
+    dev.check()
+    dev.download(got)
+    assert dev.launch_count >= 1
+    dev.close()
+    d = compare_outs(got, ref, b.n_fields)
+    assert not d, "\n".join(d)
+
+
+@pytest.mark.parametrize("preset", ["gatk_unfiltered", "DeepVariant_unfiltered", "DeepVariantWES", "weCall", "Strelka2", "xAtlas"])
+def test_gpu_presets(ctx, preset):
+    from glnexus_b200 import GlxError
+    b = synth_cases.make("c3", n_samples=300, n_sites=800, region_len=24000, preset=preset, frac_two_record_cells=0.05,
+                         frac_lost_allele=0.05, frac_homalt=0.2)
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    try:
+        oracle_lib.genotype_batch(b, ref, threads=8)
+        orc = 0
+    except oracle_lib.OracleError as e:
+        orc = e.code
+    if orc != 0:
+        with pytest.raises(GlxError) as ei:
+            ctx.genotype_batch(b, got)
+        assert ei.value.code == orc
+        return
+    ctx.genotype_batch(b, got)
+    d = compare_outs(got, ref, b.n_fields)
+    assert not d, "\n".join(d)
+
+
+def test_gpu_empty_and_ragged(ctx):
+    """No sites; a cohort where many samples have no records at all in the range."""
+    b = synth_cases.make("c2", n_samples=33, n_sites=0, region_len=500)
+    got = b.alloc_out(pinned=True)
+    ctx.genotype_batch(b, got)
+    b = synth_cases.make("c2", n_samples=257, n_sites=400, region_len=400, frac_uncovered=0.9)
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    oracle_lib.genotype_batch(b, ref, threads=4)
+    ctx.genotype_batch(b, got)
+    d = compare_outs(got, ref, b.n_fields)
+    assert not d, "\n".join(d)
