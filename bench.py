@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py — site x sample genotype cells/s of the joint-genotyping hot path on N B200s (one process per GPU).
+
+A "step" is one pass of the hot path (glx_launch: every kernel of the path) over one contig-range batch of a
+seeded synthetic DeepVariant-style cohort (BASELINE.json configs[1]: 1,000 samples x 50,000 dense exome-like
+sites, 5e7 cells). At N>1 every rank owns its own contiguous site range of the same shape (weak scaling; sites
+shard with no collective), and `value` is the cells all ranks processed over the slowest rank's
+device time.
+
+  value     device-resident throughput: batch uploaded once, K launches timed with CUDA events on the launching
+            stream (L2 flushed between steps, flush not timed)
+  e2e       same metric through the reference-facing C ABI call glx_genotype_batch with HOST buffers: H2D of the
+            record store + sites, all kernels, D2H of the packed FORMAT columns, all inside the timed region
+  roofline  algorithmic bytes (SURVEY.md §8d definition) / tiled-kernel duration vs the measured HBM copy peak
+  cpu_baseline  the C++ oracle (port of the reference algorithm) on the box's host cores over a bounded sample
+
+`--impl reference` times the reference algorithm's CPU port (oracle/, all host threads) on the same config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "site x sample genotype cells/s"
+WORKLOADS = {
+    # name: (synthetic shape, samples, sites, region_len)
+    "c2": ("c2", 1000, 50000, 50000),
+    "c3": ("c3", 10000, 4096, 262144),   # one streamed batch of configs[2]
+    "c4": ("c4", 100000, 512, 32768),    # one streamed batch of configs[3]
+    "c5": ("c5", 5000, 10000, 300000),   # a tenth of configs[4]
+}
+
+
+def algorithmic_bytes(batch, n_var_cells):
+    """int32-equivalent bytes the reference's inner loops read/write per cell.
+    out/cell = 2 (GT) + 2 (RNC) + 4 per lifted value; in/cell = 34 for a reference-band cell,
+    22 + 5a + 2a(a+1) for a variant cell with an a-allele record (a=3 for REF,ALT,<*>)."""
+    import glnexus_b200
+    out_b = glnexus_b200.out_bytes_of(batch)
+    cells = batch.n_sites * batch.n_samples
+    in_b = 34 * (cells - n_var_cells) + 61 * n_var_cells
+    return out_b + in_b, out_b, in_b
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk = float(f[0])
+                mx = float(f[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: fall back to every sample taken
+            sm = [float(l.split(",")[0]) for _, l in self.lines if l and l.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(shape, n_samples, region_per_site, target_s=12.0, preset=None):
+    """Oracle (kind 'port') on all host threads over the first sites of the same workload."""
+    import oracle_lib
+    import synth_cases
+    cores = host_cores()
+    sites = 64
+    rate = None
+    while True:
+        b = synth_cases.make(shape, n_samples=n_samples, n_sites=sites, region_len=max(sites, int(sites * region_per_site)))
+        out = b.alloc_out()
+        t = time.time()
+        oracle_lib.genotype_batch(b, out, threads=cores)
+        dt = time.time() - t
+        cells = b.n_sites * b.n_samples
+        rate = cells / dt
+        if dt >= target_s * 0.6 or sites >= 1 << 20:
+            break
+        sites = int(min(max(sites * 2, sites * target_s / max(dt, 1e-3) * 0.9), sites * 16))
+    return {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
+            "sample": f"first {b.n_sites} sites x {n_samples} samples of the same synthetic cohort ({cells} cells, {dt:.1f} s), one task per site on {cores} threads, faithful data structures"}, b
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    shape, n_samples, n_sites, region_len = WORKLOADS[args.workload]
+    if args.samples:
+        n_samples = args.samples
+    import oracle_lib
+    import synth_cases
+    cores = host_cores()
+    # bounded sample per step: sized from a probe so that (steps+warmup) steps end within a few minutes
+    probe, b = cpu_baseline(shape, n_samples, region_len / n_sites, target_s=2.0)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    sites = max(16, int(probe["value"] * min(budget, 15.0) / n_samples))
+    b = synth_cases.make(shape, n_samples=n_samples, n_sites=sites, region_len=max(sites, int(sites * region_len / n_sites)))
+    out = b.alloc_out()
+    cells = b.n_sites * b.n_samples
+    for _ in range(args.warmup):
+        oracle_lib.genotype_batch(b, out, threads=cores)
+    t = time.time()
+    for _ in range(args.steps):
+        oracle_lib.genotype_batch(b, out, threads=cores)
+    dt = time.time() - t
+    v = cells * args.steps / dt
+    sample = f"{b.n_sites} sites x {n_samples} samples per step ({cells} cells), oracle port of genotype_site, one task per site on {cores} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+        "data": "synthetic", "config": {"workload": workload_name(args.workload, n_samples, n_sites), "preset": synth_cases.SHAPES[shape][0]},
+        "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_name(w, n_samples, n_sites):
+    desc = {"c2": "BASELINE configs[1]: synthetic DeepVariant-style cohort, exome-like dense sites, biallelic-dominant",
+            "c3": "BASELINE configs[2] (one streamed 4096-site batch): synthetic WGS cohort with reference bands and MIN_DP",
+            "c4": "BASELINE configs[3] (one streamed batch): large sparse cohort, revise_genotypes AF priors on",
+            "c5": "BASELINE configs[4] (subset): multi-allelic stress, --config gatk, up to 6 ALT"}[w]
+    return f"{desc}; {n_samples} samples x {n_sites} sites per GPU"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--sites", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import glnexus_b200
+    import synth_cases
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    shape, n_samples, n_sites, region_len = WORKLOADS[args.workload]
+    if args.samples:
+        n_samples = args.samples
+    if args.sites:
+        region_len = int(region_len * args.sites / n_sites)
+        n_sites = args.sites
+    # rank r genotypes its own contiguous genomic range (weak scaling): same shape, next region, own seed stream
+    seed = synth_cases.SHAPES[shape][1]["seed"] + 1000 * rank
+    batch = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len,
+                             region_beg=10_000_000 + rank * region_len, seed=seed)
+    cells = batch.n_sites * batch.n_samples
+
+    ctx = glnexus_b200.Context(local_rank)
+    dev = ctx.upload(batch)
+    dev.set_profile(True)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            dev.launch(stream.cuda_stream)
+        dev.check()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        tiled_ms, general_ms = [], []
+        t0 = time.time()
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream)
+            dev.launch(stream.cuda_stream)
+            b.record(stream)
+            tm, gm = dev.kernel_ms()  # waits for this step's kernels
+            tiled_ms.append(tm)
+            general_ms.append(gm)
+        barrier()
+        t1 = time.time()
+        clocks = sampler.stop(t0, t1)
+    dev.check()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    launches = dev.launch_count * args.steps
+
+    # ---- end to end through the C ABI with host buffers ----
+    out = batch.alloc_out(pinned=True)
+    e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
+    ctx.genotype_batch(batch, out)  # warm the arena cache
+    barrier()
+    te = time.time()
+    for _ in range(e2e_steps):
+        ctx.genotype_batch(batch, out)
+    torch.cuda.synchronize()
+    e2e_s = time.time() - te
+    h2d = dev.in_bytes
+    d2h = dev.out_bytes
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = t.tolist()
+        c = torch.tensor([cells], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cells_all = int(c.item())
+    else:
+        cells_all = cells
+
+    if rank == 0:
+        value = cells_all * args.steps / (total_ms * 1e-3)
+        e2e_v = cells_all * e2e_steps / e2e_s
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        n_var_cells = int(batch.variant_records)
+        alg, out_b, in_b = algorithmic_bytes(batch, n_var_cells)
+        dom_ms = statistics.mean(tiled_ms) if statistics.mean(tiled_ms) >= statistics.mean(general_ms) else statistics.mean(general_ms)
+        dom = "glx_cells_tiled_kernel" if statistics.mean(tiled_ms) >= statistics.mean(general_ms) else "glx_cells_general_kernel"
+        achieved = alg / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, n_samples, n_sites), "preset": synth_cases.SHAPES[shape][0],
+                       "cells_per_gpu": cells, "records_per_gpu": int(batch.n_records), "variant_records_per_gpu": int(batch.variant_records),
+                       "l2": "flushed between timed steps (256 MiB write, untimed); outputs (%.2f GB/step) exceed L2" % (out_b / 1e9)},
+            "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+            "gpu_launches": launches,
+            "kernels": {"tiled_ms": statistics.mean(tiled_ms), "general_ms": statistics.mean(general_ms), "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "bytes_out": out_b, "bytes_in": in_b,
+                         "achieved_output_only": out_b / (dom_ms * 1e-3) / 1e9},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_baseline(shape, n_samples, region_len / n_sites)
+            line["cpu_baseline"] = cb
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    dev.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

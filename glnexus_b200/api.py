@@ -102,6 +102,12 @@ def lib():
     L.glx_free_batch.restype = None
     L.glx_synchronize.argtypes = [vp]
     L.glx_synchronize.restype = C.c_int
+    L.glx_set_profile.argtypes = [vp, vp, C.c_int]
+    L.glx_set_profile.restype = C.c_int
+    L.glx_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.glx_kernel_ms.restype = C.c_int
+    L.glx_stream.argtypes = [vp]
+    L.glx_stream.restype = vp
     _lib = L
     return L
 
@@ -239,6 +245,15 @@ class DeviceBatch:
     def download(self, out):
         self.ctx._check(lib().glx_download(self.ctx.handle, self.handle, out.ptr))
 
+    def set_profile(self, on=True):
+        self.ctx._check(lib().glx_set_profile(self.ctx.handle, self.handle, 1 if on else 0))
+
+    def kernel_ms(self):
+        """(tiled kernel ms, general kernel ms) of the last launch, from CUDA events on the launching stream."""
+        a, b = C.c_float(), C.c_float()
+        self.ctx._check(lib().glx_kernel_ms(self.ctx.handle, self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def out_bytes(self):
         return lib().glx_out_bytes(self.handle)
@@ -284,10 +299,23 @@ class Context:
     def synchronize(self):
         self._check(lib().glx_synchronize(self.handle))
 
+    @property
+    def stream_ptr(self):
+        return lib().glx_stream(self.handle)
+
     def close(self):
         if self.handle:
             lib().glx_destroy(self.handle)
             self.handle = None
+
+
+def out_bytes_of(batch):
+    """Bytes of the packed output columns of a batch (GT + RNC + lifted FORMAT values)."""
+    o = batch.alloc_out()
+    try:
+        return int(sum(a.nbytes for k, a in o.arrays().items() if k not in ("allele_used", "site_flags")))
+    finally:
+        o.close()
 
 
 def preset_text(name):

@@ -58,6 +58,51 @@ struct glx_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int sm_count = 0;
+    // freed batch arenas are kept for the next batch of the same range stream (cudaMalloc/cudaFree of GB-sized
+    // buffers costs milliseconds and would dominate a per-batch call)
+    struct Cached {
+        void* p = nullptr;
+        size_t bytes = 0;
+    } cache[6];
+    cudaError_t take(void** p, size_t bytes) {
+        int best = -1;
+        for (int i = 0; i < 6; i++)
+            if (cache[i].p && cache[i].bytes >= bytes && (best < 0 || cache[i].bytes < cache[best].bytes)) best = i;
+        if (best >= 0 && cache[best].bytes <= bytes * 2 + (1 << 20)) {
+            *p = cache[best].p;
+            cache[best] = Cached();
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) {  // release the cache and retry once
+            cudaGetLastError();
+            for (int i = 0; i < 6; i++)
+                if (cache[i].p) {
+                    cudaFree(cache[i].p);
+                    cache[i] = Cached();
+                }
+            e = cudaMalloc(p, bytes);
+        }
+        return e;
+    }
+    void give(void* p, size_t bytes) {
+        if (!p) return;
+        int slot = -1;
+        for (int i = 0; i < 6; i++)
+            if (!cache[i].p) slot = i;
+        if (slot < 0) {  // evict the smallest
+            slot = 0;
+            for (int i = 1; i < 6; i++)
+                if (cache[i].bytes < cache[slot].bytes) slot = i;
+            if (cache[slot].bytes >= bytes) {
+                cudaFree(p);
+                return;
+            }
+            cudaFree(cache[slot].p);
+        }
+        cache[slot].p = p;
+        cache[slot].bytes = bytes;
+    }
 };
 
 namespace {
@@ -93,7 +138,9 @@ struct glx_dev_batch {
     DOut O;
     char* in_base = nullptr;
     char* out_base = nullptr;
-    size_t in_bytes = 0, out_bytes = 0;
+    size_t in_bytes = 0, out_bytes = 0, in_alloc = 0, out_alloc = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool profile = false;
     uint32_t n_sites = 0, n_samples = 0, n_fields = 0;
     uint64_t n_cells = 0;
     uint64_t fld_total[GLX_MAX_FIELDS] = {};
@@ -137,6 +184,8 @@ int glx_create(glx_ctx** out, int device) {
 void glx_destroy(glx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (auto& c : ctx->cache)
+        if (c.p) cudaFree(c.p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -155,9 +204,17 @@ void* glx_stream(glx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
     if (!d) return;
     if (ctx) cudaSetDevice(ctx->device);
-    if (d->in_base) cudaFree(d->in_base);
-    if (d->out_base) cudaFree(d->out_base);
-    if (d->cnt_scratch) cudaFree(d->cnt_scratch);
+    for (auto& ev : d->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx) {
+        ctx->give(d->in_base, d->in_alloc);
+        ctx->give(d->out_base, d->out_alloc);
+        ctx->give(d->cnt_scratch, d->cnt_scratch_bytes);
+    } else {
+        if (d->in_base) cudaFree(d->in_base);
+        if (d->out_base) cudaFree(d->out_base);
+        if (d->cnt_scratch) cudaFree(d->cnt_scratch);
+    }
     delete d;
 }
 
@@ -263,7 +320,8 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     size_t total = 0;
     for (auto& it : items) total += ((it.bytes + 255) & ~(size_t)255) + 256;
     d->in_bytes = total;
-    cudaError_t e = cudaMalloc(&d->in_base, total ? total : 256);
+    d->in_alloc = total ? total : 256;
+    cudaError_t e = ctx->take((void**)&d->in_base, d->in_alloc);
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
         return cuda_fail(ctx, e, "cudaMalloc(input arena)");
@@ -299,7 +357,8 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     osz(8);
     for (uint32_t k = 0; k < cfg->n_fields; k++) osz(d->fld_total[k] * 4);
     d->out_bytes = ob;
-    e = cudaMalloc(&d->out_base, ob);
+    d->out_alloc = ob;
+    e = ctx->take((void**)&d->out_base, ob);
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
         return cuda_fail(ctx, e, "cudaMalloc(output arena)");
@@ -319,7 +378,7 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     const uint64_t cap = (uint64_t)ctx->sm_count * 16;
     d->general_blocks = (int)(want_blocks < cap ? (want_blocks ? want_blocks : 1) : cap);
     d->cnt_scratch_bytes = (size_t)d->general_blocks * threads * max_slots;
-    e = cudaMalloc(&d->cnt_scratch, d->cnt_scratch_bytes);
+    e = ctx->take((void**)&d->cnt_scratch, d->cnt_scratch_bytes);
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
         return cuda_fail(ctx, e, "cudaMalloc(scratch)");
@@ -342,11 +401,14 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     CU(cudaMemsetAsync(d->O.site_flags, 0, S + 4, st));
     CU(cudaMemsetAsync(d->O.error, 0xff, 8, st));
     d->launches_per_call = 0;
+    if (d->profile) CU(cudaEventRecord(d->ev[0], st));
+    if (d->profile) CU(cudaEventRecord(d->ev[1], st));
     if (d->n_cells) {
         glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, nullptr, d->n_cells, d->cnt_scratch, d->max_slots);
         d->launches_per_call++;
         CU(cudaGetLastError());
     }
+    if (d->profile) CU(cudaEventRecord(d->ev[2], st));
     return GLX_OK;
 }
 
@@ -381,6 +443,28 @@ int glx_download(glx_ctx* ctx, glx_dev_batch* d, glx_out* out) {
     for (uint32_t k = 0; k < d->n_fields; k++)
         if (d->fld_total[k]) CU(cudaMemcpyAsync(out->fld[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return GLX_OK;
+}
+
+int glx_set_profile(glx_ctx* ctx, glx_dev_batch* d, int on) {
+    if (!ctx || !d) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    d->profile = on != 0;
+    if (d->profile)
+        for (auto& ev : d->ev)
+            if (!ev) CU(cudaEventCreate(&ev));
+    return GLX_OK;
+}
+
+int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* d, float* tiled_ms, float* general_ms) {
+    if (!ctx || !d || !d->profile) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(d->ev[2]));
+    float a = 0, b = 0;
+    CU(cudaEventElapsedTime(&a, d->ev[0], d->ev[1]));
+    CU(cudaEventElapsedTime(&b, d->ev[1], d->ev[2]));
+    if (tiled_ms) *tiled_ms = a;
+    if (general_ms) *general_ms = b;
     return GLX_OK;
 }
 

@@ -212,6 +212,14 @@ uint64_t glx_out_bytes(const glx_dev_batch* dev);
 uint64_t glx_in_bytes(const glx_dev_batch* dev);
 int glx_launch_count(const glx_dev_batch* dev); /* kernels per glx_launch */
 void glx_free_batch(glx_ctx* ctx, glx_dev_batch* dev);
+/* Measurement aid: record CUDA events around each kernel of glx_launch on the launching stream;
+ * glx_kernel_ms waits for the last launch and returns the tiled (fast-path) and general kernel durations. */
+int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);
+int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float* tiled_ms, float* general_ms);
+void* glx_stream(glx_ctx* ctx); /* the context's cudaStream_t */
+/* pinned host memory for caller-owned buffers (cudaHostAlloc) */
+void* glx_pinned_alloc(size_t bytes);
+void glx_pinned_free(void* p);
 int glx_synchronize(glx_ctx* ctx);
 
 #ifdef __cplusplus
