@@ -104,13 +104,12 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(shape, n_samples, region_per_site, target_s=12.0, preset=None):
-    """Oracle (kind 'port') on all host threads over the first sites of the same workload."""
+def cpu_baseline(shape, n_samples, region_per_site, max_sites, target_s=12.0):
+    """Oracle (kind 'port') on all host threads over the first sites of the same workload (at most the workload)."""
     import oracle_lib
     import synth_cases
     cores = host_cores()
-    sites = 64
-    rate = None
+    sites = min(64, max_sites)
     while True:
         b = synth_cases.make(shape, n_samples=n_samples, n_sites=sites, region_len=max(sites, int(sites * region_per_site)))
         out = b.alloc_out()
@@ -118,12 +117,19 @@ def cpu_baseline(shape, n_samples, region_per_site, target_s=12.0, preset=None):
         oracle_lib.genotype_batch(b, out, threads=cores)
         dt = time.time() - t
         cells = b.n_sites * b.n_samples
-        rate = cells / dt
-        if dt >= target_s * 0.6 or sites >= 1 << 20:
+        if dt >= target_s * 0.6 or sites >= max_sites:
             break
-        sites = int(min(max(sites * 2, sites * target_s / max(dt, 1e-3) * 0.9), sites * 16))
+        sites = int(min(max(sites * 2, sites * target_s / max(dt, 1e-3) * 0.9), sites * 16, max_sites))
+    reps = 1
+    while dt < target_s * 0.6 and reps < 64:  # whole workload is shorter than the target: repeat it
+        t = time.time()
+        oracle_lib.genotype_batch(b, out, threads=cores)
+        dt += time.time() - t
+        reps += 1
+    rate = cells * reps / dt
     return {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
-            "sample": f"first {b.n_sites} sites x {n_samples} samples of the same synthetic cohort ({cells} cells, {dt:.1f} s), one task per site on {cores} threads, faithful data structures"}, b
+            "sample": f"first {b.n_sites} sites x {n_samples} samples of the same synthetic cohort ({cells} cells) x {reps} passes in {dt:.1f} s, "
+                      f"one task per site on {cores} host threads, reference-faithful data structures"}, b
 
 
 def run_reference(args, rank, world):
@@ -136,9 +142,9 @@ def run_reference(args, rank, world):
     import synth_cases
     cores = host_cores()
     # bounded sample per step: sized from a probe so that (steps+warmup) steps end within a few minutes
-    probe, b = cpu_baseline(shape, n_samples, region_len / n_sites, target_s=2.0)
+    probe, b = cpu_baseline(shape, n_samples, region_len / n_sites, n_sites, target_s=2.0)
     budget = 150.0 / max(1, args.steps + args.warmup)
-    sites = max(16, int(probe["value"] * min(budget, 15.0) / n_samples))
+    sites = min(n_sites, max(16, int(probe["value"] * min(budget, 15.0) / n_samples)))
     b = synth_cases.make(shape, n_samples=n_samples, n_sites=sites, region_len=max(sites, int(sites * region_len / n_sites)))
     out = b.alloc_out()
     cells = b.n_sites * b.n_samples
@@ -306,7 +312,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_baseline(shape, n_samples, region_len / n_sites)
+            cb, _ = cpu_baseline(shape, n_samples, region_len / n_sites, n_sites)
             line["cpu_baseline"] = cb
         else:
             line["cpu_baseline"] = None

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/glx.h"
+#include "glx_cell_fast.cuh"
 #include "glx_cell_general.cuh"
 #include "glx_dev_types.cuh"
 
@@ -22,14 +23,134 @@ using namespace glxd;
 // kernels
 // ---------------------------------------------------------------------------------------------
 
-// first record of [lo,hi) whose running max end exceeds qbeg (records with maxend <= qbeg cannot overlap the query)
-__device__ __forceinline__ uint64_t first_candidate(const int32_t* __restrict__ maxend, uint64_t lo, uint64_t hi, int qbeg) {
-    while (lo < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        if (maxend[mid] <= qbeg) lo = mid + 1;
-        else hi = mid;
+// Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
+// a cursor into its sample's records and the resolved values of the band under the cursor (shared memory, column per
+// lane). Per site each lane classifies its cell (fast_classify); finished cells are written with warp-transposed,
+// fully coalesced stores; the rest are appended to the worklist of the general kernel.
+__global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
+                                                                           uint32_t* __restrict__ worklist, uint32_t* __restrict__ n_work, uint32_t n_sample_blocks) {
+    __shared__ int s_beg[GLX_TILE_SITES], s_end[GLX_TILE_SITES], s_qbeg[GLX_TILE_SITES], s_qend[GLX_TILE_SITES];
+    __shared__ uint8_t s_flags[GLX_TILE_SITES];  // bit0: general path only (monoallelic), bit1: qbeg below the previous site's
+    __shared__ uint16_t s_cnt[GLX_MAX_FIELDS][GLX_TILE_SITES];
+    __shared__ unsigned long long s_off[GLX_MAX_FIELDS][GLX_TILE_SITES];
+    __shared__ uint32_t s_used[GLX_TILE_SITES], s_lost[GLX_TILE_SITES];
+    __shared__ int32_t s_rv[GLX_FAST_RV * GLX_TILE_THREADS];
+    __shared__ int32_t s_stage[GLX_TILE_THREADS / 32][32 * GLX_STAGE_MAX];
+
+    const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
+    const uint32_t site0 = tile * GLX_TILE_SITES;
+    const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
+    const uint32_t N = S.n_samples;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sample = sb * GLX_TILE_THREADS + tid;
+    const bool active = sample < N;
+    const uint32_t warp_sample0 = sb * GLX_TILE_THREADS + warp * 32;
+    const uint32_t nvalid = warp_sample0 >= N ? 0u : min(32u, N - warp_sample0);
+
+    for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
+        const uint32_t s = site0 + i;
+        s_beg[i] = S.beg[s];
+        s_end[i] = S.end[s];
+        const int qb = S.qbeg[s];
+        s_qbeg[i] = qb;
+        s_qend[i] = S.qend[s];
+        s_flags[i] = (S.monoallelic[s] ? 1 : 0) | ((i > 0 && qb < S.qbeg[s - 1]) ? 2 : 0);
+        s_used[i] = 0;
+        s_lost[i] = 0;
+        for (uint32_t k = 0; k < cfg.n_fields; k++) {
+            s_cnt[k][i] = S.fld_cnt[k][s];
+            s_off[k][i] = S.fld_off[k][s];
+        }
     }
-    return lo;
+    __syncthreads();
+
+    LaneCursor L;
+    L.base = 0;
+    L.n = L.c = 0;
+    L.beg_c = L.end_c = L.maxend_c = L.beg_n = 0x7fffffff;
+    if (active) cursor_init(R, L, sample, s_qbeg[0]);
+    uint32_t resolved = 0xffffffffu, rbits = 0;
+    int mrd = -1;
+    int32_t* rv = s_rv + tid;
+    int32_t* stage = s_stage[warp];
+
+    for (uint32_t i = 0; i < nsite; i++) {
+        const uint32_t s = site0 + i;
+        FastCell cell;
+        cell.type = CT_MISSING;
+        cell.a0 = cell.a1 = -1;
+        cell.rnc0 = cell.rnc1 = RNC_M;
+        if (active)
+            cell = fast_classify(cfg, plan, R, L, s_beg[i], s_end[i], s_qbeg[i], s_qend[i], s_flags[i] & 1, s_flags[i] & 2, resolved, rbits, mrd, rv,
+                                 GLX_TILE_THREADS);
+        const bool slow = active && cell.type == CT_SLOW;
+        // ---- hand unfinished cells to the general kernel (warp-aggregated append) ----
+        const uint32_t slow_mask = __ballot_sync(0xffffffffu, slow);
+        if (slow_mask) {
+            uint32_t base = 0;
+            const int leader = __ffs(slow_mask) - 1;
+            if ((int)lane == leader) base = atomicAdd(n_work, (uint32_t)__popc(slow_mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (slow) worklist[base + __popc(slow_mask & ((1u << lane) - 1))] = s * N + sample;
+        }
+        // ---- GT / RNC ----
+        if (active && !slow) {
+            const size_t c2 = ((size_t)s * N + sample) * 2;
+            *reinterpret_cast<char2*>(O.gt + c2) = make_char2((signed char)cell.a0, (signed char)cell.a1);
+            *reinterpret_cast<uchar2*>(O.rnc + c2) = make_uchar2((unsigned char)kRncChar[cell.rnc0], (unsigned char)kRncChar[cell.rnc1]);
+        }
+        uint32_t used = 0;
+        if (active && !slow && cell.a0 >= 0) used = 1u;  // fast cells only ever call allele 0
+        used = __reduce_or_sync(0xffffffffu, used);
+        const bool lost = __any_sync(0xffffffffu, active && !slow && cell.rnc0 == RNC_I);
+        if (lane == 0) {
+            if (used) atomicOr(&s_used[i], used);
+            if (lost) atomicOr(&s_lost[i], 1u);
+        }
+        // ---- lifted FORMAT fields ----
+        const int type = slow ? CT_MISSING : cell.type;  // placeholder values; the general kernel rewrites slow cells
+        for (uint32_t k = 0; k < cfg.n_fields; k++) {
+            const DFld& f = cfg.f[k];
+            const int count = s_cnt[k][i];
+            int32_t* out = O.fld[k] + s_off[k][i] + (unsigned long long)warp_sample0 * count;
+            if (count == 1) {
+                if (active) out[lane] = fast_value(f, plan, k, type, 1, 0, 0, 0, rv, GLX_TILE_THREADS);
+            } else if (count <= GLX_STAGE_MAX) {
+                if (active) {
+                    int a = 0, b = 0;
+                    for (int j = 0; j < count; j++) {
+                        stage[lane * count + j] = fast_value(f, plan, k, type, count, j, a, b, rv, GLX_TILE_THREADS);
+                        if (++b > a) {
+                            a++;
+                            b = 0;
+                        }
+                    }
+                }
+                __syncwarp();
+                const uint32_t total = nvalid * count;
+                for (uint32_t e = lane; e < total; e += 32) out[e] = stage[e];
+                __syncwarp();
+            } else if (active) {
+                int a = 0, b = 0;
+                for (int j = 0; j < count; j++) {
+                    out[(size_t)lane * count + j] = fast_value(f, plan, k, type, count, j, a, b, rv, GLX_TILE_THREADS);
+                    if (++b > a) {
+                        a++;
+                        b = 0;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
+        if (s_used[i]) atomicOr(O.allele_used + site0 + i, s_used[i]);
+        if (s_lost[i]) {
+            uint8_t* fp = O.site_flags + site0 + i;
+            uint32_t* w = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(fp) & ~(uintptr_t)3);
+            atomicOr(w, 1u << (8 * (reinterpret_cast<uintptr_t>(fp) & 3)));
+        }
+    }
 }
 
 // General path: one thread per cell, taken from a worklist (or every cell of the batch when worklist == nullptr).
@@ -150,6 +271,11 @@ struct glx_dev_batch {
     int general_blocks = 0;
     int launches_per_call = 0;
     bool force_general = false;
+    FastPlan plan;
+    uint32_t* worklist = nullptr;  // [n_cells] cell ids for the general kernel
+    uint32_t* n_work = nullptr;
+    size_t worklist_bytes = 0;
+    uint32_t n_sample_blocks = 0, n_site_tiles = 0;
 };
 
 extern "C" {
@@ -210,7 +336,9 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
         ctx->give(d->in_base, d->in_alloc);
         ctx->give(d->out_base, d->out_alloc);
         ctx->give(d->cnt_scratch, d->cnt_scratch_bytes);
+        ctx->give(d->worklist, d->worklist_bytes);
     } else {
+        if (d->worklist) cudaFree(d->worklist);
         if (d->in_base) cudaFree(d->in_base);
         if (d->out_base) cudaFree(d->out_base);
         if (d->cnt_scratch) cudaFree(d->cnt_scratch);
@@ -383,6 +511,19 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
         glx_free_batch(ctx, d);
         return cuda_fail(ctx, e, "cudaMalloc(scratch)");
     }
+    d->plan = make_fast_plan(d->cfg);
+    if (d->force_general) d->plan.enabled = 0;
+    d->n_sample_blocks = (uint32_t)((N + GLX_TILE_THREADS - 1) / GLX_TILE_THREADS);
+    d->n_site_tiles = (uint32_t)((S + GLX_TILE_SITES - 1) / GLX_TILE_SITES);
+    if (d->plan.enabled && d->n_cells) {
+        d->worklist_bytes = (d->n_cells + 64) * 4;
+        e = ctx->take((void**)&d->worklist, d->worklist_bytes);
+        if (e != cudaSuccess) {
+            glx_free_batch(ctx, d);
+            return cuda_fail(ctx, e, "cudaMalloc(worklist)");
+        }
+        d->n_work = d->worklist + d->n_cells + 32;
+    }
     e = cudaStreamSynchronize(ctx->stream);  // caller's host arrays may be released after return
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
@@ -401,10 +542,19 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     CU(cudaMemsetAsync(d->O.site_flags, 0, S + 4, st));
     CU(cudaMemsetAsync(d->O.error, 0xff, 8, st));
     d->launches_per_call = 0;
+    const bool tiled = d->plan.enabled && d->n_cells;
+    if (tiled) CU(cudaMemsetAsync(d->n_work, 0, 4, st));
     if (d->profile) CU(cudaEventRecord(d->ev[0], st));
+    if (tiled) {
+        glx_cells_tiled_kernel<<<d->n_sample_blocks * d->n_site_tiles, GLX_TILE_THREADS, 0, st>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work,
+                                                                                                d->n_sample_blocks);
+        d->launches_per_call++;
+        CU(cudaGetLastError());
+    }
     if (d->profile) CU(cudaEventRecord(d->ev[1], st));
     if (d->n_cells) {
-        glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, nullptr, d->n_cells, d->cnt_scratch, d->max_slots);
+        glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, tiled ? d->worklist : nullptr, d->n_work, d->n_cells, d->cnt_scratch,
+                                                                    d->max_slots);
         d->launches_per_call++;
         CU(cudaGetLastError());
     }

@@ -5,6 +5,7 @@
 
 #include <vector>
 
+#include "../../glnexus_b200/csrc/glx_cell_fast.cuh"
 #include "../../glnexus_b200/csrc/glx_cell_general.cuh"
 
 using namespace glxd;
@@ -27,15 +28,6 @@ static void bind(const glx_config* cfg, const glx_records* r, const glx_sites* s
     memset(&O, 0, sizeof O);
     O.gt = o->gt; O.rnc = o->rnc; O.allele_used = o->allele_used; O.site_flags = o->site_flags; O.error = err;
     for (int k = 0; k < GLX_MAX_FIELDS; k++) O.fld[k] = o->fld[k];
-}
-
-static uint64_t first_candidate(const int32_t* maxend, uint64_t lo, uint64_t hi, int qbeg) {
-    while (lo < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        if (maxend[mid] <= qbeg) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
 }
 
 extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out) {
@@ -63,6 +55,76 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
             genotype_cell_general(C, R, S, O, s, n, first_candidate(R.maxend, lo, hi, S.qbeg[s]), hi, cnt.data(), 1);
         }
     memcpy(out->site_flags, flags.data(), Sn);
+    if (err == ~0ull) return GLX_OK;
+    const int code = (int)(err & 0xff);
+    return code == 101 ? GLX_E_UNSUPPORTED : -code;
+}
+
+// The tiled kernel's per-lane state machine run lane by lane: same tiles, same cursor walk, same classify /
+// resolve / value functions; cells it declines go through the general cell. (The warp-transposed stores and
+// the worklist hand-off are CUDA-only and are covered by the GPU tests.)
+extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out, uint64_t* n_slow_out) {
+    if (recs->n_datasets != sites->n_samples) return GLX_E_UNSUPPORTED;
+    for (uint32_t d = 0; d < recs->n_datasets; d++)
+        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) return GLX_E_UNSUPPORTED;
+    DCfg C; DRecs R; DSites S; DOut O;
+    unsigned long long err = ~0ull;
+    bind(cfg, recs, sites, out, &err, C, R, S, O);
+    const FastPlan plan = make_fast_plan(C);
+    const uint32_t Sn = sites->n_sites, N = sites->n_samples;
+    std::vector<uint8_t> flags(Sn + 8, 0);
+    O.site_flags = flags.data();
+    uint32_t max_slots = 1;
+    for (uint32_t s = 0; s < Sn; s++) {
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < cfg->n_fields; k++) t += sites->fld_cnt[k][s];
+        max_slots = std::max(max_slots, t);
+        out->allele_used[s] = 0;
+    }
+    std::vector<uint8_t> cnt(max_slots);
+    uint64_t n_slow = 0;
+    for (uint32_t n = 0; n < N; n++) {
+        for (uint32_t site0 = 0; site0 < Sn; site0 += GLX_TILE_SITES) {
+            const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);
+            LaneCursor L;
+            int32_t rv[GLX_FAST_RV];
+            uint32_t resolved = 0xffffffffu, rbits = 0;
+            int mrd = -1;
+            if (plan.enabled) cursor_init(R, L, n, S.qbeg[site0]);
+            for (uint32_t i = 0; i < nsite; i++) {
+                const uint32_t s = site0 + i;
+                FastCell cell;
+                cell.type = CT_SLOW;
+                if (plan.enabled)
+                    cell = fast_classify(C, plan, R, L, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1],
+                                         resolved, rbits, mrd, rv, 1);
+                if (cell.type == CT_SLOW) {
+                    n_slow++;
+                    const uint64_t lo = R.ds_rec_off[n], hi = R.ds_rec_off[n + 1];
+                    genotype_cell_general(C, R, S, O, s, n, first_candidate(R.maxend, lo, hi, S.qbeg[s]), hi, cnt.data(), 1);
+                    continue;
+                }
+                const size_t c2 = ((size_t)s * N + n) * 2;
+                O.gt[c2] = (int8_t)cell.a0;
+                O.gt[c2 + 1] = (int8_t)cell.a1;
+                O.rnc[c2] = (uint8_t)kRncChar[cell.rnc0];
+                O.rnc[c2 + 1] = (uint8_t)kRncChar[cell.rnc1];
+                if (cell.a0 >= 0) O.allele_used[s] |= 1u;
+                if (cell.rnc0 == RNC_I) flags[s] |= 1;
+                for (uint32_t k = 0; k < C.n_fields; k++) {
+                    const int count = S.fld_cnt[k][s];
+                    int32_t* o = O.fld[k] + S.fld_off[k][s] + (uint64_t)n * count;
+                    int a = 0, b = 0;
+                    for (int j = 0; j < count; j++) {
+                        o[j] = fast_value(C.f[k], plan, k, cell.type, count, j, a, b, rv, 1);
+                        if (++b > a) { a++; b = 0; }
+                    }
+                }
+            }
+        }
+    }
+    memcpy(out->site_flags, flags.data(), Sn);
+    if (n_slow_out) *n_slow_out = n_slow;
     if (err == ~0ull) return GLX_OK;
     const int code = (int)(err & 0xff);
     return code == 101 ? GLX_E_UNSUPPORTED : -code;

@@ -27,10 +27,10 @@ def lib():
         build()
         L = C.CDLL(EMU_PATH)
         vp = C.c_void_p
-        for fn in ("glx_emu_general_batch", "glx_emu_tiled_batch"):
-            if hasattr(L, fn):
-                getattr(L, fn).argtypes = [vp, vp, vp, vp]
-                getattr(L, fn).restype = C.c_int
+        L.glx_emu_general_batch.argtypes = [vp, vp, vp, vp]
+        L.glx_emu_general_batch.restype = C.c_int
+        L.glx_emu_tiled_batch.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+        L.glx_emu_tiled_batch.restype = C.c_int
         _lib = L
     return _lib
 
@@ -40,4 +40,7 @@ def general_batch(batch, out):
 
 
 def tiled_batch(batch, out):
-    return lib().glx_emu_tiled_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr)
+    """Returns (status, number of cells the fast path declined)."""
+    n = C.c_uint64()
+    rc = lib().glx_emu_tiled_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr, C.byref(n))
+    return rc, n.value

@@ -29,10 +29,14 @@ def test_emu_general_matches_oracle(built, name):
         except oracle_lib.OracleError as e:
             orc = e.code
         rc = emu_lib.general_batch(batch, got)
+        got2 = batch.alloc_out()
+        rc2, _ = emu_lib.tiled_batch(batch, got2)
         if not batch.device_supported:
-            assert rc == -101
+            assert rc == -101 and rc2 == -101
             continue
-        assert rc == orc
+        assert rc == orc and rc2 == orc
         if rc == 0:
             d = compare_outs(got, ref, batch.n_fields)
-            assert not d, "\n".join(d)
+            assert not d, "general:\n" + "\n".join(d)
+            d = compare_outs(got2, ref, batch.n_fields)
+            assert not d, "tiled:\n" + "\n".join(d)

@@ -47,7 +47,13 @@ def test_gpu_golden(ctx, name):
     ("c4", 2000, 1500, 96000),
     ("c5", 600, 2000, 60000),
 ])
-def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len):
+@pytest.mark.parametrize("force_general", [False, True])
+def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, force_general, monkeypatch):
+    """Tiled fast path + general worklist (default) and the general kernel alone must both equal the oracle."""
+    if force_general:
+        monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
+    else:
+        monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
     b = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len)
     ref, got = b.alloc_out(), b.alloc_out(pinned=True)
     oracle_lib.genotype_batch(b, ref, threads=8)
@@ -55,7 +61,7 @@ def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len):
     dev.launch()
     dev.check()
     dev.download(got)
-    assert dev.launch_count >= 1
+    assert dev.launch_count == (1 if force_general else 2)
     dev.close()
     d = compare_outs(got, ref, b.n_fields)
     assert not d, "\n".join(d)
