@@ -12,21 +12,30 @@
 //   0/0 or Depth      by min_ref_depth = MIN_DP vs required_dp
 //   lifted fields     = the band's own values; allele map is [0,-1] so only slot 0 of allele/genotype-numbered
 //                       fields receives a value; PL2 back-fills through the symbolic allele
-// The band's field values are resolved once per (lane, record) and cached; a lane re-reads nothing while
-// consecutive sites fall in the same band.
+// The band's field values are resolved once per RECORD by a separate thread-per-record kernel into a 64-byte blob;
+// a lane copies the blob into its cache when its cursor advances and re-reads nothing while consecutive sites fall
+// in the same band.
 #pragma once
 #include "glx_cell_general.cuh"
 
 namespace glxd {
 
-#define GLX_FAST_RV 8       // resolved values cached per lane
+#define GLX_FAST_RV 24      // resolved values cached per lane (shared memory column per lane)
 #define GLX_TILE_SITES 64   // sites walked by one CTA
 #define GLX_TILE_THREADS 128
-#define GLX_STAGE_MAX 32    // per-sample vector length up to which stores are transposed through shared memory
+
+// How a field's per-sample vector is produced for a finished cell:
+//   FM_VEC      BASIC-numbered field: `count` cached values
+//   FM_PATTERN  allele/genotype-numbered field: slot 0 = x0, slot 1 = x1, first slot of every later genotype row
+//               (0,a) = xr, everything else = xt  (4 cached values; covers [v0, default...] and the PL2 back-fill)
+//   FM_CONST    nothing liftable from a lone band (PLFieldHelper): the censored form
+enum { FM_VEC = 0, FM_PATTERN = 1, FM_CONST = 2 };
 
 struct FastPlan {
     uint8_t enabled, n_rv;
-    uint8_t rv0[GLX_MAX_FIELDS], nrv[GLX_MAX_FIELDS];
+    uint8_t mode[GLX_MAX_FIELDS], rv0[GLX_MAX_FIELDS], nrv[GLX_MAX_FIELDS];
+    uint8_t vec_rule[GLX_MAX_FIELDS];  // int field, not BASIC-numbered: an all-missing vector is [missing, vector_end, ...]
+    int32_t cen[GLX_MAX_FIELDS];       // value of a censored slot
 };
 
 inline FastPlan make_fast_plan(const DCfg& c) {
@@ -37,13 +46,24 @@ inline FastPlan make_fast_plan(const DCfg& c) {
     for (uint32_t k = 0; k < c.n_fields; k++) {
         const DFld& f = c.f[k];
         int need = 0;
+        const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
+        p.cen[k] = missing;
+        p.vec_rule[k] = f.type == GLX_TYPE_INT && f.number != GLX_NUM_BASIC;
         switch (f.kind) {
             case GLX_FK_NUMERIC:
-            case GLX_FK_DP: need = f.number == GLX_NUM_BASIC ? f.count : 1; break;
-            case GLX_FK_AD: need = 1; break;
-            case GLX_FK_PL: need = 0; break;
-            case GLX_FK_PL2: need = 3; break;
-            case GLX_FK_FT: need = 1; break;
+            case GLX_FK_DP:
+                if (f.number == GLX_NUM_BASIC) {
+                    p.mode[k] = FM_VEC;
+                    need = f.count;
+                } else {
+                    p.mode[k] = FM_PATTERN;
+                    need = 4;
+                }
+                break;
+            case GLX_FK_AD: p.mode[k] = FM_PATTERN; need = 4; break;
+            case GLX_FK_PL: p.mode[k] = FM_CONST; need = 0; break;
+            case GLX_FK_PL2: p.mode[k] = FM_PATTERN; need = 4; p.cen[k] = 0; p.vec_rule[k] = 0; break;
+            case GLX_FK_FT: p.mode[k] = FM_VEC; need = 1; p.cen[k] = 0; p.vec_rule[k] = 0; break;
             default: p.enabled = 0;
         }
         p.rv0[k] = (uint8_t)n;
@@ -68,47 +88,74 @@ __device__ __forceinline__ uint64_t first_candidate(const int32_t* __restrict__ 
     return lo;
 }
 
+// ---- resolved-record blobs --------------------------------------------------------------------------------
+// Everything a lane needs from a record to finish reference-band cells, resolved ONCE per record by
+// glx_resolve_records_kernel (thread per record) instead of once per (site, sample) cell as the reference does:
+//   [0] beg  [1] end  [2] running max end  [3] RB_* bits  [4] MIN_DP as min_ref_depth  [5] beg of the sample's next
+//   record (INT_MAX after the last)  [6..6+n_rv) the cached field values of the FastPlan.  16-byte aligned rows.
+#define GLX_BLOB_HDR 6
+inline __host__ __device__ uint32_t blob_words(uint32_t n_rv) { return (GLX_BLOB_HDR + n_rv + 3u) & ~3u; }
+
 struct LaneCursor {
     uint64_t base;  // first record of the lane's sample
     uint32_t n;     // records of the sample
     uint32_t c;     // first record (relative) with maxend > current qbeg
     int beg_c, end_c, maxend_c, beg_n;
+    uint32_t bits;  // RB_* of record c
+    int mrd;
 };
 
-__device__ __forceinline__ void cursor_load(const DRecs& R, LaneCursor& L) {
+// load record c's blob: header into registers, field values into the lane's cache column
+__device__ __forceinline__ void cursor_load(const int32_t* __restrict__ blobs, uint32_t W, uint32_t n_rv, LaneCursor& L, int32_t* rv, int rvs) {
     if (L.c < L.n) {
-        const uint64_t r = L.base + L.c;
-        L.beg_c = R.beg[r];
-        L.end_c = R.end[r];
-        L.maxend_c = R.maxend[r];
-        L.beg_n = (L.c + 1 < L.n) ? R.beg[r + 1] : 0x7fffffff;
+        const int4* b = reinterpret_cast<const int4*>(blobs + (L.base + L.c) * W);
+        const int4 h = b[0];
+        L.beg_c = h.x;
+        L.end_c = h.y;
+        L.maxend_c = h.z;
+        L.bits = (uint32_t)h.w;
+        const int4 g = b[1];
+        L.mrd = g.x;
+        L.beg_n = g.y;
+        if (n_rv > 0) rv[0] = g.z;
+        if (n_rv > 1) rv[(size_t)rvs] = g.w;
+        for (uint32_t q = 2; q * 4 < W; q++) {
+            const int4 v = b[q];
+            const uint32_t j = q * 4 - GLX_BLOB_HDR;
+            if (j < n_rv) rv[(size_t)j * rvs] = v.x;
+            if (j + 1 < n_rv) rv[(size_t)(j + 1) * rvs] = v.y;
+            if (j + 2 < n_rv) rv[(size_t)(j + 2) * rvs] = v.z;
+            if (j + 3 < n_rv) rv[(size_t)(j + 3) * rvs] = v.w;
+        }
     } else {
-        L.beg_c = L.beg_n = L.maxend_c = 0x7fffffff;
-        L.end_c = 0x7fffffff;
+        L.beg_c = L.beg_n = L.maxend_c = L.end_c = 0x7fffffff;
+        L.bits = 1;
+        L.mrd = -1;
     }
 }
 
-__device__ __forceinline__ void cursor_init(const DRecs& R, LaneCursor& L, uint32_t sample, int qbeg) {
+__device__ __forceinline__ void cursor_init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t W, uint32_t n_rv, LaneCursor& L, uint32_t sample, int qbeg,
+                                            int32_t* rv, int rvs) {
     L.base = R.ds_rec_off[sample];
     const uint64_t hi = R.ds_rec_off[sample + 1];
     L.n = (uint32_t)(hi - L.base);
     L.c = (uint32_t)(first_candidate(R.maxend, L.base, hi, qbeg) - L.base);
-    cursor_load(R, L);
+    cursor_load(blobs, W, n_rv, L, rv, rvs);
 }
 
 // `back`: this site's qbeg is smaller than the previous site's (query hulls are not monotone in general)
-__device__ __forceinline__ void cursor_seek(const DRecs& R, LaneCursor& L, int qbeg, bool back) {
+__device__ __forceinline__ void cursor_seek(const int32_t* __restrict__ blobs, uint32_t W, uint32_t n_rv, LaneCursor& L, int qbeg, bool back, int32_t* rv, int rvs) {
     if (back) {
         bool moved = false;
-        while (L.c > 0 && R.maxend[L.base + L.c - 1] > qbeg) {
+        while (L.c > 0 && blobs[(L.base + L.c - 1) * W + 2] > qbeg) {
             L.c--;
             moved = true;
         }
-        if (moved) cursor_load(R, L);
+        if (moved) cursor_load(blobs, W, n_rv, L, rv, rvs);
     }
     while (L.c < L.n && L.maxend_c <= qbeg) {
         L.c++;
-        cursor_load(R, L);
+        cursor_load(blobs, W, n_rv, L, rv, rvs);
     }
 }
 
@@ -164,7 +211,12 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
                 if (f.number == GLX_NUM_BASIC) {
                     for (int j = 0; j < f.count; j++) c[(size_t)j * rvs] = found ? v[j] : dflt;
                 } else {
-                    c[0] = (found && n_val > 0) ? v[0] : dflt;
+                    // allele map of a band is [0,-1]: only slot 0 receives a value; the rest take the default
+                    const int32_t x0 = found ? v[0] : dflt;
+                    c[0] = x0;
+                    c[(size_t)rvs] = (plan.vec_rule[k] && x0 == GLXD_INT_MISSING && dflt == GLXD_INT_MISSING) ? GLXD_INT_VEND : dflt;
+                    c[(size_t)2 * rvs] = dflt;
+                    c[(size_t)3 * rvs] = dflt;
                 }
                 break;
             }
@@ -186,9 +238,11 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
                         if (p2 == GLXD_INT_MISSING) p2 = 990;
                     }
                 }
+                // back-fill through the symbolic allele: (0,0) -> PL[0], (0,a) -> PL[1], (a,b) -> PL[2]
                 c[0] = p0;
                 c[(size_t)rvs] = p1;
-                c[(size_t)2 * rvs] = p2;
+                c[(size_t)2 * rvs] = p1;
+                c[(size_t)3 * rvs] = p2;
                 break;
             }
             case GLX_FK_FT: {
@@ -208,76 +262,72 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
     return bits;
 }
 
-struct FastCell {
-    int type;        // CT_*
-    int a0, a1;      // output GT allele indices (-1 missing)
-    int rnc0, rnc1;  // RNC_* codes
-};
-
-// Classify the lane's cell at a site and, unless CT_SLOW, decide GT / RNC. `resolved` caches which record rv[] holds.
-__device__ __forceinline__ FastCell fast_classify(const DCfg& cfg, const FastPlan& plan, const DRecs& R, LaneCursor& L, int sbeg, int send, int qbeg, int qend,
-                                                  bool slow_site, bool back, uint32_t& resolved, uint32_t& rbits, int& mrd, int32_t* rv, int rvs) {
-    FastCell out;
-    out.a0 = out.a1 = -1;
-    out.rnc0 = out.rnc1 = RNC_M;
-    out.type = CT_MISSING;
-    cursor_seek(R, L, qbeg, back);
-    if (slow_site) {
-        out.type = CT_SLOW;
-        return out;
-    }
-    if (L.c >= L.n || L.beg_c >= qend) return out;  // nothing overlaps the query range: MissingData
-    if (L.beg_n < qend) {                            // a second record may overlap it
-        out.type = CT_SLOW;
-        return out;
-    }
-    if (resolved != L.c) {
-        rbits = resolve_ref_band(cfg, plan, R, L.base + L.c, rv, rvs, mrd);
-        resolved = L.c;
-    }
-    if (rbits & RB_SLOW) {
-        out.type = CT_SLOW;
-        return out;
-    }
-    if (!(L.end_c > sbeg && L.beg_c < send)) return out;  // band only inside the unification hull: not kept
-    if (!cfg.allow_partial && !(L.beg_c <= sbeg && L.end_c >= send)) {
-        out.type = CT_PARTIAL;
-        out.rnc0 = out.rnc1 = RNC_P;
-        return out;
-    }
-    out.type = CT_REF;
-    if (rbits & RB_NONCALLED) {
-        out.rnc0 = out.rnc1 = RNC_I;
-    } else if ((unsigned long long)(long long)mrd >= (unsigned long long)cfg.required_dp) {
-        out.a0 = out.a1 = 0;
-        out.rnc0 = out.rnc1 = RNC_NA;
-    } else {
-        out.rnc0 = out.rnc1 = RNC_D;
-    }
-    return out;
+// one record -> its blob (thread per record in glx_resolve_records_kernel)
+__device__ inline void build_record_blob(const DCfg& cfg, const FastPlan& plan, const DRecs& R, uint64_t r, bool last_of_sample, int32_t* blob) {
+    const uint32_t W = blob_words(plan.n_rv);
+    for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
+    int mrd = -1;
+    const uint32_t bits = resolve_ref_band(cfg, plan, R, r, blob + GLX_BLOB_HDR, 1, mrd);
+    blob[0] = R.beg[r];
+    blob[1] = R.end[r];
+    blob[2] = R.maxend[r];
+    blob[3] = (int32_t)bits;
+    blob[4] = mrd;
+    blob[5] = last_of_sample ? 0x7fffffff : R.beg[r + 1];
 }
 
-// value of slot j = genotype (a,b), b <= a (or allele/basic index j) of field k for a finished fast cell
-__device__ __forceinline__ int32_t fast_value(const DFld& f, const FastPlan& plan, int k, int type, int count, int j, int a, int b, const int32_t* rv, int rvs) {
-    const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
-    const bool vec_rule = f.type == GLX_TYPE_INT && f.number != GLX_NUM_BASIC && count > 1;  // all-missing vector => [missing, vector_end]
-    if (type != CT_REF) {  // every field censored (MissingData / PartialData)
-        if (f.kind == GLX_FK_PL2 || f.kind == GLX_FK_FT) return 0;
-        return (vec_rule && j == 1) ? GLXD_INT_VEND : missing;
+// Classify the lane's cell at a site; unless CT_SLOW, decide GT / RNC: `called` = 0/0 (else ./.), rnc = RNC_* of both slots.
+__device__ __forceinline__ int fast_classify(const DCfg& cfg, const int32_t* __restrict__ blobs, uint32_t W, uint32_t n_rv, LaneCursor& L, int sbeg, int send,
+                                             int qbeg, int qend, bool slow_site, bool back, int32_t* rv, int rvs, bool& called, int& rnc) {
+    called = false;
+    rnc = RNC_M;
+    cursor_seek(blobs, W, n_rv, L, qbeg, back, rv, rvs);
+    if (slow_site) return CT_SLOW;
+    if (L.c >= L.n || L.beg_c >= qend) return CT_MISSING;  // nothing overlaps the query range
+    if (L.beg_n < qend) return CT_SLOW;                    // a second record may overlap it
+    if (L.bits & RB_SLOW) return CT_SLOW;
+    if (!(L.end_c > sbeg && L.beg_c < send)) return CT_MISSING;  // band only inside the unification hull: not kept
+    if (!cfg.allow_partial && !(L.beg_c <= sbeg && L.end_c >= send)) {
+        rnc = RNC_P;
+        return CT_PARTIAL;
     }
+    if (L.bits & RB_NONCALLED) rnc = RNC_I;
+    else if ((unsigned long long)(long long)L.mrd >= (unsigned long long)cfg.required_dp) {
+        called = true;
+        rnc = RNC_NA;
+    } else
+        rnc = RNC_D;
+    return CT_REF;
+}
+
+// write field k's vector of a finished cell (o = the cell's first slot)
+__device__ __forceinline__ void fast_emit_field(const FastPlan& plan, int k, bool ref, int count, int32_t* __restrict__ o, const int32_t* rv, int rvs) {
+    const int32_t cen = plan.cen[k];
+    const int mode = plan.mode[k];
     const int32_t* c = rv + (size_t)plan.rv0[k] * rvs;
-    switch (f.kind) {
-        case GLX_FK_PL2: return a == 0 ? c[0] : (b == 0 ? c[(size_t)rvs] : c[(size_t)2 * rvs]);
-        case GLX_FK_FT: return c[0];
-        case GLX_FK_PL: return (vec_rule && j == 1) ? GLXD_INT_VEND : GLXD_INT_MISSING;
-        default: break;
+    if (mode == FM_VEC) {
+        for (int j = 0; j < count; j++) o[j] = ref ? c[(size_t)j * rvs] : cen;
+        return;
     }
-    if (f.number == GLX_NUM_BASIC) return c[(size_t)j * rvs];
-    const int32_t dflt = f.default_zero ? 0 : missing;
-    const int32_t v0 = c[0];
-    if (j == 0) return v0;
-    if (vec_rule && j == 1 && v0 == GLXD_INT_MISSING && dflt == GLXD_INT_MISSING) return GLXD_INT_VEND;
-    return dflt;
+    int32_t x0 = cen, x1 = plan.vec_rule[k] ? GLXD_INT_VEND : cen, xr = cen, xt = cen;
+    if (ref && mode == FM_PATTERN) {
+        x0 = c[0];
+        x1 = c[(size_t)rvs];
+        xr = c[(size_t)2 * rvs];
+        xt = c[(size_t)3 * rvs];
+    }
+    o[0] = x0;
+    if (count > 1) o[1] = x1;
+    int next_row = 3, a = 2;  // slot of genotype (0,a)
+    for (int j = 2; j < count; j++) {
+        int32_t v = xt;
+        if (j == next_row) {
+            v = xr;
+            a++;
+            next_row += a;
+        }
+        o[j] = v;
+    }
 }
 
 }  // namespace glxd

@@ -23,29 +23,43 @@ using namespace glxd;
 // kernels
 // ---------------------------------------------------------------------------------------------
 
+// Thread per record: resolve each record into its blob (glx_cell_fast.cuh). Part of every glx_launch.
+__global__ void __launch_bounds__(256) glx_resolve_records_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets, int32_t* __restrict__ blobs) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R.n_records) return;
+    // last record of its sample? find the dataset whose range holds r
+    uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= r < ds_rec_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (R.ds_rec_off[mid] <= r) lo = mid;
+        else hi = mid;
+    }
+    build_record_blob(cfg, plan, R, r, r + 1 == R.ds_rec_off[lo + 1], blobs + r * blob_words(plan.n_rv));
+}
+
 // Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
-// a cursor into its sample's records and the resolved values of the band under the cursor (shared memory, column per
-// lane). Per site each lane classifies its cell (fast_classify); finished cells are written with warp-transposed,
-// fully coalesced stores; the rest are appended to the worklist of the general kernel.
+// a cursor into its sample's records and the resolved values of the band under the cursor (shared memory, one column
+// per lane). Per site each lane classifies its cell (fast_classify) and writes a finished cell's GT, RNC and lifted
+// vectors; consecutive lanes are consecutive samples, so every store instruction of a warp covers one contiguous
+// span of the sample-major output. Unfinished cells go to the worklist of the general kernel with their cursor.
 __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
-                                                                           uint32_t* __restrict__ worklist, uint32_t* __restrict__ n_work, uint32_t n_sample_blocks) {
+                                                                           const int32_t* __restrict__ blobs, uint2* __restrict__ worklist,
+                                                                           uint32_t* __restrict__ n_work, uint32_t n_sample_blocks) {
     __shared__ int s_beg[GLX_TILE_SITES], s_end[GLX_TILE_SITES], s_qbeg[GLX_TILE_SITES], s_qend[GLX_TILE_SITES];
     __shared__ uint8_t s_flags[GLX_TILE_SITES];  // bit0: general path only (monoallelic), bit1: qbeg below the previous site's
     __shared__ uint16_t s_cnt[GLX_MAX_FIELDS][GLX_TILE_SITES];
     __shared__ unsigned long long s_off[GLX_MAX_FIELDS][GLX_TILE_SITES];
     __shared__ uint32_t s_used[GLX_TILE_SITES], s_lost[GLX_TILE_SITES];
-    __shared__ int32_t s_rv[GLX_FAST_RV * GLX_TILE_THREADS];
-    __shared__ int32_t s_stage[GLX_TILE_THREADS / 32][32 * GLX_STAGE_MAX];
+    extern __shared__ int32_t s_rv[];  // [plan.n_rv][GLX_TILE_THREADS]
 
     const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
     const uint32_t site0 = tile * GLX_TILE_SITES;
     const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
     const uint32_t N = S.n_samples;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t sample = sb * GLX_TILE_THREADS + tid;
     const bool active = sample < N;
-    const uint32_t warp_sample0 = sb * GLX_TILE_THREADS + warp * 32;
-    const uint32_t nvalid = warp_sample0 >= N ? 0u : min(32u, N - warp_sample0);
+    const uint32_t n_fields = cfg.n_fields;
 
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         const uint32_t s = site0 + i;
@@ -57,33 +71,33 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
         s_flags[i] = (S.monoallelic[s] ? 1 : 0) | ((i > 0 && qb < S.qbeg[s - 1]) ? 2 : 0);
         s_used[i] = 0;
         s_lost[i] = 0;
-        for (uint32_t k = 0; k < cfg.n_fields; k++) {
+        for (uint32_t k = 0; k < n_fields; k++) {
             s_cnt[k][i] = S.fld_cnt[k][s];
             s_off[k][i] = S.fld_off[k][s];
         }
     }
     __syncthreads();
 
+    const uint32_t n_rv = plan.n_rv, W = blob_words(n_rv);
+    int32_t* rv = s_rv + tid;
     LaneCursor L;
     L.base = 0;
     L.n = L.c = 0;
     L.beg_c = L.end_c = L.maxend_c = L.beg_n = 0x7fffffff;
-    if (active) cursor_init(R, L, sample, s_qbeg[0]);
-    uint32_t resolved = 0xffffffffu, rbits = 0;
-    int mrd = -1;
-    int32_t* rv = s_rv + tid;
-    int32_t* stage = s_stage[warp];
+    L.bits = 1;
+    L.mrd = -1;
+    if (active) cursor_init(R, blobs, W, n_rv, L, sample, s_qbeg[0], rv, GLX_TILE_THREADS);
 
     for (uint32_t i = 0; i < nsite; i++) {
         const uint32_t s = site0 + i;
-        FastCell cell;
-        cell.type = CT_MISSING;
-        cell.a0 = cell.a1 = -1;
-        cell.rnc0 = cell.rnc1 = RNC_M;
-        if (active)
-            cell = fast_classify(cfg, plan, R, L, s_beg[i], s_end[i], s_qbeg[i], s_qend[i], s_flags[i] & 1, s_flags[i] & 2, resolved, rbits, mrd, rv,
-                                 GLX_TILE_THREADS);
-        const bool slow = active && cell.type == CT_SLOW;
+        int type = CT_MISSING, rnc = RNC_M;
+        bool called = false;
+        if (active) {
+            const uint32_t fl = s_flags[i];
+            type = fast_classify(cfg, blobs, W, n_rv, L, s_beg[i], s_end[i], s_qbeg[i], s_qend[i], fl & 1, fl & 2, rv, GLX_TILE_THREADS, called, rnc);
+        }
+        const bool slow = active && type == CT_SLOW;
+        const bool done = active && !slow;
         // ---- hand unfinished cells to the general kernel (warp-aggregated append) ----
         const uint32_t slow_mask = __ballot_sync(0xffffffffu, slow);
         if (slow_mask) {
@@ -91,54 +105,28 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
             const int leader = __ffs(slow_mask) - 1;
             if ((int)lane == leader) base = atomicAdd(n_work, (uint32_t)__popc(slow_mask));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (slow) worklist[base + __popc(slow_mask & ((1u << lane) - 1))] = s * N + sample;
+            if (slow) worklist[base + __popc(slow_mask & ((1u << lane) - 1))] = make_uint2(s * N + sample, L.c);
         }
-        // ---- GT / RNC ----
-        if (active && !slow) {
-            const size_t c2 = ((size_t)s * N + sample) * 2;
-            *reinterpret_cast<char2*>(O.gt + c2) = make_char2((signed char)cell.a0, (signed char)cell.a1);
-            *reinterpret_cast<uchar2*>(O.rnc + c2) = make_uchar2((unsigned char)kRncChar[cell.rnc0], (unsigned char)kRncChar[cell.rnc1]);
-        }
-        uint32_t used = 0;
-        if (active && !slow && cell.a0 >= 0) used = 1u;  // fast cells only ever call allele 0
-        used = __reduce_or_sync(0xffffffffu, used);
-        const bool lost = __any_sync(0xffffffffu, active && !slow && cell.rnc0 == RNC_I);
+        const uint32_t called_mask = __ballot_sync(0xffffffffu, done && called);
+        const uint32_t lost_mask = __ballot_sync(0xffffffffu, done && rnc == RNC_I);
         if (lane == 0) {
-            if (used) atomicOr(&s_used[i], used);
-            if (lost) atomicOr(&s_lost[i], 1u);
+            if (called_mask) atomicOr(&s_used[i], 1u);  // fast cells only ever call allele 0
+            if (lost_mask) atomicOr(&s_lost[i], 1u);
         }
+        if (!done) continue;
+        // ---- GT / RNC ----
+        const size_t cell = (size_t)s * N + sample;
+        const signed char a = called ? 0 : -1;
+        const unsigned char rc = (unsigned char)kRncChar[rnc];
+        reinterpret_cast<char2*>(O.gt)[cell] = make_char2(a, a);
+        reinterpret_cast<uchar2*>(O.rnc)[cell] = make_uchar2(rc, rc);
         // ---- lifted FORMAT fields ----
-        const int type = slow ? CT_MISSING : cell.type;  // placeholder values; the general kernel rewrites slow cells
-        for (uint32_t k = 0; k < cfg.n_fields; k++) {
-            const DFld& f = cfg.f[k];
-            const int count = s_cnt[k][i];
-            int32_t* out = O.fld[k] + s_off[k][i] + (unsigned long long)warp_sample0 * count;
-            if (count == 1) {
-                if (active) out[lane] = fast_value(f, plan, k, type, 1, 0, 0, 0, rv, GLX_TILE_THREADS);
-            } else if (count <= GLX_STAGE_MAX) {
-                if (active) {
-                    int a = 0, b = 0;
-                    for (int j = 0; j < count; j++) {
-                        stage[lane * count + j] = fast_value(f, plan, k, type, count, j, a, b, rv, GLX_TILE_THREADS);
-                        if (++b > a) {
-                            a++;
-                            b = 0;
-                        }
-                    }
-                }
-                __syncwarp();
-                const uint32_t total = nvalid * count;
-                for (uint32_t e = lane; e < total; e += 32) out[e] = stage[e];
-                __syncwarp();
-            } else if (active) {
-                int a = 0, b = 0;
-                for (int j = 0; j < count; j++) {
-                    out[(size_t)lane * count + j] = fast_value(f, plan, k, type, count, j, a, b, rv, GLX_TILE_THREADS);
-                    if (++b > a) {
-                        a++;
-                        b = 0;
-                    }
-                }
+        const bool ref = type == CT_REF;
+#pragma unroll
+        for (uint32_t k = 0; k < GLX_MAX_FIELDS; k++) {  // unrolled: plan/O indices become static (kernel-parameter constant bank)
+            if (k < n_fields) {
+                const int count = s_cnt[k][i];
+                fast_emit_field(plan, k, ref, count, O.fld[k] + s_off[k][i] + (unsigned long long)sample * count, rv, GLX_TILE_THREADS);
             }
         }
     }
@@ -153,8 +141,9 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     }
 }
 
-// General path: one thread per cell, taken from a worklist (or every cell of the batch when worklist == nullptr).
-__global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint32_t* __restrict__ worklist,
+// General path: one thread per cell, taken from the worklist of the tiled kernel (cell id + the lane's record cursor),
+// or every cell of the batch when worklist == nullptr (then the cursor is found by binary search).
+__global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint2* __restrict__ worklist,
                                                                 const uint32_t* __restrict__ n_work_ptr, uint64_t n_all, uint8_t* __restrict__ cnt_scratch,
                                                                 uint32_t max_slots) {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -163,10 +152,16 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
     const uint64_t n_items = worklist ? (uint64_t)*n_work_ptr : n_all;
     const uint32_t N = S.n_samples;
     for (uint64_t it = tid; it < n_items; it += stride) {
-        const uint64_t cell = worklist ? worklist[it] : it;
+        uint64_t cell = it;
+        uint32_t cur = 0;
+        if (worklist) {
+            const uint2 w = worklist[it];
+            cell = w.x;
+            cur = w.y;
+        }
         const uint32_t s = (uint32_t)(cell / N), sample = (uint32_t)(cell % N);
         const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
-        const uint64_t first = first_candidate(R.maxend, lo, hi, S.qbeg[s]);
+        const uint64_t first = worklist ? lo + cur : first_candidate(R.maxend, lo, hi, S.qbeg[s]);
         genotype_cell_general(cfg, R, S, O, s, sample, first, hi, cnt, stride);
     }
 }
@@ -272,10 +267,13 @@ struct glx_dev_batch {
     int launches_per_call = 0;
     bool force_general = false;
     FastPlan plan;
-    uint32_t* worklist = nullptr;  // [n_cells] cell ids for the general kernel
+    uint2* worklist = nullptr;     // [n_cells] (cell id, record cursor) for the general kernel
     uint32_t* n_work = nullptr;
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
+    int32_t* blobs = nullptr;  // [n_records][blob_words] resolved records
+    size_t blob_bytes = 0;
+    uint32_t n_datasets = 0;
 };
 
 extern "C" {
@@ -337,8 +335,10 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
         ctx->give(d->out_base, d->out_alloc);
         ctx->give(d->cnt_scratch, d->cnt_scratch_bytes);
         ctx->give(d->worklist, d->worklist_bytes);
+        ctx->give(d->blobs, d->blob_bytes);
     } else {
         if (d->worklist) cudaFree(d->worklist);
+        if (d->blobs) cudaFree(d->blobs);
         if (d->in_base) cudaFree(d->in_base);
         if (d->out_base) cudaFree(d->out_base);
         if (d->cnt_scratch) cudaFree(d->cnt_scratch);
@@ -516,14 +516,21 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     d->n_sample_blocks = (uint32_t)((N + GLX_TILE_THREADS - 1) / GLX_TILE_THREADS);
     d->n_site_tiles = (uint32_t)((S + GLX_TILE_SITES - 1) / GLX_TILE_SITES);
     if (d->plan.enabled && d->n_cells) {
-        d->worklist_bytes = (d->n_cells + 64) * 4;
+        d->worklist_bytes = (d->n_cells + 64) * 8;
         e = ctx->take((void**)&d->worklist, d->worklist_bytes);
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
             return cuda_fail(ctx, e, "cudaMalloc(worklist)");
         }
-        d->n_work = d->worklist + d->n_cells + 32;
+        d->n_work = reinterpret_cast<uint32_t*>(d->worklist + d->n_cells + 16);
+        d->blob_bytes = (Rn + 1) * blob_words(d->plan.n_rv) * 4;
+        e = ctx->take((void**)&d->blobs, d->blob_bytes);
+        if (e != cudaSuccess) {
+            glx_free_batch(ctx, d);
+            return cuda_fail(ctx, e, "cudaMalloc(record blobs)");
+        }
     }
+    d->n_datasets = (uint32_t)D;
     e = cudaStreamSynchronize(ctx->stream);  // caller's host arrays may be released after return
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
@@ -546,8 +553,13 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     if (tiled) CU(cudaMemsetAsync(d->n_work, 0, 4, st));
     if (d->profile) CU(cudaEventRecord(d->ev[0], st));
     if (tiled) {
-        glx_cells_tiled_kernel<<<d->n_sample_blocks * d->n_site_tiles, GLX_TILE_THREADS, 0, st>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work,
-                                                                                                d->n_sample_blocks);
+        if (d->R.n_records) {
+            glx_resolve_records_kernel<<<(unsigned)((d->R.n_records + 255) / 256), 256, 0, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs);
+            d->launches_per_call++;
+            CU(cudaGetLastError());
+        }
+        glx_cells_tiled_kernel<<<d->n_sample_blocks * d->n_site_tiles, GLX_TILE_THREADS, (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4, st>>>(
+            d->cfg, d->plan, d->R, d->S, d->O, d->blobs, d->worklist, d->n_work, d->n_sample_blocks);
         d->launches_per_call++;
         CU(cudaGetLastError());
     }

@@ -15,6 +15,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 
+struct int4 { int x, y, z, w; };
 struct char2 { signed char x, y; };
 struct uchar2 { unsigned char x, y; };
 inline char2 make_char2(signed char x, signed char y) { return char2{x, y}; }

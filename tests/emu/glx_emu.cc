@@ -83,42 +83,41 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
     }
     std::vector<uint8_t> cnt(max_slots);
     uint64_t n_slow = 0;
+    // glx_resolve_records_kernel: one blob per record
+    const uint32_t n_rv = plan.n_rv, W = blob_words(n_rv);
+    std::vector<int32_t> blobs((size_t)(R.n_records + 1) * W);
+    if (plan.enabled)
+        for (uint32_t d = 0; d < N; d++)
+            for (uint64_t r = R.ds_rec_off[d]; r < R.ds_rec_off[d + 1]; r++) build_record_blob(C, plan, R, r, r + 1 == R.ds_rec_off[d + 1], blobs.data() + r * W);
     for (uint32_t n = 0; n < N; n++) {
         for (uint32_t site0 = 0; site0 < Sn; site0 += GLX_TILE_SITES) {
             const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);
             LaneCursor L;
             int32_t rv[GLX_FAST_RV];
-            uint32_t resolved = 0xffffffffu, rbits = 0;
-            int mrd = -1;
-            if (plan.enabled) cursor_init(R, L, n, S.qbeg[site0]);
+            if (plan.enabled) cursor_init(R, blobs.data(), W, n_rv, L, n, S.qbeg[site0], rv, 1);
             for (uint32_t i = 0; i < nsite; i++) {
                 const uint32_t s = site0 + i;
-                FastCell cell;
-                cell.type = CT_SLOW;
+                int type = CT_SLOW, rnc = RNC_M;
+                bool called = false;
                 if (plan.enabled)
-                    cell = fast_classify(C, plan, R, L, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1],
-                                         resolved, rbits, mrd, rv, 1);
-                if (cell.type == CT_SLOW) {
+                    type = fast_classify(C, blobs.data(), W, n_rv, L, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0,
+                                         i > 0 && S.qbeg[s] < S.qbeg[s - 1], rv, 1, called, rnc);
+                if (type == CT_SLOW) {
                     n_slow++;
                     const uint64_t lo = R.ds_rec_off[n], hi = R.ds_rec_off[n + 1];
-                    genotype_cell_general(C, R, S, O, s, n, first_candidate(R.maxend, lo, hi, S.qbeg[s]), hi, cnt.data(), 1);
+                    // the kernel passes the lane's cursor instead of searching again
+                    const uint64_t first = plan.enabled ? lo + L.c : first_candidate(R.maxend, lo, hi, S.qbeg[s]);
+                    genotype_cell_general(C, R, S, O, s, n, first, hi, cnt.data(), 1);
                     continue;
                 }
                 const size_t c2 = ((size_t)s * N + n) * 2;
-                O.gt[c2] = (int8_t)cell.a0;
-                O.gt[c2 + 1] = (int8_t)cell.a1;
-                O.rnc[c2] = (uint8_t)kRncChar[cell.rnc0];
-                O.rnc[c2 + 1] = (uint8_t)kRncChar[cell.rnc1];
-                if (cell.a0 >= 0) O.allele_used[s] |= 1u;
-                if (cell.rnc0 == RNC_I) flags[s] |= 1;
+                O.gt[c2] = O.gt[c2 + 1] = called ? 0 : -1;
+                O.rnc[c2] = O.rnc[c2 + 1] = (uint8_t)kRncChar[rnc];
+                if (called) O.allele_used[s] |= 1u;
+                if (rnc == RNC_I) flags[s] |= 1;
                 for (uint32_t k = 0; k < C.n_fields; k++) {
                     const int count = S.fld_cnt[k][s];
-                    int32_t* o = O.fld[k] + S.fld_off[k][s] + (uint64_t)n * count;
-                    int a = 0, b = 0;
-                    for (int j = 0; j < count; j++) {
-                        o[j] = fast_value(C.f[k], plan, k, cell.type, count, j, a, b, rv, 1);
-                        if (++b > a) { a++; b = 0; }
-                    }
+                    fast_emit_field(plan, k, type == CT_REF, count, O.fld[k] + S.fld_off[k][s] + (uint64_t)n * count, rv, 1);
                 }
             }
         }
