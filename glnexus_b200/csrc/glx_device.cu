@@ -16,6 +16,7 @@
 #include "glx_cell_fast.cuh"
 #include "glx_cell_general.cuh"
 #include "glx_dev_types.cuh"
+#include "glx_tiled_sig.cuh"
 
 using namespace glxd;
 
@@ -34,7 +35,11 @@ __global__ void __launch_bounds__(256) glx_resolve_records_kernel(const DCfg cfg
         if (R.ds_rec_off[mid] <= r) lo = mid;
         else hi = mid;
     }
-    build_record_blob(cfg, plan, R, r, r + 1 == R.ds_rec_off[lo + 1], blobs + r * blob_words(plan.n_rv));
+    int32_t w[(GLX_BLOB_HDR + GLX_FAST_RV + 3) & ~3];
+    build_record_blob(cfg, plan, R, r, r + 1 == R.ds_rec_off[lo + 1], w);
+    const uint32_t W = blob_words(plan.n_rv);
+    int4* dst = reinterpret_cast<int4*>(blobs + r * W);
+    for (uint32_t q = 0; q < W / 4; q++) dst[q] = make_int4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
 // Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
@@ -271,6 +276,9 @@ struct glx_dev_batch {
     uint32_t* n_work = nullptr;
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
+    typedef void (*tiled_fn)(const DCfg, const FastPlan, const DRecs, const DSites, const DOut, const int32_t*, uint2*, uint32_t*, uint32_t);
+    tiled_fn tiled_kernel = nullptr;  // signature-specialised tiled kernel, or the dynamic one
+    size_t tiled_smem = 0;
     int32_t* blobs = nullptr;  // [n_records][blob_words] resolved records
     size_t blob_bytes = 0;
     uint32_t n_datasets = 0;
@@ -531,6 +539,23 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
         }
     }
     d->n_datasets = (uint32_t)D;
+    {
+        uint32_t nf;
+        uint64_t modes, nums, nrvs;
+        d->tiled_kernel = glx_cells_tiled_kernel;
+        d->tiled_smem = (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4;
+        const char* dyn = getenv("GLX_FORCE_DYNAMIC_TILED");
+        if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
+            auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
+            if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant>;
+                d->tiled_smem = 0;
+            } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk>;
+                d->tiled_smem = 0;
+            }
+        }
+    }
     e = cudaStreamSynchronize(ctx->stream);  // caller's host arrays may be released after return
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
@@ -558,8 +583,8 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             d->launches_per_call++;
             CU(cudaGetLastError());
         }
-        glx_cells_tiled_kernel<<<d->n_sample_blocks * d->n_site_tiles, GLX_TILE_THREADS, (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4, st>>>(
-            d->cfg, d->plan, d->R, d->S, d->O, d->blobs, d->worklist, d->n_work, d->n_sample_blocks);
+        d->tiled_kernel<<<d->n_sample_blocks * d->n_site_tiles, GLX_TILE_THREADS, d->tiled_smem, st>>>(d->cfg, d->plan, d->R, d->S, d->O, d->blobs, d->worklist,
+                                                                                                     d->n_work, d->n_sample_blocks);
         d->launches_per_call++;
         CU(cudaGetLastError());
     }

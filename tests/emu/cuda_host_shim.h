@@ -16,6 +16,11 @@
 #define __launch_bounds__(...)
 
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+struct uint2 { unsigned x, y; };
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct char2 { signed char x, y; };
 struct uchar2 { unsigned char x, y; };
 inline char2 make_char2(signed char x, signed char y) { return char2{x, y}; }

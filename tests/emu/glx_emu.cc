@@ -7,6 +7,7 @@
 
 #include "../../glnexus_b200/csrc/glx_cell_fast.cuh"
 #include "../../glnexus_b200/csrc/glx_cell_general.cuh"
+#include "../../glnexus_b200/csrc/glx_tiled_sig.cuh"
 
 using namespace glxd;
 
@@ -60,10 +61,41 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
     return code == 101 ? GLX_E_UNSUPPORTED : -code;
 }
 
+// signature-specialised lanes (glx_tiled_sig.cuh), lane by lane
+template <class Sig>
+static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, const DSites& S, const DOut& O, const int32_t* blobs, std::vector<uint8_t>& flags,
+                          std::vector<uint8_t>& cnt, uint64_t& n_slow) {
+    const uint32_t Sn = S.n_sites, N = S.n_samples;
+    for (uint32_t n = 0; n < N; n++) {
+        for (uint32_t site0 = 0; site0 < Sn; site0 += GLX_TILE_SITES) {
+            const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);
+            TiledLane<Sig> L;
+            L.init(R, blobs, n, S.qbeg[site0]);
+            for (uint32_t i = 0; i < nsite; i++) {
+                const uint32_t s = site0 + i;
+                int rnc = RNC_M;
+                bool called = false;
+                const int type = L.classify(C, blobs, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1], called, rnc);
+                if (type == CT_SLOW) {
+                    n_slow++;
+                    genotype_cell_general(C, R, S, O, s, n, R.ds_rec_off[n] + L.c, R.ds_rec_off[n + 1], cnt.data(), 1);
+                    continue;
+                }
+                const size_t c2 = ((size_t)s * N + n) * 2;
+                O.gt[c2] = O.gt[c2 + 1] = called ? 0 : -1;
+                O.rnc[c2] = O.rnc[c2 + 1] = (uint8_t)kRncChar[rnc];
+                if (called) O.allele_used[s] |= 1u;
+                if (rnc == RNC_I) flags[s] |= 1;
+                L.emit(plan, O, type == CT_REF, s, N, n, S.n_allele[s], [&](uint32_t k) { return (unsigned long long)S.fld_off[k][s]; });
+            }
+        }
+    }
+}
+
 // The tiled kernel's per-lane state machine run lane by lane: same tiles, same cursor walk, same classify /
 // resolve / value functions; cells it declines go through the general cell. (The warp-transposed stores and
 // the worklist hand-off are CUDA-only and are covered by the GPU tests.)
-extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out, uint64_t* n_slow_out) {
+extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out, uint64_t* n_slow_out, int dynamic_only) {
     if (recs->n_datasets != sites->n_samples) return GLX_E_UNSUPPORTED;
     for (uint32_t d = 0; d < recs->n_datasets; d++)
         if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) return GLX_E_UNSUPPORTED;
@@ -89,6 +121,28 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
     if (plan.enabled)
         for (uint32_t d = 0; d < N; d++)
             for (uint64_t r = R.ds_rec_off[d]; r < R.ds_rec_off[d + 1]; r++) build_record_blob(C, plan, R, r, r + 1 == R.ds_rec_off[d + 1], blobs.data() + r * W);
+    {
+        uint32_t nf;
+        uint64_t modes, nums, nrvs;
+        bool handled = false;
+        if (!dynamic_only && sig_of_plan(C, plan, nf, modes, nums, nrvs)) {  // same dispatch as glx_upload
+            auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
+            if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
+                run_tiled_sig<SigDeepVariant>(C, plan, R, S, O, blobs.data(), flags, cnt, n_slow);
+                handled = true;
+            } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
+                run_tiled_sig<SigGatk>(C, plan, R, S, O, blobs.data(), flags, cnt, n_slow);
+                handled = true;
+            }
+        }
+        if (handled) {
+            memcpy(out->site_flags, flags.data(), Sn);
+            if (n_slow_out) *n_slow_out = n_slow;
+            if (err == ~0ull) return GLX_OK;
+            const int code = (int)(err & 0xff);
+            return code == 101 ? GLX_E_UNSUPPORTED : -code;
+        }
+    }
     for (uint32_t n = 0; n < N; n++) {
         for (uint32_t site0 = 0; site0 < Sn; site0 += GLX_TILE_SITES) {
             const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);

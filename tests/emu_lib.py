@@ -29,7 +29,7 @@ def lib():
         vp = C.c_void_p
         L.glx_emu_general_batch.argtypes = [vp, vp, vp, vp]
         L.glx_emu_general_batch.restype = C.c_int
-        L.glx_emu_tiled_batch.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+        L.glx_emu_tiled_batch.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint64), C.c_int]
         L.glx_emu_tiled_batch.restype = C.c_int
         _lib = L
     return _lib
@@ -39,8 +39,8 @@ def general_batch(batch, out):
     return lib().glx_emu_general_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr)
 
 
-def tiled_batch(batch, out):
-    """Returns (status, number of cells the fast path declined)."""
+def tiled_batch(batch, out, dynamic_only=False):
+    """Returns (status, number of cells the fast path declined). dynamic_only skips the signature-specialised lanes."""
     n = C.c_uint64()
-    rc = lib().glx_emu_tiled_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr, C.byref(n))
+    rc = lib().glx_emu_tiled_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr, C.byref(n), 1 if dynamic_only else 0)
     return rc, n.value

@@ -16,11 +16,12 @@ def test_emu_general_synth(built, shape):
     assert emu_lib.general_batch(b, got) == 0
     d = compare_outs(got, ref, b.n_fields)
     assert not d, "\n".join(d)
-    got2 = b.alloc_out()
-    rc, n_slow = emu_lib.tiled_batch(b, got2)
-    assert rc == 0
-    d = compare_outs(got2, ref, b.n_fields)
-    assert not d, "tiled:\n" + "\n".join(d)
+    for dyn in (False, True):
+        got2 = b.alloc_out()
+        rc, n_slow = emu_lib.tiled_batch(b, got2, dynamic_only=dyn)
+        assert rc == 0
+        d = compare_outs(got2, ref, b.n_fields)
+        assert not d, f"tiled (dynamic_only={dyn}):\n" + "\n".join(d)
     assert n_slow < 0.5 * b.n_sites * b.n_samples  # the fast path takes the bulk of the cells
     rnc = set(ref.array("rnc").tobytes().decode())
     assert {".", "M"} <= rnc
@@ -37,10 +38,13 @@ def test_emu_general_presets(built, preset):
     except oracle_lib.OracleError as e:
         orc = e.code
     assert emu_lib.general_batch(b, got) == orc
-    got2 = b.alloc_out()
+    got2, got3 = b.alloc_out(), b.alloc_out()
     assert emu_lib.tiled_batch(b, got2)[0] == orc
+    assert emu_lib.tiled_batch(b, got3, dynamic_only=True)[0] == orc
     if orc == 0:
         d = compare_outs(got, ref, b.n_fields)
         assert not d, "\n".join(d)
         d = compare_outs(got2, ref, b.n_fields)
         assert not d, "tiled:\n" + "\n".join(d)
+        d = compare_outs(got3, ref, b.n_fields)
+        assert not d, "tiled dynamic:\n" + "\n".join(d)

@@ -47,13 +47,17 @@ def test_gpu_golden(ctx, name):
     ("c4", 2000, 1500, 96000),
     ("c5", 600, 2000, 60000),
 ])
-@pytest.mark.parametrize("force_general", [False, True])
-def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, force_general, monkeypatch):
-    """Tiled fast path + general worklist (default) and the general kernel alone must both equal the oracle."""
-    if force_general:
+@pytest.mark.parametrize("path", ["sig", "dynamic", "general"])
+def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, path, monkeypatch):
+    """Signature-specialised tiled kernel (default), the dynamic tiled kernel, and the general kernel alone must all
+    equal the oracle on every output column."""
+    monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
+    monkeypatch.delenv("GLX_FORCE_DYNAMIC_TILED", raising=False)
+    if path == "general":
         monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
-    else:
-        monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
+    elif path == "dynamic":
+        monkeypatch.setenv("GLX_FORCE_DYNAMIC_TILED", "1")
+    force_general = path == "general"
     b = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len)
     ref, got = b.alloc_out(), b.alloc_out(pinned=True)
     oracle_lib.genotype_batch(b, ref, threads=8)
@@ -61,7 +65,7 @@ def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, force_general, mo
     dev.launch()
     dev.check()
     dev.download(got)
-    assert dev.launch_count == (1 if force_general else 2)
+    assert dev.launch_count == (1 if force_general else 3)  # resolve + tiled + general
     dev.close()
     d = compare_outs(got, ref, b.n_fields)
     assert not d, "\n".join(d)
