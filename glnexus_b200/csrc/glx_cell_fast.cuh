@@ -23,6 +23,7 @@ namespace glxd {
 #define GLX_FAST_RV 24      // resolved values cached per lane (shared memory column per lane)
 #define GLX_TILE_SITES 64   // sites walked by one CTA
 #define GLX_TILE_THREADS 128
+#define GLX_WORK_SINGLE 0x80000000u  // worklist cursor flag: the query range holds exactly one record (not a monoallelic site)
 
 // How a field's per-sample vector is produced for a finished cell:
 //   FM_VEC      BASIC-numbered field: `count` cached values

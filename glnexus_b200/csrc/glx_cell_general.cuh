@@ -904,4 +904,231 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Closed form for the commonest non-band cell: the query range holds exactly ONE record and it is a variant
+// record whose alleles map to distinct unified alleles (site not monoallelic, squeeze off). Then all_records =
+// variant_records = {r}, each output slot receives at most one value, nothing is censored, and the cell is one pass
+// over the record with no count scratch. Same reference lines as genotype_cell_general. Returns false (nothing
+// written) when the cell is not of this shape.
+__device__ inline bool genotype_cell_single(const DCfg& cfg, const DRecs& R, const DSites& S, const DOut& O, uint32_t s, uint32_t sample, uint64_t r) {
+    if (cfg.squeeze) return false;
+    const SiteCtx st = load_site(S, s);
+    if (st.mono) return false;
+    const uint8_t flags = R.flags[r];
+    if (flags & GLX_RF_IS_REF) return false;
+    const int na = R.n_allele[r];
+    const int rbeg = R.beg[r], rend = R.end[r];
+    int8_t map[GLX_MAX_ALLELES];
+    uint32_t del_mask;
+    compute_allele_map(R, S, st, r, na, false, map, del_mask);
+    uint32_t seen = 1u;  // unified alleles already targeted (map[0] = 0)
+    bool any_mapped = false;
+    for (int i = 1; i < na; i++) {
+        if (map[i] < 0) continue;
+        any_mapped = true;
+        if (seen >> map[i] & 1) return false;  // two record alleles on one unified allele: slots would hold >1 value
+        seen |= 1u << map[i];
+    }
+    const uint32_t N = S.n_samples;
+    int rnc0 = RNC_M, rnc1 = RNC_M, al0 = 0, al1 = 0;
+    bool lift = false;
+    int g[2] = {0, 0};
+    int gq_value = 0;
+    bool gq_revised = false;
+    int err = 0;
+    const bool kept = (rend > st.beg && rbeg < st.end) || any_mapped;
+    if (!kept) {
+        // MissingData
+    } else if (!cfg.allow_partial && !(rbeg <= st.beg && rend >= st.end)) {
+        rnc0 = rnc1 = RNC_P;
+    } else {
+        lift = true;
+        if (flags & GLX_RF_NO_GT) err = 1;
+        decode_gt(R.gt[r], flags, g[0], g[1]);
+        if (!err && ((!gt_is_missing(g[0]) && (g[0] == GLXD_INT_VEND || gt_allele(g[0]) >= na)) || (!gt_is_missing(g[1]) && (g[1] == GLXD_INT_VEND || gt_allele(g[1]) >= na))))
+            err = 2;
+        if (!err && cfg.revise) err = revise_record(cfg, R, S, st, r, na, map, g[0], g[1], gq_value, gq_revised);
+        unsigned d0 = 0;
+        if (!err) err = depth_get(cfg, R, r, na, false, 0, d0);  // AlleleDepthHelper::Load
+        if (!err) {
+            const bool non00 = gt_is_missing(g[0]) || gt_allele(g[0]) != 0 || gt_is_missing(g[1]) || gt_allele(g[1]) != 0;
+            if (!non00) {
+                const int mrd = (int)d0;  // a 0/0 variant record only lowers min_ref_depth (genotyper.cc:396-426)
+                if ((unsigned long long)(long long)mrd >= (unsigned long long)cfg.required_dp) {
+                    al0 = al1 = gt_unphased(0);
+                    rnc0 = rnc1 = RNC_NA;
+                } else
+                    rnc0 = rnc1 = RNC_D;
+            } else {
+                for (int k = 0; k < 2; k++) {  // fill_allele, min_ref_depth = -1 (no reference records)
+                    int rnc = RNC_I, al = 0;
+                    if (!gt_is_missing(g[k])) {
+                        const int a = gt_allele(g[k]);
+                        unsigned d;
+                        depth_get(cfg, R, r, na, false, a, d);
+                        if (d >= cfg.required_dp) {
+                            if (map[a] >= 0) {
+                                al = gt_unphased(map[a]);
+                                rnc = RNC_NA;
+                            } else
+                                rnc = (del_mask >> a & 1) ? RNC_LOSTDEL : RNC_LOST;
+                        } else
+                            rnc = RNC_D;
+                    }
+                    if (k == 0) {
+                        al0 = al;
+                        rnc0 = rnc;
+                    } else {
+                        al1 = al;
+                        rnc1 = rnc;
+                    }
+                }
+            }
+        }
+    }
+    // ---- fields ----
+    for (uint32_t k = 0; k < cfg.n_fields && !err; k++) {
+        const DFld& f = cfg.f[k];
+        const int count = S.fld_cnt[k][s];
+        int32_t* out = O.fld[k] + S.fld_off[k][s] + (uint64_t)sample * count;
+        const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
+        const bool vec_rule = f.type == GLX_TYPE_INT && f.number != GLX_NUM_BASIC && count > 1;
+        if (!lift) {  // every field censored
+            const int32_t c = (f.kind == GLX_FK_PL2 || f.kind == GLX_FK_FT || f.kind == GLX_FK_STRING) ? 0 : missing;
+            for (int j = 0; j < count; j++) out[j] = c;
+            if (vec_rule && c == GLXD_INT_MISSING) out[1] = GLXD_INT_VEND;
+            continue;
+        }
+        if (f.kind == GLX_FK_STRING) {
+            err = 6;
+            break;
+        }
+        if (f.kind == GLX_FK_FT) {
+            const uint32_t m = R.filt[r];
+            const int nu = __popc(m);
+            int32_t v = 0;
+            if (nu == 0) v = 0;
+            else if (nu == 1 || f.combi == GLX_COMBI_SEMICOLON) v = (int32_t)m;
+            else if (f.combi == GLX_COMBI_MISSING) v = 0;
+            else err = 2;
+            out[0] = v;
+            continue;
+        }
+        if (f.kind == GLX_FK_PL2) {
+            for (int j = 0; j < count; j++) out[j] = GLXD_INT_MISSING;
+            bool sc = false;
+            err = pl2_add(cfg, R, r, na, flags, map, st.A, count, out, sc);
+            if (err) break;
+            bool zero = false, other = false;
+            for (int j = 0; j < count; j++) {
+                const int32_t v = out[j];
+                if (v == 0) zero = true;
+                else if (v != GLXD_INT_MISSING) other = true;
+            }
+            const bool censor = !(zero && other);
+            for (int j = 0; j < count; j++) {
+                if (censor) out[j] = 0;
+                else if (out[j] == GLXD_INT_MISSING) out[j] = 990;
+            }
+            continue;
+        }
+        // numeric kinds: locate the source column (first orig_name present; AD falls back to the reference depth)
+        int n_val = count;
+        if (f.number == GLX_NUM_BASIC) n_val = f.count;
+        else if (f.number == GLX_NUM_ALT) n_val = na - 1;
+        else if (f.number == GLX_NUM_ALLELES) n_val = na;
+        else n_val = (int)n_genotypes(na > 2 ? na : 2);
+        const int32_t* v = nullptr;
+        int32_t gqv;
+        bool found = false;
+        for (int ci = 0; ci < f.n_cols && !found && !err; ci++) {
+            int rv;
+            if (gq_revised && f.cols[ci] == cfg.col_gq) {
+                gqv = gq_value;
+                v = &gqv;
+                rv = 1;
+            } else
+                rv = col_get(R, f.cols[ci], r, v);
+            if (rv == -2) err = 2;
+            else if (rv >= 0) {
+                if (rv != n_val) err = 2;
+                found = true;
+            }
+        }
+        bool fallback = false;
+        if (!found && !err && f.kind == GLX_FK_AD) {
+            int rv;
+            if (gq_revised && cfg.col_ref_dp == cfg.col_gq) {
+                gqv = gq_value;
+                v = &gqv;
+                rv = 1;
+            } else
+                rv = col_get(R, cfg.col_ref_dp, r, v);
+            if (rv == -2) err = 2;
+            else if (rv >= 0) {
+                if (rv != 1) err = 2;
+                found = fallback = true;
+                n_val = 1;
+            }
+        }
+        if (err) break;
+        const int32_t dflt = f.kind == GLX_FK_PL ? GLXD_INT_MISSING : (f.default_zero ? 0 : missing);
+        for (int j = 0; j < count; j++) out[j] = dflt;
+        int zeroes = 0, nonzeroes = 0;
+        if (found) {
+            if (f.number == GLX_NUM_GENOTYPE && !fallback) {
+                int gi = 0;
+                for (int j = 0; j < na; j++)
+                    for (int i = 0; i <= j; i++, gi++) {
+                        const int m1 = map[i], m2 = map[j];
+                        if (m1 < 0 || m2 < 0) continue;
+                        const int o = alleles_gt(m1, m2);
+                        if (o >= count) continue;
+                        out[o] = v[gi];
+                        if (v[gi] == 0) zeroes++;
+                        else nonzeroes++;
+                    }
+            } else if (f.number == GLX_NUM_ALT || f.number == GLX_NUM_ALLELES) {
+                for (int j = 0; j < n_val; j++) {
+                    const int m = j < na ? map[j] : -1;
+                    if (m < 0 || m >= count) continue;
+                    out[m] = v[j];
+                }
+            } else {
+                for (int j = 0; j < n_val && j < count; j++) out[j] = v[j];
+            }
+        }
+        if (f.kind == GLX_FK_PL && (zeroes == 0 || (zeroes == 1 && nonzeroes == 0)))
+            for (int j = 0; j < count; j++) out[j] = GLXD_INT_MISSING;
+        if (vec_rule) {
+            bool all_missing = true;
+            for (int j = 0; j < count; j++)
+                if (out[j] != GLXD_INT_MISSING) all_missing = false;
+            if (all_missing) out[1] = GLXD_INT_VEND;
+        }
+    }
+    if (err) {
+        report_error(O, s, err);
+        return true;
+    }
+    if ((al0 != 0 && al1 == 0) || al0 > al1) {
+        int tmp = al0; al0 = al1; al1 = tmp;
+        tmp = rnc0; rnc0 = rnc1; rnc1 = tmp;
+    }
+    const int a0 = gt_is_missing(al0) ? -1 : gt_allele(al0), a1 = gt_is_missing(al1) ? -1 : gt_allele(al1);
+    const size_t cell = ((size_t)s * N + sample) * 2;
+    *reinterpret_cast<char2*>(O.gt + cell) = make_char2((signed char)a0, (signed char)a1);
+    *reinterpret_cast<uchar2*>(O.rnc + cell) = make_uchar2((unsigned char)kRncChar[rnc0], (unsigned char)kRncChar[rnc1]);
+    uint32_t used = 0;
+    if (a0 >= 0) used |= 1u << a0;
+    if (a1 >= 0) used |= 1u << a1;
+    if (used) atomicOr(O.allele_used + s, used);
+    auto lost = [](int x) { return !(x == RNC_NA || x == RNC_M || x == RNC_P || x == RNC_D || x == RNC_MONO); };
+    if (lost(rnc0) || lost(rnc1)) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(O.site_flags + s) & ~(uintptr_t)3);
+        atomicOr(w, 1u << (8 * (reinterpret_cast<uintptr_t>(O.site_flags + s) & 3)));
+    }
+    return true;
+}
+
 }  // namespace glxd

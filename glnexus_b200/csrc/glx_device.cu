@@ -55,10 +55,13 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     __shared__ uint16_t s_cnt[GLX_MAX_FIELDS][GLX_TILE_SITES];
     __shared__ unsigned long long s_off[GLX_MAX_FIELDS][GLX_TILE_SITES];
     __shared__ uint32_t s_used[GLX_TILE_SITES], s_lost[GLX_TILE_SITES];
+    __shared__ uint32_t s_nslow;  // cells this CTA handed to the general kernel (its worklist region is CTA-private)
     extern __shared__ int32_t s_rv[];  // [plan.n_rv][GLX_TILE_THREADS]
 
     const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
     const uint32_t site0 = tile * GLX_TILE_SITES;
+    uint2* __restrict__ my_work = worklist + (size_t)blockIdx.x * (GLX_TILE_SITES * GLX_TILE_THREADS);
+    if (threadIdx.x == 0) s_nslow = 0;
     const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
     const uint32_t N = S.n_samples;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -108,9 +111,10 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
         if (slow_mask) {
             uint32_t base = 0;
             const int leader = __ffs(slow_mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(n_work, (uint32_t)__popc(slow_mask));
+            if ((int)lane == leader) base = atomicAdd(&s_nslow, (uint32_t)__popc(slow_mask));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (slow) worklist[base + __popc(slow_mask & ((1u << lane) - 1))] = make_uint2(s * N + sample, L.c);
+            if (slow) my_work[base + __popc(slow_mask & ((1u << lane) - 1))] =
+                    make_uint2(s * N + sample, L.c | ((!(s_flags[i] & 1) && L.c < L.n && L.beg_c < s_qend[i] && L.beg_n >= s_qend[i]) ? GLX_WORK_SINGLE : 0u));
         }
         const uint32_t called_mask = __ballot_sync(0xffffffffu, done && called);
         const uint32_t lost_mask = __ballot_sync(0xffffffffu, done && rnc == RNC_I);
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
         }
     }
     __syncthreads();
+    if (tid == 0) n_work[blockIdx.x] = s_nslow;
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         if (s_used[i]) atomicOr(O.allele_used + site0 + i, s_used[i]);
         if (s_lost[i]) {
@@ -146,28 +151,35 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     }
 }
 
-// General path: one thread per cell, taken from the worklist of the tiled kernel (cell id + the lane's record cursor),
-// or every cell of the batch when worklist == nullptr (then the cursor is found by binary search).
+// General path: one thread per cell. With a worklist, block b serves the CTA-private regions b, b+gridDim.x, ... that
+// the tiled kernel filled (cell id + the lane's record cursor; region r holds n_work[r] entries); without one it
+// takes every cell of the batch and finds the cursor by binary search.
 __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint2* __restrict__ worklist,
-                                                                const uint32_t* __restrict__ n_work_ptr, uint64_t n_all, uint8_t* __restrict__ cnt_scratch,
-                                                                uint32_t max_slots) {
+                                                                const uint32_t* __restrict__ n_work, uint32_t n_regions, uint64_t n_all,
+                                                                uint8_t* __restrict__ cnt_scratch, uint32_t max_slots) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint8_t* cnt = cnt_scratch + tid;
-    const uint64_t n_items = worklist ? (uint64_t)*n_work_ptr : n_all;
     const uint32_t N = S.n_samples;
-    for (uint64_t it = tid; it < n_items; it += stride) {
-        uint64_t cell = it;
-        uint32_t cur = 0;
-        if (worklist) {
-            const uint2 w = worklist[it];
-            cell = w.x;
-            cur = w.y;
+    if (worklist) {
+        for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+            const uint32_t n_items = n_work[reg];
+            const uint2* __restrict__ w = worklist + (size_t)reg * (GLX_TILE_SITES * GLX_TILE_THREADS);
+            for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
+                const uint2 e = w[it];
+                const uint32_t s = e.x / N, sample = e.x % N;
+                const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
+                const uint64_t first = lo + (e.y & ~GLX_WORK_SINGLE);
+                if ((e.y & GLX_WORK_SINGLE) && genotype_cell_single(cfg, R, S, O, s, sample, first)) continue;
+                genotype_cell_general(cfg, R, S, O, s, sample, first, hi, cnt, stride);
+            }
         }
+        return;
+    }
+    for (uint64_t cell = tid; cell < n_all; cell += stride) {
         const uint32_t s = (uint32_t)(cell / N), sample = (uint32_t)(cell % N);
         const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
-        const uint64_t first = worklist ? lo + cur : first_candidate(R.maxend, lo, hi, S.qbeg[s]);
-        genotype_cell_general(cfg, R, S, O, s, sample, first, hi, cnt, stride);
+        genotype_cell_general(cfg, R, S, O, s, sample, first_candidate(R.maxend, lo, hi, S.qbeg[s]), hi, cnt, stride);
     }
 }
 
@@ -524,13 +536,14 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     d->n_sample_blocks = (uint32_t)((N + GLX_TILE_THREADS - 1) / GLX_TILE_THREADS);
     d->n_site_tiles = (uint32_t)((S + GLX_TILE_SITES - 1) / GLX_TILE_SITES);
     if (d->plan.enabled && d->n_cells) {
-        d->worklist_bytes = (d->n_cells + 64) * 8;
+        const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
+        d->worklist_bytes = n_regions * (GLX_TILE_SITES * GLX_TILE_THREADS) * 8 + (n_regions + 64) * 4;
         e = ctx->take((void**)&d->worklist, d->worklist_bytes);
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
             return cuda_fail(ctx, e, "cudaMalloc(worklist)");
         }
-        d->n_work = reinterpret_cast<uint32_t*>(d->worklist + d->n_cells + 16);
+        d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * (GLX_TILE_SITES * GLX_TILE_THREADS));
         d->blob_bytes = (Rn + 1) * blob_words(d->plan.n_rv) * 4;
         e = ctx->take((void**)&d->blobs, d->blob_bytes);
         if (e != cudaSuccess) {
@@ -575,7 +588,6 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     CU(cudaMemsetAsync(d->O.error, 0xff, 8, st));
     d->launches_per_call = 0;
     const bool tiled = d->plan.enabled && d->n_cells;
-    if (tiled) CU(cudaMemsetAsync(d->n_work, 0, 4, st));
     if (d->profile) CU(cudaEventRecord(d->ev[0], st));
     if (tiled) {
         if (d->R.n_records) {
@@ -590,8 +602,8 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     }
     if (d->profile) CU(cudaEventRecord(d->ev[1], st));
     if (d->n_cells) {
-        glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, tiled ? d->worklist : nullptr, d->n_work, d->n_cells, d->cnt_scratch,
-                                                                    d->max_slots);
+        glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, tiled ? d->worklist : nullptr, d->n_work,
+                                                                    d->n_sample_blocks * d->n_site_tiles, d->n_cells, d->cnt_scratch, d->max_slots);
         d->launches_per_call++;
         CU(cudaGetLastError());
     }

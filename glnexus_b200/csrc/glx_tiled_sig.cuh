@@ -49,47 +49,70 @@ struct TiledLane {
     int mrd;
     int32_t rv[Sig::NRV_ARR];
 
+    int32_t nx[Sig::W];  // blob of record c+1, fetched one advance ahead so that a cursor advance never waits on DRAM
+
+    __device__ __forceinline__ void fetch(const int32_t* __restrict__ blobs, uint32_t idx, int32_t (&w)[Sig::W]) const {
+        const int4* b = reinterpret_cast<const int4*>(blobs + (base + idx) * Sig::W);
+#pragma unroll
+        for (uint32_t q = 0; q < Sig::W / 4; q++) {
+            const int4 v = b[q];
+            w[4 * q] = v.x;
+            w[4 * q + 1] = v.y;
+            w[4 * q + 2] = v.z;
+            w[4 * q + 3] = v.w;
+        }
+    }
+    __device__ __forceinline__ void unpack(const int32_t (&w)[Sig::W]) {
+        beg_c = w[0];
+        end_c = w[1];
+        maxend_c = w[2];
+        bits = (uint32_t)w[3];
+        mrd = w[4];
+        beg_n = w[5];
+#pragma unroll
+        for (uint32_t j = 0; j < Sig::n_rv; j++) rv[j] = w[GLX_BLOB_HDR + j];
+    }
+    __device__ __forceinline__ void sentinel() {
+        beg_c = beg_n = maxend_c = end_c = 0x7fffffff;
+        bits = RB_SLOW;
+        mrd = -1;
+    }
+    // (re)load record c and start fetching c+1
     __device__ __forceinline__ void load(const int32_t* __restrict__ blobs) {
         if (c < n) {
-            const int4* b = reinterpret_cast<const int4*>(blobs + (base + c) * Sig::W);
             int32_t w[Sig::W];
-#pragma unroll
-            for (uint32_t q = 0; q < Sig::W / 4; q++) {
-                const int4 v = b[q];
-                w[4 * q] = v.x;
-                w[4 * q + 1] = v.y;
-                w[4 * q + 2] = v.z;
-                w[4 * q + 3] = v.w;
-            }
-            beg_c = w[0];
-            end_c = w[1];
-            maxend_c = w[2];
-            bits = (uint32_t)w[3];
-            mrd = w[4];
-            beg_n = w[5];
-#pragma unroll
-            for (uint32_t j = 0; j < Sig::n_rv; j++) rv[j] = w[GLX_BLOB_HDR + j];
-        } else {
-            beg_c = beg_n = maxend_c = end_c = 0x7fffffff;
-            bits = RB_SLOW;
-            mrd = -1;
-        }
+            fetch(blobs, c, w);
+            unpack(w);
+            if (c + 1 < n) fetch(blobs, c + 1, nx);
+        } else
+            sentinel();
+    }
+    // c -> c+1 out of the prefetched blob; start fetching the one after
+    __device__ __forceinline__ void advance(const int32_t* __restrict__ blobs) {
+        c++;
+        if (c < n) {
+            unpack(nx);
+            if (c + 1 < n) fetch(blobs, c + 1, nx);
+        } else
+            sentinel();
     }
     __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t sample, int qbeg) {
         base = R.ds_rec_off[sample];
         const uint64_t hi = R.ds_rec_off[sample + 1];
         n = (uint32_t)(hi - base);
         c = (uint32_t)(first_candidate(R.maxend, base, hi, qbeg) - base);
+#pragma unroll
+        for (uint32_t j = 0; j < Sig::W; j++) nx[j] = 0;
         load(blobs);
     }
     __device__ __forceinline__ void idle() {
         base = 0;
         n = c = 0;
-        beg_c = beg_n = maxend_c = end_c = 0x7fffffff;
-        bits = RB_SLOW;
-        mrd = -1;
+        sentinel();
 #pragma unroll
         for (uint32_t j = 0; j < Sig::NRV_ARR; j++) rv[j] = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < Sig::W; j++) nx[j] = 0;
     }
     __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int qbeg, bool back) {
         if (back) {
@@ -100,10 +123,7 @@ struct TiledLane {
             }
             if (moved) load(blobs);
         }
-        while (c < n && maxend_c <= qbeg) {
-            c++;
-            load(blobs);
-        }
+        while (c < n && maxend_c <= qbeg) advance(blobs);
     }
     // same decision table as fast_classify
     __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int sbeg, int send, int qbeg, int qend, bool slow_site, bool back,
@@ -200,9 +220,12 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
     __shared__ uint32_t s_meta[GLX_TILE_SITES];  // bits 0-7 n_allele, bit 8 general path only, bit 9 qbeg below the previous site's
     __shared__ unsigned long long s_off[Sig::nf ? Sig::nf : 1][GLX_TILE_SITES];
     __shared__ uint32_t s_used[GLX_TILE_SITES], s_lost[GLX_TILE_SITES];
+    __shared__ uint32_t s_nslow;  // cells this CTA handed to the general kernel (its worklist region is CTA-private)
 
     const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
     const uint32_t site0 = tile * GLX_TILE_SITES;
+    uint2* __restrict__ my_work = worklist + (size_t)blockIdx.x * (GLX_TILE_SITES * GLX_TILE_THREADS);
+    if (threadIdx.x == 0) s_nslow = 0;
     const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
     const uint32_t N = S.n_samples;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -239,9 +262,9 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
         if (slow_mask) {
             uint32_t wbase = 0;
             const int leader = __ffs(slow_mask) - 1;
-            if ((int)lane == leader) wbase = atomicAdd(n_work, (uint32_t)__popc(slow_mask));
+            if ((int)lane == leader) wbase = atomicAdd(&s_nslow, (uint32_t)__popc(slow_mask));
             wbase = __shfl_sync(0xffffffffu, wbase, leader);
-            if (slow) worklist[wbase + __popc(slow_mask & ((1u << lane) - 1))] = make_uint2(s * N + sample, L.c);
+            if (slow) my_work[wbase + __popc(slow_mask & ((1u << lane) - 1))] = make_uint2(s * N + sample, L.c | ((!(meta & 256u) && L.c < L.n && L.beg_c < pos.w && L.beg_n >= pos.w) ? GLX_WORK_SINGLE : 0u));
         }
         const uint32_t called_mask = __ballot_sync(0xffffffffu, done && called);
         const uint32_t lost_mask = __ballot_sync(0xffffffffu, done && rnc == RNC_I);
@@ -258,6 +281,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
         L.emit(plan, O, type == CT_REF, s, N, sample, meta & 255u, [&](uint32_t k) { return s_off[k][i]; });
     }
     __syncthreads();
+    if (tid == 0) n_work[blockIdx.x] = s_nslow;
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         if (s_used[i]) atomicOr(O.allele_used + site0 + i, s_used[i]);
         if (s_lost[i]) {

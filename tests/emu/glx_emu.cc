@@ -78,6 +78,8 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                 const int type = L.classify(C, blobs, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1], called, rnc);
                 if (type == CT_SLOW) {
                     n_slow++;
+                    const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
+                    if (single && genotype_cell_single(C, R, S, O, s, n, R.ds_rec_off[n] + L.c)) continue;
                     genotype_cell_general(C, R, S, O, s, n, R.ds_rec_off[n] + L.c, R.ds_rec_off[n + 1], cnt.data(), 1);
                     continue;
                 }
@@ -161,6 +163,8 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
                     const uint64_t lo = R.ds_rec_off[n], hi = R.ds_rec_off[n + 1];
                     // the kernel passes the lane's cursor instead of searching again
                     const uint64_t first = plan.enabled ? lo + L.c : first_candidate(R.maxend, lo, hi, S.qbeg[s]);
+                    const bool single = plan.enabled && !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
+                    if (single && genotype_cell_single(C, R, S, O, s, n, first)) continue;
                     genotype_cell_general(C, R, S, O, s, n, first, hi, cnt.data(), 1);
                     continue;
                 }
