@@ -49,88 +49,90 @@ struct TiledLane {
     int mrd;
     int32_t rv[Sig::NRV_ARR];
 
-    int32_t nx[Sig::W];  // blob of record c+1, fetched one advance ahead so that a cursor advance never waits on DRAM
+    // The lane's next records are staged in a private shared-memory ring by asynchronous copies (cp.async, no register
+    // staging): records c .. c+RING-1 are always in flight or landed, so a cursor advance reads shared memory and
+    // never waits on HBM, even when a 1-bp variant record makes a lane advance on consecutive sites.
+    static constexpr uint32_t RING = 4, Q = Sig::W / 4;  // ring depth (records), 16-byte chunks per blob
 
-    __device__ __forceinline__ void fetch(const int32_t* __restrict__ blobs, uint32_t idx, int32_t (&w)[Sig::W]) const {
-        const int4* b = reinterpret_cast<const int4*>(blobs + (base + idx) * Sig::W);
+    __device__ __forceinline__ void request(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, uint32_t idx) const {
+        if (idx < n) {
+            const int4* src = reinterpret_cast<const int4*>(blobs + (base + idx) * Sig::W);
 #pragma unroll
-        for (uint32_t q = 0; q < Sig::W / 4; q++) {
-            const int4 v = b[q];
-            w[4 * q] = v.x;
-            w[4 * q + 1] = v.y;
-            w[4 * q + 2] = v.z;
-            w[4 * q + 3] = v.w;
+            for (uint32_t q = 0; q < Q; q++) cp_async16(ring + (size_t)((idx & (RING - 1)) * Q + q) * rs, src + q);
+        }
+        cp_async_commit();  // one group per record index, empty past the end, so group counting stays uniform
+    }
+    __device__ __forceinline__ void consume(const int4* ring, uint32_t rs) {
+        if (c < n) {
+            cp_async_wait_but<RING - 1>();
+            int32_t w[Sig::W];
+#pragma unroll
+            for (uint32_t q = 0; q < Q; q++) {
+                const int4 v = ring[(size_t)((c & (RING - 1)) * Q + q) * rs];
+                w[4 * q] = v.x;
+                w[4 * q + 1] = v.y;
+                w[4 * q + 2] = v.z;
+                w[4 * q + 3] = v.w;
+            }
+            beg_c = w[0];
+            end_c = w[1];
+            maxend_c = w[2];
+            bits = (uint32_t)w[3];
+            mrd = w[4];
+            beg_n = w[5];
+#pragma unroll
+            for (uint32_t j = 0; j < Sig::n_rv; j++) rv[j] = w[GLX_BLOB_HDR + j];
+        } else {
+            beg_c = beg_n = maxend_c = end_c = 0x7fffffff;
+            bits = RB_SLOW;
+            mrd = -1;
         }
     }
-    __device__ __forceinline__ void unpack(const int32_t (&w)[Sig::W]) {
-        beg_c = w[0];
-        end_c = w[1];
-        maxend_c = w[2];
-        bits = (uint32_t)w[3];
-        mrd = w[4];
-        beg_n = w[5];
+    // (re)start the ring at record c
+    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs) {
+        cp_async_wait_but<0>();
 #pragma unroll
-        for (uint32_t j = 0; j < Sig::n_rv; j++) rv[j] = w[GLX_BLOB_HDR + j];
+        for (uint32_t d = 0; d < RING; d++) request(blobs, ring, rs, c + d);
+        consume(ring, rs);
     }
-    __device__ __forceinline__ void sentinel() {
-        beg_c = beg_n = maxend_c = end_c = 0x7fffffff;
-        bits = RB_SLOW;
-        mrd = -1;
-    }
-    // (re)load record c and start fetching c+1
-    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs) {
-        if (c < n) {
-            int32_t w[Sig::W];
-            fetch(blobs, c, w);
-            unpack(w);
-            if (c + 1 < n) fetch(blobs, c + 1, nx);
-        } else
-            sentinel();
-    }
-    // c -> c+1 out of the prefetched blob; start fetching the one after
-    __device__ __forceinline__ void advance(const int32_t* __restrict__ blobs) {
+    __device__ __forceinline__ void advance(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs) {
         c++;
-        if (c < n) {
-            unpack(nx);
-            if (c + 1 < n) fetch(blobs, c + 1, nx);
-        } else
-            sentinel();
+        request(blobs, ring, rs, c + RING - 1);
+        consume(ring, rs);
     }
-    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t sample, int qbeg) {
+    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, uint32_t sample, int qbeg) {
         base = R.ds_rec_off[sample];
         const uint64_t hi = R.ds_rec_off[sample + 1];
         n = (uint32_t)(hi - base);
         c = (uint32_t)(first_candidate(R.maxend, base, hi, qbeg) - base);
-#pragma unroll
-        for (uint32_t j = 0; j < Sig::W; j++) nx[j] = 0;
-        load(blobs);
+        load(blobs, ring, rs);
     }
     __device__ __forceinline__ void idle() {
         base = 0;
         n = c = 0;
-        sentinel();
+        beg_c = beg_n = maxend_c = end_c = 0x7fffffff;
+        bits = RB_SLOW;
+        mrd = -1;
 #pragma unroll
         for (uint32_t j = 0; j < Sig::NRV_ARR; j++) rv[j] = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < Sig::W; j++) nx[j] = 0;
     }
-    __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int qbeg, bool back) {
+    __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, int qbeg, bool back) {
         if (back) {
             bool moved = false;
             while (c > 0 && blobs[(base + c - 1) * Sig::W + 2] > qbeg) {
                 c--;
                 moved = true;
             }
-            if (moved) load(blobs);
+            if (moved) load(blobs, ring, rs);
         }
-        while (c < n && maxend_c <= qbeg) advance(blobs);
+        while (c < n && maxend_c <= qbeg) advance(blobs, ring, rs);
     }
     // same decision table as fast_classify
-    __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int sbeg, int send, int qbeg, int qend, bool slow_site, bool back,
-                                            bool& called, int& rnc) {
+    __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, int sbeg, int send, int qbeg, int qend,
+                                            bool slow_site, bool back, bool& called, int& rnc) {
         called = false;
         rnc = RNC_M;
-        seek(blobs, qbeg, back);
+        seek(blobs, ring, rs, qbeg, back);
         if (slow_site) return CT_SLOW;
         if (c >= n || beg_c >= qend) return CT_MISSING;
         if (beg_n < qend) return CT_SLOW;
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
     __shared__ unsigned long long s_off[Sig::nf ? Sig::nf : 1][GLX_TILE_SITES];
     __shared__ uint32_t s_used[GLX_TILE_SITES], s_lost[GLX_TILE_SITES];
     __shared__ uint32_t s_nslow;  // cells this CTA handed to the general kernel (its worklist region is CTA-private)
+    __shared__ int4 s_ring[TiledLane<Sig>::RING * TiledLane<Sig>::Q * GLX_TILE_THREADS];  // per-lane record ring, chunk-major
 
     const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
     const uint32_t site0 = tile * GLX_TILE_SITES;
@@ -246,7 +249,8 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
     __syncthreads();
 
     TiledLane<Sig> L;
-    if (active) L.init(R, blobs, sample, s_pos[0].z);
+    int4* ring = s_ring + tid;
+    if (active) L.init(R, blobs, ring, GLX_TILE_THREADS, sample, s_pos[0].z);
     else L.idle();
 
     for (uint32_t i = 0; i < nsite; i++) {
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
         const uint32_t meta = s_meta[i];
         int type = CT_MISSING, rnc = RNC_M;
         bool called = false;
-        if (active) type = L.classify(cfg, blobs, pos.x, pos.y, pos.z, pos.w, meta & 256u, meta & 512u, called, rnc);
+        if (active) type = L.classify(cfg, blobs, ring, GLX_TILE_THREADS, pos.x, pos.y, pos.z, pos.w, meta & 256u, meta & 512u, called, rnc);
         const bool slow = active && type == CT_SLOW;
         const bool done = active && !slow;
         const uint32_t slow_mask = __ballot_sync(0xffffffffu, slow);

@@ -70,12 +70,14 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
         for (uint32_t site0 = 0; site0 < Sn; site0 += GLX_TILE_SITES) {
             const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);
             TiledLane<Sig> L;
-            L.init(R, blobs, n, S.qbeg[site0]);
+            int4 ring[TiledLane<Sig>::RING * TiledLane<Sig>::Q];
+            L.init(R, blobs, ring, 1, n, S.qbeg[site0]);
             for (uint32_t i = 0; i < nsite; i++) {
                 const uint32_t s = site0 + i;
                 int rnc = RNC_M;
                 bool called = false;
-                const int type = L.classify(C, blobs, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1], called, rnc);
+                const int type =
+                    L.classify(C, blobs, ring, 1, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1], called, rnc);
                 if (type == CT_SLOW) {
                     n_slow++;
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
