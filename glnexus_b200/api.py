@@ -50,6 +50,10 @@ def lib():
     L.glxh_batch_from_text.restype = C.c_int
     L.glxh_synth_batch.argtypes = [cp, C.POINTER(SynthParams), C.POINTER(vp), cp, sz]
     L.glxh_synth_batch.restype = C.c_int
+    L.glxh_partition_sites.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32)]
+    L.glxh_partition_sites.restype = C.c_int
+    L.glxh_batch_slice.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), cp, sz]
+    L.glxh_batch_slice.restype = C.c_int
     L.glxh_batch_free.argtypes = [vp]
     L.glxh_batch_free.restype = None
     for fn in ("glxh_config", "glxh_records", "glxh_sites"):
@@ -201,6 +205,23 @@ class Batch:
         if rc != GLX_OK:
             raise GlxError(rc, err.value.decode(errors="replace"))
         return cls(h)
+
+    def partition(self, n_parts):
+        """Cut points (n_parts+1) of contiguous site ranges of equal output weight, one range per GPU."""
+        b = (C.c_uint32 * (n_parts + 1))()
+        rc = lib().glxh_partition_sites(self.handle, n_parts, b)
+        if rc != GLX_OK:
+            raise GlxError(rc, "glxh_partition_sites")
+        return list(b)
+
+    def slice(self, site_lo, site_hi):
+        """The shard [site_lo, site_hi): those sites plus every record they can touch."""
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = lib().glxh_batch_slice(self.handle, site_lo, site_hi, C.byref(h), err, len(err))
+        if rc != GLX_OK:
+            raise GlxError(rc, err.value.decode(errors="replace"))
+        return Batch(h)
 
     @property
     def device_supported(self):

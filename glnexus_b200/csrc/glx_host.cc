@@ -1083,4 +1083,111 @@ Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& 
     return Status::OK();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range sharding: sites are independent, so a batch is cut into contiguous site ranges, one per
+// GPU; each shard carries every record overlapping its sites' query hull (records straddling a cut are replicated,
+// like the reference's bucket "danglers", src/BCFKeyValueData.cc:815-827). No collective; outputs concatenate in order.
+// ---------------------------------------------------------------------------------------------
+void partition_sites(const PackedBatch& b, int n_parts, std::vector<uint32_t>& bounds) {
+    const uint32_t S = b.sites.n_sites;
+    bounds.assign(n_parts + 1, S);
+    bounds[0] = 0;
+    std::vector<double> w(S + 1, 0.0);  // prefix of output bytes per site: N * (4 + 4 * values per sample)
+    for (uint32_t s = 0; s < S; s++) {
+        double vals = 1.0;
+        for (uint32_t k = 0; k < b.cfg.n_fields; k++) vals += b.fld_cnt[k][s];
+        w[s + 1] = w[s] + vals;
+    }
+    for (int p = 1; p < n_parts; p++) {
+        const double target = w[S] * p / n_parts;
+        bounds[p] = (uint32_t)(std::lower_bound(w.begin(), w.end(), target) - w.begin());
+        if (bounds[p] < bounds[p - 1]) bounds[p] = bounds[p - 1];
+        if (bounds[p] > S) bounds[p] = S;
+    }
+}
+
+Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, PackedBatch& o) {
+    if (site_lo > site_hi || site_hi > b.sites.n_sites) return Status::Invalid("slice_batch: bad site range");
+    Status s;
+    std::vector<unified_site> sub(b.usites.begin() + site_lo, b.usites.begin() + site_hi);
+    GLX_S(pack_sites(b.gcfg, sub, b.sites.n_samples, o));
+    o.sample_names = b.sample_names;
+    o.contigs = b.contigs;
+    o.filter_names = b.filter_names;
+    int qmin = INT32_MAX, qmax = INT32_MIN;
+    for (uint32_t i = site_lo; i < site_hi; i++) {
+        qmin = std::min(qmin, b.s_qbeg[i]);
+        qmax = std::max(qmax, b.s_qend[i]);
+    }
+    const uint32_t D = b.recs.n_datasets, C = b.cfg.n_cols;
+    const uint64_t R = b.recs.n_records;
+    o.ds_n_sample = b.ds_n_sample;
+    o.ds_sample_off = b.ds_sample_off;
+    o.sample_out = b.sample_out;
+    o.ds_rec_off.assign(1, 0);
+    std::vector<std::pair<uint64_t, uint64_t>> spans(D);
+    uint64_t Rn = 0;
+    for (uint32_t d = 0; d < D; d++) {
+        const uint64_t lo = b.ds_rec_off[d], hi = b.ds_rec_off[d + 1];
+        uint64_t first = hi, last = hi;
+        if (site_lo < site_hi) {
+            first = std::upper_bound(b.r_maxend.begin() + lo, b.r_maxend.begin() + hi, qmin) - b.r_maxend.begin();
+            last = first;
+            while (last < hi && b.r_beg[last] < qmax) last++;
+        }
+        spans[d] = {first, last};
+        Rn += last - first;
+        o.ds_rec_off.push_back(Rn);
+    }
+    o.col_val.assign((size_t)C * Rn, 0);
+    o.col_len.assign((size_t)C * Rn, GLX_LEN_ABSENT);
+    uint64_t rn = 0;
+    for (uint32_t d = 0; d < D; d++) {
+        const uint32_t ns = b.ds_n_sample[d];
+        int32_t maxend = INT32_MIN;
+        for (uint64_t r = spans[d].first; r < spans[d].second; r++, rn++) {
+            maxend = std::max(maxend, b.r_end[r]);
+            o.r_beg.push_back(b.r_beg[r]);
+            o.r_end.push_back(b.r_end[r]);
+            o.r_maxend.push_back(maxend);
+            o.r_qual.push_back(b.r_qual[r]);
+            o.r_n_allele.push_back(b.r_n_allele[r]);
+            o.r_flags.push_back(b.r_flags[r]);
+            o.r_filt.push_back(b.r_filt[r]);
+            if (ns == 1 || (b.r_flags[r] & GLX_RF_NO_GT)) o.r_gt.push_back(b.r_gt[r]);
+            else {
+                o.r_gt.push_back((uint32_t)o.gt_pool.size());
+                o.gt_pool.insert(o.gt_pool.end(), b.gt_pool.begin() + b.r_gt[r], b.gt_pool.begin() + b.r_gt[r] + 2 * ns);
+            }
+            o.r_allele_off.push_back((uint32_t)o.al_len.size());
+            if (!(b.r_flags[r] & GLX_RF_IS_REF)) {
+                for (uint32_t a = b.r_allele_off[r]; a < b.r_allele_off[r] + b.r_n_allele[r]; a++) {
+                    o.al_len.push_back(b.al_len[a]);
+                    o.al_flags.push_back(b.al_flags[a]);
+                    o.al_prefix.push_back(b.al_prefix[a]);
+                    o.al_str.push_back((uint32_t)o.al_pool.size());
+                    o.al_pool.insert(o.al_pool.end(), b.al_pool.begin() + b.al_str[a], b.al_pool.begin() + b.al_str[a] + b.al_len[a]);
+                }
+            }
+            for (uint32_t c = 0; c < C; c++) {
+                const uint16_t len = b.col_len[(size_t)c * R + r];
+                const int32_t val = b.col_val[(size_t)c * R + r];
+                o.col_len[(size_t)c * Rn + rn] = len;
+                if (len >= 0xFFF0) continue;
+                if (ns == 1 && len == 1) o.col_val[(size_t)c * Rn + rn] = val;
+                else {
+                    o.col_val[(size_t)c * Rn + rn] = (int32_t)o.pool.size();
+                    o.pool.insert(o.pool.end(), b.pool.begin() + val, b.pool.begin() + val + (size_t)ns * len);
+                }
+            }
+        }
+    }
+    o.recs.n_datasets = D;
+    o.recs.n_samples_out = b.recs.n_samples_out;
+    o.recs.n_cols = C;
+    o.recs.n_records = Rn;
+    o.rebind();
+    return Status::OK();
+}
+
 }  // namespace glx

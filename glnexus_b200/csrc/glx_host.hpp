@@ -253,6 +253,11 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
 // src/service.cc:190-241, written as VCF text (htslib vcf_format value semantics).
 Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& vcf_text);
 
+// Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
+// [site_lo, site_hi) with every record its sites can touch.
+void partition_sites(const PackedBatch& b, int n_parts, std::vector<uint32_t>& bounds);
+Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, PackedBatch& ans);
+
 }  // namespace glx
 
 // opaque handle of include/glx_host.h

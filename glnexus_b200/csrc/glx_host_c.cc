@@ -109,6 +109,26 @@ int glxh_batch_from_text(const char* preset, const char* config_text, const char
     return GLX_OK;
 }
 
+int glxh_partition_sites(const glxh_batch* b, int n_parts, uint32_t* bounds) {
+    if (!b || n_parts < 1 || !bounds) return GLX_E_INVALID;
+    std::vector<uint32_t> v;
+    glx::partition_sites(b->b, n_parts, v);
+    for (int i = 0; i <= n_parts; i++) bounds[i] = v[i];
+    return GLX_OK;
+}
+
+int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, glxh_batch** ans, char* err, size_t errlen) {
+    if (!b || !ans) return GLX_E_INVALID;
+    auto* o = new glxh_batch();
+    glx::Status s = glx::slice_batch(b->b, site_lo, site_hi, o->b);
+    if (s.bad()) {
+        delete o;
+        return fail(s, err, errlen);
+    }
+    *ans = o;
+    return GLX_OK;
+}
+
 void glxh_batch_free(glxh_batch* b) { delete b; }
 const glx_config* glxh_config(const glxh_batch* b) { return &b->b.cfg; }
 const glx_records* glxh_records(const glxh_batch* b) { return &b->b.recs; }

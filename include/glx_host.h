@@ -27,6 +27,12 @@ typedef struct glxh_out glxh_out;
 int glxh_batch_from_text(const char* preset, const char* config_text, const char* sites_text, int n_datasets,
                          const char* const* dataset_names, const char* const* vcf_texts, const char* contig,
                          int test_ingest_rules, glxh_batch** ans, char* err, size_t errlen);
+/* Multi-GPU: sites shard by contiguous range with no collective (they are independent; AF priors are inputs).
+ * glxh_partition_sites writes n_parts+1 cut points of equal output weight; glxh_batch_slice builds the shard
+ * [site_lo, site_hi) with every record its sites' query hulls can touch (records straddling a cut are replicated).
+ * The shards' output columns concatenate, in order, to the unsharded batch's. */
+int glxh_partition_sites(const glxh_batch* b, int n_parts, uint32_t* bounds);
+int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, glxh_batch** ans, char* err, size_t errlen);
 void glxh_batch_free(glxh_batch* b);
 const glx_config* glxh_config(const glxh_batch* b);
 const glx_records* glxh_records(const glxh_batch* b);
