@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libglx.so")
+LIB_PATH = os.environ.get("GLX_LIB_PATH") or os.path.join(_HERE, "libglx.so")  # override: profiling builds of the same sources
 
 GLX_OK = 0
 STATUS_NAMES = {0: "OK", -1: "Failure", -2: "Invalid", -3: "NotFound", -4: "Exists", -5: "IOError",

@@ -23,6 +23,7 @@ namespace glxd {
 #define GLX_FAST_RV 24      // resolved values cached per lane (shared memory column per lane)
 #define GLX_TILE_SITES 64   // sites walked by one CTA
 #define GLX_TILE_THREADS 128
+#define GLX_STAGE_MAX 8      // per-sample vectors of 3..8 ints are transposed through shared memory before being stored
 #define GLX_WORK_SINGLE 0x80000000u  // worklist cursor flag: the query range holds exactly one record (not a monoallelic site)
 
 // How a field's per-sample vector is produced for a finished cell:
@@ -148,12 +149,12 @@ __device__ __forceinline__ void cursor_load(const int32_t* __restrict__ blobs, u
     }
 }
 
-__device__ __forceinline__ void cursor_init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t W, uint32_t n_rv, LaneCursor& L, uint32_t sample, int qbeg,
-                                            int32_t* rv, int rvs) {
+__device__ __forceinline__ void cursor_init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t W, uint32_t n_rv, LaneCursor& L, uint32_t sample,
+                                            uint32_t tile_cursor, int32_t* rv, int rvs) {
     L.base = R.ds_rec_off[sample];
     const uint64_t hi = R.ds_rec_off[sample + 1];
     L.n = (uint32_t)(hi - L.base);
-    L.c = (uint32_t)(first_candidate(R.maxend, L.base, hi, qbeg) - L.base);
+    L.c = tile_cursor < L.n ? tile_cursor : L.n;  // from the tile cursor table; the first seek moves it on to the site's own qbeg
     cursor_load(blobs, W, n_rv, L, rv, rvs);
 }
 
@@ -274,6 +275,37 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
         }
     }
     return bits;
+}
+
+// Tile cursor table: cursor[tile][sample] = first record (relative to the sample's first) whose running max end exceeds
+// the tile's starting query position tq[tile] (tq = suffix-minimum of the tiles' first qbeg, so it is non-decreasing
+// and never later than any qbeg in the tile). Record r is that record for exactly the tiles with
+// maxend[r-1] <= tq[tile] < maxend[r], so the table is filled by the per-record kernel with two searches over the tiny
+// tq array instead of one binary search over the sample's records per (lane, tile) in the tiled kernel.
+// Entries no record claims stay 0xFFFFFFFF (= past the end).
+__device__ inline void fill_tile_cursors(const DRecs& R, uint64_t r, uint64_t sample_base, uint32_t sample, uint32_t n_samples, const int32_t* __restrict__ tq,
+                                         uint32_t n_tiles, uint32_t* __restrict__ cursors) {
+    const int cur = R.maxend[r];
+    uint32_t lo = 0, hi = n_tiles;  // t_hi = first tile with tq >= cur
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tq[mid] < cur) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t t_hi = lo;
+    uint32_t t_lo = 0;
+    if (r > sample_base) {  // first tile with tq >= maxend[r-1]
+        const int prev = R.maxend[r - 1];
+        lo = 0;
+        hi = t_hi;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (tq[mid] < prev) lo = mid + 1;
+            else hi = mid;
+        }
+        t_lo = lo;
+    }
+    for (uint32_t tile = t_lo; tile < t_hi; tile++) cursors[(size_t)tile * n_samples + sample] = (uint32_t)(r - sample_base);
 }
 
 // one record -> its blob (thread per record in glx_resolve_records_kernel)

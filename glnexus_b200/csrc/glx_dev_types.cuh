@@ -7,6 +7,8 @@
 
 namespace glxd {
 
+#define GLX_RF_DEV_LAST 0x80  // device copy of glx_records.flags only: last record of its dataset (set by glx_upload)
+
 // name-based censoring exemptions of genotype_site (src/genotyper.cc:796-821) and the squeeze path
 // (src/genotyper_utils.h:943-947): decided by FORMAT *name*, not helper class.
 enum { NF_DP = 1, NF_GQ = 2, NF_FT = 4 };

@@ -6,6 +6,9 @@
 // GLX_E_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <climits>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,22 +27,33 @@ using namespace glxd;
 // kernels
 // ---------------------------------------------------------------------------------------------
 
-// Thread per record: resolve each record into its blob (glx_cell_fast.cuh). Part of every glx_launch.
-__global__ void __launch_bounds__(256) glx_resolve_records_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets, int32_t* __restrict__ blobs) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R.n_records) return;
-    // last record of its sample? find the dataset whose range holds r
-    uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= r < ds_rec_off[hi]
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (R.ds_rec_off[mid] <= r) lo = mid;
-        else hi = mid;
+// Thread per record: resolve each record into its blob (glx_cell_fast.cuh). Part of every glx_launch. Blobs are built
+// in shared memory and written out by the whole block as one contiguous, fully coalesced span.
+#define GLX_RESOLVE_THREADS 256
+__global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets,
+                                                                                  int32_t* __restrict__ blobs, const int32_t* __restrict__ tile_q,
+                                                                                  uint32_t n_tiles, uint32_t* __restrict__ tile_cursors) {
+    extern __shared__ int4 s_blob[];  // [GLX_RESOLVE_THREADS][W/4], row r XOR-swizzled by chunk to spread banks
+    const uint32_t W = blob_words(plan.n_rv), Q = W / 4;
+    const uint64_t r0 = (uint64_t)blockIdx.x * GLX_RESOLVE_THREADS;
+    const uint64_t r = r0 + threadIdx.x;
+    if (r < R.n_records) {
+        int32_t w[(GLX_BLOB_HDR + GLX_FAST_RV + 3) & ~3];
+        build_record_blob(cfg, plan, R, r, R.flags[r] & GLX_RF_DEV_LAST, w);  // glx_upload marks each sample's last record
+        // which sample is r in? (ds_rec_off is small and cache-resident)
+        uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= r < ds_rec_off[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (R.ds_rec_off[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        fill_tile_cursors(R, r, R.ds_rec_off[lo], lo, n_datasets, tile_q, n_tiles, tile_cursors);
+        for (uint32_t q = 0; q < Q; q++) s_blob[threadIdx.x * Q + q] = make_int4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
-    int32_t w[(GLX_BLOB_HDR + GLX_FAST_RV + 3) & ~3];
-    build_record_blob(cfg, plan, R, r, r + 1 == R.ds_rec_off[lo + 1], w);
-    const uint32_t W = blob_words(plan.n_rv);
-    int4* dst = reinterpret_cast<int4*>(blobs + r * W);
-    for (uint32_t q = 0; q < W / 4; q++) dst[q] = make_int4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    __syncthreads();
+    const uint64_t n_here = min((uint64_t)GLX_RESOLVE_THREADS, R.n_records - r0);
+    int4* __restrict__ dst = reinterpret_cast<int4*>(blobs + r0 * W);
+    for (uint32_t e = threadIdx.x; e < n_here * Q; e += GLX_RESOLVE_THREADS) dst[e] = s_blob[e];
 }
 
 // Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
@@ -48,8 +62,9 @@ __global__ void __launch_bounds__(256) glx_resolve_records_kernel(const DCfg cfg
 // vectors; consecutive lanes are consecutive samples, so every store instruction of a warp covers one contiguous
 // span of the sample-major output. Unfinished cells go to the worklist of the general kernel with their cursor.
 __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
-                                                                           const int32_t* __restrict__ blobs, uint2* __restrict__ worklist,
-                                                                           uint32_t* __restrict__ n_work, uint32_t n_sample_blocks) {
+                                                                           const int32_t* __restrict__ blobs, const uint32_t* __restrict__ tile_cursors,
+                                                                           uint2* __restrict__ worklist, uint32_t* __restrict__ n_work, uint32_t n_sample_blocks,
+                                                                           uint32_t cta0) {
     __shared__ int s_beg[GLX_TILE_SITES], s_end[GLX_TILE_SITES], s_qbeg[GLX_TILE_SITES], s_qend[GLX_TILE_SITES];
     __shared__ uint8_t s_flags[GLX_TILE_SITES];  // bit0: general path only (monoallelic), bit1: qbeg below the previous site's
     __shared__ uint16_t s_cnt[GLX_MAX_FIELDS][GLX_TILE_SITES];
@@ -58,9 +73,10 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     __shared__ uint32_t s_nslow;  // cells this CTA handed to the general kernel (its worklist region is CTA-private)
     extern __shared__ int32_t s_rv[];  // [plan.n_rv][GLX_TILE_THREADS]
 
-    const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
+    const uint32_t cta = blockIdx.x + cta0;
+    const uint32_t sb = cta % n_sample_blocks, tile = cta / n_sample_blocks;
     const uint32_t site0 = tile * GLX_TILE_SITES;
-    uint2* __restrict__ my_work = worklist + (size_t)blockIdx.x * (GLX_TILE_SITES * GLX_TILE_THREADS);
+    uint2* __restrict__ my_work = worklist + (size_t)cta * (GLX_TILE_SITES * GLX_TILE_THREADS);
     if (threadIdx.x == 0) s_nslow = 0;
     const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
     const uint32_t N = S.n_samples;
@@ -94,7 +110,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     L.beg_c = L.end_c = L.maxend_c = L.beg_n = 0x7fffffff;
     L.bits = 1;
     L.mrd = -1;
-    if (active) cursor_init(R, blobs, W, n_rv, L, sample, s_qbeg[0], rv, GLX_TILE_THREADS);
+    if (active) cursor_init(R, blobs, W, n_rv, L, sample, tile_cursors[(size_t)tile * N + sample], rv, GLX_TILE_THREADS);
 
     for (uint32_t i = 0; i < nsite; i++) {
         const uint32_t s = site0 + i;
@@ -140,7 +156,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
         }
     }
     __syncthreads();
-    if (tid == 0) n_work[blockIdx.x] = s_nslow;
+    if (tid == 0) n_work[cta] = s_nslow;
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         if (s_used[i]) atomicOr(O.allele_used + site0 + i, s_used[i]);
         if (s_lost[i]) {
@@ -151,27 +167,45 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     }
 }
 
+// Worklist, pass 1: thread per worklist cell flagged "exactly one record in the query range". The closed form for a
+// lone variant record (genotype_cell_single) needs no scratch and few registers, so this kernel runs at high
+// occupancy; a cell it declines has its flag cleared in place and is left to the general kernel.
+__global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, uint2* __restrict__ worklist,
+                                                               const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions) {
+    const uint32_t N = S.n_samples;
+    for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        const uint32_t n_items = n_work[reg];
+        uint2* __restrict__ w = worklist + (size_t)reg * (GLX_TILE_SITES * GLX_TILE_THREADS);
+        for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
+            const uint2 e = w[it];
+            if (!(e.y & GLX_WORK_SINGLE)) continue;
+            const uint32_t s = e.x / N, sample = e.x % N;
+            const uint64_t first = R.ds_rec_off[sample] + (e.y & ~GLX_WORK_SINGLE);
+            if (!genotype_cell_single(cfg, R, S, O, s, sample, first)) w[it].y = e.y & ~GLX_WORK_SINGLE;
+        }
+    }
+}
+
 // General path: one thread per cell. With a worklist, block b serves the CTA-private regions b, b+gridDim.x, ... that
-// the tiled kernel filled (cell id + the lane's record cursor; region r holds n_work[r] entries); without one it
-// takes every cell of the batch and finds the cursor by binary search.
+// the tiled kernel filled (cell id + the lane's record cursor; region r holds n_work[r] entries) and takes the cells
+// the single-record pass left; without one it takes every cell of the batch and finds the cursor by binary search.
 __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint2* __restrict__ worklist,
-                                                                const uint32_t* __restrict__ n_work, uint32_t n_regions, uint64_t n_all,
+                                                                const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint64_t n_all,
                                                                 uint8_t* __restrict__ cnt_scratch, uint32_t max_slots) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint8_t* cnt = cnt_scratch + tid;
     const uint32_t N = S.n_samples;
     if (worklist) {
-        for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
             const uint32_t n_items = n_work[reg];
             const uint2* __restrict__ w = worklist + (size_t)reg * (GLX_TILE_SITES * GLX_TILE_THREADS);
             for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
                 const uint2 e = w[it];
+                if (e.y & GLX_WORK_SINGLE) continue;  // finished by glx_cells_single_kernel
                 const uint32_t s = e.x / N, sample = e.x % N;
                 const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
-                const uint64_t first = lo + (e.y & ~GLX_WORK_SINGLE);
-                if ((e.y & GLX_WORK_SINGLE) && genotype_cell_single(cfg, R, S, O, s, sample, first)) continue;
-                genotype_cell_general(cfg, R, S, O, s, sample, first, hi, cnt, stride);
+                genotype_cell_general(cfg, R, S, O, s, sample, lo + e.y, hi, cnt, stride);
             }
         }
         return;
@@ -186,9 +220,12 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+#define GLX_MAX_CHUNKS 8
 struct glx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;                      // worklist kernels of chunk j run here while the tiled kernel of chunk j+1 runs
+    cudaEvent_t chunk_ev[GLX_MAX_CHUNKS + 2] = {};   // tiled(chunk j) done / aux drained
     std::string err;
     int sm_count = 0;
     // freed batch arenas are kept for the next batch of the same range stream (cudaMalloc/cudaFree of GB-sized
@@ -283,16 +320,20 @@ struct glx_dev_batch {
     int general_blocks = 0;
     int launches_per_call = 0;
     bool force_general = false;
+    uint32_t n_chunks = 1;
     FastPlan plan;
     uint2* worklist = nullptr;     // [n_cells] (cell id, record cursor) for the general kernel
     uint32_t* n_work = nullptr;
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
-    typedef void (*tiled_fn)(const DCfg, const FastPlan, const DRecs, const DSites, const DOut, const int32_t*, uint2*, uint32_t*, uint32_t);
+    typedef void (*tiled_fn)(const DCfg, const FastPlan, const DRecs, const DSites, const DOut, const int32_t*, const uint32_t*, uint2*, uint32_t*, uint32_t,
+                             uint32_t);
     tiled_fn tiled_kernel = nullptr;  // signature-specialised tiled kernel, or the dynamic one
     size_t tiled_smem = 0;
-    int32_t* blobs = nullptr;  // [n_records][blob_words] resolved records
+    int32_t* blobs = nullptr;  // [n_records][blob_words] resolved records, then the tile cursor table and tile_q
     size_t blob_bytes = 0;
+    uint32_t* tile_cursors = nullptr;  // [n_site_tiles][n_samples]
+    int32_t* tile_q = nullptr;         // [n_site_tiles] suffix-min of each tile's first qbeg
     uint32_t n_datasets = 0;
 };
 
@@ -317,10 +358,15 @@ int glx_create(glx_ctx** out, int device) {
     auto* ctx = new glx_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return GLX_E_CUDA;
     }
+    for (auto& e : ctx->chunk_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return GLX_E_CUDA;
+        }
     *out = ctx;
     return GLX_OK;
 }
@@ -330,6 +376,9 @@ void glx_destroy(glx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& c : ctx->cache)
         if (c.p) cudaFree(c.p);
+    for (auto& e : ctx->chunk_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -406,6 +455,10 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     d->n_cells = S * N;
     const char* fg = getenv("GLX_FORCE_GENERAL");
     d->force_general = fg && *fg && *fg != '0';
+    if (const char* nc = getenv("GLX_CHUNKS")) {
+        const int v = atoi(nc);
+        if (v >= 1 && v <= GLX_MAX_CHUNKS) d->n_chunks = (uint32_t)v;
+    }
 
     const uint64_t Rn = recs->n_records, D = recs->n_datasets, C = cfg->n_cols;
     const uint64_t nA = sites->n_site_alleles, nU = sites->n_unif;
@@ -428,7 +481,10 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     add(recs->maxend, Rn * 4, &R.maxend);
     add(recs->qual, Rn * 4, &R.qual);
     add(recs->n_allele, Rn, &R.n_allele);
-    add(recs->flags, Rn, &R.flags);
+    std::vector<uint8_t> flags_dev(recs->flags, recs->flags + Rn);  // + device-private bit: last record of its dataset
+    for (uint64_t dd = 0; dd < D; dd++)
+        if (recs->ds_rec_off[dd + 1] > recs->ds_rec_off[dd]) flags_dev[recs->ds_rec_off[dd + 1] - 1] |= GLX_RF_DEV_LAST;
+    add(flags_dev.data(), Rn, &R.flags);
     add(recs->filt, Rn * 4, &R.filt);
     add(recs->gt, Rn * 4, &R.gt);
     add(recs->allele_off, Rn * 4, &R.allele_off);
@@ -544,11 +600,27 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
             return cuda_fail(ctx, e, "cudaMalloc(worklist)");
         }
         d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * (GLX_TILE_SITES * GLX_TILE_THREADS));
-        d->blob_bytes = (Rn + 1) * blob_words(d->plan.n_rv) * 4;
+        const size_t blob_part = ((Rn + 1) * blob_words(d->plan.n_rv) * 4 + 255) & ~(size_t)255;
+        const size_t cur_part = (((size_t)d->n_site_tiles * N + 1) * 4 + 255) & ~(size_t)255;
+        d->blob_bytes = blob_part + cur_part + ((size_t)d->n_site_tiles + 1) * 4;
         e = ctx->take((void**)&d->blobs, d->blob_bytes);
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
             return cuda_fail(ctx, e, "cudaMalloc(record blobs)");
+        }
+        d->tile_cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part);
+        d->tile_q = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part);
+        std::vector<int32_t> tq(d->n_site_tiles);
+        int32_t run = INT32_MAX;
+        for (uint32_t tile = d->n_site_tiles; tile-- > 0;) {  // suffix minimum: non-decreasing, never later than any later tile's start
+            run = std::min(run, sites->qbeg[(size_t)tile * GLX_TILE_SITES]);
+            tq[tile] = run;
+        }
+        e = cudaMemcpyAsync(d->tile_q, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            glx_free_batch(ctx, d);
+            return cuda_fail(ctx, e, "upload(tile_q)");
         }
     }
     d->n_datasets = (uint32_t)D;
@@ -590,22 +662,51 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     const bool tiled = d->plan.enabled && d->n_cells;
     if (d->profile) CU(cudaEventRecord(d->ev[0], st));
     if (tiled) {
+        CU(cudaMemsetAsync(d->tile_cursors, 0xff, (size_t)d->n_site_tiles * d->n_samples * 4, st));
         if (d->R.n_records) {
-            glx_resolve_records_kernel<<<(unsigned)((d->R.n_records + 255) / 256), 256, 0, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs);
+            glx_resolve_records_kernel<<<(unsigned)((d->R.n_records + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS), GLX_RESOLVE_THREADS,
+                                         (size_t)GLX_RESOLVE_THREADS * blob_words(d->plan.n_rv) * 4, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q,
+                                                                                                            d->n_site_tiles, d->tile_cursors);
             d->launches_per_call++;
             CU(cudaGetLastError());
         }
-        d->tiled_kernel<<<d->n_sample_blocks * d->n_site_tiles, GLX_TILE_THREADS, d->tiled_smem, st>>>(d->cfg, d->plan, d->R, d->S, d->O, d->blobs, d->worklist,
-                                                                                                     d->n_work, d->n_sample_blocks);
-        d->launches_per_call++;
-        CU(cudaGetLastError());
-    }
-    if (d->profile) CU(cudaEventRecord(d->ev[1], st));
-    if (d->n_cells) {
-        glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, tiled ? d->worklist : nullptr, d->n_work,
-                                                                    d->n_sample_blocks * d->n_site_tiles, d->n_cells, d->cnt_scratch, d->max_slots);
-        d->launches_per_call++;
-        CU(cudaGetLastError());
+        // The tile grid is launched in chunks: the worklist kernels of chunk j (latency-bound gathers) run on the aux
+        // stream while the tiled kernel of chunk j+1 (store-heavy) runs on the launching stream.
+        const uint32_t n_regions = d->n_sample_blocks * d->n_site_tiles;
+        uint32_t n_chunks = d->n_chunks;
+        if (n_chunks > n_regions) n_chunks = n_regions;
+        for (uint32_t j = 0; j < n_chunks; j++) {
+            const uint32_t c0 = (uint32_t)((uint64_t)n_regions * j / n_chunks), c1 = (uint32_t)((uint64_t)n_regions * (j + 1) / n_chunks);
+            if (c1 == c0) continue;
+            d->tiled_kernel<<<c1 - c0, GLX_TILE_THREADS, d->tiled_smem, st>>>(d->cfg, d->plan, d->R, d->S, d->O, d->blobs, d->tile_cursors, d->worklist, d->n_work,
+                                                                            d->n_sample_blocks, c0);
+            d->launches_per_call++;
+            CU(cudaGetLastError());
+            cudaStream_t ws = n_chunks > 1 ? ctx->aux : st;
+            if (n_chunks > 1) {
+                CU(cudaEventRecord(ctx->chunk_ev[j], st));
+                CU(cudaStreamWaitEvent(ws, ctx->chunk_ev[j], 0));
+            }
+            const uint32_t nreg = c1 - c0;
+            const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
+            glx_cells_single_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1);
+            const uint32_t g2 = nreg < (uint32_t)d->general_blocks ? nreg : (uint32_t)d->general_blocks;
+            glx_cells_general_kernel<<<g2, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, d->n_cells, d->cnt_scratch, d->max_slots);
+            d->launches_per_call += 2;
+            CU(cudaGetLastError());
+        }
+        if (d->profile) CU(cudaEventRecord(d->ev[1], st));
+        if (n_chunks > 1) {  // join
+            CU(cudaEventRecord(ctx->chunk_ev[GLX_MAX_CHUNKS], ctx->aux));
+            CU(cudaStreamWaitEvent(st, ctx->chunk_ev[GLX_MAX_CHUNKS], 0));
+        }
+    } else {
+        if (d->profile) CU(cudaEventRecord(d->ev[1], st));
+        if (d->n_cells) {
+            glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots);
+            d->launches_per_call++;
+            CU(cudaGetLastError());
+        }
     }
     if (d->profile) CU(cudaEventRecord(d->ev[2], st));
     return GLX_OK;

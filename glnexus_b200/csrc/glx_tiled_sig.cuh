@@ -49,26 +49,14 @@ struct TiledLane {
     int mrd;
     int32_t rv[Sig::NRV_ARR];
 
-    // The lane's next records are staged in a private shared-memory ring by asynchronous copies (cp.async, no register
-    // staging): records c .. c+RING-1 are always in flight or landed, so a cursor advance reads shared memory and
-    // never waits on HBM, even when a 1-bp variant record makes a lane advance on consecutive sites.
-    static constexpr uint32_t RING = 4, Q = Sig::W / 4;  // ring depth (records), 16-byte chunks per blob
-
-    __device__ __forceinline__ void request(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, uint32_t idx) const {
-        if (idx < n) {
-            const int4* src = reinterpret_cast<const int4*>(blobs + (base + idx) * Sig::W);
-#pragma unroll
-            for (uint32_t q = 0; q < Q; q++) cp_async16(ring + (size_t)((idx & (RING - 1)) * Q + q) * rs, src + q);
-        }
-        cp_async_commit();  // one group per record index, empty past the end, so group counting stays uniform
-    }
-    __device__ __forceinline__ void consume(const int4* ring, uint32_t rs) {
+    // load record c's blob straight into registers (four 128-bit loads for the preset signatures)
+    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs) {
         if (c < n) {
-            cp_async_wait_but<RING - 1>();
+            const int4* b = reinterpret_cast<const int4*>(blobs + (base + c) * Sig::W);
             int32_t w[Sig::W];
 #pragma unroll
-            for (uint32_t q = 0; q < Q; q++) {
-                const int4 v = ring[(size_t)((c & (RING - 1)) * Q + q) * rs];
+            for (uint32_t q = 0; q < Sig::W / 4; q++) {
+                const int4 v = __ldg(b + q);
                 w[4 * q] = v.x;
                 w[4 * q + 1] = v.y;
                 w[4 * q + 2] = v.z;
@@ -88,24 +76,12 @@ struct TiledLane {
             mrd = -1;
         }
     }
-    // (re)start the ring at record c
-    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs) {
-        cp_async_wait_but<0>();
-#pragma unroll
-        for (uint32_t d = 0; d < RING; d++) request(blobs, ring, rs, c + d);
-        consume(ring, rs);
-    }
-    __device__ __forceinline__ void advance(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs) {
-        c++;
-        request(blobs, ring, rs, c + RING - 1);
-        consume(ring, rs);
-    }
-    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, uint32_t sample, int qbeg) {
+    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t sample, uint32_t tile_cursor) {
         base = R.ds_rec_off[sample];
         const uint64_t hi = R.ds_rec_off[sample + 1];
         n = (uint32_t)(hi - base);
-        c = (uint32_t)(first_candidate(R.maxend, base, hi, qbeg) - base);
-        load(blobs, ring, rs);
+        c = tile_cursor < n ? tile_cursor : n;  // tile cursor table (fill_tile_cursors)
+        load(blobs);
     }
     __device__ __forceinline__ void idle() {
         base = 0;
@@ -116,23 +92,26 @@ struct TiledLane {
 #pragma unroll
         for (uint32_t j = 0; j < Sig::NRV_ARR; j++) rv[j] = 0;
     }
-    __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, int qbeg, bool back) {
+    __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int qbeg, bool back) {
         if (back) {
             bool moved = false;
             while (c > 0 && blobs[(base + c - 1) * Sig::W + 2] > qbeg) {
                 c--;
                 moved = true;
             }
-            if (moved) load(blobs, ring, rs);
+            if (moved) load(blobs);
         }
-        while (c < n && maxend_c <= qbeg) advance(blobs, ring, rs);
+        while (c < n && maxend_c <= qbeg) {
+            c++;
+            load(blobs);
+        }
     }
     // same decision table as fast_classify
-    __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int4* ring, uint32_t rs, int sbeg, int send, int qbeg, int qend,
-                                            bool slow_site, bool back, bool& called, int& rnc) {
+    __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int sbeg, int send, int qbeg, int qend, bool slow_site, bool back,
+                                            bool& called, int& rnc) {
         called = false;
         rnc = RNC_M;
-        seek(blobs, ring, rs, qbeg, back);
+        seek(blobs, qbeg, back);
         if (slow_site) return CT_SLOW;
         if (c >= n || beg_c >= qend) return CT_MISSING;
         if (beg_n < qend) return CT_SLOW;
@@ -152,11 +131,15 @@ struct TiledLane {
     }
     // field K's vector of a finished cell. A = unified alleles of the site; off_dyn(k) = fld_off[k][s] for
     // allele/genotype-numbered fields (BASIC-numbered fields sit at s*N*count).
+    // `done`: this lane finished its cell (otherwise it only takes part in the warp-wide transposed stores; the
+    // worklist kernels rewrite its slots later). `stage`: the warp's 32 x GLX_STAGE_MAX staging buffer.
     template <uint32_t K, class OffFn>
-    __device__ __forceinline__ void emit_one(const FastPlan& plan, const DOut& O, bool ref, uint32_t s, uint32_t N, uint32_t sample, uint32_t A, OffFn off_dyn) const {
+    __device__ __forceinline__ void emit_one(const FastPlan& plan, const DOut& O, bool done, bool ref, uint32_t s, uint32_t N, uint32_t sample, uint32_t A,
+                                             OffFn off_dyn, int32_t* stage, uint32_t lane, uint32_t nvalid) const {
         const int32_t cen = plan.cen[K];
         constexpr uint32_t r0 = Sig::rv0(K);
         if constexpr (Sig::mode(K) == FM_VEC) {
+            if (!done) return;
             constexpr uint32_t cnt = Sig::nrv(K);
             int32_t* __restrict__ o = O.fld[K] + ((unsigned long long)s * N + sample) * cnt;
             int32_t v[cnt ? cnt : 1];
@@ -171,7 +154,6 @@ struct TiledLane {
         } else {
             const uint32_t count = Sig::num(K) == GLX_NUM_ALLELES ? A : (Sig::num(K) == GLX_NUM_ALT ? A - 1 : A * (A + 1) / 2);
             const unsigned long long off = off_dyn(K);
-            int32_t* __restrict__ o = O.fld[K] + off + (unsigned long long)sample * count;
             int32_t x0 = cen, x1 = plan.vec_rule[K] ? GLXD_INT_VEND : cen, xr = cen, xt = cen;
             if constexpr (Sig::mode(K) == FM_PATTERN) {
                 if (ref) {
@@ -181,6 +163,35 @@ struct TiledLane {
                     xt = rv[r0 + 3];
                 }
             }
+#ifdef __CUDACC__
+            if (count >= 3 && count <= GLX_STAGE_MAX) {
+                // A lane's vector of 3..8 ints is narrower than a sector and not a power of two: written lane by lane every
+                // store instruction would touch a third of each sector. Transpose through shared memory so that the warp
+                // writes its 32*count ints as `count` fully coalesced rows.
+                int32_t* st = stage + lane * count;
+                st[0] = x0;
+                st[1] = x1;
+                st[2] = xt;
+                int next_row = 3, a = 2;
+                for (uint32_t j = 3; j < count; j++) {
+                    int32_t v = xt;
+                    if ((int)j == next_row) {
+                        v = xr;
+                        a++;
+                        next_row += a;
+                    }
+                    st[j] = v;
+                }
+                __syncwarp();
+                int32_t* __restrict__ ow = O.fld[K] + off + (unsigned long long)(sample - lane) * count;
+                const uint32_t total = nvalid * count;
+                for (uint32_t e = lane; e < total; e += 32) ow[e] = stage[e];
+                __syncwarp();
+                return;
+            }
+#endif
+            if (!done) return;
+            int32_t* __restrict__ o = O.fld[K] + off + (unsigned long long)sample * count;
             if (count == 2 && !(off & 1)) {
                 *reinterpret_cast<int2*>(o) = make_int2(x0, x1);
             } else {
@@ -201,47 +212,52 @@ struct TiledLane {
         }
     }
     template <uint32_t K, class OffFn>
-    __device__ __forceinline__ void emit_from(const FastPlan& plan, const DOut& O, bool ref, uint32_t s, uint32_t N, uint32_t sample, uint32_t A, OffFn off_dyn) const {
+    __device__ __forceinline__ void emit_from(const FastPlan& plan, const DOut& O, bool done, bool ref, uint32_t s, uint32_t N, uint32_t sample, uint32_t A,
+                                              OffFn off_dyn, int32_t* stage, uint32_t lane, uint32_t nvalid) const {
         if constexpr (K < Sig::nf) {
-            emit_one<K>(plan, O, ref, s, N, sample, A, off_dyn);
-            emit_from<K + 1>(plan, O, ref, s, N, sample, A, off_dyn);
+            emit_one<K>(plan, O, done, ref, s, N, sample, A, off_dyn, stage, lane, nvalid);
+            emit_from<K + 1>(plan, O, done, ref, s, N, sample, A, off_dyn, stage, lane, nvalid);
         }
     }
+    // all lifted vectors of the lane's cell at site s; must be called by every lane of the warp
     template <class OffFn>
-    __device__ __forceinline__ void emit(const FastPlan& plan, const DOut& O, bool ref, uint32_t s, uint32_t N, uint32_t sample, uint32_t A, OffFn off_dyn) const {
-        emit_from<0>(plan, O, ref, s, N, sample, A, off_dyn);
+    __device__ __forceinline__ void emit(const FastPlan& plan, const DOut& O, bool done, bool ref, uint32_t s, uint32_t N, uint32_t sample, uint32_t A,
+                                         OffFn off_dyn, int32_t* stage, uint32_t lane, uint32_t nvalid) const {
+        emit_from<0>(plan, O, done, ref, s, N, sample, A, off_dyn, stage, lane, nvalid);
     }
 };
 
 #ifdef __CUDACC__
 template <class Sig>
 __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
-                                                                               const int32_t* __restrict__ blobs, uint2* __restrict__ worklist,
-                                                                               uint32_t* __restrict__ n_work, uint32_t n_sample_blocks) {
-    __shared__ int4 s_pos[GLX_TILE_SITES];  // beg, end, qbeg, qend
+                                                                               const int32_t* __restrict__ blobs, const uint32_t* __restrict__ tile_cursors,
+                                                                               uint2* __restrict__ worklist,
+                                                                               uint32_t* __restrict__ n_work, uint32_t n_sample_blocks, uint32_t cta0) {
+    __shared__ int4 s_pos[GLX_TILE_SITES];       // beg, end, qbeg, qend
     __shared__ uint32_t s_meta[GLX_TILE_SITES];  // bits 0-7 n_allele, bit 8 general path only, bit 9 qbeg below the previous site's
     __shared__ unsigned long long s_off[Sig::nf ? Sig::nf : 1][GLX_TILE_SITES];
-    __shared__ uint32_t s_used[GLX_TILE_SITES], s_lost[GLX_TILE_SITES];
-    __shared__ uint32_t s_nslow;  // cells this CTA handed to the general kernel (its worklist region is CTA-private)
-    __shared__ int4 s_ring[TiledLane<Sig>::RING * TiledLane<Sig>::Q * GLX_TILE_THREADS];  // per-lane record ring, chunk-major
+    __shared__ uint32_t s_red[4][GLX_TILE_THREADS / 32];  // per-warp called/lost site masks (lo, hi words)
+    __shared__ uint32_t s_nslow;  // cells this CTA handed to the worklist kernels (its worklist region is CTA-private)
+    __shared__ int32_t s_stage[GLX_TILE_THREADS / 32][32 * GLX_STAGE_MAX];  // per-warp transposition buffer for narrow vectors
 
-    const uint32_t sb = blockIdx.x % n_sample_blocks, tile = blockIdx.x / n_sample_blocks;
+    const uint32_t cta = blockIdx.x + cta0;  // launches cover chunks of the tile grid so that the worklist kernels of one chunk overlap the next
+    const uint32_t sb = cta % n_sample_blocks, tile = cta / n_sample_blocks;
     const uint32_t site0 = tile * GLX_TILE_SITES;
-    uint2* __restrict__ my_work = worklist + (size_t)blockIdx.x * (GLX_TILE_SITES * GLX_TILE_THREADS);
+    uint2* __restrict__ my_work = worklist + (size_t)cta * (GLX_TILE_SITES * GLX_TILE_THREADS);
     if (threadIdx.x == 0) s_nslow = 0;
     const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
     const uint32_t N = S.n_samples;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t sample = sb * GLX_TILE_THREADS + tid;
     const bool active = sample < N;
+    const uint32_t warp_sample0 = sample - lane;
+    const uint32_t nvalid = warp_sample0 >= N ? 0u : min(32u, N - warp_sample0);
 
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         const uint32_t s = site0 + i;
         const int qb = S.qbeg[s];
         s_pos[i] = make_int4(S.beg[s], S.end[s], qb, S.qend[s]);
         s_meta[i] = (uint32_t)S.n_allele[s] | (S.monoallelic[s] ? 256u : 0u) | ((i > 0 && qb < S.qbeg[s - 1]) ? 512u : 0u);
-        s_used[i] = 0;
-        s_lost[i] = 0;
 #pragma unroll
         for (uint32_t k = 0; k < Sig::nf; k++)
             if (Sig::mode(k) != FM_VEC) s_off[k][i] = S.fld_off[k][s];
@@ -249,49 +265,68 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
     __syncthreads();
 
     TiledLane<Sig> L;
-    int4* ring = s_ring + tid;
-    if (active) L.init(R, blobs, ring, GLX_TILE_THREADS, sample, s_pos[0].z);
+    if (active) L.init(R, blobs, sample, tile_cursors[(size_t)tile * N + sample]);
     else L.idle();
+    // sites (bit i of the tile) where this lane called 0/0, resp. produced a "lost call" RNC; reduced once per tile
+    unsigned long long called_bits = 0, lost_bits = 0;
+    char2* __restrict__ gt_p = reinterpret_cast<char2*>(O.gt) + ((size_t)site0 * N + sample);
+    uchar2* __restrict__ rnc_p = reinterpret_cast<uchar2*>(O.rnc) + ((size_t)site0 * N + sample);
 
-    for (uint32_t i = 0; i < nsite; i++) {
+    for (uint32_t i = 0; i < nsite; i++, gt_p += N, rnc_p += N) {
         const uint32_t s = site0 + i;
         const int4 pos = s_pos[i];
         const uint32_t meta = s_meta[i];
         int type = CT_MISSING, rnc = RNC_M;
         bool called = false;
-        if (active) type = L.classify(cfg, blobs, ring, GLX_TILE_THREADS, pos.x, pos.y, pos.z, pos.w, meta & 256u, meta & 512u, called, rnc);
+        if (active) type = L.classify(cfg, blobs, pos.x, pos.y, pos.z, pos.w, meta & 256u, meta & 512u, called, rnc);
         const bool slow = active && type == CT_SLOW;
-        const bool done = active && !slow;
         const uint32_t slow_mask = __ballot_sync(0xffffffffu, slow);
         if (slow_mask) {
             uint32_t wbase = 0;
             const int leader = __ffs(slow_mask) - 1;
             if ((int)lane == leader) wbase = atomicAdd(&s_nslow, (uint32_t)__popc(slow_mask));
             wbase = __shfl_sync(0xffffffffu, wbase, leader);
-            if (slow) my_work[wbase + __popc(slow_mask & ((1u << lane) - 1))] = make_uint2(s * N + sample, L.c | ((!(meta & 256u) && L.c < L.n && L.beg_c < pos.w && L.beg_n >= pos.w) ? GLX_WORK_SINGLE : 0u));
+            if (slow)
+                my_work[wbase + __popc(slow_mask & ((1u << lane) - 1))] =
+                    make_uint2(s * N + sample, L.c | ((!(meta & 256u) && L.c < L.n && L.beg_c < pos.w && L.beg_n >= pos.w) ? GLX_WORK_SINGLE : 0u));
         }
-        const uint32_t called_mask = __ballot_sync(0xffffffffu, done && called);
-        const uint32_t lost_mask = __ballot_sync(0xffffffffu, done && rnc == RNC_I);
+        const bool done = active && !slow;
+        if (done) {
+            called_bits |= (unsigned long long)called << i;
+            lost_bits |= (unsigned long long)(rnc == RNC_I) << i;
+            const signed char a = called ? 0 : -1;
+            const unsigned char rc = (unsigned char)kRncChar[rnc];
+            *gt_p = make_char2(a, a);
+            *rnc_p = make_uchar2(rc, rc);
+        }
+        L.emit(plan, O, done, type == CT_REF, s, N, sample, meta & 255u, [&](uint32_t k) { return s_off[k][i]; }, s_stage[tid >> 5], lane, nvalid);
+    }
+    // ---- per-site reductions for the whole tile: allele 0 used / some call lost ----
+    {
+        const uint32_t w = tid >> 5;
+        const uint32_t c_lo = __reduce_or_sync(0xffffffffu, (uint32_t)called_bits), c_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(called_bits >> 32));
+        const uint32_t l_lo = __reduce_or_sync(0xffffffffu, (uint32_t)lost_bits), l_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(lost_bits >> 32));
         if (lane == 0) {
-            if (called_mask) atomicOr(&s_used[i], 1u);
-            if (lost_mask) atomicOr(&s_lost[i], 1u);
+            s_red[0][w] = c_lo;
+            s_red[1][w] = c_hi;
+            s_red[2][w] = l_lo;
+            s_red[3][w] = l_hi;
         }
-        if (!done) continue;
-        const size_t cell = (size_t)s * N + sample;
-        const signed char a = called ? 0 : -1;
-        const unsigned char rc = (unsigned char)kRncChar[rnc];
-        reinterpret_cast<char2*>(O.gt)[cell] = make_char2(a, a);
-        reinterpret_cast<uchar2*>(O.rnc)[cell] = make_uchar2(rc, rc);
-        L.emit(plan, O, type == CT_REF, s, N, sample, meta & 255u, [&](uint32_t k) { return s_off[k][i]; });
     }
     __syncthreads();
-    if (tid == 0) n_work[blockIdx.x] = s_nslow;
+    if (tid == 0) n_work[cta] = s_nslow;
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
-        if (s_used[i]) atomicOr(O.allele_used + site0 + i, s_used[i]);
-        if (s_lost[i]) {
+        uint32_t cm = 0, lm = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < GLX_TILE_THREADS / 32; w++) {
+            cm |= s_red[i >> 5][w];
+            lm |= s_red[2 + (i >> 5)][w];
+        }
+        if (cm >> (i & 31) & 1) atomicOr(O.allele_used + site0 + i, 1u);  // fast cells only ever call allele 0
+        if (lm >> (i & 31) & 1) {
             uint8_t* fp = O.site_flags + site0 + i;
-            uint32_t* w = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(fp) & ~(uintptr_t)3);
-            atomicOr(w, 1u << (8 * (reinterpret_cast<uintptr_t>(fp) & 3)));
+            uint32_t* wd = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(fp) & ~(uintptr_t)3);
+            atomicOr(wd, 1u << (8 * (reinterpret_cast<uintptr_t>(fp) & 3)));
         }
     }
 }

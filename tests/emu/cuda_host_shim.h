@@ -46,3 +46,5 @@ inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
 inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait_but() {}
+template <class T>
+inline T __ldg(const T* p) { return *p; }

@@ -63,21 +63,19 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
 
 // signature-specialised lanes (glx_tiled_sig.cuh), lane by lane
 template <class Sig>
-static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, const DSites& S, const DOut& O, const int32_t* blobs, std::vector<uint8_t>& flags,
-                          std::vector<uint8_t>& cnt, uint64_t& n_slow) {
+static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, const DSites& S, const DOut& O, const int32_t* blobs, const uint32_t* cursors,
+                          std::vector<uint8_t>& flags, std::vector<uint8_t>& cnt, uint64_t& n_slow) {
     const uint32_t Sn = S.n_sites, N = S.n_samples;
     for (uint32_t n = 0; n < N; n++) {
         for (uint32_t site0 = 0; site0 < Sn; site0 += GLX_TILE_SITES) {
             const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);
             TiledLane<Sig> L;
-            int4 ring[TiledLane<Sig>::RING * TiledLane<Sig>::Q];
-            L.init(R, blobs, ring, 1, n, S.qbeg[site0]);
+            L.init(R, blobs, n, cursors[(size_t)(site0 / GLX_TILE_SITES) * N + n]);
             for (uint32_t i = 0; i < nsite; i++) {
                 const uint32_t s = site0 + i;
                 int rnc = RNC_M;
                 bool called = false;
-                const int type =
-                    L.classify(C, blobs, ring, 1, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1], called, rnc);
+                const int type = L.classify(C, blobs, S.beg[s], S.end[s], S.qbeg[s], S.qend[s], S.monoallelic[s] != 0, i > 0 && S.qbeg[s] < S.qbeg[s - 1], called, rnc);
                 if (type == CT_SLOW) {
                     n_slow++;
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
@@ -90,7 +88,7 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                 O.rnc[c2] = O.rnc[c2 + 1] = (uint8_t)kRncChar[rnc];
                 if (called) O.allele_used[s] |= 1u;
                 if (rnc == RNC_I) flags[s] |= 1;
-                L.emit(plan, O, type == CT_REF, s, N, n, S.n_allele[s], [&](uint32_t k) { return (unsigned long long)S.fld_off[k][s]; });
+                L.emit(plan, O, true, type == CT_REF, s, N, n, S.n_allele[s], [&](uint32_t k) { return (unsigned long long)S.fld_off[k][s]; }, nullptr, 0, 1);
             }
         }
     }
@@ -125,6 +123,19 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
     if (plan.enabled)
         for (uint32_t d = 0; d < N; d++)
             for (uint64_t r = R.ds_rec_off[d]; r < R.ds_rec_off[d + 1]; r++) build_record_blob(C, plan, R, r, r + 1 == R.ds_rec_off[d + 1], blobs.data() + r * W);
+    // tile cursor table, as glx_upload + glx_resolve_records_kernel build it
+    const uint32_t n_tiles = (Sn + GLX_TILE_SITES - 1) / GLX_TILE_SITES;
+    std::vector<int32_t> tq(n_tiles + 1);
+    {
+        int32_t run = INT32_MAX;
+        for (uint32_t tile = n_tiles; tile-- > 0;) {
+            run = std::min(run, S.qbeg[(size_t)tile * GLX_TILE_SITES]);
+            tq[tile] = run;
+        }
+    }
+    std::vector<uint32_t> cursors((size_t)n_tiles * N + 1, 0xffffffffu);
+    for (uint32_t d = 0; d < N; d++)
+        for (uint64_t r = R.ds_rec_off[d]; r < R.ds_rec_off[d + 1]; r++) fill_tile_cursors(R, r, R.ds_rec_off[d], d, N, tq.data(), n_tiles, cursors.data());
     {
         uint32_t nf;
         uint64_t modes, nums, nrvs;
@@ -132,10 +143,10 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
         if (!dynamic_only && sig_of_plan(C, plan, nf, modes, nums, nrvs)) {  // same dispatch as glx_upload
             auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
             if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
-                run_tiled_sig<SigDeepVariant>(C, plan, R, S, O, blobs.data(), flags, cnt, n_slow);
+                run_tiled_sig<SigDeepVariant>(C, plan, R, S, O, blobs.data(), cursors.data(), flags, cnt, n_slow);
                 handled = true;
             } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
-                run_tiled_sig<SigGatk>(C, plan, R, S, O, blobs.data(), flags, cnt, n_slow);
+                run_tiled_sig<SigGatk>(C, plan, R, S, O, blobs.data(), cursors.data(), flags, cnt, n_slow);
                 handled = true;
             }
         }
@@ -152,7 +163,7 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
             const uint32_t nsite = std::min<uint32_t>(GLX_TILE_SITES, Sn - site0);
             LaneCursor L;
             int32_t rv[GLX_FAST_RV];
-            if (plan.enabled) cursor_init(R, blobs.data(), W, n_rv, L, n, S.qbeg[site0], rv, 1);
+            if (plan.enabled) cursor_init(R, blobs.data(), W, n_rv, L, n, cursors[(size_t)(site0 / GLX_TILE_SITES) * N + n], rv, 1);
             for (uint32_t i = 0; i < nsite; i++) {
                 const uint32_t s = site0 + i;
                 int type = CT_SLOW, rnc = RNC_M;
