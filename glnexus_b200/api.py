@@ -54,6 +54,20 @@ def lib():
     L.glxh_partition_sites.restype = C.c_int
     L.glxh_batch_slice.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), cp, sz]
     L.glxh_batch_slice.restype = C.c_int
+    L.glxh_batch_pin.argtypes = [vp]
+    L.glxh_batch_pin.restype = C.c_int
+    L.glx_upload_on.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.glx_upload_on.restype = C.c_int
+    L.glx_download_on.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.glx_download_on.restype = C.c_int
+    L.glx_status.argtypes = [vp, vp]
+    L.glx_status.restype = C.c_int
+    L.glx_stream_create.argtypes = [vp]
+    L.glx_stream_create.restype = vp
+    L.glx_stream_destroy.argtypes = [vp, vp]
+    L.glx_stream_destroy.restype = None
+    L.glx_stream_sync.argtypes = [vp, vp]
+    L.glx_stream_sync.restype = C.c_int
     L.glxh_batch_free.argtypes = [vp]
     L.glxh_batch_free.restype = None
     for fn in ("glxh_config", "glxh_records", "glxh_sites"):
@@ -206,6 +220,13 @@ class Batch:
             raise GlxError(rc, err.value.decode(errors="replace"))
         return cls(h)
 
+    def pin(self):
+        """Page-lock the batch's host arrays (uploads then run at PCIe rate and asynchronously)."""
+        rc = lib().glxh_batch_pin(self.handle)
+        if rc != GLX_OK:
+            raise GlxError(rc, "glxh_batch_pin")
+        return self
+
     def partition(self, n_parts):
         """Cut points (n_parts+1) of contiguous site ranges of equal output weight, one range per GPU."""
         b = (C.c_uint32 * (n_parts + 1))()
@@ -266,6 +287,13 @@ class DeviceBatch:
     def download(self, out):
         self.ctx._check(lib().glx_download(self.ctx.handle, self.handle, out.ptr))
 
+    def download_async(self, out, stream):
+        self.ctx._check(lib().glx_download_on(self.ctx.handle, self.handle, out.ptr, C.c_void_p(stream), 0))
+
+    def status(self):
+        """Error word of a batch whose asynchronous download has been synchronised."""
+        self.ctx._check(lib().glx_status(self.ctx.handle, self.handle))
+
     def set_profile(self, on=True):
         self.ctx._check(lib().glx_set_profile(self.ctx.handle, self.handle, 1 if on else 0))
 
@@ -316,6 +344,24 @@ class Context:
         d = C.c_void_p()
         self._check(lib().glx_upload(self.handle, batch.config_ptr, batch.records_ptr, batch.sites_ptr, C.byref(d)))
         return DeviceBatch(self, d)
+
+    def upload_async(self, batch, stream):
+        """Enqueue the batch's H2D copies on `stream`; the batch must stay alive (and should be pinned) until synchronised."""
+        d = C.c_void_p()
+        self._check(lib().glx_upload_on(self.handle, batch.config_ptr, batch.records_ptr, batch.sites_ptr, C.c_void_p(stream), 0, C.byref(d)))
+        return DeviceBatch(self, d)
+
+    def stream_create(self):
+        s = lib().glx_stream_create(self.handle)
+        if not s:
+            raise GlxError(-100, "glx_stream_create")
+        return s
+
+    def stream_destroy(self, s):
+        lib().glx_stream_destroy(self.handle, C.c_void_p(s))
+
+    def stream_sync(self, s):
+        self._check(lib().glx_stream_sync(self.handle, C.c_void_p(s)))
 
     def synchronize(self):
         self._check(lib().glx_synchronize(self.handle))

@@ -321,6 +321,9 @@ struct glx_dev_batch {
     int launches_per_call = 0;
     bool force_general = false;
     uint32_t n_chunks = 1;
+    std::vector<uint8_t> flags_dev;  // host staging that must outlive an asynchronous upload
+    std::vector<int32_t> tq_host;
+    unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
     FastPlan plan;
     uint2* worklist = nullptr;     // [n_cells] (cell id, record cursor) for the general kernel
     uint32_t* n_work = nullptr;
@@ -399,6 +402,7 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
     if (ctx) cudaSetDevice(ctx->device);
     for (auto& ev : d->ev)
         if (ev) cudaEventDestroy(ev);
+    if (d->host_err) cudaFreeHost(d->host_err);
     if (ctx) {
         ctx->give(d->in_base, d->in_alloc);
         ctx->give(d->out_base, d->out_alloc);
@@ -416,6 +420,10 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
 }
 
 int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_dev_batch** out) {
+    return glx_upload_on(ctx, cfg, recs, sites, nullptr, 1, out);
+}
+
+int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, void* stream_, int sync, glx_dev_batch** out) {
     if (!ctx) return GLX_E_INVALID;
     if (!cfg || !recs || !sites || !out) {
         ctx->err = "glx_upload: null argument";
@@ -447,6 +455,7 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
         return GLX_E_INVALID;
     }
     CU(cudaSetDevice(ctx->device));
+    cudaStream_t up = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     auto* d = new glx_dev_batch();
     d->cfg = make_dcfg(*cfg);
     d->n_sites = (uint32_t)S;
@@ -481,7 +490,8 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     add(recs->maxend, Rn * 4, &R.maxend);
     add(recs->qual, Rn * 4, &R.qual);
     add(recs->n_allele, Rn, &R.n_allele);
-    std::vector<uint8_t> flags_dev(recs->flags, recs->flags + Rn);  // + device-private bit: last record of its dataset
+    std::vector<uint8_t>& flags_dev = d->flags_dev;  // + device-private bit: last record of its dataset (kept until the batch is freed)
+    flags_dev.assign(recs->flags, recs->flags + Rn);
     for (uint64_t dd = 0; dd < D; dd++)
         if (recs->ds_rec_off[dd + 1] > recs->ds_rec_off[dd]) flags_dev[recs->ds_rec_off[dd + 1] - 1] |= GLX_RF_DEV_LAST;
     add(flags_dev.data(), Rn, &R.flags);
@@ -535,7 +545,7 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
         char* p = ar.take<char>(it.bytes ? it.bytes : 1);
         *it.dst = p;
         if (it.bytes) {
-            e = cudaMemcpyAsync(p, it.src, it.bytes, cudaMemcpyHostToDevice, ctx->stream);
+            e = cudaMemcpyAsync(p, it.src, it.bytes, cudaMemcpyHostToDevice, up);
             if (e != cudaSuccess) {
                 glx_free_batch(ctx, d);
                 return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
@@ -610,14 +620,14 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
         }
         d->tile_cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part);
         d->tile_q = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part);
-        std::vector<int32_t> tq(d->n_site_tiles);
+        std::vector<int32_t>& tq = d->tq_host;
+        tq.assign(d->n_site_tiles, 0);
         int32_t run = INT32_MAX;
         for (uint32_t tile = d->n_site_tiles; tile-- > 0;) {  // suffix minimum: non-decreasing, never later than any later tile's start
             run = std::min(run, sites->qbeg[(size_t)tile * GLX_TILE_SITES]);
             tq[tile] = run;
         }
-        e = cudaMemcpyAsync(d->tile_q, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        e = cudaMemcpyAsync(d->tile_q, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice, up);
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
             return cuda_fail(ctx, e, "upload(tile_q)");
@@ -641,7 +651,7 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
             }
         }
     }
-    e = cudaStreamSynchronize(ctx->stream);  // caller's host arrays may be released after return
+    e = sync ? cudaStreamSynchronize(up) : cudaSuccess;  // after a synchronous upload the caller's host arrays may be released
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
         return cuda_fail(ctx, e, "cudaStreamSynchronize(upload)");
@@ -727,11 +737,14 @@ int glx_check(glx_ctx* ctx, glx_dev_batch* d) {
     return code == 101 ? GLX_E_UNSUPPORTED : -code;
 }
 
-int glx_download(glx_ctx* ctx, glx_dev_batch* d, glx_out* out) {
+int glx_download(glx_ctx* ctx, glx_dev_batch* d, glx_out* out) { return glx_download_on(ctx, d, out, nullptr, 1); }
+
+int glx_download_on(glx_ctx* ctx, glx_dev_batch* d, glx_out* out, void* stream_, int sync) {
     if (!ctx || !d || !out) return GLX_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     const uint64_t S = d->n_sites, N = d->n_samples;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    if (!d->host_err) CU(cudaHostAlloc((void**)&d->host_err, 8, cudaHostAllocDefault));
     if (S * N) {
         CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->rnc, d->O.rnc, S * N * 2, cudaMemcpyDeviceToHost, st));
@@ -742,8 +755,44 @@ int glx_download(glx_ctx* ctx, glx_dev_batch* d, glx_out* out) {
     }
     for (uint32_t k = 0; k < d->n_fields; k++)
         if (d->fld_total[k]) CU(cudaMemcpyAsync(out->fld[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpyAsync(d->host_err, d->O.error, 8, cudaMemcpyDeviceToHost, st));
+    if (sync) CU(cudaStreamSynchronize(st));
     return GLX_OK;
+}
+
+// status of a batch whose (asynchronous) download has completed
+int glx_status(glx_ctx* ctx, glx_dev_batch* d) {
+    if (!ctx || !d || !d->host_err) return GLX_E_INVALID;
+    const unsigned long long w = *d->host_err;
+    if (w == ~0ull) return GLX_OK;
+    const int code = (int)(w & 0xff);
+    char buf[160];
+    snprintf(buf, sizeof buf, "genotyper: site %llu failed with status %d (first failing site of the batch)", w >> 8, -code);
+    ctx->err = buf;
+    return code == 101 ? GLX_E_UNSUPPORTED : -code;
+}
+
+void* glx_stream_create(glx_ctx* ctx) {
+    if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return (void*)s;
+}
+void glx_stream_destroy(glx_ctx* ctx, void* s) {
+    if (ctx && s) {
+        cudaSetDevice(ctx->device);
+        cudaStreamDestroy((cudaStream_t)s);
+    }
+}
+int glx_stream_sync(glx_ctx* ctx, void* s) {
+    if (!ctx) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(s ? (cudaStream_t)s : ctx->stream));
+    return GLX_OK;
+}
+int glx_host_register(void* p, size_t bytes) { return (!p || !bytes || cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) ? GLX_OK : GLX_E_CUDA; }
+void glx_host_unregister(void* p) {
+    if (p) cudaHostUnregister(p);
 }
 
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* d, int on) {

@@ -263,4 +263,6 @@ Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, Pac
 // opaque handle of include/glx_host.h
 struct glxh_batch {
     glx::PackedBatch b;
+    bool pinned = false;
+    std::vector<void*> pinned_ptrs;
 };

@@ -8,6 +8,8 @@
 // provided by the CUDA translation unit (glx_device.cu)
 extern "C" void* glx_pinned_alloc(size_t bytes);
 extern "C" void glx_pinned_free(void* p);
+extern "C" int glx_host_register(void* p, size_t bytes);
+extern "C" void glx_host_unregister(void* p);
 
 struct glxh_out {
     glx_out out{};
@@ -129,7 +131,37 @@ int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, gl
     return GLX_OK;
 }
 
-void glxh_batch_free(glxh_batch* b) { delete b; }
+// Page-lock every array of the batch so that glx_upload's copies run at PCIe rate and asynchronously
+// (the north star's "columnar pinned buffers"). Undone by glxh_batch_free.
+int glxh_batch_pin(glxh_batch* hb) {
+    if (!hb) return GLX_E_INVALID;
+    if (hb->pinned) return GLX_OK;
+    glx::PackedBatch& b = hb->b;
+    int rc = GLX_OK;
+    auto pin = [&](auto& v) {
+        if (v.empty() || rc != GLX_OK) return;
+        void* p = (void*)v.data();
+        if (glx_host_register(p, v.size() * sizeof(v[0])) != GLX_OK) rc = GLX_E_CUDA;
+        else hb->pinned_ptrs.push_back(p);
+    };
+    pin(b.ds_rec_off); pin(b.r_beg); pin(b.r_end); pin(b.r_maxend); pin(b.r_qual); pin(b.r_n_allele); pin(b.r_flags); pin(b.r_filt); pin(b.r_gt);
+    pin(b.r_allele_off); pin(b.col_val); pin(b.col_len); pin(b.pool); pin(b.al_len); pin(b.al_flags); pin(b.al_prefix); pin(b.al_str); pin(b.al_pool);
+    pin(b.s_beg); pin(b.s_end); pin(b.s_qbeg); pin(b.s_qend); pin(b.s_n_allele); pin(b.s_mono); pin(b.s_allele_off); pin(b.s_is_indel);
+    pin(b.s_hom_prior); pin(b.s_lost_prior); pin(b.s_unif_off); pin(b.u_beg); pin(b.u_end); pin(b.u_to); pin(b.u_len); pin(b.u_prefix); pin(b.u_str);
+    pin(b.u_pool);
+    for (uint32_t k = 0; k < b.cfg.n_fields; k++) {
+        pin(b.fld_cnt[k]);
+        pin(b.fld_off[k]);
+    }
+    hb->pinned = rc == GLX_OK;
+    return rc;
+}
+
+void glxh_batch_free(glxh_batch* b) {
+    if (!b) return;
+    for (void* p : b->pinned_ptrs) glx_host_unregister(p);
+    delete b;
+}
 const glx_config* glxh_config(const glxh_batch* b) { return &b->b.cfg; }
 const glx_records* glxh_records(const glxh_batch* b) { return &b->b.recs; }
 const glx_sites* glxh_sites(const glxh_batch* b) { return &b->b.sites; }

@@ -212,6 +212,20 @@ uint64_t glx_out_bytes(const glx_dev_batch* dev);
 uint64_t glx_in_bytes(const glx_dev_batch* dev);
 int glx_launch_count(const glx_dev_batch* dev); /* kernels per glx_launch */
 void glx_free_batch(glx_ctx* ctx, glx_dev_batch* dev);
+/* Asynchronous forms for pipelining successive range batches (the reference overlaps retrieval, genotyping and
+ * writing with a thread pool and futures, src/service.cc:344-418): all work of one batch goes onto `stream`
+ * (cudaStream_t from glx_stream_create); with sync == 0 the calls return once the work is enqueued, host arrays
+ * must stay valid until glx_stream_sync, and glx_status reports the batch's error word after its download landed.
+ * Host arrays should be page-locked (glx_pinned_alloc / glx_host_register) for the copies to overlap. */
+int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, void* stream, int sync,
+                  glx_dev_batch** dev);
+int glx_download_on(glx_ctx* ctx, glx_dev_batch* dev, glx_out* out, void* stream, int sync);
+int glx_status(glx_ctx* ctx, glx_dev_batch* dev);
+void* glx_stream_create(glx_ctx* ctx);
+void glx_stream_destroy(glx_ctx* ctx, void* stream);
+int glx_stream_sync(glx_ctx* ctx, void* stream);
+int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
+void glx_host_unregister(void* p);
 /* Measurement aid: record CUDA events around each kernel of glx_launch on the launching stream;
  * glx_kernel_ms waits for the last launch and returns the tiled (fast-path) and general kernel durations. */
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);

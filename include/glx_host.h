@@ -33,6 +33,8 @@ int glxh_batch_from_text(const char* preset, const char* config_text, const char
  * The shards' output columns concatenate, in order, to the unsharded batch's. */
 int glxh_partition_sites(const glxh_batch* b, int n_parts, uint32_t* bounds);
 int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, glxh_batch** ans, char* err, size_t errlen);
+/* page-lock the batch's arrays (cudaHostRegister) so uploads run at PCIe rate and can overlap other batches */
+int glxh_batch_pin(glxh_batch* b);
 void glxh_batch_free(glxh_batch* b);
 const glx_config* glxh_config(const glxh_batch* b);
 const glx_records* glxh_records(const glxh_batch* b);
