@@ -226,6 +226,8 @@ struct glx_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;                      // worklist kernels of chunk j run here while the tiled kernel of chunk j+1 runs
     cudaEvent_t chunk_ev[GLX_MAX_CHUNKS + 2] = {};   // tiled(chunk j) done / aux drained
+    unsigned long long* host_err_pool = nullptr;     // pinned error words handed to batches round-robin (allocating pinned
+    unsigned host_err_next = 0;                      // memory per batch would synchronise the device and break pipelining)
     std::string err;
     int sm_count = 0;
     // freed batch arenas are kept for the next batch of the same range stream (cudaMalloc/cudaFree of GB-sized
@@ -370,6 +372,10 @@ int glx_create(glx_ctx** out, int device) {
             delete ctx;
             return GLX_E_CUDA;
         }
+    if (cudaHostAlloc((void**)&ctx->host_err_pool, 64 * 8, cudaHostAllocDefault) != cudaSuccess) {
+        delete ctx;
+        return GLX_E_CUDA;
+    }
     *out = ctx;
     return GLX_OK;
 }
@@ -381,6 +387,7 @@ void glx_destroy(glx_ctx* ctx) {
         if (c.p) cudaFree(c.p);
     for (auto& e : ctx->chunk_ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->host_err_pool) cudaFreeHost(ctx->host_err_pool);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -402,7 +409,7 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
     if (ctx) cudaSetDevice(ctx->device);
     for (auto& ev : d->ev)
         if (ev) cudaEventDestroy(ev);
-    if (d->host_err) cudaFreeHost(d->host_err);
+
     if (ctx) {
         ctx->give(d->in_base, d->in_alloc);
         ctx->give(d->out_base, d->out_alloc);
@@ -744,7 +751,7 @@ int glx_download_on(glx_ctx* ctx, glx_dev_batch* d, glx_out* out, void* stream_,
     CU(cudaSetDevice(ctx->device));
     const uint64_t S = d->n_sites, N = d->n_samples;
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
-    if (!d->host_err) CU(cudaHostAlloc((void**)&d->host_err, 8, cudaHostAllocDefault));
+    if (!d->host_err) d->host_err = ctx->host_err_pool + (ctx->host_err_next++ & 63);
     if (S * N) {
         CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->rnc, d->O.rnc, S * N * 2, cudaMemcpyDeviceToHost, st));
