@@ -122,8 +122,10 @@ def lib():
     L.glx_synchronize.restype = C.c_int
     L.glx_set_profile.argtypes = [vp, vp, C.c_int]
     L.glx_set_profile.restype = C.c_int
-    L.glx_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.glx_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.glx_kernel_ms.restype = C.c_int
+    L.glx_work_count.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.glx_work_count.restype = C.c_int
     L.glx_stream.argtypes = [vp]
     L.glx_stream.restype = vp
     _lib = L
@@ -298,10 +300,16 @@ class DeviceBatch:
         self.ctx._check(lib().glx_set_profile(self.ctx.handle, self.handle, 1 if on else 0))
 
     def kernel_ms(self):
-        """(tiled kernel ms, general kernel ms) of the last launch, from CUDA events on the launching stream."""
-        a, b = C.c_float(), C.c_float()
-        self.ctx._check(lib().glx_kernel_ms(self.ctx.handle, self.handle, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        """(resolve, tiled, single-record worklist, general worklist) kernel ms of the last launch, from CUDA events on
+        the launching stream."""
+        ms = (C.c_float * 4)()
+        self.ctx._check(lib().glx_kernel_ms(self.ctx.handle, self.handle, ms))
+        return tuple(ms)
+
+    def work_count(self):
+        n = C.c_uint64()
+        self.ctx._check(lib().glx_work_count(self.ctx.handle, self.handle, C.byref(n)))
+        return n.value
 
     @property
     def out_bytes(self):

@@ -311,7 +311,7 @@ struct glx_dev_batch {
     char* in_base = nullptr;
     char* out_base = nullptr;
     size_t in_bytes = 0, out_bytes = 0, in_alloc = 0, out_alloc = 0;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // around resolve / tiled / single / general
     bool profile = false;
     uint32_t n_sites = 0, n_samples = 0, n_fields = 0;
     uint64_t n_cells = 0;
@@ -687,6 +687,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             d->launches_per_call++;
             CU(cudaGetLastError());
         }
+        if (d->profile) CU(cudaEventRecord(d->ev[1], st));
         // The tile grid is launched in chunks: the worklist kernels of chunk j (latency-bound gathers) run on the aux
         // stream while the tiled kernel of chunk j+1 (store-heavy) runs on the launching stream.
         const uint32_t n_regions = d->n_sample_blocks * d->n_site_tiles;
@@ -706,26 +707,35 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             }
             const uint32_t nreg = c1 - c0;
             const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
+            if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[2], st));
             glx_cells_single_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1);
+            if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[3], st));
             const uint32_t g2 = nreg < (uint32_t)d->general_blocks ? nreg : (uint32_t)d->general_blocks;
             glx_cells_general_kernel<<<g2, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, d->n_cells, d->cnt_scratch, d->max_slots);
             d->launches_per_call += 2;
             CU(cudaGetLastError());
         }
-        if (d->profile) CU(cudaEventRecord(d->ev[1], st));
+        if (d->profile && n_chunks > 1) {
+            CU(cudaEventRecord(d->ev[2], st));
+            CU(cudaEventRecord(d->ev[3], st));
+        }
         if (n_chunks > 1) {  // join
             CU(cudaEventRecord(ctx->chunk_ev[GLX_MAX_CHUNKS], ctx->aux));
             CU(cudaStreamWaitEvent(st, ctx->chunk_ev[GLX_MAX_CHUNKS], 0));
         }
     } else {
-        if (d->profile) CU(cudaEventRecord(d->ev[1], st));
+        if (d->profile) {
+            CU(cudaEventRecord(d->ev[1], st));
+            CU(cudaEventRecord(d->ev[2], st));
+            CU(cudaEventRecord(d->ev[3], st));
+        }
         if (d->n_cells) {
             glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots);
             d->launches_per_call++;
             CU(cudaGetLastError());
         }
     }
-    if (d->profile) CU(cudaEventRecord(d->ev[2], st));
+    if (d->profile) CU(cudaEventRecord(d->ev[4], st));
     return GLX_OK;
 }
 
@@ -812,15 +822,25 @@ int glx_set_profile(glx_ctx* ctx, glx_dev_batch* d, int on) {
     return GLX_OK;
 }
 
-int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* d, float* tiled_ms, float* general_ms) {
-    if (!ctx || !d || !d->profile) return GLX_E_INVALID;
+int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* d, float ms[4]) {
+    if (!ctx || !d || !d->profile || !ms) return GLX_E_INVALID;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaEventSynchronize(d->ev[2]));
-    float a = 0, b = 0;
-    CU(cudaEventElapsedTime(&a, d->ev[0], d->ev[1]));
-    CU(cudaEventElapsedTime(&b, d->ev[1], d->ev[2]));
-    if (tiled_ms) *tiled_ms = a;
-    if (general_ms) *general_ms = b;
+    CU(cudaEventSynchronize(d->ev[4]));
+    for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], d->ev[i], d->ev[i + 1]));
+    return GLX_OK;
+}
+
+// cells the tiled kernel handed to the worklist kernels in the last launch (synchronises the context stream)
+int glx_work_count(glx_ctx* ctx, glx_dev_batch* d, uint64_t* n) {
+    if (!ctx || !d || !n) return GLX_E_INVALID;
+    *n = 0;
+    if (!d->plan.enabled || !d->n_cells) return GLX_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
+    std::vector<uint32_t> h(n_regions);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h.data(), d->n_work, n_regions * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t v : h) *n += v;
     return GLX_OK;
 }
 

@@ -226,10 +226,12 @@ void glx_stream_destroy(glx_ctx* ctx, void* stream);
 int glx_stream_sync(glx_ctx* ctx, void* stream);
 int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
 void glx_host_unregister(void* p);
-/* Measurement aid: record CUDA events around each kernel of glx_launch on the launching stream;
- * glx_kernel_ms waits for the last launch and returns the tiled (fast-path) and general kernel durations. */
+/* Measurement aids: record CUDA events around each kernel of glx_launch on the launching stream; glx_kernel_ms waits
+ * for the last launch and returns the durations of {record resolve, tiled fast path, single-record worklist, general
+ * worklist} kernels; glx_work_count = cells the tiled kernel left to the worklist kernels. */
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);
-int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float* tiled_ms, float* general_ms);
+int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[4]);
+int glx_work_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);
 void* glx_stream(glx_ctx* ctx); /* the context's cudaStream_t */
 /* pinned host memory for caller-owned buffers (cudaHostAlloc) */
 void* glx_pinned_alloc(size_t bytes);

@@ -49,7 +49,7 @@ def main():
         for r in rows[2:]:
             try:
                 data.append((int(r[ist] or 0), int(r[ia]), r[isrc]))
-            except ValueError:
+            except (ValueError, IndexError):
                 pass
         tot = sum(d[0] for d in data) or 1
         print("### hottest SASS instructions by stall samples\n")
