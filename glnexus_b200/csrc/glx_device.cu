@@ -171,11 +171,11 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
 // lone variant record (genotype_cell_single) needs no scratch and few registers, so this kernel runs at high
 // occupancy; a cell it declines has its flag cleared in place and is left to the general kernel.
 __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, uint2* __restrict__ worklist,
-                                                               const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions) {
+                                                               const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint32_t region_cells) {
     const uint32_t N = S.n_samples;
     for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
         const uint32_t n_items = n_work[reg];
-        uint2* __restrict__ w = worklist + (size_t)reg * (GLX_TILE_SITES * GLX_TILE_THREADS);
+        uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
             if (!(e.y & GLX_WORK_SINGLE)) continue;
@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, c
 // the tiled kernel filled (cell id + the lane's record cursor; region r holds n_work[r] entries) and takes the cells
 // the single-record pass left; without one it takes every cell of the batch and finds the cursor by binary search.
 __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint2* __restrict__ worklist,
-                                                                const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint64_t n_all,
-                                                                uint8_t* __restrict__ cnt_scratch, uint32_t max_slots) {
+                                                                const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint32_t region_cells,
+                                                                uint64_t n_all, uint8_t* __restrict__ cnt_scratch, uint32_t max_slots) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint8_t* cnt = cnt_scratch + tid;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
     if (worklist) {
         for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
             const uint32_t n_items = n_work[reg];
-            const uint2* __restrict__ w = worklist + (size_t)reg * (GLX_TILE_SITES * GLX_TILE_THREADS);
+            const uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
             for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
                 const uint2 e = w[it];
                 if (e.y & GLX_WORK_SINGLE) continue;  // finished by glx_cells_single_kernel
@@ -331,6 +331,7 @@ struct glx_dev_batch {
     uint32_t* n_work = nullptr;
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
+    uint32_t samples_per_cta = GLX_TILE_THREADS;  // one sample per lane
     typedef void (*tiled_fn)(const DCfg, const FastPlan, const DRecs, const DSites, const DOut, const int32_t*, const uint32_t*, uint2*, uint32_t*, uint32_t,
                              uint32_t);
     tiled_fn tiled_kernel = nullptr;  // signature-specialised tiled kernel, or the dynamic one
@@ -606,17 +607,35 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     }
     d->plan = make_fast_plan(d->cfg);
     if (d->force_general) d->plan.enabled = 0;
-    d->n_sample_blocks = (uint32_t)((N + GLX_TILE_THREADS - 1) / GLX_TILE_THREADS);
+    {
+        uint32_t nf;
+        uint64_t modes, nums, nrvs;
+        d->tiled_kernel = glx_cells_tiled_kernel;
+        d->tiled_smem = (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4;
+        const char* dyn = getenv("GLX_FORCE_DYNAMIC_TILED");
+        if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
+            auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
+            if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant>;
+                d->tiled_smem = 0;
+            } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk>;
+                d->tiled_smem = 0;
+            }
+        }
+    }
+    d->n_sample_blocks = (uint32_t)((N + d->samples_per_cta - 1) / d->samples_per_cta);
     d->n_site_tiles = (uint32_t)((S + GLX_TILE_SITES - 1) / GLX_TILE_SITES);
     if (d->plan.enabled && d->n_cells) {
         const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
-        d->worklist_bytes = n_regions * (GLX_TILE_SITES * GLX_TILE_THREADS) * 8 + (n_regions + 64) * 4;
+        const size_t region_cells = (size_t)GLX_TILE_SITES * d->samples_per_cta;
+        d->worklist_bytes = n_regions * region_cells * 8 + (n_regions + 64) * 4;
         e = ctx->take((void**)&d->worklist, d->worklist_bytes);
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
             return cuda_fail(ctx, e, "cudaMalloc(worklist)");
         }
-        d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * (GLX_TILE_SITES * GLX_TILE_THREADS));
+        d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * region_cells);
         const size_t blob_part = ((Rn + 1) * blob_words(d->plan.n_rv) * 4 + 255) & ~(size_t)255;
         const size_t cur_part = (((size_t)d->n_site_tiles * N + 1) * 4 + 255) & ~(size_t)255;
         d->blob_bytes = blob_part + cur_part + ((size_t)d->n_site_tiles + 1) * 4;
@@ -641,23 +660,6 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         }
     }
     d->n_datasets = (uint32_t)D;
-    {
-        uint32_t nf;
-        uint64_t modes, nums, nrvs;
-        d->tiled_kernel = glx_cells_tiled_kernel;
-        d->tiled_smem = (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4;
-        const char* dyn = getenv("GLX_FORCE_DYNAMIC_TILED");
-        if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
-            auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
-            if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
-                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant>;
-                d->tiled_smem = 0;
-            } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
-                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk>;
-                d->tiled_smem = 0;
-            }
-        }
-    }
     e = sync ? cudaStreamSynchronize(up) : cudaSuccess;  // after a synchronous upload the caller's host arrays may be released
     if (e != cudaSuccess) {
         glx_free_batch(ctx, d);
@@ -708,10 +710,12 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             const uint32_t nreg = c1 - c0;
             const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[2], st));
-            glx_cells_single_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1);
+            const uint32_t region_cells = GLX_TILE_SITES * d->samples_per_cta;
+            glx_cells_single_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells);
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[3], st));
             const uint32_t g2 = nreg < (uint32_t)d->general_blocks ? nreg : (uint32_t)d->general_blocks;
-            glx_cells_general_kernel<<<g2, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, d->n_cells, d->cnt_scratch, d->max_slots);
+            glx_cells_general_kernel<<<g2, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->n_cells, d->cnt_scratch,
+                                                         d->max_slots);
             d->launches_per_call += 2;
             CU(cudaGetLastError());
         }
@@ -730,7 +734,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             CU(cudaEventRecord(d->ev[3], st));
         }
         if (d->n_cells) {
-            glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots);
+            glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots);
             d->launches_per_call++;
             CU(cudaGetLastError());
         }

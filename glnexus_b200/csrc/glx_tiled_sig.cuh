@@ -141,7 +141,11 @@ struct TiledLane {
         if constexpr (Sig::mode(K) == FM_VEC) {
             if (!done) return;
             constexpr uint32_t cnt = Sig::nrv(K);
+#ifdef GLX_ABLATE_WRAP
+            int32_t* __restrict__ o = O.fld[K] + ((((unsigned long long)s * N + sample) * cnt) & ((1ull << 21) - 1));
+#else
             int32_t* __restrict__ o = O.fld[K] + ((unsigned long long)s * N + sample) * cnt;
+#endif
             int32_t v[cnt ? cnt : 1];
 #pragma unroll
             for (uint32_t j = 0; j < cnt; j++) v[j] = ref ? rv[r0 + j] : cen;
@@ -183,7 +187,11 @@ struct TiledLane {
                     st[j] = v;
                 }
                 __syncwarp();
+#ifdef GLX_ABLATE_WRAP
+                int32_t* __restrict__ ow = O.fld[K] + ((off + (unsigned long long)(sample - lane) * count) & ((1ull << 21) - 1));
+#else
                 int32_t* __restrict__ ow = O.fld[K] + off + (unsigned long long)(sample - lane) * count;
+#endif
                 const uint32_t total = nvalid * count;
                 for (uint32_t e = lane; e < total; e += 32) ow[e] = stage[e];
                 __syncwarp();
@@ -191,7 +199,11 @@ struct TiledLane {
             }
 #endif
             if (!done) return;
+#ifdef GLX_ABLATE_WRAP
+            int32_t* __restrict__ o = O.fld[K] + ((off + (unsigned long long)sample * count) & ((1ull << 21) - 1));
+#else
             int32_t* __restrict__ o = O.fld[K] + off + (unsigned long long)sample * count;
+#endif
             if (count == 2 && !(off & 1)) {
                 *reinterpret_cast<int2*>(o) = make_int2(x0, x1);
             } else {
@@ -330,6 +342,7 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
         }
     }
 }
+
 #endif
 
 // instantiated signatures (mode, number, cached values per field; field 0 in the low nibble)
