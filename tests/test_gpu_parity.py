@@ -103,3 +103,51 @@ def test_gpu_empty_and_ragged(ctx):
     ctx.genotype_batch(b, got)
     d = compare_outs(got, ref, b.n_fields)
     assert not d, "\n".join(d)
+
+
+def test_gpu_pipelined_async_api(ctx):
+    """glx_upload_on / glx_launch / glx_download_on on two streams, two batches in flight (the e2e mode of bench.py):
+    every batch's columns must still equal the oracle, and glx_status must report clean error words."""
+    batches = [synth_cases.make("c3", n_samples=512, n_sites=1500, region_len=96000, seed=20200211 + i).pin() for i in range(3)]
+    refs = []
+    for b in batches:
+        r = b.alloc_out()
+        oracle_lib.genotype_batch(b, r, threads=8)
+        refs.append(r)
+    outs = [b.alloc_out(pinned=True) for b in batches]
+    streams = [ctx.stream_create(), ctx.stream_create()]
+    devs = []
+    for rep in range(2):  # second round re-uses the cached arenas
+        devs = []
+        for i, b in enumerate(batches):
+            st = streams[i & 1]
+            d = ctx.upload_async(b, st)
+            d.launch(st)
+            d.download_async(outs[i], st)
+            devs.append(d)
+        for st in streams:
+            ctx.stream_sync(st)
+        for i, d in enumerate(devs):
+            d.status()
+            d.close()
+            diffs = compare_outs(outs[i], refs[i], batches[i].n_fields)
+            assert not diffs, f"batch {i} round {rep}:\n" + "\n".join(diffs)
+    for st in streams:
+        ctx.stream_destroy(st)
+
+
+def test_gpu_error_status_propagates(ctx):
+    """A malformed record (PL vector of the wrong length on a revised call) must fail the batch with the oracle's status."""
+    from glnexus_b200 import Batch, GlxError
+    hdr = ("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"\">\n##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"\">\n"
+           "##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"\">\n##FORMAT=<ID=AD,Number=R,Type=Integer,Description=\"\">\n"
+           "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"\">\n##contig=<ID=21,length=48129895>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\n")
+    rec = "21\t1000\t.\tT\tA\t50\t.\t.\tGT:GQ:DP:AD:PL\t1/1:30:20:0,20:100,30\n"  # 2 PL values, 3 expected
+    sites = "site\t21\t999\t1000\t100\t0\t0.0\nallele\tT\t999\t1000\tT\t0\tnan\nallele\tA\t999\t1000\tA\t88\t0.01\n"
+    b = Batch.from_text(sites, [("A", hdr + rec)], preset="DeepVariant")
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    with pytest.raises(oracle_lib.OracleError) as oe:
+        oracle_lib.genotype_batch(b, ref)
+    with pytest.raises(GlxError) as ge:
+        ctx.genotype_batch(b, got)
+    assert ge.value.code == oe.value.code == -1
