@@ -151,3 +151,25 @@ def test_gpu_error_status_propagates(ctx):
     with pytest.raises(GlxError) as ge:
         ctx.genotype_batch(b, got)
     assert ge.value.code == oe.value.code == -1
+
+
+def test_gpu_full_size_configs1(ctx):
+    """BASELINE configs[1] at FULL size (1,000 samples x 50,000 sites = 5e7 cells, the bench workload): every output
+    column bit-exact against the oracle (all host threads), plus size-independent properties of the columns."""
+    import os
+    b = synth_cases.make("c2", n_samples=1000, n_sites=50000, region_len=50000)
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    oracle_lib.genotype_batch(b, ref, threads=max(4, len(os.sched_getaffinity(0))))
+    ctx.genotype_batch(b, got)
+    ga, ra = got.arrays(), ref.arrays()
+    for k in ra:
+        assert np.array_equal(ga[k], ra[k]), k
+    gt = ga["gt"].reshape(-1, 2)
+    rnc = ga["rnc"].reshape(-1, 2)
+    assert (gt[:, 0] <= gt[:, 1]).all()                       # slots ordered, missing first (genotyper.cc:862-867)
+    assert ((gt >= 0) == (rnc == ord("."))).all()               # an allele is called exactly where RNC is n/a
+    used = np.zeros(b.n_sites, dtype=np.uint32)                 # allele_used = OR over the site's called alleles
+    g = ga["gt"].reshape(b.n_sites, -1)
+    for a in range(3):
+        used |= ((g == a).any(axis=1).astype(np.uint32) << a)
+    assert np.array_equal(used, ga["allele_used"])
