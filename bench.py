@@ -195,6 +195,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Libraries (NCCL prints its version banner) write to fd 1; keep stdout clean for the one JSON line.
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import glnexus_b200
@@ -364,7 +368,7 @@ def main():
             line["cpu_baseline"] = cb
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     dev.close()
     ctx.close()
     if world > 1:
