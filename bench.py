@@ -268,32 +268,50 @@ def main():
     batch.pin()
     e2e_steps = args.e2e_steps or max(4, min(args.steps, 8))
     outs = [batch.alloc_out(pinned=True), batch.alloc_out(pinned=True)]
+    outs16 = [batch.alloc_out16(), batch.alloc_out16()]
     streams = [ctx.stream_create(), ctx.stream_create()]
 
-    def pipelined(n):
+    def pipelined(n, narrow):
         slots = [None, None]
+
+        def retire(k):
+            ctx.stream_sync(streams[k])
+            slots[k].status()
+            if narrow:
+                slots[k].narrow_finish(outs16[k])
+            slots[k].close()
+            slots[k] = None
+
         for i in range(n):
             k = i & 1
             if slots[k] is not None:
-                ctx.stream_sync(streams[k])
-                slots[k].status()
-                slots[k].close()
+                retire(k)
             dv = ctx.upload_async(batch, streams[k])
             dv.launch(streams[k])
-            dv.download_async(outs[k], streams[k])
+            if narrow:
+                dv.download_narrow_async(outs16[k], streams[k])
+            else:
+                dv.download_async(outs[k], streams[k])
             slots[k] = dv
         for k in (0, 1):
             if slots[k] is not None:
-                ctx.stream_sync(streams[k])
-                slots[k].status()
-                slots[k].close()
+                retire(k)
 
-    pipelined(2)  # warm the arena cache of both slots
+    # e2e (headline): integer columns cross PCIe as int16 wherever every value of the field fits (the type BCF would store)
+    pipelined(2, True)  # warm the arena cache of both slots
     barrier()
     te = time.time()
-    pipelined(e2e_steps)
+    pipelined(e2e_steps, True)
     torch.cuda.synchronize()
     e2e_s = time.time() - te
+    d2h_narrow = outs16[0].narrow_nbytes() + batch.n_sites * 5
+    # the same with full int32 columns
+    pipelined(2, False)
+    barrier()
+    tw = time.time()
+    pipelined(e2e_steps, False)
+    torch.cuda.synchronize()
+    e2e_wide_s = time.time() - tw
     # one synchronous call (latency of a single batch, nothing overlapped)
     ctx.genotype_batch(batch, outs[0])
     ts = time.time()
@@ -351,8 +369,11 @@ def main():
             "config": {"workload": workload_name(args.workload, n_samples, n_sites), "preset": synth_cases.SHAPES[shape][0],
                        "cells_per_gpu": cells, "records_per_gpu": int(batch.n_records), "variant_records_per_gpu": int(batch.variant_records),
                        "l2": "flushed between timed steps (256 MiB write, untimed); outputs (%.2f GB/step) exceed L2" % (out_b / 1e9)},
-            "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "mode": "pinned host buffers, batches pipelined 2 deep on 2 streams", "single_sync_call_cells_per_s": cells / sync_call_s},
+            "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_narrow), "steps": e2e_steps,
+                    "mode": "pinned host buffers, batches pipelined 2 deep on 2 streams; integer columns delivered as int16 (BCF 16-bit "
+                            "sentinels) where every value of the field fits, int32 otherwise (glx_download_narrow_on)",
+                    "int32_columns_cells_per_s": cells_all * e2e_steps / e2e_wide_s if world == 1 else None, "int32_d2h_bytes_per_step": int(d2h),
+                    "single_sync_call_cells_per_s": cells / sync_call_s},
             "gpu_launches": launches,
             "kernels": {"resolve_ms": kmean[0], "tiled_ms": kmean[1], "single_ms": kmean[2], "general_ms": kmean[3], "worklist_cells": int(n_worklist),
                         "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)},

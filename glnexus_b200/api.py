@@ -54,6 +54,20 @@ def lib():
     L.glxh_partition_sites.restype = C.c_int
     L.glxh_batch_slice.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), cp, sz]
     L.glxh_batch_slice.restype = C.c_int
+    L.glxh_out16_alloc.argtypes = [vp, C.c_int]
+    L.glxh_out16_alloc.restype = vp
+    L.glxh_out16_free.argtypes = [vp]
+    L.glxh_out16_free.restype = None
+    L.glxh_out16_struct.argtypes = [vp]
+    L.glxh_out16_struct.restype = vp
+    L.glxh_out16_array.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.glxh_out16_array.restype = C.c_int
+    L.glxh_out16_widen.argtypes = [vp, vp]
+    L.glxh_out16_widen.restype = C.c_int
+    L.glx_download_narrow_on.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.glx_download_narrow_on.restype = C.c_int
+    L.glx_narrow_finish.argtypes = [vp, vp, vp]
+    L.glx_narrow_finish.restype = C.c_int
     L.glxh_batch_pin.argtypes = [vp]
     L.glxh_batch_pin.restype = C.c_int
     L.glx_upload_on.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
@@ -182,6 +196,44 @@ class Out:
             pass
 
 
+class Out16:
+    """Host buffers of the narrow download (glx_out16): int16 columns where every value of the field fits."""
+
+    def __init__(self, batch, pinned=True):
+        self._batch = batch
+        self.handle = lib().glxh_out16_alloc(batch.handle, 1 if pinned else 0)
+        if not self.handle:
+            raise MemoryError("glxh_out16_alloc")
+        self.ptr = lib().glxh_out16_struct(self.handle)
+
+    def widen(self, out):
+        """Expand into an Out (int32 columns, 32-bit sentinels)."""
+        rc = lib().glxh_out16_widen(self.handle, out.ptr)
+        if rc != GLX_OK:
+            raise GlxError(rc, "glxh_out16_widen")
+        return out
+
+    def narrow_nbytes(self):
+        """Bytes that crossed PCIe for GT, RNC and the 16-bit columns."""
+        tot = 0
+        for which in (0, 1) + tuple(16 + k for k in range(self._batch.n_fields)):
+            p, n = C.c_void_p(), C.c_uint64()
+            lib().glxh_out16_array(self.handle, which, C.byref(p), C.byref(n))
+            tot += n.value
+        return tot
+
+    def close(self):
+        if self.handle:
+            lib().glxh_out16_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Batch:
     """One contig-range batch: flattened config + columnar record store + unified sites."""
 
@@ -253,6 +305,9 @@ class Batch:
     def alloc_out(self, pinned=False):
         return Out(self, pinned)
 
+    def alloc_out16(self, pinned=True):
+        return Out16(self, pinned)
+
     def assemble_vcf(self, out):
         t = C.c_void_p()
         err = C.create_string_buffer(1024)
@@ -291,6 +346,13 @@ class DeviceBatch:
 
     def download_async(self, out, stream):
         self.ctx._check(lib().glx_download_on(self.ctx.handle, self.handle, out.ptr, C.c_void_p(stream), 0))
+
+    def download_narrow_async(self, out16, stream):
+        self.ctx._check(lib().glx_download_narrow_on(self.ctx.handle, self.handle, out16.ptr, C.c_void_p(stream), 0))
+
+    def narrow_finish(self, out16):
+        """After the stream is synchronised: fix the per-field widths (fetches int32 for fields that did not fit)."""
+        self.ctx._check(lib().glx_narrow_finish(self.ctx.handle, self.handle, out16.ptr))
 
     def status(self):
         """Error word of a batch whose asynchronous download has been synchronised."""

@@ -217,6 +217,29 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
     }
 }
 
+// int32 column -> int16 with BCF's 16-bit sentinels; *overflow is set when some value does not fit
+__global__ void __launch_bounds__(256) glx_narrow_kernel(const int32_t* __restrict__ in, int16_t* __restrict__ out, uint64_t n, uint32_t* __restrict__ overflow) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    auto conv = [&](int32_t v) -> int16_t {
+        if (v == GLXD_INT_MISSING) return (int16_t)0x8000;
+        if (v == GLXD_INT_VEND) return (int16_t)0x8001;
+        if (v < -32760 || v > 32767) {  // -32768..-32761 are reserved in BCF
+            bad = true;
+            return 0;
+        }
+        return (int16_t)v;
+    };
+    const uint64_t n4 = n / 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int4 v = reinterpret_cast<const int4*>(in)[i];
+        const int16_t a = conv(v.x), b = conv(v.y), c = conv(v.z), d = conv(v.w);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2((uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16), (uint32_t)(uint16_t)c | ((uint32_t)(uint16_t)d << 16));
+    }
+    for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = conv(in[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(overflow, 1u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -226,6 +249,7 @@ struct glx_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;                      // worklist kernels of chunk j run here while the tiled kernel of chunk j+1 runs
     cudaEvent_t chunk_ev[GLX_MAX_CHUNKS + 2] = {};   // tiled(chunk j) done / aux drained
+    uint32_t* host_ovf_pool = nullptr;               // pinned overflow words of the narrow download, same scheme as below
     unsigned long long* host_err_pool = nullptr;     // pinned error words handed to batches round-robin (allocating pinned
     unsigned host_err_next = 0;                      // memory per batch would synchronise the device and break pipelining)
     std::string err;
@@ -326,6 +350,10 @@ struct glx_dev_batch {
     std::vector<uint8_t> flags_dev;  // host staging that must outlive an asynchronous upload
     std::vector<int32_t> tq_host;
     unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
+    int16_t* narrow = nullptr;               // device int16 images of the integer fields + overflow words
+    size_t narrow_bytes = 0;
+    uint32_t* narrow_overflow = nullptr;     // [GLX_MAX_FIELDS] device
+    uint32_t* host_overflow = nullptr;       // pinned
     FastPlan plan;
     uint2* worklist = nullptr;     // [n_cells] (cell id, record cursor) for the general kernel
     uint32_t* n_work = nullptr;
@@ -373,7 +401,8 @@ int glx_create(glx_ctx** out, int device) {
             delete ctx;
             return GLX_E_CUDA;
         }
-    if (cudaHostAlloc((void**)&ctx->host_err_pool, 64 * 8, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void**)&ctx->host_err_pool, 64 * 8, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->host_ovf_pool, 64 * GLX_MAX_FIELDS * 4, cudaHostAllocDefault) != cudaSuccess) {
         delete ctx;
         return GLX_E_CUDA;
     }
@@ -389,6 +418,7 @@ void glx_destroy(glx_ctx* ctx) {
     for (auto& e : ctx->chunk_ev)
         if (e) cudaEventDestroy(e);
     if (ctx->host_err_pool) cudaFreeHost(ctx->host_err_pool);
+    if (ctx->host_ovf_pool) cudaFreeHost(ctx->host_ovf_pool);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -417,7 +447,9 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
         ctx->give(d->cnt_scratch, d->cnt_scratch_bytes);
         ctx->give(d->worklist, d->worklist_bytes);
         ctx->give(d->blobs, d->blob_bytes);
+        ctx->give(d->narrow, d->narrow_bytes);
     } else {
+        if (d->narrow) cudaFree(d->narrow);
         if (d->worklist) cudaFree(d->worklist);
         if (d->blobs) cudaFree(d->blobs);
         if (d->in_base) cudaFree(d->in_base);
@@ -765,7 +797,11 @@ int glx_download_on(glx_ctx* ctx, glx_dev_batch* d, glx_out* out, void* stream_,
     CU(cudaSetDevice(ctx->device));
     const uint64_t S = d->n_sites, N = d->n_samples;
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
-    if (!d->host_err) d->host_err = ctx->host_err_pool + (ctx->host_err_next++ & 63);
+    if (!d->host_err) {
+        const unsigned slot = ctx->host_err_next++ & 63;
+        d->host_err = ctx->host_err_pool + slot;
+        d->host_overflow = ctx->host_ovf_pool + (size_t)slot * GLX_MAX_FIELDS;
+    }
     if (S * N) {
         CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->rnc, d->O.rnc, S * N * 2, cudaMemcpyDeviceToHost, st));
@@ -778,6 +814,77 @@ int glx_download_on(glx_ctx* ctx, glx_dev_batch* d, glx_out* out, void* stream_,
         if (d->fld_total[k]) CU(cudaMemcpyAsync(out->fld[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(d->host_err, d->O.error, 8, cudaMemcpyDeviceToHost, st));
     if (sync) CU(cudaStreamSynchronize(st));
+    return GLX_OK;
+}
+
+static bool field_is_narrowable(const glx_dev_batch* d, uint32_t k) {
+    const DFld& f = d->cfg.f[k];
+    return f.type == GLX_TYPE_INT && f.kind != GLX_FK_FT && f.kind != GLX_FK_STRING;
+}
+
+int glx_download_narrow_on(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out, void* stream_, int sync) {
+    if (!ctx || !d || !out) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t S = d->n_sites, N = d->n_samples;
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    if (!d->host_err) {
+        const unsigned slot = ctx->host_err_next++ & 63;
+        d->host_err = ctx->host_err_pool + slot;
+        d->host_overflow = ctx->host_ovf_pool + (size_t)slot * GLX_MAX_FIELDS;
+    } else if (!d->host_overflow) {
+        d->host_overflow = ctx->host_ovf_pool + (size_t)(ctx->host_err_next++ & 63) * GLX_MAX_FIELDS;
+    }
+    if (!d->narrow) {
+        size_t b = 256;
+        for (uint32_t k = 0; k < d->n_fields; k++)
+            if (field_is_narrowable(d, k)) b += ((d->fld_total[k] * 2 + 255) & ~(size_t)255);
+        d->narrow_bytes = b;
+        cudaError_t e = ctx->take((void**)&d->narrow, b);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(narrow columns)");
+    }
+    d->narrow_overflow = reinterpret_cast<uint32_t*>(d->narrow);
+    CU(cudaMemsetAsync(d->narrow_overflow, 0, GLX_MAX_FIELDS * 4, st));
+    size_t off = 256;
+    for (uint32_t k = 0; k < d->n_fields; k++) {
+        if (!d->fld_total[k]) continue;
+        if (!field_is_narrowable(d, k)) {
+            CU(cudaMemcpyAsync(out->fld32[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
+        int16_t* dst = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(d->narrow) + off);
+        off += (d->fld_total[k] * 2 + 255) & ~(size_t)255;
+        const uint64_t n = d->fld_total[k];
+        const unsigned grid = (unsigned)std::min<uint64_t>((n / 4 + 255) / 256 + 1, (uint64_t)ctx->sm_count * 16);
+        glx_narrow_kernel<<<grid, 256, 0, st>>>(d->O.fld[k], dst, n, d->narrow_overflow + k);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out->fld16[k], dst, n * 2, cudaMemcpyDeviceToHost, st));
+    }
+    if (S * N) {
+        CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->rnc, d->O.rnc, S * N * 2, cudaMemcpyDeviceToHost, st));
+    }
+    if (S) {
+        CU(cudaMemcpyAsync(out->allele_used, d->O.allele_used, S * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->site_flags, d->O.site_flags, S, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(d->host_overflow, d->narrow_overflow, GLX_MAX_FIELDS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->host_err, d->O.error, 8, cudaMemcpyDeviceToHost, st));
+    if (sync) CU(cudaStreamSynchronize(st));
+    return GLX_OK;
+}
+
+int glx_narrow_finish(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out) {
+    if (!ctx || !d || !out || !d->host_overflow) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    for (uint32_t k = 0; k < d->n_fields; k++) {
+        if (!field_is_narrowable(d, k)) {
+            out->width[k] = 4;
+        } else if (d->host_overflow[k]) {  // some value needs 32 bits: fetch the int32 column (rare; synchronous)
+            out->width[k] = 4;
+            if (d->fld_total[k]) CU(cudaMemcpy(out->fld32[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost));
+        } else
+            out->width[k] = 2;
+    }
     return GLX_OK;
 }
 

@@ -242,6 +242,95 @@ int glxh_out_array(const glxh_out* o, int which, const void** ptr, uint64_t* nby
     return GLX_OK;
 }
 
+struct glxh_out16 {
+    glx_out16 out{};
+    bool pinned = false;
+    uint32_t n_fields = 0;
+    uint64_t n_gt = 0, n_sites = 0;
+    uint64_t n_fld[GLX_MAX_FIELDS] = {};
+};
+
+glxh_out16* glxh_out16_alloc(const glxh_batch* b, int pinned) {
+    auto* o = new glxh_out16();
+    o->pinned = pinned != 0;
+    const uint64_t S = b->b.sites.n_sites, N = b->b.sites.n_samples;
+    o->n_sites = S;
+    o->n_gt = S * N * 2;
+    o->n_fields = b->b.cfg.n_fields;
+    o->out.gt = (int8_t*)out_alloc(o->n_gt, o->pinned);
+    o->out.rnc = (uint8_t*)out_alloc(o->n_gt, o->pinned);
+    o->out.allele_used = (uint32_t*)out_alloc(S * 4, o->pinned);
+    o->out.site_flags = (uint8_t*)out_alloc(S, o->pinned);
+    for (uint32_t k = 0; k < o->n_fields; k++) {
+        o->n_fld[k] = b->b.fld_off[k].empty() ? 0 : b->b.fld_off[k].back();
+        const glx_field& f = b->b.cfg.fields[k];
+        const bool narrowable = f.type == GLX_TYPE_INT && f.kind != GLX_FK_FT && f.kind != GLX_FK_STRING;
+        o->out.fld16[k] = narrowable ? (int16_t*)out_alloc(o->n_fld[k] * 2, o->pinned) : nullptr;
+        // the 32-bit form is the fallback for fields that do not fit (pageable: rare) and the home of float / FT fields
+        o->out.fld32[k] = narrowable ? (int32_t*)malloc(o->n_fld[k] * 4 + 16) : (int32_t*)out_alloc(o->n_fld[k] * 4, o->pinned);  // untouched unless needed
+    }
+    return o;
+}
+
+void glxh_out16_free(glxh_out16* o) {
+    if (!o) return;
+    out_release(o->out.gt, o->pinned);
+    out_release(o->out.rnc, o->pinned);
+    out_release(o->out.allele_used, o->pinned);
+    out_release(o->out.site_flags, o->pinned);
+    for (uint32_t k = 0; k < GLX_MAX_FIELDS; k++) {
+        const bool narrowable = o->out.fld16[k] != nullptr;
+        out_release(o->out.fld16[k], o->pinned);
+        out_release(o->out.fld32[k], narrowable ? false : o->pinned);
+    }
+    delete o;
+}
+
+glx_out16* glxh_out16_struct(glxh_out16* o) { return &o->out; }
+
+int glxh_out16_array(const glxh_out16* o, int which, const void** ptr, uint64_t* nbytes) {
+    if (!o || !ptr || !nbytes) return GLX_E_INVALID;
+    switch (which) {
+        case 0: *ptr = o->out.gt; *nbytes = o->n_gt; return GLX_OK;
+        case 1: *ptr = o->out.rnc; *nbytes = o->n_gt; return GLX_OK;
+        case 2: *ptr = o->out.allele_used; *nbytes = o->n_sites * 4; return GLX_OK;
+        case 3: *ptr = o->out.site_flags; *nbytes = o->n_sites; return GLX_OK;
+        default: break;
+    }
+    if (which >= 48) {
+        const int k = which - 48;
+        if (k >= (int)o->n_fields) return GLX_E_INVALID;
+        *ptr = o->out.fld32[k];
+        *nbytes = o->n_fld[k] * 4;
+        return GLX_OK;
+    }
+    const int k = which - 16;
+    if (k < 0 || k >= (int)o->n_fields) return GLX_E_INVALID;
+    *ptr = o->out.fld16[k];
+    *nbytes = o->out.fld16[k] ? o->n_fld[k] * 2 : 0;
+    return GLX_OK;
+}
+
+int glxh_out16_widen(const glxh_out16* o, glx_out* wide) {
+    if (!o || !wide) return GLX_E_INVALID;
+    memcpy(wide->gt, o->out.gt, o->n_gt);
+    memcpy(wide->rnc, o->out.rnc, o->n_gt);
+    memcpy(wide->allele_used, o->out.allele_used, o->n_sites * 4);
+    memcpy(wide->site_flags, o->out.site_flags, o->n_sites);
+    for (uint32_t k = 0; k < o->n_fields; k++) {
+        if (o->out.width[k] == 2) {
+            const int16_t* s = o->out.fld16[k];
+            int32_t* d = wide->fld[k];
+            for (uint64_t i = 0; i < o->n_fld[k]; i++) {
+                const int16_t v = s[i];
+                d[i] = v == GLX_INT16_MISSING ? GLX_INT_MISSING : (v == GLX_INT16_VECTOR_END ? GLX_INT_VECTOR_END : (int32_t)v);
+            }
+        } else
+            memcpy(wide->fld[k], o->out.fld32[k], o->n_fld[k] * 4);
+    }
+    return GLX_OK;
+}
+
 int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char* err, size_t errlen) {
     if (!b || !out || !text) return GLX_E_INVALID;
     std::string o;

@@ -51,6 +51,16 @@ glx_out* glxh_out_struct(glxh_out* o);
 /* raw access for comparisons: which = 0 gt, 1 rnc, 2 allele_used, 3 site_flags, 16+k field k */
 int glxh_out_array(const glxh_out* o, int which, const void** ptr, uint64_t* nbytes);
 
+/* Host buffers for the narrow download (glx_out16): 16- and 32-bit storage per field. which = 0 gt, 1 rnc,
+ * 2 allele_used, 3 site_flags, 16+k field k as int16, 48+k field k as int32. glxh_out16_widen expands into a glx_out
+ * (int32 columns, htslib 32-bit sentinels) for consumers that want the wide form. */
+typedef struct glxh_out16 glxh_out16;
+glxh_out16* glxh_out16_alloc(const glxh_batch* b, int pinned);
+void glxh_out16_free(glxh_out16* o);
+glx_out16* glxh_out16_struct(glxh_out16* o);
+int glxh_out16_array(const glxh_out16* o, int which, const void** ptr, uint64_t* nbytes);
+int glxh_out16_widen(const glxh_out16* o, glx_out* wide);
+
 /* pVCF text from packed columns. Caller frees with glxh_free_text. */
 int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char* err, size_t errlen);
 void glxh_free_text(char* text);

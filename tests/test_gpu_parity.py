@@ -173,3 +173,47 @@ def test_gpu_full_size_configs1(ctx):
     for a in range(3):
         used |= ((g == a).any(axis=1).astype(np.uint32) << a)
     assert np.array_equal(used, ga["allele_used"])
+
+
+def test_gpu_narrow_download(ctx):
+    """glx_download_narrow_on: int16 columns (BCF 16-bit sentinels) where a field fits, int32 where it does not; widened
+    on the host they must equal the oracle's int32 columns exactly."""
+    from glnexus_b200 import Batch
+    b = synth_cases.make("c3", n_samples=768, n_sites=1200, region_len=76800).pin()
+    ref = b.alloc_out()
+    oracle_lib.genotype_batch(b, ref, threads=8)
+    st = ctx.stream_create()
+    o16, wide = b.alloc_out16(), b.alloc_out()
+    dev = ctx.upload_async(b, st)
+    dev.launch(st)
+    dev.download_narrow_async(o16, st)
+    ctx.stream_sync(st)
+    dev.status()
+    dev.narrow_finish(o16)
+    dev.close()
+    o16.widen(wide)
+    d = compare_outs(wide, ref, b.n_fields)
+    assert not d, "\n".join(d)
+    assert o16.narrow_nbytes() < 0.6 * sum(a.nbytes for k, a in ref.arrays().items() if k not in ("allele_used", "site_flags"))
+    # a field with a value beyond int16 falls back to its int32 column
+    hdr = ("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"\">\n##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"\">\n"
+           "##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"\">\n##FORMAT=<ID=AD,Number=R,Type=Integer,Description=\"\">\n"
+           "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"\">\n##contig=<ID=21,length=48129895>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\n")
+    rec = "21\t1000\t.\tT\tA\t50\t.\t.\tGT:GQ:DP:AD:PL\t0/1:30:100000:50000,50000:100,0,70000\n"
+    sites = "site\t21\t999\t1000\t100\t0\t0.0\nallele\tT\t999\t1000\tT\t0\tnan\nallele\tA\t999\t1000\tA\t88\t0.01\n"
+    b2 = Batch.from_text(sites, [("A", hdr + rec)], preset="DeepVariant")
+    ref2 = b2.alloc_out()
+    oracle_lib.genotype_batch(b2, ref2)
+    o16, wide = b2.alloc_out16(), b2.alloc_out()
+    dev = ctx.upload_async(b2, st)
+    dev.launch(st)
+    dev.download_narrow_async(o16, st)
+    ctx.stream_sync(st)
+    dev.status()
+    dev.narrow_finish(o16)
+    dev.close()
+    o16.widen(wide)
+    d = compare_outs(wide, ref2, b2.n_fields)
+    assert not d, "\n".join(d)
+    assert 100000 in wide.array(0) and 70000 in wide.array(3)
+    ctx.stream_destroy(st)
