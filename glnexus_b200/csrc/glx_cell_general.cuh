@@ -28,8 +28,11 @@ __device__ __forceinline__ int gt_unphased(int a) { return (a + 1) << 1; }
 __device__ __forceinline__ unsigned n_genotypes(unsigned n) { return (n + 1) * n / 2; }
 __device__ __forceinline__ int alleles_gt(int i, int j) { return i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j; }
 
-__device__ __forceinline__ void report_error(const DOut& O, uint32_t site, int code /* positive = -status */) {
-    atomicMin(O.error, ((unsigned long long)site << 8) | (unsigned)code);
+// The batch fails with the status the reference would return: that of the first failing site and, within it, of the
+// first failing dataset (genotype_site walks datasets in order). Cells are numbered site-major, so the minimum over
+// (cell << 8 | -status) is that error.
+__device__ __forceinline__ void report_error(const DOut& O, unsigned long long cell, int code /* positive = -status */) {
+    atomicMin(O.error, (cell << 8) | (unsigned)code);
 }
 
 // decode the inline GT pair of a single-sample record as preprocess_record sees it (genotyper.cc:44-57)
@@ -505,6 +508,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
         uint64_t b1r = ~0ull, b2r = ~0ull;
         uint64_t mono_rec = ~0ull;
         bool mono_multi = false;
+        int deferred_err = 0;
         for (uint64_t r = first; r < hi && R.beg[r] < st.qend && !err; r++) {
             if (!(R.end[r] > st.qbeg) || !record_kept(R, S, st, r)) continue;
             const uint8_t flags = R.flags[r];
@@ -524,8 +528,13 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
             }
             if (is_ref) {
                 unsigned d;
-                err = depth_get(cfg, R, r, na, true, 0, d);
-                if (err) break;
+                // update_min_ref_depth runs after every record was preprocessed/revised (genotyper.cc:312-330): its error
+                // only counts if none of those failed
+                const int de = depth_get(cfg, R, r, na, true, 0, d);
+                if (de) {
+                    if (!deferred_err) deferred_err = de;
+                    continue;
+                }
                 mrd = (mrd < 0) ? (int)d : min(mrd, (int)d);
                 if (!(flags & GLX_RF_HAPLOID) && (gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0)) ref_noncalled = true;
                 continue;
@@ -587,6 +596,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
             }
         }
 
+        if (!err) err = deferred_err;
         if (!err) {
             if ((n_var == 0 || !cfg.allow_partial) && ref_noncalled) {
                 rnc0 = rnc1 = RNC_I;
@@ -707,8 +717,10 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                 }
             } else {
                 // ---- translate_monoallelic ----
-                if (mono_multi) rnc0 = rnc1 = RNC_O;
-                else if (mono_rec == ~0ull) rnc0 = rnc1 = RNC_MONO;
+                if (mono_multi) {
+                    rnc0 = rnc1 = RNC_O;
+                    used1 = mono_rec;  // the first carrier is already in variant_records_used when the second one aborts (genotyper.cc:620-628)
+                } else if (mono_rec == ~0ull) rnc0 = rnc1 = RNC_MONO;
                 else {
                     used1 = mono_rec;
                     const uint64_t r = mono_rec;
@@ -785,7 +797,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
         if (!err && used2 != ~0ull) err = lift_record(cfg, R, S, O, st, sample, used2, true, true, squeeze_mode, slot_base, cnt, stride, self_censor);
     }
     if (err) {
-        report_error(O, s, err);
+        report_error(O, (unsigned long long)s * N + sample, err);
         return;
     }
 
@@ -840,7 +852,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
             else if (n_uniq == 1 || f.combi == GLX_COMBI_SEMICOLON) v = (int32_t)uniq;
             else if (f.combi == GLX_COMBI_MISSING) v = 0;
             else {
-                report_error(O, s, 2);
+                report_error(O, (unsigned long long)s * N + sample, 2);
                 return;
             }
             if (cz) v = 0;
@@ -1108,7 +1120,7 @@ __device__ inline bool genotype_cell_single(const DCfg& cfg, const DRecs& R, con
         }
     }
     if (err) {
-        report_error(O, s, err);
+        report_error(O, (unsigned long long)s * N + sample, err);
         return true;
     }
     if ((al0 != 0 && al1 == 0) || al0 > al1) {

@@ -74,7 +74,7 @@ struct DOut {
     int32_t* fld[GLX_MAX_FIELDS];
     uint32_t* allele_used;
     uint8_t* site_flags;
-    unsigned long long* error;  // min over failing cells of (site << 8 | -status)
+    unsigned long long* error;  // min over failing cells of (cell << 8 | -status), cell = site * n_samples + sample
 };
 
 // flatten glx_config for the kernels (host side)

@@ -783,7 +783,7 @@ int glx_check(glx_ctx* ctx, glx_dev_batch* d) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (w == ~0ull) return GLX_OK;
     const int code = (int)(w & 0xff);
-    const unsigned long long site = w >> 8;
+    const unsigned long long site = (w >> 8) / (d->n_samples ? d->n_samples : 1);
     char buf[160];
     snprintf(buf, sizeof buf, "genotyper: site %llu failed with status %d (first failing site of the batch)", site, -code);
     ctx->err = buf;
@@ -895,7 +895,7 @@ int glx_status(glx_ctx* ctx, glx_dev_batch* d) {
     if (w == ~0ull) return GLX_OK;
     const int code = (int)(w & 0xff);
     char buf[160];
-    snprintf(buf, sizeof buf, "genotyper: site %llu failed with status %d (first failing site of the batch)", w >> 8, -code);
+    snprintf(buf, sizeof buf, "genotyper: site %llu failed with status %d (first failing site of the batch)", (w >> 8) / (d->n_samples ? d->n_samples : 1), -code);
     ctx->err = buf;
     return code == 101 ? GLX_E_UNSUPPORTED : -code;
 }

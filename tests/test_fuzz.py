@@ -1,0 +1,66 @@
+"""Randomised irregular cohorts (tests/fuzz_cases.py): device cell logic (host build) vs the oracle on CPU, the CUDA
+path vs the oracle on the GPU. Status codes must agree; on success every output column must be bit-exact."""
+import numpy as np
+import pytest
+
+import emu_lib
+import fuzz_cases
+import oracle_lib
+from test_emu_parity import compare_outs
+
+
+def _oracle(b):
+    ref = b.alloc_out()
+    try:
+        oracle_lib.genotype_batch(b, ref)
+        return 0, ref
+    except oracle_lib.OracleError as e:
+        return e.code, ref
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_fuzz_emu(built, chunk):
+    n_ok = 0
+    for seed in range(chunk * 60, chunk * 60 + 60):
+        b = fuzz_cases.build_batch(seed)
+        orc, ref = _oracle(b)
+        for name, run in (("general", lambda o: emu_lib.general_batch(b, o)), ("tiled", lambda o: emu_lib.tiled_batch(b, o)[0]),
+                          ("tiled-dynamic", lambda o: emu_lib.tiled_batch(b, o, True)[0])):
+            got = b.alloc_out()
+            rc = run(got)
+            assert rc == orc, f"seed {seed} {name}: status {rc} vs oracle {orc}"
+            if orc == 0:
+                d = compare_outs(got, ref, b.n_fields)
+                assert not d, f"seed {seed} {name}:\n" + "\n".join(d)
+        n_ok += orc == 0
+    assert n_ok >= 24  # enough cases must be well-formed enough to genotype (the rest compare error statuses)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["sig", "dynamic", "general"])
+def test_fuzz_gpu(built, path, monkeypatch):
+    from glnexus_b200 import Context, GlxError
+    monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
+    monkeypatch.delenv("GLX_FORCE_DYNAMIC_TILED", raising=False)
+    if path == "general":
+        monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
+    elif path == "dynamic":
+        monkeypatch.setenv("GLX_FORCE_DYNAMIC_TILED", "1")
+    ctx = Context(0)
+    n_ok = 0
+    for seed in range(1000, 1240):
+        b = fuzz_cases.build_batch(seed)
+        orc, ref = _oracle(b)
+        got = b.alloc_out(pinned=False)
+        try:
+            ctx.genotype_batch(b, got)
+            rc = 0
+        except GlxError as e:
+            rc = e.code
+        assert rc == orc, f"seed {seed}: status {rc} vs oracle {orc}"
+        if orc == 0:
+            d = compare_outs(got, ref, b.n_fields)
+            assert not d, f"seed {seed}:\n" + "\n".join(d)
+            n_ok += 1
+    ctx.close()
+    assert n_ok >= 100
