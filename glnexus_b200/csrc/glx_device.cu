@@ -33,13 +33,13 @@ using namespace glxd;
 __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets,
                                                                                   int32_t* __restrict__ blobs, const int32_t* __restrict__ tile_q,
                                                                                   uint32_t n_tiles, uint32_t* __restrict__ tile_cursors) {
-    extern __shared__ int4 s_blob[];  // [GLX_RESOLVE_THREADS][W/4], row r XOR-swizzled by chunk to spread banks
-    const uint32_t W = blob_words(plan.n_rv), Q = W / 4;
+    extern __shared__ int32_t s_blob[];  // [GLX_RESOLVE_THREADS][W + 1]: rows padded by one word so that column writes spread over the banks
+    const uint32_t W = blob_words(plan.n_rv), WP = W + 1;
     const uint64_t r0 = (uint64_t)blockIdx.x * GLX_RESOLVE_THREADS;
     const uint64_t r = r0 + threadIdx.x;
     if (r < R.n_records) {
-        int32_t w[(GLX_BLOB_HDR + GLX_FAST_RV + 3) & ~3];
-        build_record_blob(cfg, plan, R, r, R.flags[r] & GLX_RF_DEV_LAST, w);  // glx_upload marks each sample's last record
+        build_record_blob(cfg, plan, R, r, R.flags[r] & GLX_RF_DEV_LAST, s_blob + threadIdx.x * WP);  // glx_upload marks each sample's last record
+#ifndef GLX_ABLATE_CURSORS
         // which sample is r in? (ds_rec_off is small and cache-resident)
         uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= r < ds_rec_off[hi]
         while (hi - lo > 1) {
@@ -48,12 +48,12 @@ __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kerne
             else hi = mid;
         }
         fill_tile_cursors(R, r, R.ds_rec_off[lo], lo, n_datasets, tile_q, n_tiles, tile_cursors);
-        for (uint32_t q = 0; q < Q; q++) s_blob[threadIdx.x * Q + q] = make_int4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+#endif
     }
     __syncthreads();
     const uint64_t n_here = min((uint64_t)GLX_RESOLVE_THREADS, R.n_records - r0);
-    int4* __restrict__ dst = reinterpret_cast<int4*>(blobs + r0 * W);
-    for (uint32_t e = threadIdx.x; e < n_here * Q; e += GLX_RESOLVE_THREADS) dst[e] = s_blob[e];
+    int32_t* __restrict__ dst = blobs + r0 * W;
+    for (uint32_t e = threadIdx.x; e < n_here * W; e += GLX_RESOLVE_THREADS) dst[e] = s_blob[(e / W) * WP + e % W];
 }
 
 // Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
@@ -716,7 +716,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
         CU(cudaMemsetAsync(d->tile_cursors, 0xff, (size_t)d->n_site_tiles * d->n_samples * 4, st));
         if (d->R.n_records) {
             glx_resolve_records_kernel<<<(unsigned)((d->R.n_records + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS), GLX_RESOLVE_THREADS,
-                                         (size_t)GLX_RESOLVE_THREADS * blob_words(d->plan.n_rv) * 4, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q,
+                                         (size_t)GLX_RESOLVE_THREADS * (blob_words(d->plan.n_rv) + 1) * 4, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q,
                                                                                                             d->n_site_tiles, d->tile_cursors);
             d->launches_per_call++;
             CU(cudaGetLastError());
