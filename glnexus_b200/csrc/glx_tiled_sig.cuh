@@ -106,28 +106,22 @@ struct TiledLane {
             load(blobs);
         }
     }
-    // same decision table as fast_classify
+    // same decision table as fast_classify, written without early exits (a handful of predicate ops instead of a
+    // branch ladder that the warp would walk divergently)
     __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int sbeg, int send, int qbeg, int qend, bool slow_site, bool back,
                                             bool& called, int& rnc) {
-        called = false;
-        rnc = RNC_M;
         seek(blobs, qbeg, back);
-        if (slow_site) return CT_SLOW;
-        if (c >= n || beg_c >= qend) return CT_MISSING;
-        if (beg_n < qend) return CT_SLOW;
-        if (bits & RB_SLOW) return CT_SLOW;
-        if (!(end_c > sbeg && beg_c < send)) return CT_MISSING;
-        if (!cfg.allow_partial && !(beg_c <= sbeg && end_c >= send)) {
-            rnc = RNC_P;
-            return CT_PARTIAL;
-        }
-        if (bits & RB_NONCALLED) rnc = RNC_I;
-        else if ((unsigned long long)(long long)mrd >= (unsigned long long)cfg.required_dp) {
-            called = true;
-            rnc = RNC_NA;
-        } else
-            rnc = RNC_D;
-        return CT_REF;
+        const bool none = beg_c >= qend;  // also true past the sample's last record (sentinel)
+        const bool slow = slow_site | (!none & ((beg_n < qend) | ((bits & RB_SLOW) != 0)));
+        const bool overl = (end_c > sbeg) & (beg_c < send);
+        const bool spans = (beg_c <= sbeg) & (end_c >= send);
+        const bool kept = !none & !slow & overl;
+        const bool partial = kept & !cfg.allow_partial & !spans;
+        const bool ref = kept & !partial;
+        const bool noncalled = (bits & RB_NONCALLED) != 0;
+        called = ref & !noncalled & ((mrd < 0) | ((uint32_t)mrd >= cfg.required_dp));
+        rnc = partial ? RNC_P : (!ref ? RNC_M : (noncalled ? RNC_I : (called ? RNC_NA : RNC_D)));
+        return slow ? CT_SLOW : (ref ? CT_REF : (partial ? CT_PARTIAL : CT_MISSING));
     }
     // field K's vector of a finished cell. A = unified alleles of the site; off_dyn(k) = fld_off[k][s] for
     // allele/genotype-numbered fields (BASIC-numbered fields sit at s*N*count).
