@@ -68,6 +68,8 @@ def lib():
     L.glx_download_narrow_on.restype = C.c_int
     L.glx_narrow_finish.argtypes = [vp, vp, vp]
     L.glx_narrow_finish.restype = C.c_int
+    L.glxh_genotype_sites.argtypes = [cp, cp, cp, C.c_int, C.POINTER(cp), C.POINTER(cp), cp, C.c_int, C.c_uint32, C.c_int, vp, C.POINTER(C.c_uint64), cp, sz]
+    L.glxh_genotype_sites.restype = C.c_int
     L.glxh_batch_pin.argtypes = [vp]
     L.glxh_batch_pin.restype = C.c_int
     L.glx_upload_on.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
@@ -444,6 +446,22 @@ class Context:
         if self.handle:
             lib().glx_destroy(self.handle)
             self.handle = None
+
+
+def genotype_sites(sites_text, datasets, filename, preset=None, config_text=None, device=0, batch_sites=0, test_ingest_rules=False, abort=None):
+    """Service::genotype_sites on the device path (glxh_genotype_sites): text in, pVCF file out. `abort` is an optional
+    ctypes c_int polled between range batches. Returns {sites, rows, batches, cells}."""
+    L = lib()
+    n = len(datasets)
+    names = (C.c_char_p * max(n, 1))(*[_b(d[0]) for d in datasets])
+    texts = (C.c_char_p * max(n, 1))(*[_b(d[1]) for d in datasets])
+    err = C.create_string_buffer(1024)
+    st = (C.c_uint64 * 4)()
+    rc = L.glxh_genotype_sites(_b(preset), _b(config_text), _b(sites_text), n, names, texts, _b(filename), int(device), int(batch_sites),
+                               1 if test_ingest_rules else 0, C.addressof(abort) if abort is not None else None, st, err, len(err))
+    if rc != GLX_OK:
+        raise GlxError(rc, err.value.decode(errors="replace"))
+    return {"sites": st[0], "rows": st[1], "batches": st[2], "cells": st[3]}
 
 
 def out_bytes_of(batch):

@@ -937,11 +937,9 @@ static char header_number_class(const std::string& description) {
     return n.size() == 1 ? n[0] : '1';
 }
 
-Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& o) {
-    o.clear();
+// pVCF header, src/service.cc:190-241
+void vcf_header_text(const PackedBatch& b, std::string& o) {
     const genotyper_config& cfg = b.gcfg;
-    const size_t N = b.sites.n_samples;
-    // pVCF header, src/service.cc:190-241
     o += "##fileformat=VCFv4.2\n";
     o += "##FILTER=<ID=PASS,Description=\"All filters passed\">\n";
     o += "##GLnexusVersion=glnexus_b200\n";
@@ -961,7 +959,18 @@ Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& 
     o += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT";
     for (const auto& sm : b.sample_names) o += "\t" + sm;
     o += "\n";
+}
 
+Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& o) {
+    o.clear();
+    vcf_header_text(b, o);
+    return vcf_rows_text(b, out, o);
+}
+
+// one pVCF row per surviving site of the batch, appended to `o`
+Status vcf_rows_text(const PackedBatch& b, const glx_out& out, std::string& o) {
+    const genotyper_config& cfg = b.gcfg;
+    const size_t N = b.sites.n_samples;
     std::vector<char> number_class;
     for (const auto& f : cfg.liftover_fields) number_class.push_back(header_number_class(f.description));
 

@@ -252,12 +252,32 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
 // Output assembly = src/genotyper.cc:862-1003 after the per-dataset loop + the pVCF header of
 // src/service.cc:190-241, written as VCF text (htslib vcf_format value semantics).
 Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& vcf_text);
+void vcf_header_text(const PackedBatch& b, std::string& o);
+Status vcf_rows_text(const PackedBatch& b, const glx_out& out, std::string& o);
 
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
 // [site_lo, site_hi) with every record its sites can touch.
 void partition_sites(const PackedBatch& b, int n_parts, std::vector<uint32_t>& bounds);
 Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, PackedBatch& ans);
 
+}  // namespace glx
+
+// ---------------------------------------------------------------------------------------------
+// The upper seam: Service::genotype_sites (include/service.h:67-70, src/service.cc:302-428) on the device path.
+// Same contract: sites are genotyped and written to `filename` ("-" = stdout) in input order; `abort` is polled
+// between range batches (the reference polls it per site task and per dataset); the first failing site's Status is
+// returned. Instead of one task per site on a thread pool, sites go to the GPU in contiguous range batches of
+// `batch_sites`, two batches in flight on two streams (retrieval/packing of the next overlaps the kernels and the
+// download of the previous). Output is pVCF text (BCF needs htslib: SURVEY F5, "next" row N1).
+// ---------------------------------------------------------------------------------------------
+namespace glx {
+struct ServiceStats {
+    uint64_t sites = 0, sites_written = 0, batches = 0, cells = 0;
+};
+Status sample_set_of(const std::vector<GvcfDataset>& datasets, std::vector<std::string>& samples);
+Status genotype_sites(const genotyper_config& cfg, const std::vector<GvcfDataset>& datasets, const VcfHeaderInfo& hdr,
+                      const std::vector<unified_site>& sites, const std::string& filename, const volatile int* abort, int device,
+                      size_t batch_sites, ServiceStats* stats);
 }  // namespace glx
 
 // opaque handle of include/glx_host.h

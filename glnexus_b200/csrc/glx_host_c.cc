@@ -157,6 +157,47 @@ int glxh_batch_pin(glxh_batch* hb) {
     return rc;
 }
 
+// Service::genotype_sites on the device path, text in / pVCF file out (glx::genotype_sites)
+int glxh_genotype_sites(const char* preset, const char* config_text, const char* sites_text, int n_datasets, const char* const* dataset_names,
+                        const char* const* vcf_texts, const char* filename, int device, uint32_t batch_sites, int test_ingest_rules,
+                        const volatile int* abort, uint64_t stats[4], char* err, size_t errlen) {
+    using namespace glx;
+    if (!sites_text || !filename || n_datasets < 0) return GLX_E_INVALID;
+    Status s;
+    genotyper_config cfg;
+    if (preset && *preset) {
+        s = load_config_preset(preset, cfg);
+        if (s.bad()) return fail(s, err, errlen);
+    }
+    if (config_text && *config_text) {
+        s = genotyper_config::of_text(config_text, cfg);
+        if (s.bad()) return fail(s, err, errlen);
+    }
+    std::vector<GvcfDataset> datasets(n_datasets);
+    VcfHeaderInfo hdr_all;
+    for (int i = 0; i < n_datasets; i++) {
+        VcfHeaderInfo h;
+        s = read_vcf_text(vcf_texts[i], dataset_names[i], test_ingest_rules != 0, h, datasets[i]);
+        if (s.bad()) return fail(s, err, errlen);
+        if (i == 0) hdr_all.contigs = h.contigs;
+        for (const auto& p : h.format_types) hdr_all.format_types.insert(p);
+        for (const auto& p : h.info_types) hdr_all.info_types.insert(p);
+    }
+    std::vector<unified_site> sites;
+    s = sites_of_text(sites_text, hdr_all.contigs, sites);
+    if (s.bad()) return fail(s, err, errlen);
+    ServiceStats st;
+    s = genotype_sites(cfg, datasets, hdr_all, sites, filename, abort, device, batch_sites, &st);
+    if (stats) {
+        stats[0] = st.sites;
+        stats[1] = st.sites_written;
+        stats[2] = st.batches;
+        stats[3] = st.cells;
+    }
+    if (s.bad()) return fail(s, err, errlen);
+    return GLX_OK;
+}
+
 void glxh_batch_free(glxh_batch* b) {
     if (!b) return;
     for (void* p : b->pinned_ptrs) glx_host_unregister(p);

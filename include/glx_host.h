@@ -68,6 +68,14 @@ void glxh_free_text(char* text);
 /* genotyper_config preset -> text (for `--config NAME`); caller frees with glxh_free_text */
 int glxh_preset_text(const char* name, char** text);
 
+/* The upper seam: Service::genotype_sites (include/service.h:67-70, src/service.cc:302-428) on the device path. Sites are
+ * genotyped in contiguous range batches of `batch_sites` (0 = 4096), two batches in flight, rows written to `filename`
+ * ("-" = stdout) in input order as pVCF text; *abort != 0 stops between batches with GLX_E_ABORTED; the first failing
+ * site's status is returned. stats = {sites submitted, rows written, batches, cells}. Inputs as glxh_batch_from_text. */
+int glxh_genotype_sites(const char* preset, const char* config_text, const char* sites_text, int n_datasets, const char* const* dataset_names,
+                        const char* const* vcf_texts, const char* filename, int device, uint32_t batch_sites, int test_ingest_rules,
+                        const volatile int* abort, uint64_t stats[4], char* err, size_t errlen);
+
 /* Seeded synthetic cohort in record-store form (BASELINE.json configs[1..4] shapes). See DESIGN.md §synthetic. */
 typedef struct glxh_synth_params {
     uint32_t n_samples, n_sites;

@@ -46,3 +46,16 @@ def test_presets_load(built):
     assert "required_dp 1" in g and "revise_genotypes 1" in g and "field\tSB\tSB" in g
     with pytest.raises(GlxError):
         preset_text("nonesuch")
+
+
+def test_service_fails_loudly_without_gpu(built, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import glnexus_b200
+    import golden_util as gu
+    case = gu.load_case("deepvariant")
+    ds = [(d["name"], d["vcf"]) for d in case["datasets"]]
+    with pytest.raises(glnexus_b200.GlxError) as ei:
+        glnexus_b200.genotype_sites(case["sites_text"], ds, str(tmp_path / "o.vcf"), preset=case["preset"], config_text=case["config_text"])
+    assert ei.value.code == -1 and "no host fallback" in str(ei.value)

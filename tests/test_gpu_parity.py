@@ -217,3 +217,40 @@ def test_gpu_narrow_download(ctx):
     assert not d, "\n".join(d)
     assert 100000 in wide.array(0) and 70000 in wide.array(3)
     ctx.stream_destroy(st)
+
+
+@pytest.mark.parametrize("name", gu.case_names())
+def test_gpu_service_genotype_sites(name, tmp_path):
+    """The upper seam (glx::genotype_sites = Service::genotype_sites on the device path): whole cases, all contigs, tiny range
+    batches (2 sites) so that batching, two-deep pipelining and ordered writing are exercised; output pVCF vs the reference's truth."""
+    import glnexus_b200
+    case = gu.load_case(name)
+    ds = [(d["name"], d["vcf"]) for d in case["datasets"]]
+    out = str(tmp_path / "out.vcf")
+    multi = name == "vcf_services"  # multi-sample datasets: rejected, never mis-computed
+    try:
+        st = glnexus_b200.genotype_sites(case["sites_text"], ds, out, preset=case["preset"], config_text=case["config_text"], batch_sites=2,
+                                         test_ingest_rules=True)
+    except glnexus_b200.GlxError as e:
+        assert multi and e.code == -6
+        return
+    assert not multi
+    got = open(out).read()
+    diffs = vcfcmp.compare(got, case["truth_vcf"], case["formats"], case["infos"])
+    assert not diffs, "\n".join(diffs[:20])
+    n_sites = sum(1 for l in case["sites_text"].split("\n") if l.startswith("site\t"))
+    assert st["sites"] == n_sites and st["batches"] >= (n_sites + 1) // 2
+
+
+def test_gpu_service_abort_and_errors(tmp_path):
+    import ctypes
+    import glnexus_b200
+    case = gu.load_case("dv_1000G_chr21_5583275")
+    ds = [(d["name"], d["vcf"]) for d in case["datasets"]]
+    flag = ctypes.c_int(1)
+    with pytest.raises(glnexus_b200.GlxError) as ei:
+        glnexus_b200.genotype_sites(case["sites_text"], ds, str(tmp_path / "a.vcf"), preset=case["preset"], config_text=case["config_text"], abort=flag)
+    assert ei.value.code == -7  # Status::Aborted
+    with pytest.raises(glnexus_b200.GlxError) as ei:
+        glnexus_b200.genotype_sites(case["sites_text"], ds, "/nonexistent-dir/x.vcf", preset=case["preset"], config_text=case["config_text"])
+    assert ei.value.code == -5  # IOError
