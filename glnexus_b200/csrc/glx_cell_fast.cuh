@@ -23,7 +23,7 @@ namespace glxd {
 #define GLX_FAST_RV 24      // resolved values cached per lane (shared memory column per lane)
 #define GLX_TILE_SITES 64   // sites walked by one CTA
 #define GLX_TILE_THREADS 128
-#define GLX_STAGE_MAX 8      // per-sample vectors of 3..8 ints are transposed through shared memory before being stored
+#define GLX_STAGE_MAX 32     // per-sample vectors of 3..32 ints are transposed through shared memory before being stored
 #define GLX_WORK_SINGLE 0x80000000u  // worklist cursor flag: the query range holds exactly one record (not a monoallelic site)
 
 // How a field's per-sample vector is produced for a finished cell:

@@ -163,7 +163,7 @@ struct TiledLane {
             }
 #ifdef __CUDACC__
             if (count >= 3 && count <= GLX_STAGE_MAX) {
-                // A lane's vector of 3..8 ints is narrower than a sector and not a power of two: written lane by lane every
+                // A lane's vector of 3..32 ints is not a whole number of sectors: written lane by lane every
                 // store instruction would touch a third of each sector. Transpose through shared memory so that the warp
                 // writes its 32*count ints as `count` fully coalesced rows.
                 int32_t* st = stage + lane * count;
