@@ -180,3 +180,51 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def convert_real_slice():
+    """A slice of the reference's real GATK gVCF (test/data/NA12878.g.vcf.gz, used by its storage tests) as a 3-sample
+    cohort: the slice itself, a copy with every variant call made hom-ALT and every 7th band dropped, and a copy without
+    variant records. Sites = one per variant record (its DNA alleles). No truth pVCF exists for it: the tests compare the
+    kernels with the oracle on real record shapes (long bands, real PL/AD/SB, INFO fields, multi-ALT records)."""
+    import gzip
+    lines = [l.rstrip("\n") for l in gzip.open(os.path.join(REF, "test/data/NA12878.g.vcf.gz"), "rt")]
+    header = [l for l in lines if l.startswith("##")]
+    recs = [l for l in lines if not l.startswith("#")]
+    window = recs[240000:242200]
+    chrom = window[0].split("\t")[0]
+    window = [l for l in window if l.split("\t")[0] == chrom]
+    hdr_txt = "\n".join(h for h in header if not h.startswith("##contig") or f"ID={chrom}," in h) + "\n"
+    col = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    sites, a_rows, b_rows, c_rows = [], [], [], []
+    last_end = -1
+    for i, l in enumerate(window):
+        t = l.split("\t")
+        alts = [a for a in t[4].split(",") if not a.startswith("<")]
+        a_rows.append(l)
+        if alts:
+            beg, end = int(t[1]) - 1, int(t[1]) - 1 + len(t[3])
+            if beg >= last_end:
+                sites.append((beg, end, t[3], alts))
+                last_end = end
+            fmt = t[8].split(":")
+            vals = t[9].split(":")
+            vals[fmt.index("GT")] = "1/1"
+            b_rows.append("\t".join(t[:9] + [":".join(vals)]))
+        else:
+            if i % 7:
+                b_rows.append(l)
+            c_rows.append(l)
+    st = []
+    for k, (beg, end, ref, alts) in enumerate(sites):
+        st.append("\t".join(["site", chrom, str(beg), str(end), str(100 + k % 800), "0", "0.001"]))
+        st.append("\t".join(["allele", ref, str(beg), str(end), ref, "0", "nan"]))
+        for j, a in enumerate(alts):
+            st.append("\t".join(["allele", a, str(beg), str(end), a, str(50 + j), repr(0.3 / (j + 1))]))
+    ans = {"source": "test/data/NA12878.g.vcf.gz records 240000-242200", "preset": "gatk", "sites_text": "\n".join(st) + "\n",
+           "datasets": [{"name": n, "vcf": hdr_txt + col + n + "\n" + "\n".join(rows) + "\n"} for n, rows in (("NA12878", a_rows), ("NA12878_homalt", b_rows), ("NA12878_bands", c_rows))]}
+    return ans
+
+
+if __name__ == "__main__":
+    json.dump(convert_real_slice(), open(os.path.join(OUT, "_real_na12878_slice.json"), "w"))

@@ -48,3 +48,27 @@ def test_emu_general_presets(built, preset):
         assert not d, "tiled:\n" + "\n".join(d)
         d = compare_outs(got3, ref, b.n_fields)
         assert not d, "tiled dynamic:\n" + "\n".join(d)
+
+
+def _real_slice_batch():
+    import json
+    import os
+    import golden_util as gu
+    from glnexus_b200 import Batch
+    fx = json.load(open(os.path.join(gu.GOLDEN, "_real_na12878_slice.json")))
+    return Batch.from_text(fx["sites_text"], [(d["name"], d["vcf"]) for d in fx["datasets"]], preset=fx["preset"])
+
+
+def test_emu_real_gvcf_slice(built):
+    """Real GATK gVCF records (a slice of the reference's test/data/NA12878.g.vcf.gz) as a 3-sample cohort."""
+    b = _real_slice_batch()
+    assert b.n_samples == 3 and b.n_sites > 20 and b.n_records > 4000
+    ref = b.alloc_out()
+    oracle_lib.genotype_batch(b, ref)
+    for run in (lambda o: emu_lib.general_batch(b, o), lambda o: emu_lib.tiled_batch(b, o)[0], lambda o: emu_lib.tiled_batch(b, o, True)[0]):
+        got = b.alloc_out()
+        assert run(got) == 0
+        d = compare_outs(got, ref, b.n_fields)
+        assert not d, "\n".join(d)
+    rnc = ref.array("rnc").tobytes().decode()
+    assert ".." in rnc

@@ -254,3 +254,16 @@ def test_gpu_service_abort_and_errors(tmp_path):
     with pytest.raises(glnexus_b200.GlxError) as ei:
         glnexus_b200.genotype_sites(case["sites_text"], ds, "/nonexistent-dir/x.vcf", preset=case["preset"], config_text=case["config_text"])
     assert ei.value.code == -5  # IOError
+
+
+def test_gpu_real_gvcf_slice(ctx):
+    """Real GATK gVCF records (slice of the reference's NA12878.g.vcf.gz fixture) through the CUDA path vs the oracle."""
+    from test_emu_synth import _real_slice_batch
+    b = _real_slice_batch()
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    oracle_lib.genotype_batch(b, ref)
+    ctx.genotype_batch(b, got)
+    d = compare_outs(got, ref, b.n_fields)
+    assert not d, "\n".join(d)
+    vcf = b.assemble_vcf(got)
+    assert vcf.count("\n") > b.n_sites  # header + one row per site (gatk preset does not trim)
