@@ -61,6 +61,25 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
     return code == 101 ? GLX_E_UNSUPPORTED : -code;
 }
 
+// composition of the cells the fast path declines: [0] finished by the single-record closed form, [1] general path,
+// [2] of those, cells whose query range holds only reference bands, [3] of those, exactly two bands
+static uint64_t g_emu_stats[4];
+extern "C" void glx_emu_stats(uint64_t out[4]) { memcpy(out, g_emu_stats, sizeof g_emu_stats); }
+static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t first, uint64_t hi) {
+    g_emu_stats[1]++;
+    int n = 0;
+    bool all_ref = true;
+    for (uint64_t r = first; r < hi && R.beg[r] < S.qend[s]; r++) {
+        if (!(R.end[r] > S.qbeg[s])) continue;
+        n++;
+        if (!(R.flags[r] & GLX_RF_IS_REF)) all_ref = false;
+    }
+    if (all_ref && n >= 2) {
+        g_emu_stats[2]++;
+        if (n == 2) g_emu_stats[3]++;
+    }
+}
+
 // signature-specialised lanes (glx_tiled_sig.cuh), lane by lane
 template <class Sig>
 static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, const DSites& S, const DOut& O, const int32_t* blobs, const uint32_t* cursors,
@@ -79,7 +98,11 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                 if (type == CT_SLOW) {
                     n_slow++;
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
-                    if (single && genotype_cell_single(C, R, S, O, s, n, R.ds_rec_off[n] + L.c)) continue;
+                    if (single && genotype_cell_single(C, R, S, O, s, n, R.ds_rec_off[n] + L.c)) {
+                        g_emu_stats[0]++;
+                        continue;
+                    }
+                    note_general(R, S, s, R.ds_rec_off[n] + L.c, R.ds_rec_off[n + 1]);
                     genotype_cell_general(C, R, S, O, s, n, R.ds_rec_off[n] + L.c, R.ds_rec_off[n + 1], cnt.data(), 1);
                     continue;
                 }
@@ -97,6 +120,7 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
 // The tiled kernel's per-lane state machine run lane by lane: same tiles, same cursor walk, same classify /
 // resolve / value functions; cells it declines go through the general cell. (The warp-transposed stores and
 // the worklist hand-off are CUDA-only and are covered by the GPU tests.)
+extern "C" void glx_emu_stats_reset() { memset(g_emu_stats, 0, sizeof g_emu_stats); }
 extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out, uint64_t* n_slow_out, int dynamic_only) {
     if (recs->n_datasets != sites->n_samples) return GLX_E_UNSUPPORTED;
     for (uint32_t d = 0; d < recs->n_datasets; d++)
