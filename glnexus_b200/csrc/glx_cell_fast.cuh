@@ -25,6 +25,8 @@ namespace glxd {
 #define GLX_TILE_THREADS 128
 #define GLX_STAGE_MAX 32     // per-sample vectors of 3..32 ints are transposed through shared memory before being stored
 #define GLX_WORK_SINGLE 0x80000000u  // worklist cursor flag: the query range holds exactly one record (not a monoallelic site)
+#define GLX_WORK_DONE 0x40000000u    // set by the closed-form worklist kernel on an unflagged cell it finished (all-band cell)
+#define GLX_WORK_CURSOR 0x3fffffffu
 
 // How a field's per-sample vector is produced for a finished cell:
 //   FM_VEC      BASIC-numbered field: `count` cached values
@@ -175,7 +177,7 @@ __device__ __forceinline__ void cursor_seek(const int32_t* __restrict__ blobs, u
 }
 
 enum { CT_SLOW = 0, CT_MISSING = 1, CT_PARTIAL = 2, CT_REF = 3 };
-enum { RB_SLOW = 1, RB_NONCALLED = 2 };
+enum { RB_SLOW = 1, RB_NONCALLED = 2, RB_FOUND0 = 256 };  // RB_FOUND0 << k: field k found a source column on this band
 
 // Resolve a reference band into the lane's value cache. Returns RB_* bits; mrd = its MIN_DP as min_ref_depth.
 __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& plan, const DRecs& R, uint64_t r, int32_t* rv, int rvs, int& mrd) {
@@ -222,6 +224,7 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
                         found = true;
                     }
                 }
+                if (found) bits |= (uint32_t)RB_FOUND0 << k;
                 if (f.kind == GLX_FK_PL) break;  // a lone band never yields a liftable PL vector; validated only
                 if (f.number == GLX_NUM_BASIC) {
                     for (int j = 0; j < f.count; j++) c[(size_t)j * rvs] = found ? v[j] : dflt;
@@ -241,6 +244,7 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
                 int32_t p0 = 0, p1 = 0, p2 = 0;
                 if (rvv > 0) {
                     if (rvv != 3) return RB_SLOW;
+                    bits |= (uint32_t)RB_FOUND0 << k;
                     p0 = buf[0];
                     p1 = buf[1];
                     p2 = buf[2];
@@ -262,6 +266,7 @@ __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& pla
             }
             case GLX_FK_FT: {
                 const uint32_t m = R.filt[r];
+                if (m) bits |= (uint32_t)RB_FOUND0 << k;
                 const int nu = __popc(m);
                 int32_t v = 0;
                 if (nu == 0) v = 0;
@@ -344,6 +349,177 @@ __device__ __forceinline__ int fast_classify(const DCfg& cfg, const int32_t* __r
     } else
         rnc = RNC_D;
     return CT_REF;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Closed form for a cell whose query range holds SEVERAL records, all of them well-formed reference bands (a site at
+// a band boundary, or a multi-base site spanning bands): with no variant record, genotype_site reduces to folds over
+// the kept bands — span merge, min_ref_depth, "any band non-called", and per field the combination
+// (min / max / missing-if-several) of the bands' values — all available from the bands' blobs. PL2's first-record /
+// smaller-margin rule is replayed on the raw PL triples. Runs thread-per-cell in the worklist kernel; returns false
+// (nothing written) when some record is not a well-formed band or the config has a field this form does not cover.
+__device__ inline bool genotype_cell_bands(const DCfg& cfg, const FastPlan& plan, const DRecs& R, const DSites& S, const DOut& O, const int32_t* __restrict__ blobs,
+                                           uint32_t s, uint32_t sample, uint64_t first, uint64_t hi) {
+    if (!plan.enabled || S.monoallelic[s]) return false;
+    const uint32_t W = blob_words(plan.n_rv);
+    const int sbeg = S.beg[s], send = S.end[s], qbeg = S.qbeg[s], qend = S.qend[s];
+    const int A = S.n_allele[s];
+    const uint32_t N = S.n_samples;
+    for (uint32_t k = 0; k < cfg.n_fields; k++)
+        if (cfg.f[k].kind == GLX_FK_FT || cfg.f[k].kind == GLX_FK_STRING) return false;
+    // pass 1: every record of the query range must be a resolved band; fold the calling state over the kept ones
+    int n_kept = 0, mrd = -1;
+    bool spanned = false, have_cur = false, noncalled = false;
+    int cur_b = 0, cur_e = 0;
+    for (uint64_t r = first; r < hi; r++) {
+        const int32_t* b = blobs + r * W;
+        const int rb = b[0], re = b[1];
+        if (rb >= qend) break;
+        if (!(re > qbeg)) continue;
+        const uint32_t bits = (uint32_t)b[3];
+        if (bits & RB_SLOW) return false;
+        if (!(re > sbeg && rb < send)) continue;  // a band is kept only if it overlaps site.pos
+        n_kept++;
+        if (!have_cur) {
+            cur_b = rb;
+            cur_e = re;
+            have_cur = true;
+        } else if (rb <= cur_e) {
+            cur_e = max(cur_e, re);
+        } else {
+            if (cur_b <= sbeg && cur_e >= send) spanned = true;
+            cur_b = rb;
+            cur_e = re;
+        }
+        const int d = b[4];
+        mrd = (mrd < 0) ? d : min(mrd, d);
+        if (bits & RB_NONCALLED) noncalled = true;
+    }
+    if (have_cur && cur_b <= sbeg && cur_e >= send) spanned = true;
+    int rnc = RNC_M;
+    bool called = false, lift = false;
+    if (n_kept == 0) {
+    } else if (!cfg.allow_partial && !spanned) {
+        rnc = RNC_P;
+    } else {
+        lift = true;
+        if (noncalled) rnc = RNC_I;
+        else if ((unsigned long long)(long long)mrd >= (unsigned long long)cfg.required_dp) {
+            called = true;
+            rnc = RNC_NA;
+        } else
+            rnc = RNC_D;
+    }
+    // pass 2: fields
+    for (uint32_t k = 0; k < cfg.n_fields; k++) {
+        const DFld& f = cfg.f[k];
+        const int count = S.fld_cnt[k][s];
+        int32_t* out = O.fld[k] + S.fld_off[k][s] + (uint64_t)sample * count;
+        const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
+        const bool vec_rule = f.type == GLX_TYPE_INT && f.number != GLX_NUM_BASIC && count > 1;
+        if (!lift) {
+            const int32_t c = f.kind == GLX_FK_PL2 ? 0 : missing;
+            for (int j = 0; j < count; j++) out[j] = c;
+            if (vec_rule && c == GLXD_INT_MISSING) out[1] = GLXD_INT_VEND;
+            continue;
+        }
+        if (f.kind == GLX_FK_PL) {  // slot 0 gets one value per band with a PL: never a liftable vector
+            for (int j = 0; j < count; j++) out[j] = GLXD_INT_MISSING;
+            if (vec_rule) out[1] = GLXD_INT_VEND;
+            continue;
+        }
+        if (f.kind == GLX_FK_PL2) {
+            int32_t q0 = GLXD_INT_MISSING, q1 = GLXD_INT_MISSING, q2 = GLXD_INT_MISSING;
+            bool self_censor = false;
+            for (uint64_t r = first; r < hi; r++) {
+                const int32_t* b = blobs + r * W;
+                if (b[0] >= qend) break;
+                if (!(b[1] > qbeg) || !(b[1] > sbeg && b[0] < send) || !((uint32_t)b[3] & ((uint32_t)RB_FOUND0 << k))) continue;
+                const int32_t* buf = nullptr;
+                if (col_get(R, cfg.col_pl, r, buf) != 3) return false;  // cannot happen for a resolved band
+                int32_t v0 = q0;
+                if (v0 == 0) {
+                    if (buf[0] == 0) {
+                        int32_t margin = GLXD_INT_MISSING;
+                        for (int j = 1; j < 3; j++)
+                            if (buf[j] != GLXD_INT_MISSING) margin = (margin != GLXD_INT_MISSING) ? min(margin, buf[j]) : buf[j];
+                        if (margin != GLXD_INT_MISSING) {
+                            int32_t old_margin = GLXD_INT_MISSING;  // over the slots of the unified vector: (0,a) = q1, the rest = q2
+                            if (q1 != GLXD_INT_MISSING) old_margin = q1;
+                            if (q2 != GLXD_INT_MISSING) old_margin = (old_margin != GLXD_INT_MISSING) ? min(old_margin, q2) : q2;
+                            if (old_margin != GLXD_INT_MISSING && margin < old_margin) v0 = GLXD_INT_MISSING;
+                        }
+                    }
+                } else if (v0 != GLXD_INT_MISSING) {
+                    self_censor = true;
+                }
+                if (v0 == GLXD_INT_MISSING) {
+                    q0 = buf[0];
+                    q1 = buf[1];
+                    q2 = buf[2];
+                }
+            }
+            const bool zero = q0 == 0 || q1 == 0 || q2 == 0;
+            const bool other = (q0 != 0 && q0 != GLXD_INT_MISSING) || (q1 != 0 && q1 != GLXD_INT_MISSING) || (q2 != 0 && q2 != GLXD_INT_MISSING);
+            if (self_censor || !(zero && other)) q0 = q1 = q2 = 0;
+            else {
+                if (q0 == GLXD_INT_MISSING) q0 = 990;
+                if (q1 == GLXD_INT_MISSING) q1 = 990;
+                if (q2 == GLXD_INT_MISSING) q2 = 990;
+            }
+            int a = 0, bb = 0;
+            for (int j = 0; j < count; j++) {
+                out[j] = a == 0 ? q0 : (bb == 0 ? q1 : q2);
+                if (++bb > a) {
+                    a++;
+                    bb = 0;
+                }
+            }
+            continue;
+        }
+        // numeric kinds: BASIC-numbered fields combine every slot, allele/genotype-numbered ones only slot 0 (a band's map is [0,-1])
+        const int n_slots = f.number == GLX_NUM_BASIC ? count : 1;
+        const int32_t dflt = f.default_zero ? 0 : missing;
+        for (int j = 0; j < n_slots; j++) {
+            int n_found = 0;
+            int32_t acc = dflt;
+            for (uint64_t r = first; r < hi; r++) {
+                const int32_t* b = blobs + r * W;
+                if (b[0] >= qend) break;
+                if (!(b[1] > qbeg) || !(b[1] > sbeg && b[0] < send) || !((uint32_t)b[3] & ((uint32_t)RB_FOUND0 << k))) continue;
+                const int32_t v = b[GLX_BLOB_HDR + plan.rv0[k] + j];
+                if (n_found == 0) acc = v;
+                else if (f.combi == GLX_COMBI_MIN || f.combi == GLX_COMBI_MAX) {
+                    bool take;
+                    if (f.type == GLX_TYPE_FLOAT) take = f.combi == GLX_COMBI_MIN ? (__int_as_float(v) < __int_as_float(acc)) : (__int_as_float(acc) < __int_as_float(v));
+                    else take = f.combi == GLX_COMBI_MIN ? (v < acc) : (acc < v);
+                    if (take) acc = v;
+                }
+                n_found++;
+            }
+            if (n_found > 1 && f.combi != GLX_COMBI_MIN && f.combi != GLX_COMBI_MAX) acc = missing;
+            out[j] = acc;
+        }
+        for (int j = n_slots; j < count; j++) out[j] = dflt;
+        if (vec_rule) {
+            bool all_missing = true;
+            for (int j = 0; j < count; j++)
+                if (out[j] != GLXD_INT_MISSING) all_missing = false;
+            if (all_missing) out[1] = GLXD_INT_VEND;
+        }
+    }
+    const size_t cell = ((size_t)s * N + sample) * 2;
+    const signed char ga = called ? 0 : -1;
+    const unsigned char rc = (unsigned char)kRncChar[rnc];
+    *reinterpret_cast<char2*>(O.gt + cell) = make_char2(ga, ga);
+    *reinterpret_cast<uchar2*>(O.rnc + cell) = make_uchar2(rc, rc);
+    if (called) atomicOr(O.allele_used + s, 1u);
+    if (rnc == RNC_I) {
+        uint32_t* wd = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(O.site_flags + s) & ~(uintptr_t)3);
+        atomicOr(wd, 1u << (8 * (reinterpret_cast<uintptr_t>(O.site_flags + s) & 3)));
+    }
+    (void)A;
+    return true;
 }
 
 // write field k's vector of a finished cell (o = the cell's first slot)

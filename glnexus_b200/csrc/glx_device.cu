@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_kernel(const
     }
 }
 
-// Worklist, pass 1: thread per worklist cell flagged "exactly one record in the query range". The closed form for a
-// lone variant record (genotype_cell_single) needs no scratch and few registers, so this kernel runs at high
-// occupancy; a cell it declines has its flag cleared in place and is left to the general kernel.
+// Worklist, pass 1: thread per worklist cell flagged "exactly one record in the query range". The closed form for a lone
+// variant record (genotype_cell_single) needs no scratch and few registers, so this kernel runs at high occupancy; a
+// cell it declines has its flag cleared in place and is left to the general kernel.
 __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, uint2* __restrict__ worklist,
                                                                const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint32_t region_cells) {
     const uint32_t N = S.n_samples;
@@ -180,8 +180,27 @@ __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, c
             const uint2 e = w[it];
             if (!(e.y & GLX_WORK_SINGLE)) continue;
             const uint32_t s = e.x / N, sample = e.x % N;
-            const uint64_t first = R.ds_rec_off[sample] + (e.y & ~GLX_WORK_SINGLE);
-            if (!genotype_cell_single(cfg, R, S, O, s, sample, first)) w[it].y = e.y & ~GLX_WORK_SINGLE;
+            const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
+            if (!genotype_cell_single(cfg, R, S, O, s, sample, first)) w[it].y = e.y & GLX_WORK_CURSOR;
+        }
+    }
+}
+
+// Worklist, pass 2: the unflagged cells (several records in the query range) try the closed form for a run of
+// reference bands (genotype_cell_bands, computed from the record blobs); finished cells get GLX_WORK_DONE.
+__global__ void __launch_bounds__(128) glx_cells_bands_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
+                                                              uint2* __restrict__ worklist, const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions,
+                                                              uint32_t region_cells, const int32_t* __restrict__ blobs) {
+    const uint32_t N = S.n_samples;
+    for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        const uint32_t n_items = n_work[reg];
+        uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
+        for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
+            const uint2 e = w[it];
+            if (e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) continue;
+            const uint32_t s = e.x / N, sample = e.x % N;
+            const uint64_t lo = R.ds_rec_off[sample];
+            if (genotype_cell_bands(cfg, plan, R, S, O, blobs, s, sample, lo + (e.y & GLX_WORK_CURSOR), R.ds_rec_off[sample + 1])) w[it].y = e.y | GLX_WORK_DONE;
         }
     }
 }
@@ -202,10 +221,10 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
             const uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
             for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
                 const uint2 e = w[it];
-                if (e.y & GLX_WORK_SINGLE) continue;  // finished by glx_cells_single_kernel
+                if (e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) continue;  // finished by glx_cells_single_kernel
                 const uint32_t s = e.x / N, sample = e.x % N;
                 const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
-                genotype_cell_general(cfg, R, S, O, s, sample, lo + e.y, hi, cnt, stride);
+                genotype_cell_general(cfg, R, S, O, s, sample, lo + (e.y & GLX_WORK_CURSOR), hi, cnt, stride);
             }
         }
         return;
@@ -743,6 +762,8 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[2], st));
             const uint32_t region_cells = GLX_TILE_SITES * d->samples_per_cta;
+            glx_cells_bands_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->blobs);
+            d->launches_per_call++;
             glx_cells_single_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells);
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[3], st));
             const uint32_t g2 = nreg < (uint32_t)d->general_blocks ? nreg : (uint32_t)d->general_blocks;

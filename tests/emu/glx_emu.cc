@@ -62,7 +62,7 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
 }
 
 // composition of the cells the fast path declines: [0] finished by the single-record closed form, [1] general path,
-// [2] of those, cells whose query range holds only reference bands, [3] of those, exactly two bands
+// [2] finished by the all-bands closed form, [3] all-band cells that nevertheless went to the general path
 static uint64_t g_emu_stats[4];
 extern "C" void glx_emu_stats(uint64_t out[4]) { memcpy(out, g_emu_stats, sizeof g_emu_stats); }
 static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t first, uint64_t hi) {
@@ -74,10 +74,7 @@ static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t f
         n++;
         if (!(R.flags[r] & GLX_RF_IS_REF)) all_ref = false;
     }
-    if (all_ref && n >= 2) {
-        g_emu_stats[2]++;
-        if (n == 2) g_emu_stats[3]++;
-    }
+    if (all_ref && n >= 2) g_emu_stats[3]++;  // all-band cells the bands form declined
 }
 
 // signature-specialised lanes (glx_tiled_sig.cuh), lane by lane
@@ -100,6 +97,10 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
                     if (single && genotype_cell_single(C, R, S, O, s, n, R.ds_rec_off[n] + L.c)) {
                         g_emu_stats[0]++;
+                        continue;
+                    }
+                    if (!single && genotype_cell_bands(C, plan, R, S, O, blobs, s, n, R.ds_rec_off[n] + L.c, R.ds_rec_off[n + 1])) {
+                        g_emu_stats[2]++;
                         continue;
                     }
                     note_general(R, S, s, R.ds_rec_off[n] + L.c, R.ds_rec_off[n + 1]);
@@ -202,6 +203,7 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
                     const uint64_t first = plan.enabled ? lo + L.c : first_candidate(R.maxend, lo, hi, S.qbeg[s]);
                     const bool single = plan.enabled && !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
                     if (single && genotype_cell_single(C, R, S, O, s, n, first)) continue;
+                    if (!single && plan.enabled && genotype_cell_bands(C, plan, R, S, O, blobs.data(), s, n, first, hi)) continue;
                     genotype_cell_general(C, R, S, O, s, n, first, hi, cnt.data(), 1);
                     continue;
                 }

@@ -65,7 +65,7 @@ def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, path, monkeypatch
     dev.launch()
     dev.check()
     dev.download(got)
-    assert dev.launch_count >= (1 if force_general else 4)  # resolve + per chunk: tiled, single-record, general
+    assert dev.launch_count >= (1 if force_general else 5)  # resolve + per chunk: tiled, single-record, general
     dev.close()
     d = compare_outs(got, ref, b.n_fields)
     assert not d, "\n".join(d)
