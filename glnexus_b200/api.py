@@ -142,6 +142,8 @@ def lib():
     L.glx_kernel_ms.restype = C.c_int
     L.glx_work_count.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.glx_work_count.restype = C.c_int
+    L.glx_fused_count.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.glx_fused_count.restype = C.c_int
     L.glx_stream.argtypes = [vp]
     L.glx_stream.restype = vp
     _lib = L
@@ -373,6 +375,11 @@ class DeviceBatch:
     def work_count(self):
         n = C.c_uint64()
         self.ctx._check(lib().glx_work_count(self.ctx.handle, self.handle, C.byref(n)))
+        return n.value
+
+    def fused_count(self):
+        n = C.c_uint64()
+        self.ctx._check(lib().glx_fused_count(self.ctx.handle, self.handle, C.byref(n)))
         return n.value
 
     @property

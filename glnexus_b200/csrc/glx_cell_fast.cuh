@@ -27,6 +27,8 @@ namespace glxd {
 #define GLX_WORK_SINGLE 0x80000000u  // worklist cursor flag: the query range holds exactly one record (not a monoallelic site)
 #define GLX_WORK_DONE 0x40000000u    // set by the closed-form worklist kernel on an unflagged cell it finished (all-band cell)
 #define GLX_WORK_CURSOR 0x3fffffffu
+#define GLX_NWORK_MASK 0xffffu      // n_work[region]: low half = entries in the region, high half = entries the tiled kernel finished itself
+#define GLX_VIEW_COLS 6     // source columns cached in a variant record's view (glx_cell_variant.cuh)
 
 // How a field's per-sample vector is produced for a finished cell:
 //   FM_VEC      BASIC-numbered field: `count` cached values
@@ -40,6 +42,10 @@ struct FastPlan {
     uint8_t mode[GLX_MAX_FIELDS], rv0[GLX_MAX_FIELDS], nrv[GLX_MAX_FIELDS];
     uint8_t vec_rule[GLX_MAX_FIELDS];  // int field, not BASIC-numbered: an all-missing vector is [missing, vector_end, ...]
     int32_t cen[GLX_MAX_FIELDS];       // value of a censored slot
+    // record views (variant records): the source columns the genotyper reads, cached in the record's blob
+    uint8_t vview, n_vc;
+    int16_t vc[GLX_VIEW_COLS];        // cached columns
+    int8_t vc_slot[GLX_MAX_COLS];     // column -> slot in vc, -1 not cached
 };
 
 inline FastPlan make_fast_plan(const DCfg& c) {
@@ -79,6 +85,27 @@ inline FastPlan make_fast_plan(const DCfg& c) {
         }
     }
     p.n_rv = (uint8_t)n;
+    // columns a lone variant record is asked for: the genotyper's own four and every field's sources
+    for (int i = 0; i < GLX_MAX_COLS; i++) p.vc_slot[i] = -1;
+    bool ok = p.enabled && !c.xatlas;
+    auto want = [&](int col) {
+        if (col < 0 || col >= GLX_MAX_COLS || p.vc_slot[col] >= 0) return;
+        if (p.n_vc >= GLX_VIEW_COLS) {
+            ok = false;
+            return;
+        }
+        p.vc_slot[col] = (int8_t)p.n_vc;
+        p.vc[p.n_vc++] = (int16_t)col;
+    };
+    want(c.col_pl);
+    want(c.col_allele_dp);
+    want(c.col_gq);
+    want(c.col_ref_dp);
+    for (uint32_t k = 0; k < c.n_fields; k++) {
+        if (c.f[k].kind == GLX_FK_FT || c.f[k].kind == GLX_FK_STRING) ok = false;
+        for (int ci = 0; ci < c.f[k].n_cols; ci++) want(c.f[k].cols[ci]);
+    }
+    p.vview = ok;
     return p;
 }
 
@@ -110,8 +137,24 @@ __device__ __forceinline__ uint64_t first_candidate(const int32_t* __restrict__ 
 // glx_resolve_records_kernel (thread per record) instead of once per (site, sample) cell as the reference does:
 //   [0] beg  [1] end  [2] running max end  [3] RB_* bits  [4] MIN_DP as min_ref_depth  [5] beg of the sample's next
 //   record (INT_MAX after the last)  [6..6+n_rv) the cached field values of the FastPlan.  16-byte aligned rows.
+//
+// A record that is not a reference band (RB_SLOW) carries a VIEW of itself instead when the plan has one (RB_VIEW): the
+// worklist kernel for lone variant records reads the whole record with four 16-byte loads instead of one scattered
+// load per array of the columnar store:
+//   [4] GT word  [6] allele_off  [7..9] flags (8 bits), n_allele (8), then GLX_VIEW_COLS 12-bit column lengths
+//   [10..16) col_val of the cached columns (FastPlan::vc)
 #define GLX_BLOB_HDR 6
-inline __host__ __device__ uint32_t blob_words(uint32_t n_rv) { return (GLX_BLOB_HDR + n_rv + 3u) & ~3u; }
+#define GLX_BLOB_MIN 16  // words; room for the view
+inline __host__ __device__ uint32_t blob_words(uint32_t n_rv) {
+    const uint32_t w = (GLX_BLOB_HDR + n_rv + 3u) & ~3u;
+    return w < GLX_BLOB_MIN ? GLX_BLOB_MIN : w;
+}
+// 12-bit code of a glx_records.col_len entry: lengths up to 0xFF0, the three sentinels, or 0xFFC = does not fit
+__host__ __device__ inline uint32_t view_len_code(uint32_t len) {
+    if (len >= 0xFFFDu) return 0xF00u | (len & 0xFFu);
+    return len <= 0xFF0u ? len : 0xFFCu;
+}
+__host__ __device__ inline uint32_t view_len_of(uint32_t code) { return code >= 0xFFDu ? (0xF000u | code) : code; }
 
 struct LaneCursor {
     uint64_t base;  // first record of the lane's sample
@@ -177,7 +220,7 @@ __device__ __forceinline__ void cursor_seek(const int32_t* __restrict__ blobs, u
 }
 
 enum { CT_SLOW = 0, CT_MISSING = 1, CT_PARTIAL = 2, CT_REF = 3 };
-enum { RB_SLOW = 1, RB_NONCALLED = 2, RB_FOUND0 = 256 };  // RB_FOUND0 << k: field k found a source column on this band
+enum { RB_SLOW = 1, RB_NONCALLED = 2, RB_VIEW = 4, RB_FOUND0 = 256 };  // RB_FOUND0 << k: field k found a source column on this band
 
 // Resolve a reference band into the lane's value cache. Returns RB_* bits; mrd = its MIN_DP as min_ref_depth.
 __device__ inline uint32_t resolve_ref_band(const DCfg& cfg, const FastPlan& plan, const DRecs& R, uint64_t r, int32_t* rv, int rvs, int& mrd) {
@@ -318,7 +361,30 @@ __device__ inline void build_record_blob(const DCfg& cfg, const FastPlan& plan, 
     const uint32_t W = blob_words(plan.n_rv);
     for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
     int mrd = -1;
-    const uint32_t bits = resolve_ref_band(cfg, plan, R, r, blob + GLX_BLOB_HDR, 1, mrd);
+    uint32_t bits = resolve_ref_band(cfg, plan, R, r, blob + GLX_BLOB_HDR, 1, mrd);
+    if ((bits & RB_SLOW) && plan.vview && !(R.flags[r] & GLX_RF_IS_REF)) {  // a variant record: its view
+        for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
+        uint32_t pk[4] = {(uint32_t)(R.flags[r] & 0x7f) | (uint32_t)R.n_allele[r] << 8, 0u, 0u, 0u};
+        bool fits = true;
+        for (uint32_t j = 0; j < plan.n_vc; j++) {
+            const size_t idx = (size_t)plan.vc[j] * R.n_records + r;
+            const uint32_t code = view_len_code(R.col_len[idx]);
+            if (code == 0xFFCu) fits = false;
+            const uint32_t bit = 16 + 12 * j;
+            pk[bit >> 5] |= code << (bit & 31);
+            if ((bit & 31) > 20) pk[(bit >> 5) + 1] |= code >> (32 - (bit & 31));
+            blob[10 + j] = R.col_val[idx];
+        }
+        if (fits) {
+            mrd = (int)R.gt[r];
+            blob[6] = (int32_t)R.allele_off[r];
+            blob[7] = (int32_t)pk[0];
+            blob[8] = (int32_t)pk[1];
+            blob[9] = (int32_t)pk[2];
+            bits |= RB_VIEW;
+        } else
+            for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
+    }
     blob[0] = R.beg[r];
     blob[1] = R.end[r];
     blob[2] = R.maxend[r];

@@ -65,7 +65,8 @@ __device__ __forceinline__ int col_get(const DRecs& R, int col, uint64_t r, cons
 }
 
 // site.unification.find(allele(record range, dna)) — src/genotyper.cc:65-72
-__device__ inline int unif_lookup(const DRecs& R, const DSites& S, uint32_t u0, uint32_t u1, int rbeg, int rend, uint32_t a) {
+template <class RT, class ST>
+__device__ inline int unif_lookup(const RT& R, const ST& S, uint32_t u0, uint32_t u1, int rbeg, int rend, uint32_t a) {
     const uint32_t len = R.al_len[a];
     const uint64_t pre = R.al_prefix[a];
     for (uint32_t u = u0; u < u1; u++) {
@@ -110,7 +111,8 @@ __device__ __forceinline__ SiteCtx load_site(const DSites& S, uint32_t s) {
 }
 
 // allele_mapping / deletion_allele of preprocess_record. map[] has n_allele entries.
-__device__ inline void compute_allele_map(const DRecs& R, const DSites& S, const SiteCtx& st, uint64_t r, int na, bool is_ref, int8_t* map,
+template <class RT, class ST>
+__device__ inline void compute_allele_map(const RT& R, const ST& S, const SiteCtx& st, uint64_t r, int na, bool is_ref, int8_t* map,
                                           uint32_t& del_mask) {
     map[0] = 0;
     del_mask = 0;
@@ -145,7 +147,8 @@ __device__ __forceinline__ int to_int_x86(double x) {
 
 // revise_genotypes for one single-sample variant record. Returns 0 ok / positive error code.
 // g0,g1 in/out (htslib GT ints), gq out (valid when revised).
-__device__ inline int revise_record(const DCfg& cfg, const DRecs& R, const DSites& S, const SiteCtx& st, uint64_t r, int na, const int8_t* map, int& g0,
+template <class RT, class ST>
+__device__ inline int revise_record(const DCfg& cfg, const RT& R, const ST& S, const SiteCtx& st, uint64_t r, int na, const int8_t* map, int& g0,
                                     int& g1, int& gq, bool& revised) {
     revised = false;
     bool needs = false, homalt = false;
@@ -217,7 +220,8 @@ __device__ inline int revise_record(const DCfg& cfg, const DRecs& R, const DSite
 
 // AlleleDepthHelper::Load + get (genotyper_utils.h:982-1114) for a single-sample record.
 // Returns 0 ok / error code 2 (Invalid). depth out as the reference's `unsigned`.
-__device__ inline int depth_get(const DCfg& cfg, const DRecs& R, uint64_t r, int na, bool is_ref, int allele, unsigned& depth) {
+template <class RT>
+__device__ inline int depth_get(const DCfg& cfg, const RT& R, uint64_t r, int na, bool is_ref, int allele, unsigned& depth) {
     const int32_t* p = nullptr;
     depth = 0;
     if (cfg.xatlas) {
@@ -332,7 +336,8 @@ __device__ inline int numeric_add(const DFld& f, const DRecs& R, uint64_t r, int
 }
 
 // PLFieldHelper2::add_record_data (genotyper_utils.h:555-651). returns error code or 0; sets self_censor.
-__device__ inline int pl2_add(const DCfg& cfg, const DRecs& R, uint64_t r, int na, uint8_t flags, const int8_t* map, int A, int count, int32_t* out,
+template <class RT>
+__device__ inline int pl2_add(const DCfg& cfg, const RT& R, uint64_t r, int na, uint8_t flags, const int8_t* map, int A, int count, int32_t* out,
                               bool& self_censor) {
     const int32_t* buf = nullptr;
     const int rv = col_get(R, cfg.col_pl, r, buf);
@@ -922,13 +927,15 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
 // variant_records = {r}, each output slot receives at most one value, nothing is censored, and the cell is one pass
 // over the record with no count scratch. Same reference lines as genotype_cell_general. Returns false (nothing
 // written) when the cell is not of this shape.
-__device__ inline bool genotype_cell_single(const DCfg& cfg, const DRecs& R, const DSites& S, const DOut& O, uint32_t s, uint32_t sample, uint64_t r) {
+template <class RT, class ST>
+__device__ inline bool genotype_cell_single(const DCfg& cfg, const RT& R, const ST& S, const DOut& O, uint32_t s, uint32_t sample, uint64_t r) {
     if (cfg.squeeze) return false;
     const SiteCtx st = load_site(S, s);
     if (st.mono) return false;
     const uint8_t flags = R.flags[r];
     if (flags & GLX_RF_IS_REF) return false;
     const int na = R.n_allele[r];
+    if (na < 2) return false;  // REF-only record: numeric_add pads it to two alleles; left to the general path
     const int rbeg = R.beg[r], rend = R.end[r];
     int8_t map[GLX_MAX_ALLELES];
     uint32_t del_mask;

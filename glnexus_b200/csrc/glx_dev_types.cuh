@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../include/glx.h"
 
@@ -66,6 +67,9 @@ struct DSites {
     const uint16_t* fld_cnt[GLX_MAX_FIELDS];
     const uint64_t* fld_off[GLX_MAX_FIELDS];
     const uint32_t* slot_base;  // [S][n_fields+1] prefix sums of fld_cnt over fields (scratch layout of the general path)
+    // packed copies built by glx_upload (build_site_rows) so that a thread gets a site / a unification entry in two 16-byte loads:
+    const int4* site_rows;  // [S][2]: {beg, end, qbeg, qend} {n_allele | monoallelic << 8, allele_off, unif_off, unif_off[s+1]}
+    const int4* unif_rows;  // [n_unif][2]: {beg, end, len, to} {prefix lo, prefix hi, str, 0}
 };
 
 struct DOut {
@@ -114,6 +118,20 @@ inline DCfg make_dcfg(const glx_config& c) {
         if (f.kind == GLX_FK_STRING) d.has_string_field = 1;
     }
     return d;
+}
+
+// host side: the packed site / unification rows of DSites
+inline void build_site_rows(const glx_sites& s, std::vector<int4>& site_rows, std::vector<int4>& unif_rows) {
+    site_rows.resize((size_t)s.n_sites * 2 + 2);
+    unif_rows.resize((size_t)s.n_unif * 2 + 2);
+    for (uint32_t i = 0; i < s.n_sites; i++) {
+        site_rows[2 * (size_t)i] = int4{s.beg[i], s.end[i], s.qbeg[i], s.qend[i]};
+        site_rows[2 * (size_t)i + 1] = int4{(int)s.n_allele[i] | (s.monoallelic[i] ? 256 : 0), (int)s.allele_off[i], (int)s.unif_off[i], (int)s.unif_off[i + 1]};
+    }
+    for (uint64_t u = 0; u < s.n_unif; u++) {
+        unif_rows[2 * u] = int4{s.unif_beg[u], s.unif_end[u], (int)s.unif_len[u], (int)s.unif_to[u]};
+        unif_rows[2 * u + 1] = int4{(int)(uint32_t)s.unif_prefix[u], (int)(uint32_t)(s.unif_prefix[u] >> 32), (int)s.unif_str[u], 0};
+    }
 }
 
 }  // namespace glxd

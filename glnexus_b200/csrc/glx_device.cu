@@ -18,6 +18,7 @@
 #include "../../include/glx.h"
 #include "glx_cell_fast.cuh"
 #include "glx_cell_general.cuh"
+#include "glx_cell_variant.cuh"
 #include "glx_dev_types.cuh"
 #include "glx_tiled_sig.cuh"
 
@@ -174,14 +175,38 @@ __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, c
                                                                const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint32_t region_cells) {
     const uint32_t N = S.n_samples;
     for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-        const uint32_t n_items = n_work[reg];
+        const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
+        uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
+        for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
+            const uint2 e = w[it];
+            if ((e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) != GLX_WORK_SINGLE) continue;
+            const uint32_t s = e.x / N, sample = e.x % N;
+            const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
+            if (!genotype_cell_single(cfg, R, S, O, s, sample, first)) w[it].y = e.y & GLX_WORK_CURSOR;
+        }
+    }
+}
+
+// Worklist, pass 0: the same cells as pass 1, through the record's view (glx_cell_variant.cuh): all loads of the closed
+// form issued up front. Finished cells get GLX_WORK_DONE; a record without a view is left to pass 1.
+#ifndef GLX_VARIANT_MIN_BLOCKS
+#define GLX_VARIANT_MIN_BLOCKS 6  // 80 registers; measured best for the 8-allele instantiation
+#endif
+template <int CAPA>
+__global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
+                                                                uint2* __restrict__ worklist, const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions,
+                                                                uint32_t region_cells, const int32_t* __restrict__ blobs) {
+    extern __shared__ int32_t s_cols[];  // [VariantSmem<CAPA>::SLOTS][blockDim.x]: one column per thread
+    const uint32_t N = S.n_samples;
+    for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
             if (!(e.y & GLX_WORK_SINGLE)) continue;
             const uint32_t s = e.x / N, sample = e.x % N;
             const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
-            if (!genotype_cell_single(cfg, R, S, O, s, sample, first)) w[it].y = e.y & GLX_WORK_CURSOR;
+            if (genotype_cell_variant<CAPA>(cfg, plan, R, S, O, blobs, s, sample, first, s_cols + threadIdx.x, blockDim.x)) w[it].y = e.y | GLX_WORK_DONE;
         }
     }
 }
@@ -193,7 +218,7 @@ __global__ void __launch_bounds__(128) glx_cells_bands_kernel(const DCfg cfg, co
                                                               uint32_t region_cells, const int32_t* __restrict__ blobs) {
     const uint32_t N = S.n_samples;
     for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-        const uint32_t n_items = n_work[reg];
+        const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
     const uint32_t N = S.n_samples;
     if (worklist) {
         for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-            const uint32_t n_items = n_work[reg];
+            const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
             const uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
             for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
                 const uint2 e = w[it];
@@ -367,6 +392,9 @@ struct glx_dev_batch {
     bool force_general = false;
     uint32_t n_chunks = 1;
     std::vector<uint8_t> flags_dev;  // host staging that must outlive an asynchronous upload
+    std::vector<int4> site_rows_h, unif_rows_h;
+    uint32_t max_site_alleles = 0;
+    bool fused_variant = false;  // the tiled kernel finishes its own lone-variant cells
     std::vector<int32_t> tq_host;
     unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
     int16_t* narrow = nullptr;               // device int16 images of the integer fields + overflow words
@@ -585,6 +613,9 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     add(sites->unif_prefix, nU * 8, &Sx.unif_prefix);
     add(sites->unif_str, nU * 4, &Sx.unif_str);
     add(sites->unif_pool, sites->n_unif_pool, &Sx.unif_pool);
+    build_site_rows(*sites, d->site_rows_h, d->unif_rows_h);
+    add(d->site_rows_h.data(), d->site_rows_h.size() * sizeof(int4), &Sx.site_rows);
+    add(d->unif_rows_h.data(), d->unif_rows_h.size() * sizeof(int4), &Sx.unif_rows);
     for (uint32_t k = 0; k < cfg->n_fields; k++) {
         add(sites->fld_cnt[k], S * 2, &Sx.fld_cnt[k]);
         add(sites->fld_off[k], (S + 1) * 8, &Sx.fld_off[k]);
@@ -619,6 +650,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         if (t > max_slots) max_slots = t;
     }
     d->max_slots = max_slots;
+    for (uint64_t s = 0; s < S; s++) d->max_site_alleles = std::max<uint32_t>(d->max_site_alleles, sites->n_allele[s]);
 
     // ---- output arena ----
     size_t ob = 0;
@@ -665,12 +697,22 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         d->tiled_smem = (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4;
         const char* dyn = getenv("GLX_FORCE_DYNAMIC_TILED");
         if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
+            const char* nf_env = getenv("GLX_NO_FUSE");
+            const bool fuse = d->plan.vview && d->max_site_alleles <= 4 && !(nf_env && *nf_env && *nf_env != '0');
             auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
             if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
-                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant>;
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant, 0>;
+                if (fuse) {
+                    d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant, 4>;
+                    d->fused_variant = true;
+                }
                 d->tiled_smem = 0;
             } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
-                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk>;
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk, 0>;
+                if (fuse) {
+                    d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk, 4>;
+                    d->fused_variant = true;
+                }
                 d->tiled_smem = 0;
             }
         }
@@ -764,6 +806,15 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             const uint32_t region_cells = GLX_TILE_SITES * d->samples_per_cta;
             glx_cells_bands_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->blobs);
             d->launches_per_call++;
+            if (d->plan.vview && !d->fused_variant) {  // small sites keep the per-thread shared-memory columns short
+                if (d->max_site_alleles <= 4)
+                    glx_cells_variant_kernel<4><<<g1, 128, VariantSmem<4>::SLOTS * 128 * 4, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1,
+                                                                                                   region_cells, d->blobs);
+                else
+                    glx_cells_variant_kernel<8><<<g1, 128, VariantSmem<8>::SLOTS * 128 * 4, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1,
+                                                                                                   region_cells, d->blobs);
+                d->launches_per_call++;
+            }
             glx_cells_single_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells);
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[3], st));
             const uint32_t g2 = nreg < (uint32_t)d->general_blocks ? nreg : (uint32_t)d->general_blocks;
@@ -972,7 +1023,21 @@ int glx_work_count(glx_ctx* ctx, glx_dev_batch* d, uint64_t* n) {
     std::vector<uint32_t> h(n_regions);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h.data(), d->n_work, n_regions * 4, cudaMemcpyDeviceToHost));
-    for (uint32_t v : h) *n += v;
+    for (uint32_t v : h) *n += v & GLX_NWORK_MASK;
+    return GLX_OK;
+}
+
+// of those, the cells the tiled kernel finished itself (fused lone-variant-record closed form)
+int glx_fused_count(glx_ctx* ctx, glx_dev_batch* d, uint64_t* n) {
+    if (!ctx || !d || !n) return GLX_E_INVALID;
+    *n = 0;
+    if (!d->plan.enabled || !d->n_cells) return GLX_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
+    std::vector<uint32_t> h(n_regions);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h.data(), d->n_work, n_regions * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t v : h) *n += v >> 16;
     return GLX_OK;
 }
 

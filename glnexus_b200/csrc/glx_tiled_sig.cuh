@@ -6,6 +6,7 @@
 // run the dynamic kernel there. Reference lines: see glx_cell_fast.cuh.
 #pragma once
 #include "glx_cell_fast.cuh"
+#include "glx_cell_variant.cuh"
 
 namespace glxd {
 
@@ -36,7 +37,7 @@ struct TiledSig {
     static __host__ __device__ constexpr uint32_t nrv(uint32_t k) { return (uint32_t)((NRVS >> (4 * k)) & 15u); }
     static __host__ __device__ constexpr uint32_t rv0(uint32_t k) { return k == 0 ? 0u : rv0(k - 1) + nrv(k - 1); }
     static constexpr uint32_t n_rv = rv0(NF);
-    static constexpr uint32_t W = (GLX_BLOB_HDR + n_rv + 3u) & ~3u;
+    static constexpr uint32_t W = ((GLX_BLOB_HDR + n_rv + 3u) & ~3u) < GLX_BLOB_MIN ? GLX_BLOB_MIN : ((GLX_BLOB_HDR + n_rv + 3u) & ~3u);
     static constexpr uint32_t NRV_ARR = n_rv ? n_rv : 1;
 };
 
@@ -234,8 +235,13 @@ struct TiledLane {
 };
 
 #ifdef __CUDACC__
-template <class Sig>
-__global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
+// FUSE = 4: when the tile is done the CTA also finishes its own lone-variant-record cells (genotype_cell_variant<4>),
+// while the tile's output lines and record blobs are still in L2. FUSE = 0: they are left to glx_cells_variant_kernel.
+#ifndef GLX_FUSED_MIN_BLOCKS
+#define GLX_FUSED_MIN_BLOCKS 7  // 72 registers: the walk over the tile wants the occupancy more than the fused closed form wants registers
+#endif
+template <class Sig, int FUSE>
+__global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS : 1) glx_cells_tiled_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
                                                                                const int32_t* __restrict__ blobs, const uint32_t* __restrict__ tile_cursors,
                                                                                uint2* __restrict__ worklist,
                                                                                uint32_t* __restrict__ n_work, uint32_t n_sample_blocks, uint32_t cta0) {
@@ -320,7 +326,29 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS) glx_cells_tiled_sig_kernel(c
         }
     }
     __syncthreads();
-    if (tid == 0) n_work[cta] = s_nslow;
+    if (FUSE == 0 && tid == 0) n_work[cta] = s_nslow;
+    if constexpr (FUSE > 0) {
+        __shared__ uint32_t s_ndone;
+        if (tid == 0) s_ndone = 0;
+        __syncthreads();
+        uint32_t my_done = 0;
+        static_assert(VariantSmem<(FUSE > 0 ? FUSE : 1)>::SLOTS * GLX_TILE_THREADS <= (GLX_TILE_THREADS / 32) * 32 * GLX_STAGE_MAX, "columns live in s_stage");
+        const uint32_t n_items = s_nslow;
+        int32_t* cols = &s_stage[0][0] + tid;
+        for (uint32_t it = tid; it < n_items; it += GLX_TILE_THREADS) {
+            const uint2 e = my_work[it];
+            if (!(e.y & GLX_WORK_SINGLE)) continue;
+            const uint32_t ws = e.x / N, wsample = e.x - ws * N;
+            const uint64_t first = R.ds_rec_off[wsample] + (e.y & GLX_WORK_CURSOR);
+            if (genotype_cell_variant<(FUSE > 0 ? FUSE : 1)>(cfg, plan, R, S, O, blobs, ws, wsample, first, cols, GLX_TILE_THREADS)) {
+                my_work[it].y = e.y | GLX_WORK_DONE;
+                my_done++;
+            }
+        }
+        if (my_done) atomicAdd(&s_ndone, my_done);
+        __syncthreads();
+        if (tid == 0) n_work[cta] = s_nslow | (s_ndone << 16);  // high half: cells this CTA finished itself
+    }
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         uint32_t cm = 0, lm = 0;
 #pragma unroll

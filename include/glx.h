@@ -249,10 +249,12 @@ int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock cal
 void glx_host_unregister(void* p);
 /* Measurement aids: record CUDA events around each kernel of glx_launch on the launching stream; glx_kernel_ms waits
  * for the last launch and returns the durations of {record resolve, tiled fast path, single-record worklist, general
- * worklist} kernels; glx_work_count = cells the tiled kernel left to the worklist kernels. */
+ * worklist} kernels; glx_work_count = cells the tiled kernel put on its worklist, glx_fused_count = those of them it then
+ * finished itself (lone-variant-record cells, when that closed form is fused into the tiled kernel). */
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);
 int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[4]);
 int glx_work_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);
+int glx_fused_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);
 void* glx_stream(glx_ctx* ctx); /* the context's cudaStream_t */
 /* pinned host memory for caller-owned buffers (cudaHostAlloc) */
 void* glx_pinned_alloc(size_t bytes);

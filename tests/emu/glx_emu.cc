@@ -7,6 +7,7 @@
 
 #include "../../glnexus_b200/csrc/glx_cell_fast.cuh"
 #include "../../glnexus_b200/csrc/glx_cell_general.cuh"
+#include "../../glnexus_b200/csrc/glx_cell_variant.cuh"
 #include "../../glnexus_b200/csrc/glx_tiled_sig.cuh"
 
 using namespace glxd;
@@ -26,6 +27,10 @@ static void bind(const glx_config* cfg, const glx_records* r, const glx_sites* s
     S.unif_off = s->unif_off; S.unif_beg = s->unif_beg; S.unif_end = s->unif_end; S.unif_to = s->unif_to; S.unif_len = s->unif_len;
     S.unif_prefix = s->unif_prefix; S.unif_str = s->unif_str; S.unif_pool = s->unif_pool;
     for (int k = 0; k < GLX_MAX_FIELDS; k++) { S.fld_cnt[k] = s->fld_cnt[k]; S.fld_off[k] = s->fld_off[k]; }
+    static std::vector<int4> site_rows, unif_rows;  // as glx_upload packs them
+    build_site_rows(*s, site_rows, unif_rows);
+    S.site_rows = site_rows.data();
+    S.unif_rows = unif_rows.data();
     memset(&O, 0, sizeof O);
     O.gt = o->gt; O.rnc = o->rnc; O.allele_used = o->allele_used; O.site_flags = o->site_flags; O.error = err;
     for (int k = 0; k < GLX_MAX_FIELDS; k++) O.fld[k] = o->fld[k];
@@ -63,8 +68,9 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
 
 // composition of the cells the fast path declines: [0] finished by the single-record closed form, [1] general path,
 // [2] finished by the all-bands closed form, [3] all-band cells that nevertheless went to the general path
-static uint64_t g_emu_stats[4];
-extern "C" void glx_emu_stats(uint64_t out[4]) { memcpy(out, g_emu_stats, sizeof g_emu_stats); }
+static int32_t vsm[64];  // the shared-memory column of genotype_cell_variant, stride 1
+static uint64_t g_emu_stats[8];  // [0] single-record closed form [1] general [2] all-band closed form [3] bands declined [4] of [0]: through the record view
+extern "C" void glx_emu_stats(uint64_t out[8]) { memcpy(out, g_emu_stats, sizeof g_emu_stats); }
 static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t first, uint64_t hi) {
     g_emu_stats[1]++;
     int n = 0;
@@ -95,6 +101,11 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                 if (type == CT_SLOW) {
                     n_slow++;
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
+                    if (single && genotype_cell_variant<8>(C, plan, R, S, O, blobs, s, n, R.ds_rec_off[n] + L.c, vsm, 1)) {
+                        g_emu_stats[0]++;
+                        g_emu_stats[4]++;
+                        continue;
+                    }
                     if (single && genotype_cell_single(C, R, S, O, s, n, R.ds_rec_off[n] + L.c)) {
                         g_emu_stats[0]++;
                         continue;
@@ -202,6 +213,7 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
                     // the kernel passes the lane's cursor instead of searching again
                     const uint64_t first = plan.enabled ? lo + L.c : first_candidate(R.maxend, lo, hi, S.qbeg[s]);
                     const bool single = plan.enabled && !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
+                    if (single && genotype_cell_variant<4>(C, plan, R, S, O, blobs.data(), s, n, first, vsm, 1)) continue;
                     if (single && genotype_cell_single(C, R, S, O, s, n, first)) continue;
                     if (!single && plan.enabled && genotype_cell_bands(C, plan, R, S, O, blobs.data(), s, n, first, hi)) continue;
                     genotype_cell_general(C, R, S, O, s, n, first, hi, cnt.data(), 1);
