@@ -29,32 +29,78 @@ using namespace glxd;
 // ---------------------------------------------------------------------------------------------
 
 // Thread per record: resolve each record into its blob (glx_cell_fast.cuh). Part of every glx_launch. Blobs are built
-// in shared memory and written out by the whole block as one contiguous, fully coalesced span.
+// in shared memory and written out by the whole block as one contiguous, fully coalesced span. The same threads fill
+// the tile cursor table (fill_tile_cursors states what is written): record r claims the tiles [t_lo, t_hi) with
+// t_hi = first tile whose tq >= maxend[r] and t_lo = the previous record's t_hi, so each thread runs one search and
+// takes t_lo from its neighbour; when the whole block lies in one sample, maxend is non-decreasing across it and the
+// searches are confined to the block's own range of tiles.
 #define GLX_RESOLVE_THREADS 256
+__device__ __forceinline__ uint32_t first_tile_at_or_after(const int32_t* __restrict__ tq, uint32_t lo, uint32_t hi, int v) {
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tq[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
 __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets,
                                                                                   int32_t* __restrict__ blobs, const int32_t* __restrict__ tile_q,
                                                                                   uint32_t n_tiles, uint32_t* __restrict__ tile_cursors) {
     extern __shared__ int32_t s_blob[];  // [GLX_RESOLVE_THREADS][W + 1]: rows padded by one word so that column writes spread over the banks
+    __shared__ uint32_t s_edge[4];       // sample of the block's first / last record, and their t_hi
+    __shared__ uint32_t s_thi[GLX_RESOLVE_THREADS];
     const uint32_t W = blob_words(plan.n_rv), WP = W + 1;
+    const uint32_t tid = threadIdx.x;
     const uint64_t r0 = (uint64_t)blockIdx.x * GLX_RESOLVE_THREADS;
-    const uint64_t r = r0 + threadIdx.x;
-    if (r < R.n_records) {
-        build_record_blob(cfg, plan, R, r, R.flags[r] & GLX_RF_DEV_LAST, s_blob + threadIdx.x * WP);  // glx_upload marks each sample's last record
+    const uint64_t r = r0 + tid;
+    const uint64_t n_here = min((uint64_t)GLX_RESOLVE_THREADS, R.n_records - r0);
 #ifndef GLX_ABLATE_CURSORS
-        // which sample is r in? (ds_rec_off is small and cache-resident)
-        uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= r < ds_rec_off[hi]
+    if (tid < 2) {  // which samples hold the block's first and last record? (ds_rec_off is small and cache-resident)
+        const uint64_t rq = tid ? r0 + n_here - 1 : r0;
+        uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= rq < ds_rec_off[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (R.ds_rec_off[mid] <= rq) lo = mid;
+            else hi = mid;
+        }
+        s_edge[tid] = lo;
+        s_edge[2 + tid] = first_tile_at_or_after(tile_q, 0, n_tiles, R.maxend[rq]);
+    }
+#endif
+    if (r < R.n_records) build_record_blob(cfg, plan, R, r, R.flags[r] & GLX_RF_DEV_LAST, s_blob + tid * WP);  // glx_upload marks each sample's last record
+    __syncthreads();
+#ifndef GLX_ABLATE_CURSORS
+    uint32_t sample = 0, t_hi = 0;
+    uint64_t base = 0;
+    if (r < R.n_records) {
+        uint32_t lo = s_edge[0], hi = s_edge[1] + 1;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (R.ds_rec_off[mid] <= r) lo = mid;
             else hi = mid;
         }
-        fill_tile_cursors(R, r, R.ds_rec_off[lo], lo, n_datasets, tile_q, n_tiles, tile_cursors);
-#endif
+        sample = lo;
+        base = R.ds_rec_off[lo];
+        const bool one_sample = s_edge[0] == s_edge[1];
+        t_hi = first_tile_at_or_after(tile_q, one_sample ? s_edge[2] : 0u, one_sample ? s_edge[3] : n_tiles, R.maxend[r]);
+        s_thi[tid] = t_hi;
     }
     __syncthreads();
-    const uint64_t n_here = min((uint64_t)GLX_RESOLVE_THREADS, R.n_records - r0);
+    if (r < R.n_records) {
+        uint32_t t_lo = 0;
+        if (r > base) t_lo = tid > 0 ? s_thi[tid - 1] : first_tile_at_or_after(tile_q, 0, t_hi, R.maxend[r - 1]);
+        for (uint32_t tile = t_lo; tile < t_hi; tile++) tile_cursors[(size_t)tile * n_datasets + sample] = (uint32_t)(r - base);
+    }
+#endif
+    // write-out: each warp stores whole rows, a 16-byte quad per lane
     int32_t* __restrict__ dst = blobs + r0 * W;
-    for (uint32_t e = threadIdx.x; e < n_here * W; e += GLX_RESOLVE_THREADS) dst[e] = s_blob[(e / W) * WP + e % W];
+    const uint32_t qpr = W / 4, lane = tid & 31, rows_per_pass = 32 / qpr;
+    const uint32_t lrow = lane / qpr, lquad = lane - lrow * qpr;
+    if (lrow < rows_per_pass)
+        for (uint32_t row = (tid >> 5) * rows_per_pass + lrow; row < n_here; row += (GLX_RESOLVE_THREADS / 32) * rows_per_pass) {
+            const int32_t* src = s_blob + row * WP + lquad * 4;
+            *reinterpret_cast<int4*>(dst + (size_t)row * W + lquad * 4) = make_int4(src[0], src[1], src[2], src[3]);
+        }
 }
 
 // Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
