@@ -356,8 +356,183 @@ __device__ inline void fill_tile_cursors(const DRecs& R, uint64_t r, uint64_t sa
     for (uint32_t tile = t_lo; tile < t_hi; tile++) cursors[(size_t)tile * n_samples + sample] = (uint32_t)(r - sample_base);
 }
 
+// a[j] for a register array and a run-time j
+template <int N>
+__device__ __forceinline__ int32_t pick(const int32_t (&a)[N], int j) {
+    int32_t r = a[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) r = (j == i) ? a[i] : r;
+    return r;
+}
+
+// htslib-style return value of a column length (col_get's contract)
+__device__ __forceinline__ int view_rv(uint32_t len) {
+    if (len == GLX_LEN_ABSENT) return -3;
+    if (len == 0xFFFE) return -2;
+    if (len == 0xFFFD) return 0x7fffffff;
+    return (int)len;
+}
+
+// build_record_blob for a plan with record views (FastPlan::vview: every column the genotyper can ask for is one of
+// the plan's n_vc <= GLX_VIEW_COLS view columns). Same result as the general form below, but all of the record's
+// scalars and its (length, value) pairs of the view columns are fetched up front as independent loads, and both the
+// reference-band resolution and the variant view are computed from those registers; only a band's PL triple and
+// multi-value BASIC fields need a second round of loads.
+__device__ inline void build_record_blob_cached(const DCfg& cfg, const FastPlan& plan, const DRecs& R, uint64_t r, bool last_of_sample, int32_t* blob) {
+    const uint32_t W = blob_words(plan.n_rv);
+    const uint8_t flags = R.flags[r];
+    const int na = R.n_allele[r];
+    const uint32_t gtw = R.gt[r];
+    const int rbeg = R.beg[r], rend = R.end[r], rmaxend = R.maxend[r];
+    const int beg_next = last_of_sample ? 0x7fffffff : R.beg[r + 1];
+    const uint32_t a_off = R.allele_off[r];
+    int32_t clen[GLX_VIEW_COLS], cval[GLX_VIEW_COLS];
+#pragma unroll
+    for (int j = 0; j < GLX_VIEW_COLS; j++) {
+        const bool on = j < plan.n_vc;
+        const size_t idx = (on ? (size_t)plan.vc[j] * R.n_records : 0) + r;
+        const uint16_t l = R.col_len[idx];
+        const int32_t v = R.col_val[idx];
+        clen[j] = on ? (int32_t)l : (int32_t)GLX_LEN_ABSENT;
+        cval[j] = on ? v : 0;
+    }
+    auto column = [&](int col, int& rv, int32_t& val) {
+        rv = -1;
+        val = 0;
+        if (col < 0) return;
+        const int j = plan.vc_slot[col];
+        rv = view_rv((uint32_t)pick(clen, j));
+        val = pick(cval, j);
+    };
+    for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
+    int mrd = -1;
+    uint32_t bits = RB_SLOW;
+    // ---- a well-formed reference band? (resolve_ref_band) ----
+    do {
+        if (!(flags & GLX_RF_IS_REF) || na != 2 || (flags & GLX_RF_NO_GT)) break;
+        int g0, g1;
+        decode_gt(gtw, flags, g0, g1);
+        if ((!gt_is_missing(g0) && (g0 == GLXD_INT_VEND || gt_allele(g0) >= na)) || (!gt_is_missing(g1) && (g1 == GLXD_INT_VEND || gt_allele(g1) >= na))) break;
+        uint32_t b = 0;
+        if (!(flags & GLX_RF_HAPLOID) && (gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0)) b |= RB_NONCALLED;
+        int ref_rv;
+        int32_t ref_val;
+        column(cfg.col_ref_dp, ref_rv, ref_val);
+        if (ref_rv != 1) break;  // "reference depth FORMAT field is missing or malformed"
+        bool ok = true;
+        int32_t* rvp = blob + GLX_BLOB_HDR;
+        for (uint32_t k = 0; k < cfg.n_fields && ok; k++) {
+            const DFld& f = cfg.f[k];
+            int32_t* c = rvp + plan.rv0[k];
+            const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
+            const int32_t dflt = f.default_zero ? 0 : missing;
+            if (f.kind == GLX_FK_PL2) {
+                int rvv;
+                int32_t val;
+                column(cfg.col_pl, rvv, val);
+                int32_t p0 = 0, p1 = 0, p2 = 0;
+                if (rvv > 0) {
+                    if (rvv != 3) {
+                        ok = false;
+                        break;
+                    }
+                    b |= (uint32_t)RB_FOUND0 << k;
+                    const int32_t* buf = R.pool + val;
+                    p0 = buf[0];
+                    p1 = buf[1];
+                    p2 = buf[2];
+                    const bool zero = p0 == 0 || p1 == 0 || p2 == 0;
+                    const bool other = (p0 != 0 && p0 != GLXD_INT_MISSING) || (p1 != 0 && p1 != GLXD_INT_MISSING) || (p2 != 0 && p2 != GLXD_INT_MISSING);
+                    if (!(zero && other)) p0 = p1 = p2 = 0;
+                    else {
+                        if (p0 == GLXD_INT_MISSING) p0 = 990;
+                        if (p1 == GLXD_INT_MISSING) p1 = 990;
+                        if (p2 == GLXD_INT_MISSING) p2 = 990;
+                    }
+                }
+                c[0] = p0;
+                c[1] = p1;
+                c[2] = p1;
+                c[3] = p2;
+                continue;
+            }
+            // numeric kinds (plans with a view have no FT / string field)
+            int n_val = f.count;
+            if (f.number == GLX_NUM_ALT) n_val = 1;
+            else if (f.number == GLX_NUM_ALLELES) n_val = 2;
+            else if (f.number == GLX_NUM_GENOTYPE) n_val = 3;
+            bool found = false;
+            int32_t val = 0;
+            for (int ci = 0; ci < f.n_cols && !found && ok; ci++) {
+                int rvv;
+                column(f.cols[ci], rvv, val);
+                if (rvv == -2) ok = false;
+                else if (rvv >= 0) {
+                    if (rvv != n_val) ok = false;
+                    found = true;
+                }
+            }
+            if (ok && !found && f.kind == GLX_FK_AD) {  // AD falls back to the reference depth as a 1-value field
+                n_val = 1;
+                val = ref_val;  // ref_rv == 1 was checked above
+                found = true;
+            }
+            if (!ok) break;
+            if (found) b |= (uint32_t)RB_FOUND0 << k;
+            if (f.kind == GLX_FK_PL) continue;  // a lone band never yields a liftable PL vector; validated only
+            // the first value (n_val == 1: col_val itself, else the head of its pool vector)
+            const int32_t* vec = R.pool + val;
+            if (f.number == GLX_NUM_BASIC) {
+                for (int j = 0; j < f.count; j++) c[j] = found ? (n_val == 1 ? val : vec[j]) : dflt;
+            } else {
+                const int32_t x0 = found ? (n_val == 1 ? val : vec[0]) : dflt;
+                c[0] = x0;
+                c[1] = (plan.vec_rule[k] && x0 == GLXD_INT_MISSING && dflt == GLXD_INT_MISSING) ? GLXD_INT_VEND : dflt;
+                c[2] = dflt;
+                c[3] = dflt;
+            }
+        }
+        if (!ok) {
+            for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
+            break;
+        }
+        mrd = (int)(unsigned)ref_val;
+        bits = b;
+    } while (0);
+    // ---- a variant record: its view ----
+    if ((bits & RB_SLOW) && !(flags & GLX_RF_IS_REF)) {
+        bool fits = true;
+        uint32_t code[GLX_VIEW_COLS];
+#pragma unroll
+        for (int j = 0; j < GLX_VIEW_COLS; j++) {
+            code[j] = j < plan.n_vc ? view_len_code((uint32_t)clen[j]) : 0u;
+            if (code[j] == 0xFFCu) fits = false;
+        }
+        if (fits) {
+            mrd = (int)gtw;
+            blob[6] = (int32_t)a_off;
+            blob[7] = (int32_t)((uint32_t)(flags & 0x7f) | (uint32_t)na << 8 | code[0] << 16 | code[1] << 28);
+            blob[8] = (int32_t)(code[1] >> 4 | code[2] << 8 | code[3] << 20);
+            blob[9] = (int32_t)(code[4] | code[5] << 12);
+#pragma unroll
+            for (int j = 0; j < GLX_VIEW_COLS; j++) blob[10 + j] = j < plan.n_vc ? cval[j] : 0;
+            bits |= RB_VIEW;
+        }
+    }
+    blob[0] = rbeg;
+    blob[1] = rend;
+    blob[2] = rmaxend;
+    blob[3] = (int32_t)bits;
+    blob[4] = mrd;
+    blob[5] = beg_next;
+}
+
 // one record -> its blob (thread per record in glx_resolve_records_kernel)
 __device__ inline void build_record_blob(const DCfg& cfg, const FastPlan& plan, const DRecs& R, uint64_t r, bool last_of_sample, int32_t* blob) {
+    if (plan.vview) {
+        build_record_blob_cached(cfg, plan, R, r, last_of_sample, blob);
+        return;
+    }
     const uint32_t W = blob_words(plan.n_rv);
     for (uint32_t j = GLX_BLOB_HDR; j < W; j++) blob[j] = 0;
     int mrd = -1;

@@ -22,22 +22,6 @@
 
 namespace glxd {
 
-template <int N>
-__device__ __forceinline__ int32_t pick(const int32_t (&a)[N], int j) {
-    int32_t r = a[0];
-#pragma unroll
-    for (int i = 1; i < N; i++) r = (j == i) ? a[i] : r;
-    return r;
-}
-
-// htslib-style return value of a cached column length (col_get's contract)
-__device__ __forceinline__ int view_rv(uint32_t len) {
-    if (len == GLX_LEN_ABSENT) return -3;
-    if (len == 0xFFFE) return -2;
-    if (len == 0xFFFD) return 0x7fffffff;
-    return (int)len;
-}
-
 // nibble-packed allele maps: 0xF = none
 __device__ __forceinline__ int nib_get(uint32_t w, int i) {
     const int v = (int)(w >> (4 * i)) & 15;
