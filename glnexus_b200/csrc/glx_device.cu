@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, c
                                                                const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint32_t region_cells) {
     const uint32_t N = S.n_samples;
     for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-        const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
+        const uint32_t nw = n_work[reg];
+        const uint32_t n_items = nw & GLX_NWORK_MASK;
+        if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
@@ -245,7 +247,9 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
     extern __shared__ int32_t s_cols[];  // [VariantSmem<CAPA>::SLOTS][blockDim.x]: one column per thread
     const uint32_t N = S.n_samples;
     for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-        const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
+        const uint32_t nw = n_work[reg];
+        const uint32_t n_items = nw & GLX_NWORK_MASK;
+        if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
@@ -264,7 +268,9 @@ __global__ void __launch_bounds__(128) glx_cells_bands_kernel(const DCfg cfg, co
                                                               uint32_t region_cells, const int32_t* __restrict__ blobs) {
     const uint32_t N = S.n_samples;
     for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-        const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
+        const uint32_t nw = n_work[reg];
+        const uint32_t n_items = nw & GLX_NWORK_MASK;
+        if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
@@ -288,7 +294,9 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
     const uint32_t N = S.n_samples;
     if (worklist) {
         for (uint32_t reg = reg0 + blockIdx.x; reg < n_regions; reg += gridDim.x) {
-            const uint32_t n_items = n_work[reg] & GLX_NWORK_MASK;
+            const uint32_t nw = n_work[reg];
+            const uint32_t n_items = nw & GLX_NWORK_MASK;
+            if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
             const uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
             for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
                 const uint2 e = w[it];

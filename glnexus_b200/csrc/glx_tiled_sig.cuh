@@ -41,6 +41,18 @@ struct TiledSig {
     static constexpr uint32_t NRV_ARR = n_rv ? n_rv : 1;
 };
 
+// A lane reads its sample's blobs in order, one 64-byte row per cursor step, and waits for each: ask L2 to bring the
+// following rows along (256-byte prefetch granule), so that the next steps find theirs in L2 instead of HBM.
+__device__ __forceinline__ int4 ldg_blob(const int4* p) {
+#if defined(__CUDA_ARCH__) && !defined(GLX_ABLATE_BLOB_PREFETCH)
+    int4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 template <class Sig>
 struct TiledLane {
     uint64_t base;
@@ -57,7 +69,7 @@ struct TiledLane {
             int32_t w[Sig::W];
 #pragma unroll
             for (uint32_t q = 0; q < Sig::W / 4; q++) {
-                const int4 v = __ldg(b + q);
+                const int4 v = ldg_blob(b + q);
                 w[4 * q] = v.x;
                 w[4 * q + 1] = v.y;
                 w[4 * q + 2] = v.z;
@@ -188,7 +200,12 @@ struct TiledLane {
                 int32_t* __restrict__ ow = O.fld[K] + off + (unsigned long long)(sample - lane) * count;
 #endif
                 const uint32_t total = nvalid * count;
-                for (uint32_t e = lane; e < total; e += 32) ow[e] = stage[e];
+                if (count == 3) {  // biallelic site, the common case: three rows, no loop
+#pragma unroll
+                    for (uint32_t u = 0; u < 3; u++)
+                        if (lane + 32 * u < total) ow[lane + 32 * u] = stage[lane + 32 * u];
+                } else
+                    for (uint32_t e = lane; e < total; e += 32) ow[e] = stage[e];
                 __syncwarp();
                 return;
             }
