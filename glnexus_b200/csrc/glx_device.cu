@@ -448,6 +448,7 @@ struct glx_dev_batch {
     std::vector<uint8_t> flags_dev;  // host staging that must outlive an asynchronous upload
     std::vector<int4> site_rows_h, unif_rows_h;
     uint32_t max_site_alleles = 0;
+    uint32_t tile_sites = GLX_TILE_SITES;  // sites per tile of the tiled kernel in use
     bool fused_variant = false;  // the tiled kernel finishes its own lone-variant cells
     std::vector<int32_t> tq_host;
     unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
@@ -635,6 +636,8 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     flags_dev.assign(recs->flags, recs->flags + Rn);
     for (uint64_t dd = 0; dd < D; dd++)
         if (recs->ds_rec_off[dd + 1] > recs->ds_rec_off[dd]) flags_dev[recs->ds_rec_off[dd + 1] - 1] |= GLX_RF_DEV_LAST;
+    uint64_t n_variant_records = 0;
+    for (uint64_t rr = 0; rr < Rn; rr++) n_variant_records += !(recs->flags[rr] & GLX_RF_IS_REF);
     add(flags_dev.data(), Rn, &R.flags);
     add(recs->filt, Rn * 4, &R.filt);
     add(recs->gt, Rn * 4, &R.gt);
@@ -753,18 +756,22 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
             const char* nf_env = getenv("GLX_NO_FUSE");
             const bool fuse = d->plan.vview && d->max_site_alleles <= 4 && !(nf_env && *nf_env && *nf_env != '0');
+            // A CTA finishes its lone-variant-record cells when its tile is done; their output sectors are still in L2
+            // only if the tiles in flight are small enough, so variant-dense batches (>= 1 variant record per 100
+            // cells) walk half-height tiles. Sparse ones keep the full height (fewer cursor set-ups per site).
+            const bool short_tiles = fuse && n_variant_records * 100 >= d->n_cells;
             auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
             if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
-                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant, 0>;
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant, 0, GLX_TILE_SITES>;
                 if (fuse) {
-                    d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant, 4>;
+                    d->tiled_kernel = short_tiles ? glx_cells_tiled_sig_kernel<SigDeepVariant, 4, GLX_TILE_SITES / 2> : glx_cells_tiled_sig_kernel<SigDeepVariant, 4, GLX_TILE_SITES>;
                     d->fused_variant = true;
                 }
                 d->tiled_smem = 0;
             } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
-                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk, 0>;
+                d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk, 0, GLX_TILE_SITES>;
                 if (fuse) {
-                    d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk, 4>;
+                    d->tiled_kernel = short_tiles ? glx_cells_tiled_sig_kernel<SigGatk, 4, GLX_TILE_SITES / 2> : glx_cells_tiled_sig_kernel<SigGatk, 4, GLX_TILE_SITES>;
                     d->fused_variant = true;
                 }
                 d->tiled_smem = 0;
@@ -772,10 +779,11 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         }
     }
     d->n_sample_blocks = (uint32_t)((N + d->samples_per_cta - 1) / d->samples_per_cta);
-    d->n_site_tiles = (uint32_t)((S + GLX_TILE_SITES - 1) / GLX_TILE_SITES);
+    if (d->fused_variant && n_variant_records * 100 >= d->n_cells) d->tile_sites = GLX_TILE_SITES / 2;
+    d->n_site_tiles = (uint32_t)((S + d->tile_sites - 1) / d->tile_sites);
     if (d->plan.enabled && d->n_cells) {
         const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
-        const size_t region_cells = (size_t)GLX_TILE_SITES * d->samples_per_cta;
+        const size_t region_cells = (size_t)d->tile_sites * d->samples_per_cta;
         d->worklist_bytes = n_regions * region_cells * 8 + (n_regions + 64) * 4;
         e = ctx->take((void**)&d->worklist, d->worklist_bytes);
         if (e != cudaSuccess) {
@@ -797,7 +805,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         tq.assign(d->n_site_tiles, 0);
         int32_t run = INT32_MAX;
         for (uint32_t tile = d->n_site_tiles; tile-- > 0;) {  // suffix minimum: non-decreasing, never later than any later tile's start
-            run = std::min(run, sites->qbeg[(size_t)tile * GLX_TILE_SITES]);
+            run = std::min(run, sites->qbeg[(size_t)tile * d->tile_sites]);
             tq[tile] = run;
         }
         e = cudaMemcpyAsync(d->tile_q, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice, up);
@@ -857,7 +865,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             const uint32_t nreg = c1 - c0;
             const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[2], st));
-            const uint32_t region_cells = GLX_TILE_SITES * d->samples_per_cta;
+            const uint32_t region_cells = d->tile_sites * d->samples_per_cta;
             glx_cells_bands_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->blobs);
             d->launches_per_call++;
             if (d->plan.vview && !d->fused_variant) {  // small sites keep the per-thread shared-memory columns short

@@ -252,29 +252,30 @@ struct TiledLane {
 };
 
 #ifdef __CUDACC__
-// FUSE = 4: when the tile is done the CTA also finishes its own lone-variant-record cells (genotype_cell_variant<4>),
+// TS = sites per tile. FUSE = 4: when the tile is done the CTA also finishes its own lone-variant-record cells (genotype_cell_variant<4>),
 // while the tile's output lines and record blobs are still in L2. FUSE = 0: they are left to glx_cells_variant_kernel.
 #ifndef GLX_FUSED_MIN_BLOCKS
 #define GLX_FUSED_MIN_BLOCKS 7  // 72 registers: the walk over the tile wants the occupancy more than the fused closed form wants registers
 #endif
-template <class Sig, int FUSE>
+template <class Sig, int FUSE, int TS>
 __global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS : 1) glx_cells_tiled_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
                                                                                const int32_t* __restrict__ blobs, const uint32_t* __restrict__ tile_cursors,
                                                                                uint2* __restrict__ worklist,
                                                                                uint32_t* __restrict__ n_work, uint32_t n_sample_blocks, uint32_t cta0) {
-    __shared__ int4 s_pos[GLX_TILE_SITES];       // beg, end, qbeg, qend
-    __shared__ uint32_t s_meta[GLX_TILE_SITES];  // bits 0-7 n_allele, bit 8 general path only, bit 9 qbeg below the previous site's
-    __shared__ unsigned long long s_off[Sig::nf ? Sig::nf : 1][GLX_TILE_SITES];
+    static_assert(TS <= 64, "per-lane site masks are 64-bit");
+    __shared__ int4 s_pos[TS];       // beg, end, qbeg, qend
+    __shared__ uint32_t s_meta[TS];  // bits 0-7 n_allele, bit 8 general path only, bit 9 qbeg below the previous site's
+    __shared__ unsigned long long s_off[Sig::nf ? Sig::nf : 1][TS];
     __shared__ uint32_t s_red[4][GLX_TILE_THREADS / 32];  // per-warp called/lost site masks (lo, hi words)
     __shared__ uint32_t s_nslow;  // cells this CTA handed to the worklist kernels (its worklist region is CTA-private)
     __shared__ int32_t s_stage[GLX_TILE_THREADS / 32][32 * GLX_STAGE_MAX];  // per-warp transposition buffer for narrow vectors
 
     const uint32_t cta = blockIdx.x + cta0;  // launches cover chunks of the tile grid so that the worklist kernels of one chunk overlap the next
     const uint32_t sb = cta % n_sample_blocks, tile = cta / n_sample_blocks;
-    const uint32_t site0 = tile * GLX_TILE_SITES;
-    uint2* __restrict__ my_work = worklist + (size_t)cta * (GLX_TILE_SITES * GLX_TILE_THREADS);
+    const uint32_t site0 = tile * TS;
+    uint2* __restrict__ my_work = worklist + (size_t)cta * (TS * GLX_TILE_THREADS);
     if (threadIdx.x == 0) s_nslow = 0;
-    const uint32_t nsite = min((uint32_t)GLX_TILE_SITES, S.n_sites - site0);
+    const uint32_t nsite = min((uint32_t)TS, S.n_sites - site0);
     const uint32_t N = S.n_samples;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t sample = sb * GLX_TILE_THREADS + tid;
