@@ -28,6 +28,26 @@ using namespace glxd;
 // kernels
 // ---------------------------------------------------------------------------------------------
 
+// Once per upload: the device-private flag bit of each dataset's last record, and the packed site / unification rows
+// (DSites::site_rows, unif_rows; same layout as build_site_rows) from the uploaded columns.
+__global__ void __launch_bounds__(256) glx_prepare_inputs_kernel(const DRecs R, const DSites S, uint32_t n_datasets, uint64_t n_unif, uint8_t* __restrict__ flags,
+                                                                 int4* __restrict__ site_rows, int4* __restrict__ unif_rows) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_datasets && R.ds_rec_off[i + 1] > R.ds_rec_off[i]) flags[R.ds_rec_off[i + 1] - 1] |= GLX_RF_DEV_LAST;
+    if (i < S.n_sites) {
+        site_rows[2 * i] = make_int4(S.beg[i], S.end[i], S.qbeg[i], S.qend[i]);
+        site_rows[2 * i + 1] = make_int4((int)S.n_allele[i] | (S.monoallelic[i] ? 256 : 0), (int)S.allele_off[i], (int)S.unif_off[i], (int)S.unif_off[i + 1]);
+    } else if (i == S.n_sites) {
+        site_rows[2 * i] = site_rows[2 * i + 1] = make_int4(0, 0, 0, 0);
+    }
+    if (i < n_unif) {
+        unif_rows[2 * i] = make_int4(S.unif_beg[i], S.unif_end[i], (int)S.unif_len[i], (int)S.unif_to[i]);
+        unif_rows[2 * i + 1] = make_int4((int)(uint32_t)S.unif_prefix[i], (int)(uint32_t)(S.unif_prefix[i] >> 32), (int)S.unif_str[i], 0);
+    } else if (i == n_unif) {
+        unif_rows[2 * i] = unif_rows[2 * i + 1] = make_int4(0, 0, 0, 0);
+    }
+}
+
 // Thread per record: resolve each record into its blob (glx_cell_fast.cuh). Part of every glx_launch. Blobs are built
 // in shared memory and written out by the whole block as one contiguous, fully coalesced span. The same threads fill
 // the tile cursor table (fill_tile_cursors states what is written): record r claims the tiles [t_lo, t_hi) with
@@ -342,6 +362,7 @@ __global__ void __launch_bounds__(256) glx_narrow_kernel(const int32_t* __restri
 // host side
 // ---------------------------------------------------------------------------------------------
 #define GLX_MAX_CHUNKS 8
+#define GLX_ARENA_CACHE 16  // a batch owns six arenas and a range-batch driver keeps two batches in flight: no cudaFree in steady state
 struct glx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -357,10 +378,10 @@ struct glx_ctx {
     struct Cached {
         void* p = nullptr;
         size_t bytes = 0;
-    } cache[6];
+    } cache[GLX_ARENA_CACHE];
     cudaError_t take(void** p, size_t bytes) {
         int best = -1;
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < GLX_ARENA_CACHE; i++)
             if (cache[i].p && cache[i].bytes >= bytes && (best < 0 || cache[i].bytes < cache[best].bytes)) best = i;
         if (best >= 0 && cache[best].bytes <= bytes * 2 + (1 << 20)) {
             *p = cache[best].p;
@@ -370,7 +391,7 @@ struct glx_ctx {
         cudaError_t e = cudaMalloc(p, bytes);
         if (e != cudaSuccess) {  // release the cache and retry once
             cudaGetLastError();
-            for (int i = 0; i < 6; i++)
+            for (int i = 0; i < GLX_ARENA_CACHE; i++)
                 if (cache[i].p) {
                     cudaFree(cache[i].p);
                     cache[i] = Cached();
@@ -382,11 +403,11 @@ struct glx_ctx {
     void give(void* p, size_t bytes) {
         if (!p) return;
         int slot = -1;
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < GLX_ARENA_CACHE; i++)
             if (!cache[i].p) slot = i;
         if (slot < 0) {  // evict the smallest
             slot = 0;
-            for (int i = 1; i < 6; i++)
+            for (int i = 1; i < GLX_ARENA_CACHE; i++)
                 if (cache[i].bytes < cache[slot].bytes) slot = i;
             if (cache[slot].bytes >= bytes) {
                 cudaFree(p);
@@ -445,8 +466,6 @@ struct glx_dev_batch {
     int launches_per_call = 0;
     bool force_general = false;
     uint32_t n_chunks = 1;
-    std::vector<uint8_t> flags_dev;  // host staging that must outlive an asynchronous upload
-    std::vector<int4> site_rows_h, unif_rows_h;
     uint32_t max_site_alleles = 0;
     uint32_t tile_sites = GLX_TILE_SITES;  // sites per tile of the tiled kernel in use
     bool fused_variant = false;  // the tiled kernel finishes its own lone-variant cells
@@ -632,13 +651,9 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     add(recs->maxend, Rn * 4, &R.maxend);
     add(recs->qual, Rn * 4, &R.qual);
     add(recs->n_allele, Rn, &R.n_allele);
-    std::vector<uint8_t>& flags_dev = d->flags_dev;  // + device-private bit: last record of its dataset (kept until the batch is freed)
-    flags_dev.assign(recs->flags, recs->flags + Rn);
-    for (uint64_t dd = 0; dd < D; dd++)
-        if (recs->ds_rec_off[dd + 1] > recs->ds_rec_off[dd]) flags_dev[recs->ds_rec_off[dd + 1] - 1] |= GLX_RF_DEV_LAST;
     uint64_t n_variant_records = 0;
     for (uint64_t rr = 0; rr < Rn; rr++) n_variant_records += !(recs->flags[rr] & GLX_RF_IS_REF);
-    add(flags_dev.data(), Rn, &R.flags);
+    add(recs->flags, Rn, &R.flags);  // glx_prepare_inputs_kernel adds the device-private "last record of its dataset" bit
     add(recs->filt, Rn * 4, &R.filt);
     add(recs->gt, Rn * 4, &R.gt);
     add(recs->allele_off, Rn * 4, &R.allele_off);
@@ -670,17 +685,22 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     add(sites->unif_prefix, nU * 8, &Sx.unif_prefix);
     add(sites->unif_str, nU * 4, &Sx.unif_str);
     add(sites->unif_pool, sites->n_unif_pool, &Sx.unif_pool);
-    build_site_rows(*sites, d->site_rows_h, d->unif_rows_h);
-    add(d->site_rows_h.data(), d->site_rows_h.size() * sizeof(int4), &Sx.site_rows);
-    add(d->unif_rows_h.data(), d->unif_rows_h.size() * sizeof(int4), &Sx.unif_rows);
+    // packed on the device from the columns above (every source of the upload stays caller memory: a pageable staging
+    // copy in the middle of the stream would make the call wait for the copies queued before it)
+    add((const void*)nullptr, (S * 2 + 2) * sizeof(int4), &Sx.site_rows);
+    add((const void*)nullptr, (nU * 2 + 2) * sizeof(int4), &Sx.unif_rows);
     for (uint32_t k = 0; k < cfg->n_fields; k++) {
         add(sites->fld_cnt[k], S * 2, &Sx.fld_cnt[k]);
         add(sites->fld_off[k], (S + 1) * 8, &Sx.fld_off[k]);
         d->fld_total[k] = S ? sites->fld_off[k][S] : 0;
     }
     size_t total = 0;
-    for (auto& it : items) total += ((it.bytes + 255) & ~(size_t)255) + 256;
-    d->in_bytes = total;
+    size_t copied = 0;
+    for (auto& it : items) {
+        total += ((it.bytes + 255) & ~(size_t)255) + 256;
+        if (it.src) copied += it.bytes;
+    }
+    d->in_bytes = copied;  // host-to-device bytes of this upload
     d->in_alloc = total ? total : 256;
     cudaError_t e = ctx->take((void**)&d->in_base, d->in_alloc);
     if (e != cudaSuccess) {
@@ -691,12 +711,22 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     for (auto& it : items) {
         char* p = ar.take<char>(it.bytes ? it.bytes : 1);
         *it.dst = p;
-        if (it.bytes) {
+        if (it.bytes && it.src) {
             e = cudaMemcpyAsync(p, it.src, it.bytes, cudaMemcpyHostToDevice, up);
             if (e != cudaSuccess) {
                 glx_free_batch(ctx, d);
                 return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
             }
+        }
+    }
+    {
+        const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(S + 1, nU + 1), D);
+        glx_prepare_inputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, up>>>(R, Sx, (uint32_t)D, nU, const_cast<uint8_t*>(R.flags), const_cast<int4*>(Sx.site_rows),
+                                                                               const_cast<int4*>(Sx.unif_rows));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            glx_free_batch(ctx, d);
+            return cuda_fail(ctx, e, "glx_prepare_inputs_kernel");
         }
     }
     // max output slots of any cell (scratch sizing of the general path)
