@@ -298,7 +298,7 @@ def main():
             if slots[k] is not None:
                 retire(k)
 
-    # e2e (headline): integer columns cross PCIe as int16 wherever every value of the field fits (the type BCF would store)
+    # e2e (headline): integer columns cross PCIe as int8 / int16 wherever every value of the field fits (the types BCF would store)
     pipelined(2, True)  # warm the arena cache of both slots
     barrier()
     te = time.time()
@@ -371,8 +371,8 @@ def main():
                        "cells_per_gpu": cells, "records_per_gpu": int(batch.n_records), "variant_records_per_gpu": int(batch.variant_records),
                        "l2": "flushed between timed steps (256 MiB write, untimed); outputs (%.2f GB/step) exceed L2" % (out_b / 1e9)},
             "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_narrow), "steps": e2e_steps,
-                    "mode": "pinned host buffers, batches pipelined 2 deep on 2 streams; integer columns delivered as int16 (BCF 16-bit "
-                            "sentinels) where every value of the field fits, int32 otherwise (glx_download_narrow_on)",
+                    "mode": "pinned host buffers, batches pipelined 2 deep on 2 streams; integer columns delivered in the width BCF would store "
+                            "them in (int8 / int16 with BCF's sentinels where every value of the field fits, int32 otherwise; glx_download_narrow_on)",
                     "int32_columns_cells_per_s": cells_all * e2e_steps / e2e_wide_s if world == 1 else None, "int32_d2h_bytes_per_step": int(d2h),
                     "single_sync_call_cells_per_s": cells / sync_call_s},
             "gpu_launches": launches,

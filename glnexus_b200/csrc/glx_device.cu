@@ -335,27 +335,29 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
     }
 }
 
-// int32 column -> int16 with BCF's 16-bit sentinels; *overflow is set when some value does not fit
-__global__ void __launch_bounds__(256) glx_narrow_kernel(const int32_t* __restrict__ in, int16_t* __restrict__ out, uint64_t n, uint32_t* __restrict__ overflow) {
+// int32 column -> int16 or int8 with BCF's sentinels of that width. *overflow: bit 0 some value does not fit int16,
+// bit 1 some value does not fit int8 (both recorded whatever the output width: the next batch's width follows them).
+template <class T>
+__global__ void __launch_bounds__(256) glx_narrow_kernel(const int32_t* __restrict__ in, T* __restrict__ out, uint64_t n, uint32_t* __restrict__ overflow) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    bool bad = false;
-    auto conv = [&](int32_t v) -> int16_t {
-        if (v == GLXD_INT_MISSING) return (int16_t)0x8000;
-        if (v == GLXD_INT_VEND) return (int16_t)0x8001;
-        if (v < -32760 || v > 32767) {  // -32768..-32761 are reserved in BCF
-            bad = true;
-            return 0;
-        }
-        return (int16_t)v;
+    uint32_t bad = 0;
+    auto conv = [&](int32_t v) -> uint32_t {  // the value's bits in T
+        if (v == GLXD_INT_MISSING) return sizeof(T) == 1 ? 0x80u : 0x8000u;
+        if (v == GLXD_INT_VEND) return sizeof(T) == 1 ? 0x81u : 0x8001u;
+        if (v < -32760 || v > 32767) bad |= 1u;  // -32768..-32761 are reserved in BCF
+        if (v < -120 || v > 127) bad |= 2u;      // -128..-121 likewise
+        return sizeof(T) == 1 ? (uint32_t)(uint8_t)v : (uint32_t)(uint16_t)v;
     };
     const uint64_t n4 = n / 4;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int4 v = reinterpret_cast<const int4*>(in)[i];
-        const int16_t a = conv(v.x), b = conv(v.y), c = conv(v.z), d = conv(v.w);
-        reinterpret_cast<uint2*>(out)[i] = make_uint2((uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16), (uint32_t)(uint16_t)c | ((uint32_t)(uint16_t)d << 16));
+        const uint32_t a = conv(v.x), b = conv(v.y), c = conv(v.z), d = conv(v.w);
+        if (sizeof(T) == 1) reinterpret_cast<uint32_t*>(out)[i] = a | b << 8 | c << 16 | d << 24;
+        else reinterpret_cast<uint2*>(out)[i] = make_uint2(a | b << 16, c | d << 16);
     }
-    for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = conv(in[i]);
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(overflow, 1u);
+    for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (T)conv(in[i]);
+    const uint32_t any = __reduce_or_sync(0xffffffffu, bad);
+    if (any && (threadIdx.x & 31) == 0) atomicOr(overflow, any);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,6 +375,7 @@ struct glx_ctx {
     unsigned host_err_next = 0;                      // memory per batch would synchronise the device and break pipelining)
     std::string err;
     int sm_count = 0;
+    uint8_t width_hint[GLX_MAX_FIELDS];  // narrow download: 1 when every value of the field in the previous batch fitted int8, else 2
     // freed batch arenas are kept for the next batch of the same range stream (cudaMalloc/cudaFree of GB-sized
     // buffers costs milliseconds and would dominate a per-batch call)
     struct Cached {
@@ -473,6 +476,7 @@ struct glx_dev_batch {
     unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
     int16_t* narrow = nullptr;               // device int16 images of the integer fields + overflow words
     size_t narrow_bytes = 0;
+    uint8_t narrow_width[GLX_MAX_FIELDS] = {};  // width each field was sent in by the last narrow download
     uint32_t* narrow_overflow = nullptr;     // [GLX_MAX_FIELDS] device
     uint32_t* host_overflow = nullptr;       // pinned
     FastPlan plan;
@@ -513,6 +517,7 @@ int glx_create(glx_ctx** out, int device) {
     auto* ctx = new glx_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    memset(ctx->width_hint, 2, sizeof ctx->width_hint);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return GLX_E_CUDA;
@@ -1015,13 +1020,16 @@ int glx_download_narrow_on(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out, void*
             CU(cudaMemcpyAsync(out->fld32[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, st));
             continue;
         }
-        int16_t* dst = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(d->narrow) + off);
+        char* dst = reinterpret_cast<char*>(d->narrow) + off;
         off += (d->fld_total[k] * 2 + 255) & ~(size_t)255;
         const uint64_t n = d->fld_total[k];
         const unsigned grid = (unsigned)std::min<uint64_t>((n / 4 + 255) / 256 + 1, (uint64_t)ctx->sm_count * 16);
-        glx_narrow_kernel<<<grid, 256, 0, st>>>(d->O.fld[k], dst, n, d->narrow_overflow + k);
+        const int w = (ctx->width_hint[k] == 1 && out->fld8[k]) ? 1 : 2;
+        d->narrow_width[k] = (uint8_t)w;
+        if (w == 1) glx_narrow_kernel<int8_t><<<grid, 256, 0, st>>>(d->O.fld[k], reinterpret_cast<int8_t*>(dst), n, d->narrow_overflow + k);
+        else glx_narrow_kernel<int16_t><<<grid, 256, 0, st>>>(d->O.fld[k], reinterpret_cast<int16_t*>(dst), n, d->narrow_overflow + k);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(out->fld16[k], dst, n * 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(w == 1 ? (void*)out->fld8[k] : (void*)out->fld16[k], dst, n * w, cudaMemcpyDeviceToHost, st));
     }
     if (S * N) {
         CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
@@ -1043,11 +1051,16 @@ int glx_narrow_finish(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out) {
     for (uint32_t k = 0; k < d->n_fields; k++) {
         if (!field_is_narrowable(d, k)) {
             out->width[k] = 4;
-        } else if (d->host_overflow[k]) {  // some value needs 32 bits: fetch the int32 column (rare; synchronous)
+            continue;
+        }
+        const uint32_t fl = d->host_overflow[k];
+        const int w = d->narrow_width[k] ? d->narrow_width[k] : 2;
+        if (fl & (w == 1 ? 2u : 1u)) {  // some value does not fit the width sent: fetch the int32 column (rare; synchronous)
             out->width[k] = 4;
             if (d->fld_total[k]) CU(cudaMemcpy(out->fld32[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost));
         } else
-            out->width[k] = 2;
+            out->width[k] = (uint8_t)w;
+        if (d->fld_total[k]) ctx->width_hint[k] = (fl & 2u) ? 2 : 1;  // what the next batch of this range stream is sent in
     }
     return GLX_OK;
 }

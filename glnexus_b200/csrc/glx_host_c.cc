@@ -307,6 +307,7 @@ glxh_out16* glxh_out16_alloc(const glxh_batch* b, int pinned) {
         const glx_field& f = b->b.cfg.fields[k];
         const bool narrowable = f.type == GLX_TYPE_INT && f.kind != GLX_FK_FT && f.kind != GLX_FK_STRING;
         o->out.fld16[k] = narrowable ? (int16_t*)out_alloc(o->n_fld[k] * 2, o->pinned) : nullptr;
+        o->out.fld8[k] = narrowable ? (int8_t*)out_alloc(o->n_fld[k], o->pinned) : nullptr;
         // the 32-bit form is the fallback for fields that do not fit (pageable: rare) and the home of float / FT fields
         o->out.fld32[k] = narrowable ? (int32_t*)malloc(o->n_fld[k] * 4 + 16) : (int32_t*)out_alloc(o->n_fld[k] * 4, o->pinned);  // untouched unless needed
     }
@@ -322,6 +323,7 @@ void glxh_out16_free(glxh_out16* o) {
     for (uint32_t k = 0; k < GLX_MAX_FIELDS; k++) {
         const bool narrowable = o->out.fld16[k] != nullptr;
         out_release(o->out.fld16[k], o->pinned);
+        out_release(o->out.fld8[k], o->pinned);
         out_release(o->out.fld32[k], narrowable ? false : o->pinned);
     }
     delete o;
@@ -345,8 +347,13 @@ int glxh_out16_array(const glxh_out16* o, int which, const void** ptr, uint64_t*
         *nbytes = o->n_fld[k] * 4;
         return GLX_OK;
     }
-    const int k = which - 16;
+    const int k = which - 16;  // the narrow form in use: int8 when glx_narrow_finish reported width 1, else int16
     if (k < 0 || k >= (int)o->n_fields) return GLX_E_INVALID;
+    if (o->out.width[k] == 1) {
+        *ptr = o->out.fld8[k];
+        *nbytes = o->n_fld[k];
+        return GLX_OK;
+    }
     *ptr = o->out.fld16[k];
     *nbytes = o->out.fld16[k] ? o->n_fld[k] * 2 : 0;
     return GLX_OK;
@@ -359,7 +366,14 @@ int glxh_out16_widen(const glxh_out16* o, glx_out* wide) {
     memcpy(wide->allele_used, o->out.allele_used, o->n_sites * 4);
     memcpy(wide->site_flags, o->out.site_flags, o->n_sites);
     for (uint32_t k = 0; k < o->n_fields; k++) {
-        if (o->out.width[k] == 2) {
+        if (o->out.width[k] == 1) {
+            const int8_t* s = o->out.fld8[k];
+            int32_t* d = wide->fld[k];
+            for (uint64_t i = 0; i < o->n_fld[k]; i++) {
+                const int8_t v = s[i];
+                d[i] = v == GLX_INT8_MISSING ? GLX_INT_MISSING : (v == GLX_INT8_VECTOR_END ? GLX_INT_VECTOR_END : (int32_t)v);
+            }
+        } else if (o->out.width[k] == 2) {
             const int16_t* s = o->out.fld16[k];
             int32_t* d = wide->fld[k];
             for (uint64_t i = 0; i < o->n_fld[k]; i++) {

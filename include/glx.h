@@ -188,15 +188,18 @@ typedef struct glx_out {
 /* Narrow form of the lifted columns for the device->host leg. htslib stores every FORMAT vector of a BCF record in the
  * smallest integer type its values fit (bcf_enc_vint); an integer field whose every value in the batch fits int16 is
  * therefore delivered as int16 with BCF's own 16-bit sentinels. width[k] says which of fld16[k] / fld32[k] holds field k
- * after glx_narrow_finish (2 or 4 bytes per value; float fields and FT masks are always 4). */
+ * after glx_narrow_finish (1, 2 or 4 bytes per value; float fields and FT masks are always 4). */
 #define GLX_INT16_MISSING ((int16_t)0x8000)    /* bcf_int16_missing    */
 #define GLX_INT16_VECTOR_END ((int16_t)0x8001) /* bcf_int16_vector_end */
+#define GLX_INT8_MISSING ((int8_t)0x80)        /* bcf_int8_missing      */
+#define GLX_INT8_VECTOR_END ((int8_t)0x81)     /* bcf_int8_vector_end   */
 typedef struct glx_out16 {
     int8_t* gt;
     uint8_t* rnc;
     int16_t* fld16[GLX_MAX_FIELDS]; /* caller-allocated, one int16 per value */
     int32_t* fld32[GLX_MAX_FIELDS]; /* caller-allocated, one int32 per value (used when the field does not fit) */
-    uint8_t width[GLX_MAX_FIELDS];  /* out: 2 or 4 */
+    int8_t* fld8[GLX_MAX_FIELDS];   /* caller-allocated, one int8 per value (used when the previous batch of the context fitted int8) */
+    uint8_t width[GLX_MAX_FIELDS];  /* out: 1, 2 or 4 = which of fld8 / fld16 / fld32 holds field k */
     uint32_t* allele_used;
     uint8_t* site_flags;
 } glx_out16;
@@ -237,9 +240,11 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
                   glx_dev_batch** dev);
 int glx_download_on(glx_ctx* ctx, glx_dev_batch* dev, glx_out* out, void* stream, int sync);
 int glx_status(glx_ctx* ctx, glx_dev_batch* dev);
-/* Narrow download: one extra pass packs each integer field to int16 on the device (recording whether it fits), then GT,
- * RNC and the 16-bit columns cross PCIe (18 instead of 32 bytes per biallelic DeepVariant cell). After the stream is
- * synchronised glx_narrow_finish sets width[] and fetches, synchronously, the int32 form of any field that did not fit. */
+/* Narrow download: one extra pass packs each integer field to int16 — or to int8 when every value of that field in the
+ * context's previous batch fitted BCF's int8 range, as htslib's typed-integer encoding would — on the device, recording
+ * whether it fits; then GT, RNC and the narrow columns cross PCIe (18, or 14 with 8-bit DP/AD/GQ, instead of 32 bytes per
+ * biallelic DeepVariant cell). After the stream is synchronised glx_narrow_finish sets width[] and fetches, synchronously,
+ * the int32 form of any field that did not fit the width it was sent in. */
 int glx_download_narrow_on(glx_ctx* ctx, glx_dev_batch* dev, glx_out16* out, void* stream, int sync);
 int glx_narrow_finish(glx_ctx* ctx, glx_dev_batch* dev, glx_out16* out);
 void* glx_stream_create(glx_ctx* ctx);

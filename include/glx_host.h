@@ -51,8 +51,8 @@ glx_out* glxh_out_struct(glxh_out* o);
 /* raw access for comparisons: which = 0 gt, 1 rnc, 2 allele_used, 3 site_flags, 16+k field k */
 int glxh_out_array(const glxh_out* o, int which, const void** ptr, uint64_t* nbytes);
 
-/* Host buffers for the narrow download (glx_out16): 16- and 32-bit storage per field. which = 0 gt, 1 rnc,
- * 2 allele_used, 3 site_flags, 16+k field k as int16, 48+k field k as int32. glxh_out16_widen expands into a glx_out
+/* Host buffers for the narrow download (glx_out16): 8-, 16- and 32-bit storage per field. which = 0 gt, 1 rnc,
+ * 2 allele_used, 3 site_flags, 16+k field k in the narrow form in use (int8 if width[k] == 1, else int16), 48+k field k as int32. glxh_out16_widen expands into a glx_out
  * (int32 columns, htslib 32-bit sentinels) for consumers that want the wide form. */
 typedef struct glxh_out16 glxh_out16;
 glxh_out16* glxh_out16_alloc(const glxh_batch* b, int pinned);

@@ -194,8 +194,24 @@ def test_gpu_narrow_download(ctx):
     o16.widen(wide)
     d = compare_outs(wide, ref, b.n_fields)
     assert not d, "\n".join(d)
-    assert o16.narrow_nbytes() < 0.6 * sum(a.nbytes for k, a in ref.arrays().items() if k not in ("allele_used", "site_flags"))
-    # a field with a value beyond int16 falls back to its int32 column
+    wide_bytes = sum(a.nbytes for k, a in ref.arrays().items() if k not in ("allele_used", "site_flags"))
+    n16 = o16.narrow_nbytes()
+    assert n16 < 0.6 * wide_bytes
+    # the next batch of the same context is sent in int8 wherever the previous one fitted BCF's 8-bit range (GQ at least)
+    o8, wide8 = b.alloc_out16(), b.alloc_out()
+    dev = ctx.upload_async(b, st)
+    dev.launch(st)
+    dev.download_narrow_async(o8, st)
+    ctx.stream_sync(st)
+    dev.status()
+    dev.narrow_finish(o8)
+    dev.close()
+    o8.widen(wide8)
+    d = compare_outs(wide8, ref, b.n_fields)
+    assert not d, "\n".join(d)
+    assert o8.narrow_nbytes() < n16
+    # a field with a value beyond the width it is sent in (here: beyond int16, and beyond the int8 the previous batch
+    # suggested) falls back to its int32 column
     hdr = ("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"\">\n##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"\">\n"
            "##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"\">\n##FORMAT=<ID=AD,Number=R,Type=Integer,Description=\"\">\n"
            "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"\">\n##contig=<ID=21,length=48129895>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\n")
