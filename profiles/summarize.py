@@ -38,6 +38,17 @@ def main():
                     stalls.append((float(r[i]), h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")))
                 except ValueError:
                     pass
+        if not stalls:  # newer ncu: stalled warps per issued instruction
+            for i, h in enumerate(hdr):
+                if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                    try:
+                        stalls.append((float(r[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+                    except ValueError:
+                        pass
+            stalls.sort(reverse=True)
+            print("| warp stall reasons (stalled warps per issued instruction) | " + ", ".join(f"{n} {v:.2f}" for v, n in stalls[:7]) + " |")
+            print()
+            continue
         stalls.sort(reverse=True)
         print("| top warp stall reasons (% of active warp cycles) | " + ", ".join(f"{n} {v:.1f}" for v, n in stalls[:6]) + " |")
         print()
