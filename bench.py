@@ -341,7 +341,8 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        names = ["glx_resolve_records_kernel", "glx_cells_tiled_sig_kernel", "glx_cells_single_kernel", "glx_cells_general_kernel"]
+        names = ["glx_resolve_records_kernel", "glx_cells_tiled_sig_kernel", "closed-form worklist kernels (glx_cells_bands/variant/single_kernel)",
+                 "glx_cells_general_kernel"]
         kmean = [statistics.mean(k[i] for k in kms) for i in range(4)]
         n_var_cells = int(batch.variant_records)
         alg, out_b, in_b = algorithmic_bytes(batch, n_var_cells)

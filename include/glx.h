@@ -252,9 +252,9 @@ void glx_stream_destroy(glx_ctx* ctx, void* stream);
 int glx_stream_sync(glx_ctx* ctx, void* stream);
 int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
 void glx_host_unregister(void* p);
-/* Measurement aids: record CUDA events around each kernel of glx_launch on the launching stream; glx_kernel_ms waits
- * for the last launch and returns the durations of {record resolve, tiled fast path, single-record worklist, general
- * worklist} kernels; glx_work_count = cells the tiled kernel put on its worklist, glx_fused_count = those of them it then
+/* Measurement aids: record CUDA events around the stages of glx_launch on the launching stream; glx_kernel_ms waits
+ * for the last launch and returns the durations of {record resolve kernel, tiled fast-path kernel (incl. the fused
+ * lone-variant closed form), closed-form worklist kernels (bands, variant, single-record), general worklist kernel}; glx_work_count = cells the tiled kernel put on its worklist, glx_fused_count = those of them it then
  * finished itself (lone-variant-record cells, when that closed form is fused into the tiled kernel). */
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);
 int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[4]);
