@@ -123,6 +123,66 @@ __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kerne
         }
 }
 
+// The same, for a config whose field signature is instantiated (the preset signatures) and whose plan has record views:
+// the row is built in registers by the unrolled builder and stored as four 16-byte vectors; the tile-cursor searches are
+// confined and exchanged inside the warp (shuffles), so the kernel has no shared memory and no block barrier.
+template <class Sig>
+__global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets,
+                                                                              int32_t* __restrict__ blobs, const int32_t* __restrict__ tile_q, uint32_t n_tiles,
+                                                                              uint32_t* __restrict__ tile_cursors) {
+    const uint64_t r = (uint64_t)blockIdx.x * GLX_RESOLVE_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool valid = r < R.n_records;
+    const uint64_t rr = valid ? r : R.n_records - 1;  // idle lanes shadow the last record (they take part in the shuffles)
+    int32_t w[Sig::W];
+    const uint8_t fl = R.flags[rr];
+    build_record_blob_sig<Sig>(cfg, plan, R, rr, fl & GLX_RF_DEV_LAST, w);
+    if (valid) {
+        int4* dst = reinterpret_cast<int4*>(blobs + r * Sig::W);
+#pragma unroll
+        for (uint32_t q = 0; q < Sig::W / 4; q++) dst[q] = make_int4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
+#ifndef GLX_ABLATE_CURSORS
+    // sample of the record: searched by the warp's first and last lane, then inside their range
+    uint32_t lo = 0, hi = n_datasets;
+    if (lane == 0 || lane == 31) {
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (R.ds_rec_off[mid] <= rr) lo = mid;
+            else hi = mid;
+        }
+    }
+    const uint32_t s_first = __shfl_sync(0xffffffffu, lo, 0), s_last = __shfl_sync(0xffffffffu, lo, 31);
+    if (lane != 0 && lane != 31) {
+        lo = s_first;
+        hi = s_last + 1;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (R.ds_rec_off[mid] <= rr) lo = mid;
+            else hi = mid;
+        }
+    }
+    const uint32_t sample = lo;
+    const uint64_t base = R.ds_rec_off[sample];
+    // t_hi = first tile whose tq >= maxend[r]; inside one sample maxend is non-decreasing, so the warp's searches are
+    // confined to the range of its first and last lane
+    const int my_maxend = w[2];
+    uint32_t t_hi = 0;
+    if (lane == 0 || lane == 31) t_hi = first_tile_at_or_after(tile_q, 0, n_tiles, my_maxend);
+    const uint32_t th_first = __shfl_sync(0xffffffffu, t_hi, 0), th_last = __shfl_sync(0xffffffffu, t_hi, 31);
+    if (lane != 0 && lane != 31) {
+        const bool one_sample = s_first == s_last;
+        t_hi = first_tile_at_or_after(tile_q, one_sample ? th_first : 0u, one_sample ? th_last : n_tiles, my_maxend);
+    }
+    uint32_t t_lo = __shfl_up_sync(0xffffffffu, t_hi, 1);  // the previous record's t_hi
+    if (valid) {
+        if (r == base) t_lo = 0;
+        else if (lane == 0) t_lo = first_tile_at_or_after(tile_q, 0, t_hi, R.maxend[r - 1]);
+        for (uint32_t tile = t_lo; tile < t_hi; tile++) tile_cursors[(size_t)tile * n_datasets + sample] = (uint32_t)(r - base);
+    }
+#endif
+}
+
 // Tiled fast path. CTA = 128 lanes = 128 consecutive samples; it walks GLX_TILE_SITES consecutive sites. Lane state:
 // a cursor into its sample's records and the resolved values of the band under the cursor (shared memory, one column
 // per lane). Per site each lane classifies its cell (fast_classify) and writes a finished cell's GT, RNC and lifted
@@ -485,8 +545,10 @@ struct glx_dev_batch {
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
     uint32_t samples_per_cta = GLX_TILE_THREADS;  // one sample per lane
+    typedef void (*resolve_fn)(const DCfg, const FastPlan, const DRecs, uint32_t, int32_t*, const int32_t*, uint32_t, uint32_t*);
     typedef void (*tiled_fn)(const DCfg, const FastPlan, const DRecs, const DSites, const DOut, const int32_t*, const uint32_t*, uint2*, uint32_t*, uint32_t,
                              uint32_t);
+    resolve_fn resolve_sig = nullptr;  // signature-specialised resolve kernel (plans with record views), else the generic one
     tiled_fn tiled_kernel = nullptr;  // signature-specialised tiled kernel, or the dynamic one
     size_t tiled_smem = 0;
     int32_t* blobs = nullptr;  // [n_records][blob_words] resolved records, then the tile cursor table and tile_q
@@ -789,6 +851,8 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         d->tiled_smem = (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4;
         const char* dyn = getenv("GLX_FORCE_DYNAMIC_TILED");
         if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
+            const char* nr_env = getenv("GLX_NO_RESOLVE_SIG");
+            const bool no_rsig = nr_env && *nr_env && *nr_env != '0';
             const char* nf_env = getenv("GLX_NO_FUSE");
             const bool fuse = d->plan.vview && d->max_site_alleles <= 4 && !(nf_env && *nf_env && *nf_env != '0');
             // A CTA finishes its lone-variant-record cells when its tile is done; their output sectors are still in L2
@@ -798,6 +862,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
             auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
             if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
                 d->tiled_kernel = glx_cells_tiled_sig_kernel<SigDeepVariant, 0, GLX_TILE_SITES>;
+                if (d->plan.vview && !no_rsig) d->resolve_sig = glx_resolve_sig_kernel<SigDeepVariant>;
                 if (fuse) {
                     d->tiled_kernel = short_tiles ? glx_cells_tiled_sig_kernel<SigDeepVariant, 4, GLX_TILE_SITES / 2> : glx_cells_tiled_sig_kernel<SigDeepVariant, 4, GLX_TILE_SITES>;
                     d->fused_variant = true;
@@ -805,6 +870,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
                 d->tiled_smem = 0;
             } else if (match(5, 0x20010ull, 0x20030ull, 0x01441ull)) {
                 d->tiled_kernel = glx_cells_tiled_sig_kernel<SigGatk, 0, GLX_TILE_SITES>;
+                if (d->plan.vview && !no_rsig) d->resolve_sig = glx_resolve_sig_kernel<SigGatk>;
                 if (fuse) {
                     d->tiled_kernel = short_tiles ? glx_cells_tiled_sig_kernel<SigGatk, 4, GLX_TILE_SITES / 2> : glx_cells_tiled_sig_kernel<SigGatk, 4, GLX_TILE_SITES>;
                     d->fused_variant = true;
@@ -873,9 +939,12 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     if (tiled) {
         CU(cudaMemsetAsync(d->tile_cursors, 0xff, (size_t)d->n_site_tiles * d->n_samples * 4, st));
         if (d->R.n_records) {
-            glx_resolve_records_kernel<<<(unsigned)((d->R.n_records + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS), GLX_RESOLVE_THREADS,
-                                         (size_t)GLX_RESOLVE_THREADS * (blob_words(d->plan.n_rv) + 1) * 4, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q,
-                                                                                                            d->n_site_tiles, d->tile_cursors);
+            const unsigned rgrid = (unsigned)((d->R.n_records + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS);
+            if (d->resolve_sig)
+                d->resolve_sig<<<rgrid, GLX_RESOLVE_THREADS, 0, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors);
+            else
+                glx_resolve_records_kernel<<<rgrid, GLX_RESOLVE_THREADS, (size_t)GLX_RESOLVE_THREADS * (blob_words(d->plan.n_rv) + 1) * 4, st>>>(
+                    d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors);
             d->launches_per_call++;
             CU(cudaGetLastError());
         }

@@ -5,6 +5,9 @@
 // glx_cell_fast.cuh (same blobs, same classification, same patterns); configs whose signature has no instantiation
 // run the dynamic kernel there. Reference lines: see glx_cell_fast.cuh.
 #pragma once
+#include <type_traits>
+#include <utility>
+
 #include "glx_cell_fast.cuh"
 #include "glx_cell_variant.cuh"
 
@@ -29,6 +32,16 @@ inline bool sig_of_plan(const DCfg& c, const FastPlan& p, uint32_t& nf, uint64_t
     return true;
 }
 
+// f(integral_constant<uint32_t, 0>) ... f(integral_constant<uint32_t, N - 1>): a loop whose index is a constant expression
+template <class F, uint32_t... Ks>
+__host__ __device__ __forceinline__ void glx_static_for_impl(F&& f, std::integer_sequence<uint32_t, Ks...>) {
+    (f(std::integral_constant<uint32_t, Ks>{}), ...);
+}
+template <uint32_t N, class F>
+__host__ __device__ __forceinline__ void glx_static_for(F&& f) {
+    glx_static_for_impl(f, std::make_integer_sequence<uint32_t, N>{});
+}
+
 template <uint32_t NF, uint64_t MODES, uint64_t NUMS, uint64_t NRVS>
 struct TiledSig {
     static constexpr uint32_t nf = NF;
@@ -40,6 +53,163 @@ struct TiledSig {
     static constexpr uint32_t W = ((GLX_BLOB_HDR + n_rv + 3u) & ~3u) < GLX_BLOB_MIN ? GLX_BLOB_MIN : ((GLX_BLOB_HDR + n_rv + 3u) & ~3u);
     static constexpr uint32_t NRV_ARR = n_rv ? n_rv : 1;
 };
+
+// build_record_blob_cached with the field table unrolled over the signature: the blob is a register array with
+// compile-time word positions, so the resolve kernel can store its row straight from registers (no shared-memory staging,
+// no block barrier). Same result as build_record_blob for a plan with views whose signature is Sig.
+template <class Sig>
+__device__ __forceinline__ void build_record_blob_sig(const DCfg& cfg, const FastPlan& plan, const DRecs& R, uint64_t r, bool last_of_sample, int32_t (&w)[Sig::W]) {
+    static_assert(Sig::W == 16, "the variant view occupies words 6..15 of a 16-word row");
+    const uint8_t flags = R.flags[r];
+    const int na = R.n_allele[r];
+    const uint32_t gtw = R.gt[r];
+    const int rbeg = R.beg[r], rend = R.end[r], rmaxend = R.maxend[r];
+    const int beg_next = last_of_sample ? 0x7fffffff : R.beg[r + 1];
+    const uint32_t a_off = R.allele_off[r];
+    int32_t clen[GLX_VIEW_COLS], cval[GLX_VIEW_COLS];
+#pragma unroll
+    for (int j = 0; j < GLX_VIEW_COLS; j++) {
+        const bool on = j < plan.n_vc;
+        const size_t idx = (on ? (size_t)plan.vc[j] * R.n_records : 0) + r;
+        const uint16_t l = R.col_len[idx];
+        const int32_t v = R.col_val[idx];
+        clen[j] = on ? (int32_t)l : (int32_t)GLX_LEN_ABSENT;
+        cval[j] = on ? v : 0;
+    }
+    auto column = [&](int col, int& rv, int32_t& val) {
+        rv = -1;
+        val = 0;
+        if (col < 0) return;
+        const int j = plan.vc_slot[col];
+        rv = view_rv((uint32_t)pick(clen, j));
+        val = pick(cval, j);
+    };
+#pragma unroll
+    for (uint32_t j = GLX_BLOB_HDR; j < Sig::W; j++) w[j] = 0;
+    int mrd = -1;
+    uint32_t bits = RB_SLOW;
+    // ---- a well-formed reference band? ----
+    do {
+        if (!(flags & GLX_RF_IS_REF) || na != 2 || (flags & GLX_RF_NO_GT)) break;
+        int g0, g1;
+        decode_gt(gtw, flags, g0, g1);
+        if ((!gt_is_missing(g0) && (g0 == GLXD_INT_VEND || gt_allele(g0) >= na)) || (!gt_is_missing(g1) && (g1 == GLXD_INT_VEND || gt_allele(g1) >= na))) break;
+        uint32_t b = 0;
+        if (!(flags & GLX_RF_HAPLOID) && (gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0)) b |= RB_NONCALLED;
+        int ref_rv;
+        int32_t ref_val;
+        column(cfg.col_ref_dp, ref_rv, ref_val);
+        if (ref_rv != 1) break;  // "reference depth FORMAT field is missing or malformed"
+        bool ok = true;
+        glx_static_for<Sig::nf>([&](auto kc) {
+            constexpr uint32_t k = decltype(kc)::value;
+            if (!ok) return;
+            const DFld& f = cfg.f[k];
+            constexpr uint32_t c0 = GLX_BLOB_HDR + Sig::rv0(k);
+            const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
+            const int32_t dflt = f.default_zero ? 0 : missing;
+            if (Sig::mode(k) == FM_PATTERN && f.kind == GLX_FK_PL2) {
+                int rvv;
+                int32_t val;
+                column(cfg.col_pl, rvv, val);
+                int32_t p0 = 0, p1 = 0, p2 = 0;
+                if (rvv > 0) {
+                    if (rvv != 3) {
+                        ok = false;
+                        return;
+                    }
+                    b |= (uint32_t)RB_FOUND0 << k;
+                    const int32_t* buf = R.pool + val;
+                    p0 = buf[0];
+                    p1 = buf[1];
+                    p2 = buf[2];
+                    const bool zero = p0 == 0 || p1 == 0 || p2 == 0;
+                    const bool other = (p0 != 0 && p0 != GLXD_INT_MISSING) || (p1 != 0 && p1 != GLXD_INT_MISSING) || (p2 != 0 && p2 != GLXD_INT_MISSING);
+                    if (!(zero && other)) p0 = p1 = p2 = 0;
+                    else {
+                        if (p0 == GLXD_INT_MISSING) p0 = 990;
+                        if (p1 == GLXD_INT_MISSING) p1 = 990;
+                        if (p2 == GLXD_INT_MISSING) p2 = 990;
+                    }
+                }
+                if (Sig::nrv(k) >= 4) {
+                    w[c0] = p0;
+                    w[c0 + 1] = p1;
+                    w[c0 + 2] = p1;
+                    w[c0 + 3] = p2;
+                }
+                return;
+            }
+            int n_val = f.count;
+            if (Sig::num(k) == GLX_NUM_ALT) n_val = 1;
+            else if (Sig::num(k) == GLX_NUM_ALLELES) n_val = 2;
+            else if (Sig::num(k) == GLX_NUM_GENOTYPE) n_val = 3;
+            bool found = false;
+            int32_t val = 0;
+            for (int ci = 0; ci < f.n_cols && !found && ok; ci++) {
+                int rvv;
+                column(f.cols[ci], rvv, val);
+                if (rvv == -2) ok = false;
+                else if (rvv >= 0) {
+                    if (rvv != n_val) ok = false;
+                    found = true;
+                }
+            }
+            if (ok && !found && f.kind == GLX_FK_AD) {  // AD falls back to the reference depth as a 1-value field
+                n_val = 1;
+                val = ref_val;
+                found = true;
+            }
+            if (!ok) return;
+            if (found) b |= (uint32_t)RB_FOUND0 << k;
+            if (Sig::mode(k) == FM_CONST) return;  // PL of a lone band: validated only
+            const int32_t* vec = R.pool + val;
+            if (Sig::mode(k) == FM_VEC) {
+#pragma unroll
+                for (uint32_t j = 0; j < Sig::nrv(k); j++) w[c0 + j] = found ? (n_val == 1 ? val : vec[j]) : dflt;
+            } else if (Sig::nrv(k) >= 4) {
+                const int32_t x0 = found ? (n_val == 1 ? val : vec[0]) : dflt;
+                w[c0] = x0;
+                w[c0 + 1] = (plan.vec_rule[k] && x0 == GLXD_INT_MISSING && dflt == GLXD_INT_MISSING) ? GLXD_INT_VEND : dflt;
+                w[c0 + 2] = dflt;
+                w[c0 + 3] = dflt;
+            }
+        });
+        if (!ok) {
+#pragma unroll
+            for (uint32_t j = GLX_BLOB_HDR; j < Sig::W; j++) w[j] = 0;
+            break;
+        }
+        mrd = (int)(unsigned)ref_val;
+        bits = b;
+    } while (0);
+    // ---- a variant record: its view ----
+    if ((bits & RB_SLOW) && !(flags & GLX_RF_IS_REF)) {
+        bool fits = true;
+        uint32_t code[GLX_VIEW_COLS];
+#pragma unroll
+        for (int j = 0; j < GLX_VIEW_COLS; j++) {
+            code[j] = j < plan.n_vc ? view_len_code((uint32_t)clen[j]) : 0u;
+            if (code[j] == 0xFFCu) fits = false;
+        }
+        if (fits) {
+            mrd = (int)gtw;
+            w[6] = (int32_t)a_off;
+            w[7] = (int32_t)((uint32_t)(flags & 0x7f) | (uint32_t)na << 8 | code[0] << 16 | code[1] << 28);
+            w[8] = (int32_t)(code[1] >> 4 | code[2] << 8 | code[3] << 20);
+            w[9] = (int32_t)(code[4] | code[5] << 12);
+#pragma unroll
+            for (int j = 0; j < GLX_VIEW_COLS; j++) w[10 + j] = j < plan.n_vc ? cval[j] : 0;
+            bits |= RB_VIEW;
+        }
+    }
+    w[0] = rbeg;
+    w[1] = rend;
+    w[2] = rmaxend;
+    w[3] = (int32_t)bits;
+    w[4] = mrd;
+    w[5] = beg_next;
+}
 
 // A lane reads its sample's blobs in order, one 64-byte row per cursor step, and waits for each: ask L2 to bring the
 // following rows along (256-byte prefetch granule), so that the next steps find theirs in L2 instead of HBM.

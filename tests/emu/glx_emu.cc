@@ -178,6 +178,20 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
         bool handled = false;
         if (!dynamic_only && sig_of_plan(C, plan, nf, modes, nums, nrvs)) {  // same dispatch as glx_upload
             auto match = [&](uint32_t NF, uint64_t M, uint64_t Nu, uint64_t Nr) { return nf == NF && modes == M && nums == Nu && nrvs == Nr; };
+            // glx_resolve_sig_kernel builds its rows with the signature's unrolled builder: must be the same rows
+            auto check_rows = [&](auto sig) -> bool {
+                using Sig = decltype(sig);
+                if (!plan.vview) return true;
+                for (uint32_t d = 0; d < N; d++)
+                    for (uint64_t r = R.ds_rec_off[d]; r < R.ds_rec_off[d + 1]; r++) {
+                        int32_t w[Sig::W];
+                        build_record_blob_sig<Sig>(C, plan, R, r, r + 1 == R.ds_rec_off[d + 1], w);
+                        if (memcmp(w, blobs.data() + r * W, sizeof w) != 0) return false;
+                    }
+                return true;
+            };
+            if (match(4, 0x1010ull, 0x2030ull, 0x4141ull) ? !check_rows(SigDeepVariant()) : (match(5, 0x20010ull, 0x20030ull, 0x01441ull) ? !check_rows(SigGatk()) : false))
+                return GLX_E_INVALID - 1000;  // signature builder disagrees with build_record_blob
             if (match(4, 0x1010ull, 0x2030ull, 0x4141ull)) {
                 run_tiled_sig<SigDeepVariant>(C, plan, R, S, O, blobs.data(), cursors.data(), flags, cnt, n_slow);
                 handled = true;
