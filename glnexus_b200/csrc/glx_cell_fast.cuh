@@ -16,6 +16,9 @@
 // a lane copies the blob into its cache when its cursor advances and re-reads nothing while consecutive sites fall
 // in the same band.
 #pragma once
+#include <type_traits>
+#include <utility>
+
 #include "glx_cell_general.cuh"
 
 namespace glxd {
@@ -356,6 +359,16 @@ __device__ inline void fill_tile_cursors(const DRecs& R, uint64_t r, uint64_t sa
         t_lo = lo;
     }
     for (uint32_t tile = t_lo; tile < t_hi; tile++) cursors[(size_t)tile * n_samples + sample] = (uint32_t)(r - sample_base);
+}
+
+// f(integral_constant<uint32_t, 0>) ... f(integral_constant<uint32_t, N - 1>): a loop whose index is a constant expression
+template <class F, uint32_t... Ks>
+__host__ __device__ __forceinline__ void glx_static_for_impl(F&& f, std::integer_sequence<uint32_t, Ks...>) {
+    (f(std::integral_constant<uint32_t, Ks>{}), ...);
+}
+template <uint32_t N, class F>
+__host__ __device__ __forceinline__ void glx_static_for(F&& f) {
+    glx_static_for_impl(f, std::make_integer_sequence<uint32_t, N>{});
 }
 
 // a[j] for a register array and a run-time j

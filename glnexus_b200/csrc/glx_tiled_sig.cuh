@@ -5,9 +5,6 @@
 // glx_cell_fast.cuh (same blobs, same classification, same patterns); configs whose signature has no instantiation
 // run the dynamic kernel there. Reference lines: see glx_cell_fast.cuh.
 #pragma once
-#include <type_traits>
-#include <utility>
-
 #include "glx_cell_fast.cuh"
 #include "glx_cell_variant.cuh"
 
@@ -30,16 +27,6 @@ inline bool sig_of_plan(const DCfg& c, const FastPlan& p, uint32_t& nf, uint64_t
         nrvs |= (uint64_t)p.nrv[k] << (4 * k);
     }
     return true;
-}
-
-// f(integral_constant<uint32_t, 0>) ... f(integral_constant<uint32_t, N - 1>): a loop whose index is a constant expression
-template <class F, uint32_t... Ks>
-__host__ __device__ __forceinline__ void glx_static_for_impl(F&& f, std::integer_sequence<uint32_t, Ks...>) {
-    (f(std::integral_constant<uint32_t, Ks>{}), ...);
-}
-template <uint32_t N, class F>
-__host__ __device__ __forceinline__ void glx_static_for(F&& f) {
-    glx_static_for_impl(f, std::make_integer_sequence<uint32_t, N>{});
 }
 
 template <uint32_t NF, uint64_t MODES, uint64_t NUMS, uint64_t NRVS>

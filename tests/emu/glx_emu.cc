@@ -101,7 +101,7 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                 if (type == CT_SLOW) {
                     n_slow++;
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
-                    if (single && genotype_cell_variant<8>(C, plan, R, S, O, blobs, s, n, R.ds_rec_off[n] + L.c, vsm, 1)) {
+                    if (single && genotype_cell_variant<8, Sig>(C, plan, R, S, O, blobs, s, n, R.ds_rec_off[n] + L.c, vsm, 1)) {
                         g_emu_stats[0]++;
                         g_emu_stats[4]++;
                         continue;
