@@ -51,6 +51,32 @@ def algorithmic_bytes(batch, n_var_cells):
     return out_b + in_b, out_b, in_b
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs local to its GPU's PCIe root complex (sysfs local_cpulist of the device), so that the
+    pinned host buffers it allocates are first-touched on that NUMA node. Returns the node, or None if unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        node = int(open(base + "/numa_node").read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -207,6 +233,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)  # pinned host buffers land next to the GPU's PCIe root (first touch)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -369,7 +397,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, n_samples, n_sites), "preset": synth_cases.SHAPES[shape][0],
-                       "cells_per_gpu": cells, "records_per_gpu": int(batch.n_records), "variant_records_per_gpu": int(batch.variant_records),
+                       "cells_per_gpu": cells, "numa_node": numa, "records_per_gpu": int(batch.n_records), "variant_records_per_gpu": int(batch.variant_records),
                        "l2": "flushed between timed steps (256 MiB write, untimed); outputs (%.2f GB/step) exceed L2" % (out_b / 1e9)},
             "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_narrow), "steps": e2e_steps,
                     "mode": "pinned host buffers, batches pipelined 2 deep on 2 streams; integer columns delivered in the width BCF would store "
@@ -389,6 +417,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core back
             cb, _ = cpu_baseline(shape, n_samples, region_len / n_sites, n_sites)
             line["cpu_baseline"] = cb
         else:

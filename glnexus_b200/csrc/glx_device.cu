@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
             const uint2 e = w[it];
-            if (!(e.y & GLX_WORK_SINGLE)) continue;
+            if ((e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) != GLX_WORK_SINGLE) continue;
             const uint32_t s = e.x / N, sample = e.x % N;
             const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
             if (genotype_cell_variant<CAPA>(cfg, plan, R, S, O, blobs, s, sample, first, s_cols + threadIdx.x, blockDim.x)) w[it].y = e.y | GLX_WORK_DONE;
@@ -854,7 +854,13 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
             const char* nr_env = getenv("GLX_NO_RESOLVE_SIG");
             const bool no_rsig = nr_env && *nr_env && *nr_env != '0';
             const char* nf_env = getenv("GLX_NO_FUSE");
-            const bool fuse = d->plan.vview && d->max_site_alleles <= 4 && !(nf_env && *nf_env && *nf_env != '0');
+            // Fusing pays when the output the resident CTAs have in flight (~1,000 half-height tiles) is of the order of
+            // L2: up to ~48 output bytes per cell (DeepVariant-style fields at mostly biallelic sites are 32; gatk-style
+            // cohorts with up to 7 alleles are ~100 and measured 6 % slower fused). Cells of sites with more than 4
+            // alleles are declined by the fused form and go to glx_cells_variant_kernel<8>.
+            uint64_t out_bytes = d->n_cells * 4;
+            for (uint32_t k = 0; k < cfg->n_fields; k++) out_bytes += d->fld_total[k] * 4;
+            const bool fuse = d->plan.vview && out_bytes <= d->n_cells * 48 && !(nf_env && *nf_env && *nf_env != '0');
             // A CTA finishes its lone-variant-record cells when its tile is done; their output sectors are still in L2
             // only if the tiles in flight are small enough, so variant-dense batches (>= 1 variant record per 100
             // cells) walk half-height tiles. Sparse ones keep the full height (fewer cursor set-ups per site).
@@ -972,7 +978,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             const uint32_t region_cells = d->tile_sites * d->samples_per_cta;
             glx_cells_bands_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->blobs);
             d->launches_per_call++;
-            if (d->plan.vview && !d->fused_variant) {  // small sites keep the per-thread shared-memory columns short
+            if (d->plan.vview && (!d->fused_variant || d->max_site_alleles > 4)) {  // small sites keep the per-thread shared-memory columns short
                 if (d->max_site_alleles <= 4)
                     glx_cells_variant_kernel<4><<<g1, 128, VariantSmem<4>::SLOTS * 128 * 4, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1,
                                                                                                    region_cells, d->blobs);

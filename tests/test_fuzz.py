@@ -37,11 +37,16 @@ def test_fuzz_emu(built, chunk):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["sig", "dynamic", "general"])
+@pytest.mark.parametrize("path", ["sig", "sig-unfused", "dynamic", "general"])
 def test_fuzz_gpu(built, path, monkeypatch):
     from glnexus_b200 import Context, GlxError
     monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
     monkeypatch.delenv("GLX_FORCE_DYNAMIC_TILED", raising=False)
+    monkeypatch.delenv("GLX_NO_FUSE", raising=False)
+    monkeypatch.delenv("GLX_NO_RESOLVE_SIG", raising=False)
+    if path == "sig-unfused":  # signature tiled kernel + separate variant kernel + generic resolve kernel
+        monkeypatch.setenv("GLX_NO_FUSE", "1")
+        monkeypatch.setenv("GLX_NO_RESOLVE_SIG", "1")
     if path == "general":
         monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
     elif path == "dynamic":

@@ -47,12 +47,17 @@ def test_gpu_golden(ctx, name):
     ("c4", 2000, 1500, 96000),
     ("c5", 600, 2000, 60000),
 ])
-@pytest.mark.parametrize("path", ["sig", "dynamic", "general"])
+@pytest.mark.parametrize("path", ["sig", "sig-unfused", "dynamic", "general"])
 def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, path, monkeypatch):
     """Signature-specialised tiled kernel (default), the dynamic tiled kernel, and the general kernel alone must all
     equal the oracle on every output column."""
     monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
     monkeypatch.delenv("GLX_FORCE_DYNAMIC_TILED", raising=False)
+    monkeypatch.delenv("GLX_NO_FUSE", raising=False)
+    monkeypatch.delenv("GLX_NO_RESOLVE_SIG", raising=False)
+    if path == "sig-unfused":  # signature tiled kernel + separate variant kernel + generic resolve kernel
+        monkeypatch.setenv("GLX_NO_FUSE", "1")
+        monkeypatch.setenv("GLX_NO_RESOLVE_SIG", "1")
     if path == "general":
         monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
     elif path == "dynamic":
