@@ -123,13 +123,34 @@ __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kerne
         }
 }
 
+// Once per upload: for every block of GLX_RESOLVE_THREADS records, the sample of its first record and that record's
+// t_hi (first tile whose tq >= its maxend); entry n_blocks closes the table with (last sample, n_tiles). The resolve
+// kernel's per-record searches then run inside [hint[b], hint[b + 1]] instead of over all samples / all tiles.
+__global__ void __launch_bounds__(256) glx_block_hints_kernel(const DRecs R, uint32_t n_datasets, const int32_t* __restrict__ tile_q, uint32_t n_tiles,
+                                                              uint2* __restrict__ hints, uint32_t n_blocks) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_blocks) return;
+    if (b == n_blocks) {
+        hints[b] = make_uint2(n_datasets ? n_datasets - 1 : 0u, n_tiles);
+        return;
+    }
+    const uint64_t r = (uint64_t)b * GLX_RESOLVE_THREADS;
+    uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= r < ds_rec_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (R.ds_rec_off[mid] <= r) lo = mid;
+        else hi = mid;
+    }
+    hints[b] = make_uint2(lo, first_tile_at_or_after(tile_q, 0, n_tiles, R.maxend[r]));
+}
+
 // The same, for a config whose field signature is instantiated (the preset signatures) and whose plan has record views:
 // the row is built in registers by the unrolled builder and stored as four 16-byte vectors; the tile-cursor searches are
 // confined and exchanged inside the warp (shuffles), so the kernel has no shared memory and no block barrier.
 template <class Sig>
 __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets,
                                                                               int32_t* __restrict__ blobs, const int32_t* __restrict__ tile_q, uint32_t n_tiles,
-                                                                              uint32_t* __restrict__ tile_cursors) {
+                                                                              uint32_t* __restrict__ tile_cursors, const uint2* __restrict__ hints) {
     const uint64_t r = (uint64_t)blockIdx.x * GLX_RESOLVE_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = r < R.n_records;
@@ -143,41 +164,24 @@ __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_sig_kernel(co
         for (uint32_t q = 0; q < Sig::W / 4; q++) dst[q] = make_int4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
 #ifndef GLX_ABLATE_CURSORS
-    // sample of the record: searched by the warp's first and last lane, then inside their range
-    uint32_t lo = 0, hi = n_datasets;
-    if (lane == 0 || lane == 31) {
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (R.ds_rec_off[mid] <= rr) lo = mid;
-            else hi = mid;
-        }
-    }
-    const uint32_t s_first = __shfl_sync(0xffffffffu, lo, 0), s_last = __shfl_sync(0xffffffffu, lo, 31);
-    if (lane != 0 && lane != 31) {
-        lo = s_first;
-        hi = s_last + 1;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (R.ds_rec_off[mid] <= rr) lo = mid;
-            else hi = mid;
-        }
+    // sample of the record and its t_hi (first tile whose tq >= maxend[r]): searched inside the block's hint range.
+    // Inside one sample maxend is non-decreasing, so t_hi lies between the hints of this block and the next.
+    const uint2 h0 = hints[blockIdx.x], h1 = hints[blockIdx.x + 1];
+    uint32_t lo = h0.x, hi = h1.x + 1;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (R.ds_rec_off[mid] <= rr) lo = mid;
+        else hi = mid;
     }
     const uint32_t sample = lo;
     const uint64_t base = R.ds_rec_off[sample];
-    // t_hi = first tile whose tq >= maxend[r]; inside one sample maxend is non-decreasing, so the warp's searches are
-    // confined to the range of its first and last lane
-    const int my_maxend = w[2];
-    uint32_t t_hi = 0;
-    if (lane == 0 || lane == 31) t_hi = first_tile_at_or_after(tile_q, 0, n_tiles, my_maxend);
-    const uint32_t th_first = __shfl_sync(0xffffffffu, t_hi, 0), th_last = __shfl_sync(0xffffffffu, t_hi, 31);
-    if (lane != 0 && lane != 31) {
-        const bool one_sample = s_first == s_last;
-        t_hi = first_tile_at_or_after(tile_q, one_sample ? th_first : 0u, one_sample ? th_last : n_tiles, my_maxend);
-    }
+    const bool one_sample = h0.x == h1.x;
+    const uint32_t t_hi = first_tile_at_or_after(tile_q, one_sample ? h0.y : 0u, one_sample ? h1.y : n_tiles, w[2]);
     uint32_t t_lo = __shfl_up_sync(0xffffffffu, t_hi, 1);  // the previous record's t_hi
     if (valid) {
         if (r == base) t_lo = 0;
-        else if (lane == 0) t_lo = first_tile_at_or_after(tile_q, 0, t_hi, R.maxend[r - 1]);
+        else if (lane == 0)  // the previous record is another warp's (for thread 0: another block's, below this block's hint)
+            t_lo = first_tile_at_or_after(tile_q, (one_sample && threadIdx.x) ? h0.y : 0u, t_hi, R.maxend[r - 1]);
         for (uint32_t tile = t_lo; tile < t_hi; tile++) tile_cursors[(size_t)tile * n_datasets + sample] = (uint32_t)(r - base);
     }
 #endif
@@ -545,7 +549,7 @@ struct glx_dev_batch {
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
     uint32_t samples_per_cta = GLX_TILE_THREADS;  // one sample per lane
-    typedef void (*resolve_fn)(const DCfg, const FastPlan, const DRecs, uint32_t, int32_t*, const int32_t*, uint32_t, uint32_t*);
+    typedef void (*resolve_fn)(const DCfg, const FastPlan, const DRecs, uint32_t, int32_t*, const int32_t*, uint32_t, uint32_t*, const uint2*);
     typedef void (*tiled_fn)(const DCfg, const FastPlan, const DRecs, const DSites, const DOut, const int32_t*, const uint32_t*, uint2*, uint32_t*, uint32_t,
                              uint32_t);
     resolve_fn resolve_sig = nullptr;  // signature-specialised resolve kernel (plans with record views), else the generic one
@@ -555,6 +559,7 @@ struct glx_dev_batch {
     size_t blob_bytes = 0;
     uint32_t* tile_cursors = nullptr;  // [n_site_tiles][n_samples]
     int32_t* tile_q = nullptr;         // [n_site_tiles] suffix-min of each tile's first qbeg
+    uint2* block_hints = nullptr;      // [resolve blocks + 1] (sample, t_hi) of each block's first record (glx_block_hints_kernel)
     uint32_t n_datasets = 0;
 };
 
@@ -900,7 +905,9 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * region_cells);
         const size_t blob_part = ((Rn + 1) * blob_words(d->plan.n_rv) * 4 + 255) & ~(size_t)255;
         const size_t cur_part = (((size_t)d->n_site_tiles * N + 1) * 4 + 255) & ~(size_t)255;
-        d->blob_bytes = blob_part + cur_part + ((size_t)d->n_site_tiles + 1) * 4;
+        const size_t tq_part = (((size_t)d->n_site_tiles + 1) * 4 + 255) & ~(size_t)255;
+        const size_t n_rblocks = (Rn + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS;
+        d->blob_bytes = blob_part + cur_part + tq_part + (n_rblocks + 2) * sizeof(uint2);
         e = ctx->take((void**)&d->blobs, d->blob_bytes);
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
@@ -919,6 +926,13 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         if (e != cudaSuccess) {
             glx_free_batch(ctx, d);
             return cuda_fail(ctx, e, "upload(tile_q)");
+        }
+        d->block_hints = reinterpret_cast<uint2*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part + tq_part);
+        glx_block_hints_kernel<<<(unsigned)((n_rblocks + 1 + 255) / 256), 256, 0, up>>>(d->R, (uint32_t)D, d->tile_q, d->n_site_tiles, d->block_hints, (uint32_t)n_rblocks);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            glx_free_batch(ctx, d);
+            return cuda_fail(ctx, e, "glx_block_hints_kernel");
         }
     }
     d->n_datasets = (uint32_t)D;
@@ -947,7 +961,8 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
         if (d->R.n_records) {
             const unsigned rgrid = (unsigned)((d->R.n_records + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS);
             if (d->resolve_sig)
-                d->resolve_sig<<<rgrid, GLX_RESOLVE_THREADS, 0, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors);
+                d->resolve_sig<<<rgrid, GLX_RESOLVE_THREADS, 0, st>>>(d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors,
+                                                                      d->block_hints);
             else
                 glx_resolve_records_kernel<<<rgrid, GLX_RESOLVE_THREADS, (size_t)GLX_RESOLVE_THREADS * (blob_words(d->plan.n_rv) + 1) * 4, st>>>(
                     d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors);
