@@ -69,7 +69,7 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
 // composition of the cells the fast path declines: [0] finished by the single-record closed form, [1] general path,
 // [2] finished by the all-bands closed form, [3] all-band cells that nevertheless went to the general path
 static int32_t vsm[64];  // the shared-memory column of genotype_cell_variant, stride 1
-static uint64_t g_emu_stats[8];  // [0] single-record closed form [1] general [2] all-band closed form [3] bands declined [4] of [0]: through the record view
+static uint64_t g_emu_stats[8];  // [0] single-record closed form [1] general [2] all-band closed form [3] bands declined [4] of [0]: through the record view; [5..7] see note_general
 extern "C" void glx_emu_stats(uint64_t out[8]) { memcpy(out, g_emu_stats, sizeof g_emu_stats); }
 static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t first, uint64_t hi) {
     g_emu_stats[1]++;
@@ -81,6 +81,14 @@ static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t f
         if (!(R.flags[r] & GLX_RF_IS_REF)) all_ref = false;
     }
     if (all_ref && n >= 2) g_emu_stats[3]++;  // all-band cells the bands form declined
+    if (S.monoallelic[s]) g_emu_stats[5]++;   // [5] cells of monoallelic sites
+    else if (!all_ref) {
+        int nv = 0;
+        for (uint64_t r = first; r < hi && R.beg[r] < S.qend[s]; r++)
+            if (R.end[r] > S.qbeg[s] && !(R.flags[r] & GLX_RF_IS_REF)) nv++;
+        if (nv == 1) g_emu_stats[6]++;        // [6] bands + exactly one variant record
+        else g_emu_stats[7]++;                // [7] several variant records
+    }
 }
 
 // signature-specialised lanes (glx_tiled_sig.cuh), lane by lane
