@@ -114,19 +114,6 @@ inline FastPlan make_fast_plan(const DCfg& c) {
     return p;
 }
 
-#ifdef __CUDACC__
-// Ampere+ asynchronous global->shared copies (SASS LDGSTS); 16-byte granules, L2-only (.cg): blobs are read once
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_but() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-#endif
-
 // first record of [lo,hi) whose running max end exceeds qbeg (records with maxend <= qbeg cannot overlap the query)
 __device__ __forceinline__ uint64_t first_candidate(const int32_t* __restrict__ maxend, uint64_t lo, uint64_t hi, int qbeg) {
     while (lo < hi) {

@@ -41,10 +41,5 @@ inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
-// asynchronous copies degrade to immediate ones on the host
-inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
-inline void cp_async_commit() {}
-template <int N>
-inline void cp_async_wait_but() {}
 template <class T>
 inline T __ldg(const T* p) { return *p; }
