@@ -366,12 +366,14 @@ __global__ void __launch_bounds__(128) glx_cells_bands_kernel(const DCfg cfg, co
     }
 }
 
+__device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // General path: one thread per cell. With a worklist, block b serves the CTA-private regions b, b+gridDim.x, ... that
 // the tiled kernel filled (cell id + the lane's record cursor; region r holds n_work[r] entries) and takes the cells
 // the single-record pass left; without one it takes every cell of the batch and finds the cursor by binary search.
 __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, const DRecs R, const DSites S, const DOut O, const uint2* __restrict__ worklist,
                                                                 const uint32_t* __restrict__ n_work, uint32_t reg0, uint32_t n_regions, uint32_t region_cells,
-                                                                uint64_t n_all, uint8_t* __restrict__ cnt_scratch, uint32_t max_slots) {
+                                                                uint64_t n_all, uint8_t* __restrict__ cnt_scratch, uint32_t max_slots, uint32_t n_cols) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint8_t* cnt = cnt_scratch + tid;
@@ -387,6 +389,17 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
                 if (e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) continue;  // finished by glx_cells_single_kernel
                 const uint32_t s = e.x / N, sample = e.x % N;
                 const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
+#ifndef GLX_ABLATE_GENERAL_PREFETCH
+                // The general form walks the cell's records one dependent load at a time; ask L2 for their lines first.
+                for (uint64_t r = lo + (e.y & GLX_WORK_CURSOR), k = 0; r < hi && k < 4; r++, k++) {
+                    pf_l2(R.beg + r); pf_l2(R.end + r); pf_l2(R.flags + r); pf_l2(R.n_allele + r); pf_l2(R.gt + r); pf_l2(R.allele_off + r);
+                    pf_l2(R.qual + r); pf_l2(R.filt + r);
+                    for (uint32_t c = 0; c < n_cols; c++) {
+                        pf_l2(R.col_len + (size_t)c * R.n_records + r);
+                        pf_l2(R.col_val + (size_t)c * R.n_records + r);
+                    }
+                }
+#endif
                 genotype_cell_general(cfg, R, S, O, s, sample, lo + (e.y & GLX_WORK_CURSOR), hi, cnt, stride);
             }
         }
@@ -534,6 +547,7 @@ struct glx_dev_batch {
     bool force_general = false;
     uint32_t n_chunks = 1;
     uint32_t max_site_alleles = 0;
+    uint32_t n_cols = 0;  // source columns of the record store
     uint32_t tile_sites = GLX_TILE_SITES;  // sites per tile of the tiled kernel in use
     bool fused_variant = false;  // the tiled kernel finishes its own lone-variant cells
     std::vector<int32_t> tq_host;
@@ -694,6 +708,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     d->n_sites = (uint32_t)S;
     d->n_samples = (uint32_t)N;
     d->n_fields = cfg->n_fields;
+    d->n_cols = cfg->n_cols;
     d->n_cells = S * N;
     const char* fg = getenv("GLX_FORCE_GENERAL");
     d->force_general = fg && *fg && *fg != '0';
@@ -1006,7 +1021,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[3], st));
             const uint32_t g2 = nreg < (uint32_t)d->general_blocks ? nreg : (uint32_t)d->general_blocks;
             glx_cells_general_kernel<<<g2, 128, 0, ws>>>(d->cfg, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->n_cells, d->cnt_scratch,
-                                                         d->max_slots);
+                                                         d->max_slots, d->n_cols);
             d->launches_per_call += 2;
             CU(cudaGetLastError());
         }
@@ -1025,7 +1040,8 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             CU(cudaEventRecord(d->ev[3], st));
         }
         if (d->n_cells) {
-            glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots);
+            glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots,
+                                                                        d->n_cols);
             d->launches_per_call++;
             CU(cudaGetLastError());
         }
