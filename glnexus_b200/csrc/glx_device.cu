@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) glx_prepare_inputs_kernel(const DRecs R, 
 // in shared memory and written out by the whole block as one contiguous, fully coalesced span. The same threads fill
 // the tile cursor table (fill_tile_cursors states what is written): record r claims the tiles [t_lo, t_hi) with
 // t_hi = first tile whose tq >= maxend[r] and t_lo = the previous record's t_hi, so each thread runs one search and
-// takes t_lo from its neighbour; when the whole block lies in one sample, maxend is non-decreasing across it and the
-// searches are confined to the block's own range of tiles.
+// takes t_lo from its neighbour; the per-block hints of glx_block_hints_kernel confine the searches (when the whole block
+// lies in one sample, maxend is non-decreasing across it, so t_hi lies between this block's hint and the next one's).
 #define GLX_RESOLVE_THREADS 256
 __device__ __forceinline__ uint32_t first_tile_at_or_after(const int32_t* __restrict__ tq, uint32_t lo, uint32_t hi, int v) {
     while (lo < hi) {
@@ -65,35 +65,24 @@ __device__ __forceinline__ uint32_t first_tile_at_or_after(const int32_t* __rest
 }
 __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, uint32_t n_datasets,
                                                                                   int32_t* __restrict__ blobs, const int32_t* __restrict__ tile_q,
-                                                                                  uint32_t n_tiles, uint32_t* __restrict__ tile_cursors) {
+                                                                                  uint32_t n_tiles, uint32_t* __restrict__ tile_cursors,
+                                                                                  const uint2* __restrict__ hints) {
     extern __shared__ int32_t s_blob[];  // [GLX_RESOLVE_THREADS][W + 1]: rows padded by one word so that column writes spread over the banks
-    __shared__ uint32_t s_edge[4];       // sample of the block's first / last record, and their t_hi
     __shared__ uint32_t s_thi[GLX_RESOLVE_THREADS];
     const uint32_t W = blob_words(plan.n_rv), WP = W + 1;
     const uint32_t tid = threadIdx.x;
     const uint64_t r0 = (uint64_t)blockIdx.x * GLX_RESOLVE_THREADS;
     const uint64_t r = r0 + tid;
     const uint64_t n_here = min((uint64_t)GLX_RESOLVE_THREADS, R.n_records - r0);
-#ifndef GLX_ABLATE_CURSORS
-    if (tid < 2) {  // which samples hold the block's first and last record? (ds_rec_off is small and cache-resident)
-        const uint64_t rq = tid ? r0 + n_here - 1 : r0;
-        uint32_t lo = 0, hi = n_datasets;  // invariant: ds_rec_off[lo] <= rq < ds_rec_off[hi]
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (R.ds_rec_off[mid] <= rq) lo = mid;
-            else hi = mid;
-        }
-        s_edge[tid] = lo;
-        s_edge[2 + tid] = first_tile_at_or_after(tile_q, 0, n_tiles, R.maxend[rq]);
-    }
-#endif
     if (r < R.n_records) build_record_blob(cfg, plan, R, r, R.flags[r] & GLX_RF_DEV_LAST, s_blob + tid * WP);  // glx_upload marks each sample's last record
     __syncthreads();
 #ifndef GLX_ABLATE_CURSORS
     uint32_t sample = 0, t_hi = 0;
     uint64_t base = 0;
     if (r < R.n_records) {
-        uint32_t lo = s_edge[0], hi = s_edge[1] + 1;
+        // (sample, t_hi) of this block's and the next block's first record (glx_block_hints_kernel) bound both searches
+        const uint2 h0 = hints[blockIdx.x], h1 = hints[blockIdx.x + 1];
+        uint32_t lo = h0.x, hi = h1.x + 1;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (R.ds_rec_off[mid] <= r) lo = mid;
@@ -101,8 +90,8 @@ __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kerne
         }
         sample = lo;
         base = R.ds_rec_off[lo];
-        const bool one_sample = s_edge[0] == s_edge[1];
-        t_hi = first_tile_at_or_after(tile_q, one_sample ? s_edge[2] : 0u, one_sample ? s_edge[3] : n_tiles, R.maxend[r]);
+        const bool one_sample = h0.x == h1.x;
+        t_hi = first_tile_at_or_after(tile_q, one_sample ? h0.y : 0u, one_sample ? h1.y : n_tiles, R.maxend[r]);
         s_thi[tid] = t_hi;
     }
     __syncthreads();
@@ -980,7 +969,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
                                                                       d->block_hints);
             else
                 glx_resolve_records_kernel<<<rgrid, GLX_RESOLVE_THREADS, (size_t)GLX_RESOLVE_THREADS * (blob_words(d->plan.n_rv) + 1) * 4, st>>>(
-                    d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors);
+                    d->cfg, d->plan, d->R, d->n_datasets, d->blobs, d->tile_q, d->n_site_tiles, d->tile_cursors, d->block_hints);
             d->launches_per_call++;
             CU(cudaGetLastError());
         }
