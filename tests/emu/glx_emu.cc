@@ -259,3 +259,62 @@ extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* rec
     const int code = (int)(err & 0xff);
     return code == 101 ? GLX_E_UNSUPPORTED : -code;
 }
+
+// The resolve kernels confine their per-record searches with per-block hints (glx_block_hints_kernel) and take t_lo from
+// the neighbouring record. Replay that arithmetic for every record — block size `block`, tiles of `tile_sites` sites —
+// and compare the claimed tile range with fill_tile_cursors' definition (two full searches). Returns the mismatches.
+static uint32_t lower_tile(const int32_t* tq, uint32_t lo, uint32_t hi, int v) {
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tq[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+extern "C" int glx_emu_check_hints(const glx_records* recs, const glx_sites* sites, uint32_t tile_sites, uint32_t block) {
+    const uint64_t Rn = recs->n_records;
+    const uint32_t D = recs->n_datasets, Sn = sites->n_sites;
+    if (!Rn || !Sn) return 0;
+    const uint32_t n_tiles = (Sn + tile_sites - 1) / tile_sites;
+    std::vector<int32_t> tq(n_tiles);
+    int32_t run = INT32_MAX;
+    for (uint32_t tile = n_tiles; tile-- > 0;) {
+        run = std::min(run, sites->qbeg[(size_t)tile * tile_sites]);
+        tq[tile] = run;
+    }
+    auto sample_of = [&](uint64_t r, uint32_t lo, uint32_t hi) {
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (recs->ds_rec_off[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    };
+    const uint64_t n_blocks = (Rn + block - 1) / block;
+    std::vector<uint32_t> hs(n_blocks + 1), ht(n_blocks + 1);
+    for (uint64_t b = 0; b < n_blocks; b++) {
+        hs[b] = sample_of(b * block, 0, D);
+        ht[b] = lower_tile(tq.data(), 0, n_tiles, recs->maxend[b * block]);
+    }
+    hs[n_blocks] = D - 1;
+    ht[n_blocks] = n_tiles;
+    int bad = 0;
+    std::vector<uint32_t> thi(Rn);
+    for (uint64_t r = 0; r < Rn; r++) {
+        const uint64_t b = r / block;
+        const uint32_t sample = sample_of(r, hs[b], hs[b + 1] + 1);
+        if (!(recs->ds_rec_off[sample] <= r && r < recs->ds_rec_off[sample + 1])) bad++;
+        const bool one = hs[b] == hs[b + 1];
+        thi[r] = lower_tile(tq.data(), one ? ht[b] : 0u, one ? ht[b + 1] : n_tiles, recs->maxend[r]);
+        if (thi[r] != lower_tile(tq.data(), 0, n_tiles, recs->maxend[r])) bad++;
+        const uint64_t base = recs->ds_rec_off[sample];
+        uint32_t t_lo = 0;
+        if (r > base) {
+            const bool first_of_warp = (r % 32) == 0, first_of_block = (r % block) == 0;
+            t_lo = first_of_warp ? lower_tile(tq.data(), (one && !first_of_block) ? ht[b] : 0u, thi[r], recs->maxend[r - 1]) : thi[r - 1];
+            if (t_lo != lower_tile(tq.data(), 0, thi[r], recs->maxend[r - 1])) bad++;
+        }
+    }
+    return bad;
+}
+

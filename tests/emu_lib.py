@@ -31,6 +31,8 @@ def lib():
         L.glx_emu_general_batch.restype = C.c_int
         L.glx_emu_tiled_batch.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint64), C.c_int]
         L.glx_emu_tiled_batch.restype = C.c_int
+        L.glx_emu_check_hints.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+        L.glx_emu_check_hints.restype = C.c_int
         _lib = L
     return _lib
 
@@ -44,3 +46,9 @@ def tiled_batch(batch, out, dynamic_only=False):
     n = C.c_uint64()
     rc = lib().glx_emu_tiled_batch(batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr, C.byref(n), 1 if dynamic_only else 0)
     return rc, n.value
+
+
+def check_hints(batch, tile_sites, block):
+    """Mismatches between the resolve kernels' hint-confined tile searches and the full searches (0 = identical)."""
+    return lib().glx_emu_check_hints(batch.records_ptr, batch.sites_ptr, tile_sites, block)
+

@@ -72,3 +72,16 @@ def test_emu_real_gvcf_slice(built):
         assert not d, "\n".join(d)
     rnc = ref.array("rnc").tobytes().decode()
     assert ".." in rnc
+
+
+@pytest.mark.parametrize("tile_sites,block", [(64, 256), (32, 256), (32, 64), (16, 32)])
+def test_resolve_hint_arithmetic(built, tile_sites, block):
+    """The resolve kernels' confined searches (per-block hints, neighbour's t_hi as t_lo) must claim exactly the tiles
+    fill_tile_cursors defines, on the synthetic shapes and on irregular cohorts (several samples per block, empty samples)."""
+    import fuzz_cases
+    for shape, (ns, nsite, rl) in {"c2": (96, 700, 700), "c3": (300, 512, 32768), "c4": (2000, 128, 8192), "c5": (64, 300, 9000)}.items():
+        b = synth_cases.make(shape, n_samples=ns, n_sites=nsite, region_len=rl)
+        assert emu_lib.check_hints(b, tile_sites, block) == 0, shape
+    for seed in range(120):
+        assert emu_lib.check_hints(fuzz_cases.build_batch(seed), tile_sites, block) == 0, seed
+
