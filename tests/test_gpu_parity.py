@@ -180,6 +180,33 @@ def test_gpu_full_size_configs1(ctx):
     assert np.array_equal(used, ga["allele_used"])
 
 
+@pytest.mark.parametrize("shape,n_samples,n_sites,region_len", [
+    ("c3", 10000, 4096, 262144),   # one streamed batch of configs[2]
+    ("c4", 100000, 512, 32768),    # one streamed batch of configs[3]
+    ("c5", 5000, 10000, 300000),   # a tenth of configs[4] (gatk preset, up to 7 alleles)
+])
+def test_gpu_full_size_batches(ctx, shape, n_samples, n_sites, region_len):
+    """The other BASELINE shapes at the batch sizes bench.py runs (4e7-5e7 cells each): every output column bit-exact
+    against the oracle (all host threads), plus the size-independent column properties."""
+    import os
+    b = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len)
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    oracle_lib.genotype_batch(b, ref, threads=max(4, len(os.sched_getaffinity(0))))
+    ctx.genotype_batch(b, got)
+    ga, ra = got.arrays(), ref.arrays()
+    for k in ra:
+        assert np.array_equal(ga[k], ra[k]), k
+    gt = ga["gt"].reshape(-1, 2)
+    rnc = ga["rnc"].reshape(-1, 2)
+    assert (gt[:, 0] <= gt[:, 1]).all()
+    assert ((gt >= 0) == (rnc == ord("."))).all()
+    used = np.zeros(b.n_sites, dtype=np.uint32)
+    g = ga["gt"].reshape(b.n_sites, -1)
+    for a in range(int(g.max()) + 1):
+        used |= ((g == a).any(axis=1).astype(np.uint32) << a)
+    assert np.array_equal(used, ga["allele_used"])
+
+
 def test_gpu_narrow_download(ctx):
     """glx_download_narrow_on: int16 columns (BCF 16-bit sentinels) where a field fits, int32 where it does not; widened
     on the host they must equal the oracle's int32 columns exactly."""
