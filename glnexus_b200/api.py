@@ -107,6 +107,8 @@ def lib():
     L.glxh_free_text.restype = None
     L.glxh_preset_text.argtypes = [cp, C.POINTER(vp)]
     L.glxh_preset_text.restype = C.c_int
+    L.glxh_load_config.argtypes = [cp, cp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.glxh_load_config.restype = C.c_int
     L.glxh_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.glxh_batch_stats.restype = None
     # device ABI
@@ -478,6 +480,18 @@ def out_bytes_of(batch):
         return int(sum(a.nbytes for k, a in o.arrays().items() if k not in ("allele_used", "site_flags")))
     finally:
         o.close()
+
+
+def load_config(name=None, config_text=None, more_PL=False, squeeze=False, trim_uncalled_alleles=False):
+    """glnexus_cli's load_config: preset and/or config text, then the -P/-S/-a switches OR-ed in; returns the config text."""
+    t = C.c_void_p()
+    rc = lib().glxh_load_config(_b(name), _b(config_text), int(more_PL), int(squeeze), int(trim_uncalled_alleles), C.byref(t))
+    if rc != GLX_OK:
+        raise GlxError(rc, f"load_config({name})")
+    try:
+        return C.string_at(t.value).decode()
+    finally:
+        lib().glxh_free_text(t)
 
 
 def preset_text(name):

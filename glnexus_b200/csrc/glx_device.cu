@@ -437,11 +437,16 @@ struct glx_ctx {
     cudaStream_t aux = nullptr;                      // worklist kernels of chunk j run here while the tiled kernel of chunk j+1 runs
     cudaEvent_t chunk_ev[GLX_MAX_CHUNKS + 2] = {};   // tiled(chunk j) done / aux drained
     uint32_t* host_ovf_pool = nullptr;               // pinned overflow words of the narrow download, same scheme as below
-    unsigned long long* host_err_pool = nullptr;     // pinned error words handed to batches round-robin (allocating pinned
-    unsigned host_err_next = 0;                      // memory per batch would synchronise the device and break pipelining)
+    unsigned long long* host_err_pool = nullptr;     // 64 pinned error words, one per live batch (allocating pinned memory
+                                                     // per batch would synchronise the device and break pipelining)
     std::string err;
     int sm_count = 0;
     uint8_t width_hint[GLX_MAX_FIELDS];  // narrow download: 1 when every value of the field in the previous batch fitted int8, else 2
+    // kernel-path switches of the parity tests and ablations (glx_set_option); all 0 in production
+    struct Options {
+        int force_general = 0, force_dynamic_tiled = 0, no_resolve_sig = 0, no_fuse = 0, chunks = 1, profile_upload = 0;
+    } opt;
+    unsigned long long err_slots_used = 0;  // bit i: slot i of host_err_pool / host_ovf_pool belongs to a live batch
     // freed batch arenas are kept for the next batch of the same range stream (cudaMalloc/cudaFree of GB-sized
     // buffers costs milliseconds and would dominate a per-batch call)
     struct Cached {
@@ -541,6 +546,10 @@ struct glx_dev_batch {
     bool fused_variant = false;  // the tiled kernel finishes its own lone-variant cells
     std::vector<int32_t> tq_host;
     unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
+    int err_slot = -1;                       // slot of the context's pinned pools, or -1: host_err / host_overflow are the batch's own allocation
+    cudaStream_t last_stream = nullptr;      // stream of the last glx_launch (glx_check waits on it)
+    cudaStream_t dl_stream = nullptr;        // stream of the last download
+    cudaEvent_t up_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around the two upload-side kernels (option profile_upload)
     int16_t* narrow = nullptr;               // device int16 images of the integer fields + overflow words
     size_t narrow_bytes = 0;
     uint8_t narrow_width[GLX_MAX_FIELDS] = {};  // width each field was sent in by the last narrow download

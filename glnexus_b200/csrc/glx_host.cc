@@ -341,6 +341,30 @@ static void parse_numeric_vector(const std::string& txt, uint8_t type, std::vect
     }
 }
 
+Status reconcile_contigs(const VcfHeaderInfo& db, const VcfHeaderInfo& h, GvcfDataset& ds) {
+    const char* msg = "Incompatible gVCF. The reference contigs must match the database configuration exactly.";
+    if (db.n_declared_contigs && h.n_declared_contigs) {
+        if (db.n_declared_contigs != h.n_declared_contigs) return Status::Invalid(msg, ds.name);
+        for (size_t i = 0; i < h.n_declared_contigs; i++)
+            if (h.contigs[i].first != db.contigs[i].first || (h.contigs[i].second > 0 && db.contigs[i].second > 0 && h.contigs[i].second != db.contigs[i].second))
+                return Status::Invalid(msg, ds.name);
+    }
+    // rid of every record by contig NAME in the shared table (identity when the declared tables matched)
+    std::vector<int> remap(h.contigs.size(), -1);
+    bool identity = true;
+    for (size_t i = 0; i < h.contigs.size(); i++) {
+        for (size_t j = 0; j < db.contigs.size(); j++)
+            if (db.contigs[j].first == h.contigs[i].first) remap[i] = (int)j;
+        if (remap[i] != (int)i) identity = false;
+    }
+    if (identity) return Status::OK();
+    for (auto& r : ds.records) {
+        if (r.rid < 0 || r.rid >= (int)remap.size() || remap[r.rid] < 0) return Status::Invalid(msg, ds.name);
+        r.rid = remap[r.rid];
+    }
+    return Status::OK();
+}
+
 Status read_vcf_text(const std::string& text, const std::string& dataset_name, bool test_ingest_rules,
                      VcfHeaderInfo& hdr, GvcfDataset& ans) {
     ans = GvcfDataset();
@@ -358,6 +382,7 @@ Status read_vcf_text(const std::string& text, const std::string& dataset_name, b
                 long l = 0;
                 parse_int(len, l);
                 hdr.contigs.emplace_back(header_attr(line, "ID"), (size_t)l);
+                hdr.n_declared_contigs = hdr.contigs.size();
             }
             continue;
         }

@@ -181,6 +181,7 @@ struct GvcfDataset {
 
 struct VcfHeaderInfo {
     std::vector<std::pair<std::string, size_t>> contigs;
+    size_t n_declared_contigs = 0;  // contigs[0..n) come from ##contig lines; the rest were added on first appearance
     std::map<std::string, uint8_t> format_types, info_types;  // GLX_TYPE_*
 };
 
@@ -188,6 +189,11 @@ struct VcfHeaderInfo {
 // validate_bcf do at ingest in the reference's tests (test/utils.cc:75-84, src/BCF_utils.cc:54-66).
 Status read_vcf_text(const std::string& text, const std::string& dataset_name, bool test_ingest_rules,
                      VcfHeaderInfo& hdr, GvcfDataset& ans);
+
+// gvcf_compatible (src/BCF_utils.cc:9-33, :198): every gVCF must declare exactly the database's contigs, order included.
+// `db` is the shared contig table (the first dataset's). A dataset whose ##contig lines differ is rejected with
+// Status::Invalid; a dataset without ##contig lines has its records' rid remapped by contig name into `db`.
+Status reconcile_contigs(const VcfHeaderInfo& db, const VcfHeaderInfo& h, GvcfDataset& ds);
 
 Status sites_of_text(const std::string& txt, const std::vector<std::pair<std::string, size_t>>& contigs,
                      std::vector<unified_site>& ans);

@@ -64,11 +64,15 @@ int glxh_batch_from_text(const char* preset, const char* config_text, const char
         s = read_vcf_text(vcf_texts[i], dataset_names[i], test_ingest_rules != 0, h, datasets[i]);
         if (s.bad()) return fail(s, err, errlen);
         if (i == 0) hdr0 = h;  // VCFData::contigs serves the first dataset's contigs (test/utils.cc:128-131)
+        else {
+            s = reconcile_contigs(hdr0, h, datasets[i]);  // gvcf_compatible, src/BCF_utils.cc:9-33
+            if (s.bad()) return fail(s, err, errlen);
+        }
         for (const auto& p : h.format_types) hdr_all.format_types.insert(p);
         for (const auto& p : h.info_types) hdr_all.info_types.insert(p);
     }
     hdr_all.contigs = hdr0.contigs;
-    // every dataset must number contigs the same way for rid comparisons to be meaningful
+    hdr_all.n_declared_contigs = hdr0.n_declared_contigs;
     std::vector<unified_site> sites;
     s = sites_of_text(sites_text, hdr_all.contigs, sites);
     if (s.bad()) return fail(s, err, errlen);
@@ -179,7 +183,13 @@ int glxh_genotype_sites(const char* preset, const char* config_text, const char*
         VcfHeaderInfo h;
         s = read_vcf_text(vcf_texts[i], dataset_names[i], test_ingest_rules != 0, h, datasets[i]);
         if (s.bad()) return fail(s, err, errlen);
-        if (i == 0) hdr_all.contigs = h.contigs;
+        if (i == 0) {
+            hdr_all.contigs = h.contigs;
+            hdr_all.n_declared_contigs = h.n_declared_contigs;
+        } else {
+            s = reconcile_contigs(hdr_all, h, datasets[i]);  // gvcf_compatible, src/BCF_utils.cc:9-33
+            if (s.bad()) return fail(s, err, errlen);
+        }
         for (const auto& p : h.format_types) hdr_all.format_types.insert(p);
         for (const auto& p : h.info_types) hdr_all.info_types.insert(p);
     }
@@ -397,6 +407,28 @@ int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char
 }
 
 void glxh_free_text(char* text) { free(text); }
+
+int glxh_load_config(const char* name, const char* config_text, int more_PL, int squeeze, int trim_uncalled_alleles, char** text) {
+    if (!text) return GLX_E_INVALID;
+    *text = nullptr;
+    glx::genotyper_config cfg;
+    glx::Status s;
+    if (name && *name) {
+        s = glx::load_config_preset(name, cfg);
+        if (s.bad()) return s.c_code();
+    }
+    if (config_text && *config_text) {
+        s = glx::genotyper_config::of_text(config_text, cfg);
+        if (s.bad()) return s.c_code();
+    }
+    cfg.more_PL = cfg.more_PL || more_PL;  // src/cli_utils.cc:1206-1208
+    cfg.squeeze = cfg.squeeze || squeeze;
+    cfg.trim_uncalled_alleles = cfg.trim_uncalled_alleles || trim_uncalled_alleles;
+    std::string o = cfg.text();
+    *text = (char*)malloc(o.size() + 1);
+    memcpy(*text, o.c_str(), o.size() + 1);
+    return GLX_OK;
+}
 
 int glxh_preset_text(const char* name, char** text) {
     glx::genotyper_config cfg;

@@ -68,6 +68,12 @@ void glxh_free_text(char* text);
 /* genotyper_config preset -> text (for `--config NAME`); caller frees with glxh_free_text */
 int glxh_preset_text(const char* name, char** text);
 
+/* glnexus_cli's load_config (src/cli_utils.cc:1190-1265): the preset `name` (may be NULL) is loaded, `config_text` (may be
+ * NULL/empty) then replaces it wholesale as genotyper_config::of_yaml does, and the command-line switches -P/--more-PL,
+ * -S/--squeeze and -a/--trim-uncalled-alleles are OR-ed into the result (:1206-1208). *text = the resulting config in the
+ * line format (pass it as config_text to the calls above); caller frees with glxh_free_text. Unknown preset: GLX_E_NOT_FOUND. */
+int glxh_load_config(const char* name, const char* config_text, int more_PL, int squeeze, int trim_uncalled_alleles, char** text);
+
 /* The upper seam: Service::genotype_sites (include/service.h:67-70, src/service.cc:302-428) on the device path. Sites are
  * genotyped in contiguous range batches of `batch_sites` (0 = 4096), two batches in flight, rows written to `filename`
  * ("-" = stdout) in input order as pVCF text; *abort != 0 stops between batches with GLX_E_ABORTED; the first failing

@@ -13,6 +13,9 @@ KEYS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
+    ("FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak, dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("FBSP.TriageCompute.dram__read_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM read throughput % of peak"),
+    ("FBSP.TriageCompute.dram__write_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM write throughput % of peak"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "global store sectors"),
     ("l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "global store requests"),

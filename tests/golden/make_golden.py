@@ -165,6 +165,20 @@ def convert_revise_kats():
     return {"source": "test/genotyper.cc:25-172", "config_text": config_text(yaml.safe_load(cfg_yml)), "cases": cases}
 
 
+def convert_presets():
+    """The `glnexus_cli --config` presets (src/cli_utils.cc:465-1188): the YAML literal parsed with PyYAML; per preset the
+    genotyper_config half in the line format (config_text) and as plain values for a field-by-field check."""
+    src = open(os.path.join(REF, "src/cli_utils.cc")).read()
+    m = re.search(r'config_presets_yml = R"eof\(\n(.*?)\)eof"', src, re.S)
+    presets = yaml.safe_load(m.group(1))
+    out = {"source": "src/cli_utils.cc:465-1188", "presets": {}}
+    for name, node in presets.items():
+        g = node.get("genotyper_config", {}) or {}
+        out["presets"][name] = {"config_text": config_text(g), "genotyper_config": g}
+    assert len(out["presets"]) == 13, sorted(out["presets"])
+    return out
+
+
 def main():
     import glob
     n = 0
@@ -175,6 +189,7 @@ def main():
         json.dump(c, open(os.path.join(OUT, c["name"] + ".json"), "w"), indent=1)
         n += 1
     json.dump(convert_revise_kats(), open(os.path.join(OUT, "_revise_genotypes_kats.json"), "w"), indent=1)
+    json.dump(convert_presets(), open(os.path.join(OUT, "_presets.json"), "w"), indent=1)
     print(f"wrote {n} fixture cases + revise_genotypes KATs to {OUT}")
 
 
