@@ -148,6 +148,10 @@ def lib():
     L.glx_fused_count.restype = C.c_int
     L.glx_stream.argtypes = [vp]
     L.glx_stream.restype = vp
+    L.glx_set_option.argtypes = [vp, cp, C.c_int]
+    L.glx_set_option.restype = C.c_int
+    L.glx_upload_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.glx_upload_kernel_ms.restype = C.c_int
     _lib = L
     return L
 
@@ -374,6 +378,12 @@ class DeviceBatch:
         self.ctx._check(lib().glx_kernel_ms(self.ctx.handle, self.handle, ms))
         return tuple(ms)
 
+    def upload_kernel_ms(self):
+        """(glx_prepare_inputs_kernel, glx_block_hints_kernel) ms of this batch's upload (context option profile_upload)."""
+        ms = (C.c_float * 2)()
+        self.ctx._check(lib().glx_upload_kernel_ms(self.ctx.handle, self.handle, ms))
+        return tuple(ms)
+
     def work_count(self):
         n = C.c_uint64()
         self.ctx._check(lib().glx_work_count(self.ctx.handle, self.handle, C.byref(n)))
@@ -416,6 +426,17 @@ class Context:
         if rc != GLX_OK:
             msg = lib().glx_last_error(self.handle)
             raise GlxError(rc, msg.decode(errors="replace") if msg else "")
+
+    PATHS = {"sig": {}, "sig-unfused": {"no_fuse": 1, "no_resolve_sig": 1}, "dynamic": {"force_dynamic_tiled": 1}, "general": {"force_general": 1}}
+
+    def set_option(self, name, value):
+        """Kernel-path switch for batches uploaded afterwards (glx_set_option)."""
+        self._check(lib().glx_set_option(self.handle, _b(name), int(value)))
+
+    def select_path(self, path):
+        """Parity tests: 'sig' (default kernels), 'sig-unfused', 'dynamic' (dynamic tiled kernel), 'general' (general kernel alone)."""
+        for k in ("no_fuse", "no_resolve_sig", "force_dynamic_tiled", "force_general"):
+            self.set_option(k, self.PATHS[path].get(k, 0))
 
     def genotype_batch(self, batch, out):
         """Host buffers in, host buffers out (H2D + kernels + D2H)."""

@@ -520,6 +520,9 @@ int cuda_fail(glx_ctx* ctx, cudaError_t e, const char* what) {
 
 }  // namespace
 
+struct glx_dev_batch;
+static int take_err_slot(glx_ctx* ctx, glx_dev_batch* d);
+
 struct glx_dev_batch {
     DCfg cfg;
     DRecs R;
@@ -574,6 +577,26 @@ struct glx_dev_batch {
     uint2* block_hints = nullptr;      // [resolve blocks + 1] (sample, t_hi) of each block's first record (glx_block_hints_kernel)
     uint32_t n_datasets = 0;
 };
+
+// Pinned status / overflow words of a batch: a free slot of the context's pools, held until glx_free_batch; with 64
+// batches alive the batch gets its own allocation (slow: cudaHostAlloc synchronises the device).
+static int take_err_slot(glx_ctx* ctx, glx_dev_batch* d) {
+    if (d->host_err) return GLX_OK;
+    for (int i = 0; i < 64; i++)
+        if (!(ctx->err_slots_used >> i & 1)) {
+            ctx->err_slots_used |= 1ull << i;
+            d->err_slot = i;
+            d->host_err = ctx->host_err_pool + i;
+            d->host_overflow = ctx->host_ovf_pool + (size_t)i * GLX_MAX_FIELDS;
+            return GLX_OK;
+        }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 8 + GLX_MAX_FIELDS * 4, cudaHostAllocDefault) != cudaSuccess) return GLX_E_CUDA;
+    d->err_slot = -1;
+    d->host_err = static_cast<unsigned long long*>(p);
+    d->host_overflow = reinterpret_cast<uint32_t*>(static_cast<char*>(p) + 8);
+    return GLX_OK;
+}
 
 extern "C" {
 
@@ -645,6 +668,12 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
     if (ctx) cudaSetDevice(ctx->device);
     for (auto& ev : d->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : d->up_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (d->host_err) {
+        if (d->err_slot >= 0 && ctx) ctx->err_slots_used &= ~(1ull << d->err_slot);
+        else if (d->err_slot < 0) cudaFreeHost(d->host_err);
+    }
 
     if (ctx) {
         ctx->give(d->in_base, d->in_alloc);
@@ -708,12 +737,9 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     d->n_fields = cfg->n_fields;
     d->n_cols = cfg->n_cols;
     d->n_cells = S * N;
-    const char* fg = getenv("GLX_FORCE_GENERAL");
-    d->force_general = fg && *fg && *fg != '0';
-    if (const char* nc = getenv("GLX_CHUNKS")) {
-        const int v = atoi(nc);
-        if (v >= 1 && v <= GLX_MAX_CHUNKS) d->n_chunks = (uint32_t)v;
-    }
+    d->force_general = ctx->opt.force_general != 0;
+    // chunked launches share the context's aux stream and events: only for batches on the context's own stream
+    d->n_chunks = (stream_ && (cudaStream_t)stream_ != ctx->stream) ? 1u : (uint32_t)ctx->opt.chunks;
 
     const uint64_t Rn = recs->n_records, D = recs->n_datasets, C = cfg->n_cols;
     const uint64_t nA = sites->n_site_alleles, nU = sites->n_unif;
@@ -725,6 +751,12 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     };
     std::vector<Item> items;
     auto add = [&](const void* src, size_t bytes, auto** dst) { items.push_back(Item{src, bytes, (void**)dst}); };
+    // failure after work was queued: wait for it before the arenas return to the cache (another stream may take them)
+    auto bail = [&](cudaError_t err, const char* what) {
+        cudaStreamSynchronize(up);
+        glx_free_batch(ctx, d);
+        return cuda_fail(ctx, err, what);
+    };
     DRecs& R = d->R;
     DSites& Sx = d->S;
     memset(&R, 0, sizeof R);
@@ -788,31 +820,27 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     d->in_bytes = copied;  // host-to-device bytes of this upload
     d->in_alloc = total ? total : 256;
     cudaError_t e = ctx->take((void**)&d->in_base, d->in_alloc);
-    if (e != cudaSuccess) {
-        glx_free_batch(ctx, d);
-        return cuda_fail(ctx, e, "cudaMalloc(input arena)");
-    }
+    if (e != cudaSuccess) return bail(e, "cudaMalloc(input arena)");
     Arena ar{d->in_base, total, 0};
     for (auto& it : items) {
         char* p = ar.take<char>(it.bytes ? it.bytes : 1);
         *it.dst = p;
         if (it.bytes && it.src) {
             e = cudaMemcpyAsync(p, it.src, it.bytes, cudaMemcpyHostToDevice, up);
-            if (e != cudaSuccess) {
-                glx_free_batch(ctx, d);
-                return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
-            }
+            if (e != cudaSuccess) return bail(e, "cudaMemcpyAsync(H2D)");
         }
     }
     {
         const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(S + 1, nU + 1), D);
+        if (ctx->opt.profile_upload) {
+            for (int i = 0; i < 2; i++) cudaEventCreate(&d->up_ev[i]);
+            cudaEventRecord(d->up_ev[0], up);
+        }
         glx_prepare_inputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, up>>>(R, Sx, (uint32_t)D, nU, const_cast<uint8_t*>(R.flags), const_cast<int4*>(Sx.site_rows),
                                                                                const_cast<int4*>(Sx.unif_rows));
         e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            glx_free_batch(ctx, d);
-            return cuda_fail(ctx, e, "glx_prepare_inputs_kernel");
-        }
+        if (ctx->opt.profile_upload) cudaEventRecord(d->up_ev[1], up);
+        if (e != cudaSuccess) return bail(e, "glx_prepare_inputs_kernel");
     }
     // max output slots of any cell (scratch sizing of the general path)
     uint32_t max_slots = 1;
@@ -836,10 +864,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     d->out_bytes = ob;
     d->out_alloc = ob;
     e = ctx->take((void**)&d->out_base, ob);
-    if (e != cudaSuccess) {
-        glx_free_batch(ctx, d);
-        return cuda_fail(ctx, e, "cudaMalloc(output arena)");
-    }
+    if (e != cudaSuccess) return bail(e, "cudaMalloc(output arena)");
     Arena oa{d->out_base, ob, 0};
     memset(&d->O, 0, sizeof d->O);
     d->O.gt = oa.take<int8_t>(S * N * 2);
@@ -856,10 +881,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     d->general_blocks = (int)(want_blocks < cap ? (want_blocks ? want_blocks : 1) : cap);
     d->cnt_scratch_bytes = (size_t)d->general_blocks * threads * max_slots;
     e = ctx->take((void**)&d->cnt_scratch, d->cnt_scratch_bytes);
-    if (e != cudaSuccess) {
-        glx_free_batch(ctx, d);
-        return cuda_fail(ctx, e, "cudaMalloc(scratch)");
-    }
+    if (e != cudaSuccess) return bail(e, "cudaMalloc(scratch)");
     d->plan = make_fast_plan(d->cfg);
     if (d->force_general) d->plan.enabled = 0;
     {
@@ -867,18 +889,15 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         uint64_t modes, nums, nrvs;
         d->tiled_kernel = glx_cells_tiled_kernel;
         d->tiled_smem = (size_t)d->plan.n_rv * GLX_TILE_THREADS * 4;
-        const char* dyn = getenv("GLX_FORCE_DYNAMIC_TILED");
-        if (!(dyn && *dyn && *dyn != '0') && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
-            const char* nr_env = getenv("GLX_NO_RESOLVE_SIG");
-            const bool no_rsig = nr_env && *nr_env && *nr_env != '0';
-            const char* nf_env = getenv("GLX_NO_FUSE");
+        if (!ctx->opt.force_dynamic_tiled && sig_of_plan(d->cfg, d->plan, nf, modes, nums, nrvs)) {
+            const bool no_rsig = ctx->opt.no_resolve_sig != 0;
             // Fusing pays when the output the resident CTAs have in flight (~1,000 half-height tiles) is of the order of
             // L2: up to ~48 output bytes per cell (DeepVariant-style fields at mostly biallelic sites are 32; gatk-style
             // cohorts with up to 7 alleles are ~100 and measured 6 % slower fused). Cells of sites with more than 4
             // alleles are declined by the fused form and go to glx_cells_variant_kernel<8>.
             uint64_t out_bytes = d->n_cells * 4;
             for (uint32_t k = 0; k < cfg->n_fields; k++) out_bytes += d->fld_total[k] * 4;
-            const bool fuse = d->plan.vview && out_bytes <= d->n_cells * 48 && !(nf_env && *nf_env && *nf_env != '0');
+            const bool fuse = d->plan.vview && out_bytes <= d->n_cells * 48 && !ctx->opt.no_fuse;
             // A CTA finishes its lone-variant-record cells when its tile is done; their output sectors are still in L2
             // only if the tiles in flight are small enough, so variant-dense batches (>= 1 variant record per 100
             // cells) walk half-height tiles. Sparse ones keep the full height (fewer cursor set-ups per site).
@@ -911,10 +930,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         const size_t region_cells = (size_t)d->tile_sites * d->samples_per_cta;
         d->worklist_bytes = n_regions * region_cells * 8 + (n_regions + 64) * 4;
         e = ctx->take((void**)&d->worklist, d->worklist_bytes);
-        if (e != cudaSuccess) {
-            glx_free_batch(ctx, d);
-            return cuda_fail(ctx, e, "cudaMalloc(worklist)");
-        }
+        if (e != cudaSuccess) return bail(e, "cudaMalloc(worklist)");
         d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * region_cells);
         const size_t blob_part = ((Rn + 1) * blob_words(d->plan.n_rv) * 4 + 255) & ~(size_t)255;
         const size_t cur_part = (((size_t)d->n_site_tiles * N + 1) * 4 + 255) & ~(size_t)255;
@@ -922,10 +938,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         const size_t n_rblocks = (Rn + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS;
         d->blob_bytes = blob_part + cur_part + tq_part + (n_rblocks + 2) * sizeof(uint2);
         e = ctx->take((void**)&d->blobs, d->blob_bytes);
-        if (e != cudaSuccess) {
-            glx_free_batch(ctx, d);
-            return cuda_fail(ctx, e, "cudaMalloc(record blobs)");
-        }
+        if (e != cudaSuccess) return bail(e, "cudaMalloc(record blobs)");
         d->tile_cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part);
         d->tile_q = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part);
         std::vector<int32_t>& tq = d->tq_host;
@@ -936,24 +949,20 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
             tq[tile] = run;
         }
         e = cudaMemcpyAsync(d->tile_q, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice, up);
-        if (e != cudaSuccess) {
-            glx_free_batch(ctx, d);
-            return cuda_fail(ctx, e, "upload(tile_q)");
-        }
+        if (e != cudaSuccess) return bail(e, "upload(tile_q)");
         d->block_hints = reinterpret_cast<uint2*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part + tq_part);
+        if (ctx->opt.profile_upload) {
+            for (int i = 2; i < 4; i++) cudaEventCreate(&d->up_ev[i]);
+            cudaEventRecord(d->up_ev[2], up);
+        }
         glx_block_hints_kernel<<<(unsigned)((n_rblocks + 1 + 255) / 256), 256, 0, up>>>(d->R, (uint32_t)D, d->tile_q, d->n_site_tiles, d->block_hints, (uint32_t)n_rblocks);
         e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            glx_free_batch(ctx, d);
-            return cuda_fail(ctx, e, "glx_block_hints_kernel");
-        }
+        if (ctx->opt.profile_upload) cudaEventRecord(d->up_ev[3], up);
+        if (e != cudaSuccess) return bail(e, "glx_block_hints_kernel");
     }
     d->n_datasets = (uint32_t)D;
     e = sync ? cudaStreamSynchronize(up) : cudaSuccess;  // after a synchronous upload the caller's host arrays may be released
-    if (e != cudaSuccess) {
-        glx_free_batch(ctx, d);
-        return cuda_fail(ctx, e, "cudaStreamSynchronize(upload)");
-    }
+    if (e != cudaSuccess) return bail(e, "cudaStreamSynchronize(upload)");
     *out = d;
     return GLX_OK;
 }
@@ -962,6 +971,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
     if (!ctx || !d) return GLX_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    d->last_stream = st;
     const uint64_t S = d->n_sites;
     CU(cudaMemsetAsync(d->O.allele_used, 0, S * 4, st));
     CU(cudaMemsetAsync(d->O.site_flags, 0, S + 4, st));
@@ -986,7 +996,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
         // The tile grid is launched in chunks: the worklist kernels of chunk j (latency-bound gathers) run on the aux
         // stream while the tiled kernel of chunk j+1 (store-heavy) runs on the launching stream.
         const uint32_t n_regions = d->n_sample_blocks * d->n_site_tiles;
-        uint32_t n_chunks = d->n_chunks;
+        uint32_t n_chunks = st == ctx->stream ? d->n_chunks : 1u;  // the aux stream and its events belong to the context stream
         if (n_chunks > n_regions) n_chunks = n_regions;
         for (uint32_t j = 0; j < n_chunks; j++) {
             const uint32_t c0 = (uint32_t)((uint64_t)n_regions * j / n_chunks), c1 = (uint32_t)((uint64_t)n_regions * (j + 1) / n_chunks);
@@ -1052,8 +1062,9 @@ int glx_check(glx_ctx* ctx, glx_dev_batch* d) {
     if (!ctx || !d) return GLX_E_INVALID;
     CU(cudaSetDevice(ctx->device));
     unsigned long long w = 0;
-    CU(cudaMemcpyAsync(&w, d->O.error, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    cudaStream_t st = d->last_stream ? d->last_stream : ctx->stream;  // the stream the batch's kernels were launched on
+    CU(cudaMemcpyAsync(&w, d->O.error, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (w == ~0ull) return GLX_OK;
     const int code = (int)(w & 0xff);
     const unsigned long long site = (w >> 8) / (d->n_samples ? d->n_samples : 1);
@@ -1070,11 +1081,8 @@ int glx_download_on(glx_ctx* ctx, glx_dev_batch* d, glx_out* out, void* stream_,
     CU(cudaSetDevice(ctx->device));
     const uint64_t S = d->n_sites, N = d->n_samples;
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
-    if (!d->host_err) {
-        const unsigned slot = ctx->host_err_next++ & 63;
-        d->host_err = ctx->host_err_pool + slot;
-        d->host_overflow = ctx->host_ovf_pool + (size_t)slot * GLX_MAX_FIELDS;
-    }
+    if (take_err_slot(ctx, d) != GLX_OK) return cuda_fail(ctx, cudaErrorMemoryAllocation, "pinned status word");
+    d->dl_stream = st;
     if (S * N) {
         CU(cudaMemcpyAsync(out->gt, d->O.gt, S * N * 2, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->rnc, d->O.rnc, S * N * 2, cudaMemcpyDeviceToHost, st));
@@ -1100,13 +1108,8 @@ int glx_download_narrow_on(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out, void*
     CU(cudaSetDevice(ctx->device));
     const uint64_t S = d->n_sites, N = d->n_samples;
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
-    if (!d->host_err) {
-        const unsigned slot = ctx->host_err_next++ & 63;
-        d->host_err = ctx->host_err_pool + slot;
-        d->host_overflow = ctx->host_ovf_pool + (size_t)slot * GLX_MAX_FIELDS;
-    } else if (!d->host_overflow) {
-        d->host_overflow = ctx->host_ovf_pool + (size_t)(ctx->host_err_next++ & 63) * GLX_MAX_FIELDS;
-    }
+    if (take_err_slot(ctx, d) != GLX_OK) return cuda_fail(ctx, cudaErrorMemoryAllocation, "pinned status word");
+    d->dl_stream = st;
     if (!d->narrow) {
         size_t b = 256;
         for (uint32_t k = 0; k < d->n_fields; k++)
@@ -1152,6 +1155,7 @@ int glx_download_narrow_on(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out, void*
 int glx_narrow_finish(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out) {
     if (!ctx || !d || !out || !d->host_overflow) return GLX_E_INVALID;
     CU(cudaSetDevice(ctx->device));
+    bool refetched = false;
     for (uint32_t k = 0; k < d->n_fields; k++) {
         if (!field_is_narrowable(d, k)) {
             out->width[k] = 4;
@@ -1159,13 +1163,17 @@ int glx_narrow_finish(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out) {
         }
         const uint32_t fl = d->host_overflow[k];
         const int w = d->narrow_width[k] ? d->narrow_width[k] : 2;
-        if (fl & (w == 1 ? 2u : 1u)) {  // some value does not fit the width sent: fetch the int32 column (rare; synchronous)
+        if (fl & (w == 1 ? 2u : 1u)) {  // some value does not fit the width sent: fetch the int32 column (rare) on the batch's own stream
             out->width[k] = 4;
-            if (d->fld_total[k]) CU(cudaMemcpy(out->fld32[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost));
+            if (d->fld_total[k]) {
+                CU(cudaMemcpyAsync(out->fld32[k], d->O.fld[k], d->fld_total[k] * 4, cudaMemcpyDeviceToHost, d->dl_stream ? d->dl_stream : ctx->stream));
+                refetched = true;
+            }
         } else
             out->width[k] = (uint8_t)w;
         if (d->fld_total[k]) ctx->width_hint[k] = (fl & 2u) ? 2 : 1;  // what the next batch of this range stream is sent in
     }
+    if (refetched) CU(cudaStreamSynchronize(d->dl_stream ? d->dl_stream : ctx->stream));  // other streams keep running
     return GLX_OK;
 }
 
@@ -1202,6 +1210,38 @@ int glx_stream_sync(glx_ctx* ctx, void* s) {
 int glx_host_register(void* p, size_t bytes) { return (!p || !bytes || cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) ? GLX_OK : GLX_E_CUDA; }
 void glx_host_unregister(void* p) {
     if (p) cudaHostUnregister(p);
+}
+
+int glx_set_option(glx_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return GLX_E_INVALID;
+    const std::string n(name);
+    if (n == "force_general") ctx->opt.force_general = value;
+    else if (n == "force_dynamic_tiled") ctx->opt.force_dynamic_tiled = value;
+    else if (n == "no_resolve_sig") ctx->opt.no_resolve_sig = value;
+    else if (n == "no_fuse") ctx->opt.no_fuse = value;
+    else if (n == "profile_upload") ctx->opt.profile_upload = value;
+    else if (n == "chunks") {
+        if (value < 1 || value > GLX_MAX_CHUNKS) return GLX_E_INVALID;
+        ctx->opt.chunks = value;
+    } else {
+        ctx->err = "glx_set_option: unknown option " + n;
+        return GLX_E_INVALID;
+    }
+    return GLX_OK;
+}
+
+// durations of the two upload-side kernels of a batch uploaded with option profile_upload set
+int glx_upload_kernel_ms(glx_ctx* ctx, glx_dev_batch* d, float ms[2]) {
+    if (!ctx || !d || !ms || !d->up_ev[0]) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    ms[0] = ms[1] = 0.f;
+    CU(cudaEventSynchronize(d->up_ev[1]));
+    CU(cudaEventElapsedTime(&ms[0], d->up_ev[0], d->up_ev[1]));
+    if (d->up_ev[3]) {
+        CU(cudaEventSynchronize(d->up_ev[3]));
+        CU(cudaEventElapsedTime(&ms[1], d->up_ev[2], d->up_ev[3]));
+    }
+    return GLX_OK;
 }
 
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* d, int on) {

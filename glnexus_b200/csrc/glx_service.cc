@@ -115,12 +115,14 @@ Status genotype_sites(const genotyper_config& cfg, const std::vector<GvcfDataset
 
     // retire one slot: wait, check the batch's status, write its rows in order
     bool header_written = false;
-    auto retire = [&](Slot& sl) -> Status {
+    // `write` false: an earlier batch failed — wait and free only, no rows after the gap (the reference stops writing at
+    // the first failing site, src/service.cc:388-418)
+    auto retire = [&](Slot& sl, bool write = true) -> Status {
         if (!sl.dev) return Status::OK();
         Status rs = status_of(glx_stream_sync(ctx, sl.stream), ctx);
         if (rs.ok()) rs = status_of(glx_status(ctx, sl.dev), ctx);
         std::string rows;
-        if (rs.ok()) {
+        if (rs.ok() && write) {
             if (!header_written) {
                 vcf_header_text(*sl.batch, rows);
                 header_written = true;
@@ -186,7 +188,7 @@ Status genotype_sites(const genotyper_config& cfg, const std::vector<GvcfDataset
     // drain in submission order; the first error wins (src/service.cc:388-418)
     for (int k = 0; k < 2; k++) {
         Slot& sl = slots[(n_submitted + k) & 1];
-        Status rs = retire(sl);
+        Status rs = retire(sl, s.ok());
         if (s.ok() && rs.bad()) s = rs;
     }
     if (s.ok() && !header_written) {  // no sites: header only, like an empty pVCF

@@ -226,7 +226,7 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
                glx_dev_batch** dev);
 int glx_launch(glx_ctx* ctx, glx_dev_batch* dev, void* stream /* cudaStream_t or NULL = ctx stream */);
 int glx_download(glx_ctx* ctx, glx_dev_batch* dev, glx_out* out);
-int glx_check(glx_ctx* ctx, glx_dev_batch* dev); /* device-side error word -> status */
+int glx_check(glx_ctx* ctx, glx_dev_batch* dev); /* device-side error word -> status; waits for the batch's last glx_launch on the stream it was given */
 uint64_t glx_out_bytes(const glx_dev_batch* dev);
 uint64_t glx_in_bytes(const glx_dev_batch* dev);
 int glx_launch_count(const glx_dev_batch* dev); /* kernels per glx_launch */
@@ -257,6 +257,12 @@ void glx_host_unregister(void* p);
  * lone-variant closed form), closed-form worklist kernels (bands, variant, single-record), general worklist kernel}; glx_work_count = cells the tiled kernel put on its worklist, glx_fused_count = those of them it then
  * finished itself (lone-variant-record cells, when that closed form is fused into the tiled kernel). */
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);
+/* Kernel-path switches used by the parity tests and ablations (all 0 by default; they apply to batches uploaded afterwards):
+ * "force_general" (the general kernel alone computes every cell), "force_dynamic_tiled", "no_resolve_sig", "no_fuse",
+ * "chunks" (1..8), "profile_upload" (time the two upload-side kernels: glx_upload_kernel_ms). Unknown name: GLX_E_INVALID. */
+int glx_set_option(glx_ctx* ctx, const char* name, int value);
+/* {glx_prepare_inputs_kernel, glx_block_hints_kernel} ms of this batch's upload (option profile_upload) */
+int glx_upload_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[2]);
 int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[4]);
 int glx_work_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);
 int glx_fused_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);

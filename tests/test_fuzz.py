@@ -38,20 +38,10 @@ def test_fuzz_emu(built, chunk):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", ["sig", "sig-unfused", "dynamic", "general"])
-def test_fuzz_gpu(built, path, monkeypatch):
+def test_fuzz_gpu(built, path):
     from glnexus_b200 import Context, GlxError
-    monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
-    monkeypatch.delenv("GLX_FORCE_DYNAMIC_TILED", raising=False)
-    monkeypatch.delenv("GLX_NO_FUSE", raising=False)
-    monkeypatch.delenv("GLX_NO_RESOLVE_SIG", raising=False)
-    if path == "sig-unfused":  # signature tiled kernel + separate variant kernel + generic resolve kernel
-        monkeypatch.setenv("GLX_NO_FUSE", "1")
-        monkeypatch.setenv("GLX_NO_RESOLVE_SIG", "1")
-    if path == "general":
-        monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
-    elif path == "dynamic":
-        monkeypatch.setenv("GLX_FORCE_DYNAMIC_TILED", "1")
     ctx = Context(0)
+    ctx.select_path(path)
     n_ok = 0
     for seed in range(1000, 1240):
         b = fuzz_cases.build_batch(seed)

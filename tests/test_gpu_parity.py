@@ -48,20 +48,10 @@ def test_gpu_golden(ctx, name):
     ("c5", 600, 2000, 60000),
 ])
 @pytest.mark.parametrize("path", ["sig", "sig-unfused", "dynamic", "general"])
-def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, path, monkeypatch):
+def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, path):
     """Signature-specialised tiled kernel (default), the dynamic tiled kernel, and the general kernel alone must all
     equal the oracle on every output column."""
-    monkeypatch.delenv("GLX_FORCE_GENERAL", raising=False)
-    monkeypatch.delenv("GLX_FORCE_DYNAMIC_TILED", raising=False)
-    monkeypatch.delenv("GLX_NO_FUSE", raising=False)
-    monkeypatch.delenv("GLX_NO_RESOLVE_SIG", raising=False)
-    if path == "sig-unfused":  # signature tiled kernel + separate variant kernel + generic resolve kernel
-        monkeypatch.setenv("GLX_NO_FUSE", "1")
-        monkeypatch.setenv("GLX_NO_RESOLVE_SIG", "1")
-    if path == "general":
-        monkeypatch.setenv("GLX_FORCE_GENERAL", "1")
-    elif path == "dynamic":
-        monkeypatch.setenv("GLX_FORCE_DYNAMIC_TILED", "1")
+    ctx.select_path(path)  # glx_set_option switches; applies to batches uploaded from here on
     force_general = path == "general"
     b = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len)
     ref, got = b.alloc_out(), b.alloc_out(pinned=True)
@@ -72,6 +62,7 @@ def test_gpu_synth(ctx, shape, n_samples, n_sites, region_len, path, monkeypatch
     dev.download(got)
     assert dev.launch_count >= (1 if force_general else 5)  # resolve + per chunk: tiled, single-record, general
     dev.close()
+    ctx.select_path("sig")
     d = compare_outs(got, ref, b.n_fields)
     assert not d, "\n".join(d)
 
