@@ -5,7 +5,7 @@ GENCODE := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 $(GENCODE) -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-sign-compare
 CSRC := glnexus_b200/csrc
-HOST_SRCS := $(CSRC)/glx_host.cc $(CSRC)/glx_host_c.cc $(CSRC)/glx_presets.cc $(CSRC)/glx_synth.cc $(CSRC)/glx_service.cc
+HOST_SRCS := $(CSRC)/glx_host.cc $(CSRC)/glx_host_c.cc $(CSRC)/glx_presets.cc $(CSRC)/glx_synth.cc $(CSRC)/glx_service.cc $(CSRC)/glx_bcf_host.cc
 HOST_OBJS := $(HOST_SRCS:.cc=.o)
 
 all: glnexus_b200/libglx.so oracle/libglx_oracle.so
@@ -19,8 +19,8 @@ $(CSRC)/glx_device.o: $(CSRC)/glx_device.cu $(wildcard $(CSRC)/*.cuh) include/gl
 glnexus_b200/libglx.so: $(HOST_OBJS) $(CSRC)/glx_device.o
 	$(NVCC) -shared $(GENCODE) -o $@ $^ -cudart static -lpthread
 
-oracle/libglx_oracle.so: oracle/glx_oracle.cc include/glx.h
-	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -o $@ $< -lpthread
+oracle/libglx_oracle.so: oracle/glx_oracle.cc oracle/glx_bcf_oracle.cc include/glx.h
+	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -o $@ oracle/glx_oracle.cc oracle/glx_bcf_oracle.cc -lpthread
 
 clean:
 	rm -f $(CSRC)/*.o glnexus_b200/libglx.so oracle/libglx_oracle.so $(CSRC)/*.ptxas.log

@@ -107,6 +107,14 @@ def lib():
     L.glxh_free_text.restype = None
     L.glxh_preset_text.argtypes = [cp, C.POINTER(vp)]
     L.glxh_preset_text.restype = C.c_int
+    L.glxh_bcf_meta.argtypes = [vp]
+    L.glxh_bcf_meta.restype = vp
+    L.glxh_bcf_prologue.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.glxh_bcf_prologue.restype = C.c_int
+    L.glxh_bgzf_stored.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.glxh_bgzf_stored.restype = C.c_int
+    L.glxh_bgzf_eof.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.glxh_bgzf_eof.restype = C.c_int
     L.glxh_load_config.argtypes = [cp, cp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.glxh_load_config.restype = C.c_int
     L.glxh_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -148,6 +156,8 @@ def lib():
     L.glx_fused_count.restype = C.c_int
     L.glx_stream.argtypes = [vp]
     L.glx_stream.restype = vp
+    L.glx_selftest_diploid.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.glx_selftest_diploid.restype = C.c_int
     L.glx_set_option.argtypes = [vp, cp, C.c_int]
     L.glx_set_option.restype = C.c_int
     L.glx_upload_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
@@ -329,6 +339,22 @@ class Batch:
         finally:
             lib().glxh_free_text(t)
 
+    @property
+    def bcf_meta_ptr(self):
+        """glx_bcf_meta of the batch (per-site strings + header dictionary for the BCF record encoder)."""
+        return lib().glxh_bcf_meta(self.handle)
+
+    def bcf_prologue(self):
+        """Uncompressed bytes before the first record of a BCF file (magic, l_text, header text)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        rc = lib().glxh_bcf_prologue(self.handle, C.byref(p), C.byref(n))
+        if rc != GLX_OK:
+            raise GlxError(rc, "glxh_bcf_prologue")
+        try:
+            return C.string_at(p.value, n.value)
+        finally:
+            lib().glxh_free_text(p)
+
     def close(self):
         if self.handle:
             lib().glxh_batch_free(self.handle)
@@ -438,6 +464,13 @@ class Context:
         for k in ("no_fuse", "no_resolve_sig", "force_dynamic_tiled", "force_general"):
             self.set_option(k, self.PATHS[path].get(k, 0))
 
+    def selftest_diploid(self, n_allele):
+        """[(alleles_gt(i,j), alleles_gt(j,i))] in genotype order, from the device's index math."""
+        n = n_allele * (n_allele + 1) // 2
+        buf = (C.c_uint32 * n)()
+        self._check(lib().glx_selftest_diploid(self.handle, n_allele, buf))
+        return [(v & 0xffff, v >> 16) for v in buf]
+
     def genotype_batch(self, batch, out):
         """Host buffers in, host buffers out (H2D + kernels + D2H)."""
         self._check(lib().glx_genotype_batch(self.handle, batch.config_ptr, batch.records_ptr, batch.sites_ptr, out.ptr))
@@ -513,6 +546,27 @@ def load_config(name=None, config_text=None, more_PL=False, squeeze=False, trim_
         return C.string_at(t.value).decode()
     finally:
         lib().glxh_free_text(t)
+
+
+def bgzf_stored(data):
+    """data as BGZF blocks of stored deflate blocks (the header block of a BCF file)."""
+    p, n = C.c_void_p(), C.c_uint64()
+    rc = lib().glxh_bgzf_stored(data, len(data), C.byref(p), C.byref(n))
+    if rc != GLX_OK:
+        raise GlxError(rc, "glxh_bgzf_stored")
+    try:
+        return C.string_at(p.value, n.value)
+    finally:
+        lib().glxh_free_text(p)
+
+
+def bgzf_eof():
+    p, n = C.c_void_p(), C.c_uint64()
+    lib().glxh_bgzf_eof(C.byref(p), C.byref(n))
+    try:
+        return C.string_at(p.value, n.value)
+    finally:
+        lib().glxh_free_text(p)
 
 
 def preset_text(name):

@@ -426,6 +426,13 @@ __global__ void __launch_bounds__(256) glx_narrow_kernel(const int32_t* __restri
     if (any && (threadIdx.x & 31) == 0) atomicOr(overflow, any);
 }
 
+// Known-answer aid (tests): the device's diploid index math, out[j(j+1)/2 + i] = alleles_gt(i, j) | alleles_gt(j, i) << 16
+// for all i <= j < n (src/diploid.cc:12-50, test/diploid.cc:9-39).
+__global__ void glx_selftest_diploid_kernel(uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t j = blockIdx.x, i = threadIdx.x;
+    if (j < n && i <= j) out[j * (j + 1) / 2 + i] = (uint32_t)alleles_gt((int)i, (int)j) | (uint32_t)alleles_gt((int)j, (int)i) << 16;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1210,6 +1217,20 @@ int glx_stream_sync(glx_ctx* ctx, void* s) {
 int glx_host_register(void* p, size_t bytes) { return (!p || !bytes || cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) ? GLX_OK : GLX_E_CUDA; }
 void glx_host_unregister(void* p) {
     if (p) cudaHostUnregister(p);
+}
+
+int glx_selftest_diploid(glx_ctx* ctx, uint32_t n_allele, uint32_t* out) {
+    if (!ctx || !out || n_allele == 0 || n_allele > GLX_MAX_ALLELES) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_allele * (n_allele + 1) / 2;
+    uint32_t* dv = nullptr;
+    CU(cudaMalloc(&dv, n * 4));
+    glx_selftest_diploid_kernel<<<n_allele, GLX_MAX_ALLELES, 0, ctx->stream>>>(n_allele, dv);
+    cudaError_t e = cudaMemcpyAsync(out, dv, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dv);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "glx_selftest_diploid");
+    return GLX_OK;
 }
 
 int glx_set_option(glx_ctx* ctx, const char* name, int value) {

@@ -198,6 +198,17 @@ Status reconcile_contigs(const VcfHeaderInfo& db, const VcfHeaderInfo& h, GvcfDa
 Status sites_of_text(const std::string& txt, const std::vector<std::pair<std::string, size_t>>& contigs,
                      std::vector<unified_site>& ans);
 
+// Owner of the arrays behind glx_bcf_meta (include/glx.h): built from the batch by build_bcf_meta().
+struct BcfMetaStore {
+    bool built = false;
+    glx_bcf_meta meta{};
+    std::vector<int32_t> rid, norm_beg, norm_end, aq;
+    std::vector<float> qual;
+    std::vector<uint32_t> dna_off, norm_off, contig_off, filter_off;
+    std::vector<char> dna_pool, norm_pool, contig_pool, filter_pool;
+    std::vector<std::string> dict;  // BCF_DT_ID dictionary in header order (PASS first)
+};
+
 // ---------------------------------------------------------------------------------------------
 // Packed batch: owns every array the C ABI structs point at.
 // ---------------------------------------------------------------------------------------------
@@ -236,6 +247,7 @@ struct PackedBatch {
     std::vector<char> u_pool;
     std::vector<uint16_t> fld_cnt[GLX_MAX_FIELDS];
     std::vector<uint64_t> fld_off[GLX_MAX_FIELDS];
+    BcfMetaStore bcf;  // N1: what the BCF record encoder needs (lazily built; see build_bcf_meta)
     void rebind();  // refresh the raw pointers after the vectors are final
 };
 
@@ -260,6 +272,20 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
 Status assemble_vcf_text(const PackedBatch& b, const glx_out& out, std::string& vcf_text);
 void vcf_header_text(const PackedBatch& b, std::string& o);
 Status vcf_rows_text(const PackedBatch& b, const glx_out& out, std::string& o);
+
+// ---------------------------------------------------------------------------------------------
+// N1: BCF2 output (glx_bcf_host.cc). The records themselves are encoded on the device (glx_bcf.cu); the host owns the
+// header (src/service.cc:190-241), the BCF file prologue and the BGZF framing of those few bytes.
+// ---------------------------------------------------------------------------------------------
+const glx_bcf_meta& build_bcf_meta(PackedBatch& b);
+// pVCF header as htslib writes it into a BCF file: every FILTER/INFO/FORMAT/contig line carries its IDX
+std::string bcf_header_text(const PackedBatch& b);
+// "BCF\2\2", l_text, header text, NUL — the bytes before the first record (uncompressed)
+std::string bcf_file_prologue(const PackedBatch& b);
+uint32_t crc32_ieee(const uint8_t* p, size_t n, uint32_t crc = 0);
+// one BGZF block (RFC 1952 member with the BC extra field) holding p[0..n) as a stored deflate block; n <= 65280
+std::string bgzf_block_stored(const uint8_t* p, size_t n);
+std::string bgzf_eof_block();
 
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
 // [site_lo, site_hi) with every record its sites can touch.

@@ -1,4 +1,5 @@
 // glx_host_c.cc — C entry points of include/glx_host.h over the C++ host pipeline.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -407,6 +408,32 @@ int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char
 }
 
 void glxh_free_text(char* text) { free(text); }
+
+static int give_bytes(const std::string& o, char** bytes, uint64_t* n_bytes) {
+    if (!bytes || !n_bytes) return GLX_E_INVALID;
+    *bytes = (char*)malloc(o.size() + 1);
+    if (!*bytes) return GLX_E_FAILURE;
+    memcpy(*bytes, o.data(), o.size());
+    (*bytes)[o.size()] = 0;
+    *n_bytes = o.size();
+    return GLX_OK;
+}
+
+const glx_bcf_meta* glxh_bcf_meta(glxh_batch* b) { return b ? &glx::build_bcf_meta(b->b) : nullptr; }
+
+int glxh_bcf_prologue(const glxh_batch* b, char** bytes, uint64_t* n_bytes) {
+    if (!b) return GLX_E_INVALID;
+    return give_bytes(glx::bcf_file_prologue(b->b), bytes, n_bytes);
+}
+
+int glxh_bgzf_stored(const void* p, uint64_t n, char** bytes, uint64_t* n_bytes) {
+    if (!p && n) return GLX_E_INVALID;
+    std::string o;
+    for (uint64_t off = 0; off < n; off += 65280) o += glx::bgzf_block_stored(static_cast<const uint8_t*>(p) + off, (size_t)std::min<uint64_t>(65280, n - off));
+    return give_bytes(o, bytes, n_bytes);
+}
+
+int glxh_bgzf_eof(char** bytes, uint64_t* n_bytes) { return give_bytes(glx::bgzf_eof_block(), bytes, n_bytes); }
 
 int glxh_load_config(const char* name, const char* config_text, int more_PL, int squeeze, int trim_uncalled_alleles, char** text) {
     if (!text) return GLX_E_INVALID;

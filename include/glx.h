@@ -204,6 +204,33 @@ typedef struct glx_out16 {
     uint8_t* site_flags;
 } glx_out16;
 
+/* ---- N1: BCF2 record encoder (replaces the tail of genotype_site, src/genotyper.cc:869-1003, and the serialisation
+ * htslib does for it: bcf_update_* / bcf_trim_alleles / bcf1_sync, written out by bcf_write in src/service.cc:266-275) ----
+ * glx_bcf_meta is everything of a site's record that is not computed per cell, plus the header's dictionary indices
+ * (header lines of src/service.cc:190-241 in htslib's BCF_DT_ID order). Per-allele arrays are indexed like
+ * glx_sites.allele_off. Strings are not NUL-terminated; string i of a pool is [off[i], off[i+1]). */
+typedef struct glx_bcf_meta {
+    uint32_t n_sites, n_contigs, n_filters, _pad;
+    const int32_t* rid;         /* [S] CHROM (index among the ##contig lines) */
+    const float* qual;          /* [S] (float)unified_site::qual */
+    const uint32_t* dna_off;    /* [nA+1] unified_allele::dna */
+    const char* dna_pool;
+    const int32_t* norm_beg;    /* [nA] unified_allele::normalized.pos */
+    const int32_t* norm_end;
+    const uint32_t* norm_off;   /* [nA+1] unified_allele::normalized.dna */
+    const char* norm_pool;
+    const int32_t* aq;          /* [nA] unified_allele::quality (INFO AQ); INFO AF comes from glx_sites.allele_af */
+    const uint32_t* contig_off; /* [n_contigs+1] contig names (ID column) */
+    const char* contig_pool;
+    const uint32_t* filter_off; /* [n_filters+1] names of glx_records.filter_names (FT strings) */
+    const char* filter_pool;
+    uint64_t n_dna_pool, n_norm_pool, n_contig_pool, n_filter_pool;
+    int32_t id_AF, id_AQ, id_MONOALLELIC, id_GT, id_RNC; /* BCF_DT_ID dictionary indices */
+    int32_t id_field[GLX_MAX_FIELDS];
+    uint8_t field_vl[GLX_MAX_FIELDS]; /* header Number of the field's description line: 'A', 'R', 'G', else 0 (what
+                                         bcf_remove_allele_set looks at when it trims) */
+} glx_bcf_meta;
+
 typedef struct glx_ctx glx_ctx;
 
 /* lifecycle */
@@ -266,6 +293,9 @@ int glx_upload_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[2]);
 int glx_kernel_ms(glx_ctx* ctx, glx_dev_batch* dev, float ms[4]);
 int glx_work_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);
 int glx_fused_count(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n);
+/* Known-answer aid: out[j(j+1)/2 + i] = alleles_gt(i, j) | alleles_gt(j, i) << 16 for i <= j < n_allele, computed by the
+ * device's diploid index math (src/diploid.cc:12-50; test/diploid.cc:9-39). out holds n_allele(n_allele+1)/2 words. */
+int glx_selftest_diploid(glx_ctx* ctx, uint32_t n_allele, uint32_t* out);
 void* glx_stream(glx_ctx* ctx); /* the context's cudaStream_t */
 /* pinned host memory for caller-owned buffers (cudaHostAlloc) */
 void* glx_pinned_alloc(size_t bytes);

@@ -65,6 +65,16 @@ int glxh_out16_widen(const glxh_out16* o, glx_out* wide);
 int glxh_assemble_vcf(const glxh_batch* b, const glx_out* out, char** text, char* err, size_t errlen);
 void glxh_free_text(char* text);
 
+/* ---- N1: BCF2 output. The records are encoded (and BGZF-compressed) on the device, see glx_encode_bcf_on in glx.h; the host
+ * supplies the per-site strings / header dictionary (glx_bcf_meta) and writes the few bytes that are not records. ---- */
+const glx_bcf_meta* glxh_bcf_meta(glxh_batch* b);
+/* The uncompressed bytes that precede the first record of a BCF file: "BCF\2\2", l_text, header text, NUL; the header is
+ * what prepare_bcf_header builds (src/service.cc:190-241) with htslib's IDX attributes. Caller frees with glxh_free_text. */
+int glxh_bcf_prologue(const glxh_batch* b, char** bytes, uint64_t* n_bytes);
+/* BGZF framing for those bytes: p[0..n) as consecutive BGZF blocks holding stored deflate blocks; and the 28-byte EOF block. */
+int glxh_bgzf_stored(const void* p, uint64_t n, char** bytes, uint64_t* n_bytes);
+int glxh_bgzf_eof(char** bytes, uint64_t* n_bytes);
+
 /* genotyper_config preset -> text (for `--config NAME`); caller frees with glxh_free_text */
 int glxh_preset_text(const char* name, char** text);
 

@@ -25,6 +25,10 @@ def lib():
         L.glx_oracle_pl_to_gll.restype = C.c_double
         L.glx_oracle_revise_kat.argtypes = [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
         L.glx_oracle_revise_kat.restype = C.c_int
+        L.glx_oracle_bcf_records.argtypes = [vp, vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.glx_oracle_bcf_records.restype = C.c_int
+        L.glx_oracle_free.argtypes = [vp]
+        L.glx_oracle_free.restype = None
         _lib = L
     return _lib
 
@@ -50,3 +54,16 @@ def revise_kat(batch):
     if rc != 0:
         raise OracleError(rc, err.value.decode(errors="replace"))
     return a1.value, a2.value, gq.value
+
+
+def bcf_records(batch, out):
+    """(bytes, rec_off): the batch's BCF2 records, uncompressed, from the packed output columns (BCF oracle)."""
+    p, n = C.c_void_p(), C.c_uint64()
+    off = (C.c_uint64 * (batch.n_sites + 1))()
+    rc = lib().glx_oracle_bcf_records(batch.config_ptr, batch.sites_ptr, batch.bcf_meta_ptr, out.ptr, C.byref(p), C.byref(n), off)
+    if rc != 0:
+        raise OracleError(rc, "glx_oracle_bcf_records")
+    try:
+        return C.string_at(p.value, n.value), list(off)
+    finally:
+        lib().glx_oracle_free(p)

@@ -1,5 +1,8 @@
 """Parity tests proper: the CUDA path, called through the C ABI (glx_genotype_batch / glx_upload+launch+download),
 against the oracle — bit-exact on every output column — and against the reference's truth pVCFs."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -39,6 +42,45 @@ def test_gpu_golden(ctx, name):
         texts.append(batch.assemble_vcf(got))
     diffs = vcfcmp.compare(gu.merge_vcf_texts(texts), case["truth_vcf"], case["formats"], case["infos"])
     assert not diffs, "\n".join(diffs[:20])
+
+
+KATS = json.load(open(os.path.join(gu.GOLDEN, "_revise_genotypes_kats.json")))
+
+
+@pytest.mark.parametrize("path", ["sig", "dynamic", "general"])
+@pytest.mark.parametrize("i", range(len(KATS["cases"])))
+def test_gpu_revise_genotypes_kats(ctx, i, path):
+    """The 14 revise_genotypes known answers of test/genotyper.cc:110-172 through glx_genotype_batch on the GPU: every
+    column equals the oracle's genotype_site, and where the revised call is representable at the site GT and GQ equal the
+    reference's expected (allele1, allele2, GQ)."""
+    from glnexus_b200 import Batch
+    case = KATS["cases"][i]
+    b = Batch.from_text(case["sites_text"], [("A", case["vcf"])], config_text=KATS["config_text"])
+    assert oracle_lib.revise_kat(b) == (case["a1"], case["a2"], case["gq"])
+    ref, got = b.alloc_out(), b.alloc_out(pinned=True)
+    oracle_lib.genotype_batch(b, ref)
+    ctx.select_path(path)
+    try:
+        ctx.genotype_batch(b, got)
+    finally:
+        ctx.select_path("sig")
+    d = compare_outs(got, ref, b.n_fields)
+    assert not d, "\n".join(d)
+    if got.array("rnc").tobytes() == b"..":
+        assert sorted(int(x) for x in got.array("gt")[:2]) == sorted([case["a1"], case["a2"]])
+        assert int(got.array(0)[0]) == case["gq"]  # the KAT config lifts GQ only
+
+
+def test_gpu_diploid_kats(ctx):
+    """test/diploid.cc:9-39 on the device's index math, exhaustive for n_allele <= 32."""
+    for n_allele in range(1, 33):
+        got = ctx.selftest_diploid(n_allele)
+        want, x = [], 0
+        for j in range(n_allele):
+            for i in range(j + 1):
+                want.append((x, x))
+                x += 1
+        assert got == want, n_allele
 
 
 @pytest.mark.parametrize("shape,n_samples,n_sites,region_len", [
