@@ -16,7 +16,10 @@ $(CSRC)/%.o: $(CSRC)/%.cc $(CSRC)/glx_host.hpp include/glx.h include/glx_host.h
 $(CSRC)/glx_device.o: $(CSRC)/glx_device.cu $(wildcard $(CSRC)/*.cuh) include/glx.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(CSRC)/glx_device.ptxas.log || (cat $(CSRC)/glx_device.ptxas.log; false)
 
-glnexus_b200/libglx.so: $(HOST_OBJS) $(CSRC)/glx_device.o
+$(CSRC)/glx_bcf.o: $(CSRC)/glx_bcf.cu $(wildcard $(CSRC)/*.cuh) include/glx.h
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(CSRC)/glx_bcf.ptxas.log || (cat $(CSRC)/glx_bcf.ptxas.log; false)
+
+glnexus_b200/libglx.so: $(HOST_OBJS) $(CSRC)/glx_device.o $(CSRC)/glx_bcf.o
 	$(NVCC) -shared $(GENCODE) -o $@ $^ -cudart static -lpthread
 
 oracle/libglx_oracle.so: oracle/glx_oracle.cc oracle/glx_bcf_oracle.cc include/glx.h

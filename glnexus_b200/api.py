@@ -158,6 +158,22 @@ def lib():
     L.glx_stream.restype = vp
     L.glx_selftest_diploid.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.glx_selftest_diploid.restype = C.c_int
+    L.glx_bcf_attach.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.glx_bcf_attach.restype = C.c_int
+    L.glx_encode_bcf_on.argtypes = [vp, vp, C.c_int, vp]
+    L.glx_encode_bcf_on.restype = C.c_int
+    L.glx_bcf_length.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    L.glx_bcf_length.restype = C.c_int
+    L.glx_download_bcf_on.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_int]
+    L.glx_download_bcf_on.restype = C.c_int
+    L.glx_bcf_record_offsets.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.glx_bcf_record_offsets.restype = C.c_int
+    L.glx_bcf_bound.argtypes = [vp]
+    L.glx_bcf_bound.restype = C.c_uint64
+    L.glx_pinned_alloc.argtypes = [sz]
+    L.glx_pinned_alloc.restype = vp
+    L.glx_pinned_free.argtypes = [vp]
+    L.glx_pinned_free.restype = None
     L.glx_set_option.argtypes = [vp, cp, C.c_int]
     L.glx_set_option.restype = C.c_int
     L.glx_upload_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
@@ -246,6 +262,30 @@ class Out16:
         if self.handle:
             lib().glxh_out16_free(self.handle)
             self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host bytes (cudaHostAlloc) for asynchronous downloads."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().glx_pinned_alloc(max(16, self.nbytes))
+        if not self.ptr:
+            raise MemoryError("glx_pinned_alloc")
+
+    def bytes(self, n):
+        return C.string_at(self.ptr, n)
+
+    def close(self):
+        if self.ptr:
+            lib().glx_pinned_free(self.ptr)
+            self.ptr = None
 
     def __del__(self):
         try:
@@ -393,6 +433,40 @@ class DeviceBatch:
     def status(self):
         """Error word of a batch whose asynchronous download has been synchronised."""
         self.ctx._check(lib().glx_status(self.ctx.handle, self.handle))
+
+    # ---- N1: BCF2 records / BGZF blocks encoded on the device ----
+    def bcf_attach(self, batch, stream=None):
+        self.ctx._check(lib().glx_bcf_attach(self.ctx.handle, self.handle, batch.sites_ptr, batch.bcf_meta_ptr, batch.config_ptr, C.c_void_p(stream or 0)))
+        self._n_sites = batch.n_sites
+
+    def encode_bcf(self, mode=0, stream=None):
+        """mode 0: uncompressed record stream; mode 1: BGZF blocks."""
+        self.ctx._check(lib().glx_encode_bcf_on(self.ctx.handle, self.handle, int(mode), C.c_void_p(stream or 0)))
+
+    def bcf_length(self):
+        """(encoded bytes, uncompressed stream bytes, BGZF blocks); waits for the encoder's size event."""
+        n, r, b = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        self.ctx._check(lib().glx_bcf_length(self.ctx.handle, self.handle, C.byref(n), C.byref(r), C.byref(b)))
+        return n.value, r.value, b.value
+
+    @property
+    def bcf_bound(self):
+        return lib().glx_bcf_bound(self.handle)
+
+    def download_bcf(self, host_buf=None, stream=None, sync=True):
+        """The encoded bytes. host_buf: a PinnedBuffer to receive them (asynchronously when sync is False); default: a fresh bytes object."""
+        if host_buf is None:
+            n, _, _ = self.bcf_length()
+            tmp = C.create_string_buffer(max(1, n))
+            self.ctx._check(lib().glx_download_bcf_on(self.ctx.handle, self.handle, tmp, n, C.c_void_p(stream or 0), 1))
+            return tmp.raw[:n]
+        self.ctx._check(lib().glx_download_bcf_on(self.ctx.handle, self.handle, C.c_void_p(host_buf.ptr), host_buf.nbytes, C.c_void_p(stream or 0), 1 if sync else 0))
+        return None
+
+    def bcf_record_offsets(self):
+        off = (C.c_uint64 * (self._n_sites + 1))()
+        self.ctx._check(lib().glx_bcf_record_offsets(self.ctx.handle, self.handle, off))
+        return list(off)
 
     def set_profile(self, on=True):
         self.ctx._check(lib().glx_set_profile(self.ctx.handle, self.handle, 1 if on else 0))

@@ -1,0 +1,600 @@
+// glx_bcf.cuh — BCF2 record encoder on the device: the packed FORMAT columns of a batch become the
+// finished, byte-packed BCF records the reference's writer thread would emit (src/genotyper.cc:869-1003 + htslib's
+// bcf_update_* / bcf_trim_alleles / bcf1_sync; rules restated in oracle/glx_bcf_oracle.cc, which pins them).
+//
+// Stages (kernels in glx_bcf.cu; every stage is a block-level function of (tid, nt) here so that the host build of this
+// header — tests/emu — can run it with one virtual thread and diff it against the oracle):
+//   scan    per (site, field): min / max of the values that survive allele trimming  -> integer width per SITE (bcf_enc_vint)
+//   layout  per site: surviving alleles, widths, FORMAT block offsets, l_shared / l_indiv, record length
+//   offsets exclusive scans: record offsets in the stream, offsets of the header+shared bytes in a side pool
+//   headers per site: l_shared, l_indiv and the shared part (ID, alleles, FILTER, INFO AF/AQ) into the side pool
+//   span    per 65,280-byte span of the output stream (= the payload of one BGZF block): gather the span in shared
+//           memory — header bytes, FORMAT block headers, typed per-sample vectors converted from the int32 columns —
+//           then hand it to the writer (raw: one bulk store; BGZF: deflate + CRC in glx_bgzf.cuh)
+#pragma once
+#include "glx_dev_types.cuh"
+
+namespace glxd {
+
+#define GLX_BCF_SPAN 65280u  // uncompressed bytes per span / BGZF block (htslib's BGZF_BLOCK_SIZE 0xff00)
+#define GLX_BCF_MAXBLK (GLX_MAX_FIELDS + 2)
+#define GLX_BCF_G_MAX (GLX_MAX_ALLELES * (GLX_MAX_ALLELES + 1) / 2)
+#define GLX_BCF_HDR_MAX 12  // typed key (<= 5 bytes) + typed count descriptor (<= 6 bytes)
+
+#if defined(__CUDA_ARCH__)
+#define GLX_BLOCK_SYNC() __syncthreads()
+#else
+#define GLX_BLOCK_SYNC() ((void)0)
+#endif
+
+#define GLXB_MISSING ((int32_t)0x80000000)  // bcf_int32_missing
+#define GLXB_VEND ((int32_t)0x80000001)     // bcf_int32_vector_end
+enum { BCF_BT_NULL = 0, BCF_BT_INT8 = 1, BCF_BT_INT16 = 2, BCF_BT_INT32 = 3, BCF_BT_FLOAT = 5, BCF_BT_CHAR = 7 };
+
+struct DBcfMeta {
+    const int32_t* rid;
+    const float* qual;
+    const uint32_t* dna_off;
+    const char* dna_pool;
+    const int32_t *norm_beg, *norm_end;
+    const uint32_t* norm_off;
+    const char* norm_pool;
+    const int32_t* aq;
+    const float* af;
+    const uint32_t* contig_off;
+    const char* contig_pool;
+    const uint32_t* filter_off;
+    const char* filter_pool;
+    uint32_t n_filters;
+    int32_t id_AF, id_AQ, id_MONO, id_GT, id_RNC;
+    int32_t id_field[GLX_MAX_FIELDS];
+};
+
+struct BcfSitePlan {
+    uint32_t keep_mask;  // surviving unified alleles (bit 0 = REF); 0 = the site has no record
+    uint32_t l_shared, l_indiv;
+    uint8_t n_keep, trimmed, n_blk, _pad;
+    uint32_t blk_off[GLX_BCF_MAXBLK];  // FORMAT blocks in record order (GT, lifted fields, RNC): offset of the block's key byte in indiv
+    uint16_t blk_cnt[GLX_BCF_MAXBLK];  // values (chars) per sample after trimming
+    uint8_t blk_width[GLX_BCF_MAXBLK];
+    uint8_t blk_hdr_len[GLX_BCF_MAXBLK];
+    uint8_t blk_hdr[GLX_BCF_MAXBLK][GLX_BCF_HDR_MAX];  // typed key + typed descriptor
+};
+
+struct BcfEnc {
+    uint32_t n_sites, n_samples, n_fields;
+    uint8_t trim, _pad[3];
+    uint8_t fkind[GLX_MAX_FIELDS], ftype[GLX_MAX_FIELDS], fvl[GLX_MAX_FIELDS];
+    const int32_t* beg;
+    const uint8_t *n_allele, *monoallelic;
+    const uint32_t* allele_off;
+    const uint16_t* fld_cnt[GLX_MAX_FIELDS];
+    const uint64_t* fld_off[GLX_MAX_FIELDS];
+    const int8_t* gt;
+    const uint8_t* rnc;
+    const int32_t* fld[GLX_MAX_FIELDS];
+    const uint32_t* allele_used;
+    DBcfMeta m;
+    int32_t* mm;  // [S][n_fields][2]: min, max over surviving non-sentinel values (string fields: [1] = longest string)
+    BcfSitePlan* plan;
+    unsigned long long* rec_off;  // [S+1] record lengths, then their exclusive scan
+    unsigned long long* hdr_off;  // [S+1] likewise for 8 + l_shared
+    uint8_t* hdr_pool;
+};
+
+// host side: the scalar part of BcfEnc from the ABI structs (pointers are bound by the caller)
+inline void bcf_enc_scalars(BcfEnc& E, const glx_config& c, const glx_bcf_meta& m, uint32_t n_sites, uint32_t n_samples) {
+    E.n_sites = n_sites;
+    E.n_samples = n_samples;
+    E.n_fields = c.n_fields;
+    E.trim = c.trim_uncalled_alleles;
+    for (uint32_t k = 0; k < c.n_fields; k++) {
+        E.fkind[k] = c.fields[k].kind;
+        E.ftype[k] = c.fields[k].type;
+        E.fvl[k] = m.field_vl[k];
+        E.m.id_field[k] = m.id_field[k];
+    }
+    E.m.n_filters = m.n_filters;
+    E.m.id_AF = m.id_AF;
+    E.m.id_AQ = m.id_AQ;
+    E.m.id_MONO = m.id_MONOALLELIC;
+    E.m.id_GT = m.id_GT;
+    E.m.id_RNC = m.id_RNC;
+}
+
+// ---- small helpers ----
+__host__ __device__ __forceinline__ uint32_t bcf_keep_mask(const BcfEnc& E, uint32_t s) {
+    const uint32_t A = E.n_allele[s];
+    const uint32_t all = A >= 32 ? 0xffffffffu : (1u << A) - 1u;
+    return E.trim ? ((E.allele_used[s] | 1u) & all) : all;
+}
+__host__ __device__ __forceinline__ int bcf_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+// genotype index j -> (ia <= ib), src/diploid.cc:28-50
+__host__ __device__ __forceinline__ void bcf_gt_alleles(uint32_t j, uint32_t& ia, uint32_t& ib) {
+    uint32_t b = (uint32_t)((sqrtf(8.0f * (float)j + 1.0f) - 1.0f) * 0.5f);
+    while ((b + 1) * (b + 2) / 2 <= j) b++;
+    while (b * (b + 1) / 2 > j) b--;
+    ib = b;
+    ia = j - b * (b + 1) / 2;
+}
+__host__ __device__ __forceinline__ bool bcf_is_arg(uint8_t vl) { return vl == 'A' || vl == 'R' || vl == 'G'; }
+// does source slot j of a Number=vl field survive the trim to keep mask km?
+__host__ __device__ __forceinline__ bool bcf_slot_kept(uint8_t vl, uint32_t j, uint32_t km) {
+    if (vl == 'R') return j < 32 && (km >> j & 1u);
+    if (vl == 'A') return j + 1 < 32 && (km >> (j + 1) & 1u);
+    uint32_t ia, ib;
+    bcf_gt_alleles(j, ia, ib);
+    return ib < 32 && (km >> ia & 1u) && (km >> ib & 1u);
+}
+// its slot after the trim
+__host__ __device__ __forceinline__ uint32_t bcf_slot_new(uint8_t vl, uint32_t j, uint32_t km) {
+    if (vl == 'R') return (uint32_t)bcf_popc(km & ((1u << j) - 1u));
+    if (vl == 'A') return (uint32_t)bcf_popc(km & ((1u << (j + 1)) - 1u)) - 1u;
+    uint32_t ia, ib;
+    bcf_gt_alleles(j, ia, ib);
+    const uint32_t ra = (uint32_t)bcf_popc(km & ((1u << ia) - 1u)), rb = (uint32_t)bcf_popc(km & ((1u << ib) - 1u));
+    return rb * (rb + 1) / 2 + ra;
+}
+__host__ __device__ __forceinline__ uint32_t bcf_count_new(uint8_t vl, uint32_t cnt, uint32_t n_keep, bool trimmed) {
+    if (!trimmed || !bcf_is_arg(vl)) return cnt;
+    return vl == 'R' ? n_keep : (vl == 'A' ? n_keep - 1 : n_keep * (n_keep + 1) / 2);
+}
+// length of the FT string of a filter mask ("." when empty; names joined by ';')
+__host__ __device__ __forceinline__ uint32_t bcf_ft_len(const DBcfMeta& m, uint32_t mask) {
+    if (!mask) return 1;
+    uint32_t n = 0, k = 0;
+    for (uint32_t i = 0; i < m.n_filters; i++)
+        if (mask >> i & 1u) {
+            n += m.filter_off[i + 1] - m.filter_off[i];
+            k++;
+        }
+    return n ? n + k - 1 : 1;
+}
+__host__ __device__ __forceinline__ uint8_t bcf_ft_char(const DBcfMeta& m, uint32_t mask, uint32_t ci) {
+    if (!mask) return ci == 0 ? (uint8_t)'.' : 0;
+    uint32_t pos = 0;
+    bool first = true;
+    for (uint32_t i = 0; i < m.n_filters; i++)
+        if (mask >> i & 1u) {
+            if (!first) {
+                if (ci == pos) return (uint8_t)';';
+                pos++;
+            }
+            first = false;
+            const uint32_t len = m.filter_off[i + 1] - m.filter_off[i];
+            if (ci < pos + len) return (uint8_t)m.filter_pool[m.filter_off[i] + (ci - pos)];
+            pos += len;
+        }
+    if (pos == 0) return ci == 0 ? (uint8_t)'.' : 0;  // mask bits beyond the dictionary
+    return 0;
+}
+
+// ---- typed-value encoders over a byte sink (count or write) ----
+struct BcfCount {
+    uint32_t n = 0;
+    __host__ __device__ void put(uint32_t) { n++; }
+};
+struct BcfWrite {
+    uint8_t* p;
+    __host__ __device__ void put(uint32_t b) { *p++ = (uint8_t)b; }
+};
+template <class Sink>
+__host__ __device__ inline void bcf_put32(Sink& o, uint32_t v) {
+    o.put(v & 0xff);
+    o.put(v >> 8 & 0xff);
+    o.put(v >> 16 & 0xff);
+    o.put(v >> 24);
+}
+template <class Sink>
+__host__ __device__ inline void bcf_enc_size(Sink& o, uint32_t size, int type) {
+    if (size >= 15) {
+        o.put(15u << 4 | (uint32_t)type);
+        if (size >= 128) {
+            if (size >= 32768) {
+                o.put(1u << 4 | BCF_BT_INT32);
+                bcf_put32(o, size);
+            } else {
+                o.put(1u << 4 | BCF_BT_INT16);
+                o.put(size & 0xff);
+                o.put(size >> 8);
+            }
+        } else {
+            o.put(1u << 4 | BCF_BT_INT8);
+            o.put(size);
+        }
+    } else
+        o.put(size << 4 | (uint32_t)type);
+}
+__host__ __device__ __forceinline__ int bcf_int_width(int32_t mn, int32_t mx) {  // bcf_enc_vint's type choice
+    if (mx <= 127 && mn >= -120) return 1;
+    if (mx <= 32767 && mn >= -32760) return 2;
+    return 4;
+}
+template <class Sink>
+__host__ __device__ inline void bcf_enc_int1(Sink& o, int32_t x) {
+    if (x == GLXB_VEND || x == GLXB_MISSING) {
+        bcf_enc_size(o, 1, BCF_BT_INT8);
+        o.put(x == GLXB_VEND ? 0x81u : 0x80u);
+        return;
+    }
+    const int w = bcf_int_width(x, x);
+    bcf_enc_size(o, 1, w == 1 ? BCF_BT_INT8 : (w == 2 ? BCF_BT_INT16 : BCF_BT_INT32));
+    for (int i = 0; i < w; i++) o.put((uint32_t)x >> (8 * i) & 0xff);
+}
+template <class Sink>
+__host__ __device__ inline void bcf_enc_pool_str(Sink& o, const char* pool, uint32_t lo, uint32_t hi) {
+    bcf_enc_size(o, hi - lo, BCF_BT_CHAR);
+    for (uint32_t i = lo; i < hi; i++) o.put((uint8_t)pool[i]);
+}
+template <class Sink>
+__host__ __device__ inline void bcf_put_decimal(Sink& o, uint32_t v) {
+    char d[10];
+    int n = 0;
+    do {
+        d[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) o.put((uint8_t)d[--n]);
+}
+__host__ __device__ __forceinline__ uint32_t bcf_decimal_len(uint32_t v) {
+    uint32_t n = 1;
+    while (v >= 10) {
+        v /= 10;
+        n++;
+    }
+    return n;
+}
+
+// The shared part of site s (src/genotyper.cc:869-912,950-993 through bcf1_sync): fixed fields, ID, alleles, FILTER, INFO.
+template <class Sink>
+__host__ __device__ inline void bcf_emit_shared(const BcfEnc& E, uint32_t s, uint32_t km, uint32_t n_fmt, Sink& o) {
+    const DBcfMeta& m = E.m;
+    const uint32_t A = E.n_allele[s], a0 = E.allele_off[s];
+    const uint32_t n_keep = (uint32_t)bcf_popc(km);
+    const int32_t beg = E.beg[s];
+    bool output_af = true, any_aq = false;
+    for (uint32_t a = 1; a < A; a++) {
+        const float f = m.af[a0 + a];
+        if (f != f) output_af = false;
+        if (m.aq[a0 + a]) any_aq = true;
+    }
+    bcf_put32(o, (uint32_t)m.rid[s]);
+    bcf_put32(o, (uint32_t)beg);
+    bcf_put32(o, m.dna_off[a0 + 1] - m.dna_off[a0]);  // rlen = strlen(REF)
+    uint32_t qb;
+    {
+        const float q = m.qual[s];
+        memcpy(&qb, &q, 4);
+    }
+    bcf_put32(o, qb);
+    bcf_put32(o, n_keep << 16 | ((output_af ? 1u : 0u) + (any_aq ? 1u : 0u)));
+    bcf_put32(o, n_fmt << 24 | E.n_samples);
+    // ID: chrom_pos_ref_alt of each surviving ALT's normalized form, ';'-joined
+    const uint32_t c_lo = m.contig_off[m.rid[s]], c_hi = m.contig_off[m.rid[s] + 1];
+    uint32_t id_len = 0;
+    for (uint32_t a = 1; a < A; a++)
+        if (km >> a & 1u) {
+            const uint32_t nb = (uint32_t)m.norm_beg[a0 + a], ne = (uint32_t)m.norm_end[a0 + a];
+            id_len += (id_len ? 1u : 0u) + (c_hi - c_lo) + 1 + bcf_decimal_len(nb + 1) + 1 + (ne - nb) + 1 + (m.norm_off[a0 + a + 1] - m.norm_off[a0 + a]);
+        }
+    bcf_enc_size(o, id_len, BCF_BT_CHAR);
+    bool first = true;
+    for (uint32_t a = 1; a < A; a++)
+        if (km >> a & 1u) {
+            const uint32_t nb = (uint32_t)m.norm_beg[a0 + a], ne = (uint32_t)m.norm_end[a0 + a];
+            if (!first) o.put(';');
+            first = false;
+            for (uint32_t i = c_lo; i < c_hi; i++) o.put((uint8_t)m.contig_pool[i]);
+            o.put('_');
+            bcf_put_decimal(o, nb + 1);
+            o.put('_');
+            const uint32_t r0 = m.dna_off[a0] + (nb - (uint32_t)beg);
+            for (uint32_t i = 0; i < ne - nb; i++) o.put((uint8_t)m.dna_pool[r0 + i]);
+            o.put('_');
+            for (uint32_t i = m.norm_off[a0 + a]; i < m.norm_off[a0 + a + 1]; i++) o.put((uint8_t)m.norm_pool[i]);
+        }
+    for (uint32_t a = 0; a < A; a++)
+        if (km >> a & 1u) bcf_enc_pool_str(o, m.dna_pool, m.dna_off[a0 + a], m.dna_off[a0 + a + 1]);
+    if (E.monoallelic[s]) bcf_enc_int1(o, m.id_MONO);  // FILTER: bcf_enc_vint of one id
+    else bcf_enc_size(o, 0, BCF_BT_NULL);
+    if (output_af) {
+        bcf_enc_int1(o, m.id_AF);
+        bcf_enc_size(o, n_keep - 1, BCF_BT_FLOAT);
+        for (uint32_t a = 1; a < A; a++)
+            if (km >> a & 1u) {
+                uint32_t b;
+                const float f = m.af[a0 + a];
+                memcpy(&b, &f, 4);
+                bcf_put32(o, b);
+            }
+    }
+    if (any_aq) {
+        bcf_enc_int1(o, m.id_AQ);
+        if (n_keep - 1 == 1) {
+            for (uint32_t a = 1; a < A; a++)
+                if (km >> a & 1u) bcf_enc_int1(o, m.aq[a0 + a]);
+        } else {
+            int32_t mn = INT32_MAX, mx = INT32_MIN + 1;
+            for (uint32_t a = 1; a < A; a++)
+                if (km >> a & 1u) {
+                    const int32_t v = m.aq[a0 + a];
+                    if (v == GLXB_MISSING || v == GLXB_VEND) continue;
+                    mn = v < mn ? v : mn;
+                    mx = v > mx ? v : mx;
+                }
+            const int w = bcf_int_width(mn, mx);
+            bcf_enc_size(o, n_keep - 1, w == 1 ? BCF_BT_INT8 : (w == 2 ? BCF_BT_INT16 : BCF_BT_INT32));
+            for (uint32_t a = 1; a < A; a++)
+                if (km >> a & 1u) {
+                    const int32_t v = m.aq[a0 + a];
+                    uint32_t x = (uint32_t)v;
+                    if (w < 4 && v == GLXB_MISSING) x = w == 1 ? 0x80u : 0x8000u;
+                    if (w < 4 && v == GLXB_VEND) x = w == 1 ? 0x81u : 0x8001u;
+                    for (int i = 0; i < w; i++) o.put(x >> (8 * i) & 0xff);
+                }
+        }
+    }
+}
+
+// ---- stage: scan. One block takes samples [n0, n1) of site s. s_mm = [n_fields][2] block-shared ints. ----
+__host__ __device__ inline void bcf_scan_init(const BcfEnc& E, int32_t* s_mm, uint32_t tid, uint32_t nt) {
+    for (uint32_t i = tid; i < E.n_fields; i += nt) {
+        s_mm[2 * i] = INT32_MAX;
+        s_mm[2 * i + 1] = INT32_MIN + 1;
+    }
+}
+__host__ __device__ __forceinline__ void bcf_mm_merge(int32_t* dst, int32_t mn, int32_t mx) {
+#if defined(__CUDA_ARCH__)
+    if (mn != INT32_MAX) atomicMin(dst, mn);
+    if (mx != INT32_MIN + 1) atomicMax(dst + 1, mx);
+#else
+    if (mn < dst[0]) dst[0] = mn;
+    if (mx > dst[1]) dst[1] = mx;
+#endif
+}
+__host__ __device__ inline void bcf_scan_accum(const BcfEnc& E, uint32_t s, uint32_t n0, uint32_t n1, int32_t* s_mm, uint32_t tid, uint32_t nt) {
+    const uint32_t km = bcf_keep_mask(E, s);
+    const bool trimmed = (uint32_t)bcf_popc(km) != E.n_allele[s];
+    for (uint32_t k = 0; k < E.n_fields; k++) {
+        const uint32_t cnt = E.fld_cnt[k][s];
+        const int32_t* __restrict__ base = E.fld[k] + E.fld_off[k][s];
+        int32_t mn = INT32_MAX, mx = INT32_MIN + 1;
+        if (E.fkind[k] == GLX_FK_FT || E.fkind[k] == GLX_FK_STRING) {
+            for (uint32_t n = n0 + tid; n < n1; n += nt) {
+                const int32_t len = (int32_t)bcf_ft_len(E.m, (uint32_t)base[(size_t)n * cnt]);
+                mx = len > mx ? len : mx;
+            }
+        } else if (E.ftype[k] == GLX_TYPE_FLOAT) {
+            continue;
+        } else if (trimmed && bcf_is_arg(E.fvl[k])) {
+            // bcf_remove_allele_set rewrites the vector: only surviving slots before the sample's first end-of-vector count
+            const uint8_t vl = E.fvl[k];
+            for (uint32_t n = n0 + tid; n < n1; n += nt) {
+                const int32_t* p = base + (size_t)n * cnt;
+                for (uint32_t j = 0; j < cnt; j++) {
+                    const int32_t v = p[j];
+                    if (v == GLXB_VEND) break;
+                    if (v == GLXB_MISSING || !bcf_slot_kept(vl, j, km)) continue;
+                    mn = v < mn ? v : mn;
+                    mx = v > mx ? v : mx;
+                }
+            }
+        } else {
+            const size_t e0 = (size_t)n0 * cnt, e1 = (size_t)n1 * cnt;
+            for (size_t e = e0 + tid; e < e1; e += nt) {
+                const int32_t v = base[e];
+                if (v == GLXB_MISSING || v == GLXB_VEND) continue;
+                mn = v < mn ? v : mn;
+                mx = v > mx ? v : mx;
+            }
+        }
+        bcf_mm_merge(s_mm + 2 * k, mn, mx);
+    }
+}
+__host__ __device__ inline void bcf_scan_flush(const BcfEnc& E, uint32_t s, const int32_t* s_mm, uint32_t tid, uint32_t nt) {
+    for (uint32_t i = tid; i < E.n_fields; i += nt) bcf_mm_merge(E.mm + ((size_t)s * E.n_fields + i) * 2, s_mm[2 * i], s_mm[2 * i + 1]);
+}
+
+// ---- stage: layout. One thread per site. ----
+__host__ __device__ inline void bcf_layout_site(const BcfEnc& E, uint32_t s) {
+    BcfSitePlan& P = E.plan[s];
+    const uint32_t km = bcf_keep_mask(E, s);
+    const uint32_t n_keep = (uint32_t)bcf_popc(km), N = E.n_samples;
+    if (n_keep < 2) {  // ans.reset(): no record
+        P.keep_mask = 0;
+        P.l_shared = P.l_indiv = 0;
+        P.n_keep = (uint8_t)n_keep;
+        P.trimmed = 1;
+        P.n_blk = 0;
+        E.rec_off[s] = 0;
+        E.hdr_off[s] = 0;
+        return;
+    }
+    const bool trimmed = n_keep != E.n_allele[s];
+    const uint32_t n_blk = E.n_fields + 2;
+    P.keep_mask = km;
+    P.n_keep = (uint8_t)n_keep;
+    P.trimmed = trimmed ? 1 : 0;
+    P.n_blk = (uint8_t)n_blk;
+    uint32_t off = 0;
+    for (uint32_t b = 0; b < n_blk; b++) {
+        int32_t id;
+        uint32_t cnt, width;
+        int type;
+        if (b == 0) {  // GT: htslib GT ints of alleles < 32 always fit int8
+            id = E.m.id_GT;
+            cnt = 2;
+            width = 1;
+            type = BCF_BT_INT8;
+        } else if (b == n_blk - 1) {
+            id = E.m.id_RNC;
+            cnt = 2;
+            width = 1;
+            type = BCF_BT_CHAR;
+        } else {
+            const uint32_t k = b - 1;
+            id = E.m.id_field[k];
+            const int32_t* mm = E.mm + ((size_t)s * E.n_fields + k) * 2;
+            if (E.fkind[k] == GLX_FK_FT || E.fkind[k] == GLX_FK_STRING) {
+                cnt = mm[1] < 1 ? 1u : (uint32_t)mm[1];
+                width = 1;
+                type = BCF_BT_CHAR;
+            } else {
+                cnt = bcf_count_new(E.fvl[k], E.fld_cnt[k][s], n_keep, trimmed);
+                if (E.ftype[k] == GLX_TYPE_FLOAT) {
+                    width = 4;
+                    type = BCF_BT_FLOAT;
+                } else {
+                    width = (uint32_t)bcf_int_width(mm[0], mm[1]);
+                    type = width == 1 ? BCF_BT_INT8 : (width == 2 ? BCF_BT_INT16 : BCF_BT_INT32);
+                }
+            }
+        }
+        BcfWrite w{P.blk_hdr[b]};
+        bcf_enc_int1(w, id);
+        bcf_enc_size(w, cnt, type);
+        const uint32_t hl = (uint32_t)(w.p - P.blk_hdr[b]);
+        P.blk_off[b] = off;
+        P.blk_cnt[b] = (uint16_t)cnt;
+        P.blk_width[b] = (uint8_t)width;
+        P.blk_hdr_len[b] = (uint8_t)hl;
+        off += hl + N * cnt * width;
+    }
+    P.l_indiv = off;
+    BcfCount c;
+    bcf_emit_shared(E, s, km, n_blk, c);
+    P.l_shared = c.n;
+    E.rec_off[s] = 8ull + c.n + off;
+    E.hdr_off[s] = 8ull + c.n;
+}
+
+// ---- stage: headers. One thread per site (after the offset scans). ----
+__host__ __device__ inline void bcf_header_site(const BcfEnc& E, uint32_t s) {
+    const BcfSitePlan& P = E.plan[s];
+    if (!P.keep_mask) return;
+    BcfWrite w{E.hdr_pool + E.hdr_off[s]};
+    bcf_put32(w, P.l_shared);
+    bcf_put32(w, P.l_indiv);
+    bcf_emit_shared(E, s, P.keep_mask, P.n_blk, w);
+}
+
+// ---- stage: span. Gather bytes [lo, hi) of the record stream into buf[0 .. hi-lo). s_src: GLX_BCF_G_MAX uint16 ----
+__host__ __device__ __forceinline__ uint32_t bcf_first_site(const BcfEnc& E, unsigned long long pos) {  // first s with rec_off[s+1] > pos
+    uint32_t a = 0, b = E.n_sites;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (E.rec_off[mid + 1] > pos) b = mid;
+        else a = mid + 1;
+    }
+    return a;
+}
+__host__ __device__ __forceinline__ uint32_t bcf_conv(int32_t v, uint32_t width) {
+    if (width == 4) return (uint32_t)v;
+    if (v == GLXB_MISSING) return width == 1 ? 0x80u : 0x8000u;
+    if (v == GLXB_VEND) return width == 1 ? 0x81u : 0x8001u;
+    return (uint32_t)v;
+}
+__host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long long lo, unsigned long long hi, uint8_t* buf, uint16_t* s_src, uint32_t tid,
+                                              uint32_t nt) {
+    const uint32_t N = E.n_samples;
+    for (uint32_t s = bcf_first_site(E, lo); s < E.n_sites && E.rec_off[s] < hi; s++) {
+        const unsigned long long r0 = E.rec_off[s], r1 = E.rec_off[s + 1];
+        if (r1 == r0) continue;
+        const BcfSitePlan& P = E.plan[s];
+        const uint32_t hdr_len = 8 + P.l_shared;
+        // clip [a, a+len) to the span; returns the part as offsets relative to a
+        auto clip = [&](unsigned long long a, unsigned long long len, unsigned long long& c0, unsigned long long& c1) {
+            const unsigned long long b = a + len;
+            const unsigned long long x0 = a > lo ? a : lo, x1 = b < hi ? b : hi;
+            if (x1 <= x0) return false;
+            c0 = x0 - a;
+            c1 = x1 - a;
+            return true;
+        };
+        unsigned long long c0, c1;
+        if (clip(r0, hdr_len, c0, c1)) {
+            const uint8_t* src = E.hdr_pool + E.hdr_off[s];
+            for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[r0 + q - lo] = src[q];
+        }
+        const unsigned long long ibase = r0 + hdr_len;
+        const uint32_t km = P.keep_mask;
+        for (uint32_t b = 0; b < P.n_blk; b++) {
+            const unsigned long long bstart = ibase + P.blk_off[b];
+            const uint32_t hl = P.blk_hdr_len[b], cn = P.blk_cnt[b], w = P.blk_width[b];
+            if (bstart >= hi) break;
+            if (clip(bstart, hl, c0, c1))
+                for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[bstart + q - lo] = P.blk_hdr[b][q];
+            const unsigned long long dstart = bstart + hl, dlen = (unsigned long long)N * cn * w;
+            if (!clip(dstart, dlen, c0, c1)) continue;
+            const unsigned long long ob = dstart - lo;  // buf index of the block's first data byte (mod 2^64 when it lies before the span:
+                                                        // only bytes q in [c0, c1) are touched, for which ob + q is in range)
+#define out(q) buf[(size_t)(ob + (q))]
+            if (b == 0) {  // GT
+                const int8_t* g = E.gt + (size_t)s * N * 2;
+                for (unsigned long long q = c0 + tid; q < c1; q += nt) {
+                    const int a = g[q];
+                    out(q) = a < 0 ? (uint8_t)0 : (uint8_t)((bcf_popc(km & ((1u << a) - 1u)) + 1) << 1);
+                }
+            } else if (b == (uint32_t)P.n_blk - 1) {  // RNC
+                const uint8_t* r = E.rnc + (size_t)s * N * 2;
+                for (unsigned long long q = c0 + tid; q < c1; q += nt) out(q) = r[q];
+            } else {
+                const uint32_t k = b - 1, cnt = E.fld_cnt[k][s];
+                const int32_t* __restrict__ base = E.fld[k] + E.fld_off[k][s];
+                if (E.fkind[k] == GLX_FK_FT || E.fkind[k] == GLX_FK_STRING) {
+                    for (unsigned long long q = c0 + tid; q < c1; q += nt) {
+                        const uint32_t n = (uint32_t)(q / cn), ci = (uint32_t)(q - (unsigned long long)n * cn);
+                        out(q) = bcf_ft_char(E.m, (uint32_t)base[(size_t)n * cnt], ci);
+                    }
+                } else if (P.trimmed && bcf_is_arg(E.fvl[k]) && E.ftype[k] != GLX_TYPE_STRING) {
+                    // trimmed vector: new slot -> source slot table, then per element the "first end-of-vector" rule
+                    const uint8_t vl = E.fvl[k];
+                    const int32_t vend = E.ftype[k] == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_VECTOR_END_BITS : GLXB_VEND;
+                    GLX_BLOCK_SYNC();
+                    for (uint32_t j = tid; j < cnt; j += nt)
+                        if (bcf_slot_kept(vl, j, km)) s_src[bcf_slot_new(vl, j, km)] = (uint16_t)j;
+                    GLX_BLOCK_SYNC();
+                    const unsigned long long e0 = c0 / w, e1 = (c1 + w - 1) / w;
+                    for (unsigned long long e = e0 + tid; e < e1; e += nt) {
+                        const uint32_t n = (uint32_t)(e / cn), jn = (uint32_t)(e - (unsigned long long)n * cn);
+                        const int32_t* p = base + (size_t)n * cnt;
+                        const uint32_t j = s_src[jn];
+                        int32_t v = p[j];
+                        for (uint32_t i = 0; i < j; i++)
+                            if (p[i] == vend) {
+                                v = vend;
+                                break;
+                            }
+                        const uint32_t x = E.ftype[k] == GLX_TYPE_FLOAT ? (uint32_t)v : bcf_conv(v, w);
+                        for (uint32_t i = 0; i < w; i++) {
+                            const unsigned long long q = e * w + i;
+                            if (q >= c0 && q < c1) out(q) = (uint8_t)(x >> (8 * i));
+                        }
+                    }
+                } else if (w == 1) {
+                    for (unsigned long long q = c0 + tid; q < c1; q += nt) out(q) = (uint8_t)bcf_conv(base[q], 1);
+                } else {
+                    const bool raw = E.ftype[k] == GLX_TYPE_FLOAT;
+                    const unsigned long long e0 = c0 / w, e1 = (c1 + w - 1) / w;
+                    for (unsigned long long e = e0 + tid; e < e1; e += nt) {
+                        const int32_t v = base[e];
+                        const uint32_t x = raw ? (uint32_t)v : bcf_conv(v, w);
+                        for (uint32_t i = 0; i < w; i++) {
+                            const unsigned long long q = e * w + i;
+                            if (q >= c0 && q < c1) out(q) = (uint8_t)(x >> (8 * i));
+                        }
+                    }
+                }
+            }
+#undef out
+        }
+    }
+}
+
+}  // namespace glxd

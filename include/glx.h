@@ -279,6 +279,22 @@ void glx_stream_destroy(glx_ctx* ctx, void* stream);
 int glx_stream_sync(glx_ctx* ctx, void* stream);
 int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
 void glx_host_unregister(void* p);
+/* ---- N1: BCF2 records (and BGZF blocks) encoded on the device. After glx_launch, on the same stream:
+ *   glx_bcf_attach     once per batch: uploads glx_bcf_meta (+ allele_af of `sites`, the glx_sites the batch was uploaded
+ *                      with) and sizes the encoder's buffers; host arrays must stay valid until the stream reaches it
+ *   glx_encode_bcf_on  mode 0: the batch's records as one uncompressed stream, exactly what bcf_write would hand to bgzf
+ *                      (sites dropped after allele trimming have no record); mode 1: that stream cut into 65,280-byte BGZF
+ *                      blocks (DEFLATE + CRC-32 on the device), contiguous, ready to append to the output file
+ *   glx_bcf_length     waits until the encoder's sizes are known (an event early in the encode, not the whole stream)
+ *   glx_download_bcf_on copies exactly the encoded bytes to `dst` (and the batch's status word, see glx_status)
+ * glx_bcf_bound = bytes `dst` must hold in the worst case. */
+int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* dev, const glx_sites* sites, const glx_bcf_meta* meta, const glx_config* cfg, void* stream);
+int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, int mode, void* stream);
+int glx_bcf_length(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n_bytes, uint64_t* n_raw_bytes, uint32_t* n_blocks);
+int glx_download_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, void* dst, uint64_t capacity, void* stream, int sync);
+int glx_bcf_record_offsets(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* rec_off /* [n_sites + 1] */);
+uint64_t glx_bcf_bound(const glx_dev_batch* dev);
+
 /* Measurement aids: record CUDA events around the stages of glx_launch on the launching stream; glx_kernel_ms waits
  * for the last launch and returns the durations of {record resolve kernel, tiled fast-path kernel (incl. the fused
  * lone-variant closed form), closed-form worklist kernels (bands, variant, single-record), general worklist kernel}; glx_work_count = cells the tiled kernel put on its worklist, glx_fused_count = those of them it then

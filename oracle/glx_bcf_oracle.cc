@@ -258,11 +258,12 @@ int glx_oracle_bcf_records(const glx_config* cfg, const glx_sites* sites, const 
                     if ((int)j + shift < A && renum[j + shift] >= 0) src.push_back(j);
             }
             const size_t cn = src.size();
+            const bool recoded = trimmed && (vl == 'A' || vl == 'R' || vl == 'G');  // bcf_remove_allele_set rewrites the vector
             std::vector<int32_t> v(N * cn);
             for (size_t n = 0; n < N; n++) {
                 const int32_t* p = base + n * cnt;
                 unsigned size = cnt;  // entries before the sample's first end-of-vector
-                for (unsigned j = 0; j < cnt; j++)
+                for (unsigned j = 0; recoded && j < cnt; j++)
                     if (p[j] == vend) {
                         size = j;
                         break;

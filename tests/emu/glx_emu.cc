@@ -3,12 +3,14 @@
 // oracle without a GPU. Not part of libglx.so.
 #include "cuda_host_shim.h"
 
+#include <memory>
 #include <vector>
 
 #include "../../glnexus_b200/csrc/glx_cell_fast.cuh"
 #include "../../glnexus_b200/csrc/glx_cell_general.cuh"
 #include "../../glnexus_b200/csrc/glx_cell_variant.cuh"
 #include "../../glnexus_b200/csrc/glx_tiled_sig.cuh"
+#include "../../glnexus_b200/csrc/glx_bcf.cuh"
 
 using namespace glxd;
 
@@ -318,3 +320,113 @@ extern "C" int glx_emu_check_hints(const glx_records* recs, const glx_sites* sit
     return bad;
 }
 
+
+// The device BCF2 record encoder (glx_bcf.cuh) run stage by stage with one virtual thread per block.
+struct EmuBcf {
+    BcfEnc E;
+    std::vector<int32_t> mm;
+    std::vector<BcfSitePlan> plan;
+    std::vector<unsigned long long> roff, hoff;
+    std::vector<uint8_t> pool;
+    unsigned long long total = 0;
+    EmuBcf(const glx_config* cfg, const glx_sites* sites, const glx_bcf_meta* meta, const glx_out* out, uint32_t chunk) {
+        const uint32_t S = sites->n_sites, N = sites->n_samples, F = cfg->n_fields;
+        memset(&E, 0, sizeof E);
+        bcf_enc_scalars(E, *cfg, *meta, S, N);
+        E.beg = sites->beg; E.n_allele = sites->n_allele; E.monoallelic = sites->monoallelic; E.allele_off = sites->allele_off;
+        for (uint32_t k = 0; k < F; k++) { E.fld_cnt[k] = sites->fld_cnt[k]; E.fld_off[k] = sites->fld_off[k]; E.fld[k] = out->fld[k]; }
+        E.gt = out->gt; E.rnc = out->rnc; E.allele_used = out->allele_used;
+        E.m.rid = meta->rid; E.m.qual = meta->qual; E.m.dna_off = meta->dna_off; E.m.dna_pool = meta->dna_pool;
+        E.m.norm_beg = meta->norm_beg; E.m.norm_end = meta->norm_end; E.m.norm_off = meta->norm_off; E.m.norm_pool = meta->norm_pool;
+        E.m.aq = meta->aq; E.m.af = sites->allele_af; E.m.contig_off = meta->contig_off; E.m.contig_pool = meta->contig_pool;
+        E.m.filter_off = meta->filter_off; E.m.filter_pool = meta->filter_pool;
+        mm.assign((size_t)S * F * 2 + 2, 0);
+        for (size_t i = 0; i < (size_t)S * F; i++) { mm[2 * i] = INT32_MAX; mm[2 * i + 1] = INT32_MIN + 1; }
+        plan.resize(S + 1);
+        roff.assign(S + 1, 0);
+        hoff.assign(S + 1, 0);
+        E.mm = mm.data(); E.plan = plan.data(); E.rec_off = roff.data(); E.hdr_off = hoff.data();
+        if (chunk == 0) chunk = 2048;
+        std::vector<int32_t> s_mm(2 * GLX_MAX_FIELDS);
+        for (uint32_t s = 0; s < S; s++)
+            for (uint32_t n0 = 0; n0 < N; n0 += chunk) {
+                bcf_scan_init(E, s_mm.data(), 0, 1);
+                bcf_scan_accum(E, s, n0, std::min(N, n0 + chunk), s_mm.data(), 0, 1);
+                bcf_scan_flush(E, s, s_mm.data(), 0, 1);
+            }
+        for (uint32_t s = 0; s < S; s++) bcf_layout_site(E, s);
+        unsigned long long ra = 0, ha = 0;
+        for (uint32_t s = 0; s <= S; s++) {  // exclusive scans
+            const unsigned long long r = s < S ? roff[s] : 0, h = s < S ? hoff[s] : 0;
+            roff[s] = ra; hoff[s] = ha;
+            ra += r; ha += h;
+        }
+        pool.resize(ha + 16);
+        E.hdr_pool = pool.data();
+        for (uint32_t s = 0; s < S; s++) bcf_header_site(E, s);
+        total = roff[S];
+    }
+};
+
+// `span` = bytes per span (the device uses GLX_BCF_SPAN; small values exercise the clipping at span boundaries), `chunk` =
+// samples per scan block. *bytes is malloc'd (free()).
+extern "C" int glx_emu_bcf_records(const glx_config* cfg, const glx_sites* sites, const glx_bcf_meta* meta, const glx_out* out, uint32_t span, uint32_t chunk,
+                                   uint8_t** bytes, uint64_t* n_bytes, uint64_t* rec_off) {
+    EmuBcf X(cfg, sites, meta, out, chunk);
+    uint8_t* o = (uint8_t*)malloc(X.total ? X.total : 1);
+    memset(o, 0xEE, X.total);
+    std::vector<uint16_t> s_src(GLX_BCF_G_MAX + 8);
+    if (span == 0) span = GLX_BCF_SPAN;
+    for (unsigned long long lo = 0; lo < X.total; lo += span)
+        bcf_fill_span(X.E, lo, std::min<unsigned long long>(X.total, lo + span), o + lo, s_src.data(), 0, 1);
+    for (uint32_t s = 0; s <= sites->n_sites; s++) rec_off[s] = X.roff[s];
+    *bytes = o;
+    *n_bytes = X.total;
+    return 0;
+}
+
+// The BGZF stage (glx_bgzf.cuh) on top: every span becomes one BGZF block; the blocks are concatenated. `span` <= GLX_BCF_SPAN.
+#include "../../glnexus_b200/csrc/glx_bgzf.cuh"
+extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const glx_bcf_meta* meta, const glx_out* out, uint32_t span, uint8_t** bytes,
+                            uint64_t* n_bytes, uint32_t* n_stored) {
+    EmuBcf X(cfg, sites, meta, out, 0);
+    if (span == 0 || span > GLX_BCF_SPAN) span = GLX_BCF_SPAN;
+    std::vector<uint8_t> all;
+    std::vector<uint8_t> in(GLX_BCF_SPAN + 16);
+    std::vector<uint32_t> stage_w((GLX_BGZF_OUT + 64) / 4);
+    std::vector<uint16_t> s_src(GLX_BCF_G_MAX + 8);
+    auto sh = std::make_unique<BgzfShared>();
+    *n_stored = 0;
+    for (unsigned long long lo = 0; lo < X.total; lo += span) {
+        const unsigned long long hi = std::min<unsigned long long>(X.total, lo + span);
+        const uint32_t n = (uint32_t)(hi - lo);
+        std::fill(stage_w.begin(), stage_w.end(), 0u);
+        uint8_t* stage = reinterpret_cast<uint8_t*>(stage_w.data());
+        uint32_t* out_words = reinterpret_cast<uint32_t*>(stage + GLX_BGZF_LEAD + 18);
+        bcf_fill_span(X.E, lo, hi, in.data(), s_src.data(), 0, 1);
+        sh->n_in = n;
+        bgzf_segments(*sh, X.E, lo, hi);
+        bgzf_crc_setup(*sh, n, 0, 1);
+        bgzf_hist_init(*sh, 0, 1);
+        bgzf_crc_parts(*sh, in.data(), n, 0, 1);
+        bgzf_hist(*sh, in.data(), n, 0, 1);
+        for (uint32_t l = 0; l < 10; l++) bgzf_crc_level(*sh, l, 0, 1);
+        bgzf_crc_finish(*sh);
+        bgzf_build_codes(*sh, out_words);
+        bgzf_count_bits(*sh, in.data(), n, 0, 1);
+        bgzf_scan_bits_serial(*sh);
+        bgzf_emit(*sh, in.data(), n, out_words, 0, 1);
+        bgzf_finish_deflate(*sh, out_words);
+        if (sh->stored) {
+            bgzf_store_raw(*sh, in.data(), stage, 0, 1);
+            (*n_stored)++;
+        }
+        bgzf_frame(*sh, stage);
+        all.insert(all.end(), stage + GLX_BGZF_LEAD, stage + GLX_BGZF_LEAD + sh->block_len);
+    }
+    uint8_t* o = (uint8_t*)malloc(all.size() ? all.size() : 1);
+    memcpy(o, all.data(), all.size());
+    *bytes = o;
+    *n_bytes = all.size();
+    return 0;
+}

@@ -33,6 +33,10 @@ def lib():
         L.glx_emu_tiled_batch.restype = C.c_int
         L.glx_emu_check_hints.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
         L.glx_emu_check_hints.restype = C.c_int
+        L.glx_emu_bcf_records.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.glx_emu_bcf_records.restype = C.c_int
+        L.glx_emu_bgzf.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.glx_emu_bgzf.restype = C.c_int
         _lib = L
     return _lib
 
@@ -52,3 +56,30 @@ def check_hints(batch, tile_sites, block):
     """Mismatches between the resolve kernels' hint-confined tile searches and the full searches (0 = identical)."""
     return lib().glx_emu_check_hints(batch.records_ptr, batch.sites_ptr, tile_sites, block)
 
+
+
+def bcf_records(batch, out, span=0, chunk=0):
+    """(bytes, rec_off) from the device BCF encoder's stages run on the host (one virtual thread per block)."""
+    p, n = C.c_void_p(), C.c_uint64()
+    off = (C.c_uint64 * (batch.n_sites + 1))()
+    rc = lib().glx_emu_bcf_records(batch.config_ptr, batch.sites_ptr, batch.bcf_meta_ptr, out.ptr, span, chunk, C.byref(p), C.byref(n), off)
+    assert rc == 0
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    try:
+        return C.string_at(p.value, n.value), list(off)
+    finally:
+        libc.free(p)
+
+
+def bgzf_blocks(batch, out, span=0):
+    """(bytes, stored blocks): the BGZF blocks of the batch's record stream from the device encoder's stages run on the host."""
+    p, n, ns = C.c_void_p(), C.c_uint64(), C.c_uint32()
+    rc = lib().glx_emu_bgzf(batch.config_ptr, batch.sites_ptr, batch.bcf_meta_ptr, out.ptr, span, C.byref(p), C.byref(n), C.byref(ns))
+    assert rc == 0
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    try:
+        return C.string_at(p.value, n.value), ns.value
+    finally:
+        libc.free(p)

@@ -116,3 +116,101 @@ def test_prologue_and_bgzf_framing(built):
     whole = glnexus_b200.bgzf_stored(pro) + glnexus_b200.bgzf_stored(stream) + eof
     assert gzip.decompress(whole) == pro + stream
     assert bcfdec.bcf_file_to_vcf_text(whole).count("\n") == text.count("\n") + len(bcfdec.records_to_rows(stream, ids, contigs))
+
+
+# ---- the device encoder's stages (glx_bcf.cuh) compiled for the host vs the oracle: byte for byte ----
+import emu_lib  # noqa: E402
+
+
+def check_emu(batch, out, spans=(0, 997, 64)):
+    want, woff = oracle_lib.bcf_records(batch, out)
+    for span in spans:
+        got, goff = emu_lib.bcf_records(batch, out, span=span, chunk=7 if span else 0)
+        assert goff == woff, f"record offsets differ (span {span})"
+        if got != want:
+            i = next(i for i in range(min(len(got), len(want))) if got[i] != want[i])
+            raise AssertionError(f"span {span}: first difference at byte {i} of {len(want)}: got {got[i:i+16].hex()} want {want[i:i+16].hex()}")
+
+
+@pytest.mark.parametrize("name", gu.case_names())
+def test_bcf_device_logic_golden(built, name):
+    for batch in gu.batches_of_case(gu.load_case(name)):
+        out = batch.alloc_out()
+        oracle_lib.genotype_batch(batch, out)
+        check_emu(batch, out)
+
+
+@pytest.mark.parametrize("shape,ns,nsites,region", [("c2", 40, 300, 300), ("c3", 50, 200, 12000), ("c4", 60, 150, 9000), ("c5", 40, 200, 6000)])
+def test_bcf_device_logic_synth(built, shape, ns, nsites, region):
+    b = synth_cases.make(shape, n_samples=ns, n_sites=nsites, region_len=region)
+    out = b.alloc_out()
+    oracle_lib.genotype_batch(b, out, threads=4)
+    check_emu(b, out, spans=(0, 4093))
+
+
+@pytest.mark.parametrize("preset", ["xAtlas", "weCall", "Strelka2", "gatk_unfiltered", "DeepVariantWES"])
+def test_bcf_device_logic_presets(built, preset):
+    b = synth_cases.make("c3", n_samples=30, n_sites=200, region_len=6000, preset=preset, frac_two_record_cells=0.05, frac_lost_allele=0.05, frac_homalt=0.2)
+    out = b.alloc_out()
+    try:
+        oracle_lib.genotype_batch(b, out, threads=4)
+    except oracle_lib.OracleError:
+        pytest.skip("oracle rejects this cohort under the preset")
+    check_emu(b, out, spans=(0, 1021))
+
+
+def test_bcf_device_logic_fuzz(built):
+    n = 0
+    for seed in range(1000, 1080):
+        b = fuzz_cases.build_batch(seed)
+        out = b.alloc_out()
+        try:
+            oracle_lib.genotype_batch(b, out)
+        except oracle_lib.OracleError:
+            continue
+        check_emu(b, out, spans=(0, 333))
+        n += 1
+    assert n >= 30
+
+
+# ---- the device BGZF stage (glx_bgzf.cuh) compiled for the host: blocks must inflate (zlib) to the oracle's stream ----
+def check_bgzf(batch, out, spans=(0,)):
+    want, _ = oracle_lib.bcf_records(batch, out)
+    ratios = []
+    for span in spans:
+        blob, n_stored = emu_lib.bgzf_blocks(batch, out, span=span)
+        raw, n_blocks = bcfdec.bgzf_decompress(blob)  # checks BSIZE, CRC32, ISIZE of every block
+        assert raw == want, f"span {span}: inflated stream differs"
+        assert n_blocks == (len(want) + (span or 65280) - 1) // (span or 65280)
+        ratios.append((len(want) / max(1, len(blob)), n_stored, n_blocks))
+    return ratios
+
+
+@pytest.mark.parametrize("name", gu.case_names())
+def test_bgzf_device_logic_golden(built, name):
+    for batch in gu.batches_of_case(gu.load_case(name)):
+        out = batch.alloc_out()
+        oracle_lib.genotype_batch(batch, out)
+        check_bgzf(batch, out, spans=(0, 300))
+
+
+@pytest.mark.parametrize("shape,ns,nsites,region", [("c2", 400, 300, 300), ("c3", 500, 200, 12000), ("c4", 600, 150, 9000), ("c5", 200, 200, 6000)])
+def test_bgzf_device_logic_synth(built, shape, ns, nsites, region):
+    b = synth_cases.make(shape, n_samples=ns, n_sites=nsites, region_len=region)
+    out = b.alloc_out()
+    oracle_lib.genotype_batch(b, out, threads=4)
+    r = check_bgzf(b, out, spans=(0, 20000))
+    assert r[0][0] > 1.5, r  # the stream of a real cohort must actually compress
+    print(shape, r)
+
+
+def test_bgzf_device_logic_incompressible_and_tiny(built):
+    """Random-looking payloads fall back to stored blocks; a batch with no records gives no blocks."""
+    b = synth_cases.make("c5", n_samples=3, n_sites=40, region_len=1200)
+    out = b.alloc_out()
+    oracle_lib.genotype_batch(b, out)
+    check_bgzf(b, out, spans=(0, 64, 17))
+    b = synth_cases.make("c2", n_samples=4, n_sites=0, region_len=100)
+    out = b.alloc_out()
+    blob, _ = emu_lib.bgzf_blocks(b, out)
+    assert blob == b""
