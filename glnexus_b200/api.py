@@ -115,6 +115,18 @@ def lib():
     L.glxh_bgzf_stored.restype = C.c_int
     L.glxh_bgzf_eof.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.glxh_bgzf_eof.restype = C.c_int
+    L.glxh_stream_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), cp, sz]
+    L.glxh_stream_open.restype = C.c_int
+    L.glxh_stream_submit.argtypes = [vp, vp, cp, sz]
+    L.glxh_stream_submit.restype = C.c_int
+    L.glxh_stream_drain.argtypes = [vp, cp, sz]
+    L.glxh_stream_drain.restype = C.c_int
+    L.glxh_stream_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.glxh_stream_stats.restype = None
+    L.glxh_stream_output.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.glxh_stream_output.restype = C.c_int
+    L.glxh_stream_close.argtypes = [vp]
+    L.glxh_stream_close.restype = None
     L.glxh_load_config.argtypes = [cp, cp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.glxh_load_config.restype = C.c_int
     L.glxh_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -583,6 +595,55 @@ class Context:
         if self.handle:
             lib().glx_destroy(self.handle)
             self.handle = None
+
+
+class RangeStream:
+    """glxh_stream: the streamed range-batch driver (depth batches in flight on one device, retired in order).
+    mode: 'columns' | 'bcf' (uncompressed BCF2 records) | 'bgzf' (BGZF blocks)."""
+    MODES = {"columns": 0, "bcf": 2, "bgzf": 3}
+
+    def __init__(self, device=0, mode="bgzf", depth=3, capture=False):
+        h = C.c_void_p()
+        self._err = C.create_string_buffer(1024)
+        rc = lib().glxh_stream_open(int(device), self.MODES[mode], int(depth), 1 if capture else 0, C.byref(h), self._err, len(self._err))
+        if rc != GLX_OK:
+            raise GlxError(rc, self._err.value.decode(errors="replace"))
+        self.handle = h
+        self._keep = []
+
+    def submit(self, batch):
+        self._keep.append(batch)  # the batch's arrays must outlive its time in flight
+        if len(self._keep) > 16:
+            self._keep.pop(0)
+        rc = lib().glxh_stream_submit(self.handle, batch.handle, self._err, len(self._err))
+        if rc != GLX_OK:
+            raise GlxError(rc, self._err.value.decode(errors="replace"))
+
+    def drain(self):
+        rc = lib().glxh_stream_drain(self.handle, self._err, len(self._err))
+        if rc != GLX_OK:
+            raise GlxError(rc, self._err.value.decode(errors="replace"))
+
+    def stats(self):
+        st = (C.c_uint64 * 8)()
+        lib().glxh_stream_stats(self.handle, st)
+        return dict(zip(("batches", "batches_retired", "sites", "cells", "records", "h2d_bytes", "d2h_bytes", "raw_bcf_bytes"), [int(x) for x in st]))
+
+    def output(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        lib().glxh_stream_output(self.handle, C.byref(p), C.byref(n))
+        return C.string_at(p.value, n.value) if n.value else b""
+
+    def close(self):
+        if self.handle:
+            lib().glxh_stream_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def genotype_sites(sites_text, datasets, filename, preset=None, config_text=None, device=0, batch_sites=0, test_ingest_rules=False, abort=None):

@@ -47,10 +47,13 @@ __global__ void __launch_bounds__(GLX_BCF_SCAN_THREADS) glx_bcf_offsets_kernel(B
     const uint32_t per = (n + GLX_BCF_SCAN_THREADS - 1) / GLX_BCF_SCAN_THREADS;
     const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
     unsigned long long r = 0, h = 0;
+    uint32_t nrec = 0;
     for (uint32_t i = i0; i < i1; i++) {
         r += E.rec_off[i];
         h += E.hdr_off[i];
+        nrec += E.rec_off[i] != 0;
     }
+    if (nrec) atomicAdd(totals + 4, (unsigned long long)nrec);  // sites that have a record (zeroed before the encode)
     s_r[tid] = r;
     s_h[tid] = h;
     __syncthreads();
@@ -421,9 +424,9 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
         glx_bcf_init_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)S * d->n_fields + 255) / 256 + 1, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(E);
         glx_bcf_scan_kernel<<<dim3(S, (N + chunk - 1) / chunk), 256, 0, st>>>(E, chunk);
         glx_bcf_layout_kernel<<<(S + 127) / 128, 128, 0, st>>>(E);
-    } else if (S) {
-        CU(cudaMemsetAsync(E.rec_off, 0, (S + 1) * 8, st));
-        CU(cudaMemsetAsync(E.hdr_off, 0, (S + 1) * 8, st));
+    } else {  // no cells: no records
+        CU(cudaMemsetAsync(E.rec_off, 0, ((size_t)S + 1) * 8, st));
+        CU(cudaMemsetAsync(E.hdr_off, 0, ((size_t)S + 1) * 8, st));
     }
     if (S && N) {
         glx_bcf_offsets_kernel<<<1, GLX_BCF_SCAN_THREADS, 0, st>>>(E, B.totals);
@@ -444,8 +447,7 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
         CU(cudaGetLastError());
     }
     // lengths -> the batch's pinned words {., raw stream bytes, BGZF bytes, BGZF blocks}
-    CU(cudaMemcpyAsync(d->host_err + 1, B.totals, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->host_err + 2, B.totals + 2, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->host_err + 1, B.totals, 40, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(B.len_ev, st));
     return GLX_OK;
 }
@@ -455,10 +457,13 @@ int glx_bcf_length(glx_ctx* ctx, glx_dev_batch* d, uint64_t* n_bytes, uint64_t* 
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(d->bcf.len_ev));
     if (n_raw_bytes) *n_raw_bytes = d->host_err[1];
-    if (n_bytes) *n_bytes = d->bcf.mode == 0 ? d->host_err[1] : d->host_err[2];
-    if (n_blocks) *n_blocks = d->bcf.mode == 0 ? 0u : (uint32_t)d->host_err[3];
+    if (n_bytes) *n_bytes = d->bcf.mode == 0 ? d->host_err[1] : d->host_err[3];
+    if (n_blocks) *n_blocks = d->bcf.mode == 0 ? 0u : (uint32_t)d->host_err[4];
     return GLX_OK;
 }
+
+// records in the encoded batch (sites that survived allele trimming); valid after glx_bcf_length
+uint64_t glx_bcf_records(const glx_dev_batch* d) { return d && d->bcf.attached && d->host_err ? d->host_err[5] : 0; }
 
 int glx_download_bcf_on(glx_ctx* ctx, glx_dev_batch* d, void* dst, uint64_t capacity, void* stream_, int sync) {
     if (!ctx || !d || !dst) return GLX_E_INVALID;

@@ -446,15 +446,15 @@ int glx_take_err_slot(glx_ctx* ctx, glx_dev_batch* d) {
         if (!(ctx->err_slots_used >> i & 1)) {
             ctx->err_slots_used |= 1ull << i;
             d->err_slot = i;
-            d->host_err = ctx->host_err_pool + 4 * i;  // {error word, BCF stream bytes, BGZF bytes, BGZF blocks}
+            d->host_err = ctx->host_err_pool + 8 * i;  // {error word, then the BCF encoder's totals: stream bytes, header bytes, BGZF bytes, BGZF blocks, records}
             d->host_overflow = ctx->host_ovf_pool + (size_t)i * GLX_MAX_FIELDS;
             return GLX_OK;
         }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, 32 + GLX_MAX_FIELDS * 4, cudaHostAllocDefault) != cudaSuccess) return GLX_E_CUDA;
+    if (cudaHostAlloc(&p, 64 + GLX_MAX_FIELDS * 4, cudaHostAllocDefault) != cudaSuccess) return GLX_E_CUDA;
     d->err_slot = -1;
     d->host_err = static_cast<unsigned long long*>(p);
-    d->host_overflow = reinterpret_cast<uint32_t*>(static_cast<char*>(p) + 32);
+    d->host_overflow = reinterpret_cast<uint32_t*>(static_cast<char*>(p) + 64);
     return GLX_OK;
 }
 
@@ -489,7 +489,7 @@ int glx_create(glx_ctx** out, int device) {
             delete ctx;
             return GLX_E_CUDA;
         }
-    if (cudaHostAlloc((void**)&ctx->host_err_pool, 64 * 32, cudaHostAllocDefault) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&ctx->host_err_pool, 64 * 64, cudaHostAllocDefault) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->host_ovf_pool, 64 * GLX_MAX_FIELDS * 4, cudaHostAllocDefault) != cudaSuccess) {
         delete ctx;
         return GLX_E_CUDA;

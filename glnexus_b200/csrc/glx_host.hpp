@@ -300,9 +300,56 @@ Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, Pac
 // between range batches (the reference polls it per site task and per dataset); the first failing site's Status is
 // returned. Instead of one task per site on a thread pool, sites go to the GPU in contiguous range batches of
 // `batch_sites`, two batches in flight on two streams (retrieval/packing of the next overlaps the kernels and the
-// download of the previous). Output is pVCF text (BCF needs htslib: SURVEY F5, "next" row N1).
+// download of the previous). Output follows cfg.output_format like BCFFileSink::Open (src/service.cc:254-265): BCF = a
+// BGZF-compressed BCF2 file whose records are encoded and compressed on the device (N1), VCF = uncompressed pVCF text.
 // ---------------------------------------------------------------------------------------------
+#include <functional>
 namespace glx {
+// ---------------------------------------------------------------------------------------------
+// RangeStream (glx_stream.cc): the streamed range-batch driver. `depth` batches in flight on one device, retired in
+// submission order through `sink` — the device-side analogue of the thread pool + ordered drain of
+// Service::genotype_sites (src/service.cc:344-418). Modes: COLUMNS (packed int32 FORMAT columns, include/glx.h glx_out),
+// BCF (finished uncompressed BCF2 records), BGZF (those records as BGZF blocks, ready to append to the output file).
+// ---------------------------------------------------------------------------------------------
+struct StreamStats {
+    uint64_t batches = 0, batches_retired = 0, sites = 0, cells = 0, records = 0, h2d_bytes = 0, d2h_bytes = 0, raw_bcf_bytes = 0;
+};
+class RangeStream {
+public:
+    enum class Mode { COLUMNS = 0, BCF = 2, BGZF = 3 };
+    struct Result {
+        const PackedBatch* batch = nullptr;
+        uint64_t index = 0;             // submission index
+        const glx_out* cols = nullptr;  // COLUMNS
+        const uint8_t* bytes = nullptr; // BCF / BGZF
+        uint64_t n_bytes = 0, n_raw_bytes = 0, n_records = 0;
+        uint32_t n_blocks = 0;
+    };
+    typedef std::function<Status(const Result&)> Sink;
+    RangeStream();
+    ~RangeStream();
+    Status open(int device, Mode mode, int depth, Sink sink);
+    // Queue one batch (upload, kernels, encoder). `b` must stay valid until it has been retired; pass `owned` to hand it over.
+    Status submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned = nullptr);
+    Status drain();  // retire everything in flight, in order; the first error wins and later batches produce no output
+    void close();
+    const StreamStats& stats() const { return stats_; }
+    glx_ctx* ctx() const { return ctx_; }
+
+private:
+    struct Slot;
+    Status ensure_cols(Slot& sl, const PackedBatch& b);
+    Status start_download(Slot& sl);
+    Status retire(Slot& sl);
+    glx_ctx* ctx_ = nullptr;
+    Mode mode_ = Mode::COLUMNS;
+    Sink sink_;
+    std::vector<std::unique_ptr<Slot>> slots_;
+    uint64_t n_submitted_ = 0, n_retired_ = 0;
+    StreamStats stats_;
+    Status failed_;
+};
+
 struct ServiceStats {
     uint64_t sites = 0, sites_written = 0, batches = 0, cells = 0;
 };

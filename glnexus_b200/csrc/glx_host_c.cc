@@ -457,6 +457,62 @@ int glxh_load_config(const char* name, const char* config_text, int more_PL, int
     return GLX_OK;
 }
 
+struct glxh_stream {
+    glx::RangeStream rs;
+    bool capture = false;
+    std::string captured;
+};
+
+int glxh_stream_open(int device, int mode, int depth, int capture, glxh_stream** out, char* err, size_t errlen) {
+    if (!out || (mode != 0 && mode != 2 && mode != 3)) return GLX_E_INVALID;
+    *out = nullptr;
+    auto* h = new glxh_stream();
+    h->capture = capture != 0;
+    glx::Status s = h->rs.open(device, (glx::RangeStream::Mode)mode, depth, [h](const glx::RangeStream::Result& r) -> glx::Status {
+        if (h->capture && r.bytes) h->captured.append(reinterpret_cast<const char*>(r.bytes), r.n_bytes);
+        return glx::Status::OK();
+    });
+    if (s.bad()) {
+        delete h;
+        return fail(s, err, errlen);
+    }
+    *out = h;
+    return GLX_OK;
+}
+
+int glxh_stream_submit(glxh_stream* h, glxh_batch* b, char* err, size_t errlen) {
+    if (!h || !b) return GLX_E_INVALID;
+    glx::Status s = h->rs.submit(&b->b);
+    return s.ok() ? GLX_OK : fail(s, err, errlen);
+}
+
+int glxh_stream_drain(glxh_stream* h, char* err, size_t errlen) {
+    if (!h) return GLX_E_INVALID;
+    glx::Status s = h->rs.drain();
+    return s.ok() ? GLX_OK : fail(s, err, errlen);
+}
+
+void glxh_stream_stats(const glxh_stream* h, uint64_t st[8]) {
+    const glx::StreamStats& t = h->rs.stats();
+    st[0] = t.batches;
+    st[1] = t.batches_retired;
+    st[2] = t.sites;
+    st[3] = t.cells;
+    st[4] = t.records;
+    st[5] = t.h2d_bytes;
+    st[6] = t.d2h_bytes;
+    st[7] = t.raw_bcf_bytes;
+}
+
+int glxh_stream_output(const glxh_stream* h, const char** bytes, uint64_t* n_bytes) {
+    if (!h || !bytes || !n_bytes) return GLX_E_INVALID;
+    *bytes = h->captured.data();
+    *n_bytes = h->captured.size();
+    return GLX_OK;
+}
+
+void glxh_stream_close(glxh_stream* h) { delete h; }
+
 int glxh_preset_text(const char* name, char** text) {
     glx::genotyper_config cfg;
     glx::Status s = glx::load_config_preset(name ? name : "", cfg);

@@ -19,61 +19,6 @@ Status sample_set_of(const std::vector<GvcfDataset>& datasets, std::vector<std::
     return Status::OK();
 }
 
-namespace {
-
-Status status_of(int rc, glx_ctx* ctx) {
-    if (rc == GLX_OK) return Status::OK();
-    const std::string msg = ctx ? glx_last_error(ctx) : "";
-    switch (rc) {
-        case GLX_E_INVALID: return Status::Invalid("genotyper", msg);
-        case GLX_E_NOT_FOUND: return Status::NotFound("genotyper", msg);
-        case GLX_E_EXISTS: return Status::Exists("genotyper", msg);
-        case GLX_E_IO_ERROR: return Status::IOError("genotyper", msg);
-        case GLX_E_NOT_IMPLEMENTED: return Status::NotImplemented("genotyper", msg);
-        case GLX_E_UNSUPPORTED: return Status::NotImplemented("genotyper: input outside the device path", msg);
-        case GLX_E_ABORTED: return Status::Aborted();
-        case GLX_E_CUDA: return Status::Failure("genotyper: CUDA", msg);
-        default: return Status::Failure("genotyper", msg);
-    }
-}
-
-// pinned host columns of one batch
-struct PinnedOut {
-    glx_out out{};
-    std::vector<void*> ptrs;
-    ~PinnedOut() {
-        for (void* p : ptrs) glx_pinned_free(p);
-    }
-    template <class T>
-    T* take(size_t n) {
-        void* p = glx_pinned_alloc((n ? n : 1) * sizeof(T));
-        if (p) ptrs.push_back(p);
-        return static_cast<T*>(p);
-    }
-    bool allocate(const PackedBatch& b) {
-        const size_t S = b.sites.n_sites, N = b.sites.n_samples;
-        out.gt = take<int8_t>(S * N * 2);
-        out.rnc = take<uint8_t>(S * N * 2);
-        out.allele_used = take<uint32_t>(S);
-        out.site_flags = take<uint8_t>(S);
-        bool ok = out.gt && out.rnc && out.allele_used && out.site_flags;
-        for (uint32_t k = 0; k < b.cfg.n_fields; k++) {
-            out.fld[k] = take<int32_t>(b.fld_off[k].empty() ? 0 : b.fld_off[k].back());
-            ok = ok && out.fld[k];
-        }
-        return ok;
-    }
-};
-
-struct Slot {
-    std::unique_ptr<PackedBatch> batch;
-    std::unique_ptr<PinnedOut> out;
-    glx_dev_batch* dev = nullptr;
-    void* stream = nullptr;
-};
-
-}  // namespace
-
 Status genotype_sites(const genotyper_config& cfg, const std::vector<GvcfDataset>& datasets, const VcfHeaderInfo& hdr,
                       const std::vector<unified_site>& sites, const std::string& filename, const volatile int* abort, int device,
                       size_t batch_sites, ServiceStats* stats) {
@@ -81,67 +26,48 @@ Status genotype_sites(const genotyper_config& cfg, const std::vector<GvcfDataset
     if (batch_sites == 0) batch_sites = 4096;
     std::vector<std::string> samples;
     GLX_S(sample_set_of(datasets, samples));
+    const bool bcf = cfg.output_format == GLnexusOutputFormat::BCF;
 
-    glx_ctx* ctx = nullptr;
-    int rc = glx_create(&ctx, device);
-    if (rc != GLX_OK) return Status::Failure("genotype_sites: no usable sm_100 CUDA device; this path has no host fallback");
-    Slot slots[2];
     FILE* fp = nullptr;
     ServiceStats st;
-    auto cleanup = [&]() {
-        for (auto& sl : slots) {
-            if (sl.stream) glx_stream_sync(ctx, sl.stream);
-            if (sl.dev) glx_free_batch(ctx, sl.dev);
-            sl.dev = nullptr;
-            if (sl.stream) glx_stream_destroy(ctx, sl.stream);
-            sl.stream = nullptr;
-        }
-        if (fp && fp != stdout) fclose(fp);
-        glx_destroy(ctx);
-        if (stats) *stats = st;
-    };
-    for (auto& sl : slots) {
-        sl.stream = glx_stream_create(ctx);
-        if (!sl.stream) {
-            cleanup();
-            return Status::Failure("genotype_sites: cudaStreamCreate");
-        }
-    }
-    fp = filename == "-" ? stdout : fopen(filename.c_str(), "w");
-    if (!fp) {
-        cleanup();
-        return Status::IOError("failed to open output file for write", filename);
-    }
-
-    // retire one slot: wait, check the batch's status, write its rows in order
     bool header_written = false;
-    // `write` false: an earlier batch failed — wait and free only, no rows after the gap (the reference stops writing at
-    // the first failing site, src/service.cc:388-418)
-    auto retire = [&](Slot& sl, bool write = true) -> Status {
-        if (!sl.dev) return Status::OK();
-        Status rs = status_of(glx_stream_sync(ctx, sl.stream), ctx);
-        if (rs.ok()) rs = status_of(glx_status(ctx, sl.dev), ctx);
-        std::string rows;
-        if (rs.ok() && write) {
-            if (!header_written) {
-                vcf_header_text(*sl.batch, rows);
-                header_written = true;
-            }
-            const size_t before = std::count(rows.begin(), rows.end(), '\n');
-            rs = vcf_rows_text(*sl.batch, sl.out->out, rows);
-            st.sites_written += std::count(rows.begin(), rows.end(), '\n') - before;
-        }
-        if (rs.ok() && fwrite(rows.data(), 1, rows.size(), fp) != rows.size()) rs = Status::IOError("bcf_write", filename);
-        glx_free_batch(ctx, sl.dev);
-        sl.dev = nullptr;
-        sl.batch.reset();
-        sl.out.reset();
-        return rs;
+    auto write_all = [&](const void* p, size_t n) -> Status {
+        return fwrite(p, 1, n, fp) == n ? Status::OK() : Status::IOError("bcf_write", filename);
     };
+    auto write_header = [&](const PackedBatch& b) -> Status {
+        if (header_written) return Status::OK();
+        header_written = true;
+        if (!bcf) {
+            std::string h;
+            vcf_header_text(b, h);
+            return write_all(h.data(), h.size());
+        }
+        const std::string pro = bcf_file_prologue(b);  // bcf_hdr_write: its own BGZF block(s)
+        std::string blocks;
+        for (size_t off = 0; off < pro.size(); off += 65280)
+            blocks += bgzf_block_stored(reinterpret_cast<const uint8_t*>(pro.data()) + off, std::min<size_t>(65280, pro.size() - off));
+        return write_all(blocks.data(), blocks.size());
+    };
+    RangeStream rs;
+    s = rs.open(device, bcf ? RangeStream::Mode::BGZF : RangeStream::Mode::COLUMNS, 3, [&](const RangeStream::Result& r) -> Status {
+        Status ws = write_header(*r.batch);
+        if (ws.bad()) return ws;
+        if (bcf) {
+            st.sites_written += r.n_records;
+            return write_all(r.bytes, r.n_bytes);
+        }
+        std::string rows;
+        ws = vcf_rows_text(*r.batch, *r.cols, rows);
+        if (ws.bad()) return ws;
+        st.sites_written += std::count(rows.begin(), rows.end(), '\n');
+        return write_all(rows.data(), rows.size());
+    });
+    if (s.bad()) return s;
+    fp = filename == "-" ? stdout : fopen(filename.c_str(), "wb");
+    if (!fp) return Status::IOError("failed to open output file for write", filename);
 
     // contigs in order of first appearance; sites of one contig are packed once, then cut into range batches
-    size_t i = 0, n_submitted = 0;
-    PackedBatch header_only;  // used when there are no sites at all
+    size_t i = 0;
     while (i < sites.size() && s.ok()) {
         const int rid = sites[i].pos.rid;
         size_t j = i;
@@ -163,45 +89,37 @@ Status genotype_sites(const genotyper_config& cfg, const std::vector<GvcfDataset
                 break;
             }
             const size_t hi = std::min(contig_sites.size(), lo + batch_sites);
-            Slot& sl = slots[n_submitted & 1];
-            s = retire(sl);  // the batch submitted two steps ago
+            std::unique_ptr<PackedBatch> b(new PackedBatch());
+            s = slice_batch(whole, (uint32_t)lo, (uint32_t)hi, *b);
             if (s.bad()) break;
-            sl.batch.reset(new PackedBatch());
-            s = slice_batch(whole, (uint32_t)lo, (uint32_t)hi, *sl.batch);
-            if (s.bad()) break;
-            sl.out.reset(new PinnedOut());
-            if (!sl.out->allocate(*sl.batch)) {
-                s = Status::Failure("genotype_sites: pinned allocation failed");
-                break;
-            }
-            s = status_of(glx_upload_on(ctx, &sl.batch->cfg, &sl.batch->recs, &sl.batch->sites, sl.stream, 0, &sl.dev), ctx);
-            if (s.ok()) s = status_of(glx_launch(ctx, sl.dev, sl.stream), ctx);
-            if (s.ok()) s = status_of(glx_download_on(ctx, sl.dev, &sl.out->out, sl.stream, 0), ctx);
-            if (s.bad()) break;
-            n_submitted++;
-            st.batches++;
-            st.sites += hi - lo;
-            st.cells += (uint64_t)(hi - lo) * samples.size();
+            PackedBatch* raw = b.get();
+            s = rs.submit(raw, std::move(b));
         }
         i = j;
     }
     // drain in submission order; the first error wins (src/service.cc:388-418)
-    for (int k = 0; k < 2; k++) {
-        Slot& sl = slots[(n_submitted + k) & 1];
-        Status rs = retire(sl, s.ok());
-        if (s.ok() && rs.bad()) s = rs;
-    }
+    Status ds = rs.drain();
+    if (s.ok()) s = ds;
+    st.batches = rs.stats().batches;
+    st.sites = rs.stats().sites;
+    st.cells = rs.stats().cells;
     if (s.ok() && !header_written) {  // no sites: header only, like an empty pVCF
+        PackedBatch header_only;
         s = pack_sites(cfg, {}, (uint32_t)samples.size(), header_only);
         if (s.ok()) {
             header_only.sample_names = samples;
             header_only.contigs = hdr.contigs;
-            std::string h;
-            vcf_header_text(header_only, h);
-            if (fwrite(h.data(), 1, h.size(), fp) != h.size()) s = Status::IOError("bcf_write", filename);
+            s = write_header(header_only);
         }
     }
-    cleanup();
+    if (s.ok() && bcf) {
+        const std::string eof = bgzf_eof_block();  // bcf_close
+        s = write_all(eof.data(), eof.size());
+    }
+    if (fp != stdout) fclose(fp);
+    else fflush(fp);
+    rs.close();
+    if (stats) *stats = st;
     return s;
 }
 

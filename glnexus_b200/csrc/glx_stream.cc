@@ -1,0 +1,231 @@
+// glx_stream.cc — glx::RangeStream: the streamed range-batch driver of the device path. One device, `depth` batches in
+// flight on `depth` streams, results retired strictly in submission order — the device-side analogue of the reference's
+// thread pool + ordered drain in Service::genotype_sites (src/service.cc:344-418): while batch i's kernels run, batch
+// i+1 uploads and batch i-1's encoded records cross PCIe. Everything device-side goes through the C ABI of include/glx.h.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "glx_host.hpp"
+
+namespace glx {
+
+static Status status_of_rc(int rc, glx_ctx* ctx) {
+    if (rc == GLX_OK) return Status::OK();
+    const std::string msg = ctx ? glx_last_error(ctx) : "";
+    switch (rc) {
+        case GLX_E_INVALID: return Status::Invalid("genotyper", msg);
+        case GLX_E_NOT_FOUND: return Status::NotFound("genotyper", msg);
+        case GLX_E_EXISTS: return Status::Exists("genotyper", msg);
+        case GLX_E_IO_ERROR: return Status::IOError("genotyper", msg);
+        case GLX_E_NOT_IMPLEMENTED: return Status::NotImplemented("genotyper", msg);
+        case GLX_E_UNSUPPORTED: return Status::NotImplemented("genotyper: input outside the device path", msg);
+        case GLX_E_ABORTED: return Status::Aborted();
+        case GLX_E_CUDA: return Status::Failure("genotyper: CUDA", msg);
+        default: return Status::Failure("genotyper", msg);
+    }
+}
+
+struct RangeStream::Slot {
+    PackedBatch* batch = nullptr;
+    std::unique_ptr<PackedBatch> owned;
+    glx_dev_batch* dev = nullptr;
+    void* stream = nullptr;
+    int state = 0;  // 0 free, 1 kernels (+ encoder) queued, 2 download queued
+    // encoded output (modes BCF / BGZF): pinned, grown on demand, reused across batches
+    uint8_t* pinned = nullptr;
+    size_t pinned_cap = 0;
+    uint64_t n_out = 0, n_raw = 0, n_records = 0;
+    uint32_t n_blocks = 0;
+    // column output (mode COLUMNS): pinned arrays sized for the largest batch seen
+    glx_out cols{};
+    size_t cap_cells = 0, cap_sites = 0, cap_fld[GLX_MAX_FIELDS] = {};
+};
+
+RangeStream::RangeStream() = default;
+
+RangeStream::~RangeStream() { close(); }
+
+Status RangeStream::open(int device, Mode mode, int depth, Sink sink) {
+    close();
+    if (depth < 2) depth = 2;
+    if (depth > 8) depth = 8;
+    mode_ = mode;
+    sink_ = std::move(sink);
+    if (glx_create(&ctx_, device) != GLX_OK) return Status::Failure("genotype_sites: no usable sm_100 CUDA device; this path has no host fallback");
+    slots_.clear();
+    for (int i = 0; i < depth; i++) {
+        slots_.emplace_back(new Slot());
+        slots_.back()->stream = glx_stream_create(ctx_);
+        if (!slots_.back()->stream) return Status::Failure("RangeStream: cudaStreamCreate");
+    }
+    n_submitted_ = n_retired_ = 0;
+    stats_ = StreamStats();
+    failed_ = Status::OK();
+    return Status::OK();
+}
+
+void RangeStream::close() {
+    if (!ctx_) return;
+    for (auto& sp : slots_) {
+        Slot& sl = *sp;
+        if (sl.stream) glx_stream_sync(ctx_, sl.stream);
+        if (sl.dev) glx_free_batch(ctx_, sl.dev);
+        if (sl.stream) glx_stream_destroy(ctx_, sl.stream);
+        if (sl.pinned) glx_pinned_free(sl.pinned);
+        if (sl.cols.gt) glx_pinned_free(sl.cols.gt);
+        if (sl.cols.rnc) glx_pinned_free(sl.cols.rnc);
+        if (sl.cols.allele_used) glx_pinned_free(sl.cols.allele_used);
+        if (sl.cols.site_flags) glx_pinned_free(sl.cols.site_flags);
+        for (auto& f : sl.cols.fld)
+            if (f) glx_pinned_free(f);
+    }
+    slots_.clear();
+    glx_destroy(ctx_);
+    ctx_ = nullptr;
+}
+
+static bool grow(void** p, size_t* cap, size_t need) {
+    if (*p && *cap >= need) return true;
+    if (*p) glx_pinned_free(*p);
+    *cap = need + need / 4 + 4096;
+    *p = glx_pinned_alloc(*cap);
+    return *p != nullptr;
+}
+
+Status RangeStream::ensure_cols(Slot& sl, const PackedBatch& b) {
+    const size_t cells = (size_t)b.sites.n_sites * b.sites.n_samples, S = b.sites.n_sites;
+    size_t c = sl.cap_cells;
+    bool ok = grow((void**)&sl.cols.gt, &c, cells * 2);
+    c = sl.cap_cells;
+    ok = ok && grow((void**)&sl.cols.rnc, &c, cells * 2);
+    sl.cap_cells = c;
+    size_t s4 = sl.cap_sites;
+    ok = ok && grow((void**)&sl.cols.allele_used, &s4, S * 4 + 16);
+    s4 = sl.cap_sites;
+    ok = ok && grow((void**)&sl.cols.site_flags, &s4, S * 4 + 16);
+    sl.cap_sites = s4;
+    for (uint32_t k = 0; k < b.cfg.n_fields && ok; k++) ok = grow((void**)&sl.cols.fld[k], &sl.cap_fld[k], (b.fld_off[k].empty() ? 0 : b.fld_off[k].back()) * 4 + 16);
+    return ok ? Status::OK() : Status::Failure("RangeStream: pinned allocation failed");
+}
+
+// queue the device->host copy of a slot whose kernels are queued (BCF modes: needs the encoded size, known early in the encode)
+Status RangeStream::start_download(Slot& sl) {
+    if (sl.state != 1) return Status::OK();
+    if (mode_ == Mode::COLUMNS) {
+        sl.state = 2;  // queued at submit
+        return Status::OK();
+    }
+    uint64_t n = 0, raw = 0;
+    uint32_t blocks = 0;
+    Status s = status_of_rc(glx_bcf_length(ctx_, sl.dev, &n, &raw, &blocks), ctx_);
+    if (s.bad()) return s;
+    if (!grow((void**)&sl.pinned, &sl.pinned_cap, (size_t)n + 64)) return Status::Failure("RangeStream: pinned allocation failed");
+    sl.n_out = n;
+    sl.n_raw = raw;
+    sl.n_blocks = blocks;
+    sl.n_records = glx_bcf_records(sl.dev);
+    s = status_of_rc(glx_download_bcf_on(ctx_, sl.dev, sl.pinned, sl.pinned_cap, sl.stream, 0), ctx_);
+    if (s.ok()) sl.state = 2;
+    return s;
+}
+
+// wait for the slot, check its status word, hand the result to the sink; after a failure later slots are freed without output
+Status RangeStream::retire(Slot& sl) {
+    if (sl.state == 0) return Status::OK();
+    Status s = start_download(sl);
+    if (s.ok()) s = status_of_rc(glx_stream_sync(ctx_, sl.stream), ctx_);
+    else glx_stream_sync(ctx_, sl.stream);
+    if (s.ok()) s = status_of_rc(glx_status(ctx_, sl.dev), ctx_);
+    if (s.ok() && failed_.ok() && sink_) {
+        Result r;
+        r.batch = sl.batch;
+        r.index = n_retired_;
+        if (mode_ == Mode::COLUMNS) r.cols = &sl.cols;
+        else {
+            r.bytes = sl.pinned;
+            r.n_bytes = sl.n_out;
+            r.n_raw_bytes = sl.n_raw;
+            r.n_blocks = sl.n_blocks;
+            r.n_records = sl.n_records;
+        }
+        s = sink_(r);
+    }
+    if (s.ok() && failed_.ok()) {
+        stats_.batches_retired++;
+        stats_.d2h_bytes += mode_ == Mode::COLUMNS ? glx_out_bytes(sl.dev) : sl.n_out;
+        stats_.raw_bcf_bytes += sl.n_raw;
+    }
+    glx_free_batch(ctx_, sl.dev);
+    sl.dev = nullptr;
+    sl.batch = nullptr;
+    sl.owned.reset();
+    sl.state = 0;
+    n_retired_++;
+    if (s.bad() && failed_.ok()) failed_ = s;
+    return s;
+}
+
+Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned) {
+    if (!ctx_) return Status::Invalid("RangeStream: not open");
+    if (failed_.bad()) return failed_;
+    const size_t depth = slots_.size();
+    Slot& sl = *slots_[n_submitted_ % depth];
+    Status s = retire(sl);  // the batch submitted `depth` steps ago
+    if (s.bad()) return s;
+    sl.batch = b;
+    sl.owned = std::move(owned);
+    s = status_of_rc(glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev), ctx_);
+    if (s.ok()) s = status_of_rc(glx_launch(ctx_, sl.dev, sl.stream), ctx_);
+    if (s.ok()) {
+        if (mode_ == Mode::COLUMNS) {
+            s = ensure_cols(sl, *b);
+            if (s.ok()) s = status_of_rc(glx_download_on(ctx_, sl.dev, &sl.cols, sl.stream, 0), ctx_);
+        } else {
+            const glx_bcf_meta& meta = build_bcf_meta(*b);
+            s = status_of_rc(glx_bcf_attach(ctx_, sl.dev, &b->sites, &meta, &b->cfg, sl.stream), ctx_);
+            if (s.ok()) s = status_of_rc(glx_encode_bcf_on(ctx_, sl.dev, mode_ == Mode::BGZF ? 1 : 0, sl.stream), ctx_);
+        }
+    }
+    if (s.bad()) {
+        if (sl.dev) {
+            glx_stream_sync(ctx_, sl.stream);
+            glx_free_batch(ctx_, sl.dev);
+            sl.dev = nullptr;
+        }
+        sl.batch = nullptr;
+        sl.owned.reset();
+        failed_ = s;
+        return s;
+    }
+    sl.state = 1;
+    stats_.batches++;
+    stats_.sites += b->sites.n_sites;
+    stats_.cells += (uint64_t)b->sites.n_sites * b->sites.n_samples;
+    stats_.records += b->recs.n_records;
+    stats_.h2d_bytes += glx_in_bytes(sl.dev);
+    n_submitted_++;
+    // the batch before this one has had time to reach its size event: queue its download behind its encoder now, so that it
+    // overlaps this batch's upload and kernels
+    if (n_submitted_ >= 2) {
+        Slot& prev = *slots_[(n_submitted_ - 2) % depth];
+        s = start_download(prev);
+        if (s.bad() && failed_.ok()) failed_ = s;
+    }
+    return s;
+}
+
+Status RangeStream::drain() {
+    if (!ctx_) return Status::OK();
+    Status s = failed_;
+    const size_t depth = slots_.size();
+    for (size_t k = 0; k < depth; k++) {  // oldest first
+        Slot& sl = *slots_[(n_submitted_ + k) % depth];
+        Status rs = retire(sl);
+        if (s.ok() && rs.bad()) s = rs;
+    }
+    return s.ok() ? failed_ : s;
+}
+
+}  // namespace glx

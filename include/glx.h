@@ -294,6 +294,7 @@ int glx_bcf_length(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n_bytes, uint64_t
 int glx_download_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, void* dst, uint64_t capacity, void* stream, int sync);
 int glx_bcf_record_offsets(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* rec_off /* [n_sites + 1] */);
 uint64_t glx_bcf_bound(const glx_dev_batch* dev);
+uint64_t glx_bcf_records(const glx_dev_batch* dev); /* records in the encoded batch; valid after glx_bcf_length */
 
 /* Measurement aids: record CUDA events around the stages of glx_launch on the launching stream; glx_kernel_ms waits
  * for the last launch and returns the durations of {record resolve kernel, tiled fast-path kernel (incl. the fused

@@ -92,6 +92,22 @@ int glxh_genotype_sites(const char* preset, const char* config_text, const char*
                         const char* const* vcf_texts, const char* filename, int device, uint32_t batch_sites, int test_ingest_rules,
                         const volatile int* abort, uint64_t stats[4], char* err, size_t errlen);
 
+/* The streamed range-batch driver under glxh_genotype_sites, for callers that bring their own packed batches (one per contig
+ * range, in genomic order): `depth` batches in flight on one device, results retired strictly in submission order.
+ *   mode 0  packed int32 FORMAT columns (glx_out)            mode 2  finished, uncompressed BCF2 records
+ *   mode 3  those records as BGZF blocks (DEFLATE + CRC-32 on the device), ready to append to the output file
+ * A submitted batch must stay alive until `depth` later submits or glxh_stream_drain have retired it. With capture != 0 the
+ * encoded bytes of every batch (modes 2, 3) are kept, concatenated in order, for glxh_stream_output; otherwise results are
+ * dropped after their status check (measurement). stats = {batches, batches retired, sites, cells, records, H2D bytes, D2H
+ * bytes, uncompressed BCF bytes}. */
+typedef struct glxh_stream glxh_stream;
+int glxh_stream_open(int device, int mode, int depth, int capture, glxh_stream** s, char* err, size_t errlen);
+int glxh_stream_submit(glxh_stream* s, glxh_batch* b, char* err, size_t errlen);
+int glxh_stream_drain(glxh_stream* s, char* err, size_t errlen);
+void glxh_stream_stats(const glxh_stream* s, uint64_t stats[8]);
+int glxh_stream_output(const glxh_stream* s, const char** bytes, uint64_t* n_bytes);
+void glxh_stream_close(glxh_stream* s);
+
 /* Seeded synthetic cohort in record-store form (BASELINE.json configs[1..4] shapes). See DESIGN.md §synthetic. */
 typedef struct glxh_synth_params {
     uint32_t n_samples, n_sites;

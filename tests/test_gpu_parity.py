@@ -300,27 +300,39 @@ def test_gpu_narrow_download(ctx):
     ctx.stream_destroy(st)
 
 
+@pytest.mark.parametrize("fmt", ["BCF", "VCF"])
 @pytest.mark.parametrize("name", gu.case_names())
-def test_gpu_service_genotype_sites(name, tmp_path):
+def test_gpu_service_genotype_sites(name, fmt, tmp_path):
     """The upper seam (glx::genotype_sites = Service::genotype_sites on the device path): whole cases, all contigs, tiny range
-    batches (2 sites) so that batching, two-deep pipelining and ordered writing are exercised; output pVCF vs the reference's truth."""
+    batches (2 sites) so that batching, pipelining and ordered writing are exercised. Output follows cfg.output_format like the
+    reference's BCFFileSink: BCF (default) = a BGZF-compressed BCF2 file encoded on the device, read back here with the
+    independent BCF reader; VCF = pVCF text. Both against the reference's truth pVCF."""
+    import bcfdec
     import glnexus_b200
     case = gu.load_case(name)
     ds = [(d["name"], d["vcf"]) for d in case["datasets"]]
-    out = str(tmp_path / "out.vcf")
+    out = str(tmp_path / ("out." + fmt.lower()))
+    cfg_text = glnexus_b200.load_config(case["preset"], case["config_text"])
+    assert "output_format BCF" in cfg_text  # the reference's default
+    cfg_text = cfg_text.replace("output_format BCF", "output_format " + fmt)
     multi = name == "vcf_services"  # multi-sample datasets: rejected, never mis-computed
     try:
-        st = glnexus_b200.genotype_sites(case["sites_text"], ds, out, preset=case["preset"], config_text=case["config_text"], batch_sites=2,
-                                         test_ingest_rules=True)
+        st = glnexus_b200.genotype_sites(case["sites_text"], ds, out, config_text=cfg_text, batch_sites=2, test_ingest_rules=True)
     except glnexus_b200.GlxError as e:
         assert multi and e.code == -6
         return
     assert not multi
-    got = open(out).read()
+    raw = open(out, "rb").read()
+    if fmt == "BCF":
+        assert raw[:4] == b"\x1f\x8b\x08\x04" and raw.endswith(glnexus_b200.bgzf_eof())
+        got = bcfdec.bcf_file_to_vcf_text(raw)
+    else:
+        got = raw.decode()
     diffs = vcfcmp.compare(got, case["truth_vcf"], case["formats"], case["infos"])
     assert not diffs, "\n".join(diffs[:20])
     n_sites = sum(1 for l in case["sites_text"].split("\n") if l.startswith("site\t"))
     assert st["sites"] == n_sites and st["batches"] >= (n_sites + 1) // 2
+    assert st["rows"] == sum(1 for l in got.split("\n") if l and not l.startswith("#"))
 
 
 def test_gpu_service_abort_and_errors(tmp_path):
