@@ -3,14 +3,16 @@
 
 A "step" is one pass of the hot path (glx_launch: every kernel of the path) over one contig-range batch of a
 seeded synthetic DeepVariant-style cohort (BASELINE.json configs[1]: 1,000 samples x 50,000 dense exome-like
-sites, 5e7 cells). At N>1 every rank owns its own contiguous site range of the same shape (weak scaling; sites
-shard with no collective), and `value` is the cells all ranks processed over the slowest rank's
-device time.
+sites, 5e7 cells). The cohort is 6 x N such segments; it is cut into N contiguous site ranges of equal output weight by
+the product's own partitioner (glxh_partition_cohort / glxh_batch_slice) and rank r takes range r (weak scaling; sites
+shard with no collective). `value` is the cells all ranks processed over the slowest rank's device time.
+`--segments G` fixes the cohort at G segments whatever N is (strong scaling).
 
   value     device-resident throughput: batch uploaded once, K launches timed with CUDA events on the launching
             stream (L2 flushed between steps, flush not timed)
-  e2e       same metric through the reference-facing C ABI call glx_genotype_batch with HOST buffers: H2D of the
-            record store + sites, all kernels, D2H of the packed FORMAT columns, all inside the timed region
+  e2e       same metric through the reference-facing C ABI with HOST buffers: the C++ range-batch driver (glxh_stream_*)
+            streams the rank's range batches — H2D of the record store + sites, all kernels, the on-device BCF2/BGZF
+            encoder, D2H of the finished BGZF blocks — all inside the timed region
   roofline  algorithmic bytes (SURVEY.md §8d definition) / tiled-kernel duration vs the measured HBM copy peak
   cpu_baseline  the C++ oracle (port of the reference algorithm) on the box's host cores over a bounded sample
 
@@ -200,6 +202,59 @@ def workload_name(w, n_samples, n_sites):
     return f"{desc}; {n_samples} samples x {n_sites} sites per GPU"
 
 
+def build_rank_batches(shape, n_samples, n_sites, region_len, n_segments, world, rank, pin=True):
+    """The cohort is `n_segments` consecutive genomic segments of the workload's shape (segment g: its own region and seed).
+    It is cut into `world` contiguous site ranges of equal output weight with the product's glxh_partition_cohort; this rank
+    generates the segments its range touches and slices the two boundary segments with glxh_batch_slice. Returns the rank's
+    range batches in genomic order."""
+    import glnexus_b200
+    import synth_cases
+    seed0 = synth_cases.SHAPES[shape][1]["seed"]
+
+    def seg(g, sites_only):
+        return synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len, region_beg=10_000_000 + g * region_len,
+                                seed=seed0 + 7919 * g, sites_only=1 if sites_only else 0)
+
+    skeleton = [seg(g, True) for g in range(n_segments)]
+    cuts = glnexus_b200.partition_cohort(skeleton, world)
+    (g_lo, s_lo), (g_hi, s_hi) = cuts[rank], cuts[rank + 1]
+    batches = []
+    for g in range(g_lo, min(n_segments, g_hi + 1)):
+        a = s_lo if g == g_lo else 0
+        b = s_hi if g == g_hi else skeleton[g].n_sites
+        if b <= a:
+            continue
+        full = seg(g, False)
+        part = full if (a == 0 and b == full.n_sites) else full.slice(a, b)
+        if part is not full:
+            full.close()
+        if pin:
+            part.pin()
+        batches.append(part)
+    for sk in skeleton:
+        sk.close()
+    return batches, cuts
+
+
+def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3):
+    """Wall seconds to stream `batches` x `passes` through the C++ range-batch driver (glxh_stream_*): per batch the H2D of the
+    record store + sites, all kernels, the on-device encoder and the D2H of its output. Returns (seconds, stats)."""
+    rs = glnexus_b200.RangeStream(device, mode, depth)
+    for b in batches[:min(len(batches), depth)]:  # warm the arena cache and the pinned result buffers of every slot
+        rs.submit(b)
+    rs.drain()
+    st0 = rs.stats()
+    t = time.time()
+    for _ in range(passes):
+        for b in batches:
+            rs.submit(b)
+    rs.drain()
+    dt = time.time() - t
+    st = {k: v - st0[k] for k, v in rs.stats().items()}
+    rs.close()
+    return dt, st
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,7 +265,9 @@ def main():
     ap.add_argument("--samples", type=int, default=0)
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--segments", type=int, default=0, help="segments (range batches) of the streamed cohort; default 6 per GPU (weak scaling)")
+    ap.add_argument("--passes", type=int, default=1, help="times the rank's batches are streamed in the timed end-to-end region")
+    ap.add_argument("--e2e-modes", default="bgzf,bcf,columns")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -245,14 +302,19 @@ def main():
     if args.sites:
         region_len = int(region_len * args.sites / n_sites)
         n_sites = args.sites
-    # rank r genotypes its own contiguous genomic range (weak scaling): same shape, next region, own seed stream
-    seed = synth_cases.SHAPES[shape][1]["seed"] + 1000 * rank
-    batch = synth_cases.make(shape, n_samples=n_samples, n_sites=n_sites, region_len=region_len,
-                             region_beg=10_000_000 + rank * region_len, seed=seed)
+    strong = args.segments > 0
+    n_segments = args.segments if strong else 6 * world
+    t_gen = time.time()
+    batches, cuts = build_rank_batches(shape, n_samples, n_sites, region_len, n_segments, world, rank)
+    gen_s = time.time() - t_gen
+    batch = max(batches, key=lambda b: b.n_sites)  # the device-resident measurement runs on the rank's largest range batch
     cells = batch.n_sites * batch.n_samples
+    rank_cells = sum(b.n_sites * b.n_samples for b in batches)
 
     ctx = glnexus_b200.Context(local_rank)
+    ctx.set_option("profile_upload", 1)
     dev = ctx.upload(batch)
+    up_ms = dev.upload_kernel_ms()
     dev.set_profile(True)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -283,85 +345,74 @@ def main():
         barrier()
         t1 = time.time()
         clocks = sampler.stop(t0, t1)
+        # the on-device BCF2 encoder (N1), timed the same way: raw records, and records + BGZF (DEFLATE + CRC-32)
+        dev.bcf_attach(batch, stream.cuda_stream)
+        enc_ms = {}
+        for mode, name in ((0, "bcf_records_ms"), (1, "bcf_bgzf_ms")):
+            dev.encode_bcf(mode, stream.cuda_stream)
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(max(3, args.steps // 2)):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                dev.encode_bcf(mode, stream.cuda_stream)
+                b.record(stream)
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            enc_ms[name] = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        enc_bytes, enc_raw, enc_blocks = dev.bcf_length()
     dev.check()
     n_worklist = dev.work_count()
     n_fused = dev.fused_count()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     launches = dev.launch_count * args.steps
+    h2d_one = dev.in_bytes
+    d2h_cols = dev.out_bytes
+    dev.close()
+    ctx.close()
 
-    # ---- end to end through the C ABI with host buffers ----
-    # Every step uploads the batch's record store + sites from pinned host memory, runs all kernels and downloads every
-    # output column into pinned host memory. Steps are pipelined two deep on two streams (glx_upload_on / glx_launch /
-    # glx_download_on), the way a range-batch driver would run: the D2H of one batch overlaps the H2D + kernels of the next.
-    batch.pin()
-    e2e_steps = args.e2e_steps or max(4, min(args.steps, 8))
-    outs = [batch.alloc_out(pinned=True), batch.alloc_out(pinned=True)]
-    outs16 = [batch.alloc_out16(), batch.alloc_out16()]
-    streams = [ctx.stream_create(), ctx.stream_create()]
+    # ---- end to end through the C ABI with host buffers: the streamed range-batch driver over the rank's share of the cohort ----
+    modes = [m for m in args.e2e_modes.split(",") if m]
+    e2e = {}
+    solo = None
+    if world > 1:  # rank 0 alone first: the one-GPU rate of the same code on the same box, for the scaling efficiency
+        if rank == 0:
+            solo = stream_pass(glnexus_b200, local_rank, modes[0], batches, args.passes)
+        barrier()
+    for m in modes:
+        barrier()
+        dt, st = stream_pass(glnexus_b200, local_rank, m, batches, args.passes)
+        barrier()
+        e2e[m] = (dt, st)
 
-    def pipelined(n, narrow):
-        slots = [None, None]
-
-        def retire(k):
-            ctx.stream_sync(streams[k])
-            slots[k].status()
-            if narrow:
-                slots[k].narrow_finish(outs16[k])
-            slots[k].close()
-            slots[k] = None
-
-        for i in range(n):
-            k = i & 1
-            if slots[k] is not None:
-                retire(k)
-            dv = ctx.upload_async(batch, streams[k])
-            dv.launch(streams[k])
-            if narrow:
-                dv.download_narrow_async(outs16[k], streams[k])
-            else:
-                dv.download_async(outs[k], streams[k])
-            slots[k] = dv
-        for k in (0, 1):
-            if slots[k] is not None:
-                retire(k)
-
-    # e2e (headline): integer columns cross PCIe as int8 / int16 wherever every value of the field fits (the types BCF would store)
-    pipelined(2, True)  # warm the arena cache of both slots
-    barrier()
-    te = time.time()
-    pipelined(e2e_steps, True)
-    torch.cuda.synchronize()
-    e2e_s = time.time() - te
-    d2h_narrow = outs16[0].narrow_nbytes() + batch.n_sites * 5
-    # the same with full int32 columns
-    pipelined(2, False)
-    barrier()
-    tw = time.time()
-    pipelined(e2e_steps, False)
-    torch.cuda.synchronize()
-    e2e_wide_s = time.time() - tw
-    # one synchronous call (latency of a single batch, nothing overlapped)
-    ctx.genotype_batch(batch, outs[0])
-    ts = time.time()
-    ctx.genotype_batch(batch, outs[0])
-    sync_call_s = time.time() - ts
-    h2d = dev.in_bytes
-    d2h = dev.out_bytes
-
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = t.tolist()
-        c = torch.tensor([cells], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        cells_all = int(c.item())
-    else:
-        cells_all = cells
+        return t.item()
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
+    total_ms = allmax(total_ms)
+    cells_all = int(allsum(cells))
+    e2e_red = {}
+    for m in modes:
+        dt, st = e2e[m]
+        e2e_red[m] = {"s": allmax(dt), "cells": int(allsum(st["cells"])), "h2d": int(allsum(st["h2d_bytes"])), "d2h": int(allsum(st["d2h_bytes"])),
+                      "raw": int(allsum(st["raw_bcf_bytes"])), "batches": int(allsum(st["batches"]))}
 
     if rank == 0:
         value = cells_all * args.steps / (total_ms * 1e-3)
-        e2e_v = cells_all * e2e_steps / e2e_s
+        head = e2e_red[modes[0]]
+        e2e_v = head["cells"] / head["s"]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -386,28 +437,42 @@ def main():
         dom_alg = alg_by_kernel[dom_i] if alg_by_kernel[dom_i] is not None else alg
         achieved = dom_alg / (dom_ms * 1e-3) / 1e9
         traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if tr.get("workload") == args.workload and tr.get("cells") == cells:
-                traffic = tr["dram_bytes"].get(dom)
-        except Exception:
-            pass
+        for tf in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", tf)))
+                if tr.get("workload") == args.workload and tr.get("cells") == cells:
+                    traffic = tr["dram_bytes"].get(dom)
+                    break
+            except Exception:
+                pass
+        n_b = max(1, head["batches"])
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, n_samples, n_sites), "preset": synth_cases.SHAPES[shape][0],
-                       "cells_per_gpu": cells, "numa_node": numa, "records_per_gpu": int(batch.n_records), "variant_records_per_gpu": int(batch.variant_records),
-                       "l2": "flushed between timed steps (256 MiB write, untimed); outputs (%.2f GB/step) exceed L2" % (out_b / 1e9)},
-            "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_narrow), "steps": e2e_steps,
-                    "mode": "pinned host buffers, batches pipelined 2 deep on 2 streams; integer columns delivered in the width BCF would store "
-                            "them in (int8 / int16 with BCF's sentinels where every value of the field fits, int32 otherwise; glx_download_narrow_on)",
-                    "int32_columns_cells_per_s": cells_all * e2e_steps / e2e_wide_s if world == 1 else None, "int32_d2h_bytes_per_step": int(d2h),
-                    "single_sync_call_cells_per_s": cells / sync_call_s},
+            "config": {"workload": workload_name(args.workload, n_samples, n_sites), "preset": synth_cases.SHAPES[shape][0]},
+            "details": {"cells_per_step_per_gpu": cells, "numa_node": numa, "records_per_step_per_gpu": int(batch.n_records),
+                        "variant_records_per_step_per_gpu": int(batch.variant_records),
+                        "cohort": f"{n_segments} consecutive segments of {n_sites} sites x {n_samples} samples, cut into {world} contiguous site ranges of equal "
+                                  f"output weight (glxh_partition_cohort); this line's rank 0 range = segments/sites {cuts[0]}..{cuts[1]}",
+                        "synthetic_generation_s": gen_s,
+                        "l2": "flushed between timed steps (256 MiB write, untimed); outputs (%.2f GB/step) exceed L2" % (out_b / 1e9),
+                        "value_excludes": "the two upload-side kernels (glx_prepare_inputs_kernel %.3f ms, glx_block_hints_kernel %.3f ms per upload) and three O(records)/O(sites) "
+                                          "host loops of glx_upload_on; e2e includes them" % (up_ms[0], up_ms[1])},
+            "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(head["h2d"] / n_b), "d2h_bytes_per_step": int(head["d2h"] / n_b),
+                    "steps": int(n_b), "cells": head["cells"], "seconds": head["s"],
+                    "mode": "glxh_stream_* (C++ range-batch driver, 3 batches in flight): per range batch H2D of the record store + sites from pinned host memory, all genotyping "
+                            "kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF blocks into pinned host memory; every rank streams its "
+                            "own contiguous site range of one cohort",
+                    "d2h_bytes_per_cell": head["d2h"] / max(1, head["cells"]), "h2d_bytes_per_cell": head["h2d"] / max(1, head["cells"]),
+                    "uncompressed_bcf_bytes_per_cell": head["raw"] / max(1, head["cells"]),
+                    "other_modes": {m: {"cells_per_s": e2e_red[m]["cells"] / e2e_red[m]["s"], "d2h_bytes_per_cell": e2e_red[m]["d2h"] / max(1, e2e_red[m]["cells"])}
+                                    for m in modes[1:]}},
             "gpu_launches": launches,
             "kernels": {"resolve_ms": kmean[0], "tiled_ms": kmean[1], "single_ms": kmean[2], "general_ms": kmean[3], "worklist_cells": int(n_worklist),
-                        "fused_cells": int(n_fused),
-                        "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)},
+                        "fused_cells": int(n_fused), "upload_prepare_ms": up_ms[0], "upload_hints_ms": up_ms[1],
+                        "step_ms_min": min(step_ms), "step_ms_max": max(step_ms), **enc_ms,
+                        "bcf_bytes_per_cell": enc_raw / cells, "bgzf_bytes_per_cell": enc_bytes / cells, "bgzf_blocks": enc_blocks},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_alg,
                          "definition": "SURVEY 8(d): 34 B in per reference-band cell (61 B per variant cell) + output bytes, x the cells this kernel finishes "
@@ -416,6 +481,10 @@ def main():
                                         "frac": alg / (total_ms / args.steps * 1e-3) / 1e9 / peak}},
             "clocks": clocks,
         }
+        if solo is not None:
+            one = solo[1]["cells"] / solo[0]
+            line["e2e"]["one_gpu_same_run_cells_per_s"] = one
+            line["e2e"]["e2e_efficiency"] = e2e_v / (world * one)
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core back
             cb, _ = cpu_baseline(shape, n_samples, region_len / n_sites, n_sites)
@@ -423,8 +492,8 @@ def main():
         else:
             line["cpu_baseline"] = None
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    dev.close()
-    ctx.close()
+    for b in batches:
+        b.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,7 +30,7 @@ class SynthParams(C.Structure):
                 ("frac_multiallelic", C.c_float), ("frac_indel", C.c_float), ("af_max", C.c_float),
                 ("band_mean_len", C.c_float), ("frac_uncovered", C.c_float), ("frac_two_record_cells", C.c_float),
                 ("frac_lost_allele", C.c_float), ("frac_homalt", C.c_float), ("gatk_style", C.c_uint8),
-                ("_pad", C.c_uint8 * 3)]
+                ("sites_only", C.c_uint8), ("_pad", C.c_uint8 * 2)]
 
 
 _lib = None
@@ -52,6 +52,8 @@ def lib():
     L.glxh_synth_batch.restype = C.c_int
     L.glxh_partition_sites.argtypes = [vp, C.c_int, C.POINTER(C.c_uint32)]
     L.glxh_partition_sites.restype = C.c_int
+    L.glxh_partition_cohort.argtypes = [C.POINTER(vp), C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.glxh_partition_cohort.restype = C.c_int
     L.glxh_batch_slice.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), cp, sz]
     L.glxh_batch_slice.restype = C.c_int
     L.glxh_out16_alloc.argtypes = [vp, C.c_int]
@@ -702,6 +704,16 @@ def bgzf_eof():
         return C.string_at(p.value, n.value)
     finally:
         lib().glxh_free_text(p)
+
+
+def partition_cohort(segments, n_parts):
+    """Cut points [(segment, site)] * (n_parts + 1) of equal output weight over a cohort held as consecutive segment batches."""
+    arr = (C.c_void_p * len(segments))(*[b.handle for b in segments])
+    cs, ci = (C.c_uint32 * (n_parts + 1))(), (C.c_uint32 * (n_parts + 1))()
+    rc = lib().glxh_partition_cohort(arr, len(segments), n_parts, cs, ci)
+    if rc != GLX_OK:
+        raise GlxError(rc, "glxh_partition_cohort")
+    return list(zip(cs, ci))
 
 
 def preset_text(name):

@@ -1140,6 +1140,33 @@ void partition_sites(const PackedBatch& b, int n_parts, std::vector<uint32_t>& b
     }
 }
 
+// the same over a cohort held as consecutive segments: cut p = (segment, site within it); cuts[n_parts] = (n_segments, 0)
+void partition_cohort(const std::vector<const PackedBatch*>& segments, int n_parts, std::vector<std::pair<uint32_t, uint32_t>>& cuts) {
+    std::vector<double> seg_w(segments.size() + 1, 0.0);
+    auto site_w = [](const PackedBatch& b, uint32_t s) {
+        double vals = 1.0;
+        for (uint32_t k = 0; k < b.cfg.n_fields; k++) vals += b.fld_cnt[k][s];
+        return vals;
+    };
+    for (size_t g = 0; g < segments.size(); g++) {
+        double w = 0;
+        for (uint32_t s = 0; s < segments[g]->sites.n_sites; s++) w += site_w(*segments[g], s);
+        seg_w[g + 1] = seg_w[g] + w;
+    }
+    cuts.assign(n_parts + 1, {(uint32_t)segments.size(), 0u});
+    cuts[0] = {0u, 0u};
+    for (int p = 1; p < n_parts; p++) {
+        const double target = seg_w.back() * p / n_parts;
+        size_t g = 0;
+        while (g + 1 < segments.size() && seg_w[g + 1] <= target) g++;
+        double acc = seg_w[g];
+        uint32_t s = 0;
+        while (s < segments[g]->sites.n_sites && acc < target) acc += site_w(*segments[g], s++);
+        cuts[p] = {(uint32_t)g, s};
+        if (cuts[p] < cuts[p - 1]) cuts[p] = cuts[p - 1];
+    }
+}
+
 Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, PackedBatch& o) {
     if (site_lo > site_hi || site_hi > b.sites.n_sites) return Status::Invalid("slice_batch: bad site range");
     Status s;

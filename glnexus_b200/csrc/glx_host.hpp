@@ -290,6 +290,7 @@ std::string bgzf_eof_block();
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
 // [site_lo, site_hi) with every record its sites can touch.
 void partition_sites(const PackedBatch& b, int n_parts, std::vector<uint32_t>& bounds);
+void partition_cohort(const std::vector<const PackedBatch*>& segments, int n_parts, std::vector<std::pair<uint32_t, uint32_t>>& cuts);
 Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, PackedBatch& ans);
 
 }  // namespace glx

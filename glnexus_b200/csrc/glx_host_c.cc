@@ -124,6 +124,19 @@ int glxh_partition_sites(const glxh_batch* b, int n_parts, uint32_t* bounds) {
     return GLX_OK;
 }
 
+int glxh_partition_cohort(const glxh_batch* const* segments, uint32_t n_segments, int n_parts, uint32_t* cut_seg, uint32_t* cut_site) {
+    if (!segments || !n_segments || n_parts < 1 || !cut_seg || !cut_site) return GLX_E_INVALID;
+    std::vector<const glx::PackedBatch*> v;
+    for (uint32_t g = 0; g < n_segments; g++) v.push_back(&segments[g]->b);
+    std::vector<std::pair<uint32_t, uint32_t>> cuts;
+    glx::partition_cohort(v, n_parts, cuts);
+    for (int p = 0; p <= n_parts; p++) {
+        cut_seg[p] = cuts[p].first;
+        cut_site[p] = cuts[p].second;
+    }
+    return GLX_OK;
+}
+
 int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, glxh_batch** ans, char* err, size_t errlen) {
     if (!b || !ans) return GLX_E_INVALID;
     auto* o = new glxh_batch();

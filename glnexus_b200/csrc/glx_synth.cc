@@ -389,6 +389,7 @@ extern "C" int glxh_synth_batch(const char* preset, const glxh_synth_params* pp,
     // ---- records, generated per sample on a few threads ----
     unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (p.n_samples < T) T = p.n_samples;
+    if (p.sites_only) T = 0;  // unified sites only: every sample's record list stays empty
     std::vector<RecBuf> bufs(T);
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < T; t++) {
@@ -402,6 +403,12 @@ extern "C" int glxh_synth_batch(const char* preset, const glxh_synth_params* pp,
         });
     }
     for (auto& th : pool) th.join();
+    if (p.sites_only) {
+        bufs.resize(1);
+        bufs[0].ds_count.assign(p.n_samples, 0);
+        bufs[0].cv.resize(n_cols);
+        bufs[0].cl.resize(n_cols);
+    }
 
     size_t R = 0;
     for (auto& rb : bufs) R += rb.beg.size();

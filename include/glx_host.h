@@ -32,6 +32,9 @@ int glxh_batch_from_text(const char* preset, const char* config_text, const char
  * [site_lo, site_hi) with every record its sites' query hulls can touch (records straddling a cut are replicated).
  * The shards' output columns concatenate, in order, to the unsharded batch's. */
 int glxh_partition_sites(const glxh_batch* b, int n_parts, uint32_t* bounds);
+/* The same cut over a cohort held as several consecutive segments (batches of consecutive genomic ranges): cut point p lies in
+ * segment cut_seg[p] at site cut_site[p] of that segment (n_parts + 1 entries each; the last one is {n_segments, 0}). */
+int glxh_partition_cohort(const glxh_batch* const* segments, uint32_t n_segments, int n_parts, uint32_t* cut_seg, uint32_t* cut_site);
 int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, glxh_batch** ans, char* err, size_t errlen);
 /* page-lock the batch's arrays (cudaHostRegister) so uploads run at PCIe rate and can overlap other batches */
 int glxh_batch_pin(glxh_batch* b);
@@ -123,7 +126,8 @@ typedef struct glxh_synth_params {
     float frac_lost_allele;         /* carrier records whose ALT is absent from the unified site */
     float frac_homalt;              /* carriers called hom-ALT (forces revise_genotypes) */
     uint8_t gatk_style;             /* <NON_REF> + SB field, no PL on bands */
-    uint8_t _pad[3];
+    uint8_t sites_only;             /* unified sites without any records (cheap: for partitioning a cohort of several segments) */
+    uint8_t _pad[2];
 } glxh_synth_params;
 int glxh_synth_batch(const char* preset, const glxh_synth_params* p, glxh_batch** ans, char* err, size_t errlen);
 
