@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(GLX_BCF_SPAN_THREADS) glx_bcf_span_raw_kernel(
     const unsigned long long lo = (unsigned long long)blockIdx.x * GLX_BCF_SPAN;
     if (lo >= total) return;
     const unsigned long long hi = min(total, lo + GLX_BCF_SPAN);
-    bcf_fill_span(E, lo, hi, s_buf, s_src, threadIdx.x, blockDim.x);
+    bcf_fill_span<BcfLinear>(E, lo, hi, s_buf, s_src, threadIdx.x, blockDim.x);
     const uint32_t n = (uint32_t)(hi - lo), n16 = n & ~15u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the bulk-copy engine
     __syncthreads();
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(GLX_BCF_SPAN_THREADS) glx_bcf_span_raw_kernel(
 #define GLX_BGZF_THREADS 1024
 #define GLX_BGZF_OUT_PAD ((GLX_BGZF_OUT + 15u) & ~15u)
 struct BgzfSmem {
-    uint8_t in[GLX_BCF_SPAN];
+    uint8_t in[(GLX_BGZF_IN_PAD + 15u) & ~15u];  // BcfPadded layout
     uint8_t out[GLX_BGZF_OUT_PAD];
     BgzfShared sh;
     uint16_t src[GLX_BCF_G_MAX + 8];
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS) glx_bgzf_span_kernel(BcfEnc 
     const uint32_t n = (uint32_t)(hi - lo);
     uint32_t* out_words = reinterpret_cast<uint32_t*>(M.out + GLX_BGZF_LEAD + 18);
     for (uint32_t i = tid; i < GLX_BGZF_OUT_PAD / 4; i += nt) reinterpret_cast<uint32_t*>(M.out)[i] = 0;
-    bcf_fill_span(E, lo, hi, M.in, M.src, tid, nt);
+    bcf_fill_span<BcfPadded>(E, lo, hi, M.in, M.src, tid, nt);
     if (tid == 0) {
         M.sh.n_in = n;
         bgzf_segments(M.sh, E, lo, hi);
@@ -139,17 +139,15 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS) glx_bgzf_span_kernel(BcfEnc 
     bgzf_hist_init(M.sh, tid, nt);
     __syncthreads();
     bgzf_crc_parts(M.sh, M.in, n, tid, nt);
-    bgzf_hist(M.sh, M.in, n, tid, nt);
+    bgzf_tokenize(M.sh, M.in, n, tid, nt);
     __syncthreads();
     for (uint32_t l = 0; l < 10; l++) {
         bgzf_crc_level(M.sh, l, tid, nt);
         __syncthreads();
     }
-    if (tid == 0) {
-        bgzf_crc_finish(M.sh);
-        bgzf_build_codes(M.sh, out_words);
-    }
+    if (tid == 0) bgzf_crc_finish(M.sh);
     __syncthreads();
+    bgzf_build_codes(M.sh, out_words, tid, nt);
     bgzf_count_bits(M.sh, M.in, n, tid, nt);
     __syncthreads();
     {  // exclusive scan of the 1024 bit counts (+ header bits)

@@ -342,6 +342,23 @@ __host__ __device__ inline void bcf_emit_shared(const BcfEnc& E, uint32_t s, uin
     }
 }
 
+struct BcfVec4 {
+    int32_t v[4];
+};
+__host__ __device__ __forceinline__ BcfVec4 bcf_load16i(const int32_t* p) {
+    BcfVec4 r;
+#if defined(__CUDA_ARCH__)
+    const int4 x = __ldg(reinterpret_cast<const int4*>(p));
+    r.v[0] = x.x;
+    r.v[1] = x.y;
+    r.v[2] = x.z;
+    r.v[3] = x.w;
+#else
+    memcpy(&r, p, 16);
+#endif
+    return r;
+}
+
 // ---- stage: scan. One block takes samples [n0, n1) of site s. s_mm = [n_fields][2] block-shared ints. ----
 __host__ __device__ inline void bcf_scan_init(const BcfEnc& E, int32_t* s_mm, uint32_t tid, uint32_t nt) {
     for (uint32_t i = tid; i < E.n_fields; i += nt) {
@@ -387,12 +404,26 @@ __host__ __device__ inline void bcf_scan_accum(const BcfEnc& E, uint32_t s, uint
             }
         } else {
             const size_t e0 = (size_t)n0 * cnt, e1 = (size_t)n1 * cnt;
-            for (size_t e = e0 + tid; e < e1; e += nt) {
-                const int32_t v = base[e];
-                if (v == GLXB_MISSING || v == GLXB_VEND) continue;
+            auto fold = [&](int32_t v) {
+                if (v == GLXB_MISSING || v == GLXB_VEND) return;
                 mn = v < mn ? v : mn;
                 mx = v > mx ? v : mx;
+            };
+            size_t a0 = e0 + ((4 - ((reinterpret_cast<uintptr_t>(base + e0) >> 2) & 3)) & 3);  // first 16-byte aligned element
+            if (a0 > e1) a0 = e1;
+            for (size_t e = e0 + tid; e < a0; e += nt) fold(base[e]);
+            const size_t ng = (e1 - a0) / 4;
+            size_t g = tid;
+            for (; g + nt < ng; g += 2 * (size_t)nt) {  // two 16-byte loads in flight per thread
+                const BcfVec4 x = bcf_load16i(base + a0 + g * 4), y = bcf_load16i(base + a0 + (g + nt) * 4);
+                for (int i = 0; i < 4; i++) fold(x.v[i]);
+                for (int i = 0; i < 4; i++) fold(y.v[i]);
             }
+            if (g < ng) {
+                const BcfVec4 x = bcf_load16i(base + a0 + g * 4);
+                for (int i = 0; i < 4; i++) fold(x.v[i]);
+            }
+            for (size_t e = a0 + ng * 4 + tid; e < e1; e += nt) fold(base[e]);
         }
         bcf_mm_merge(s_mm + 2 * k, mn, mx);
     }
@@ -500,6 +531,75 @@ __host__ __device__ __forceinline__ uint32_t bcf_conv(int32_t v, uint32_t width)
     if (v == GLXB_VEND) return width == 1 ? 0x81u : 0x8001u;
     return (uint32_t)v;
 }
+// where byte i of the span lives in the staging buffer: linear (raw stream), or with 4 bytes of padding after every 64
+// (BGZF stage: its workers walk 64-byte chunks, and a 68-byte stride spreads them over the shared-memory banks)
+struct BcfLinear {
+    static __host__ __device__ __forceinline__ size_t phys(unsigned long long i) { return (size_t)i; }
+};
+struct BcfPadded {
+    static __host__ __device__ __forceinline__ size_t phys(unsigned long long i) { return (size_t)(i + ((i >> 6) << 2)); }
+};
+
+// 16 aligned bytes of global memory as V elements
+template <class T>
+struct BcfVec {
+    T v[16 / sizeof(T)];
+};
+template <class T>
+__host__ __device__ __forceinline__ BcfVec<T> bcf_load16(const T* p) {
+    BcfVec<T> r;
+#if defined(__CUDA_ARCH__)
+    const int4 x = __ldg(reinterpret_cast<const int4*>(p));
+    memcpy(&r, &x, 16);
+#else
+    memcpy(&r, p, 16);
+#endif
+    return r;
+}
+
+// A run of a FORMAT data region: element e of src becomes the OUTW bytes conv(src[e]) at region offsets [e*OUTW, (e+1)*OUTW);
+// only offsets in [c0, c1) are written, to buf[phys(ob + offset)]. Interior elements go 16 source bytes per load, two loads
+// in flight per thread (the pass is bound by memory-level parallelism, not by instructions).
+template <int OUTW, class Addr, class T, class Conv>
+__host__ __device__ inline void bcf_run(const T* __restrict__ src, unsigned long long c0, unsigned long long c1, unsigned long long ob, uint8_t* buf, Conv conv,
+                                        uint32_t tid, uint32_t nt) {
+    constexpr unsigned V = 16 / sizeof(T);
+    auto emit = [&](unsigned long long e, uint32_t x, bool clip) {
+#pragma unroll
+        for (int i = 0; i < OUTW; i++) {
+            const unsigned long long q = e * OUTW + i;
+            if (!clip || (q >= c0 && q < c1)) buf[Addr::phys(ob + q)] = (uint8_t)(x >> (8 * i));
+        }
+    };
+    const unsigned long long e0 = c0 / OUTW, e1 = (c1 + OUTW - 1) / OUTW;  // elements touching [c0, c1)
+    unsigned long long i0 = (c0 + OUTW - 1) / OUTW, i1 = c1 / OUTW;        // elements wholly inside: [i0, i1)
+    // clipped boundary elements (the span starts or ends inside them)
+    const bool first_clipped = e0 < i0, last_clipped = i1 < e1;
+    if (tid == 0 && first_clipped) emit(e0, conv(src[e0]), true);
+    if (tid == (nt > 1 ? 1u : 0u) && last_clipped && !(first_clipped && i1 == e0)) emit(i1, conv(src[i1]), true);
+    if (i1 < i0) i1 = i0;
+    // interior: scalar up to the first 16-byte aligned source element, vectors, scalar tail
+    unsigned long long a0 = i0 + ((V - ((reinterpret_cast<uintptr_t>(src + i0) / sizeof(T)) & (V - 1))) & (V - 1));
+    if (a0 > i1) a0 = i1;
+    for (unsigned long long e = i0 + tid; e < a0; e += nt) emit(e, conv(src[e]), false);
+    const unsigned long long ng = (i1 - a0) / V;
+    unsigned long long g = tid;
+    for (; g + nt < ng; g += 2ull * nt) {
+        const BcfVec<T> x = bcf_load16(src + a0 + g * V), y = bcf_load16(src + a0 + (g + nt) * V);
+#pragma unroll
+        for (unsigned v = 0; v < V; v++) emit(a0 + g * V + v, conv(x.v[v]), false);
+#pragma unroll
+        for (unsigned v = 0; v < V; v++) emit(a0 + (g + nt) * V + v, conv(y.v[v]), false);
+    }
+    if (g < ng) {
+        const BcfVec<T> x = bcf_load16(src + a0 + g * V);
+#pragma unroll
+        for (unsigned v = 0; v < V; v++) emit(a0 + g * V + v, conv(x.v[v]), false);
+    }
+    for (unsigned long long e = a0 + ng * V + tid; e < i1; e += nt) emit(e, conv(src[e]), false);
+}
+
+template <class Addr>
 __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long long lo, unsigned long long hi, uint8_t* buf, uint16_t* s_src, uint32_t tid,
                                               uint32_t nt) {
     const uint32_t N = E.n_samples;
@@ -520,7 +620,7 @@ __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long lon
         unsigned long long c0, c1;
         if (clip(r0, hdr_len, c0, c1)) {
             const uint8_t* src = E.hdr_pool + E.hdr_off[s];
-            for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[r0 + q - lo] = src[q];
+            for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[Addr::phys(r0 + q - lo)] = src[q];
         }
         const unsigned long long ibase = r0 + hdr_len;
         const uint32_t km = P.keep_mask;
@@ -529,21 +629,17 @@ __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long lon
             const uint32_t hl = P.blk_hdr_len[b], cn = P.blk_cnt[b], w = P.blk_width[b];
             if (bstart >= hi) break;
             if (clip(bstart, hl, c0, c1))
-                for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[bstart + q - lo] = P.blk_hdr[b][q];
+                for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[Addr::phys(bstart + q - lo)] = P.blk_hdr[b][q];
             const unsigned long long dstart = bstart + hl, dlen = (unsigned long long)N * cn * w;
             if (!clip(dstart, dlen, c0, c1)) continue;
             const unsigned long long ob = dstart - lo;  // buf index of the block's first data byte (mod 2^64 when it lies before the span:
                                                         // only bytes q in [c0, c1) are touched, for which ob + q is in range)
-#define out(q) buf[(size_t)(ob + (q))]
-            if (b == 0) {  // GT
-                const int8_t* g = E.gt + (size_t)s * N * 2;
-                for (unsigned long long q = c0 + tid; q < c1; q += nt) {
-                    const int a = g[q];
-                    out(q) = a < 0 ? (uint8_t)0 : (uint8_t)((bcf_popc(km & ((1u << a) - 1u)) + 1) << 1);
-                }
+#define out(q) buf[Addr::phys(ob + (q))]
+            if (b == 0) {  // GT: unified allele index -> htslib GT int of the allele's rank among the survivors
+                bcf_run<1, Addr>(E.gt + (size_t)s * N * 2, c0, c1, ob, buf,
+                                 [km](int8_t a) -> uint32_t { return a < 0 ? 0u : (uint32_t)((bcf_popc(km & ((1u << a) - 1u)) + 1) << 1); }, tid, nt);
             } else if (b == (uint32_t)P.n_blk - 1) {  // RNC
-                const uint8_t* r = E.rnc + (size_t)s * N * 2;
-                for (unsigned long long q = c0 + tid; q < c1; q += nt) out(q) = r[q];
+                bcf_run<1, Addr>(E.rnc + (size_t)s * N * 2, c0, c1, ob, buf, [](uint8_t c) -> uint32_t { return c; }, tid, nt);
             } else {
                 const uint32_t k = b - 1, cnt = E.fld_cnt[k][s];
                 const int32_t* __restrict__ base = E.fld[k] + E.fld_off[k][s];
@@ -552,7 +648,7 @@ __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long lon
                         const uint32_t n = (uint32_t)(q / cn), ci = (uint32_t)(q - (unsigned long long)n * cn);
                         out(q) = bcf_ft_char(E.m, (uint32_t)base[(size_t)n * cnt], ci);
                     }
-                } else if (P.trimmed && bcf_is_arg(E.fvl[k]) && E.ftype[k] != GLX_TYPE_STRING) {
+                } else if (P.trimmed && bcf_is_arg(E.fvl[k])) {
                     // trimmed vector: new slot -> source slot table, then per element the "first end-of-vector" rule
                     const uint8_t vl = E.fvl[k];
                     const int32_t vend = E.ftype[k] == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_VECTOR_END_BITS : GLXB_VEND;
@@ -578,18 +674,11 @@ __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long lon
                         }
                     }
                 } else if (w == 1) {
-                    for (unsigned long long q = c0 + tid; q < c1; q += nt) out(q) = (uint8_t)bcf_conv(base[q], 1);
-                } else {
-                    const bool raw = E.ftype[k] == GLX_TYPE_FLOAT;
-                    const unsigned long long e0 = c0 / w, e1 = (c1 + w - 1) / w;
-                    for (unsigned long long e = e0 + tid; e < e1; e += nt) {
-                        const int32_t v = base[e];
-                        const uint32_t x = raw ? (uint32_t)v : bcf_conv(v, w);
-                        for (uint32_t i = 0; i < w; i++) {
-                            const unsigned long long q = e * w + i;
-                            if (q >= c0 && q < c1) out(q) = (uint8_t)(x >> (8 * i));
-                        }
-                    }
+                    bcf_run<1, Addr>(base, c0, c1, ob, buf, [](int32_t v) -> uint32_t { return bcf_conv(v, 1); }, tid, nt);
+                } else if (w == 2) {
+                    bcf_run<2, Addr>(base, c0, c1, ob, buf, [](int32_t v) -> uint32_t { return bcf_conv(v, 2); }, tid, nt);
+                } else {  // int32 and float: raw
+                    bcf_run<4, Addr>(base, c0, c1, ob, buf, [](int32_t v) -> uint32_t { return (uint32_t)v; }, tid, nt);
                 }
             }
 #undef out

@@ -24,6 +24,7 @@ namespace glxd {
 #define GLX_BGZF_SLOT 65536u                    // bytes reserved per block before compaction
 #define GLX_BGZF_LEAD 14u                       // the block starts at byte 14 of its staging buffer, so that the deflate data is word-aligned (14 + 18)
 #define GLX_BGZF_OUT (GLX_BGZF_LEAD + 18u + 5u + GLX_BCF_SPAN + 8u + 16u)
+#define GLX_BGZF_IN_PAD (GLX_BCF_SPAN + (GLX_BCF_SPAN / 64u + 2u) * 4u)  // the span with 4 bytes of padding after every 64 (BcfPadded)
 #define GLX_BGZF_SEG_MAX 512u
 #define GLX_BGZF_LITS 286u
 #define GLX_BGZF_DISTS 30u
@@ -33,8 +34,11 @@ struct BgzfShared {
     uint8_t lit_len[288], dist_len[32];
     uint16_t lit_code[288], dist_code[32];  // bit-reversed canonical codes
     uint32_t wbits[GLX_BGZF_WORKERS];       // CRC parts, then per-worker bit counts -> bit offsets
+    unsigned long long tok[GLX_BGZF_WORKERS];   // bit i: a token starts at byte i of the worker's chunk (literal = 1 byte, match = to the next start)
+    unsigned long long useD[GLX_BGZF_WORKERS];  // bit i: the match starting there copies from the structural distance D, not from distance 1
+    uint16_t hdr_tok[320 + 8];                  // run-length coded code lengths of the block header: symbol | extra value << 5
     uint32_t seg_start[GLX_BGZF_SEG_MAX], seg_dist[GLX_BGZF_SEG_MAX];  // data segments of the span and their "same value, previous record" distance
-    uint32_t n_seg, n_in, hdr_bits, data_bits, crc, stored, block_len;
+    uint32_t n_seg, n_in, hdr_bits, data_bits, crc, stored, block_len, n_hdr_tok, lit_total, dist_total, lit_kraft, dist_kraft;
     uint32_t crc_table[256];
     uint32_t crc_shift[12];  // x^(8 * 64 * 2^l) mod P, l = 0..9; [10] = x^(8 n) mod P for this span
 };
@@ -102,7 +106,7 @@ __host__ __device__ inline void bgzf_crc_parts(BgzfShared& sh, const uint8_t* in
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
         const uint32_t v0 = w * GLX_BGZF_CHUNK, v1 = v0 + GLX_BGZF_CHUNK;
         uint32_t c = 0;
-        for (uint32_t v = v0 < pad ? pad : v0; v < v1; v++) c = sh.crc_table[(c ^ in[v - pad]) & 0xff] ^ (c >> 8);
+        for (uint32_t v = v0 < pad ? pad : v0; v < v1; v++) c = sh.crc_table[(c ^ in[BcfPadded::phys(v - pad)]) & 0xff] ^ (c >> 8);
         sh.wbits[w] = c;
     }
 }
@@ -149,43 +153,159 @@ __host__ __device__ __forceinline__ void bgzf_dist_sym(uint32_t dist, uint32_t& 
     eval = x & ((1u << e) - 1);
 }
 
-// ---- tokenizer: worker chunk [c0, c1) of in[0, n) -> literals and matches at distance 1 or D(position) ----
-template <class F>
-__host__ __device__ inline void bgzf_tokenize(const BgzfShared& sh, const uint8_t* in, uint32_t c0, uint32_t c1, F&& emit) {
-    // segment of c0: last segment with start <= c0
-    uint32_t sg = 0;
-    {
-        uint32_t a = 0, b = sh.n_seg;
-        while (a < b) {
-            const uint32_t mid = (a + b) >> 1;
-            if (sh.seg_start[mid] <= c0) a = mid + 1;
-            else b = mid;
+// ---- tokenizer ----
+__host__ __device__ __forceinline__ uint32_t bgzf_eq_nibble(uint32_t x, uint32_t y) {  // bit b: byte b of x == byte b of y
+    const uint32_t d = x ^ y;
+    const uint32_t z = ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;  // 0x80 in every byte of d that is zero
+    return (z * 0x00204081u) >> 28;
+}
+__host__ __device__ __forceinline__ uint32_t bgzf_run(unsigned long long m, uint32_t i) {  // ones of m from bit i up
+    const unsigned long long z = ~(m >> i);
+    if (z == 0) return 64 - i;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffsll((long long)z) - 1;
+#else
+    return (uint32_t)__builtin_ffsll((long long)z) - 1;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t bgzf_lowbit(unsigned long long m) {  // index of the lowest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffsll((long long)m) - 1;
+#else
+    return (uint32_t)__builtin_ffsll((long long)m) - 1;
+#endif
+}
+
+// Pass 1. Worker w owns bytes [64w, 64w+64) of the span (in = the BcfPadded staging buffer). It finds, per byte, whether the
+// byte repeats the one before it (distance 1) and whether it repeats the byte at the structural distance D of its segment,
+// as two 64-bit masks, then walks them greedily — a D-match of >= 4 bytes that is longer than the distance-1 run, else a
+// distance-1 run of >= 3, else a literal — recording the token starts and counting symbols. Matches end at the chunk's end.
+__host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
+    for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
+        const uint32_t c0 = w * GLX_BGZF_CHUNK;
+        if (c0 >= n) {
+            sh.tok[w] = sh.useD[w] = 0;
+            continue;
         }
-        sg = a;  // number of segments starting at or before c0
+        const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
+        const unsigned long long live = L == 64 ? ~0ull : ((1ull << L) - 1);
+        const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));  // the chunk is contiguous and word-aligned
+        unsigned long long eq1 = 0;
+        uint32_t carry = c0 ? in[BcfPadded::phys(c0 - 1)] : 0u;
+        for (uint32_t k = 0; k < 16; k++) {
+            const uint32_t x = W[k];
+            eq1 |= (unsigned long long)bgzf_eq_nibble(x, (x << 8) | carry) << (4 * k);
+            carry = x >> 24;
+        }
+        if (!c0) eq1 &= ~1ull;  // the span's first byte has no predecessor
+        eq1 &= live;
+        unsigned long long eqD = 0, brk = 0;  // brk: a segment (another D) starts here: a D-match must not run across
+        {  // segments overlapping the chunk: [a, b) with distance D
+            uint32_t lo = 0, hi = sh.n_seg;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sh.seg_start[mid] <= c0) lo = mid + 1;
+                else hi = mid;
+            }
+            uint32_t sg = lo ? lo - 1 : 0;  // segment holding c0 (or the first one)
+            for (; sg < sh.n_seg && sh.seg_start[sg] < c0 + L; sg++) {
+                const uint32_t D = sh.seg_dist[sg];
+                if (sh.seg_start[sg] > c0) brk |= 1ull << (sh.seg_start[sg] - c0);
+                if (D <= 1 || D > 32768) continue;
+                const uint32_t a = sh.seg_start[sg] > c0 ? sh.seg_start[sg] : c0;
+                const uint32_t e = sg + 1 < sh.n_seg && sh.seg_start[sg + 1] < c0 + L ? sh.seg_start[sg + 1] : c0 + L;
+                for (uint32_t i = a < D ? D : a; i < e; i++)
+                    if (in[BcfPadded::phys(i)] == in[BcfPadded::phys(i - D)]) eqD |= 1ull << (i - c0);
+            }
+        }
+        unsigned long long tok = 0, useD = 0;
+        uint32_t i = 0;
+        while (i < L) {
+            const uint32_t r1 = bgzf_run(eq1, i);
+            uint32_t rD = bgzf_run(eqD, i);
+            if (i < 63) {
+                const unsigned long long nb = brk >> (i + 1);
+                if (nb) {
+                    const uint32_t lim = bgzf_lowbit(nb) + 1;
+                    rD = rD < lim ? rD : lim;
+                }
+            }
+            tok |= 1ull << i;
+            if (rD >= 4 && rD > r1) {
+                useD |= 1ull << i;
+                i += rD;
+            } else if (r1 >= 3) {
+                i += r1;
+            } else {
+                bgzf_add(&sh.lit_freq[in[BcfPadded::phys(c0 + i)]], 1);
+                i++;
+            }
+        }
+        sh.tok[w] = tok;
+        sh.useD[w] = useD;
+        // match symbols: second walk over the recorded starts (keeps the first loop short)
+        unsigned long long t = tok;
+        uint32_t sg = 0xffffffffu;
+        while (t) {
+            const uint32_t p = bgzf_lowbit(t);
+            t &= t - 1;
+            const uint32_t q = t ? bgzf_lowbit(t) : L;
+            if (q - p < 3) continue;
+            uint32_t sym, eb, ev;
+            bgzf_len_sym(q - p, sym, eb, ev);
+            bgzf_add(&sh.lit_freq[sym], 1);
+            uint32_t D = 1;
+            if (useD >> p & 1ull) {
+                if (sg == 0xffffffffu) {
+                    uint32_t lo = 0, hi = sh.n_seg;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (sh.seg_start[mid] <= c0 + p) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    sg = lo;
+                } else
+                    while (sg < sh.n_seg && sh.seg_start[sg] <= c0 + p) sg++;
+                D = sh.seg_dist[sg - 1];
+            }
+            bgzf_dist_sym(D, sym, eb, ev);
+            bgzf_add(&sh.dist_freq[sym], 1);
+        }
     }
-    uint32_t i = c0;
-    while (i < c1) {
-        while (sg < sh.n_seg && sh.seg_start[sg] <= i) sg++;
-        const uint32_t D = sg ? sh.seg_dist[sg - 1] : 0;
-        const uint32_t maxlen = c1 - i < 258 ? c1 - i : 258;
-        uint32_t l1 = 0, lD = 0;
-        if (i >= 1) {
-            const uint8_t b = in[i - 1];
-            while (l1 < maxlen && in[i + l1] == b) l1++;
+}
+
+// the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance)
+template <class F>
+__host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t w, F&& emit) {
+    const uint32_t c0 = w * GLX_BGZF_CHUNK;
+    if (c0 >= n) return;
+    const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
+    unsigned long long t = sh.tok[w];
+    const unsigned long long useD = sh.useD[w];
+    uint32_t sg = 0xffffffffu;
+    while (t) {
+        const uint32_t p = bgzf_lowbit(t);
+        t &= t - 1;
+        const uint32_t q = t ? bgzf_lowbit(t) : L;
+        if (q - p < 3) {
+            emit(false, (uint32_t)in[BcfPadded::phys(c0 + p)], 0u);
+            continue;
         }
-        if (D > 1 && D <= i && D <= 32768) {
-            while (lD < maxlen && in[i + lD] == in[i + lD - D]) lD++;
+        uint32_t D = 1;
+        if (useD >> p & 1ull) {
+            if (sg == 0xffffffffu) {
+                uint32_t lo = 0, hi = sh.n_seg;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sh.seg_start[mid] <= c0 + p) lo = mid + 1;
+                    else hi = mid;
+                }
+                sg = lo;
+            } else
+                while (sg < sh.n_seg && sh.seg_start[sg] <= c0 + p) sg++;
+            D = sh.seg_dist[sg - 1];
         }
-        if (lD >= 4 && lD > l1) {
-            emit(true, lD, D);
-            i += lD;
-        } else if (l1 >= 3) {
-            emit(true, l1, 1u);
-            i += l1;
-        } else {
-            emit(false, (uint32_t)in[i], 0u);
-            i++;
-        }
+        emit(true, q - p, D);
     }
 }
 
@@ -193,58 +313,31 @@ __host__ __device__ inline void bgzf_hist_init(BgzfShared& sh, uint32_t tid, uin
     for (uint32_t i = tid; i < 288; i += nt) sh.lit_freq[i] = i == 256 ? 1u : 0u;  // one end-of-block
     for (uint32_t i = tid; i < 32; i += nt) sh.dist_freq[i] = 0;
 }
-__host__ __device__ inline void bgzf_hist(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
-    for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
-        const uint32_t c0 = w * GLX_BGZF_CHUNK, c1 = c0 + GLX_BGZF_CHUNK < n ? c0 + GLX_BGZF_CHUNK : n;
-        if (c0 >= n) continue;
-        bgzf_tokenize(sh, in, c0, c1, [&](bool match, uint32_t v, uint32_t d) {
-            if (!match) bgzf_add(&sh.lit_freq[v], 1);
-            else {
-                uint32_t s, eb, ev;
-                bgzf_len_sym(v, s, eb, ev);
-                bgzf_add(&sh.lit_freq[s], 1);
-                bgzf_dist_sym(d, s, eb, ev);
-                bgzf_add(&sh.dist_freq[s], 1);
-            }
-        });
-    }
-}
 
-// Code lengths <= maxbits forming a COMPLETE prefix code (zlib's inflate rejects incomplete literal/length sets): start from
-// ceil(log2(total / f)), repair the Kraft sum if the clamp at maxbits oversubscribed it, then hand the slack out by
-// shortening symbols until the sum is exactly one. One thread; n <= 288.
-__host__ __device__ inline void bgzf_code_lengths(const uint32_t* freq, uint32_t n, uint32_t maxbits, uint8_t* len) {
-    uint32_t used = 0, last = 0;
-    unsigned long long total = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        len[i] = 0;
-        if (freq[i]) {
-            used++;
-            last = i;
-            total += freq[i];
-        }
-    }
+// ---- Huffman codes. Code lengths <= maxbits forming a COMPLETE prefix code (zlib's inflate rejects incomplete literal/length
+// sets): start from ceil(log2(total / f)) per symbol (parallel), repair the Kraft sum if the clamp at maxbits oversubscribed
+// it, then hand the slack out by shortening symbols until the sum is exactly one (one thread per alphabet). ----
+__host__ __device__ __forceinline__ uint32_t bgzf_len0(uint32_t f, uint32_t total, uint32_t maxbits) {
+    uint32_t l = 1;
+    while (l < maxbits && ((unsigned long long)f << l) < total) l++;
+    return l;
+}
+// serial part for one alphabet: lengths initialised, K = their Kraft sum in units of 2^-maxbits, used = symbols with f > 0
+__host__ __device__ inline void bgzf_len_settle(const uint32_t* freq, uint32_t n, uint32_t maxbits, uint8_t* len, uint32_t K, uint32_t used) {
     if (used == 0) return;
     if (used == 1) {
-        len[last] = 1;
+        for (uint32_t i = 0; i < n; i++)
+            if (freq[i]) len[i] = 1;
         return;
     }
     const uint32_t full = 1u << maxbits;
-    unsigned long long K = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if (!freq[i]) continue;
-        uint32_t l = 1;
-        while (l < maxbits && ((unsigned long long)freq[i] << l) < total) l++;
-        len[i] = (uint8_t)l;
-        K += full >> l;
-    }
     for (uint32_t L = maxbits - 1; K > full && L >= 1; L--)  // oversubscribed: lengthen the longest codes first
         for (uint32_t i = 0; i < n && K > full; i++)
             if (len[i] == L) {
                 len[i]++;
                 K -= full >> (L + 1);
             }
-    unsigned long long slack = full - K;
+    uint32_t slack = full - K;
     while (slack) {  // each pass shortens at least one code of the current maximum length
         for (uint32_t i = 0; i < n && slack; i++) {
             const uint32_t l = len[i];
@@ -255,7 +348,34 @@ __host__ __device__ inline void bgzf_code_lengths(const uint32_t* freq, uint32_t
         }
     }
 }
-// canonical codes, bit-reversed for LSB-first packing. One thread.
+// stand-alone form (the 19-symbol code-length alphabet of the header). One thread.
+__host__ __device__ inline void bgzf_code_lengths(const uint32_t* freq, uint32_t n, uint32_t maxbits, uint8_t* len) {
+    uint32_t used = 0, total = 0, K = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        len[i] = 0;
+        used += freq[i] != 0;
+        total += freq[i];
+    }
+    for (uint32_t i = 0; i < n; i++)
+        if (freq[i]) {
+            len[i] = (uint8_t)bgzf_len0(freq[i], total, maxbits);
+            K += (1u << maxbits) >> len[i];
+        }
+    bgzf_len_settle(freq, n, maxbits, len, K, used);
+}
+__host__ __device__ __forceinline__ uint32_t bgzf_rev(uint32_t v, uint32_t l) {  // low l bits of v, reversed
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - l);
+#else
+    uint32_t r = 0;
+    for (uint32_t b = 0; b < l; b++) {
+        r = r << 1 | (v & 1);
+        v >>= 1;
+    }
+    return r;
+#endif
+}
+// canonical codes, bit-reversed for LSB-first packing. One thread (small alphabets).
 __host__ __device__ inline void bgzf_assign_codes(const uint8_t* len, uint32_t n, uint16_t* code) {
     uint32_t bl_count[16] = {0}, next[16];
     for (uint32_t i = 0; i < n; i++) bl_count[len[i]]++;
@@ -267,16 +387,7 @@ __host__ __device__ inline void bgzf_assign_codes(const uint8_t* len, uint32_t n
     }
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t l = len[i];
-        if (!l) {
-            code[i] = 0;
-            continue;
-        }
-        uint32_t v = next[l]++, r = 0;
-        for (uint32_t b = 0; b < l; b++) {
-            r = r << 1 | (v & 1);
-            v >>= 1;
-        }
-        code[i] = (uint16_t)r;
+        code[i] = l ? (uint16_t)bgzf_rev(next[l]++, l) : (uint16_t)0;
     }
 }
 
@@ -293,59 +404,60 @@ struct BgzfBits {
     }
 };
 
-// Dynamic-block header (BFINAL = 1, BTYPE = 10) from the two length tables. One thread. Returns the header's bit count.
-__host__ __device__ inline uint32_t bgzf_write_header(BgzfShared& sh, uint32_t* out_words) {
+// Dynamic-block header (BFINAL = 1, BTYPE = 10) from the two length tables. One thread. Sets sh.hdr_bits.
+__host__ __device__ inline void bgzf_write_header(BgzfShared& sh, uint32_t* out_words) {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     uint32_t hlit = 286, hdist = 30;
     while (hlit > 257 && sh.lit_len[hlit - 1] == 0) hlit--;
     while (hdist > 1 && sh.dist_len[hdist - 1] == 0) hdist--;
-    // run-length code of the concatenated length sequence: two passes (count, then write)
+    // run-length code of the concatenated length sequence, kept as tokens (symbol | extra value << 5)
     uint32_t cl_freq[19];
     uint8_t cl_len[19];
     uint16_t cl_code[19];
     for (int i = 0; i < 19; i++) cl_freq[i] = 0;
     const uint32_t n_all = hlit + hdist;
-    auto seq = [&](uint32_t i) -> uint32_t { return i < hlit ? sh.lit_len[i] : sh.dist_len[i - hlit]; };
-    auto walk = [&](auto&& sink) {
-        uint32_t i = 0;
-        while (i < n_all) {
-            const uint32_t v = seq(i);
-            uint32_t run = 1;
-            while (i + run < n_all && seq(i + run) == v) run++;
-            if (v == 0) {
-                uint32_t r = run;
-                while (r >= 11) {
-                    const uint32_t t = r > 138 ? 138 : r;
-                    sink(18, t - 11, 7);
-                    r -= t;
-                }
-                if (r >= 3) {
-                    sink(17, r - 3, 3);
-                    r = 0;
-                }
-                while (r--) sink(0, 0, 0);
-            } else {
-                sink(v, 0, 0);
-                uint32_t r = run - 1;
-                while (r >= 3) {
-                    const uint32_t t = r > 6 ? 6 : r;
-                    sink(16, t - 3, 2);
-                    r -= t;
-                }
-                while (r--) sink(v, 0, 0);
-            }
-            i += run;
-        }
+    uint32_t nt = 0;
+    auto sink = [&](uint32_t sym, uint32_t ev) {
+        sh.hdr_tok[nt++] = (uint16_t)(sym | ev << 5);
+        cl_freq[sym]++;
     };
-    walk([&](uint32_t sym, uint32_t, uint32_t) { cl_freq[sym]++; });
+    uint32_t i = 0;
+    while (i < n_all) {
+        const uint32_t v = i < hlit ? sh.lit_len[i] : sh.dist_len[i - hlit];
+        uint32_t run = 1;
+        while (i + run < n_all && (i + run < hlit ? sh.lit_len[i + run] : sh.dist_len[i + run - hlit]) == v) run++;
+        i += run;
+        if (v == 0) {
+            while (run >= 11) {
+                const uint32_t t = run > 138 ? 138 : run;
+                sink(18, t - 11);
+                run -= t;
+            }
+            if (run >= 3) {
+                sink(17, run - 3);
+                run = 0;
+            }
+            while (run--) sink(0, 0);
+        } else {
+            sink(v, 0);
+            run--;
+            while (run >= 3) {
+                const uint32_t t = run > 6 ? 6 : run;
+                sink(16, t - 3);
+                run -= t;
+            }
+            while (run--) sink(v, 0);
+        }
+    }
+    sh.n_hdr_tok = nt;
     bgzf_code_lengths(cl_freq, 19, 7, cl_len);
     {
         uint32_t used = 0;
-        for (int i = 0; i < 19; i++) used += cl_len[i] != 0;
+        for (int k = 0; k < 19; k++) used += cl_len[k] != 0;
         if (used == 1) {  // a lone code-length symbol needs a partner for the code to be complete
-            for (int i = 0; i < 19; i++)
-                if (!cl_len[i]) {
-                    cl_len[i] = 1;
+            for (int k = 0; k < 19; k++)
+                if (!cl_len[k]) {
+                    cl_len[k] = 1;
                     break;
                 }
         }
@@ -359,44 +471,98 @@ __host__ __device__ inline uint32_t bgzf_write_header(BgzfShared& sh, uint32_t* 
     bw.put(hlit - 257, 5);
     bw.put(hdist - 1, 5);
     bw.put(hclen - 4, 4);
-    for (uint32_t i = 0; i < hclen; i++) bw.put(cl_len[order[i]], 3);
-    walk([&](uint32_t sym, uint32_t ev, uint32_t eb) {
+    for (uint32_t k = 0; k < hclen; k++) bw.put(cl_len[order[k]], 3);
+    for (uint32_t k = 0; k < nt; k++) {
+        const uint32_t sym = sh.hdr_tok[k] & 31u, ev = sh.hdr_tok[k] >> 5;
         bw.put(cl_code[sym], cl_len[sym]);
-        bw.put(ev, eb);
-    });
-    return bw.pos;
+        bw.put(ev, sym == 16 ? 2u : (sym == 17 ? 3u : (sym == 18 ? 7u : 0u)));
+    }
+    sh.hdr_bits = bw.pos;
 }
 
-// one thread: both Huffman codes + the header. out_words = word-aligned start of the deflate data (zeroed)
-__host__ __device__ inline void bgzf_build_codes(BgzfShared& sh, uint32_t* out_words) {
-    bgzf_code_lengths(sh.lit_freq, GLX_BGZF_LITS, 15, sh.lit_len);
-    bgzf_code_lengths(sh.dist_freq, GLX_BGZF_DISTS, 15, sh.dist_len);
-    {
-        uint32_t used = 0;
-        for (uint32_t i = 0; i < GLX_BGZF_DISTS; i++) used += sh.dist_len[i] != 0;
-        if (used == 0) sh.dist_len[0] = 1;  // "one distance code of one bit" keeps every inflater happy
+// Both Huffman codes and the block header, by the whole block (every thread calls it). out_words = word-aligned, zeroed
+// start of the deflate data.
+__host__ __device__ inline void bgzf_build_codes(BgzfShared& sh, uint32_t* out_words, uint32_t tid, uint32_t nt) {
+    uint32_t* cnt = sh.wbits;  // scratch: [0..16) literal/length code-length counts, [16..32) distance, [32..34) used symbols
+    for (uint32_t i = tid; i < 40; i += nt) cnt[i] = 0;
+    if (tid == 0) sh.lit_total = sh.dist_total = sh.lit_kraft = sh.dist_kraft = 0;
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < 288 + 32; i += nt) {
+        const bool lit = i < 288;
+        const uint32_t f = lit ? (i < GLX_BGZF_LITS ? sh.lit_freq[i] : 0u) : (i - 288 < GLX_BGZF_DISTS ? sh.dist_freq[i - 288] : 0u);
+        if (f) {
+            bgzf_add(lit ? &sh.lit_total : &sh.dist_total, f);
+            bgzf_add(&cnt[lit ? 32 : 33], 1);
+        }
     }
-    bgzf_assign_codes(sh.lit_len, GLX_BGZF_LITS, sh.lit_code);
-    bgzf_assign_codes(sh.dist_len, GLX_BGZF_DISTS, sh.dist_code);
-    sh.hdr_bits = bgzf_write_header(sh, out_words);
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < 288 + 32; i += nt) {
+        const bool lit = i < 288;
+        const uint32_t j = lit ? i : i - 288;
+        const uint32_t f = lit ? (j < GLX_BGZF_LITS ? sh.lit_freq[j] : 0u) : (j < GLX_BGZF_DISTS ? sh.dist_freq[j] : 0u);
+        uint32_t l = 0;
+        if (f) {
+            l = bgzf_len0(f, lit ? sh.lit_total : sh.dist_total, 15);
+            bgzf_add(lit ? &sh.lit_kraft : &sh.dist_kraft, 32768u >> l);
+        }
+        (lit ? sh.lit_len : sh.dist_len)[j] = (uint8_t)l;
+    }
+    GLX_BLOCK_SYNC();
+    // the two serial settles run side by side on two warps
+    if (tid == 0) bgzf_len_settle(sh.lit_freq, GLX_BGZF_LITS, 15, sh.lit_len, sh.lit_kraft, cnt[32]);
+    if (tid == (nt > 32 ? 32u : 0u)) {
+        bgzf_len_settle(sh.dist_freq, GLX_BGZF_DISTS, 15, sh.dist_len, sh.dist_kraft, cnt[33]);
+        if (cnt[33] == 0) sh.dist_len[0] = 1;  // "one distance code of one bit" keeps every inflater happy
+    }
+    GLX_BLOCK_SYNC();
+    // canonical codes: count per length, first code per length, then code = first + rank among earlier symbols of that length
+    for (uint32_t i = tid; i < 288 + 32; i += nt) {
+        const bool lit = i < 288;
+        const uint32_t l = lit ? sh.lit_len[i] : sh.dist_len[i - 288];
+        if (l) bgzf_add(&cnt[(lit ? 0 : 16) + l], 1);
+    }
+    GLX_BLOCK_SYNC();
+    if (tid == 0 || tid == (nt > 32 ? 32u : 0u)) {
+        for (uint32_t a = 0; a < 2; a++) {
+            if (nt > 32 && a != (tid ? 1u : 0u)) continue;
+            uint32_t* c = cnt + 16 * a;
+            uint32_t code = 0, prev = 0;
+            for (uint32_t b = 1; b < 16; b++) {  // c[b]: count -> first code of length b
+                code = (code + prev) << 1;
+                prev = c[b];
+                c[b] = code;
+            }
+        }
+    }
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < 288 + 32; i += nt) {
+        const bool lit = i < 288;
+        const uint32_t j = lit ? i : i - 288;
+        const uint8_t* len = lit ? sh.lit_len : sh.dist_len;
+        const uint32_t l = len[j];
+        uint32_t rank = 0;
+        for (uint32_t e = 0; e < j; e++) rank += len[e] == l;
+        (lit ? sh.lit_code : sh.dist_code)[j] = l ? (uint16_t)bgzf_rev(cnt[(lit ? 0 : 16) + l] + rank, l) : (uint16_t)0;
+    }
+    GLX_BLOCK_SYNC();
+    if (tid == 0) bgzf_write_header(sh, out_words);
+    GLX_BLOCK_SYNC();
 }
 
 // per-worker bit counts
 __host__ __device__ inline void bgzf_count_bits(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
-        const uint32_t c0 = w * GLX_BGZF_CHUNK, c1 = c0 + GLX_BGZF_CHUNK < n ? c0 + GLX_BGZF_CHUNK : n;
         uint32_t bits = 0;
-        if (c0 < n)
-            bgzf_tokenize(sh, in, c0, c1, [&](bool match, uint32_t v, uint32_t d) {
-                if (!match) bits += sh.lit_len[v];
-                else {
-                    uint32_t s, eb, ev;
-                    bgzf_len_sym(v, s, eb, ev);
-                    bits += sh.lit_len[s] + eb;
-                    bgzf_dist_sym(d, s, eb, ev);
-                    bits += sh.dist_len[s] + eb;
-                }
-            });
+        bgzf_replay(sh, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
+            if (!match) bits += sh.lit_len[v];
+            else {
+                uint32_t s, eb, ev;
+                bgzf_len_sym(v, s, eb, ev);
+                bits += sh.lit_len[s] + eb;
+                bgzf_dist_sym(d, s, eb, ev);
+                bits += sh.dist_len[s] + eb;
+            }
+        });
         sh.wbits[w] = bits;
     }
 }
@@ -413,12 +579,11 @@ __host__ __device__ inline void bgzf_scan_bits_serial(BgzfShared& sh) {
 // each worker writes its codes at its bit offset: interior words are its own (plain stores), the two boundary words are shared
 __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t* out_words, uint32_t tid, uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
-        const uint32_t c0 = w * GLX_BGZF_CHUNK, c1 = c0 + GLX_BGZF_CHUNK < n ? c0 + GLX_BGZF_CHUNK : n;
-        if (c0 >= n) continue;
-        uint32_t pos = sh.wbits[w];
+        if (w * GLX_BGZF_CHUNK >= n) continue;
+        const uint32_t pos = sh.wbits[w];
         uint32_t word = pos >> 5;
         unsigned long long acc = 0;
-        uint32_t fill = pos & 31;  // bits of `acc` already spoken for (the low `fill` bits belong to the previous worker)
+        uint32_t fill = pos & 31;  // the low `fill` bits of the first word belong to the previous worker
         bool first = true;
         auto put = [&](uint32_t v, uint32_t nb) {
             acc |= (unsigned long long)v << fill;
@@ -432,7 +597,7 @@ __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const uint8_t* in, uin
                 fill -= 32;
             }
         };
-        bgzf_tokenize(sh, in, c0, c1, [&](bool match, uint32_t v, uint32_t d) {
+        bgzf_replay(sh, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
             if (!match) put(sh.lit_code[v], sh.lit_len[v]);
             else {
                 uint32_t s, eb, ev;
@@ -473,7 +638,7 @@ __host__ __device__ inline void bgzf_store_raw(const BgzfShared& sh, const uint8
     uint8_t* d = stage + GLX_BGZF_LEAD + 18;
     const uint32_t n = sh.n_in;
     for (uint32_t i = tid; i < 5; i += nt) d[i] = i == 0 ? 1 : (i == 1 ? (uint8_t)(n & 0xff) : (i == 2 ? (uint8_t)(n >> 8) : (i == 3 ? (uint8_t)(~n & 0xff) : (uint8_t)((~n >> 8) & 0xff))));
-    for (uint32_t i = tid; i < n; i += nt) d[5 + i] = in[i];
+    for (uint32_t i = tid; i < n; i += nt) d[5 + i] = in[BcfPadded::phys(i)];
 }
 
 // "same value at the previous record" distances of the span's FORMAT data segments (one thread). Segment starts are

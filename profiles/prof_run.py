@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Minimal launcher for ncu captures: build one synthetic batch of a BASELINE shape, upload it once and run the hot path
-`launches` times on the context stream. Usage: prof_run.py <c2|c3|c4|c5> [launches] [samples] [sites]"""
+`launches` times on the context stream. Usage: prof_run.py <c2|c3|c4|c5> [launches] [samples] [sites] [encoder mode]"""
 import os
 import sys
 
@@ -25,9 +25,15 @@ def main():
     b = synth_cases.make(w, n_samples=ns, n_sites=nsites, region_len=region)
     ctx = Context(0)
     dev = ctx.upload(b)
+    enc = int(sys.argv[5]) if len(sys.argv) > 5 else -1  # -1: hot path only; 0 / 1: also the BCF encoder (raw records / BGZF)
     for _ in range(n):
         dev.launch()
     dev.check()
+    if enc >= 0:
+        dev.bcf_attach(b)
+        for _ in range(n):
+            dev.encode_bcf(enc)
+        print("encoded bytes, raw bytes, blocks:", dev.bcf_length())
     print(f"{w}: {b.n_sites} sites x {b.n_samples} samples, {b.n_records} records, {dev.launch_count} kernels per launch")
     dev.close()
     ctx.close()

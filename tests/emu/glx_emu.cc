@@ -378,7 +378,7 @@ extern "C" int glx_emu_bcf_records(const glx_config* cfg, const glx_sites* sites
     std::vector<uint16_t> s_src(GLX_BCF_G_MAX + 8);
     if (span == 0) span = GLX_BCF_SPAN;
     for (unsigned long long lo = 0; lo < X.total; lo += span)
-        bcf_fill_span(X.E, lo, std::min<unsigned long long>(X.total, lo + span), o + lo, s_src.data(), 0, 1);
+        bcf_fill_span<BcfLinear>(X.E, lo, std::min<unsigned long long>(X.total, lo + span), o + lo, s_src.data(), 0, 1);
     for (uint32_t s = 0; s <= sites->n_sites; s++) rec_off[s] = X.roff[s];
     *bytes = o;
     *n_bytes = X.total;
@@ -392,7 +392,7 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
     EmuBcf X(cfg, sites, meta, out, 0);
     if (span == 0 || span > GLX_BCF_SPAN) span = GLX_BCF_SPAN;
     std::vector<uint8_t> all;
-    std::vector<uint8_t> in(GLX_BCF_SPAN + 16);
+    std::vector<uint8_t> in(GLX_BGZF_IN_PAD + 64);
     std::vector<uint32_t> stage_w((GLX_BGZF_OUT + 64) / 4);
     std::vector<uint16_t> s_src(GLX_BCF_G_MAX + 8);
     auto sh = std::make_unique<BgzfShared>();
@@ -403,16 +403,16 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
         std::fill(stage_w.begin(), stage_w.end(), 0u);
         uint8_t* stage = reinterpret_cast<uint8_t*>(stage_w.data());
         uint32_t* out_words = reinterpret_cast<uint32_t*>(stage + GLX_BGZF_LEAD + 18);
-        bcf_fill_span(X.E, lo, hi, in.data(), s_src.data(), 0, 1);
+        bcf_fill_span<BcfPadded>(X.E, lo, hi, in.data(), s_src.data(), 0, 1);
         sh->n_in = n;
         bgzf_segments(*sh, X.E, lo, hi);
         bgzf_crc_setup(*sh, n, 0, 1);
         bgzf_hist_init(*sh, 0, 1);
         bgzf_crc_parts(*sh, in.data(), n, 0, 1);
-        bgzf_hist(*sh, in.data(), n, 0, 1);
+        bgzf_tokenize(*sh, in.data(), n, 0, 1);
         for (uint32_t l = 0; l < 10; l++) bgzf_crc_level(*sh, l, 0, 1);
         bgzf_crc_finish(*sh);
-        bgzf_build_codes(*sh, out_words);
+        bgzf_build_codes(*sh, out_words, 0, 1);
         bgzf_count_bits(*sh, in.data(), n, 0, 1);
         bgzf_scan_bits_serial(*sh);
         bgzf_emit(*sh, in.data(), n, out_words, 0, 1);
