@@ -182,6 +182,8 @@ def lib():
     L.glx_download_bcf_on.restype = C.c_int
     L.glx_bcf_record_offsets.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.glx_bcf_record_offsets.restype = C.c_int
+    L.glx_debug_bgzf_phases.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.glx_debug_bgzf_phases.restype = C.c_int
     L.glx_bcf_bound.argtypes = [vp]
     L.glx_bcf_bound.restype = C.c_uint64
     L.glx_pinned_alloc.argtypes = [sz]
@@ -551,6 +553,11 @@ class Context:
         """Parity tests: 'sig' (default kernels), 'sig-unfused', 'dynamic' (dynamic tiled kernel), 'general' (general kernel alone)."""
         for k in ("no_fuse", "no_resolve_sig", "force_dynamic_tiled", "force_general"):
             self.set_option(k, self.PATHS[path].get(k, 0))
+
+    def bgzf_phase_cycles(self):
+        out = (C.c_uint64 * 16)()
+        self._check(lib().glx_debug_bgzf_phases(self.handle, out))
+        return [int(x) for x in out]
 
     def selftest_diploid(self, n_allele):
         """[(alleles_gt(i,j), alleles_gt(j,i))] in genotype order, from the device's index math."""

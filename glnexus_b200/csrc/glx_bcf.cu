@@ -85,38 +85,94 @@ __global__ void __launch_bounds__(128) glx_bcf_headers_kernel(BcfEnc E) {
     if (s < E.n_sites) bcf_header_site(E, s);
 }
 
+// first site of every span (thread per span), so that a span's block starts with one load instead of a binary search
+__global__ void __launch_bounds__(256) glx_bcf_span_index_kernel(BcfEnc E, uint32_t* __restrict__ span_site, uint32_t n_spans) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_spans) return;
+    const unsigned long long lo = (unsigned long long)b * GLX_BCF_SPAN;
+    span_site[b] = lo < E.rec_off[E.n_sites] ? bcf_first_site(E, lo) : E.n_sites;
+}
+
 // One CTA per 65,280-byte span of the record stream: gather it in shared memory, then one bulk (TMA) store.
-#define GLX_BCF_SPAN_THREADS 256
-__global__ void __launch_bounds__(GLX_BCF_SPAN_THREADS) glx_bcf_span_raw_kernel(BcfEnc E, uint8_t* __restrict__ out) {
-    extern __shared__ __align__(128) uint8_t s_buf[];  // [GLX_BCF_SPAN] span bytes, then the slot table
-    uint16_t* s_src = reinterpret_cast<uint16_t*>(s_buf + GLX_BCF_SPAN);
+#define GLX_BCF_SPAN_THREADS 512
+struct RawSmem {
+    uint8_t buf[GLX_BCF_SPAN];
+    BcfSpanTab tab;
+};
+__global__ void __launch_bounds__(GLX_BCF_SPAN_THREADS, 3) glx_bcf_span_raw_kernel(BcfEnc E, const uint32_t* __restrict__ span_site, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    RawSmem& M = *reinterpret_cast<RawSmem*>(s_raw);
     const unsigned long long total = E.rec_off[E.n_sites];
     const unsigned long long lo = (unsigned long long)blockIdx.x * GLX_BCF_SPAN;
     if (lo >= total) return;
     const unsigned long long hi = min(total, lo + GLX_BCF_SPAN);
-    bcf_fill_span<BcfLinear>(E, lo, hi, s_buf, s_src, threadIdx.x, blockDim.x);
+    bcf_fill_span<BcfLinear>(E, lo, hi, span_site[blockIdx.x], M.buf, M.tab, threadIdx.x, blockDim.x);
     const uint32_t n = (uint32_t)(hi - lo), n16 = n & ~15u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the bulk-copy engine
     __syncthreads();
     if (threadIdx.x == 0 && n16) {
-        const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_buf);
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(M.buf);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + lo), "r"(src), "r"(n16) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the source may be released once it has been read
     }
-    for (uint32_t i = n16 + threadIdx.x; i < n; i += blockDim.x) out[lo + i] = s_buf[i];  // tail of the stream's last span
+    for (uint32_t i = n16 + threadIdx.x; i < n; i += blockDim.x) out[lo + i] = M.buf[i];  // tail of the stream's last span
 }
 
-// One CTA per span: gather the span, CRC-32, DEFLATE and BGZF framing in shared memory, one bulk store into the block's slot.
+// Phase clock of the BGZF kernel (thread 0 of every block; a dozen clock reads and atomics per 64 KB block): where a block's
+// time goes, for profiles/ — glx_debug_bgzf_phases.
+__device__ unsigned long long glx_bgzf_phase_cycles[16];
+#define GLX_PHASE(i)                                                                    \
+    do {                                                                                \
+        if (tid == 0) {                                                                 \
+            const long long now_ = clock64();                                           \
+            atomicAdd(&glx_bgzf_phase_cycles[i], (unsigned long long)(now_ - t_phase)); \
+            t_phase = now_;                                                             \
+        }                                                                               \
+    } while (0)
+
 #define GLX_BGZF_THREADS 1024
 #define GLX_BGZF_OUT_PAD ((GLX_BGZF_OUT + 15u) & ~15u)
 struct BgzfSmem {
     uint8_t in[(GLX_BGZF_IN_PAD + 15u) & ~15u];  // BcfPadded layout
     uint8_t out[GLX_BGZF_OUT_PAD];
     BgzfShared sh;
-    uint16_t src[GLX_BCF_G_MAX + 8];
+    BcfSpanTab tab;
 };
-__global__ void __launch_bounds__(GLX_BGZF_THREADS) glx_bgzf_span_kernel(BcfEnc E, uint8_t* __restrict__ slots, uint32_t* __restrict__ sizes) {
+struct BgzfSampleSmem {
+    uint8_t in[(GLX_BGZF_IN_PAD + 15u) & ~15u];
+    BgzfShared sh;
+    BcfSpanTab tab;
+};
+
+// Sampling: GLX_BGZF_SAMPLES spans spread over the stream are gathered and tokenized; their symbol counts go to hist[320].
+__global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_sample_kernel(BcfEnc E, const uint32_t* __restrict__ span_site, uint32_t* __restrict__ hist) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    BgzfSampleSmem& M = *reinterpret_cast<BgzfSampleSmem*>(s_raw);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const unsigned long long total = E.rec_off[E.n_sites];
+    const unsigned long long n_spans = (total + GLX_BCF_SPAN - 1) / GLX_BCF_SPAN;
+    if (blockIdx.x >= n_spans) return;
+    const unsigned long long b = n_spans <= gridDim.x ? blockIdx.x : (unsigned long long)blockIdx.x * n_spans / gridDim.x;
+    const unsigned long long lo = b * GLX_BCF_SPAN, hi = min(total, lo + GLX_BCF_SPAN);
+    const uint32_t n = (uint32_t)(hi - lo);
+    for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt) M.sh.freq[i] = 0;
+    bcf_fill_span<BcfPadded>(E, lo, hi, span_site[b], M.in, M.tab, tid, nt);
+    bgzf_tokenize<true, false>(M.sh, M.tab, M.in, n, tid, nt);
+    __syncthreads();
+    for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt)
+        if (M.sh.freq[i]) atomicAdd(&hist[i], M.sh.freq[i]);
+}
+
+__global__ void glx_bgzf_table_kernel(const uint32_t* __restrict__ hist, BgzfTable* __restrict__ tab) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) bgzf_table_build(hist, *tab);
+}
+
+// One CTA per span: gather the span, CRC-32, DEFLATE under the batch's code and BGZF framing in shared memory, one bulk store
+// into the block's slot.
+__global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_span_kernel(BcfEnc E, const uint32_t* __restrict__ span_site, const BgzfTable* __restrict__ gtab,
+                                                                         const uint32_t* __restrict__ crc_pw, uint8_t* __restrict__ slots,
+                                                                         uint32_t* __restrict__ sizes) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     BgzfSmem& M = *reinterpret_cast<BgzfSmem*>(s_raw);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -129,43 +185,48 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS) glx_bgzf_span_kernel(BcfEnc 
     const unsigned long long hi = min(total, lo + GLX_BCF_SPAN);
     const uint32_t n = (uint32_t)(hi - lo);
     uint32_t* out_words = reinterpret_cast<uint32_t*>(M.out + GLX_BGZF_LEAD + 18);
+    long long t_phase = clock64();
     for (uint32_t i = tid; i < GLX_BGZF_OUT_PAD / 4; i += nt) reinterpret_cast<uint32_t*>(M.out)[i] = 0;
-    bcf_fill_span<BcfPadded>(E, lo, hi, M.in, M.src, tid, nt);
-    if (tid == 0) {
-        M.sh.n_in = n;
-        bgzf_segments(M.sh, E, lo, hi);
-    }
-    bgzf_crc_setup(M.sh, n, tid, nt);
-    bgzf_hist_init(M.sh, tid, nt);
+    for (uint32_t i = tid; i < sizeof(BgzfTable) / 4; i += nt) reinterpret_cast<uint32_t*>(&M.sh.tab)[i] = reinterpret_cast<const uint32_t*>(gtab)[i];
+    if (tid == 0) M.sh.n_in = n;
+    bgzf_crc_setup(M.sh, tid, nt);
+    bcf_fill_span<BcfPadded>(E, lo, hi, span_site[blockIdx.x], M.in, M.tab, tid, nt);  // ends with a barrier
+    GLX_PHASE(0);
+    bgzf_put_header(M.sh, out_words, tid, nt);
+    bgzf_crc_parts(M.sh, crc_pw, M.in, n, tid, nt);
+    GLX_PHASE(3);
+    bgzf_tokenize<false, true>(M.sh, M.tab, M.in, n, tid, nt);
     __syncthreads();
-    bgzf_crc_parts(M.sh, M.in, n, tid, nt);
-    bgzf_tokenize(M.sh, M.in, n, tid, nt);
-    __syncthreads();
-    for (uint32_t l = 0; l < 10; l++) {
-        bgzf_crc_level(M.sh, l, tid, nt);
-        __syncthreads();
-    }
-    if (tid == 0) bgzf_crc_finish(M.sh);
-    __syncthreads();
-    bgzf_build_codes(M.sh, out_words, tid, nt);
-    bgzf_count_bits(M.sh, M.in, n, tid, nt);
-    __syncthreads();
-    {  // exclusive scan of the 1024 bit counts (+ header bits)
+    GLX_PHASE(4);
+    if (tid == 0) bgzf_crc_finish(M.sh, crc_pw);
+    {  // exclusive scan of the 1024 bit counts (+ header bits): warp scans, then the 32 warp totals
+        __shared__ uint32_t s_wsum[32];
         const uint32_t mine = M.sh.wbits[tid];
-        for (uint32_t d = 1; d < GLX_BGZF_WORKERS; d <<= 1) {
-            const uint32_t a = tid >= d ? M.sh.wbits[tid - d] : 0;
-            __syncthreads();
-            M.sh.wbits[tid] += a;
-            __syncthreads();
+        uint32_t incl = mine;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += a;
         }
-        const uint32_t incl = M.sh.wbits[tid];
+        if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
         __syncthreads();
-        M.sh.wbits[tid] = incl - mine + M.sh.hdr_bits;
-        if (tid == GLX_BGZF_WORKERS - 1) M.sh.data_bits = incl + M.sh.hdr_bits;
+        if (tid < 32) {
+            uint32_t v = s_wsum[tid];
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, v, d);
+                if (tid >= d) v += a;
+            }
+            s_wsum[tid] = v;
+        }
+        __syncthreads();
+        const uint32_t base = (tid >> 5) ? s_wsum[(tid >> 5) - 1] : 0u;
+        M.sh.wbits[tid] = base + incl - mine + M.sh.tab.hdr_bits;
+        if (tid == GLX_BGZF_WORKERS - 1) M.sh.data_bits = base + incl + M.sh.tab.hdr_bits;
     }
     __syncthreads();
-    bgzf_emit(M.sh, M.in, n, out_words, tid, nt);
+    GLX_PHASE(7);
+    bgzf_emit(M.sh, M.tab, M.in, n, out_words, tid, nt);
     __syncthreads();
+    GLX_PHASE(8);
     if (tid == 0) bgzf_finish_deflate(M.sh, out_words);
     __syncthreads();
     if (M.sh.stored) {
@@ -184,6 +245,7 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS) glx_bgzf_span_kernel(BcfEnc 
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         sizes[blockIdx.x] = M.sh.block_len;
     }
+    GLX_PHASE(9);
 }
 
 // exclusive scan of the block sizes (one block); totals[2] = BGZF bytes, totals[3] = blocks with data
@@ -243,16 +305,19 @@ __global__ void __launch_bounds__(256) glx_bgzf_pack_kernel(const uint8_t* __res
     for (uint32_t i = head + nw * 4 + threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
 }
 
-static int glx_bgzf_launch(glx_ctx* ctx, const BcfEnc& E, uint8_t* slots, uint8_t* packed, unsigned long long* totals, uint32_t* sizes,
-                           unsigned long long* offsets, uint32_t n_spans, cudaStream_t st) {
+static int glx_bgzf_launch(glx_ctx* ctx, const BcfEnc& E, const uint32_t* span_site, GlxBcfState& B, uint32_t n_spans, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(glx_bgzf_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSmem)));
+        CU(cudaFuncSetAttribute(glx_bgzf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSampleSmem)));
         attr_set = true;
     }
-    glx_bgzf_span_kernel<<<n_spans, GLX_BGZF_THREADS, sizeof(BgzfSmem), st>>>(E, slots, sizes);
-    glx_bgzf_offsets_kernel<<<1, 1024, 0, st>>>(sizes, n_spans, offsets, totals);
-    glx_bgzf_pack_kernel<<<n_spans, 256, 0, st>>>(slots, sizes, offsets, packed);
+    CU(cudaMemsetAsync(B.hist, 0, GLX_BGZF_HIST * 4, st));
+    glx_bgzf_sample_kernel<<<std::min<uint32_t>(n_spans, GLX_BGZF_SAMPLES), GLX_BGZF_THREADS, sizeof(BgzfSampleSmem), st>>>(E, span_site, B.hist);
+    glx_bgzf_table_kernel<<<1, 32, 0, st>>>(B.hist, B.table);
+    glx_bgzf_span_kernel<<<n_spans, GLX_BGZF_THREADS, sizeof(BgzfSmem), st>>>(E, span_site, B.table, ctx->crc_pw, B.stream, B.blk_sizes);
+    glx_bgzf_offsets_kernel<<<1, 1024, 0, st>>>(B.blk_sizes, n_spans, B.blk_offsets, B.totals);
+    glx_bgzf_pack_kernel<<<n_spans, 256, 0, st>>>(B.stream, B.blk_sizes, B.blk_offsets, B.packed);
     CU(cudaGetLastError());
     return GLX_OK;
 }
@@ -353,7 +418,7 @@ int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* d, const glx_sites* sites, const
     // ---- working arena ----
     const size_t n_spans_b = (size_t)((B.stream_bound + GLX_BCF_SPAN - 1) / GLX_BCF_SPAN) + 1;
     const size_t wb = 256 + pad256(S * F * 8 + 16) + pad256((S + 1) * sizeof(BcfSitePlan)) + 2 * pad256((S + 1) * 8) + pad256(hdr_bound + 16) + pad256(64) +
-                      pad256(n_spans_b * 4) + pad256(n_spans_b * 8);
+                      2 * pad256(n_spans_b * 4) + pad256(n_spans_b * 8) + pad256(GLX_BGZF_HIST * 4) + pad256(sizeof(BgzfTable));
     if (!B.work_base || B.work_bytes < wb) {
         if (B.work_base) ctx->give(B.work_base, B.work_bytes);
         B.work_base = nullptr;
@@ -370,6 +435,15 @@ int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* d, const glx_sites* sites, const
     B.totals = wa.take<unsigned long long>(8);
     B.blk_sizes = wa.take<uint32_t>(n_spans_b);
     B.blk_offsets = wa.take<unsigned long long>(n_spans_b);
+    B.span_site = wa.take<uint32_t>(n_spans_b);
+    B.hist = wa.take<uint32_t>(GLX_BGZF_HIST);
+    B.table = wa.take<BgzfTable>(1);
+    if (!ctx->crc_pw) {  // the 1,025 CRC powers, once per context
+        std::vector<uint32_t> pw(GLX_BGZF_WORKERS + 1);
+        bgzf_crc_powers(pw.data());
+        CU(cudaMalloc((void**)&ctx->crc_pw, pw.size() * 4));
+        CU(cudaMemcpy(ctx->crc_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
+    }
     // the batch's own device arrays
     E.beg = d->S.beg;
     E.n_allele = d->S.n_allele;
@@ -429,17 +503,18 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
     if (S && N) {
         glx_bcf_offsets_kernel<<<1, GLX_BCF_SCAN_THREADS, 0, st>>>(E, B.totals);
         glx_bcf_headers_kernel<<<(S + 127) / 128, 128, 0, st>>>(E);
+        glx_bcf_span_index_kernel<<<(n_spans + 255) / 256, 256, 0, st>>>(E, B.span_site, n_spans);
         CU(cudaGetLastError());
         if (mode == 0) {
-            const size_t smem = GLX_BCF_SPAN + (GLX_BCF_G_MAX + 8) * 2;
+            const size_t smem = sizeof(RawSmem);
             static bool attr_set = false;
             if (!attr_set) {
                 CU(cudaFuncSetAttribute(glx_bcf_span_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr_set = true;
             }
-            glx_bcf_span_raw_kernel<<<n_spans, GLX_BCF_SPAN_THREADS, smem, st>>>(E, B.stream);
+            glx_bcf_span_raw_kernel<<<n_spans, GLX_BCF_SPAN_THREADS, smem, st>>>(E, B.span_site, B.stream);
         } else {
-            int rc = glx_bgzf_launch(ctx, E, B.stream, B.packed, B.totals, B.blk_sizes, B.blk_offsets, n_spans, st);
+            int rc = glx_bgzf_launch(ctx, E, B.span_site, B, n_spans, st);
             if (rc != GLX_OK) return rc;
         }
         CU(cudaGetLastError());
@@ -487,6 +562,19 @@ int glx_bcf_record_offsets(glx_ctx* ctx, glx_dev_batch* d, uint64_t* rec_off) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(d->bcf.len_ev));
     CU(cudaMemcpy(rec_off, d->bcf.E.rec_off, ((size_t)d->n_sites + 1) * 8, cudaMemcpyDeviceToHost));
+    return GLX_OK;
+}
+
+// cycles thread 0 of the BGZF blocks spent per phase since the last call (gather, segments, setup, crc, tokenize, crc tree,
+// codes + header, count + scan, emit, finish + store); out[15] unused
+int glx_debug_bgzf_phases(glx_ctx* ctx, uint64_t out[16]) {
+    if (!ctx || !out) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long h[16], z[16] = {0};
+    CU(cudaMemcpyFromSymbol(h, glx_bgzf_phase_cycles, sizeof h));
+    CU(cudaMemcpyToSymbol(glx_bgzf_phase_cycles, z, sizeof z));
+    for (int i = 0; i < 16; i++) out[i] = h[i];
     return GLX_OK;
 }
 

@@ -540,150 +540,246 @@ struct BcfPadded {
     static __host__ __device__ __forceinline__ size_t phys(unsigned long long i) { return (size_t)(i + ((i >> 6) << 2)); }
 };
 
-// 16 aligned bytes of global memory as V elements
-template <class T>
-struct BcfVec {
-    T v[16 / sizeof(T)];
+// The span's piece table (shared memory): every run of bytes of the records overlapping the span — header + shared part,
+// each FORMAT block's key/descriptor bytes, each FORMAT block's data — with where its bytes come from. Built by the whole
+// block (one thread per piece, so the plan loads of all pieces are in flight together), then the span is filled word by
+// word: a thread finds its word's piece by binary search and converts the source values, 16 independent words per thread.
+#define GLX_BCF_TAB_MAX 256
+#define GLX_BCF_REC_MAX 24
+enum { BCF_PK_BYTES = 0, BCF_PK_GT = 1, BCF_PK_INT = 2, BCF_PK_RAW4 = 3, BCF_PK_TRIM = 4, BCF_PK_STR = 5 };
+struct BcfSpanTab {
+    long long start[GLX_BCF_TAB_MAX + 1];  // span-relative offset of the piece's first byte (negative: begins before the span); non-decreasing; [n] = end
+    const void* src[GLX_BCF_TAB_MAX];
+    uint32_t info[GLX_BCF_TAB_MAX];  // kind | width << 4 | values per sample after trimming << 8 | values per sample in the source << 20
+    uint32_t km[GLX_BCF_TAB_MAX];    // keep mask of the site (GT renumbering, trimmed vectors)
+    uint32_t dist[GLX_BCF_TAB_MAX];  // FORMAT data: distance to the same block's data in the previous record (0: none / other layout)
+    uint8_t fld[GLX_BCF_TAB_MAX];    // lifted field index (trimmed vectors, strings)
+    unsigned long long roff[GLX_BCF_REC_MAX + 2];
+    uint32_t n, n_rec, site0, site_next, complete;  // complete: the table holds every piece of the span (one round)
+    long long cov_lo, cov_hi;                       // span-relative byte range the table covers
 };
-template <class T>
-__host__ __device__ __forceinline__ BcfVec<T> bcf_load16(const T* p) {
-    BcfVec<T> r;
-#if defined(__CUDA_ARCH__)
-    const int4 x = __ldg(reinterpret_cast<const int4*>(p));
-    memcpy(&r, &x, 16);
-#else
-    memcpy(&r, p, 16);
-#endif
-    return r;
-}
 
-// A run of a FORMAT data region: element e of src becomes the OUTW bytes conv(src[e]) at region offsets [e*OUTW, (e+1)*OUTW);
-// only offsets in [c0, c1) are written, to buf[phys(ob + offset)]. Interior elements go 16 source bytes per load, two loads
-// in flight per thread (the pass is bound by memory-level parallelism, not by instructions).
-template <int OUTW, class Addr, class T, class Conv>
-__host__ __device__ inline void bcf_run(const T* __restrict__ src, unsigned long long c0, unsigned long long c1, unsigned long long ob, uint8_t* buf, Conv conv,
-                                        uint32_t tid, uint32_t nt) {
-    constexpr unsigned V = 16 / sizeof(T);
-    auto emit = [&](unsigned long long e, uint32_t x, bool clip) {
-#pragma unroll
-        for (int i = 0; i < OUTW; i++) {
-            const unsigned long long q = e * OUTW + i;
-            if (!clip || (q >= c0 && q < c1)) buf[Addr::phys(ob + q)] = (uint8_t)(x >> (8 * i));
+// source slot of new slot jn of a trimmed Number=vl vector
+__host__ __device__ __forceinline__ uint32_t bcf_nth_kept(uint32_t km, uint32_t r) {  // index of the r-th (0-based) set bit
+    for (uint32_t a = 0; a < 32; a++)
+        if (km >> a & 1u) {
+            if (r == 0) return a;
+            r--;
         }
-    };
-    const unsigned long long e0 = c0 / OUTW, e1 = (c1 + OUTW - 1) / OUTW;  // elements touching [c0, c1)
-    unsigned long long i0 = (c0 + OUTW - 1) / OUTW, i1 = c1 / OUTW;        // elements wholly inside: [i0, i1)
-    // clipped boundary elements (the span starts or ends inside them)
-    const bool first_clipped = e0 < i0, last_clipped = i1 < e1;
-    if (tid == 0 && first_clipped) emit(e0, conv(src[e0]), true);
-    if (tid == (nt > 1 ? 1u : 0u) && last_clipped && !(first_clipped && i1 == e0)) emit(i1, conv(src[i1]), true);
-    if (i1 < i0) i1 = i0;
-    // interior: scalar up to the first 16-byte aligned source element, vectors, scalar tail
-    unsigned long long a0 = i0 + ((V - ((reinterpret_cast<uintptr_t>(src + i0) / sizeof(T)) & (V - 1))) & (V - 1));
-    if (a0 > i1) a0 = i1;
-    for (unsigned long long e = i0 + tid; e < a0; e += nt) emit(e, conv(src[e]), false);
-    const unsigned long long ng = (i1 - a0) / V;
-    unsigned long long g = tid;
-    for (; g + nt < ng; g += 2ull * nt) {
-        const BcfVec<T> x = bcf_load16(src + a0 + g * V), y = bcf_load16(src + a0 + (g + nt) * V);
-#pragma unroll
-        for (unsigned v = 0; v < V; v++) emit(a0 + g * V + v, conv(x.v[v]), false);
-#pragma unroll
-        for (unsigned v = 0; v < V; v++) emit(a0 + (g + nt) * V + v, conv(y.v[v]), false);
-    }
-    if (g < ng) {
-        const BcfVec<T> x = bcf_load16(src + a0 + g * V);
-#pragma unroll
-        for (unsigned v = 0; v < V; v++) emit(a0 + g * V + v, conv(x.v[v]), false);
-    }
-    for (unsigned long long e = a0 + ng * V + tid; e < i1; e += nt) emit(e, conv(src[e]), false);
+    return 31;
+}
+__host__ __device__ __forceinline__ uint32_t bcf_slot_src(uint8_t vl, uint32_t jn, uint32_t km) {
+    if (vl == 'R') return bcf_nth_kept(km, jn);
+    if (vl == 'A') return bcf_nth_kept(km, jn + 1) - 1;
+    uint32_t ra, rb;
+    bcf_gt_alleles(jn, ra, rb);
+    const uint32_t ia = bcf_nth_kept(km, ra), ib = bcf_nth_kept(km, rb);
+    return ib * (ib + 1) / 2 + ia;
 }
 
-template <class Addr>
-__host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long long lo, unsigned long long hi, uint8_t* buf, uint16_t* s_src, uint32_t tid,
+// Pieces of the records of sites [s_begin, ...) that overlap span [lo, hi): as many records as the table holds. Every thread calls it.
+__host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, unsigned long long lo, unsigned long long hi, uint32_t s_begin, uint32_t tid,
                                               uint32_t nt) {
+    const uint32_t slots = 1 + 2 * (E.n_fields + 2);  // pieces per record
+    const uint32_t max_rec = GLX_BCF_TAB_MAX / slots < GLX_BCF_REC_MAX ? GLX_BCF_TAB_MAX / slots : GLX_BCF_REC_MAX;
+    for (uint32_t j = tid; j <= max_rec; j += nt) T.roff[j] = s_begin + j <= E.n_sites ? E.rec_off[s_begin + j] : ~0ull;
+    GLX_BLOCK_SYNC();
+    if (tid == 0) {
+        uint32_t nr = 0;
+        while (nr < max_rec && s_begin + nr < E.n_sites && T.roff[nr] < hi) nr++;
+        T.n_rec = nr;
+        T.site0 = s_begin;
+        T.site_next = s_begin + nr;
+        T.n = nr * slots;
+        T.cov_lo = (long long)(T.roff[0] > lo ? T.roff[0] - lo : 0);
+        const unsigned long long end = nr ? T.roff[nr] : lo;  // roff[nr] = start of the first record not in the table
+        T.cov_hi = (long long)((end < hi ? end : hi) - lo);
+        T.start[nr * slots] = (long long)(end - lo);
+    }
+    GLX_BLOCK_SYNC();
     const uint32_t N = E.n_samples;
-    for (uint32_t s = bcf_first_site(E, lo); s < E.n_sites && E.rec_off[s] < hi; s++) {
-        const unsigned long long r0 = E.rec_off[s], r1 = E.rec_off[s + 1];
-        if (r1 == r0) continue;
+    for (uint32_t idx = tid; idx < T.n; idx += nt) {
+        const uint32_t j = idx / slots, p = idx - j * slots, s = s_begin + j;
+        const unsigned long long r0 = T.roff[j];
+        const bool has = T.roff[j + 1] > r0;
         const BcfSitePlan& P = E.plan[s];
-        const uint32_t hdr_len = 8 + P.l_shared;
-        // clip [a, a+len) to the span; returns the part as offsets relative to a
-        auto clip = [&](unsigned long long a, unsigned long long len, unsigned long long& c0, unsigned long long& c1) {
-            const unsigned long long b = a + len;
-            const unsigned long long x0 = a > lo ? a : lo, x1 = b < hi ? b : hi;
-            if (x1 <= x0) return false;
-            c0 = x0 - a;
-            c1 = x1 - a;
-            return true;
-        };
-        unsigned long long c0, c1;
-        if (clip(r0, hdr_len, c0, c1)) {
-            const uint8_t* src = E.hdr_pool + E.hdr_off[s];
-            for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[Addr::phys(r0 + q - lo)] = src[q];
-        }
-        const unsigned long long ibase = r0 + hdr_len;
-        const uint32_t km = P.keep_mask;
-        for (uint32_t b = 0; b < P.n_blk; b++) {
-            const unsigned long long bstart = ibase + P.blk_off[b];
-            const uint32_t hl = P.blk_hdr_len[b], cn = P.blk_cnt[b], w = P.blk_width[b];
-            if (bstart >= hi) break;
-            if (clip(bstart, hl, c0, c1))
-                for (unsigned long long q = c0 + tid; q < c1; q += nt) buf[Addr::phys(bstart + q - lo)] = P.blk_hdr[b][q];
-            const unsigned long long dstart = bstart + hl, dlen = (unsigned long long)N * cn * w;
-            if (!clip(dstart, dlen, c0, c1)) continue;
-            const unsigned long long ob = dstart - lo;  // buf index of the block's first data byte (mod 2^64 when it lies before the span:
-                                                        // only bytes q in [c0, c1) are touched, for which ob + q is in range)
-#define out(q) buf[Addr::phys(ob + (q))]
-            if (b == 0) {  // GT: unified allele index -> htslib GT int of the allele's rank among the survivors
-                bcf_run<1, Addr>(E.gt + (size_t)s * N * 2, c0, c1, ob, buf,
-                                 [km](int8_t a) -> uint32_t { return a < 0 ? 0u : (uint32_t)((bcf_popc(km & ((1u << a) - 1u)) + 1) << 1); }, tid, nt);
-            } else if (b == (uint32_t)P.n_blk - 1) {  // RNC
-                bcf_run<1, Addr>(E.rnc + (size_t)s * N * 2, c0, c1, ob, buf, [](uint8_t c) -> uint32_t { return c; }, tid, nt);
+        long long st = (long long)(r0 - lo);
+        const void* src = nullptr;
+        uint32_t info = BCF_PK_BYTES, dist = 0, fld = 0;
+        if (has) {
+            const uint32_t hdr_len = 8 + P.l_shared;
+            if (p == 0) {
+                src = E.hdr_pool + E.hdr_off[s];
             } else {
-                const uint32_t k = b - 1, cnt = E.fld_cnt[k][s];
-                const int32_t* __restrict__ base = E.fld[k] + E.fld_off[k][s];
-                if (E.fkind[k] == GLX_FK_FT || E.fkind[k] == GLX_FK_STRING) {
-                    for (unsigned long long q = c0 + tid; q < c1; q += nt) {
-                        const uint32_t n = (uint32_t)(q / cn), ci = (uint32_t)(q - (unsigned long long)n * cn);
-                        out(q) = bcf_ft_char(E.m, (uint32_t)base[(size_t)n * cnt], ci);
-                    }
-                } else if (P.trimmed && bcf_is_arg(E.fvl[k])) {
-                    // trimmed vector: new slot -> source slot table, then per element the "first end-of-vector" rule
-                    const uint8_t vl = E.fvl[k];
-                    const int32_t vend = E.ftype[k] == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_VECTOR_END_BITS : GLXB_VEND;
-                    GLX_BLOCK_SYNC();
-                    for (uint32_t j = tid; j < cnt; j += nt)
-                        if (bcf_slot_kept(vl, j, km)) s_src[bcf_slot_new(vl, j, km)] = (uint16_t)j;
-                    GLX_BLOCK_SYNC();
-                    const unsigned long long e0 = c0 / w, e1 = (c1 + w - 1) / w;
-                    for (unsigned long long e = e0 + tid; e < e1; e += nt) {
-                        const uint32_t n = (uint32_t)(e / cn), jn = (uint32_t)(e - (unsigned long long)n * cn);
-                        const int32_t* p = base + (size_t)n * cnt;
-                        const uint32_t j = s_src[jn];
-                        int32_t v = p[j];
-                        for (uint32_t i = 0; i < j; i++)
-                            if (p[i] == vend) {
-                                v = vend;
-                                break;
-                            }
-                        const uint32_t x = E.ftype[k] == GLX_TYPE_FLOAT ? (uint32_t)v : bcf_conv(v, w);
-                        for (uint32_t i = 0; i < w; i++) {
-                            const unsigned long long q = e * w + i;
-                            if (q >= c0 && q < c1) out(q) = (uint8_t)(x >> (8 * i));
+                const uint32_t b = (p - 1) >> 1;
+                if (b >= P.n_blk) {
+                    st = (long long)(T.roff[j + 1] - lo);  // unused slot: empty piece at the record's end
+                } else {
+                    const unsigned long long bstart = r0 + hdr_len + P.blk_off[b];
+                    if ((p - 1) & 1) {  // data
+                        const unsigned long long dstart = bstart + P.blk_hdr_len[b];
+                        st = (long long)(dstart - lo);
+                        const uint32_t cn = P.blk_cnt[b], w = P.blk_width[b];
+                        if (b == 0) {
+                            src = E.gt + (size_t)s * N * 2;
+                            info = BCF_PK_GT | 1u << 4 | 2u << 8 | 2u << 20;
+                        } else if (b == (uint32_t)P.n_blk - 1) {
+                            src = E.rnc + (size_t)s * N * 2;
+                            info = BCF_PK_BYTES | 1u << 4 | 2u << 8 | 2u << 20;
+                        } else {
+                            const uint32_t k = b - 1, cnt = E.fld_cnt[k][s];
+                            fld = k;
+                            src = E.fld[k] + E.fld_off[k][s];
+                            uint32_t kind;
+                            if (E.fkind[k] == GLX_FK_FT || E.fkind[k] == GLX_FK_STRING) kind = BCF_PK_STR;
+                            else if (P.trimmed && bcf_is_arg(E.fvl[k])) kind = BCF_PK_TRIM;
+                            else if (w == 4) kind = BCF_PK_RAW4;
+                            else kind = BCF_PK_INT;
+                            info = kind | w << 4 | (cn & 0xfffu) << 8 | (cnt & 0xfffu) << 20;
                         }
+                        // the same block's data in the previous record, if that record has the same layout
+                        uint32_t q = s;
+                        while (q-- > 0)
+                            if (E.rec_off[q + 1] > E.rec_off[q]) break;
+                        if (q != 0xffffffffu) {
+                            const BcfSitePlan& Q = E.plan[q];
+                            if (Q.n_blk == P.n_blk && Q.blk_cnt[b] == P.blk_cnt[b] && Q.blk_width[b] == P.blk_width[b]) {
+                                const unsigned long long pstart = E.rec_off[q] + 8 + Q.l_shared + Q.blk_off[b] + Q.blk_hdr_len[b];
+                                if (dstart - pstart <= 32768) dist = (uint32_t)(dstart - pstart);
+                            }
+                        }
+                    } else {  // the block's typed key + descriptor
+                        st = (long long)(bstart - lo);
+                        src = P.blk_hdr[b];
                     }
-                } else if (w == 1) {
-                    bcf_run<1, Addr>(base, c0, c1, ob, buf, [](int32_t v) -> uint32_t { return bcf_conv(v, 1); }, tid, nt);
-                } else if (w == 2) {
-                    bcf_run<2, Addr>(base, c0, c1, ob, buf, [](int32_t v) -> uint32_t { return bcf_conv(v, 2); }, tid, nt);
-                } else {  // int32 and float: raw
-                    bcf_run<4, Addr>(base, c0, c1, ob, buf, [](int32_t v) -> uint32_t { return (uint32_t)v; }, tid, nt);
                 }
             }
-#undef out
+        }
+        T.start[idx] = st;
+        T.src[idx] = src;
+        T.info[idx] = info;
+        T.km[idx] = has ? P.keep_mask : 0u;
+        T.dist[idx] = dist;
+        T.fld[idx] = (uint8_t)fld;
+    }
+    GLX_BLOCK_SYNC();
+}
+
+// piece holding span byte x (x inside the table's coverage): last piece with start <= x
+__host__ __device__ __forceinline__ uint32_t bcf_tab_find(const BcfSpanTab& T, long long x) {
+    uint32_t a = 0, b = T.n;
+    while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (T.start[mid] <= x) a = mid + 1;
+        else b = mid;
+    }
+    return a - 1;
+}
+// one byte of a piece, any kind (word-straddling positions, trimmed vectors, strings)
+__host__ __device__ inline uint8_t bcf_piece_byte(const BcfEnc& E, const BcfSpanTab& T, uint32_t p, unsigned long long off) {
+    const uint32_t info = T.info[p], kind = info & 15u, w = info >> 4 & 15u, cn = info >> 8 & 0xfffu, cnt = info >> 20;
+    switch (kind) {
+        case BCF_PK_BYTES: return static_cast<const uint8_t*>(T.src[p])[off];
+        case BCF_PK_GT: {
+            const int a = static_cast<const int8_t*>(T.src[p])[off];
+            return a < 0 ? (uint8_t)0 : (uint8_t)((bcf_popc(T.km[p] & ((1u << a) - 1u)) + 1) << 1);
+        }
+        case BCF_PK_INT: return (uint8_t)(bcf_conv(static_cast<const int32_t*>(T.src[p])[off / w], w) >> (8 * (off % w)));
+        case BCF_PK_RAW4: return (uint8_t)((uint32_t) static_cast<const int32_t*>(T.src[p])[off >> 2] >> (8 * (off & 3)));
+        case BCF_PK_STR: {
+            const unsigned long long n = off / cn;
+            return bcf_ft_char(E.m, (uint32_t) static_cast<const int32_t*>(T.src[p])[n * cnt], (uint32_t)(off - n * cn));
+        }
+        default: {  // BCF_PK_TRIM: bcf_remove_allele_set's rewrite — surviving slots, end-of-vector after the sample's first one
+            const uint32_t k = T.fld[p];
+            const bool flt = E.ftype[k] == GLX_TYPE_FLOAT;
+            const int32_t vend = flt ? (int32_t)GLX_FLOAT_VECTOR_END_BITS : GLXB_VEND;
+            const unsigned long long e = off / w, n = e / cn;
+            const uint32_t jn = (uint32_t)(e - n * cn), j = bcf_slot_src(E.fvl[k], jn, T.km[p]);
+            const int32_t* v = static_cast<const int32_t*>(T.src[p]) + n * cnt;
+            int32_t x = v[j];
+            for (uint32_t i = 0; i < j; i++)
+                if (v[i] == vend) {
+                    x = vend;
+                    break;
+                }
+            return (uint8_t)((flt ? (uint32_t)x : bcf_conv(x, w)) >> (8 * (off % w)));
         }
     }
+}
+
+// fill the covered bytes of the span from the table, one 4-byte word per thread and step
+template <class Addr>
+__host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, const BcfSpanTab& T, uint8_t* buf, uint32_t tid, uint32_t nt) {
+    if (T.cov_hi <= T.cov_lo) return;
+    const long long w0 = T.cov_lo >> 2, w1 = (T.cov_hi + 3) >> 2;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+    for (long long wi = w0 + tid; wi < w1; wi += nt) {
+        const long long x0 = wi << 2;
+        const long long a = x0 < T.cov_lo ? T.cov_lo : x0, e = x0 + 4 > T.cov_hi ? T.cov_hi : x0 + 4;
+        const uint32_t p = bcf_tab_find(T, a);
+        const uint32_t info = T.info[p], kind = info & 15u, w = info >> 4 & 15u;
+        const long long off = a - T.start[p];
+        if (e - a == 4 && T.start[p + 1] >= e && (kind == BCF_PK_INT || kind == BCF_PK_RAW4 || kind == BCF_PK_GT || (kind == BCF_PK_BYTES && w == 1)) &&
+            (w == 1 || (off % w) == 0)) {
+            // the whole word comes from one typed vector, element-aligned: 4, 2 or 1 source values
+            uint32_t word;
+            if (kind == BCF_PK_INT && w == 1) {
+                const int32_t* v = static_cast<const int32_t*>(T.src[p]) + off;
+                word = bcf_conv(v[0], 1) | bcf_conv(v[1], 1) << 8 | bcf_conv(v[2], 1) << 16 | bcf_conv(v[3], 1) << 24;
+            } else if (kind == BCF_PK_INT && w == 2) {
+                const int32_t* v = static_cast<const int32_t*>(T.src[p]) + off / 2;
+                word = bcf_conv(v[0], 2) | bcf_conv(v[1], 2) << 16;
+            } else if (kind == BCF_PK_INT || kind == BCF_PK_RAW4) {
+                word = (uint32_t) static_cast<const int32_t*>(T.src[p])[off >> 2];
+            } else if (kind == BCF_PK_GT) {
+                const int8_t* g = static_cast<const int8_t*>(T.src[p]) + off;
+                const uint32_t km = T.km[p];
+                word = 0;
+                for (int i = 0; i < 4; i++) {
+                    const int al = g[i];
+                    word |= (al < 0 ? 0u : (uint32_t)((bcf_popc(km & ((1u << al) - 1u)) + 1) << 1)) << (8 * i);
+                }
+            } else {
+                const uint8_t* c = static_cast<const uint8_t*>(T.src[p]) + off;
+                word = c[0] | c[1] << 8 | c[2] << 16 | (uint32_t)c[3] << 24;
+            }
+            // both layouts keep an aligned word contiguous
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<uint32_t*>(buf + Addr::phys((unsigned long long)x0)) = word;
+#else
+            memcpy(buf + Addr::phys((unsigned long long)x0), &word, 4);  // the host build also runs odd span sizes
+#endif
+        } else {
+            uint32_t q = p;
+            for (long long x = a; x < e; x++) {
+                while (T.start[q + 1] <= x) q++;
+                buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, q, (unsigned long long)(x - T.start[q]));
+            }
+        }
+    }
+}
+
+// Gather bytes [lo, hi) of the record stream into buf (layout Addr). s_first = first site whose record reaches into the span
+// (bcf_first_site(E, lo), or the span index table). Every thread calls it.
+template <class Addr>
+__host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long long lo, unsigned long long hi, uint32_t s_first, uint8_t* buf, BcfSpanTab& T,
+                                              uint32_t tid, uint32_t nt) {
+    uint32_t s = s_first, rounds = 0;
+    for (;;) {
+        bcf_tab_build(E, T, lo, hi, s, tid, nt);
+        bcf_tab_fill<Addr>(E, T, buf, tid, nt);
+        const uint32_t next = T.site_next;
+        const bool more = next < E.n_sites && T.n_rec > 0 && T.roff[T.n_rec] < hi;
+        rounds++;
+        GLX_BLOCK_SYNC();  // the table is rebuilt (or read by the caller) after everyone has finished with it
+        if (!more) break;
+        s = next;
+    }
+    if (tid == 0) T.complete = rounds == 1 ? 1u : 0u;
+    GLX_BLOCK_SYNC();
 }
 
 }  // namespace glxd

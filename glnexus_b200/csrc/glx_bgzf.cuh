@@ -7,7 +7,12 @@
 // typed vector for all samples. Two redundancies dominate: (1) runs of one byte (GT of hom-ref cells, RNC "..",
 // zero high bytes), caught by distance-1 matches; (2) a sample's value at this site equals its value at the previous
 // site whenever the same reference band covers both, caught by matches at the distance D between the same FORMAT block of
-// consecutive records (known from the layout, no hashing). Everything else is literals under a per-block Huffman code.
+// consecutive records (known from the layout, no hashing). Everything else is literals under a Huffman code.
+//
+// The Huffman code is built ONCE PER BATCH (blocks of one batch hold the same mix of fields): a sampling kernel tokenizes a
+// few hundred spans into a histogram, one small block turns it into code lengths, canonical codes and the finished
+// dynamic-block header bits, and every BGZF block then only tokenizes, counts, scans and emits. Symbols the sample never
+// saw still get a code (every frequency is smoothed by one).
 //
 // Every phase is a block-level function over GLX_BGZF_WORKERS virtual workers (64-byte chunks of the span), written so
 // that the host build (tests/emu) runs it with one thread and checks the result with zlib.
@@ -20,27 +25,33 @@
 namespace glxd {
 
 #define GLX_BGZF_WORKERS 1024u
-#define GLX_BGZF_CHUNK 64u                      // bytes per worker: 1024 x 64 = 65,536 >= GLX_BCF_SPAN
-#define GLX_BGZF_SLOT 65536u                    // bytes reserved per block before compaction
-#define GLX_BGZF_LEAD 14u                       // the block starts at byte 14 of its staging buffer, so that the deflate data is word-aligned (14 + 18)
+#define GLX_BGZF_CHUNK 64u    // bytes per worker: 1024 x 64 = 65,536 >= GLX_BCF_SPAN
+#define GLX_BGZF_SLOT 65536u  // bytes reserved per block before compaction
+#define GLX_BGZF_LEAD 14u     // the block starts at byte 14 of its staging buffer, so that the deflate data is word-aligned (14 + 18)
 #define GLX_BGZF_OUT (GLX_BGZF_LEAD + 18u + 5u + GLX_BCF_SPAN + 8u + 16u)
 #define GLX_BGZF_IN_PAD (GLX_BCF_SPAN + (GLX_BCF_SPAN / 64u + 2u) * 4u)  // the span with 4 bytes of padding after every 64 (BcfPadded)
-#define GLX_BGZF_SEG_MAX 512u
 #define GLX_BGZF_LITS 286u
 #define GLX_BGZF_DISTS 30u
+#define GLX_BGZF_HIST (288u + 32u)
+#define GLX_BGZF_HDR_WORDS 96u
+#define GLX_BGZF_SAMPLES 384u  // spans tokenized for the batch's histogram
 
-struct BgzfShared {
-    uint32_t lit_freq[288], dist_freq[32];
+// the batch's Huffman code and the finished header of every dynamic block
+struct BgzfTable {
     uint8_t lit_len[288], dist_len[32];
     uint16_t lit_code[288], dist_code[32];  // bit-reversed canonical codes
-    uint32_t wbits[GLX_BGZF_WORKERS];       // CRC parts, then per-worker bit counts -> bit offsets
+    uint32_t hdr_bits;
+    uint32_t hdr_words[GLX_BGZF_HDR_WORDS];
+};
+
+struct BgzfShared {
+    BgzfTable tab;
+    uint32_t freq[GLX_BGZF_HIST];               // sampling: literal/length counts [0, 288), distance counts [288, 320)
+    uint32_t wbits[GLX_BGZF_WORKERS];           // per-worker bit counts -> bit offsets
     unsigned long long tok[GLX_BGZF_WORKERS];   // bit i: a token starts at byte i of the worker's chunk (literal = 1 byte, match = to the next start)
     unsigned long long useD[GLX_BGZF_WORKERS];  // bit i: the match starting there copies from the structural distance D, not from distance 1
-    uint16_t hdr_tok[320 + 8];                  // run-length coded code lengths of the block header: symbol | extra value << 5
-    uint32_t seg_start[GLX_BGZF_SEG_MAX], seg_dist[GLX_BGZF_SEG_MAX];  // data segments of the span and their "same value, previous record" distance
-    uint32_t n_seg, n_in, hdr_bits, data_bits, crc, stored, block_len, n_hdr_tok, lit_total, dist_total, lit_kraft, dist_kraft;
+    uint32_t n_in, data_bits, crc, crc_acc, stored, block_len;
     uint32_t crc_table[256];
-    uint32_t crc_shift[12];  // x^(8 * 64 * 2^l) mod P, l = 0..9; [10] = x^(8 n) mod P for this span
 };
 
 __host__ __device__ __forceinline__ int bgzf_log2(uint32_t x) {  // floor(log2 x), x > 0
@@ -82,7 +93,7 @@ __host__ __device__ inline uint32_t crc_multmodp(uint32_t a, uint32_t b) {  // a
     return p;
 }
 __host__ __device__ inline uint32_t crc_x_pow_8n(uint32_t n) {  // x^(8n) mod P
-    uint32_t p = 1u << 31;  // x^0
+    uint32_t p = 1u << 31;   // x^0
     uint32_t sq = 1u << 23;  // x^8
     while (n) {
         if (n & 1) p = crc_multmodp(sq, p);
@@ -91,35 +102,46 @@ __host__ __device__ inline uint32_t crc_x_pow_8n(uint32_t n) {  // x^(8n) mod P
     }
     return p;
 }
-__host__ __device__ inline void bgzf_crc_setup(BgzfShared& sh, uint32_t n, uint32_t tid, uint32_t nt) {
+// CRC of the span from the workers' chunk CRCs without a combine tree: with the data right-aligned in the 1024 x 64 byte
+// frame (leading zeros leave a raw, init-0 register untouched), crc_raw(span) = XOR_w crc_raw(chunk w) * x^(8 * 64 * (1023 - w)).
+// The 1024 powers are computed once on the host (bgzf_crc_powers) and live in global memory.
+inline void bgzf_crc_powers(uint32_t* pw /* [GLX_BGZF_WORKERS + 1]; last = x^(8 * GLX_BCF_SPAN) */) {
+    uint32_t p = 1u << 31;
+    const uint32_t step = crc_x_pow_8n(GLX_BGZF_CHUNK);
+    for (uint32_t k = 0; k < GLX_BGZF_WORKERS; k++) {
+        pw[k] = p;
+        p = crc_multmodp(step, p);
+    }
+    pw[GLX_BGZF_WORKERS] = crc_x_pow_8n(GLX_BCF_SPAN);
+}
+__host__ __device__ __forceinline__ void bgzf_xor(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicXor(p, v);
+#else
+    *p ^= v;
+#endif
+}
+__host__ __device__ inline void bgzf_crc_setup(BgzfShared& sh, uint32_t tid, uint32_t nt) {
     for (uint32_t i = tid; i < 256; i += nt) {
         uint32_t c = i;
         for (int k = 0; k < 8; k++) c = c & 1 ? (c >> 1) ^ GLX_CRC_POLY : c >> 1;
         sh.crc_table[i] = c;
     }
-    for (uint32_t l = tid; l < 11; l += nt) sh.crc_shift[l] = l < 10 ? crc_x_pow_8n(GLX_BGZF_CHUNK << l) : crc_x_pow_8n(n);
+    if (tid == 0) sh.crc_acc = 0;
 }
-// raw (init 0, no final xor) CRC of each worker's chunk; the data is right-aligned in the 1024 x 64 byte frame, so that
-// leading zero padding leaves the raw register untouched and every combine step shifts by a fixed power
-__host__ __device__ inline void bgzf_crc_parts(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
+__host__ __device__ inline void bgzf_crc_parts(BgzfShared& sh, const uint32_t* __restrict__ pw, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
     const uint32_t pad = GLX_BGZF_WORKERS * GLX_BGZF_CHUNK - n;
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
         const uint32_t v0 = w * GLX_BGZF_CHUNK, v1 = v0 + GLX_BGZF_CHUNK;
+        if (v1 <= pad) continue;
         uint32_t c = 0;
         for (uint32_t v = v0 < pad ? pad : v0; v < v1; v++) c = sh.crc_table[(c ^ in[BcfPadded::phys(v - pad)]) & 0xff] ^ (c >> 8);
-        sh.wbits[w] = c;
+        if (c) bgzf_xor(&sh.crc_acc, crc_multmodp(pw[GLX_BGZF_WORKERS - 1 - w], c));
     }
 }
-// one level of the combine tree: pairs (2i, 2i+1) at stride 2^l -> crc(A||B) = crc(A) * x^(8|B|) + crc(B)
-__host__ __device__ inline void bgzf_crc_level(BgzfShared& sh, uint32_t l, uint32_t tid, uint32_t nt) {
-    const uint32_t stride = 1u << l, pairs = GLX_BGZF_WORKERS >> (l + 1);
-    for (uint32_t i = tid; i < pairs; i += nt) {
-        const uint32_t a = i * 2 * stride, b = a + stride;
-        sh.wbits[a] = crc_multmodp(sh.crc_shift[l], sh.wbits[a]) ^ sh.wbits[b];
-    }
-}
-__host__ __device__ inline void bgzf_crc_finish(BgzfShared& sh) {  // one thread
-    sh.crc = ~(sh.wbits[0] ^ crc_multmodp(sh.crc_shift[10], 0xffffffffu));
+__host__ __device__ inline void bgzf_crc_finish(BgzfShared& sh, const uint32_t* __restrict__ pw) {  // one thread
+    const uint32_t xn = sh.n_in == GLX_BCF_SPAN ? pw[GLX_BGZF_WORKERS] : crc_x_pow_8n(sh.n_in);
+    sh.crc = ~(sh.crc_acc ^ crc_multmodp(xn, 0xffffffffu));
 }
 
 // ---- DEFLATE symbols ----
@@ -175,50 +197,76 @@ __host__ __device__ __forceinline__ uint32_t bgzf_lowbit(unsigned long long m) {
     return (uint32_t)__builtin_ffsll((long long)m) - 1;
 #endif
 }
+__host__ __device__ __forceinline__ uint32_t bgzf_popcll(unsigned long long m) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(m);
+#else
+    return (uint32_t)__builtin_popcountll(m);
+#endif
+}
+// the structural distance at span byte x: the piece table's, when it holds the whole span
+__host__ __device__ __forceinline__ uint32_t bgzf_dist_at(const BcfSpanTab& T, uint32_t x) { return T.complete && T.n ? T.dist[bcf_tab_find(T, (long long)x)] : 0u; }
 
-// Pass 1. Worker w owns bytes [64w, 64w+64) of the span (in = the BcfPadded staging buffer). It finds, per byte, whether the
-// byte repeats the one before it (distance 1) and whether it repeats the byte at the structural distance D of its segment,
-// as two 64-bit masks, then walks them greedily — a D-match of >= 4 bytes that is longer than the distance-1 run, else a
-// distance-1 run of >= 3, else a literal — recording the token starts and counting symbols. Matches end at the chunk's end.
-__host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
+// the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance)
+template <class F>
+__host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t w, F&& emit) {
+    const uint32_t c0 = w * GLX_BGZF_CHUNK;
+    if (c0 >= n) return;
+    const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
+    unsigned long long t = sh.tok[w];
+    const unsigned long long useD = sh.useD[w];
+    while (t) {
+        const uint32_t p = bgzf_lowbit(t);
+        t &= t - 1;
+        const uint32_t q = t ? bgzf_lowbit(t) : L;
+        if (q - p < 3) emit(false, (uint32_t)in[BcfPadded::phys(c0 + p)], 0u);
+        else emit(true, q - p, (useD >> p & 1ull) ? bgzf_dist_at(T, c0 + p) : 1u);
+    }
+}
+
+// Worker w owns bytes [64w, 64w+64) of the span (in = the BcfPadded staging buffer). It finds, per byte, whether the byte
+// repeats the one before it (distance 1) and whether it repeats the byte at the structural distance D of its piece, as two
+// 64-bit masks, then walks them greedily — a D-match of >= 4 bytes that is longer than the distance-1 run, else a distance-1
+// run of >= 3, else a literal — recording the token starts. Matches end at the chunk's end and at piece boundaries.
+// HIST: count the symbols into sh.freq (sampling). COUNT: the worker's bit count under sh.tab into sh.wbits.
+template <bool HIST, bool COUNT>
+__host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
         const uint32_t c0 = w * GLX_BGZF_CHUNK;
         if (c0 >= n) {
             sh.tok[w] = sh.useD[w] = 0;
+            if (COUNT) sh.wbits[w] = 0;
             continue;
         }
         const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
         const unsigned long long live = L == 64 ? ~0ull : ((1ull << L) - 1);
         const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));  // the chunk is contiguous and word-aligned
-        unsigned long long eq1 = 0;
+        unsigned long long eq1 = 0, zero = 0;
         uint32_t carry = c0 ? in[BcfPadded::phys(c0 - 1)] : 0u;
         for (uint32_t k = 0; k < 16; k++) {
             const uint32_t x = W[k];
             eq1 |= (unsigned long long)bgzf_eq_nibble(x, (x << 8) | carry) << (4 * k);
+            if (HIST) zero |= (unsigned long long)bgzf_eq_nibble(x, 0u) << (4 * k);
             carry = x >> 24;
         }
         if (!c0) eq1 &= ~1ull;  // the span's first byte has no predecessor
         eq1 &= live;
-        unsigned long long eqD = 0, brk = 0;  // brk: a segment (another D) starts here: a D-match must not run across
-        {  // segments overlapping the chunk: [a, b) with distance D
-            uint32_t lo = 0, hi = sh.n_seg;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (sh.seg_start[mid] <= c0) lo = mid + 1;
-                else hi = mid;
-            }
-            uint32_t sg = lo ? lo - 1 : 0;  // segment holding c0 (or the first one)
-            for (; sg < sh.n_seg && sh.seg_start[sg] < c0 + L; sg++) {
-                const uint32_t D = sh.seg_dist[sg];
-                if (sh.seg_start[sg] > c0) brk |= 1ull << (sh.seg_start[sg] - c0);
+        unsigned long long eqD = 0, brk = 0;  // brk: another piece (another D) starts here: a D-match must not run across
+        if (T.complete && T.n) {
+            uint32_t pc = bcf_tab_find(T, (long long)c0);
+            for (; pc < T.n && T.start[pc] < (long long)(c0 + L); pc++) {
+                const long long ps = T.start[pc], pe = T.start[pc + 1];
+                if (pe <= ps) continue;
+                if (ps > (long long)c0) brk |= 1ull << (ps - c0);
+                const uint32_t D = T.dist[pc];
                 if (D <= 1 || D > 32768) continue;
-                const uint32_t a = sh.seg_start[sg] > c0 ? sh.seg_start[sg] : c0;
-                const uint32_t e = sg + 1 < sh.n_seg && sh.seg_start[sg + 1] < c0 + L ? sh.seg_start[sg + 1] : c0 + L;
+                const uint32_t a = ps > (long long)c0 ? (uint32_t)ps : c0;
+                const uint32_t e = pe < (long long)(c0 + L) ? (uint32_t)pe : c0 + L;
                 for (uint32_t i = a < D ? D : a; i < e; i++)
                     if (in[BcfPadded::phys(i)] == in[BcfPadded::phys(i - D)]) eqD |= 1ull << (i - c0);
             }
         }
-        unsigned long long tok = 0, useD = 0;
+        unsigned long long tok = 0, useD = 0, lits = 0;
         uint32_t i = 0;
         while (i < L) {
             const uint32_t r1 = bgzf_run(eq1, i);
@@ -237,107 +285,75 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const uint8_t* in,
             } else if (r1 >= 3) {
                 i += r1;
             } else {
-                bgzf_add(&sh.lit_freq[in[BcfPadded::phys(c0 + i)]], 1);
+                lits |= 1ull << i;
                 i++;
             }
         }
         sh.tok[w] = tok;
         sh.useD[w] = useD;
-        // match symbols: second walk over the recorded starts (keeps the first loop short)
-        unsigned long long t = tok;
-        uint32_t sg = 0xffffffffu;
-        while (t) {
-            const uint32_t p = bgzf_lowbit(t);
-            t &= t - 1;
-            const uint32_t q = t ? bgzf_lowbit(t) : L;
-            if (q - p < 3) continue;
-            uint32_t sym, eb, ev;
-            bgzf_len_sym(q - p, sym, eb, ev);
-            bgzf_add(&sh.lit_freq[sym], 1);
-            uint32_t D = 1;
-            if (useD >> p & 1ull) {
-                if (sg == 0xffffffffu) {
-                    uint32_t lo = 0, hi = sh.n_seg;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (sh.seg_start[mid] <= c0 + p) lo = mid + 1;
-                        else hi = mid;
-                    }
-                    sg = lo;
-                } else
-                    while (sg < sh.n_seg && sh.seg_start[sg] <= c0 + p) sg++;
-                D = sh.seg_dist[sg - 1];
-            }
-            bgzf_dist_sym(D, sym, eb, ev);
-            bgzf_add(&sh.dist_freq[sym], 1);
+        if (HIST) {
+            // zero is by far the most common literal of typed integer vectors: one add for all of the worker's
+            const uint32_t nz = bgzf_popcll(lits & zero);
+            if (nz) bgzf_add(&sh.freq[0], nz);
+            for (unsigned long long m = lits & ~zero; m; m &= m - 1) bgzf_add(&sh.freq[in[BcfPadded::phys(c0 + bgzf_lowbit(m))]], 1);
         }
-    }
-}
-
-// the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance)
-template <class F>
-__host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t w, F&& emit) {
-    const uint32_t c0 = w * GLX_BGZF_CHUNK;
-    if (c0 >= n) return;
-    const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
-    unsigned long long t = sh.tok[w];
-    const unsigned long long useD = sh.useD[w];
-    uint32_t sg = 0xffffffffu;
-    while (t) {
-        const uint32_t p = bgzf_lowbit(t);
-        t &= t - 1;
-        const uint32_t q = t ? bgzf_lowbit(t) : L;
-        if (q - p < 3) {
-            emit(false, (uint32_t)in[BcfPadded::phys(c0 + p)], 0u);
-            continue;
-        }
-        uint32_t D = 1;
-        if (useD >> p & 1ull) {
-            if (sg == 0xffffffffu) {
-                uint32_t lo = 0, hi = sh.n_seg;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (sh.seg_start[mid] <= c0 + p) lo = mid + 1;
-                    else hi = mid;
+        if (HIST || COUNT) {
+            uint32_t bits = 0;
+            if (COUNT)
+                for (unsigned long long m = lits; m; m &= m - 1) bits += sh.tab.lit_len[in[BcfPadded::phys(c0 + bgzf_lowbit(m))]];
+            for (unsigned long long t = tok & ~lits; t; t &= t - 1) {  // matches
+                const uint32_t p = bgzf_lowbit(t);
+                const unsigned long long rest = tok >> p >> 1;
+                const uint32_t q = rest ? p + 1 + bgzf_lowbit(rest) : L;
+                uint32_t sym, eb, ev, dsym, deb;
+                bgzf_len_sym(q - p, sym, eb, ev);
+                bgzf_dist_sym((useD >> p & 1ull) ? bgzf_dist_at(T, c0 + p) : 1u, dsym, deb, ev);
+                if (HIST) {
+                    bgzf_add(&sh.freq[sym], 1);
+                    bgzf_add(&sh.freq[288 + dsym], 1);
                 }
-                sg = lo;
-            } else
-                while (sg < sh.n_seg && sh.seg_start[sg] <= c0 + p) sg++;
-            D = sh.seg_dist[sg - 1];
+                if (COUNT) bits += sh.tab.lit_len[sym] + eb + sh.tab.dist_len[dsym] + deb;
+            }
+            if (COUNT) sh.wbits[w] = bits;
         }
-        emit(true, q - p, D);
     }
 }
 
-__host__ __device__ inline void bgzf_hist_init(BgzfShared& sh, uint32_t tid, uint32_t nt) {
-    for (uint32_t i = tid; i < 288; i += nt) sh.lit_freq[i] = i == 256 ? 1u : 0u;  // one end-of-block
-    for (uint32_t i = tid; i < 32; i += nt) sh.dist_freq[i] = 0;
-}
-
-// ---- Huffman codes. Code lengths <= maxbits forming a COMPLETE prefix code (zlib's inflate rejects incomplete literal/length
-// sets): start from ceil(log2(total / f)) per symbol (parallel), repair the Kraft sum if the clamp at maxbits oversubscribed
-// it, then hand the slack out by shortening symbols until the sum is exactly one (one thread per alphabet). ----
-__host__ __device__ __forceinline__ uint32_t bgzf_len0(uint32_t f, uint32_t total, uint32_t maxbits) {
-    uint32_t l = 1;
-    while (l < maxbits && ((unsigned long long)f << l) < total) l++;
-    return l;
-}
-// serial part for one alphabet: lengths initialised, K = their Kraft sum in units of 2^-maxbits, used = symbols with f > 0
-__host__ __device__ inline void bgzf_len_settle(const uint32_t* freq, uint32_t n, uint32_t maxbits, uint8_t* len, uint32_t K, uint32_t used) {
+// ---- Huffman code of the batch (one thread; runs once per batch). Code lengths <= maxbits forming a COMPLETE prefix code
+// (zlib's inflate rejects incomplete literal/length sets): start from ceil(log2(total / f)) per symbol, repair the Kraft sum
+// if the clamp at maxbits oversubscribed it, then hand the slack out by shortening symbols until the sum is exactly one. ----
+__host__ __device__ inline void bgzf_code_lengths(const uint32_t* freq, uint32_t n, uint32_t maxbits, uint8_t* len) {
+    uint32_t used = 0, last = 0;
+    unsigned long long total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        len[i] = 0;
+        if (freq[i]) {
+            used++;
+            last = i;
+            total += freq[i];
+        }
+    }
     if (used == 0) return;
     if (used == 1) {
-        for (uint32_t i = 0; i < n; i++)
-            if (freq[i]) len[i] = 1;
+        len[last] = 1;
         return;
     }
     const uint32_t full = 1u << maxbits;
+    unsigned long long K = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!freq[i]) continue;
+        uint32_t l = 1;
+        while (l < maxbits && ((unsigned long long)freq[i] << l) < total) l++;
+        len[i] = (uint8_t)l;
+        K += full >> l;
+    }
     for (uint32_t L = maxbits - 1; K > full && L >= 1; L--)  // oversubscribed: lengthen the longest codes first
         for (uint32_t i = 0; i < n && K > full; i++)
             if (len[i] == L) {
                 len[i]++;
                 K -= full >> (L + 1);
             }
-    uint32_t slack = full - K;
+    unsigned long long slack = full - K;
     while (slack) {  // each pass shortens at least one code of the current maximum length
         for (uint32_t i = 0; i < n && slack; i++) {
             const uint32_t l = len[i];
@@ -348,34 +364,7 @@ __host__ __device__ inline void bgzf_len_settle(const uint32_t* freq, uint32_t n
         }
     }
 }
-// stand-alone form (the 19-symbol code-length alphabet of the header). One thread.
-__host__ __device__ inline void bgzf_code_lengths(const uint32_t* freq, uint32_t n, uint32_t maxbits, uint8_t* len) {
-    uint32_t used = 0, total = 0, K = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        len[i] = 0;
-        used += freq[i] != 0;
-        total += freq[i];
-    }
-    for (uint32_t i = 0; i < n; i++)
-        if (freq[i]) {
-            len[i] = (uint8_t)bgzf_len0(freq[i], total, maxbits);
-            K += (1u << maxbits) >> len[i];
-        }
-    bgzf_len_settle(freq, n, maxbits, len, K, used);
-}
-__host__ __device__ __forceinline__ uint32_t bgzf_rev(uint32_t v, uint32_t l) {  // low l bits of v, reversed
-#if defined(__CUDA_ARCH__)
-    return __brev(v) >> (32 - l);
-#else
-    uint32_t r = 0;
-    for (uint32_t b = 0; b < l; b++) {
-        r = r << 1 | (v & 1);
-        v >>= 1;
-    }
-    return r;
-#endif
-}
-// canonical codes, bit-reversed for LSB-first packing. One thread (small alphabets).
+// canonical codes, bit-reversed for LSB-first packing
 __host__ __device__ inline void bgzf_assign_codes(const uint8_t* len, uint32_t n, uint16_t* code) {
     uint32_t bl_count[16] = {0}, next[16];
     for (uint32_t i = 0; i < n; i++) bl_count[len[i]]++;
@@ -387,11 +376,20 @@ __host__ __device__ inline void bgzf_assign_codes(const uint8_t* len, uint32_t n
     }
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t l = len[i];
-        code[i] = l ? (uint16_t)bgzf_rev(next[l]++, l) : (uint16_t)0;
+        if (!l) {
+            code[i] = 0;
+            continue;
+        }
+        uint32_t v = next[l]++, r = 0;
+        for (uint32_t b = 0; b < l; b++) {
+            r = r << 1 | (v & 1);
+            v >>= 1;
+        }
+        code[i] = (uint16_t)r;
     }
 }
 
-// serial bit writer over a zeroed, word-aligned buffer (the block header, end-of-block)
+// serial bit writer over a zeroed, word-aligned buffer
 struct BgzfBits {
     uint32_t* words;
     uint32_t pos;  // in bits
@@ -404,52 +402,46 @@ struct BgzfBits {
     }
 };
 
-// Dynamic-block header (BFINAL = 1, BTYPE = 10) from the two length tables. One thread. Sets sh.hdr_bits.
-__host__ __device__ inline void bgzf_write_header(BgzfShared& sh, uint32_t* out_words) {
+// freq[320] (literal/length, then distance counts of the sampled spans) -> the batch's table: smoothed frequencies, both
+// codes, and the dynamic-block header (BFINAL = 1, BTYPE = 10, the run-length coded code lengths). One thread.
+__host__ __device__ inline void bgzf_table_build(const uint32_t* freq, BgzfTable& tab) {
+    uint32_t f[288];
+    for (uint32_t i = 0; i < 288; i++) f[i] = i < GLX_BGZF_LITS ? freq[i] + 1 : 0;  // + 1: every symbol can be coded
+    bgzf_code_lengths(f, GLX_BGZF_LITS, 15, tab.lit_len);
+    tab.lit_len[286] = tab.lit_len[287] = 0;
+    uint32_t d[32];
+    for (uint32_t i = 0; i < 32; i++) d[i] = i < GLX_BGZF_DISTS ? freq[288 + i] + 1 : 0;
+    bgzf_code_lengths(d, GLX_BGZF_DISTS, 15, tab.dist_len);
+    tab.dist_len[30] = tab.dist_len[31] = 0;
+    bgzf_assign_codes(tab.lit_len, 288, tab.lit_code);
+    bgzf_assign_codes(tab.dist_len, 32, tab.dist_code);
+    for (uint32_t i = 0; i < GLX_BGZF_HDR_WORDS; i++) tab.hdr_words[i] = 0;
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-    uint32_t hlit = 286, hdist = 30;
-    while (hlit > 257 && sh.lit_len[hlit - 1] == 0) hlit--;
-    while (hdist > 1 && sh.dist_len[hdist - 1] == 0) hdist--;
-    // run-length code of the concatenated length sequence, kept as tokens (symbol | extra value << 5)
+    const uint32_t hlit = 286, hdist = 30;  // every symbol has a code
     uint32_t cl_freq[19];
     uint8_t cl_len[19];
     uint16_t cl_code[19];
     for (int i = 0; i < 19; i++) cl_freq[i] = 0;
     const uint32_t n_all = hlit + hdist;
-    uint32_t nt = 0;
-    auto sink = [&](uint32_t sym, uint32_t ev) {
-        sh.hdr_tok[nt++] = (uint16_t)(sym | ev << 5);
-        cl_freq[sym]++;
-    };
-    uint32_t i = 0;
-    while (i < n_all) {
-        const uint32_t v = i < hlit ? sh.lit_len[i] : sh.dist_len[i - hlit];
-        uint32_t run = 1;
-        while (i + run < n_all && (i + run < hlit ? sh.lit_len[i + run] : sh.dist_len[i + run - hlit]) == v) run++;
-        i += run;
-        if (v == 0) {
-            while (run >= 11) {
-                const uint32_t t = run > 138 ? 138 : run;
-                sink(18, t - 11);
-                run -= t;
-            }
-            if (run >= 3) {
-                sink(17, run - 3);
-                run = 0;
-            }
-            while (run--) sink(0, 0);
-        } else {
-            sink(v, 0);
+    auto seq = [&](uint32_t i) -> uint32_t { return i < hlit ? tab.lit_len[i] : tab.dist_len[i - hlit]; };
+    auto walk = [&](auto&& sink) {  // all lengths are >= 1 here: a length, then repeats of it in groups of 3..6
+        uint32_t i = 0;
+        while (i < n_all) {
+            const uint32_t v = seq(i);
+            uint32_t run = 1;
+            while (i + run < n_all && seq(i + run) == v) run++;
+            i += run;
+            sink(v, 0, 0);
             run--;
             while (run >= 3) {
                 const uint32_t t = run > 6 ? 6 : run;
-                sink(16, t - 3);
+                sink(16, t - 3, 2);
                 run -= t;
             }
-            while (run--) sink(v, 0);
+            while (run--) sink(v, 0, 0);
         }
-    }
-    sh.n_hdr_tok = nt;
+    };
+    walk([&](uint32_t sym, uint32_t, uint32_t) { cl_freq[sym]++; });
     bgzf_code_lengths(cl_freq, 19, 7, cl_len);
     {
         uint32_t used = 0;
@@ -465,110 +457,23 @@ __host__ __device__ inline void bgzf_write_header(BgzfShared& sh, uint32_t* out_
     bgzf_assign_codes(cl_len, 19, cl_code);
     uint32_t hclen = 19;
     while (hclen > 4 && cl_len[order[hclen - 1]] == 0) hclen--;
-    BgzfBits bw{out_words, 0};
+    BgzfBits bw{tab.hdr_words, 0};
     bw.put(1, 1);  // BFINAL
     bw.put(2, 2);  // BTYPE = dynamic Huffman
     bw.put(hlit - 257, 5);
     bw.put(hdist - 1, 5);
     bw.put(hclen - 4, 4);
     for (uint32_t k = 0; k < hclen; k++) bw.put(cl_len[order[k]], 3);
-    for (uint32_t k = 0; k < nt; k++) {
-        const uint32_t sym = sh.hdr_tok[k] & 31u, ev = sh.hdr_tok[k] >> 5;
+    walk([&](uint32_t sym, uint32_t ev, uint32_t eb) {
         bw.put(cl_code[sym], cl_len[sym]);
-        bw.put(ev, sym == 16 ? 2u : (sym == 17 ? 3u : (sym == 18 ? 7u : 0u)));
-    }
-    sh.hdr_bits = bw.pos;
+        bw.put(ev, eb);
+    });
+    tab.hdr_bits = bw.pos;
 }
 
-// Both Huffman codes and the block header, by the whole block (every thread calls it). out_words = word-aligned, zeroed
-// start of the deflate data.
-__host__ __device__ inline void bgzf_build_codes(BgzfShared& sh, uint32_t* out_words, uint32_t tid, uint32_t nt) {
-    uint32_t* cnt = sh.wbits;  // scratch: [0..16) literal/length code-length counts, [16..32) distance, [32..34) used symbols
-    for (uint32_t i = tid; i < 40; i += nt) cnt[i] = 0;
-    if (tid == 0) sh.lit_total = sh.dist_total = sh.lit_kraft = sh.dist_kraft = 0;
-    GLX_BLOCK_SYNC();
-    for (uint32_t i = tid; i < 288 + 32; i += nt) {
-        const bool lit = i < 288;
-        const uint32_t f = lit ? (i < GLX_BGZF_LITS ? sh.lit_freq[i] : 0u) : (i - 288 < GLX_BGZF_DISTS ? sh.dist_freq[i - 288] : 0u);
-        if (f) {
-            bgzf_add(lit ? &sh.lit_total : &sh.dist_total, f);
-            bgzf_add(&cnt[lit ? 32 : 33], 1);
-        }
-    }
-    GLX_BLOCK_SYNC();
-    for (uint32_t i = tid; i < 288 + 32; i += nt) {
-        const bool lit = i < 288;
-        const uint32_t j = lit ? i : i - 288;
-        const uint32_t f = lit ? (j < GLX_BGZF_LITS ? sh.lit_freq[j] : 0u) : (j < GLX_BGZF_DISTS ? sh.dist_freq[j] : 0u);
-        uint32_t l = 0;
-        if (f) {
-            l = bgzf_len0(f, lit ? sh.lit_total : sh.dist_total, 15);
-            bgzf_add(lit ? &sh.lit_kraft : &sh.dist_kraft, 32768u >> l);
-        }
-        (lit ? sh.lit_len : sh.dist_len)[j] = (uint8_t)l;
-    }
-    GLX_BLOCK_SYNC();
-    // the two serial settles run side by side on two warps
-    if (tid == 0) bgzf_len_settle(sh.lit_freq, GLX_BGZF_LITS, 15, sh.lit_len, sh.lit_kraft, cnt[32]);
-    if (tid == (nt > 32 ? 32u : 0u)) {
-        bgzf_len_settle(sh.dist_freq, GLX_BGZF_DISTS, 15, sh.dist_len, sh.dist_kraft, cnt[33]);
-        if (cnt[33] == 0) sh.dist_len[0] = 1;  // "one distance code of one bit" keeps every inflater happy
-    }
-    GLX_BLOCK_SYNC();
-    // canonical codes: count per length, first code per length, then code = first + rank among earlier symbols of that length
-    for (uint32_t i = tid; i < 288 + 32; i += nt) {
-        const bool lit = i < 288;
-        const uint32_t l = lit ? sh.lit_len[i] : sh.dist_len[i - 288];
-        if (l) bgzf_add(&cnt[(lit ? 0 : 16) + l], 1);
-    }
-    GLX_BLOCK_SYNC();
-    if (tid == 0 || tid == (nt > 32 ? 32u : 0u)) {
-        for (uint32_t a = 0; a < 2; a++) {
-            if (nt > 32 && a != (tid ? 1u : 0u)) continue;
-            uint32_t* c = cnt + 16 * a;
-            uint32_t code = 0, prev = 0;
-            for (uint32_t b = 1; b < 16; b++) {  // c[b]: count -> first code of length b
-                code = (code + prev) << 1;
-                prev = c[b];
-                c[b] = code;
-            }
-        }
-    }
-    GLX_BLOCK_SYNC();
-    for (uint32_t i = tid; i < 288 + 32; i += nt) {
-        const bool lit = i < 288;
-        const uint32_t j = lit ? i : i - 288;
-        const uint8_t* len = lit ? sh.lit_len : sh.dist_len;
-        const uint32_t l = len[j];
-        uint32_t rank = 0;
-        for (uint32_t e = 0; e < j; e++) rank += len[e] == l;
-        (lit ? sh.lit_code : sh.dist_code)[j] = l ? (uint16_t)bgzf_rev(cnt[(lit ? 0 : 16) + l] + rank, l) : (uint16_t)0;
-    }
-    GLX_BLOCK_SYNC();
-    if (tid == 0) bgzf_write_header(sh, out_words);
-    GLX_BLOCK_SYNC();
-}
-
-// per-worker bit counts
-__host__ __device__ inline void bgzf_count_bits(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
-    for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
-        uint32_t bits = 0;
-        bgzf_replay(sh, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
-            if (!match) bits += sh.lit_len[v];
-            else {
-                uint32_t s, eb, ev;
-                bgzf_len_sym(v, s, eb, ev);
-                bits += sh.lit_len[s] + eb;
-                bgzf_dist_sym(d, s, eb, ev);
-                bits += sh.dist_len[s] + eb;
-            }
-        });
-        sh.wbits[w] = bits;
-    }
-}
 // exclusive scan of wbits (+ header bits); one thread here, a block scan in the kernel
 __host__ __device__ inline void bgzf_scan_bits_serial(BgzfShared& sh) {
-    uint32_t acc = sh.hdr_bits;
+    uint32_t acc = sh.tab.hdr_bits;
     for (uint32_t w = 0; w < GLX_BGZF_WORKERS; w++) {
         const uint32_t b = sh.wbits[w];
         sh.wbits[w] = acc;
@@ -576,8 +481,13 @@ __host__ __device__ inline void bgzf_scan_bits_serial(BgzfShared& sh) {
     }
     sh.data_bits = acc;  // position of the end-of-block code
 }
+// the header bits (whole words; the last, partial one is OR-ed because worker 0 shares it)
+__host__ __device__ inline void bgzf_put_header(const BgzfShared& sh, uint32_t* out_words, uint32_t tid, uint32_t nt) {
+    const uint32_t nw = (sh.tab.hdr_bits + 31) >> 5;
+    for (uint32_t i = tid; i < nw; i += nt) bgzf_or(&out_words[i], sh.tab.hdr_words[i]);
+}
 // each worker writes its codes at its bit offset: interior words are its own (plain stores), the two boundary words are shared
-__host__ __device__ inline void bgzf_emit(BgzfShared& sh, const uint8_t* in, uint32_t n, uint32_t* out_words, uint32_t tid, uint32_t nt) {
+__host__ __device__ inline void bgzf_emit(BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t* out_words, uint32_t tid, uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
         if (w * GLX_BGZF_CHUNK >= n) continue;
         const uint32_t pos = sh.wbits[w];
@@ -597,15 +507,15 @@ __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const uint8_t* in, uin
                 fill -= 32;
             }
         };
-        bgzf_replay(sh, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
-            if (!match) put(sh.lit_code[v], sh.lit_len[v]);
+        bgzf_replay(sh, T, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
+            if (!match) put(sh.tab.lit_code[v], sh.tab.lit_len[v]);
             else {
                 uint32_t s, eb, ev;
                 bgzf_len_sym(v, s, eb, ev);
-                put(sh.lit_code[s], sh.lit_len[s]);
+                put(sh.tab.lit_code[s], sh.tab.lit_len[s]);
                 put(ev, eb);
                 bgzf_dist_sym(d, s, eb, ev);
-                put(sh.dist_code[s], sh.dist_len[s]);
+                put(sh.tab.dist_code[s], sh.tab.dist_len[s]);
                 put(ev, eb);
             }
         });
@@ -613,11 +523,10 @@ __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const uint8_t* in, uin
     }
 }
 
-// one thread: end-of-block, stored fallback decision, BGZF header and trailer. `stage` = staging buffer (block at stage + GLX_BGZF_LEAD).
-// Returns via sh.block_len the total BGZF block size; sh.stored says whether the caller must copy the raw bytes (stored block).
+// one thread: end-of-block, stored fallback decision, total block length
 __host__ __device__ inline void bgzf_finish_deflate(BgzfShared& sh, uint32_t* out_words) {
     BgzfBits bw{out_words, sh.data_bits};
-    bw.put(sh.lit_code[256], sh.lit_len[256]);
+    bw.put(sh.tab.lit_code[256], sh.tab.lit_len[256]);
     const uint32_t dbytes = (bw.pos + 7) >> 3;
     sh.stored = dbytes >= sh.n_in + 5 ? 1u : 0u;
     sh.block_len = 18 + (sh.stored ? sh.n_in + 5 : dbytes) + 8;
@@ -639,52 +548,6 @@ __host__ __device__ inline void bgzf_store_raw(const BgzfShared& sh, const uint8
     const uint32_t n = sh.n_in;
     for (uint32_t i = tid; i < 5; i += nt) d[i] = i == 0 ? 1 : (i == 1 ? (uint8_t)(n & 0xff) : (i == 2 ? (uint8_t)(n >> 8) : (i == 3 ? (uint8_t)(~n & 0xff) : (uint8_t)((~n >> 8) & 0xff))));
     for (uint32_t i = tid; i < n; i += nt) d[5 + i] = in[BcfPadded::phys(i)];
-}
-
-// "same value at the previous record" distances of the span's FORMAT data segments (one thread). Segment starts are
-// span-relative; a segment that begins before the span starts at 0.
-__host__ __device__ inline void bgzf_segments(BgzfShared& sh, const BcfEnc& E, unsigned long long lo, unsigned long long hi) {
-    uint32_t ns = 0;
-    uint32_t prev = 0xffffffffu;  // previous site that has a record
-    const uint32_t s0 = bcf_first_site(E, lo);
-    for (uint32_t p = s0; p-- > 0;)
-        if (E.rec_off[p + 1] > E.rec_off[p]) {
-            prev = p;
-            break;
-        }
-    for (uint32_t s = s0; s < E.n_sites && E.rec_off[s] < hi && ns + 2 < GLX_BGZF_SEG_MAX; s++) {
-        const unsigned long long r0 = E.rec_off[s];
-        if (E.rec_off[s + 1] == r0) continue;
-        const BcfSitePlan& P = E.plan[s];
-        const unsigned long long ibase = r0 + 8 + P.l_shared;
-        // header + shared bytes: no structural distance
-        if (r0 >= lo || s == s0) {
-            sh.seg_start[ns] = r0 > lo ? (uint32_t)(r0 - lo) : 0u;
-            sh.seg_dist[ns] = 0;
-            ns++;
-        }
-        for (uint32_t b = 0; b < P.n_blk && ns + 2 < GLX_BGZF_SEG_MAX; b++) {
-            const unsigned long long dstart = ibase + P.blk_off[b] + P.blk_hdr_len[b];
-            const unsigned long long dend = dstart + (unsigned long long)E.n_samples * P.blk_cnt[b] * P.blk_width[b];
-            if (dend <= lo) continue;
-            if (dstart >= hi) break;
-            uint32_t dist = 0;
-            if (prev != 0xffffffffu) {
-                const BcfSitePlan& Q = E.plan[prev];
-                if (Q.n_blk == P.n_blk && Q.blk_cnt[b] == P.blk_cnt[b] && Q.blk_width[b] == P.blk_width[b]) {
-                    const unsigned long long pstart = E.rec_off[prev] + 8 + Q.l_shared + Q.blk_off[b] + Q.blk_hdr_len[b];
-                    const unsigned long long dd = dstart - pstart;
-                    if (dd <= 32768) dist = (uint32_t)dd;
-                }
-            }
-            // the block's own key/descriptor bytes belong to the previous segment; data starts here
-            sh.seg_start[ns] = dstart > lo ? (uint32_t)(dstart - lo) : 0u;
-            sh.seg_dist[ns] = dist;
-            ns++;
-        }
-        prev = s;
-    }
-    sh.n_seg = ns;
 }
 
 }  // namespace glxd

@@ -7,7 +7,7 @@
 #include <vector>
 
 #include "../../include/glx.h"
-#include "glx_bcf.cuh"
+#include "glx_bgzf.cuh"
 #include "glx_cell_fast.cuh"
 #include "glx_dev_types.cuh"
 
@@ -25,6 +25,7 @@ struct glx_ctx {
                                                      // per batch would synchronise the device and break pipelining)
     std::string err;
     int sm_count = 0;
+    uint32_t* crc_pw = nullptr;  // device: x^(8 * 64 * k) mod P for the BGZF stage's CRC-32
     uint8_t width_hint[GLX_MAX_FIELDS];  // narrow download: 1 when every value of the field in the previous batch fitted int8, else 2
     // kernel-path switches of the parity tests and ablations (glx_set_option); all 0 in production
     struct Options {
@@ -122,6 +123,9 @@ struct GlxBcfState {
     unsigned long long* totals = nullptr;  // device: {stream bytes, header-pool bytes, BGZF bytes, BGZF blocks}
     uint32_t* blk_sizes = nullptr;           // BGZF: size of each span's block, then
     unsigned long long* blk_offsets = nullptr;  // its offset in the contiguous output
+    uint32_t* span_site = nullptr;           // first site of every span
+    uint32_t* hist = nullptr;                // BGZF: symbol counts of the sampled spans
+    struct glxd::BgzfTable* table = nullptr; // BGZF: the batch's Huffman code + block header
     uint64_t stream_bound = 0, hdr_bound = 0;
     BcfEnc E;
     cudaEvent_t len_ev = nullptr;  // recorded when the lengths have landed in the batch's pinned words

@@ -505,6 +505,7 @@ void glx_destroy(glx_ctx* ctx) {
         if (c.p) cudaFree(c.p);
     for (auto& e : ctx->chunk_ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->crc_pw) cudaFree(ctx->crc_pw);
     if (ctx->host_err_pool) cudaFreeHost(ctx->host_err_pool);
     if (ctx->host_ovf_pool) cudaFreeHost(ctx->host_ovf_pool);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);

@@ -293,6 +293,7 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, int mode, void* stream);
 int glx_bcf_length(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n_bytes, uint64_t* n_raw_bytes, uint32_t* n_blocks);
 int glx_download_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, void* dst, uint64_t capacity, void* stream, int sync);
 int glx_bcf_record_offsets(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* rec_off /* [n_sites + 1] */);
+int glx_debug_bgzf_phases(glx_ctx* ctx, uint64_t cycles[16]); /* profiling aid: cycles per phase of the BGZF kernel since the last call */
 uint64_t glx_bcf_bound(const glx_dev_batch* dev);
 uint64_t glx_bcf_records(const glx_dev_batch* dev); /* records in the encoded batch; valid after glx_bcf_length */
 

@@ -34,6 +34,12 @@ def main():
         for _ in range(n):
             dev.encode_bcf(enc)
         print("encoded bytes, raw bytes, blocks:", dev.bcf_length())
+        if enc == 1:
+            cyc = ctx.bgzf_phase_cycles()
+            names = ["gather", "segments", "setup", "crc parts", "tokenize", "crc tree", "codes+header", "count+scan", "emit", "finish+store"]
+            tot = sum(cyc) or 1
+            print("BGZF kernel, thread-0 cycles per phase:", ", ".join(f"{nm} {100 * c / tot:.1f}%" for nm, c in zip(names, cyc)),
+                  f"; {tot / max(1, n * dev.bcf_length()[2]):.0f} cycles per block")
     print(f"{w}: {b.n_sites} sites x {b.n_samples} samples, {b.n_records} records, {dev.launch_count} kernels per launch")
     dev.close()
     ctx.close()

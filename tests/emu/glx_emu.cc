@@ -3,6 +3,8 @@
 // oracle without a GPU. Not part of libglx.so.
 #include "cuda_host_shim.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 
@@ -370,23 +372,24 @@ struct EmuBcf {
 
 // `span` = bytes per span (the device uses GLX_BCF_SPAN; small values exercise the clipping at span boundaries), `chunk` =
 // samples per scan block. *bytes is malloc'd (free()).
+#include "../../glnexus_b200/csrc/glx_bgzf.cuh"
 extern "C" int glx_emu_bcf_records(const glx_config* cfg, const glx_sites* sites, const glx_bcf_meta* meta, const glx_out* out, uint32_t span, uint32_t chunk,
                                    uint8_t** bytes, uint64_t* n_bytes, uint64_t* rec_off) {
     EmuBcf X(cfg, sites, meta, out, chunk);
-    uint8_t* o = (uint8_t*)malloc(X.total ? X.total : 1);
+    uint8_t* o = (uint8_t*)malloc(X.total ? X.total + 8 : 8);
     memset(o, 0xEE, X.total);
-    std::vector<uint16_t> s_src(GLX_BCF_G_MAX + 8);
+    auto tab = std::make_unique<BcfSpanTab>();
     if (span == 0) span = GLX_BCF_SPAN;
     for (unsigned long long lo = 0; lo < X.total; lo += span)
-        bcf_fill_span<BcfLinear>(X.E, lo, std::min<unsigned long long>(X.total, lo + span), o + lo, s_src.data(), 0, 1);
+        bcf_fill_span<BcfLinear>(X.E, lo, std::min<unsigned long long>(X.total, lo + span), bcf_first_site(X.E, lo), o + lo, *tab, 0, 1);
     for (uint32_t s = 0; s <= sites->n_sites; s++) rec_off[s] = X.roff[s];
     *bytes = o;
     *n_bytes = X.total;
     return 0;
 }
 
-// The BGZF stage (glx_bgzf.cuh) on top: every span becomes one BGZF block; the blocks are concatenated. `span` <= GLX_BCF_SPAN.
-#include "../../glnexus_b200/csrc/glx_bgzf.cuh"
+// The BGZF stage (glx_bgzf.cuh) on top: sample spans -> the batch's Huffman table -> every span becomes one BGZF block; the
+// blocks are concatenated. `span` <= GLX_BCF_SPAN.
 extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const glx_bcf_meta* meta, const glx_out* out, uint32_t span, uint8_t** bytes,
                             uint64_t* n_bytes, uint32_t* n_stored) {
     EmuBcf X(cfg, sites, meta, out, 0);
@@ -394,28 +397,39 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
     std::vector<uint8_t> all;
     std::vector<uint8_t> in(GLX_BGZF_IN_PAD + 64);
     std::vector<uint32_t> stage_w((GLX_BGZF_OUT + 64) / 4);
-    std::vector<uint16_t> s_src(GLX_BCF_G_MAX + 8);
+    std::vector<uint32_t> pw(GLX_BGZF_WORKERS + 1);
+    bgzf_crc_powers(pw.data());
     auto sh = std::make_unique<BgzfShared>();
+    auto tab = std::make_unique<BcfSpanTab>();
     *n_stored = 0;
+    const unsigned long long n_spans = (X.total + span - 1) / span;
+    // sampling pass
+    std::vector<uint32_t> hist(GLX_BGZF_HIST, 0);
+    const unsigned long long n_samp = std::min<unsigned long long>(n_spans, GLX_BGZF_SAMPLES);
+    for (unsigned long long i = 0; i < n_samp; i++) {
+        const unsigned long long b = n_spans <= GLX_BGZF_SAMPLES ? i : i * n_spans / GLX_BGZF_SAMPLES;
+        const unsigned long long lo = b * span, hi = std::min<unsigned long long>(X.total, lo + span);
+        for (uint32_t k = 0; k < GLX_BGZF_HIST; k++) sh->freq[k] = 0;
+        bcf_fill_span<BcfPadded>(X.E, lo, hi, bcf_first_site(X.E, lo), in.data(), *tab, 0, 1);
+        bgzf_tokenize<true, false>(*sh, *tab, in.data(), (uint32_t)(hi - lo), 0, 1);
+        for (uint32_t k = 0; k < GLX_BGZF_HIST; k++) hist[k] += sh->freq[k];
+    }
+    bgzf_table_build(hist.data(), sh->tab);
     for (unsigned long long lo = 0; lo < X.total; lo += span) {
         const unsigned long long hi = std::min<unsigned long long>(X.total, lo + span);
         const uint32_t n = (uint32_t)(hi - lo);
         std::fill(stage_w.begin(), stage_w.end(), 0u);
         uint8_t* stage = reinterpret_cast<uint8_t*>(stage_w.data());
         uint32_t* out_words = reinterpret_cast<uint32_t*>(stage + GLX_BGZF_LEAD + 18);
-        bcf_fill_span<BcfPadded>(X.E, lo, hi, in.data(), s_src.data(), 0, 1);
         sh->n_in = n;
-        bgzf_segments(*sh, X.E, lo, hi);
-        bgzf_crc_setup(*sh, n, 0, 1);
-        bgzf_hist_init(*sh, 0, 1);
-        bgzf_crc_parts(*sh, in.data(), n, 0, 1);
-        bgzf_tokenize(*sh, in.data(), n, 0, 1);
-        for (uint32_t l = 0; l < 10; l++) bgzf_crc_level(*sh, l, 0, 1);
-        bgzf_crc_finish(*sh);
-        bgzf_build_codes(*sh, out_words, 0, 1);
-        bgzf_count_bits(*sh, in.data(), n, 0, 1);
+        bgzf_crc_setup(*sh, 0, 1);
+        bcf_fill_span<BcfPadded>(X.E, lo, hi, bcf_first_site(X.E, lo), in.data(), *tab, 0, 1);
+        bgzf_put_header(*sh, out_words, 0, 1);
+        bgzf_crc_parts(*sh, pw.data(), in.data(), n, 0, 1);
+        bgzf_tokenize<false, true>(*sh, *tab, in.data(), n, 0, 1);
+        bgzf_crc_finish(*sh, pw.data());
         bgzf_scan_bits_serial(*sh);
-        bgzf_emit(*sh, in.data(), n, out_words, 0, 1);
+        bgzf_emit(*sh, *tab, in.data(), n, out_words, 0, 1);
         bgzf_finish_deflate(*sh, out_words);
         if (sh->stored) {
             bgzf_store_raw(*sh, in.data(), stage, 0, 1);
