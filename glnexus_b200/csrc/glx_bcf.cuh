@@ -554,7 +554,12 @@ struct BcfSpanTab {
     uint32_t km[GLX_BCF_TAB_MAX];    // keep mask of the site (GT renumbering, trimmed vectors)
     uint32_t dist[GLX_BCF_TAB_MAX];  // FORMAT data: distance to the same block's data in the previous record (0: none / other layout)
     uint8_t fld[GLX_BCF_TAB_MAX];    // lifted field index (trimmed vectors, strings)
-    unsigned long long roff[GLX_BCF_REC_MAX + 2];
+    // staged copies of what the pieces are made from: one round of independent global loads instead of dependent chains
+    BcfSitePlan plan[GLX_BCF_REC_MAX + 1];           // [0] = the site before the first, [1 + j] = site site0 + j
+    unsigned long long roff[GLX_BCF_REC_MAX + 3];    // [0] = rec_off[site0 - 1], [1 + j] = rec_off[site0 + j]
+    unsigned long long hoff[GLX_BCF_REC_MAX + 1];
+    unsigned long long foff[GLX_BCF_REC_MAX][GLX_MAX_FIELDS];
+    uint16_t fcnt[GLX_BCF_REC_MAX][GLX_MAX_FIELDS];
     uint32_t n, n_rec, site0, site_next, complete;  // complete: the table holds every piece of the span (one round)
     long long cov_lo, cov_hi;                       // span-relative byte range the table covers
 };
@@ -580,19 +585,38 @@ __host__ __device__ __forceinline__ uint32_t bcf_slot_src(uint8_t vl, uint32_t j
 // Pieces of the records of sites [s_begin, ...) that overlap span [lo, hi): as many records as the table holds. Every thread calls it.
 __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, unsigned long long lo, unsigned long long hi, uint32_t s_begin, uint32_t tid,
                                               uint32_t nt) {
-    const uint32_t slots = 1 + 2 * (E.n_fields + 2);  // pieces per record
+    const uint32_t F = E.n_fields, slots = 1 + 2 * (F + 2);  // pieces per record
     const uint32_t max_rec = GLX_BCF_TAB_MAX / slots < GLX_BCF_REC_MAX ? GLX_BCF_TAB_MAX / slots : GLX_BCF_REC_MAX;
-    for (uint32_t j = tid; j <= max_rec; j += nt) T.roff[j] = s_begin + j <= E.n_sites ? E.rec_off[s_begin + j] : ~0ull;
+    // ---- stage: offsets, plans and field layouts of sites s_begin - 1 .. s_begin + max_rec (every load independent) ----
+    for (uint32_t j = tid; j <= max_rec + 1; j += nt) {
+        const long long s = (long long)s_begin - 1 + j;
+        T.roff[j] = s < 0 ? 0ull : (s <= (long long)E.n_sites ? E.rec_off[s] : ~0ull);
+        if (j >= 1 && j <= max_rec) T.hoff[j - 1] = s < (long long)E.n_sites ? E.hdr_off[s] : 0ull;
+    }
+    {
+        constexpr uint32_t PW = sizeof(BcfSitePlan) / 4;
+        static_assert(sizeof(BcfSitePlan) % 4 == 0, "plans are copied as words");
+        uint32_t* dst = reinterpret_cast<uint32_t*>(T.plan);
+        for (uint32_t i = tid; i < (max_rec + 1) * PW; i += nt) {
+            const long long s = (long long)s_begin - 1 + i / PW;
+            dst[i] = (s >= 0 && s < (long long)E.n_sites) ? reinterpret_cast<const uint32_t*>(E.plan + s)[i % PW] : 0u;
+        }
+    }
+    for (uint32_t i = tid; i < max_rec * F; i += nt) {
+        const uint32_t j = i / F, k = i - j * F, s = s_begin + j;
+        T.fcnt[j][k] = s < E.n_sites ? E.fld_cnt[k][s] : (uint16_t)0;
+        T.foff[j][k] = s < E.n_sites ? E.fld_off[k][s] : 0ull;
+    }
     GLX_BLOCK_SYNC();
     if (tid == 0) {
         uint32_t nr = 0;
-        while (nr < max_rec && s_begin + nr < E.n_sites && T.roff[nr] < hi) nr++;
+        while (nr < max_rec && s_begin + nr < E.n_sites && T.roff[1 + nr] < hi) nr++;
         T.n_rec = nr;
         T.site0 = s_begin;
         T.site_next = s_begin + nr;
         T.n = nr * slots;
-        T.cov_lo = (long long)(T.roff[0] > lo ? T.roff[0] - lo : 0);
-        const unsigned long long end = nr ? T.roff[nr] : lo;  // roff[nr] = start of the first record not in the table
+        T.cov_lo = (long long)(T.roff[1] > lo ? T.roff[1] - lo : 0);
+        const unsigned long long end = nr ? T.roff[1 + nr] : lo;  // start of the first record not in the table
         T.cov_hi = (long long)((end < hi ? end : hi) - lo);
         T.start[nr * slots] = (long long)(end - lo);
     }
@@ -600,20 +624,20 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
     const uint32_t N = E.n_samples;
     for (uint32_t idx = tid; idx < T.n; idx += nt) {
         const uint32_t j = idx / slots, p = idx - j * slots, s = s_begin + j;
-        const unsigned long long r0 = T.roff[j];
-        const bool has = T.roff[j + 1] > r0;
-        const BcfSitePlan& P = E.plan[s];
+        const unsigned long long r0 = T.roff[1 + j];
+        const bool has = T.roff[2 + j] > r0;
+        const BcfSitePlan& P = T.plan[1 + j];
         long long st = (long long)(r0 - lo);
         const void* src = nullptr;
         uint32_t info = BCF_PK_BYTES, dist = 0, fld = 0;
         if (has) {
             const uint32_t hdr_len = 8 + P.l_shared;
             if (p == 0) {
-                src = E.hdr_pool + E.hdr_off[s];
+                src = E.hdr_pool + T.hoff[j];
             } else {
                 const uint32_t b = (p - 1) >> 1;
                 if (b >= P.n_blk) {
-                    st = (long long)(T.roff[j + 1] - lo);  // unused slot: empty piece at the record's end
+                    st = (long long)(T.roff[2 + j] - lo);  // unused slot: empty piece at the record's end
                 } else {
                     const unsigned long long bstart = r0 + hdr_len + P.blk_off[b];
                     if ((p - 1) & 1) {  // data
@@ -627,9 +651,9 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
                             src = E.rnc + (size_t)s * N * 2;
                             info = BCF_PK_BYTES | 1u << 4 | 2u << 8 | 2u << 20;
                         } else {
-                            const uint32_t k = b - 1, cnt = E.fld_cnt[k][s];
+                            const uint32_t k = b - 1, cnt = T.fcnt[j][k];
                             fld = k;
-                            src = E.fld[k] + E.fld_off[k][s];
+                            src = E.fld[k] + T.foff[j][k];
                             uint32_t kind;
                             if (E.fkind[k] == GLX_FK_FT || E.fkind[k] == GLX_FK_STRING) kind = BCF_PK_STR;
                             else if (P.trimmed && bcf_is_arg(E.fvl[k])) kind = BCF_PK_TRIM;
@@ -637,20 +661,19 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
                             else kind = BCF_PK_INT;
                             info = kind | w << 4 | (cn & 0xfffu) << 8 | (cnt & 0xfffu) << 20;
                         }
-                        // the same block's data in the previous record, if that record has the same layout
-                        uint32_t q = s;
-                        while (q-- > 0)
-                            if (E.rec_off[q + 1] > E.rec_off[q]) break;
-                        if (q != 0xffffffffu) {
-                            const BcfSitePlan& Q = E.plan[q];
-                            if (Q.n_blk == P.n_blk && Q.blk_cnt[b] == P.blk_cnt[b] && Q.blk_width[b] == P.blk_width[b]) {
-                                const unsigned long long pstart = E.rec_off[q] + 8 + Q.l_shared + Q.blk_off[b] + Q.blk_hdr_len[b];
+                        // the same block's data in the record just before, if that site has a record of the same layout
+                        int u = (int)j;  // staged index of the nearest earlier site that has a record (u = 0: the site before s_begin)
+                        while (u >= 0 && !(T.roff[u + 1] > T.roff[u])) u--;
+                        if (u >= 0 && (u > 0 || s_begin > 0)) {
+                            const BcfSitePlan& Q = T.plan[u];
+                            if (Q.keep_mask && Q.n_blk == P.n_blk && Q.blk_cnt[b] == P.blk_cnt[b] && Q.blk_width[b] == P.blk_width[b]) {
+                                const unsigned long long pstart = T.roff[u] + 8 + Q.l_shared + Q.blk_off[b] + Q.blk_hdr_len[b];
                                 if (dstart - pstart <= 32768) dist = (uint32_t)(dstart - pstart);
                             }
                         }
                     } else {  // the block's typed key + descriptor
                         st = (long long)(bstart - lo);
-                        src = P.blk_hdr[b];
+                        src = P.blk_hdr[b];  // the staged copy: valid until the table is rebuilt
                     }
                 }
             }
@@ -708,55 +731,75 @@ __host__ __device__ inline uint8_t bcf_piece_byte(const BcfEnc& E, const BcfSpan
     }
 }
 
-// fill the covered bytes of the span from the table, one 4-byte word per thread and step
+// One aligned 4-byte word of the span taken wholly from a typed vector: byte offset `off` of the piece's data.
+__host__ __device__ __forceinline__ uint32_t bcf_piece_word(const void* src, uint32_t kind, uint32_t w, uint32_t km, unsigned long long off) {
+    if (kind == BCF_PK_INT && w == 1) {
+        const int32_t* v = static_cast<const int32_t*>(src) + off;
+        return bcf_conv(v[0], 1) | bcf_conv(v[1], 1) << 8 | bcf_conv(v[2], 1) << 16 | bcf_conv(v[3], 1) << 24;
+    }
+    if (kind == BCF_PK_INT && w == 2) {  // three values when the word starts in the middle of one
+        const int32_t* v = static_cast<const int32_t*>(src) + (off >> 1);
+        unsigned long long x = (unsigned long long)(bcf_conv(v[0], 2) & 0xffffu) | (unsigned long long)(bcf_conv(v[1], 2) & 0xffffu) << 16;
+        if (off & 1) x |= (unsigned long long)(bcf_conv(v[2], 2) & 0xffffu) << 32;
+        return (uint32_t)(x >> (8 * (off & 1)));
+    }
+    if (kind == BCF_PK_INT || kind == BCF_PK_RAW4) {
+        const int32_t* v = static_cast<const int32_t*>(src) + (off >> 2);
+        unsigned long long x = (uint32_t)v[0];
+        if (off & 3) x |= (unsigned long long)(uint32_t)v[1] << 32;
+        return (uint32_t)(x >> (8 * (off & 3)));
+    }
+    if (kind == BCF_PK_GT) {
+        const int8_t* g = static_cast<const int8_t*>(src) + off;
+        uint32_t word = 0;
+        for (int i = 0; i < 4; i++) {
+            const int al = g[i];
+            word |= (al < 0 ? 0u : (uint32_t)((bcf_popc(km & ((1u << al) - 1u)) + 1) << 1)) << (8 * i);
+        }
+        return word;
+    }
+    const uint8_t* c = static_cast<const uint8_t*>(src) + off;
+    return c[0] | c[1] << 8 | c[2] << 16 | (uint32_t)c[3] << 24;
+}
+template <class Addr>
+__host__ __device__ __forceinline__ void bcf_put_word(uint8_t* buf, long long x0, uint32_t word) {  // both layouts keep an aligned word contiguous
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint32_t*>(buf + Addr::phys((unsigned long long)x0)) = word;
+#else
+    memcpy(buf + Addr::phys((unsigned long long)x0), &word, 4);  // the host build also runs odd span sizes
+#endif
+}
+
+// Fill the covered bytes of the span from the table. The span is cut into 1 KB items; a warp takes an item, walks the pieces
+// that overlap it and converts their words lane by lane, two independent words per lane in flight — 32 warps on 32 items.
 template <class Addr>
 __host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, const BcfSpanTab& T, uint8_t* buf, uint32_t tid, uint32_t nt) {
     if (T.cov_hi <= T.cov_lo) return;
-    const long long w0 = T.cov_lo >> 2, w1 = (T.cov_hi + 3) >> 2;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 4
-#endif
-    for (long long wi = w0 + tid; wi < w1; wi += nt) {
-        const long long x0 = wi << 2;
-        const long long a = x0 < T.cov_lo ? T.cov_lo : x0, e = x0 + 4 > T.cov_hi ? T.cov_hi : x0 + 4;
-        const uint32_t p = bcf_tab_find(T, a);
-        const uint32_t info = T.info[p], kind = info & 15u, w = info >> 4 & 15u;
-        const long long off = a - T.start[p];
-        if (e - a == 4 && T.start[p + 1] >= e && (kind == BCF_PK_INT || kind == BCF_PK_RAW4 || kind == BCF_PK_GT || (kind == BCF_PK_BYTES && w == 1)) &&
-            (w == 1 || (off % w) == 0)) {
-            // the whole word comes from one typed vector, element-aligned: 4, 2 or 1 source values
-            uint32_t word;
-            if (kind == BCF_PK_INT && w == 1) {
-                const int32_t* v = static_cast<const int32_t*>(T.src[p]) + off;
-                word = bcf_conv(v[0], 1) | bcf_conv(v[1], 1) << 8 | bcf_conv(v[2], 1) << 16 | bcf_conv(v[3], 1) << 24;
-            } else if (kind == BCF_PK_INT && w == 2) {
-                const int32_t* v = static_cast<const int32_t*>(T.src[p]) + off / 2;
-                word = bcf_conv(v[0], 2) | bcf_conv(v[1], 2) << 16;
-            } else if (kind == BCF_PK_INT || kind == BCF_PK_RAW4) {
-                word = (uint32_t) static_cast<const int32_t*>(T.src[p])[off >> 2];
-            } else if (kind == BCF_PK_GT) {
-                const int8_t* g = static_cast<const int8_t*>(T.src[p]) + off;
-                const uint32_t km = T.km[p];
-                word = 0;
-                for (int i = 0; i < 4; i++) {
-                    const int al = g[i];
-                    word |= (al < 0 ? 0u : (uint32_t)((bcf_popc(km & ((1u << al) - 1u)) + 1) << 1)) << (8 * i);
+    const uint32_t n_lanes = nt < 32 ? nt : 32, lane = tid % n_lanes, warp = tid / n_lanes, n_warps = nt / n_lanes;
+    const long long it0 = T.cov_lo >> 10, it1 = (T.cov_hi + 1023) >> 10;
+    for (long long it = it0 + warp; it < it1; it += n_warps) {
+        const long long a_it = (it << 10) < T.cov_lo ? T.cov_lo : (it << 10), e_it = ((it + 1) << 10) > T.cov_hi ? T.cov_hi : ((it + 1) << 10);
+        for (uint32_t p = bcf_tab_find(T, a_it); p < T.n && T.start[p] < e_it; p++) {
+            const long long ps = T.start[p] < a_it ? a_it : T.start[p], pe = T.start[p + 1] > e_it ? e_it : T.start[p + 1];
+            if (pe <= ps) continue;
+            const long long base = T.start[p];
+            const uint32_t info = T.info[p], kind = info & 15u, w = info >> 4 & 15u, km = T.km[p];
+            const void* src = T.src[p];
+            const bool fast = kind == BCF_PK_INT || kind == BCF_PK_RAW4 || kind == BCF_PK_GT || (kind == BCF_PK_BYTES && w == 1);
+            long long wa = (ps + 3) & ~3ll, we = pe & ~3ll;
+            if (!fast || wa >= we) wa = we = pe;  // everything byte by byte
+            for (long long x = ps + lane; x < (wa < pe ? wa : pe); x += n_lanes) buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(x - base));
+            if (wa < we) {
+                const long long step = 4ll * n_lanes;
+                long long x0 = wa + 4ll * lane;
+                for (; x0 + step < we; x0 += 2 * step) {
+                    const uint32_t u = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base));
+                    const uint32_t v = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 + step - base));
+                    bcf_put_word<Addr>(buf, x0, u);
+                    bcf_put_word<Addr>(buf, x0 + step, v);
                 }
-            } else {
-                const uint8_t* c = static_cast<const uint8_t*>(T.src[p]) + off;
-                word = c[0] | c[1] << 8 | c[2] << 16 | (uint32_t)c[3] << 24;
-            }
-            // both layouts keep an aligned word contiguous
-#if defined(__CUDA_ARCH__)
-            *reinterpret_cast<uint32_t*>(buf + Addr::phys((unsigned long long)x0)) = word;
-#else
-            memcpy(buf + Addr::phys((unsigned long long)x0), &word, 4);  // the host build also runs odd span sizes
-#endif
-        } else {
-            uint32_t q = p;
-            for (long long x = a; x < e; x++) {
-                while (T.start[q + 1] <= x) q++;
-                buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, q, (unsigned long long)(x - T.start[q]));
+                if (x0 < we) bcf_put_word<Addr>(buf, x0, bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base)));
+                for (long long x = we + lane; x < pe; x += n_lanes) buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(x - base));
             }
         }
     }
@@ -772,7 +815,7 @@ __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long lon
         bcf_tab_build(E, T, lo, hi, s, tid, nt);
         bcf_tab_fill<Addr>(E, T, buf, tid, nt);
         const uint32_t next = T.site_next;
-        const bool more = next < E.n_sites && T.n_rec > 0 && T.roff[T.n_rec] < hi;
+        const bool more = next < E.n_sites && T.n_rec > 0 && T.roff[1 + T.n_rec] < hi;
         rounds++;
         GLX_BLOCK_SYNC();  // the table is rebuilt (or read by the caller) after everyone has finished with it
         if (!more) break;

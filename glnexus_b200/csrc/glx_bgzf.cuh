@@ -204,8 +204,36 @@ __host__ __device__ __forceinline__ uint32_t bgzf_popcll(unsigned long long m) {
     return (uint32_t)__builtin_popcountll(m);
 #endif
 }
-// the structural distance at span byte x: the piece table's, when it holds the whole span
-__host__ __device__ __forceinline__ uint32_t bgzf_dist_at(const BcfSpanTab& T, uint32_t x) { return T.complete && T.n ? T.dist[bcf_tab_find(T, (long long)x)] : 0u; }
+// What a worker needs to know about the pieces under its 64-byte chunk: where another piece starts inside it (a D-match
+// must not run across: the distance changes) and the structural distance of the first four pieces (more: no D-matches there).
+struct BgzfChunkCtx {
+    unsigned long long brk;  // bit i (i >= 1): a piece starts at chunk byte i
+    uint32_t D[4];
+    uint32_t a[4], e[4];  // span-relative byte range of those pieces inside the chunk
+    uint32_t np;
+};
+__host__ __device__ inline void bgzf_chunk_ctx(const BcfSpanTab& T, uint32_t c0, uint32_t L, BgzfChunkCtx& C) {
+    C.brk = 0;
+    C.np = 0;
+    for (int i = 0; i < 4; i++) C.D[i] = C.a[i] = C.e[i] = 0;
+    if (!T.complete || !T.n) return;
+    for (uint32_t pc = bcf_tab_find(T, (long long)c0); pc < T.n && T.start[pc] < (long long)(c0 + L); pc++) {
+        const long long ps = T.start[pc], pe = T.start[pc + 1];
+        if (pe <= ps) continue;
+        if (ps > (long long)c0) C.brk |= 1ull << (ps - c0);
+        if (C.np < 4) {
+            const uint32_t D = T.dist[pc];
+            C.D[C.np] = (D > 1 && D <= 32768) ? D : 0u;
+            C.a[C.np] = ps > (long long)c0 ? (uint32_t)ps : c0;
+            C.e[C.np] = pe < (long long)(c0 + L) ? (uint32_t)pe : c0 + L;
+        }
+        C.np++;
+    }
+}
+__host__ __device__ __forceinline__ uint32_t bgzf_D_at(const BgzfChunkCtx& C, uint32_t p) {  // distance of the piece holding chunk byte p
+    const uint32_t ord = bgzf_popcll(C.brk & ((2ull << p) - 1ull));
+    return ord < 4 ? C.D[ord] : 0u;
+}
 
 // the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance)
 template <class F>
@@ -215,20 +243,23 @@ __host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const BcfSpanT
     const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
     unsigned long long t = sh.tok[w];
     const unsigned long long useD = sh.useD[w];
+    BgzfChunkCtx C;
+    if (useD) bgzf_chunk_ctx(T, c0, L, C);
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));
     while (t) {
         const uint32_t p = bgzf_lowbit(t);
         t &= t - 1;
         const uint32_t q = t ? bgzf_lowbit(t) : L;
-        if (q - p < 3) emit(false, (uint32_t)in[BcfPadded::phys(c0 + p)], 0u);
-        else emit(true, q - p, (useD >> p & 1ull) ? bgzf_dist_at(T, c0 + p) : 1u);
+        if (q - p < 3) emit(false, (W[p >> 2] >> (8 * (p & 3))) & 0xffu, 0u);
+        else emit(true, q - p, (useD >> p & 1ull) ? bgzf_D_at(C, p) : 1u);
     }
 }
 
 // Worker w owns bytes [64w, 64w+64) of the span (in = the BcfPadded staging buffer). It finds, per byte, whether the byte
 // repeats the one before it (distance 1) and whether it repeats the byte at the structural distance D of its piece, as two
-// 64-bit masks, then walks them greedily — a D-match of >= 4 bytes that is longer than the distance-1 run, else a distance-1
-// run of >= 3, else a literal — recording the token starts. Matches end at the chunk's end and at piece boundaries.
-// HIST: count the symbols into sh.freq (sampling). COUNT: the worker's bit count under sh.tab into sh.wbits.
+// 64-bit masks (word-wise compares), then walks them greedily — a D-match of >= 4 bytes that is longer than the distance-1
+// run, else a distance-1 run of >= 3, else a literal — recording the token starts. Matches end at the chunk's end and at
+// piece boundaries. HIST: count the symbols into sh.freq (sampling). COUNT: the worker's bit count under sh.tab into sh.wbits.
 template <bool HIST, bool COUNT>
 __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
@@ -251,20 +282,33 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& 
         }
         if (!c0) eq1 &= ~1ull;  // the span's first byte has no predecessor
         eq1 &= live;
-        unsigned long long eqD = 0, brk = 0;  // brk: another piece (another D) starts here: a D-match must not run across
-        if (T.complete && T.n) {
-            uint32_t pc = bcf_tab_find(T, (long long)c0);
-            for (; pc < T.n && T.start[pc] < (long long)(c0 + L); pc++) {
-                const long long ps = T.start[pc], pe = T.start[pc + 1];
-                if (pe <= ps) continue;
-                if (ps > (long long)c0) brk |= 1ull << (ps - c0);
-                const uint32_t D = T.dist[pc];
-                if (D <= 1 || D > 32768) continue;
-                const uint32_t a = ps > (long long)c0 ? (uint32_t)ps : c0;
-                const uint32_t e = pe < (long long)(c0 + L) ? (uint32_t)pe : c0 + L;
-                for (uint32_t i = a < D ? D : a; i < e; i++)
-                    if (in[BcfPadded::phys(i)] == in[BcfPadded::phys(i - D)]) eqD |= 1ull << (i - c0);
+        BgzfChunkCtx C;
+        bgzf_chunk_ctx(T, c0, L, C);
+        unsigned long long eqD = 0;
+        for (uint32_t pi = 0; pi < (C.np < 4 ? C.np : 4u); pi++) {
+            const uint32_t D = C.D[pi];
+            if (!D) continue;
+            const uint32_t a = C.a[pi] < D ? D : C.a[pi], e = C.e[pi];  // positions below D have no source inside the span
+            if (a >= e) continue;
+            unsigned long long m = 0;
+            for (uint32_t k = (a - c0) >> 2; k <= (e - 1 - c0) >> 2; k++) {
+                const uint32_t i0 = c0 + 4 * k;
+                uint32_t ref;
+                if (i0 >= D) {
+                    const uint32_t r0 = i0 - D, al = r0 & ~3u, shf = (r0 & 3u) * 8;
+                    const uint32_t lo = *reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(al));
+                    const uint32_t hi = *reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(al + 4));
+                    ref = shf ? (lo >> shf) | (hi << (32 - shf)) : lo;
+                } else {  // the word straddles position D: its first bytes have no source; they are masked below
+                    ref = 0;
+                    for (uint32_t bb = 0; bb < 4; bb++)
+                        if (i0 + bb >= D) ref |= (uint32_t)in[BcfPadded::phys(i0 + bb - D)] << (8 * bb);
+                }
+                m |= (unsigned long long)bgzf_eq_nibble(W[k], ref) << (4 * k);
             }
+            const uint32_t ra = a - c0, re = e - c0;  // keep positions [ra, re)
+            const unsigned long long keep = (re >= 64 ? ~0ull : ((1ull << re) - 1)) & ~((1ull << ra) - 1);
+            eqD |= m & keep;
         }
         unsigned long long tok = 0, useD = 0, lits = 0;
         uint32_t i = 0;
@@ -272,7 +316,7 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& 
             const uint32_t r1 = bgzf_run(eq1, i);
             uint32_t rD = bgzf_run(eqD, i);
             if (i < 63) {
-                const unsigned long long nb = brk >> (i + 1);
+                const unsigned long long nb = C.brk >> (i + 1);
                 if (nb) {
                     const uint32_t lim = bgzf_lowbit(nb) + 1;
                     rD = rD < lim ? rD : lim;
@@ -295,19 +339,25 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& 
             // zero is by far the most common literal of typed integer vectors: one add for all of the worker's
             const uint32_t nz = bgzf_popcll(lits & zero);
             if (nz) bgzf_add(&sh.freq[0], nz);
-            for (unsigned long long m = lits & ~zero; m; m &= m - 1) bgzf_add(&sh.freq[in[BcfPadded::phys(c0 + bgzf_lowbit(m))]], 1);
+            for (unsigned long long m = lits & ~zero; m; m &= m - 1) {
+                const uint32_t p = bgzf_lowbit(m);
+                bgzf_add(&sh.freq[(W[p >> 2] >> (8 * (p & 3))) & 0xffu], 1);
+            }
         }
         if (HIST || COUNT) {
             uint32_t bits = 0;
             if (COUNT)
-                for (unsigned long long m = lits; m; m &= m - 1) bits += sh.tab.lit_len[in[BcfPadded::phys(c0 + bgzf_lowbit(m))]];
+                for (unsigned long long m = lits; m; m &= m - 1) {
+                    const uint32_t p = bgzf_lowbit(m);
+                    bits += sh.tab.lit_len[(W[p >> 2] >> (8 * (p & 3))) & 0xffu];
+                }
             for (unsigned long long t = tok & ~lits; t; t &= t - 1) {  // matches
                 const uint32_t p = bgzf_lowbit(t);
                 const unsigned long long rest = tok >> p >> 1;
                 const uint32_t q = rest ? p + 1 + bgzf_lowbit(rest) : L;
                 uint32_t sym, eb, ev, dsym, deb;
                 bgzf_len_sym(q - p, sym, eb, ev);
-                bgzf_dist_sym((useD >> p & 1ull) ? bgzf_dist_at(T, c0 + p) : 1u, dsym, deb, ev);
+                bgzf_dist_sym((useD >> p & 1ull) ? bgzf_D_at(C, p) : 1u, dsym, deb, ev);
                 if (HIST) {
                     bgzf_add(&sh.freq[sym], 1);
                     bgzf_add(&sh.freq[288 + dsym], 1);
