@@ -548,7 +548,7 @@ struct BcfPadded {
 #define GLX_BCF_REC_MAX 24
 enum { BCF_PK_BYTES = 0, BCF_PK_GT = 1, BCF_PK_INT = 2, BCF_PK_RAW4 = 3, BCF_PK_TRIM = 4, BCF_PK_STR = 5 };
 struct BcfSpanTab {
-    long long start[GLX_BCF_TAB_MAX + 1];  // span-relative offset of the piece's first byte (negative: begins before the span); non-decreasing; [n] = end
+    int32_t start[GLX_BCF_TAB_MAX + 1];    // span-relative offset of the piece's first byte (negative: begins before the span); non-decreasing; [n] = end
     const void* src[GLX_BCF_TAB_MAX];
     uint32_t info[GLX_BCF_TAB_MAX];  // kind | width << 4 | values per sample after trimming << 8 | values per sample in the source << 20
     uint32_t km[GLX_BCF_TAB_MAX];    // keep mask of the site (GT renumbering, trimmed vectors)
@@ -618,7 +618,7 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
         T.cov_lo = (long long)(T.roff[1] > lo ? T.roff[1] - lo : 0);
         const unsigned long long end = nr ? T.roff[1 + nr] : lo;  // start of the first record not in the table
         T.cov_hi = (long long)((end < hi ? end : hi) - lo);
-        T.start[nr * slots] = (long long)(end - lo);
+        T.start[nr * slots] = (int32_t)(long long)(end - lo);
     }
     GLX_BLOCK_SYNC();
     const uint32_t N = E.n_samples;
@@ -678,7 +678,7 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
                 }
             }
         }
-        T.start[idx] = st;
+        T.start[idx] = (int32_t)st;
         T.src[idx] = src;
         T.info[idx] = info;
         T.km[idx] = has ? P.keep_mask : 0u;
@@ -689,7 +689,8 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
 }
 
 // piece holding span byte x (x inside the table's coverage): last piece with start <= x
-__host__ __device__ __forceinline__ uint32_t bcf_tab_find(const BcfSpanTab& T, long long x) {
+__host__ __device__ __forceinline__ uint32_t bcf_tab_find(const BcfSpanTab& T, long long x_) {
+    const int32_t x = (int32_t)x_;
     uint32_t a = 0, b = T.n;
     while (a < b) {
         const uint32_t mid = (a + b) >> 1;

@@ -40,6 +40,7 @@ namespace glxd {
 struct BgzfTable {
     uint8_t lit_len[288], dist_len[32];
     uint16_t lit_code[288], dist_code[32];  // bit-reversed canonical codes
+    uint32_t lit_cl[288], dist_cl[32];      // code | length << 16: one load per symbol when emitting
     uint32_t hdr_bits;
     uint32_t hdr_words[GLX_BGZF_HDR_WORDS];
 };
@@ -235,24 +236,44 @@ __host__ __device__ __forceinline__ uint32_t bgzf_D_at(const BgzfChunkCtx& C, ui
     return ord < 4 ? C.D[ord] : 0u;
 }
 
-// the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance)
+__host__ __device__ __forceinline__ uint32_t bgzf_low32(uint32_t m) {  // index of the lowest set bit, m != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)m) - 1;
+#else
+    return (uint32_t)__builtin_ffs((int)m) - 1;
+#endif
+}
+// the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance). The start mask is walked
+// as two 32-bit halves, one token behind (a token ends where the next one starts).
 template <class F>
 __host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t w, F&& emit) {
     const uint32_t c0 = w * GLX_BGZF_CHUNK;
     if (c0 >= n) return;
     const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
-    unsigned long long t = sh.tok[w];
-    const unsigned long long useD = sh.useD[w];
+    const unsigned long long t = sh.tok[w], useD = sh.useD[w];
     BgzfChunkCtx C;
     if (useD) bgzf_chunk_ctx(T, c0, L, C);
     const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));
-    while (t) {
-        const uint32_t p = bgzf_lowbit(t);
-        t &= t - 1;
-        const uint32_t q = t ? bgzf_lowbit(t) : L;
+    uint32_t prev = 0;  // bit 0 of tok is always set: the chunk's first token starts at 0
+    auto token = [&](uint32_t p, uint32_t q) {
         if (q - p < 3) emit(false, (W[p >> 2] >> (8 * (p & 3))) & 0xffu, 0u);
         else emit(true, q - p, (useD >> p & 1ull) ? bgzf_D_at(C, p) : 1u);
+    };
+    uint32_t m = (uint32_t)t & ~1u;
+    while (m) {
+        const uint32_t q = bgzf_low32(m);
+        m &= m - 1;
+        token(prev, q);
+        prev = q;
     }
+    m = (uint32_t)(t >> 32);
+    while (m) {
+        const uint32_t q = 32 + bgzf_low32(m);
+        m &= m - 1;
+        token(prev, q);
+        prev = q;
+    }
+    token(prev, L);
 }
 
 // Worker w owns bytes [64w, 64w+64) of the span (in = the BcfPadded staging buffer). It finds, per byte, whether the byte
@@ -310,29 +331,33 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& 
             const unsigned long long keep = (re >= 64 ? ~0ull : ((1ull << re) - 1)) & ~((1ull << ra) - 1);
             eqD |= m & keep;
         }
+        // greedy walk, jumping from candidate to candidate: a distance-1 run of >= 3 or a D-run of >= 4 can only start where
+        // the next 3 (4) mask bits are set; everything in between is literals
+        const unsigned long long contD = eqD & ~C.brk;  // a D-run continues into byte j iff eqD[j] and no piece starts there
+        const unsigned long long cand1 = eq1 & (eq1 >> 1) & (eq1 >> 2);
+        const unsigned long long candD = eqD & (contD >> 1) & (contD >> 2) & (contD >> 3);
+        const unsigned long long cand = cand1 | candD;
         unsigned long long tok = 0, useD = 0, lits = 0;
         uint32_t i = 0;
         while (i < L) {
-            const uint32_t r1 = bgzf_run(eq1, i);
-            uint32_t rD = bgzf_run(eqD, i);
-            if (i < 63) {
-                const unsigned long long nb = C.brk >> (i + 1);
-                if (nb) {
-                    const uint32_t lim = bgzf_lowbit(nb) + 1;
-                    rD = rD < lim ? rD : lim;
-                }
+            const unsigned long long c = cand >> i;
+            if (!c) {  // literals to the end
+                lits |= live & ~((1ull << i) - 1);
+                break;
             }
-            tok |= 1ull << i;
+            const uint32_t j = i + bgzf_lowbit(c);
+            if (j > i) lits |= ((1ull << j) - 1) & ~((1ull << i) - 1);
+            const uint32_t r1 = bgzf_run(eq1, j);
+            const uint32_t rD = (eqD >> j & 1ull) ? 1 + (j < 63 ? bgzf_run(contD, j + 1) : 0u) : 0u;
+            tok |= 1ull << j;
             if (rD >= 4 && rD > r1) {
-                useD |= 1ull << i;
-                i += rD;
-            } else if (r1 >= 3) {
-                i += r1;
+                useD |= 1ull << j;
+                i = j + rD;
             } else {
-                lits |= 1ull << i;
-                i++;
+                i = j + r1;  // a candidate that is not a D-match is a distance-1 run of >= 3
             }
         }
+        tok |= lits;
         sh.tok[w] = tok;
         sh.useD[w] = useD;
         if (HIST) {
@@ -346,11 +371,18 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& 
         }
         if (HIST || COUNT) {
             uint32_t bits = 0;
-            if (COUNT)
-                for (unsigned long long m = lits; m; m &= m - 1) {
-                    const uint32_t p = bgzf_lowbit(m);
-                    bits += sh.tab.lit_len[(W[p >> 2] >> (8 * (p & 3))) & 0xffu];
+            if (COUNT) {
+                const uint32_t lo = (uint32_t)lits, hi = (uint32_t)(lits >> 32);
+                for (uint32_t k = 0; k < 16; k++) {
+                    const uint32_t nib = ((k < 8 ? lo : hi) >> (4 * (k & 7))) & 15u;
+                    if (!nib) continue;
+                    const uint32_t x = W[k];
+                    if (nib & 1u) bits += sh.tab.lit_len[x & 0xffu];
+                    if (nib & 2u) bits += sh.tab.lit_len[x >> 8 & 0xffu];
+                    if (nib & 4u) bits += sh.tab.lit_len[x >> 16 & 0xffu];
+                    if (nib & 8u) bits += sh.tab.lit_len[x >> 24];
                 }
+            }
             for (unsigned long long t = tok & ~lits; t; t &= t - 1) {  // matches
                 const uint32_t p = bgzf_lowbit(t);
                 const unsigned long long rest = tok >> p >> 1;
@@ -465,6 +497,8 @@ __host__ __device__ inline void bgzf_table_build(const uint32_t* freq, BgzfTable
     tab.dist_len[30] = tab.dist_len[31] = 0;
     bgzf_assign_codes(tab.lit_len, 288, tab.lit_code);
     bgzf_assign_codes(tab.dist_len, 32, tab.dist_code);
+    for (uint32_t i = 0; i < 288; i++) tab.lit_cl[i] = tab.lit_code[i] | (uint32_t)tab.lit_len[i] << 16;
+    for (uint32_t i = 0; i < 32; i++) tab.dist_cl[i] = tab.dist_code[i] | (uint32_t)tab.dist_len[i] << 16;
     for (uint32_t i = 0; i < GLX_BGZF_HDR_WORDS; i++) tab.hdr_words[i] = 0;
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     const uint32_t hlit = 286, hdist = 30;  // every symbol has a code
@@ -558,14 +592,17 @@ __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const BcfSpanTab& T, c
             }
         };
         bgzf_replay(sh, T, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
-            if (!match) put(sh.tab.lit_code[v], sh.tab.lit_len[v]);
-            else {
+            if (!match) {
+                const uint32_t cl = sh.tab.lit_cl[v];
+                put(cl & 0xffffu, cl >> 16);
+            } else {
                 uint32_t s, eb, ev;
                 bgzf_len_sym(v, s, eb, ev);
-                put(sh.tab.lit_code[s], sh.tab.lit_len[s]);
-                put(ev, eb);
+                uint32_t cl = sh.tab.lit_cl[s];
+                put((cl & 0xffffu) | ev << (cl >> 16), (cl >> 16) + eb);  // code (<= 15 bits) and its extra bits (<= 5) in one go
                 bgzf_dist_sym(d, s, eb, ev);
-                put(sh.tab.dist_code[s], sh.tab.dist_len[s]);
+                cl = sh.tab.dist_cl[s];
+                put(cl & 0xffffu, cl >> 16);
                 put(ev, eb);
             }
         });
