@@ -526,9 +526,10 @@ __host__ __device__ __forceinline__ uint32_t bcf_first_site(const BcfEnc& E, uns
     return a;
 }
 __host__ __device__ __forceinline__ uint32_t bcf_conv(int32_t v, uint32_t width) {
-    if (width == 4) return (uint32_t)v;
-    if (v == GLXB_MISSING) return width == 1 ? 0x80u : 0x8000u;
-    if (v == GLXB_VEND) return width == 1 ? 0x81u : 0x8001u;
+    // bcf_int32_missing / vector_end (0x80000000 / 0x80000001) -> the narrow type's own sentinels (0x80 / 0x81, 0x8000 / 0x8001);
+    // every other value of a vector typed int8 / int16 already carries its sign bit in the low byte(s)
+    if (width == 1) return ((uint32_t)v & 0xffu) | ((uint32_t)v >> 24 & 0x80u);
+    if (width == 2) return ((uint32_t)v & 0xffffu) | ((uint32_t)v >> 16 & 0x8000u);
     return (uint32_t)v;
 }
 // where byte i of the span lives in the staging buffer: linear (raw stream), or with 4 bytes of padding after every 64
@@ -629,7 +630,7 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
         const BcfSitePlan& P = T.plan[1 + j];
         long long st = (long long)(r0 - lo);
         const void* src = nullptr;
-        uint32_t info = BCF_PK_BYTES, dist = 0, fld = 0;
+        uint32_t info = BCF_PK_BYTES | 1u << 4, dist = 0, fld = 0;
         if (has) {
             const uint32_t hdr_len = 8 + P.l_shared;
             if (p == 0) {
@@ -732,16 +733,36 @@ __host__ __device__ inline uint8_t bcf_piece_byte(const BcfEnc& E, const BcfSpan
     }
 }
 
-// One aligned 4-byte word of the span taken wholly from a typed vector: byte offset `off` of the piece's data.
+// byte `off` of a plainly typed piece (INT / RAW4 / GT / BYTES), no divisions: w is 1, 2 or 4
+__host__ __device__ __forceinline__ uint32_t bcf_fast_byte(const void* src, uint32_t kind, uint32_t w, uint32_t km, unsigned long long off) {
+    if (kind == BCF_PK_BYTES) return static_cast<const uint8_t*>(src)[off];
+    if (kind == BCF_PK_GT) {
+        const int a = static_cast<const int8_t*>(src)[off];
+        return a < 0 ? 0u : (uint32_t)((bcf_popc(km & ((1u << a) - 1u)) + 1) << 1);
+    }
+    const uint32_t sh = w >> 1;  // log2(w)
+    return (bcf_conv(static_cast<const int32_t*>(src)[off >> sh], w) >> (8 * (uint32_t)(off & (w - 1)))) & 0xffu;
+}
+// One aligned 4-byte word of the span taken wholly from a plainly typed piece: byte offset `off` of the piece's data.
 __host__ __device__ __forceinline__ uint32_t bcf_piece_word(const void* src, uint32_t kind, uint32_t w, uint32_t km, unsigned long long off) {
     if (kind == BCF_PK_INT && w == 1) {
         const int32_t* v = static_cast<const int32_t*>(src) + off;
-        return bcf_conv(v[0], 1) | bcf_conv(v[1], 1) << 8 | bcf_conv(v[2], 1) << 16 | bcf_conv(v[3], 1) << 24;
+        int32_t a, b, c, d;
+#if defined(__CUDA_ARCH__)
+        if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+            const int4 q = __ldg(reinterpret_cast<const int4*>(v));
+            a = q.x, b = q.y, c = q.z, d = q.w;
+        } else
+#endif
+        {
+            a = v[0], b = v[1], c = v[2], d = v[3];
+        }
+        return bcf_conv(a, 1) | bcf_conv(b, 1) << 8 | bcf_conv(c, 1) << 16 | bcf_conv(d, 1) << 24;
     }
     if (kind == BCF_PK_INT && w == 2) {  // three values when the word starts in the middle of one
         const int32_t* v = static_cast<const int32_t*>(src) + (off >> 1);
-        unsigned long long x = (unsigned long long)(bcf_conv(v[0], 2) & 0xffffu) | (unsigned long long)(bcf_conv(v[1], 2) & 0xffffu) << 16;
-        if (off & 1) x |= (unsigned long long)(bcf_conv(v[2], 2) & 0xffffu) << 32;
+        unsigned long long x = (unsigned long long)bcf_conv(v[0], 2) | (unsigned long long)bcf_conv(v[1], 2) << 16;
+        if (off & 1) x |= (unsigned long long)bcf_conv(v[2], 2) << 32;
         return (uint32_t)(x >> (8 * (off & 1)));
     }
     if (kind == BCF_PK_INT || kind == BCF_PK_RAW4) {
@@ -781,27 +802,39 @@ __host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, const BcfSpanTab& 
     for (long long it = it0 + warp; it < it1; it += n_warps) {
         const long long a_it = (it << 10) < T.cov_lo ? T.cov_lo : (it << 10), e_it = ((it + 1) << 10) > T.cov_hi ? T.cov_hi : ((it + 1) << 10);
         for (uint32_t p = bcf_tab_find(T, a_it); p < T.n && T.start[p] < e_it; p++) {
-            const long long ps = T.start[p] < a_it ? a_it : T.start[p], pe = T.start[p + 1] > e_it ? e_it : T.start[p + 1];
-            if (pe <= ps) continue;
             const long long base = T.start[p];
+            const long long ps = base < a_it ? a_it : base, pe = T.start[p + 1] > e_it ? e_it : T.start[p + 1];
+            if (pe <= ps) continue;
             const uint32_t info = T.info[p], kind = info & 15u, w = info >> 4 & 15u, km = T.km[p];
             const void* src = T.src[p];
-            const bool fast = kind == BCF_PK_INT || kind == BCF_PK_RAW4 || kind == BCF_PK_GT || (kind == BCF_PK_BYTES && w == 1);
-            long long wa = (ps + 3) & ~3ll, we = pe & ~3ll;
-            if (!fast || wa >= we) wa = we = pe;  // everything byte by byte
-            for (long long x = ps + lane; x < (wa < pe ? wa : pe); x += n_lanes) buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(x - base));
-            if (wa < we) {
-                const long long step = 4ll * n_lanes;
-                long long x0 = wa + 4ll * lane;
-                for (; x0 + step < we; x0 += 2 * step) {
-                    const uint32_t u = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base));
-                    const uint32_t v = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 + step - base));
-                    bcf_put_word<Addr>(buf, x0, u);
-                    bcf_put_word<Addr>(buf, x0 + step, v);
-                }
-                if (x0 < we) bcf_put_word<Addr>(buf, x0, bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base)));
-                for (long long x = we + lane; x < pe; x += n_lanes) buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(x - base));
+            if (kind == BCF_PK_TRIM || kind == BCF_PK_STR) {  // rewritten vectors and strings: byte by byte
+                for (long long x = ps + lane; x < pe; x += n_lanes) buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(x - base));
+                continue;
             }
+            long long wa = (ps + 3) & ~3ll, we = pe & ~3ll;
+            if (wa > we) wa = we = pe;
+            // the up to 3 + 3 bytes around the aligned words, in one go
+            {
+                const long long nh = wa - ps, ntl = pe - we;
+                if ((long long)lane < nh + ntl) {
+                    const long long x = (long long)lane < nh ? ps + lane : we + (lane - nh);
+                    buf[Addr::phys((unsigned long long)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (unsigned long long)(x - base));
+                }
+                if (n_lanes < 6)  // the host build's single lane
+                    for (long long i = n_lanes; i < nh + ntl; i++) {
+                        const long long x = i < nh ? ps + i : we + (i - nh);
+                        if (lane == 0) buf[Addr::phys((unsigned long long)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (unsigned long long)(x - base));
+                    }
+            }
+            const long long step = 4ll * n_lanes;
+            long long x0 = wa + 4ll * lane;
+            for (; x0 + step < we; x0 += 2 * step) {
+                const uint32_t u = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base));
+                const uint32_t v = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 + step - base));
+                bcf_put_word<Addr>(buf, x0, u);
+                bcf_put_word<Addr>(buf, x0 + step, v);
+            }
+            if (x0 < we) bcf_put_word<Addr>(buf, x0, bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base)));
         }
     }
 }

@@ -52,7 +52,7 @@ struct BgzfShared {
     unsigned long long tok[GLX_BGZF_WORKERS];   // bit i: a token starts at byte i of the worker's chunk (literal = 1 byte, match = to the next start)
     unsigned long long useD[GLX_BGZF_WORKERS];  // bit i: the match starting there copies from the structural distance D, not from distance 1
     uint32_t n_in, data_bits, crc, crc_acc, stored, block_len;
-    uint32_t crc_table[256];
+    uint32_t crc_table[4][256];
 };
 
 __host__ __device__ __forceinline__ int bgzf_log2(uint32_t x) {  // floor(log2 x), x > 0
@@ -123,10 +123,14 @@ __host__ __device__ __forceinline__ void bgzf_xor(uint32_t* p, uint32_t v) {
 #endif
 }
 __host__ __device__ inline void bgzf_crc_setup(BgzfShared& sh, uint32_t tid, uint32_t nt) {
-    for (uint32_t i = tid; i < 256; i += nt) {
+    for (uint32_t i = tid; i < 256; i += nt) {  // slice-by-4 tables: crc_table[k][i] = CRC of byte i followed by k zero bytes
         uint32_t c = i;
         for (int k = 0; k < 8; k++) c = c & 1 ? (c >> 1) ^ GLX_CRC_POLY : c >> 1;
-        sh.crc_table[i] = c;
+        sh.crc_table[0][i] = c;
+        for (int t = 1; t < 4; t++) {
+            for (int k = 0; k < 8; k++) c = c & 1 ? (c >> 1) ^ GLX_CRC_POLY : c >> 1;
+            sh.crc_table[t][i] = c;
+        }
     }
     if (tid == 0) sh.crc_acc = 0;
 }
@@ -136,7 +140,14 @@ __host__ __device__ inline void bgzf_crc_parts(BgzfShared& sh, const uint32_t* _
         const uint32_t v0 = w * GLX_BGZF_CHUNK, v1 = v0 + GLX_BGZF_CHUNK;
         if (v1 <= pad) continue;
         uint32_t c = 0;
-        for (uint32_t v = v0 < pad ? pad : v0; v < v1; v++) c = sh.crc_table[(c ^ in[BcfPadded::phys(v - pad)]) & 0xff] ^ (c >> 8);
+        if ((pad & 3u) == 0 && v0 >= pad) {  // whole aligned words (every full span: pad = 256)
+            for (uint32_t v = v0; v < v1; v += 4) {
+                const uint32_t x = c ^ *reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(v - pad));
+                c = sh.crc_table[3][x & 0xff] ^ sh.crc_table[2][x >> 8 & 0xff] ^ sh.crc_table[1][x >> 16 & 0xff] ^ sh.crc_table[0][x >> 24];
+            }
+        } else {
+            for (uint32_t v = v0 < pad ? pad : v0; v < v1; v++) c = sh.crc_table[0][(c ^ in[BcfPadded::phys(v - pad)]) & 0xff] ^ (c >> 8);
+        }
         if (c) bgzf_xor(&sh.crc_acc, crc_multmodp(pw[GLX_BGZF_WORKERS - 1 - w], c));
     }
 }
