@@ -5,7 +5,7 @@ GENCODE := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 $(GENCODE) -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-sign-compare
 CSRC := glnexus_b200/csrc
-HOST_SRCS := $(CSRC)/glx_host.cc $(CSRC)/glx_host_c.cc $(CSRC)/glx_presets.cc $(CSRC)/glx_synth.cc $(CSRC)/glx_service.cc $(CSRC)/glx_bcf_host.cc $(CSRC)/glx_stream.cc
+HOST_SRCS := $(CSRC)/glx_host.cc $(CSRC)/glx_host_c.cc $(CSRC)/glx_presets.cc $(CSRC)/glx_synth.cc $(CSRC)/glx_service.cc $(CSRC)/glx_bcf_host.cc $(CSRC)/glx_stream.cc $(CSRC)/glx_wire_host.cc
 HOST_OBJS := $(HOST_SRCS:.cc=.o)
 
 all: glnexus_b200/libglx.so oracle/libglx_oracle.so

@@ -117,6 +117,14 @@ def lib():
     L.glxh_bgzf_stored.restype = C.c_int
     L.glxh_bgzf_eof.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.glxh_bgzf_eof.restype = C.c_int
+    L.glxh_batch_wire.argtypes = [vp, C.POINTER(vp)]
+    L.glxh_batch_wire.restype = C.c_int
+    L.glx_upload_wire_on.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.glx_upload_wire_on.restype = C.c_int
+    L.glx_debug_compare_records.argtypes = [vp, vp, vp, C.POINTER(C.c_uint32)]
+    L.glx_debug_compare_records.restype = C.c_int
+    L.glxh_stream_use_wire.argtypes = [vp, C.c_int]
+    L.glxh_stream_use_wire.restype = None
     L.glxh_stream_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), cp, sz]
     L.glxh_stream_open.restype = C.c_int
     L.glxh_stream_submit.argtypes = [vp, vp, cp, sz]
@@ -395,6 +403,15 @@ class Batch:
         finally:
             lib().glxh_free_text(t)
 
+    def wire(self):
+        """(pointer, bytes) of the batch's compact wire form (glx_wire), built on first use."""
+        p = C.c_void_p()
+        rc = lib().glxh_batch_wire(self.handle, C.byref(p))
+        if rc != GLX_OK:
+            raise GlxError(rc, "glxh_batch_wire")
+        n_bytes = C.c_uint64.from_address(p.value + 8).value
+        return p.value, n_bytes
+
     @property
     def bcf_meta_ptr(self):
         """glx_bcf_meta of the batch (per-site strings + header dictionary for the BCF record encoder)."""
@@ -575,6 +592,21 @@ class Context:
         self._check(lib().glx_upload(self.handle, batch.config_ptr, batch.records_ptr, batch.sites_ptr, C.byref(d)))
         return DeviceBatch(self, d)
 
+    def upload_wire(self, batch, stream=None, sync=True):
+        """Upload through the compact wire form; the device expands it into the same record store glx_upload builds."""
+        d = C.c_void_p()
+        wp, _ = batch.wire()
+        self._check(lib().glx_upload_wire_on(self.handle, batch.config_ptr, C.c_void_p(wp), batch.sites_ptr, C.c_void_p(stream or 0), 1 if sync else 0, C.byref(d)))
+        return DeviceBatch(self, d)
+
+    def compare_records(self, dev, batch):
+        """Names of the device's record-store arrays that differ from the batch's host arrays (test aid)."""
+        names = ["beg", "end", "maxend", "qual", "n_allele", "flags", "filt", "gt", "allele_off", "col_val", "col_len", "pool", "al_len", "al_flags",
+                 "al_prefix", "al_str", "al_pool"]
+        diff = C.c_uint32()
+        self._check(lib().glx_debug_compare_records(self.handle, dev.handle, batch.records_ptr, C.byref(diff)))
+        return [n for i, n in enumerate(names) if diff.value >> i & 1] + (["size"] if diff.value == 0xffffffff else [])
+
     def upload_async(self, batch, stream):
         """Enqueue the batch's H2D copies on `stream`; the batch must stay alive (and should be pinned) until synchronised."""
         d = C.c_void_p()
@@ -611,7 +643,7 @@ class RangeStream:
     mode: 'columns' | 'bcf' (uncompressed BCF2 records) | 'bgzf' (BGZF blocks)."""
     MODES = {"columns": 0, "bcf": 2, "bgzf": 3}
 
-    def __init__(self, device=0, mode="bgzf", depth=3, capture=False):
+    def __init__(self, device=0, mode="bgzf", depth=3, capture=False, wire=False):
         h = C.c_void_p()
         self._err = C.create_string_buffer(1024)
         rc = lib().glxh_stream_open(int(device), self.MODES[mode], int(depth), 1 if capture else 0, C.byref(h), self._err, len(self._err))
@@ -619,6 +651,8 @@ class RangeStream:
             raise GlxError(rc, self._err.value.decode(errors="replace"))
         self.handle = h
         self._keep = []
+        if wire:
+            lib().glxh_stream_use_wire(h, 1)
 
     def submit(self, batch):
         self._keep.append(batch)  # the batch's arrays must outlive its time in flight

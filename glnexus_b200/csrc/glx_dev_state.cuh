@@ -134,6 +134,8 @@ struct GlxBcfState {
 
 struct glx_dev_batch {
     GlxBcfState bcf;
+    void* wire_sums = nullptr;     // wire upload: block sums of the record scan / of the allele-length scan (inside the input arena)
+    void* wire_al_sums = nullptr;
     DCfg cfg;
     DRecs R;
     DSites S;

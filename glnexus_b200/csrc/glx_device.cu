@@ -21,6 +21,7 @@
 #include "glx_cell_variant.cuh"
 #include "glx_dev_types.cuh"
 #include "glx_tiled_sig.cuh"
+#include "glx_wire.cuh"
 
 using namespace glxd;
 
@@ -567,11 +568,32 @@ int glx_upload(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, con
     return glx_upload_on(ctx, cfg, recs, sites, nullptr, 1, out);
 }
 
-int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, void* stream_, int sync, glx_dev_batch** out) {
+}  // extern "C"
+
+static inline int32_t* WO_pool_ptr(const DRecs& R) { return const_cast<int32_t*>(R.pool); }
+
+// recs: the kernel-facing record store on the host (classic upload), or wire: its compact wire form (expanded on the device)
+static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_wire* wire, const glx_sites* sites, void* stream_, int sync,
+                       glx_dev_batch** out) {
     if (!ctx) return GLX_E_INVALID;
-    if (!cfg || !recs || !sites || !out) {
+    if (!cfg || (!recs && !wire) || !sites || !out) {
         ctx->err = "glx_upload: null argument";
         return GLX_E_INVALID;
+    }
+    glx_records wrec;  // the counts of a wire batch, in the shape the code below reads
+    if (wire) {
+        if (wire->magic != GLX_WIRE_MAGIC || wire->n_cols != cfg->n_cols) {
+            ctx->err = "glx_upload_wire: not a wire buffer of this config";
+            return GLX_E_INVALID;
+        }
+        memset(&wrec, 0, sizeof wrec);
+        wrec.n_datasets = wrec.n_samples_out = wire->n_datasets;
+        wrec.n_cols = wire->n_cols;
+        wrec.n_records = wire->n_records;
+        wrec.n_pool = wire->n_pool;
+        wrec.n_al = wire->n_al;
+        wrec.n_al_pool = wire->n_al_pool;
+        recs = &wrec;
     }
     *out = nullptr;
     if (cfg->abi_version != GLX_ABI_VERSION) {
@@ -583,7 +605,7 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         ctx->err = "glx_upload: device path needs one single-sample dataset per output sample";
         return GLX_E_UNSUPPORTED;
     }
-    for (uint32_t d = 0; d < recs->n_datasets; d++) {
+    for (uint32_t d = 0; !wire && d < recs->n_datasets; d++) {  // (the wire builder has checked this)
         if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) {
             ctx->err = "glx_upload: multi-sample or out-of-order dataset is outside the device path";
             return GLX_E_UNSUPPORTED;
@@ -638,8 +660,8 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     add(recs->maxend, Rn * 4, &R.maxend);
     add(recs->qual, Rn * 4, &R.qual);
     add(recs->n_allele, Rn, &R.n_allele);
-    uint64_t n_variant_records = 0;
-    for (uint64_t rr = 0; rr < Rn; rr++) n_variant_records += !(recs->flags[rr] & GLX_RF_IS_REF);
+    uint64_t n_variant_records = wire ? wire->n_variant : 0;
+    for (uint64_t rr = 0; !wire && rr < Rn; rr++) n_variant_records += !(recs->flags[rr] & GLX_RF_IS_REF);
     add(recs->flags, Rn, &R.flags);  // glx_prepare_inputs_kernel adds the device-private "last record of its dataset" bit
     add(recs->filt, Rn * 4, &R.filt);
     add(recs->gt, Rn * 4, &R.gt);
@@ -681,6 +703,14 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
         add(sites->fld_off[k], (S + 1) * 8, &Sx.fld_off[k]);
         d->fld_total[k] = S ? sites->fld_off[k][S] : 0;
     }
+    char* wire_dev = nullptr;
+    if (wire) {  // the wire buffer rides in the same arena; the record-store arrays above have no host source and are expanded from it
+        add((const void*)wire, (size_t)wire->n_bytes, &wire_dev);
+        const size_t nb = (Rn + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS) + 1;
+        const size_t nab = (recs->n_al + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS) + 1;
+        add((const void*)nullptr, nb * sizeof(uint3x), &d->wire_sums);
+        add((const void*)nullptr, nab * sizeof(uint3x), &d->wire_al_sums);
+    }
     size_t total = 0;
     size_t copied = 0;
     for (auto& it : items) {
@@ -699,6 +729,64 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
             e = cudaMemcpyAsync(p, it.src, it.bytes, cudaMemcpyHostToDevice, up);
             if (e != cudaSuccess) return bail(e, "cudaMemcpyAsync(H2D)");
         }
+    }
+    if (wire) {  // expand the wire form into the arrays the kernels read
+        DWire W;
+        memset(&W, 0, sizeof W);
+        W.n_records = Rn;
+        W.n_variant = wire->n_variant;
+        W.n_al = wire->n_al;
+        W.n_al_pool = wire->n_al_pool;
+        W.n_pool = wire->n_pool;
+        W.n_exc = wire->n_maxend_exc;
+        W.n_cols = wire->n_cols;
+        W.flags = wire->flags;
+        W.base = reinterpret_cast<const uint8_t*>(wire_dev);
+        uint64_t co = wire->off[GLX_WS_COL_VAL];
+        for (uint32_t c = 0; c < wire->n_cols; c++) {
+            W.col_w[c] = wire->col_w[c];
+            W.col_val_off[c] = co;
+            co += ((Rn * wire->col_w[c]) + 15) & ~(uint64_t)15;
+        }
+        for (int i = 0; i < GLX_WS_COUNT; i++) W.off[i] = wire->off[i];
+        // columns that travel as they are
+        R.ds_rec_off = reinterpret_cast<const uint64_t*>(wire_dev + wire->off[GLX_WS_DS_REC_OFF]);
+        R.beg = reinterpret_cast<const int32_t*>(wire_dev + wire->off[GLX_WS_BEG]);
+        R.flags = reinterpret_cast<const uint8_t*>(wire_dev + wire->off[GLX_WS_FLAGS]);
+        R.n_allele = reinterpret_cast<const uint8_t*>(wire_dev + wire->off[GLX_WS_NALLELE]);
+        R.al_pool = wire_dev + wire->off[GLX_WS_AL_POOL];
+        const unsigned nb = (unsigned)((Rn + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS));
+        const unsigned nab = (unsigned)((recs->n_al + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS));
+        uint3x* sums = reinterpret_cast<uint3x*>(d->wire_sums);
+        uint3x* al_sums = reinterpret_cast<uint3x*>(d->wire_al_sums);
+        if (nab) {
+            glx_wire_al_sums_kernel<<<nab, GLX_WIRE_BLOCK, 0, up>>>(W, al_sums);
+            glx_wire_scan_sums_kernel<<<1, GLX_WIRE_BLOCK, 0, up>>>(al_sums, nab);
+            glx_wire_alleles_kernel<<<nab, GLX_WIRE_BLOCK, 0, up>>>(W, al_sums, const_cast<uint32_t*>(R.al_len), const_cast<uint32_t*>(R.al_str),
+                                                                      const_cast<uint64_t*>(R.al_prefix));
+        }
+        if (nb) {
+            glx_wire_sums_kernel<<<nb, GLX_WIRE_BLOCK, 0, up>>>(W, sums);
+            glx_wire_scan_sums_kernel<<<1, GLX_WIRE_BLOCK, 0, up>>>(sums, nb);
+            WireOut WO;
+            WO.end = const_cast<int32_t*>(R.end);
+            WO.maxend = const_cast<int32_t*>(R.maxend);
+            WO.col_val = const_cast<int32_t*>(R.col_val);
+            WO.pool = const_cast<int32_t*>(R.pool);
+            WO.qual = const_cast<float*>(R.qual);
+            WO.filt = const_cast<uint32_t*>(R.filt);
+            WO.gt = const_cast<uint32_t*>(R.gt);
+            WO.allele_off = const_cast<uint32_t*>(R.allele_off);
+            WO.col_len = const_cast<uint16_t*>(R.col_len);
+            WO.al_flags = const_cast<uint8_t*>(R.al_flags);
+            WO.al_len = R.al_len;
+            WO.al_str = R.al_str;
+            glx_wire_records_kernel<<<nb, GLX_WIRE_BLOCK, 0, up>>>(W, sums, WO);
+            if (W.n_exc) glx_wire_maxend_kernel<<<(unsigned)((W.n_exc + 255) / 256), 256, 0, up>>>(W, WO.maxend);
+        }
+        if (W.n_pool) glx_wire_pool_kernel<<<(unsigned)std::min<uint64_t>((W.n_pool + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, up>>>(W, WO_pool_ptr(R));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return bail(e, "wire expansion kernels");
     }
     {
         const uint64_t n = std::max<uint64_t>(std::max<uint64_t>(S + 1, nU + 1), D);
@@ -834,6 +922,83 @@ int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, 
     e = sync ? cudaStreamSynchronize(up) : cudaSuccess;  // after a synchronous upload the caller's host arrays may be released
     if (e != cudaSuccess) return bail(e, "cudaStreamSynchronize(upload)");
     *out = d;
+    return GLX_OK;
+}
+
+extern "C" {
+
+int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, void* stream, int sync, glx_dev_batch** dev) {
+    if (!recs) {
+        if (ctx) ctx->err = "glx_upload: null argument";
+        return GLX_E_INVALID;
+    }
+    return upload_impl(ctx, cfg, recs, nullptr, sites, stream, sync, dev);
+}
+
+int glx_upload_wire_on(glx_ctx* ctx, const glx_config* cfg, const glx_wire* wire, const glx_sites* sites, void* stream, int sync, glx_dev_batch** dev) {
+    if (!wire) {
+        if (ctx) ctx->err = "glx_upload_wire: null argument";
+        return GLX_E_INVALID;
+    }
+    return upload_impl(ctx, cfg, nullptr, wire, sites, stream, sync, dev);
+}
+
+// test aid: which record-store arrays on the device differ from the host's
+int glx_debug_compare_records(glx_ctx* ctx, glx_dev_batch* d, const glx_records* recs, uint32_t* diff) {
+    if (!ctx || !d || !recs || !diff) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    *diff = 0;
+    const uint64_t Rn = recs->n_records, C = d->n_cols;
+    if (Rn != d->R.n_records) {
+        *diff = ~0u;
+        return GLX_OK;
+    }
+    std::vector<char> tmp;
+    auto fetch = [&](const void* dev, size_t bytes) -> const char* {
+        tmp.assign(bytes + 8, 0);
+        if (bytes && cudaMemcpy(tmp.data(), dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
+        return tmp.data();
+    };
+    auto whole = [&](int bit, const void* dev, const void* host, size_t bytes) {
+        const char* g = fetch(dev, bytes);
+        if (!g || (bytes && memcmp(g, host, bytes) != 0)) *diff |= 1u << bit;
+    };
+    const bool var_only = true;
+    whole(0, d->R.beg, recs->beg, Rn * 4);
+    whole(1, d->R.end, recs->end, Rn * 4);
+    whole(2, d->R.maxend, recs->maxend, Rn * 4);
+    whole(4, d->R.n_allele, recs->n_allele, Rn);
+    whole(7, d->R.gt, recs->gt, Rn * 4);
+    whole(10, d->R.col_len, recs->col_len, C * Rn * 2);
+    whole(11, d->R.pool, recs->pool, recs->n_pool * 4);
+    whole(12, d->R.al_len, recs->al_len, recs->n_al * 4);
+    whole(13, d->R.al_flags, recs->al_flags, recs->n_al);
+    whole(14, d->R.al_prefix, recs->al_prefix, recs->n_al * 8);
+    whole(15, d->R.al_str, recs->al_str, recs->n_al * 4);
+    whole(16, d->R.al_pool, recs->al_pool, recs->n_al_pool);
+    {  // qual (3), filt (6), allele_off (8): compared on non-reference records; flags (5) without the device-private bit
+        const char* g = fetch(d->R.qual, Rn * 4);
+        for (uint64_t r = 0; g && r < Rn; r++)
+            if (!(recs->flags[r] & GLX_RF_IS_REF) && memcmp(g + 4 * r, &recs->qual[r], 4) != 0) *diff |= 1u << 3;
+        if (!g) *diff |= 1u << 3;
+        g = fetch(d->R.filt, Rn * 4);
+        for (uint64_t r = 0; g && r < Rn; r++)
+            if ((!(recs->flags[r] & GLX_RF_IS_REF) || !var_only) && memcmp(g + 4 * r, &recs->filt[r], 4) != 0) *diff |= 1u << 6;
+        if (!g) *diff |= 1u << 6;
+        g = fetch(d->R.allele_off, Rn * 4);
+        for (uint64_t r = 0; g && r < Rn; r++)
+            if (!(recs->flags[r] & GLX_RF_IS_REF) && memcmp(g + 4 * r, &recs->allele_off[r], 4) != 0) *diff |= 1u << 8;
+        if (!g) *diff |= 1u << 8;
+        g = fetch(d->R.flags, Rn);
+        for (uint64_t r = 0; g && r < Rn; r++)
+            if (((uint8_t)g[r] & 0x7f) != (recs->flags[r] & 0x7f)) *diff |= 1u << 5;
+        if (!g) *diff |= 1u << 5;
+        g = fetch(d->R.col_val, C * Rn * 4);
+        for (uint64_t i = 0; g && i < C * Rn; i++)
+            if (recs->col_len[i] < 0xFFF0 && memcmp(g + 4 * i, &recs->col_val[i], 4) != 0) *diff |= 1u << 9;
+        if (!g) *diff |= 1u << 9;
+    }
     return GLX_OK;
 }
 

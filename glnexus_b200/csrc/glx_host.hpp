@@ -287,6 +287,9 @@ uint32_t crc32_ieee(const uint8_t* p, size_t n, uint32_t crc = 0);
 std::string bgzf_block_stored(const uint8_t* p, size_t n);
 std::string bgzf_eof_block();
 
+// N2 (start): the compact wire form of the batch's record store (glx_wire, include/glx.h) — glx_wire_host.cc
+Status build_wire(const PackedBatch& b, std::vector<uint8_t>& wire);
+
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
 // [site_lo, site_hi) with every record its sites can touch.
 void partition_sites(const PackedBatch& b, int n_parts, std::vector<uint32_t>& bounds);
@@ -331,7 +334,8 @@ public:
     ~RangeStream();
     Status open(int device, Mode mode, int depth, Sink sink);
     // Queue one batch (upload, kernels, encoder). `b` must stay valid until it has been retired; pass `owned` to hand it over.
-    Status submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned = nullptr);
+    // `wire`: the batch's compact wire form (build_wire) to upload instead of its full-width record store
+    Status submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned = nullptr, const glx_wire* wire = nullptr);
     Status drain();  // retire everything in flight, in order; the first error wins and later batches produce no output
     void close();
     const StreamStats& stats() const { return stats_; }
@@ -365,4 +369,6 @@ struct glxh_batch {
     glx::PackedBatch b;
     bool pinned = false;
     std::vector<void*> pinned_ptrs;
+    std::vector<uint8_t> wire;  // built on demand (glxh_batch_wire)
+    bool wire_pinned = false;
 };

@@ -175,6 +175,23 @@ int glxh_batch_pin(glxh_batch* hb) {
     return rc;
 }
 
+int glxh_batch_wire(glxh_batch* hb, const glx_wire** wire) {
+    if (!hb || !wire) return GLX_E_INVALID;
+    if (hb->wire.empty()) {
+        glx::Status s = glx::build_wire(hb->b, hb->wire);
+        if (s.bad()) {
+            hb->wire.clear();
+            return s.c_code();
+        }
+    }
+    if (hb->pinned && !hb->wire_pinned && glx_host_register(hb->wire.data(), hb->wire.size()) == GLX_OK) {
+        hb->wire_pinned = true;
+        hb->pinned_ptrs.push_back(hb->wire.data());
+    }
+    *wire = reinterpret_cast<const glx_wire*>(hb->wire.data());
+    return GLX_OK;
+}
+
 // Service::genotype_sites on the device path, text in / pVCF file out (glx::genotype_sites)
 int glxh_genotype_sites(const char* preset, const char* config_text, const char* sites_text, int n_datasets, const char* const* dataset_names,
                         const char* const* vcf_texts, const char* filename, int device, uint32_t batch_sites, int test_ingest_rules,
@@ -472,7 +489,7 @@ int glxh_load_config(const char* name, const char* config_text, int more_PL, int
 
 struct glxh_stream {
     glx::RangeStream rs;
-    bool capture = false;
+    bool capture = false, use_wire = false;
     std::string captured;
 };
 
@@ -493,9 +510,18 @@ int glxh_stream_open(int device, int mode, int depth, int capture, glxh_stream**
     return GLX_OK;
 }
 
+void glxh_stream_use_wire(glxh_stream* h, int on) {
+    if (h) h->use_wire = on != 0;
+}
+
 int glxh_stream_submit(glxh_stream* h, glxh_batch* b, char* err, size_t errlen) {
     if (!h || !b) return GLX_E_INVALID;
-    glx::Status s = h->rs.submit(&b->b);
+    const glx_wire* wire = nullptr;
+    if (h->use_wire) {
+        int rc = glxh_batch_wire(b, &wire);
+        if (rc != GLX_OK) return fail(glx::Status::NotImplemented("glxh_stream_submit: the batch has no wire form"), err, errlen);
+    }
+    glx::Status s = h->rs.submit(&b->b, nullptr, wire);
     return s.ok() ? GLX_OK : fail(s, err, errlen);
 }
 

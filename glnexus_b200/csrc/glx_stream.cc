@@ -167,7 +167,7 @@ Status RangeStream::retire(Slot& sl) {
     return s;
 }
 
-Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned) {
+Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, const glx_wire* wire) {
     if (!ctx_) return Status::Invalid("RangeStream: not open");
     if (failed_.bad()) return failed_;
     const size_t depth = slots_.size();
@@ -176,7 +176,9 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned) {
     if (s.bad()) return s;
     sl.batch = b;
     sl.owned = std::move(owned);
-    s = status_of_rc(glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev), ctx_);
+    s = status_of_rc(wire ? glx_upload_wire_on(ctx_, &b->cfg, wire, &b->sites, sl.stream, 0, &sl.dev)
+                          : glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev),
+                     ctx_);
     if (s.ok()) s = status_of_rc(glx_launch(ctx_, sl.dev, sl.stream), ctx_);
     if (s.ok()) {
         if (mode_ == Mode::COLUMNS) {

@@ -1,0 +1,188 @@
+// glx_wire_host.cc — builds the compact wire form of a packed batch's record store (glx_wire, include/glx.h): what crosses
+// PCIe instead of the kernel-facing columns. SURVEY.md §8f N2 (start): the packer's output at the width the data needs.
+#include <cstring>
+
+#include "glx_host.hpp"
+
+namespace glx {
+
+namespace {
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+bool fits16(int32_t v) { return v == GLX_INT_MISSING || v == GLX_INT_VECTOR_END || (v >= -32760 && v <= 32767); }
+int16_t to16(int32_t v) { return v == GLX_INT_MISSING ? (int16_t)0x8000 : (v == GLX_INT_VECTOR_END ? (int16_t)0x8001 : (int16_t)v); }
+}  // namespace
+
+Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
+    const glx_records& r = b.recs;
+    const uint64_t R = r.n_records, D = r.n_datasets, C = r.n_cols;
+    if (r.n_datasets != r.n_samples_out) return Status::NotImplemented("build_wire: multi-sample datasets have no wire form");
+    for (uint32_t d = 0; d < D; d++)
+        if (r.ds_n_sample[d] != 1 || r.sample_out[r.ds_sample_off[d]] != (int32_t)d) return Status::NotImplemented("build_wire: multi-sample datasets have no wire form");
+    if (R >= (1ull << 32)) return Status::NotImplemented("build_wire: more than 2^32 records");
+    glx_wire h;
+    memset(&h, 0, sizeof h);
+    h.magic = GLX_WIRE_MAGIC;
+    h.n_records = R;
+    h.n_datasets = (uint32_t)D;
+    h.n_cols = (uint32_t)C;
+    h.n_al = r.n_al;
+    h.n_al_pool = r.n_al_pool;
+    h.n_pool = r.n_pool;
+    // ---- what fits ----
+    bool len16 = true, gt8 = true, collen8 = true, pool16 = true, allen16 = true;
+    uint64_t n_variant = 0;
+    std::vector<uint32_t> exc;  // (record, maxend) pairs where maxend != end
+    for (uint64_t i = 0; i < R; i++) {
+        const int64_t len = (int64_t)r.end[i] - r.beg[i];
+        if (len < 0 || len > 65535) len16 = false;
+        if (!(r.flags[i] & GLX_RF_IS_REF)) n_variant++;
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
+            if (!(g == GLX_GT16_VECTOR_END || (g >= 0 && g <= 508 && !(g & 1)))) gt8 = false;
+        }
+        if (r.maxend[i] != r.end[i]) {
+            exc.push_back((uint32_t)i);
+            exc.push_back((uint32_t)r.maxend[i]);
+        }
+    }
+    // the pool must be laid out record-major, column-minor (what pack_records / slice_batch / the generator write): offsets are then prefix sums
+    {
+        uint64_t run = 0;
+        for (uint64_t i = 0; i < R; i++)
+            for (uint64_t c = 0; c < C; c++) {
+                const uint16_t len = r.col_len[c * R + i];
+                if (len >= 0xFD && len < 0xFFF0) collen8 = false;
+                if (len >= 0xFFF0 || len == 1) continue;
+                if ((uint64_t)(uint32_t)r.col_val[c * R + i] != run) return Status::NotImplemented("build_wire: value pool is not in record order");
+                run += len;
+            }
+        if (run != r.n_pool) return Status::NotImplemented("build_wire: value pool has entries no record refers to");
+    }
+    for (uint64_t i = 0; i < r.n_pool && pool16; i++) pool16 = fits16(r.pool[i]);
+    for (uint64_t c = 0; c < C; c++) {
+        bool any = false, f16 = true;
+        for (uint64_t i = 0; i < R; i++)
+            if (r.col_len[c * R + i] == 1) {
+                any = true;
+                if (!fits16(r.col_val[c * R + i])) f16 = false;
+            }
+        h.col_w[c] = !any ? 0 : (f16 ? 2 : 4);
+    }
+    for (uint64_t a = 0; a < r.n_al && allen16; a++) allen16 = r.al_len[a] <= 65535;
+    bool filt_variant = true;
+    for (uint32_t k = 0; k < b.cfg.n_fields; k++)
+        if (b.cfg.fields[k].kind == GLX_FK_FT || b.cfg.fields[k].kind == GLX_FK_STRING) filt_variant = false;
+    h.n_variant = n_variant;
+    h.n_maxend_exc = exc.size() / 2;
+    h.flags = (len16 ? GLX_WF_LEN16 : 0) | (gt8 ? GLX_WF_GT8 : 0) | (collen8 ? GLX_WF_COLLEN8 : 0) | (pool16 ? GLX_WF_POOL16 : 0) |
+              (filt_variant ? GLX_WF_FILT_VARIANT : 0) | (allen16 ? GLX_WF_ALLEN16 : 0);
+    // ---- layout ----
+    size_t off = align16(sizeof(glx_wire));
+    auto place = [&](int sec, size_t bytes) {
+        h.off[sec] = off;
+        off = align16(off + bytes);
+    };
+    size_t colval_bytes = 0;
+    for (uint64_t c = 0; c < C; c++) colval_bytes += align16(R * h.col_w[c]);
+    place(GLX_WS_DS_REC_OFF, (D + 1) * 8);
+    place(GLX_WS_BEG, R * 4);
+    place(GLX_WS_LEN, R * (len16 ? 2 : 4));
+    place(GLX_WS_FLAGS, R);
+    place(GLX_WS_NALLELE, R);
+    place(GLX_WS_GT, R * (gt8 ? 2 : 4));
+    place(GLX_WS_QUAL, n_variant * 4);
+    place(GLX_WS_FILT, (filt_variant ? n_variant : R) * 4);
+    place(GLX_WS_COL_LEN, C * R * (collen8 ? 1 : 2));
+    place(GLX_WS_COL_VAL, colval_bytes);
+    place(GLX_WS_POOL, r.n_pool * (pool16 ? 2 : 4));
+    place(GLX_WS_AL_LEN, r.n_al * (allen16 ? 2 : 4));
+    place(GLX_WS_AL_POOL, r.n_al_pool);
+    place(GLX_WS_MAXEND_EXC, exc.size() * 4);
+    h.n_bytes = off;
+    w.assign(off, 0);
+    memcpy(w.data(), &h, sizeof h);
+    uint8_t* p = w.data();
+    memcpy(p + h.off[GLX_WS_DS_REC_OFF], r.ds_rec_off, (D + 1) * 8);
+    memcpy(p + h.off[GLX_WS_BEG], r.beg, R * 4);
+    memcpy(p + h.off[GLX_WS_FLAGS], r.flags, R);
+    memcpy(p + h.off[GLX_WS_NALLELE], r.n_allele, R);
+    {
+        uint16_t* l16 = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_LEN]);
+        uint32_t* l32 = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_LEN]);
+        uint8_t* g8 = p + h.off[GLX_WS_GT];
+        uint32_t* g32 = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_GT]);
+        float* q = reinterpret_cast<float*>(p + h.off[GLX_WS_QUAL]);
+        uint32_t* f = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_FILT]);
+        uint64_t v = 0;
+        for (uint64_t i = 0; i < R; i++) {
+            const uint32_t len = (uint32_t)(r.end[i] - r.beg[i]);
+            if (len16) l16[i] = (uint16_t)len;
+            else l32[i] = len;
+            if (gt8) {
+                for (int hlf = 0; hlf < 2; hlf++) {
+                    const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
+                    g8[2 * i + hlf] = g == GLX_GT16_VECTOR_END ? (uint8_t)0xFF : (uint8_t)(g >> 1);
+                }
+            } else
+                g32[i] = r.gt[i];
+            if (!(r.flags[i] & GLX_RF_IS_REF)) {
+                q[v] = r.qual[i];
+                if (filt_variant) f[v] = r.filt[i];
+                v++;
+            }
+            if (!filt_variant) f[i] = r.filt[i];
+        }
+    }
+    {
+        uint8_t* c8 = p + h.off[GLX_WS_COL_LEN];
+        uint16_t* c16 = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_COL_LEN]);
+        for (uint64_t i = 0; i < C * R; i++) {
+            const uint16_t len = r.col_len[i];
+            if (collen8) c8[i] = len >= 0xFFF0 ? (uint8_t)(len & 0xFF) : (uint8_t)len;  // 0xFFFF -> 0xFF, 0xFFFE -> 0xFE, 0xFFFD -> 0xFD
+            else c16[i] = len;
+        }
+        size_t co = h.off[GLX_WS_COL_VAL];
+        for (uint64_t c = 0; c < C; c++) {
+            if (h.col_w[c] == 2) {
+                int16_t* d = reinterpret_cast<int16_t*>(p + co);
+                for (uint64_t i = 0; i < R; i++) d[i] = r.col_len[c * R + i] == 1 ? to16(r.col_val[c * R + i]) : (int16_t)0;
+            } else if (h.col_w[c] == 4) {
+                int32_t* d = reinterpret_cast<int32_t*>(p + co);
+                for (uint64_t i = 0; i < R; i++) d[i] = r.col_len[c * R + i] == 1 ? r.col_val[c * R + i] : 0;
+            }
+            co += align16(R * h.col_w[c]);
+        }
+    }
+    if (pool16) {
+        int16_t* d = reinterpret_cast<int16_t*>(p + h.off[GLX_WS_POOL]);
+        for (uint64_t i = 0; i < r.n_pool; i++) d[i] = to16(r.pool[i]);
+    } else
+        memcpy(p + h.off[GLX_WS_POOL], r.pool, r.n_pool * 4);
+    if (allen16) {
+        uint16_t* d = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_AL_LEN]);
+        for (uint64_t a = 0; a < r.n_al; a++) d[a] = (uint16_t)r.al_len[a];
+    } else
+        memcpy(p + h.off[GLX_WS_AL_LEN], r.al_len, r.n_al * 4);
+    // allele strings must be laid out in allele order for their offsets to be prefix sums
+    {
+        uint64_t run = 0;
+        for (uint64_t a = 0; a < r.n_al; a++) {
+            if (r.al_str[a] != run) return Status::NotImplemented("build_wire: allele strings are not in allele order");
+            run += r.al_len[a];
+        }
+        if (run != r.n_al_pool) return Status::NotImplemented("build_wire: allele string pool has bytes no allele refers to");
+        // allele descriptors must follow the non-reference records in order
+        uint64_t ao = 0;
+        for (uint64_t i = 0; i < R; i++)
+            if (!(r.flags[i] & GLX_RF_IS_REF)) {
+                if (r.allele_off[i] != ao) return Status::NotImplemented("build_wire: allele descriptors are not in record order");
+                ao += r.n_allele[i];
+            }
+        if (ao != r.n_al) return Status::NotImplemented("build_wire: allele descriptors no record refers to");
+    }
+    memcpy(p + h.off[GLX_WS_AL_POOL], r.al_pool, r.n_al_pool);
+    if (!exc.empty()) memcpy(p + h.off[GLX_WS_MAXEND_EXC], exc.data(), exc.size() * 4);
+    return Status::OK();
+}
+
+}  // namespace glx

@@ -144,6 +144,33 @@ typedef struct glx_records {
     const char* const* filter_names; /* sorted; host-side only */
 } glx_records;
 
+/* ---- N2 (start): compact wire form of glx_records for the host->device leg. The record store above is laid out for the
+ * kernels (int32 columns, absolute offsets, running maxima); on the wire every column goes in the narrowest type the batch's
+ * values fit, and everything the device can derive is left out: end = beg + len; maxend = end except for the listed
+ * records; allele descriptor offsets, value-pool offsets and string offsets are prefix sums; allele flags / prefixes come from
+ * the allele strings; QUAL (and FILTER, unless a lifted field reads it) only exist for non-reference records. glxh_batch_wire
+ * builds it from a packed batch; glx_upload_wire_on expands it on the device into exactly the arrays glx_upload_on would copy.
+ * One contiguous buffer: this header, then the sections at off[GLX_WS_*] (each 16-byte aligned). */
+enum { GLX_WS_DS_REC_OFF = 0, GLX_WS_BEG, GLX_WS_LEN, GLX_WS_FLAGS, GLX_WS_NALLELE, GLX_WS_GT, GLX_WS_QUAL, GLX_WS_FILT, GLX_WS_COL_LEN, GLX_WS_COL_VAL,
+       GLX_WS_POOL, GLX_WS_AL_LEN, GLX_WS_AL_POOL, GLX_WS_MAXEND_EXC, GLX_WS_COUNT };
+enum {
+    GLX_WF_LEN16 = 1,          /* end - beg as uint16 (else uint32) */
+    GLX_WF_GT8 = 2,            /* GT pair as two uint8: htslib GT int / 2, 0xFF = vector end (else the uint32 of glx_records.gt) */
+    GLX_WF_COLLEN8 = 4,        /* col_len as uint8: 0xFF absent, 0xFE type clash, 0xFD length error (else uint16) */
+    GLX_WF_POOL16 = 8,         /* value pool as int16 with BCF's 16-bit sentinels (else int32) */
+    GLX_WF_FILT_VARIANT = 16,  /* FILTER masks only for non-reference records (no lifted field reads FILTER) */
+    GLX_WF_ALLEN16 = 32        /* allele lengths as uint16 (else uint32) */
+};
+#define GLX_WIRE_MAGIC 0x57584c47u /* "GLXW" */
+typedef struct glx_wire {
+    uint32_t magic, flags;
+    uint64_t n_bytes; /* the whole buffer, header included */
+    uint64_t n_records, n_variant, n_al, n_al_pool, n_pool, n_maxend_exc;
+    uint32_t n_datasets, n_cols;
+    uint8_t col_w[GLX_MAX_COLS]; /* bytes per scalar value of column c on the wire: 0 (the column has no scalar entry), 2 or 4 */
+    uint64_t off[GLX_WS_COUNT];
+} glx_wire;
+
 enum { GLX_RF_IS_REF = 1, GLX_RF_HAPLOID = 2, GLX_RF_SYMBOLIC_LAST = 4, GLX_RF_NO_GT = 8 };
 enum { GLX_AF_IS_DNA = 1, GLX_AF_DELETION = 2, GLX_AF_SYMBOLIC = 4 };
 
@@ -265,6 +292,13 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* dev);
  * Host arrays should be page-locked (glx_pinned_alloc / glx_host_register) for the copies to overlap. */
 int glx_upload_on(glx_ctx* ctx, const glx_config* cfg, const glx_records* recs, const glx_sites* sites, void* stream, int sync,
                   glx_dev_batch** dev);
+/* The same from the wire form (glx_wire header + sections in one buffer, page-locked for the copy to overlap): one H2D copy of
+ * wire->n_bytes, then expansion kernels. The batch is indistinguishable from one uploaded with glx_upload_on. */
+int glx_upload_wire_on(glx_ctx* ctx, const glx_config* cfg, const glx_wire* wire, const glx_sites* sites, void* stream, int sync, glx_dev_batch** dev);
+/* Test aid: compare the device's record-store arrays with a host glx_records; bit i of *diff = array i differs (order of the
+ * per-record arrays in glx_records: beg, end, maxend, qual, n_allele, flags, filt, gt, allele_off, col_val, col_len, pool,
+ * al_len, al_flags, al_prefix, al_str, al_pool). qual / filt of reference records and col_val of absent entries are skipped. */
+int glx_debug_compare_records(glx_ctx* ctx, glx_dev_batch* dev, const glx_records* recs, uint32_t* diff);
 int glx_download_on(glx_ctx* ctx, glx_dev_batch* dev, glx_out* out, void* stream, int sync);
 int glx_status(glx_ctx* ctx, glx_dev_batch* dev);
 /* Narrow download: one extra pass packs each integer field to int16 — or to int8 when every value of that field in the

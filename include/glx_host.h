@@ -38,6 +38,10 @@ int glxh_partition_cohort(const glxh_batch* const* segments, uint32_t n_segments
 int glxh_batch_slice(const glxh_batch* b, uint32_t site_lo, uint32_t site_hi, glxh_batch** ans, char* err, size_t errlen);
 /* page-lock the batch's arrays (cudaHostRegister) so uploads run at PCIe rate and can overlap other batches */
 int glxh_batch_pin(glxh_batch* b);
+/* The compact wire form of the batch's record store (glx_wire, include/glx.h), built on first use and page-locked when the
+ * batch is pinned; owned by the batch. Pass it to glx_upload_wire_on. GLX_E_NOT_IMPLEMENTED when the batch has no wire form
+ * (multi-sample datasets). */
+int glxh_batch_wire(glxh_batch* b, const glx_wire** wire);
 void glxh_batch_free(glxh_batch* b);
 const glx_config* glxh_config(const glxh_batch* b);
 const glx_records* glxh_records(const glxh_batch* b);
@@ -106,6 +110,8 @@ int glxh_genotype_sites(const char* preset, const char* config_text, const char*
 typedef struct glxh_stream glxh_stream;
 int glxh_stream_open(int device, int mode, int depth, int capture, glxh_stream** s, char* err, size_t errlen);
 int glxh_stream_submit(glxh_stream* s, glxh_batch* b, char* err, size_t errlen);
+/* upload through the wire form (glxh_batch_wire + glx_upload_wire_on) instead of the full-width columns */
+void glxh_stream_use_wire(glxh_stream* s, int on);
 int glxh_stream_drain(glxh_stream* s, char* err, size_t errlen);
 void glxh_stream_stats(const glxh_stream* s, uint64_t stats[8]);
 int glxh_stream_output(const glxh_stream* s, const char** bytes, uint64_t* n_bytes);
