@@ -236,10 +236,10 @@ def build_rank_batches(shape, n_samples, n_sites, region_len, n_segments, world,
     return batches, cuts
 
 
-def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3):
+def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3, wire=False):
     """Wall seconds to stream `batches` x `passes` through the C++ range-batch driver (glxh_stream_*): per batch the H2D of the
     record store + sites, all kernels, the on-device encoder and the D2H of its output. Returns (seconds, stats)."""
-    rs = glnexus_b200.RangeStream(device, mode, depth)
+    rs = glnexus_b200.RangeStream(device, mode, depth, wire=wire)
     for b in batches[:min(len(batches), depth)]:  # warm the arena cache and the pinned result buffers of every slot
         rs.submit(b)
     rs.drain()
@@ -267,7 +267,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--segments", type=int, default=0, help="segments (range batches) of the streamed cohort; default 6 per GPU (weak scaling)")
     ap.add_argument("--passes", type=int, default=1, help="times the rank's batches are streamed in the timed end-to-end region")
-    ap.add_argument("--e2e-modes", default="bgzf,bcf,columns")
+    ap.add_argument("--e2e-modes", default="bgzf+wire,bgzf,bcf,columns")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -375,15 +375,25 @@ def main():
 
     # ---- end to end through the C ABI with host buffers: the streamed range-batch driver over the rank's share of the cohort ----
     modes = [m for m in args.e2e_modes.split(",") if m]
+    if world > 1:
+        modes = modes[:1]
+    t_wire = time.time()
+    wire_bytes = sum(b.wire()[1] for b in batches)  # built (and page-locked) once per batch, outside the timed region, like the packing itself
+    wire_s = time.time() - t_wire
+
+    def run_mode(m):
+        base, _, opt = m.partition("+")
+        return stream_pass(glnexus_b200, local_rank, base, batches, args.passes, wire=opt == "wire")
+
     e2e = {}
     solo = None
     if world > 1:  # rank 0 alone first: the one-GPU rate of the same code on the same box, for the scaling efficiency
         if rank == 0:
-            solo = stream_pass(glnexus_b200, local_rank, modes[0], batches, args.passes)
+            solo = run_mode(modes[0])
         barrier()
     for m in modes:
         barrier()
-        dt, st = stream_pass(glnexus_b200, local_rank, m, batches, args.passes)
+        dt, st = run_mode(m)
         barrier()
         e2e[m] = (dt, st)
 
@@ -461,9 +471,10 @@ def main():
                                           "host loops of glx_upload_on; e2e includes them" % (up_ms[0], up_ms[1])},
             "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(head["h2d"] / n_b), "d2h_bytes_per_step": int(head["d2h"] / n_b),
                     "steps": int(n_b), "cells": head["cells"], "seconds": head["s"],
-                    "mode": "glxh_stream_* (C++ range-batch driver, 3 batches in flight): per range batch H2D of the record store + sites from pinned host memory, all genotyping "
-                            "kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF blocks into pinned host memory; every rank streams its "
-                            "own contiguous site range of one cohort",
+                    "mode": "glxh_stream_* (C++ range-batch driver, 3 batches in flight): per range batch H2D of the record store in its compact wire form (glx_wire) + sites "
+                            "from pinned host memory, expansion + all genotyping kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF "
+                            "blocks into pinned host memory; every rank streams its own contiguous site range of one cohort",
+                    "wire_build_s_untimed": wire_s, "wire_bytes_per_record": wire_bytes / max(1, sum(b.n_records for b in batches)),
                     "d2h_bytes_per_cell": head["d2h"] / max(1, head["cells"]), "h2d_bytes_per_cell": head["h2d"] / max(1, head["cells"]),
                     "uncompressed_bcf_bytes_per_cell": head["raw"] / max(1, head["cells"]),
                     "other_modes": {m: {"cells_per_s": e2e_red[m]["cells"] / e2e_red[m]["s"], "d2h_bytes_per_cell": e2e_red[m]["d2h"] / max(1, e2e_red[m]["cells"])}
