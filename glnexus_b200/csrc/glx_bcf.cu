@@ -306,11 +306,10 @@ __global__ void __launch_bounds__(256) glx_bgzf_pack_kernel(const uint8_t* __res
 }
 
 static int glx_bgzf_launch(glx_ctx* ctx, const BcfEnc& E, const uint32_t* span_site, GlxBcfState& B, uint32_t n_spans, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->func_attrs & 1)) {  // per device: a process may drive several
         CU(cudaFuncSetAttribute(glx_bgzf_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSmem)));
         CU(cudaFuncSetAttribute(glx_bgzf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSampleSmem)));
-        attr_set = true;
+        ctx->func_attrs |= 1;
     }
     CU(cudaMemsetAsync(B.hist, 0, GLX_BGZF_HIST * 4, st));
     glx_bgzf_sample_kernel<<<std::min<uint32_t>(n_spans, GLX_BGZF_SAMPLES), GLX_BGZF_THREADS, sizeof(BgzfSampleSmem), st>>>(E, span_site, B.hist);
@@ -507,10 +506,9 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
         CU(cudaGetLastError());
         if (mode == 0) {
             const size_t smem = sizeof(RawSmem);
-            static bool attr_set = false;
-            if (!attr_set) {
+            if (!(ctx->func_attrs & 2)) {
                 CU(cudaFuncSetAttribute(glx_bcf_span_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+                ctx->func_attrs |= 2;
             }
             glx_bcf_span_raw_kernel<<<n_spans, GLX_BCF_SPAN_THREADS, smem, st>>>(E, B.span_site, B.stream);
         } else {

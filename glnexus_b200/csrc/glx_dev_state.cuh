@@ -26,6 +26,7 @@ struct glx_ctx {
     std::string err;
     int sm_count = 0;
     uint32_t* crc_pw = nullptr;  // device: x^(8 * 64 * k) mod P for the BGZF stage's CRC-32
+    uint32_t func_attrs = 0;     // which large-shared-memory kernels have had their attribute set on this device
     uint8_t width_hint[GLX_MAX_FIELDS];  // narrow download: 1 when every value of the field in the previous batch fitted int8, else 2
     // kernel-path switches of the parity tests and ablations (glx_set_option); all 0 in production
     struct Options {

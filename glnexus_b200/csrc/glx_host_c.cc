@@ -171,6 +171,13 @@ int glxh_batch_pin(glxh_batch* hb) {
         pin(b.fld_cnt[k]);
         pin(b.fld_off[k]);
     }
+    pin(b.s_af);
+    {  // what the BCF encoder uploads per batch (glx_bcf_attach): page-locked too, or its copies would stall the stream
+        glx::build_bcf_meta(b);
+        glx::BcfMetaStore& m = b.bcf;
+        pin(m.rid); pin(m.qual); pin(m.dna_off); pin(m.dna_pool); pin(m.norm_beg); pin(m.norm_end); pin(m.norm_off); pin(m.norm_pool); pin(m.aq);
+        pin(m.contig_off); pin(m.contig_pool); pin(m.filter_off); pin(m.filter_pool);
+    }
     hb->pinned = rc == GLX_OK;
     return rc;
 }
