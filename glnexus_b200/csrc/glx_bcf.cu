@@ -405,7 +405,7 @@ int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* d, const glx_sites* sites, const
         if (B.meta_base) ctx->give(B.meta_base, B.meta_bytes);
         B.meta_base = nullptr;
         B.meta_bytes = mb;
-        cudaError_t e = ctx->take((void**)&B.meta_base, mb);
+        cudaError_t e = ctx->take((void**)&B.meta_base, &B.meta_bytes);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(bcf meta)");
     }
     Arena2 ar{B.meta_base};
@@ -422,7 +422,7 @@ int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* d, const glx_sites* sites, const
         if (B.work_base) ctx->give(B.work_base, B.work_bytes);
         B.work_base = nullptr;
         B.work_bytes = wb;
-        cudaError_t e = ctx->take((void**)&B.work_base, wb);
+        cudaError_t e = ctx->take((void**)&B.work_base, &B.work_bytes);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(bcf work)");
     }
     Arena2 wa{B.work_base};
@@ -476,7 +476,7 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
         if (B.stream) ctx->give(B.stream, B.stream_bytes);
         B.stream = nullptr;
         B.stream_bytes = need;
-        cudaError_t e = ctx->take((void**)&B.stream, need);
+        cudaError_t e = ctx->take((void**)&B.stream, &B.stream_bytes);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(bcf stream)");
     }
     if (mode == 1) {
@@ -485,7 +485,7 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
             if (B.packed) ctx->give(B.packed, B.packed_bytes);
             B.packed = nullptr;
             B.packed_bytes = pneed;
-            cudaError_t e = ctx->take((void**)&B.packed, pneed);
+            cudaError_t e = ctx->take((void**)&B.packed, &B.packed_bytes);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(bgzf blocks)");
         }
     }

@@ -14,7 +14,7 @@
 using namespace glxd;
 
 #define GLX_MAX_CHUNKS 8
-#define GLX_ARENA_CACHE 32  // a batch owns up to ten arenas and a range-batch driver keeps two or three batches in flight: no cudaFree in steady state
+#define GLX_ARENA_CACHE 64  // a batch owns up to ten arenas and a range-batch driver keeps two or three batches in flight: no cudaFree in steady state
 struct glx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -39,12 +39,16 @@ struct glx_ctx {
         void* p = nullptr;
         size_t bytes = 0;
     } cache[GLX_ARENA_CACHE];
-    cudaError_t take(void** p, size_t bytes) {
+    // *bytes in: wanted; out: what the block really holds (hand that to give())
+    cudaError_t take(void** p, size_t* bytes_io) {
+        const size_t bytes = *bytes_io;
         int best = -1;
         for (int i = 0; i < GLX_ARENA_CACHE; i++)
             if (cache[i].p && cache[i].bytes >= bytes && (best < 0 || cache[i].bytes < cache[best].bytes)) best = i;
-        if (best >= 0 && cache[best].bytes <= bytes * 2 + (1 << 20)) {
+        if (best >= 0) {  // best fit, however loose: range batches of one stream differ in size (a shard's first and last
+                          // batch are slices) and a cudaMalloc / cudaFree of a GB-sized arena stalls the whole device
             *p = cache[best].p;
+            *bytes_io = cache[best].bytes;
             cache[best] = Cached();
             return cudaSuccess;
         }

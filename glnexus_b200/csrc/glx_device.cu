@@ -719,7 +719,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     }
     d->in_bytes = copied;  // host-to-device bytes of this upload
     d->in_alloc = total ? total : 256;
-    cudaError_t e = ctx->take((void**)&d->in_base, d->in_alloc);
+    cudaError_t e = ctx->take((void**)&d->in_base, &d->in_alloc);
     if (e != cudaSuccess) return bail(e, "cudaMalloc(input arena)");
     Arena ar{d->in_base, total, 0};
     for (auto& it : items) {
@@ -821,7 +821,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     for (uint32_t k = 0; k < cfg->n_fields; k++) osz(d->fld_total[k] * 4);
     d->out_bytes = ob;
     d->out_alloc = ob;
-    e = ctx->take((void**)&d->out_base, ob);
+    e = ctx->take((void**)&d->out_base, &d->out_alloc);
     if (e != cudaSuccess) return bail(e, "cudaMalloc(output arena)");
     Arena oa{d->out_base, ob, 0};
     memset(&d->O, 0, sizeof d->O);
@@ -838,7 +838,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     const uint64_t cap = (uint64_t)ctx->sm_count * 16;
     d->general_blocks = (int)(want_blocks < cap ? (want_blocks ? want_blocks : 1) : cap);
     d->cnt_scratch_bytes = (size_t)d->general_blocks * threads * max_slots;
-    e = ctx->take((void**)&d->cnt_scratch, d->cnt_scratch_bytes);
+    e = ctx->take((void**)&d->cnt_scratch, &d->cnt_scratch_bytes);
     if (e != cudaSuccess) return bail(e, "cudaMalloc(scratch)");
     d->plan = make_fast_plan(d->cfg);
     if (d->force_general) d->plan.enabled = 0;
@@ -887,7 +887,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
         const size_t region_cells = (size_t)d->tile_sites * d->samples_per_cta;
         d->worklist_bytes = n_regions * region_cells * 8 + (n_regions + 64) * 4;
-        e = ctx->take((void**)&d->worklist, d->worklist_bytes);
+        e = ctx->take((void**)&d->worklist, &d->worklist_bytes);
         if (e != cudaSuccess) return bail(e, "cudaMalloc(worklist)");
         d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * region_cells);
         const size_t blob_part = ((Rn + 1) * blob_words(d->plan.n_rv) * 4 + 255) & ~(size_t)255;
@@ -895,7 +895,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         const size_t tq_part = (((size_t)d->n_site_tiles + 1) * 4 + 255) & ~(size_t)255;
         const size_t n_rblocks = (Rn + GLX_RESOLVE_THREADS - 1) / GLX_RESOLVE_THREADS;
         d->blob_bytes = blob_part + cur_part + tq_part + (n_rblocks + 2) * sizeof(uint2);
-        e = ctx->take((void**)&d->blobs, d->blob_bytes);
+        e = ctx->take((void**)&d->blobs, &d->blob_bytes);
         if (e != cudaSuccess) return bail(e, "cudaMalloc(record blobs)");
         d->tile_cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part);
         d->tile_q = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part);
@@ -1150,7 +1150,7 @@ int glx_download_narrow_on(glx_ctx* ctx, glx_dev_batch* d, glx_out16* out, void*
         for (uint32_t k = 0; k < d->n_fields; k++)
             if (field_is_narrowable(d, k)) b += ((d->fld_total[k] * 2 + 255) & ~(size_t)255);
         d->narrow_bytes = b;
-        cudaError_t e = ctx->take((void**)&d->narrow, b);
+        cudaError_t e = ctx->take((void**)&d->narrow, &d->narrow_bytes);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(narrow columns)");
     }
     d->narrow_overflow = reinterpret_cast<uint32_t*>(d->narrow);
