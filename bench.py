@@ -240,16 +240,21 @@ def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3, wire=False
     """Wall seconds to stream `batches` x `passes` through the C++ range-batch driver (glxh_stream_*): per batch the H2D of the
     record store + sites, all kernels, the on-device encoder and the D2H of its output. Returns (seconds, stats)."""
     rs = glnexus_b200.RangeStream(device, mode, depth, wire=wire)
-    for b in batches[:min(len(batches), depth)]:  # warm the arena cache and the pinned result buffers of every slot
+    for b in batches:  # one untimed pass: the arena cache and every slot's pinned result buffer have then seen the largest batch
         rs.submit(b)
     rs.drain()
     st0 = rs.stats()
     t = time.time()
+    marks = []
     for _ in range(passes):
         for b in batches:
             rs.submit(b)
+            marks.append(time.time() - t)
     rs.drain()
     dt = time.time() - t
+    if os.environ.get("GLX_BENCH_DEBUG"):
+        print(f"[rank {os.environ.get('RANK', '0')}] {mode} wire={wire}: sites per batch {[b.n_sites for b in batches]}, submit returns at (ms) "
+              f"{[round(m * 1e3, 1) for m in marks]}, drained at {dt * 1e3:.1f} ms", file=sys.stderr)
     st = {k: v - st0[k] for k, v in rs.stats().items()}
     rs.close()
     return dt, st
