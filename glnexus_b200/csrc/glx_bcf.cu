@@ -39,44 +39,61 @@ __global__ void __launch_bounds__(128) glx_bcf_layout_kernel(BcfEnc E) {
     if (s < E.n_sites) bcf_layout_site(E, s);
 }
 
-// one block: exclusive scans of rec_off[0..S] and hdr_off[0..S] in place (entry S = the totals)
+// one block: exclusive scans of rec_off[0..S] and hdr_off[0..S] in place (entry S = the totals), tile by tile with coalesced
+// loads; totals[4] counts the sites that have a record
 #define GLX_BCF_SCAN_THREADS 1024
 __global__ void __launch_bounds__(GLX_BCF_SCAN_THREADS) glx_bcf_offsets_kernel(BcfEnc E, unsigned long long* __restrict__ totals) {
-    __shared__ unsigned long long s_r[GLX_BCF_SCAN_THREADS], s_h[GLX_BCF_SCAN_THREADS];
-    const uint32_t n = E.n_sites, tid = threadIdx.x;
-    const uint32_t per = (n + GLX_BCF_SCAN_THREADS - 1) / GLX_BCF_SCAN_THREADS;
-    const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
-    unsigned long long r = 0, h = 0;
-    uint32_t nrec = 0;
-    for (uint32_t i = i0; i < i1; i++) {
-        r += E.rec_off[i];
-        h += E.hdr_off[i];
-        nrec += E.rec_off[i] != 0;
-    }
-    if (nrec) atomicAdd(totals + 4, (unsigned long long)nrec);  // sites that have a record (zeroed before the encode)
-    s_r[tid] = r;
-    s_h[tid] = h;
+    __shared__ unsigned long long s_r[32], s_h[32];
+    __shared__ uint32_t s_n[32];
+    __shared__ unsigned long long s_carry[3];
+    const uint32_t n = E.n_sites, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry[0] = s_carry[1] = s_carry[2] = 0;
     __syncthreads();
-    for (uint32_t d = 1; d < GLX_BCF_SCAN_THREADS; d <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
-        const unsigned long long ar = tid >= d ? s_r[tid - d] : 0, ah = tid >= d ? s_h[tid - d] : 0;
+    for (uint32_t base = 0; base < n; base += GLX_BCF_SCAN_THREADS) {
+        const uint32_t i = base + tid;
+        const unsigned long long r = i < n ? E.rec_off[i] : 0ull, h = i < n ? E.hdr_off[i] : 0ull;
+        unsigned long long ir = r, ih = h;
+        uint32_t in_ = r != 0;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const unsigned long long a = __shfl_up_sync(0xffffffffu, ir, d), b = __shfl_up_sync(0xffffffffu, ih, d);
+            const uint32_t c = __shfl_up_sync(0xffffffffu, in_, d);
+            if (lane >= d) {
+                ir += a;
+                ih += b;
+                in_ += c;
+            }
+        }
+        if (lane == 31) {
+            s_r[wid] = ir;
+            s_h[wid] = ih;
+            s_n[wid] = in_;
+        }
         __syncthreads();
-        s_r[tid] += ar;
-        s_h[tid] += ah;
+        unsigned long long br = s_carry[0], bh = s_carry[1];
+        for (uint32_t k = 0; k < wid; k++) {
+            br += s_r[k];
+            bh += s_h[k];
+        }
+        if (i < n) {
+            E.rec_off[i] = br + ir - r;
+            E.hdr_off[i] = bh + ih - h;
+        }
+        __syncthreads();
+        if (tid == GLX_BCF_SCAN_THREADS - 1) {
+            uint32_t cn = 0;
+            for (uint32_t k = 0; k < 32; k++) cn += s_n[k];
+            s_carry[0] = br + ir;
+            s_carry[1] = bh + ih;
+            s_carry[2] += cn;
+        }
         __syncthreads();
     }
-    unsigned long long br = tid ? s_r[tid - 1] : 0, bh = tid ? s_h[tid - 1] : 0;
-    for (uint32_t i = i0; i < i1; i++) {
-        const unsigned long long lr = E.rec_off[i], lh = E.hdr_off[i];
-        E.rec_off[i] = br;
-        E.hdr_off[i] = bh;
-        br += lr;
-        bh += lh;
-    }
-    if (tid == GLX_BCF_SCAN_THREADS - 1) {
-        E.rec_off[n] = s_r[tid];
-        E.hdr_off[n] = s_h[tid];
-        totals[0] = s_r[tid];
-        totals[1] = s_h[tid];
+    if (tid == 0) {
+        E.rec_off[n] = s_carry[0];
+        E.hdr_off[n] = s_carry[1];
+        totals[0] = s_carry[0];
+        totals[1] = s_carry[1];
+        totals[4] = s_carry[2];
     }
 }
 
@@ -158,14 +175,18 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_sample_kernel(Bc
     const uint32_t n = (uint32_t)(hi - lo);
     for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt) M.sh.freq[i] = 0;
     bcf_fill_span<BcfPadded>(E, lo, hi, span_site[b], M.in, M.tab, tid, nt);
-    bgzf_tokenize<true, false>(M.sh, M.tab, M.in, n, tid, nt);
+    bgzf_tokenize<true, false>(M.sh, M.tab, M.in, n, nullptr, tid, nt);
     __syncthreads();
     for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt)
         if (M.sh.freq[i]) atomicAdd(&hist[i], M.sh.freq[i]);
 }
 
-__global__ void glx_bgzf_table_kernel(const uint32_t* __restrict__ hist, BgzfTable* __restrict__ tab) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) bgzf_table_build(hist, *tab);
+__global__ void __launch_bounds__(320) glx_bgzf_table_kernel(const uint32_t* __restrict__ hist, BgzfTable* __restrict__ tab) {
+    __shared__ BgzfTable s_tab;
+    __shared__ uint32_t s_scratch[64];
+    bgzf_table_build(hist, s_tab, s_scratch, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < sizeof(BgzfTable) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tab)[i] = reinterpret_cast<const uint32_t*>(&s_tab)[i];
 }
 
 // One CTA per span: gather the span, CRC-32, DEFLATE under the batch's code and BGZF framing in shared memory, one bulk store
@@ -193,9 +214,7 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_span_kernel(BcfE
     bcf_fill_span<BcfPadded>(E, lo, hi, span_site[blockIdx.x], M.in, M.tab, tid, nt);  // ends with a barrier
     GLX_PHASE(0);
     bgzf_put_header(M.sh, out_words, tid, nt);
-    bgzf_crc_parts(M.sh, crc_pw, M.in, n, tid, nt);
-    GLX_PHASE(3);
-    bgzf_tokenize<false, true>(M.sh, M.tab, M.in, n, tid, nt);
+    bgzf_tokenize<false, true>(M.sh, M.tab, M.in, n, crc_pw, tid, nt);
     __syncthreads();
     GLX_PHASE(4);
     if (tid == 0) bgzf_crc_finish(M.sh, crc_pw);
@@ -313,7 +332,7 @@ static int glx_bgzf_launch(glx_ctx* ctx, const BcfEnc& E, const uint32_t* span_s
     }
     CU(cudaMemsetAsync(B.hist, 0, GLX_BGZF_HIST * 4, st));
     glx_bgzf_sample_kernel<<<std::min<uint32_t>(n_spans, GLX_BGZF_SAMPLES), GLX_BGZF_THREADS, sizeof(BgzfSampleSmem), st>>>(E, span_site, B.hist);
-    glx_bgzf_table_kernel<<<1, 32, 0, st>>>(B.hist, B.table);
+    glx_bgzf_table_kernel<<<1, 320, 0, st>>>(B.hist, B.table);
     glx_bgzf_span_kernel<<<n_spans, GLX_BGZF_THREADS, sizeof(BgzfSmem), st>>>(E, span_site, B.table, ctx->crc_pw, B.stream, B.blk_sizes);
     glx_bgzf_offsets_kernel<<<1, 1024, 0, st>>>(B.blk_sizes, n_spans, B.blk_offsets, B.totals);
     glx_bgzf_pack_kernel<<<n_spans, 256, 0, st>>>(B.stream, B.blk_sizes, B.blk_offsets, B.packed);

@@ -51,7 +51,7 @@ struct BgzfShared {
     uint32_t wbits[GLX_BGZF_WORKERS];           // per-worker bit counts -> bit offsets
     unsigned long long tok[GLX_BGZF_WORKERS];   // bit i: a token starts at byte i of the worker's chunk (literal = 1 byte, match = to the next start)
     unsigned long long useD[GLX_BGZF_WORKERS];  // bit i: the match starting there copies from the structural distance D, not from distance 1
-    uint32_t n_in, data_bits, crc, crc_acc, stored, block_len;
+    uint32_t n_in, data_bits, crc, crc_acc, crc_tail, stored, block_len;
     uint32_t crc_table[4][256];
 };
 
@@ -132,28 +132,16 @@ __host__ __device__ inline void bgzf_crc_setup(BgzfShared& sh, uint32_t tid, uin
             sh.crc_table[t][i] = c;
         }
     }
-    if (tid == 0) sh.crc_acc = 0;
+    if (tid == 0) sh.crc_acc = sh.crc_tail = 0;
 }
-__host__ __device__ inline void bgzf_crc_parts(BgzfShared& sh, const uint32_t* __restrict__ pw, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
-    const uint32_t pad = GLX_BGZF_WORKERS * GLX_BGZF_CHUNK - n;
-    for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
-        const uint32_t v0 = w * GLX_BGZF_CHUNK, v1 = v0 + GLX_BGZF_CHUNK;
-        if (v1 <= pad) continue;
-        uint32_t c = 0;
-        if ((pad & 3u) == 0 && v0 >= pad) {  // whole aligned words (every full span: pad = 256)
-            for (uint32_t v = v0; v < v1; v += 4) {
-                const uint32_t x = c ^ *reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(v - pad));
-                c = sh.crc_table[3][x & 0xff] ^ sh.crc_table[2][x >> 8 & 0xff] ^ sh.crc_table[1][x >> 16 & 0xff] ^ sh.crc_table[0][x >> 24];
-            }
-        } else {
-            for (uint32_t v = v0 < pad ? pad : v0; v < v1; v++) c = sh.crc_table[0][(c ^ in[BcfPadded::phys(v - pad)]) & 0xff] ^ (c >> 8);
-        }
-        if (c) bgzf_xor(&sh.crc_acc, crc_multmodp(pw[GLX_BGZF_WORKERS - 1 - w], c));
-    }
-}
+// The span's CRC from the workers' chunk CRCs (computed inside the tokenizer's word loop): raw (init 0, no final xor) CRCs
+// combine as crc(A || B) = crc(A) * x^(8|B|) + crc(B); with 64-byte chunks, chunk w of n_full full chunks is followed by
+// 64 * (n_full - 1 - w) + (n mod 64) bytes, so crc_raw(span) = (XOR_w crc_w * pw[n_full - 1 - w]) * x^(8 (n mod 64)) + crc(tail).
 __host__ __device__ inline void bgzf_crc_finish(BgzfShared& sh, const uint32_t* __restrict__ pw) {  // one thread
-    const uint32_t xn = sh.n_in == GLX_BCF_SPAN ? pw[GLX_BGZF_WORKERS] : crc_x_pow_8n(sh.n_in);
-    sh.crc = ~(sh.crc_acc ^ crc_multmodp(xn, 0xffffffffu));
+    const uint32_t n = sh.n_in, r = n % GLX_BGZF_CHUNK;
+    const uint32_t raw = (r ? crc_multmodp(crc_x_pow_8n(r), sh.crc_acc) : sh.crc_acc) ^ sh.crc_tail;
+    const uint32_t xn = n == GLX_BCF_SPAN ? pw[GLX_BGZF_WORKERS] : crc_x_pow_8n(n);
+    sh.crc = ~(raw ^ crc_multmodp(xn, 0xffffffffu));
 }
 
 // ---- DEFLATE symbols ----
@@ -293,7 +281,8 @@ __host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const BcfSpanT
 // run, else a distance-1 run of >= 3, else a literal — recording the token starts. Matches end at the chunk's end and at
 // piece boundaries. HIST: count the symbols into sh.freq (sampling). COUNT: the worker's bit count under sh.tab into sh.wbits.
 template <bool HIST, bool COUNT>
-__host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t tid, uint32_t nt) {
+__host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, const uint32_t* __restrict__ crc_pw, uint32_t tid,
+                                              uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
         const uint32_t c0 = w * GLX_BGZF_CHUNK;
         if (c0 >= n) {
@@ -305,12 +294,24 @@ __host__ __device__ inline void bgzf_tokenize(BgzfShared& sh, const BcfSpanTab& 
         const unsigned long long live = L == 64 ? ~0ull : ((1ull << L) - 1);
         const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));  // the chunk is contiguous and word-aligned
         unsigned long long eq1 = 0, zero = 0;
-        uint32_t carry = c0 ? in[BcfPadded::phys(c0 - 1)] : 0u;
+        uint32_t carry = c0 ? in[BcfPadded::phys(c0 - 1)] : 0u, crc = 0;
         for (uint32_t k = 0; k < 16; k++) {
             const uint32_t x = W[k];
             eq1 |= (unsigned long long)bgzf_eq_nibble(x, (x << 8) | carry) << (4 * k);
             if (HIST) zero |= (unsigned long long)bgzf_eq_nibble(x, 0u) << (4 * k);
             carry = x >> 24;
+            if (COUNT && L == 64) {  // CRC-32 of the chunk, four bytes per step (the compressing pass only)
+                const uint32_t y = crc ^ x;
+                crc = sh.crc_table[3][y & 0xff] ^ sh.crc_table[2][y >> 8 & 0xff] ^ sh.crc_table[1][y >> 16 & 0xff] ^ sh.crc_table[0][y >> 24];
+            }
+        }
+        if (COUNT) {
+            if (L == 64) {
+                if (crc) bgzf_xor(&sh.crc_acc, crc_multmodp(crc_pw[n / GLX_BGZF_CHUNK - 1 - w], crc));
+            } else {  // the span's short last chunk
+                for (uint32_t i = 0; i < L; i++) crc = sh.crc_table[0][(crc ^ in[BcfPadded::phys(c0 + i)]) & 0xff] ^ (crc >> 8);
+                sh.crc_tail = crc;
+            }
         }
         if (!c0) eq1 &= ~1ull;  // the span's first byte has no predecessor
         eq1 &= live;
@@ -496,21 +497,92 @@ struct BgzfBits {
 };
 
 // freq[320] (literal/length, then distance counts of the sampled spans) -> the batch's table: smoothed frequencies, both
-// codes, and the dynamic-block header (BFINAL = 1, BTYPE = 10, the run-length coded code lengths). One thread.
-__host__ __device__ inline void bgzf_table_build(const uint32_t* freq, BgzfTable& tab) {
-    uint32_t f[288];
-    for (uint32_t i = 0; i < 288; i++) f[i] = i < GLX_BGZF_LITS ? freq[i] + 1 : 0;  // + 1: every symbol can be coded
-    bgzf_code_lengths(f, GLX_BGZF_LITS, 15, tab.lit_len);
-    tab.lit_len[286] = tab.lit_len[287] = 0;
-    uint32_t d[32];
-    for (uint32_t i = 0; i < 32; i++) d[i] = i < GLX_BGZF_DISTS ? freq[288 + i] + 1 : 0;
-    bgzf_code_lengths(d, GLX_BGZF_DISTS, 15, tab.dist_len);
-    tab.dist_len[30] = tab.dist_len[31] = 0;
-    bgzf_assign_codes(tab.lit_len, 288, tab.lit_code);
-    bgzf_assign_codes(tab.dist_len, 32, tab.dist_code);
-    for (uint32_t i = 0; i < 288; i++) tab.lit_cl[i] = tab.lit_code[i] | (uint32_t)tab.lit_len[i] << 16;
-    for (uint32_t i = 0; i < 32; i++) tab.dist_cl[i] = tab.dist_code[i] | (uint32_t)tab.dist_len[i] << 16;
-    for (uint32_t i = 0; i < GLX_BGZF_HDR_WORDS; i++) tab.hdr_words[i] = 0;
+// codes, and the dynamic-block header (BFINAL = 1, BTYPE = 10, the run-length coded code lengths). A block-level function
+// (every thread calls it): per-symbol work runs in parallel, the two Kraft settles and the header walk on single threads.
+// scratch: 64 words of shared memory.
+__host__ __device__ inline void bgzf_table_build(const uint32_t* freq, BgzfTable& tab, uint32_t* scratch, uint32_t tid, uint32_t nt) {
+    uint32_t* tot = scratch;       // [0] literal/length total, [1] distance total, [2] / [3] their Kraft sums (units of 2^-15)
+    uint32_t* cnt = scratch + 8;   // [0..16) literal/length code-length counts -> first codes, [16..32) distance
+    for (uint32_t i = tid; i < 48; i += nt) scratch[i] = 0;
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt) {  // + 1: every symbol can be coded
+        const bool lit = i < 288;
+        const uint32_t j = lit ? i : i - 288;
+        if (lit ? j < GLX_BGZF_LITS : j < GLX_BGZF_DISTS) bgzf_add(&tot[lit ? 0 : 1], freq[i] + 1);
+    }
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt) {
+        const bool lit = i < 288;
+        const uint32_t j = lit ? i : i - 288;
+        uint32_t l = 0;
+        if (lit ? j < GLX_BGZF_LITS : j < GLX_BGZF_DISTS) {
+            const uint32_t f = freq[i] + 1, total = tot[lit ? 0 : 1];
+            l = 1;
+            while (l < 15 && ((unsigned long long)f << l) < total) l++;
+            bgzf_add(&tot[lit ? 2 : 3], 32768u >> l);
+        }
+        (lit ? tab.lit_len : tab.dist_len)[j] = (uint8_t)l;
+    }
+    GLX_BLOCK_SYNC();
+    // settle each code to a Kraft sum of exactly one: lengthen the longest codes while oversubscribed, then shorten codes in
+    // index order while slack remains (each pass shortens at least one code of the current maximum length)
+    for (uint32_t a = 0; a < 2; a++) {
+        if (tid != (nt > 32 ? a * 32 : 0u)) continue;
+        uint8_t* len = a ? tab.dist_len : tab.lit_len;
+        const uint32_t n = a ? GLX_BGZF_DISTS : GLX_BGZF_LITS, full = 32768u;
+        uint32_t K = tot[2 + a];
+        for (uint32_t L = 14; K > full && L >= 1; L--)
+            for (uint32_t i = 0; i < n && K > full; i++)
+                if (len[i] == L) {
+                    len[i]++;
+                    K -= full >> (L + 1);
+                }
+        uint32_t slack = full - K;
+        while (slack)
+            for (uint32_t i = 0; i < n && slack; i++) {
+                const uint32_t l = len[i];
+                if (l > 1 && (full >> l) <= slack) {
+                    len[i] = (uint8_t)(l - 1);
+                    slack -= full >> l;
+                }
+            }
+    }
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt) {  // canonical codes: count per length ...
+        const bool lit = i < 288;
+        const uint32_t l = lit ? tab.lit_len[i] : tab.dist_len[i - 288];
+        if (l) bgzf_add(&cnt[(lit ? 0 : 16) + l], 1);
+    }
+    GLX_BLOCK_SYNC();
+    if (tid == 0)  // ... first code per length ...
+        for (uint32_t a = 0; a < 2; a++) {
+            uint32_t* c = cnt + 16 * a;
+            uint32_t code = 0, prev = 0;
+            for (uint32_t b = 1; b < 16; b++) {
+                code = (code + prev) << 1;
+                prev = c[b];
+                c[b] = code;
+            }
+        }
+    GLX_BLOCK_SYNC();
+    for (uint32_t i = tid; i < GLX_BGZF_HIST; i += nt) {  // ... code = first + rank among earlier symbols of that length, bit-reversed
+        const bool lit = i < 288;
+        const uint32_t j = lit ? i : i - 288;
+        const uint8_t* len = lit ? tab.lit_len : tab.dist_len;
+        const uint32_t l = len[j];
+        uint32_t rank = 0;
+        for (uint32_t e = 0; e < j; e++) rank += len[e] == l;
+        uint32_t v = l ? cnt[(lit ? 0 : 16) + l] + rank : 0u, r = 0;
+        for (uint32_t b = 0; b < l; b++) {
+            r = r << 1 | (v & 1);
+            v >>= 1;
+        }
+        (lit ? tab.lit_code : tab.dist_code)[j] = (uint16_t)r;
+        (lit ? tab.lit_cl : tab.dist_cl)[j] = r | l << 16;
+    }
+    for (uint32_t i = tid; i < GLX_BGZF_HDR_WORDS; i += nt) tab.hdr_words[i] = 0;
+    GLX_BLOCK_SYNC();
+    if (tid != 0) return;
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     const uint32_t hlit = 286, hdist = 30;  // every symbol has a code
     uint32_t cl_freq[19];

@@ -411,10 +411,11 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
         const unsigned long long lo = b * span, hi = std::min<unsigned long long>(X.total, lo + span);
         for (uint32_t k = 0; k < GLX_BGZF_HIST; k++) sh->freq[k] = 0;
         bcf_fill_span<BcfPadded>(X.E, lo, hi, bcf_first_site(X.E, lo), in.data(), *tab, 0, 1);
-        bgzf_tokenize<true, false>(*sh, *tab, in.data(), (uint32_t)(hi - lo), 0, 1);
+        bgzf_tokenize<true, false>(*sh, *tab, in.data(), (uint32_t)(hi - lo), nullptr, 0, 1);
         for (uint32_t k = 0; k < GLX_BGZF_HIST; k++) hist[k] += sh->freq[k];
     }
-    bgzf_table_build(hist.data(), sh->tab);
+    uint32_t scratch[64];
+    bgzf_table_build(hist.data(), sh->tab, scratch, 0, 1);
     for (unsigned long long lo = 0; lo < X.total; lo += span) {
         const unsigned long long hi = std::min<unsigned long long>(X.total, lo + span);
         const uint32_t n = (uint32_t)(hi - lo);
@@ -425,8 +426,7 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
         bgzf_crc_setup(*sh, 0, 1);
         bcf_fill_span<BcfPadded>(X.E, lo, hi, bcf_first_site(X.E, lo), in.data(), *tab, 0, 1);
         bgzf_put_header(*sh, out_words, 0, 1);
-        bgzf_crc_parts(*sh, pw.data(), in.data(), n, 0, 1);
-        bgzf_tokenize<false, true>(*sh, *tab, in.data(), n, 0, 1);
+        bgzf_tokenize<false, true>(*sh, *tab, in.data(), n, pw.data(), 0, 1);
         bgzf_crc_finish(*sh, pw.data());
         bgzf_scan_bits_serial(*sh);
         bgzf_emit(*sh, *tab, in.data(), n, out_words, 0, 1);
