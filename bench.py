@@ -240,8 +240,9 @@ def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3, wire=False
     """Wall seconds to stream `batches` x `passes` through the C++ range-batch driver (glxh_stream_*): per batch the H2D of the
     record store + sites, all kernels, the on-device encoder and the D2H of its output. Returns (seconds, stats)."""
     rs = glnexus_b200.RangeStream(device, mode, depth, wire=wire)
-    for b in batches:  # one untimed pass: the arena cache and every slot's pinned result buffer have then seen the largest batch
-        rs.submit(b)
+    for _ in range(depth):  # untimed passes: the arena cache and EVERY slot's pinned result buffer have then seen every batch size
+        for b in batches:   # (slots rotate, so one pass is not enough when the batch count is not a multiple of the depth)
+            rs.submit(b)
     rs.drain()
     st0 = rs.stats()
     t = time.time()

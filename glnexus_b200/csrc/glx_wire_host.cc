@@ -1,12 +1,24 @@
 // glx_wire_host.cc — builds the compact wire form of a packed batch's record store (glx_wire, include/glx.h): what crosses
 // PCIe instead of the kernel-facing columns. SURVEY.md §8f N2 (start): the packer's output at the width the data needs.
 #include <cstring>
+#include <thread>
 
 #include "glx_host.hpp"
 
 namespace glx {
 
 namespace {
+// fn(t, lo, hi) over [0, n) cut into T contiguous chunks, one thread each
+template <class F>
+void parallel_chunks(uint64_t n, unsigned T, F&& fn) {
+    if (T <= 1 || n < 65536) {
+        fn(0u, (uint64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; t++) pool.emplace_back([&, t]() { fn(t, n * t / T, n * (t + 1) / T); });
+    for (auto& th : pool) th.join();
+}
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 bool fits16(int32_t v) { return v == GLX_INT_MISSING || v == GLX_INT_VECTOR_END || (v >= -32760 && v <= 32767); }
 int16_t to16(int32_t v) { return v == GLX_INT_MISSING ? (int16_t)0x8000 : (v == GLX_INT_VECTOR_END ? (int16_t)0x8001 : (int16_t)v); }
@@ -28,45 +40,82 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
     h.n_al = r.n_al;
     h.n_al_pool = r.n_al_pool;
     h.n_pool = r.n_pool;
-    // ---- what fits ----
+    // ---- what fits (one pass over the records on T threads; per-chunk results merged below) ----
+    const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    struct Part {
+        bool len16 = true, gt8 = true, collen8 = true, pool16 = true, pool_order = true;
+        uint64_t n_variant = 0, pool_units = 0;
+        std::vector<uint32_t> exc;
+        bool any[GLX_MAX_COLS] = {}, f16[GLX_MAX_COLS];
+    };
+    std::vector<Part> parts(T);
+    std::vector<uint64_t> chunk_lo(T + 1, R);
+    parallel_chunks(R, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
+        Part& P = parts[t];
+        chunk_lo[t] = lo;
+        for (uint64_t c = 0; c < C; c++) P.f16[c] = true;
+        for (uint64_t i = lo; i < hi; i++) {
+            const int64_t len = (int64_t)r.end[i] - r.beg[i];
+            if (len < 0 || len > 65535) P.len16 = false;
+            if (!(r.flags[i] & GLX_RF_IS_REF)) P.n_variant++;
+            for (int hlf = 0; hlf < 2; hlf++) {
+                const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
+                if (!(g == GLX_GT16_VECTOR_END || (g >= 0 && g <= 508 && !(g & 1)))) P.gt8 = false;
+            }
+            if (r.maxend[i] != r.end[i]) {
+                P.exc.push_back((uint32_t)i);
+                P.exc.push_back((uint32_t)r.maxend[i]);
+            }
+            for (uint64_t c = 0; c < C; c++) {
+                const uint16_t cl = r.col_len[c * R + i];
+                if (cl >= 0xFD && cl < 0xFFF0) P.collen8 = false;
+                if (cl == 1) {
+                    P.any[c] = true;
+                    if (!fits16(r.col_val[c * R + i])) P.f16[c] = false;
+                } else if (cl < 0xFFF0)
+                    P.pool_units += cl;
+            }
+        }
+    });
     bool len16 = true, gt8 = true, collen8 = true, pool16 = true, allen16 = true;
     uint64_t n_variant = 0;
     std::vector<uint32_t> exc;  // (record, maxend) pairs where maxend != end
-    for (uint64_t i = 0; i < R; i++) {
-        const int64_t len = (int64_t)r.end[i] - r.beg[i];
-        if (len < 0 || len > 65535) len16 = false;
-        if (!(r.flags[i] & GLX_RF_IS_REF)) n_variant++;
-        for (int hlf = 0; hlf < 2; hlf++) {
-            const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
-            if (!(g == GLX_GT16_VECTOR_END || (g >= 0 && g <= 508 && !(g & 1)))) gt8 = false;
-        }
-        if (r.maxend[i] != r.end[i]) {
-            exc.push_back((uint32_t)i);
-            exc.push_back((uint32_t)r.maxend[i]);
-        }
+    std::vector<uint64_t> pool_base(T + 1, 0), var_base(T + 1, 0);
+    for (unsigned t = 0; t < T; t++) {
+        const Part& P = parts[t];
+        len16 = len16 && P.len16;
+        gt8 = gt8 && P.gt8;
+        collen8 = collen8 && P.collen8;
+        exc.insert(exc.end(), P.exc.begin(), P.exc.end());
+        pool_base[t + 1] = pool_base[t] + P.pool_units;
+        var_base[t + 1] = var_base[t] + P.n_variant;
+        for (uint64_t c = 0; c < C; c++) h.col_w[c] = std::max<uint8_t>(h.col_w[c], !P.any[c] ? 0 : (P.f16[c] ? 2 : 4));
     }
+    n_variant = var_base[T];
+    if (pool_base[T] != r.n_pool) return Status::NotImplemented("build_wire: value pool has entries no record refers to");
     // the pool must be laid out record-major, column-minor (what pack_records / slice_batch / the generator write): offsets are then prefix sums
-    {
-        uint64_t run = 0;
-        for (uint64_t i = 0; i < R; i++)
+    parallel_chunks(R, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
+        uint64_t run = pool_base[t];
+        for (uint64_t i = lo; i < hi; i++)
             for (uint64_t c = 0; c < C; c++) {
-                const uint16_t len = r.col_len[c * R + i];
-                if (len >= 0xFD && len < 0xFFF0) collen8 = false;
-                if (len >= 0xFFF0 || len == 1) continue;
-                if ((uint64_t)(uint32_t)r.col_val[c * R + i] != run) return Status::NotImplemented("build_wire: value pool is not in record order");
-                run += len;
+                const uint16_t cl = r.col_len[c * R + i];
+                if (cl >= 0xFFF0 || cl == 1) continue;
+                if ((uint64_t)(uint32_t)r.col_val[c * R + i] != run) parts[t].pool_order = false;
+                run += cl;
             }
-        if (run != r.n_pool) return Status::NotImplemented("build_wire: value pool has entries no record refers to");
-    }
-    for (uint64_t i = 0; i < r.n_pool && pool16; i++) pool16 = fits16(r.pool[i]);
-    for (uint64_t c = 0; c < C; c++) {
-        bool any = false, f16 = true;
-        for (uint64_t i = 0; i < R; i++)
-            if (r.col_len[c * R + i] == 1) {
-                any = true;
-                if (!fits16(r.col_val[c * R + i])) f16 = false;
-            }
-        h.col_w[c] = !any ? 0 : (f16 ? 2 : 4);
+    });
+    for (unsigned t = 0; t < T; t++)
+        if (!parts[t].pool_order) return Status::NotImplemented("build_wire: value pool is not in record order");
+    {
+        std::vector<char> ok(T, 1);
+        parallel_chunks(r.n_pool, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
+            for (uint64_t i = lo; i < hi; i++)
+                if (!fits16(r.pool[i])) {
+                    ok[t] = 0;
+                    break;
+                }
+        });
+        for (char o : ok) pool16 = pool16 && o;
     }
     for (uint64_t a = 0; a < r.n_al && allen16; a++) allen16 = r.al_len[a] <= 65535;
     bool filt_variant = true;
@@ -113,49 +162,48 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
         uint32_t* g32 = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_GT]);
         float* q = reinterpret_cast<float*>(p + h.off[GLX_WS_QUAL]);
         uint32_t* f = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_FILT]);
-        uint64_t v = 0;
-        for (uint64_t i = 0; i < R; i++) {
-            const uint32_t len = (uint32_t)(r.end[i] - r.beg[i]);
-            if (len16) l16[i] = (uint16_t)len;
-            else l32[i] = len;
-            if (gt8) {
-                for (int hlf = 0; hlf < 2; hlf++) {
-                    const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
-                    g8[2 * i + hlf] = g == GLX_GT16_VECTOR_END ? (uint8_t)0xFF : (uint8_t)(g >> 1);
-                }
-            } else
-                g32[i] = r.gt[i];
-            if (!(r.flags[i] & GLX_RF_IS_REF)) {
-                q[v] = r.qual[i];
-                if (filt_variant) f[v] = r.filt[i];
-                v++;
-            }
-            if (!filt_variant) f[i] = r.filt[i];
-        }
-    }
-    {
         uint8_t* c8 = p + h.off[GLX_WS_COL_LEN];
         uint16_t* c16 = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_COL_LEN]);
-        for (uint64_t i = 0; i < C * R; i++) {
-            const uint16_t len = r.col_len[i];
-            if (collen8) c8[i] = len >= 0xFFF0 ? (uint8_t)(len & 0xFF) : (uint8_t)len;  // 0xFFFF -> 0xFF, 0xFFFE -> 0xFE, 0xFFFD -> 0xFD
-            else c16[i] = len;
-        }
-        size_t co = h.off[GLX_WS_COL_VAL];
-        for (uint64_t c = 0; c < C; c++) {
-            if (h.col_w[c] == 2) {
-                int16_t* d = reinterpret_cast<int16_t*>(p + co);
-                for (uint64_t i = 0; i < R; i++) d[i] = r.col_len[c * R + i] == 1 ? to16(r.col_val[c * R + i]) : (int16_t)0;
-            } else if (h.col_w[c] == 4) {
-                int32_t* d = reinterpret_cast<int32_t*>(p + co);
-                for (uint64_t i = 0; i < R; i++) d[i] = r.col_len[c * R + i] == 1 ? r.col_val[c * R + i] : 0;
+        std::vector<size_t> col_off(C + 1, h.off[GLX_WS_COL_VAL]);
+        for (uint64_t c = 0; c < C; c++) col_off[c + 1] = col_off[c] + align16(R * h.col_w[c]);
+        parallel_chunks(R, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
+            uint64_t v = var_base[t];
+            for (uint64_t i = lo; i < hi; i++) {
+                const uint32_t len = (uint32_t)(r.end[i] - r.beg[i]);
+                if (len16) l16[i] = (uint16_t)len;
+                else l32[i] = len;
+                if (gt8) {
+                    for (int hlf = 0; hlf < 2; hlf++) {
+                        const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
+                        g8[2 * i + hlf] = g == GLX_GT16_VECTOR_END ? (uint8_t)0xFF : (uint8_t)(g >> 1);
+                    }
+                } else
+                    g32[i] = r.gt[i];
+                if (!(r.flags[i] & GLX_RF_IS_REF)) {
+                    q[v] = r.qual[i];
+                    if (filt_variant) f[v] = r.filt[i];
+                    v++;
+                }
+                if (!filt_variant) f[i] = r.filt[i];
             }
-            co += align16(R * h.col_w[c]);
-        }
+            for (uint64_t c = 0; c < C; c++) {
+                int16_t* d16 = reinterpret_cast<int16_t*>(p + col_off[c]);
+                int32_t* d32 = reinterpret_cast<int32_t*>(p + col_off[c]);
+                for (uint64_t i = lo; i < hi; i++) {
+                    const uint16_t cl = r.col_len[c * R + i];
+                    if (collen8) c8[c * R + i] = cl >= 0xFFF0 ? (uint8_t)(cl & 0xFF) : (uint8_t)cl;  // 0xFFFF -> 0xFF, 0xFFFE -> 0xFE, 0xFFFD -> 0xFD
+                    else c16[c * R + i] = cl;
+                    if (h.col_w[c] == 2) d16[i] = cl == 1 ? to16(r.col_val[c * R + i]) : (int16_t)0;
+                    else if (h.col_w[c] == 4) d32[i] = cl == 1 ? r.col_val[c * R + i] : 0;
+                }
+            }
+        });
     }
     if (pool16) {
         int16_t* d = reinterpret_cast<int16_t*>(p + h.off[GLX_WS_POOL]);
-        for (uint64_t i = 0; i < r.n_pool; i++) d[i] = to16(r.pool[i]);
+        parallel_chunks(r.n_pool, T, [&](unsigned, uint64_t lo, uint64_t hi) {
+            for (uint64_t i = lo; i < hi; i++) d[i] = to16(r.pool[i]);
+        });
     } else
         memcpy(p + h.off[GLX_WS_POOL], r.pool, r.n_pool * 4);
     if (allen16) {
