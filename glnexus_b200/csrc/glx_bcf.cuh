@@ -545,6 +545,7 @@ struct BcfPadded {
 // each FORMAT block's key/descriptor bytes, each FORMAT block's data — with where its bytes come from. Built by the whole
 // block (one thread per piece, so the plan loads of all pieces are in flight together), then the span is filled word by
 // word: a thread finds its word's piece by binary search and converts the source values, 16 independent words per thread.
+#define GLX_BCF_FILL_UNROLL 4
 #define GLX_BCF_TAB_MAX 256
 #define GLX_BCF_REC_MAX 24
 enum { BCF_PK_BYTES = 0, BCF_PK_GT = 1, BCF_PK_INT = 2, BCF_PK_RAW4 = 3, BCF_PK_TRIM = 4, BCF_PK_STR = 5 };
@@ -826,15 +827,26 @@ __host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, const BcfSpanTab& 
                         if (lane == 0) buf[Addr::phys((unsigned long long)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (unsigned long long)(x - base));
                     }
             }
+            // aligned words, lane-strided; each lane keeps GLX_BCF_FILL_UNROLL independent loads in flight (the fill is bound by
+            // memory latency, not by instructions: one dependent round trip per piece part otherwise)
             const long long step = 4ll * n_lanes;
-            long long x0 = wa + 4ll * lane;
-            for (; x0 + step < we; x0 += 2 * step) {
-                const uint32_t u = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base));
-                const uint32_t v = bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 + step - base));
-                bcf_put_word<Addr>(buf, x0, u);
-                bcf_put_word<Addr>(buf, x0 + step, v);
+            for (long long xb = wa + 4ll * lane; xb < we; xb += GLX_BCF_FILL_UNROLL * step) {
+                uint32_t v[GLX_BCF_FILL_UNROLL];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int u = 0; u < GLX_BCF_FILL_UNROLL; u++) {
+                    const long long x0 = xb + u * step;
+                    v[u] = x0 < we ? bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base)) : 0u;
+                }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int u = 0; u < GLX_BCF_FILL_UNROLL; u++) {
+                    const long long x0 = xb + u * step;
+                    if (x0 < we) bcf_put_word<Addr>(buf, x0, v[u]);
+                }
             }
-            if (x0 < we) bcf_put_word<Addr>(buf, x0, bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base)));
         }
     }
 }
