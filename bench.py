@@ -245,6 +245,9 @@ def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3, wire=False
             rs.submit(b)
     rs.drain()
     st0 = rs.stats()
+    debug = bool(os.environ.get("GLX_BENCH_DEBUG"))
+    if debug:
+        rs.trace(True)
     t = time.time()
     marks = []
     for _ in range(passes):
@@ -253,9 +256,12 @@ def stream_pass(glnexus_b200, device, mode, batches, passes, depth=3, wire=False
             marks.append(time.time() - t)
     rs.drain()
     dt = time.time() - t
-    if os.environ.get("GLX_BENCH_DEBUG"):
+    if debug:
         print(f"[rank {os.environ.get('RANK', '0')}] {mode} wire={wire}: sites per batch {[b.n_sites for b in batches]}, submit returns at (ms) "
               f"{[round(m * 1e3, 1) for m in marks]}, drained at {dt * 1e3:.1f} ms", file=sys.stderr)
+        for i, r in enumerate(rs.trace_rows()):
+            print(f"[rank {os.environ.get('RANK', '0')}]   batch {i}: device upload {r[0]:.2f}-{r[1]:.2f}, kernels done {r[2]:.2f}, encoder done {r[3]:.2f}, download done {r[4]:.2f}"
+                  f" | host submit {r[5]:.2f}-{r[6]:.2f}, download queued {r[7]:.2f}", file=sys.stderr)
     st = {k: v - st0[k] for k, v in rs.stats().items()}
     rs.close()
     return dt, st

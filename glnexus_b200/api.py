@@ -133,6 +133,10 @@ def lib():
     L.glxh_stream_drain.restype = C.c_int
     L.glxh_stream_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.glxh_stream_stats.restype = None
+    L.glxh_stream_trace.argtypes = [vp, C.c_int]
+    L.glxh_stream_trace.restype = None
+    L.glxh_stream_trace_rows.argtypes = [vp, C.POINTER(C.c_float), C.c_uint32]
+    L.glxh_stream_trace_rows.restype = C.c_uint32
     L.glxh_stream_output.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.glxh_stream_output.restype = C.c_int
     L.glxh_stream_close.argtypes = [vp]
@@ -671,6 +675,17 @@ class RangeStream:
         st = (C.c_uint64 * 8)()
         lib().glxh_stream_stats(self.handle, st)
         return dict(zip(("batches", "batches_retired", "sites", "cells", "records", "h2d_bytes", "d2h_bytes", "raw_bcf_bytes"), [int(x) for x in st]))
+
+    def trace(self, on=True):
+        """start (or stop) the per-batch timeline; rows come from trace_rows() once batches have retired"""
+        lib().glxh_stream_trace(self.handle, 1 if on else 0)
+
+    def trace_rows(self):
+        """[(upload begins, upload done, kernels done, encoder done, download done | host: submit entered, returned, download queued)] ms"""
+        n = lib().glxh_stream_trace_rows(self.handle, None, 0)
+        buf = (C.c_float * (8 * max(1, n)))()
+        lib().glxh_stream_trace_rows(self.handle, buf, n)
+        return [tuple(round(float(buf[8 * i + k]), 3) for k in range(8)) for i in range(n)]
 
     def output(self):
         p, n = C.c_void_p(), C.c_uint64()

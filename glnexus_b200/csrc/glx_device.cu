@@ -1242,6 +1242,28 @@ int glx_stream_sync(glx_ctx* ctx, void* s) {
     CU(cudaStreamSynchronize(s ? (cudaStream_t)s : ctx->stream));
     return GLX_OK;
 }
+void* glx_mark(glx_ctx* ctx, void* s) {
+    if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    if (cudaEventRecord(e, s ? (cudaStream_t)s : ctx->stream) != cudaSuccess) {
+        cudaEventDestroy(e);
+        return nullptr;
+    }
+    return (void*)e;
+}
+float glx_mark_ms(glx_ctx* ctx, void* a, void* b) {
+    float ms = -1.f;
+    if (!ctx || !a || !b || cudaSetDevice(ctx->device) != cudaSuccess) return ms;
+    if (cudaEventSynchronize((cudaEvent_t)b) != cudaSuccess || cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) return -1.f;
+    return ms;
+}
+void glx_mark_free(glx_ctx* ctx, void* m) {
+    if (ctx && m) {
+        cudaSetDevice(ctx->device);
+        cudaEventDestroy((cudaEvent_t)m);
+    }
+}
 int glx_host_register(void* p, size_t bytes) { return (!p || !bytes || cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) ? GLX_OK : GLX_E_CUDA; }
 void glx_host_unregister(void* p) {
     if (p) cudaHostUnregister(p);

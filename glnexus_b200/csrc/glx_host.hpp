@@ -307,6 +307,7 @@ Status slice_batch(const PackedBatch& b, uint32_t site_lo, uint32_t site_hi, Pac
 // download of the previous). Output follows cfg.output_format like BCFFileSink::Open (src/service.cc:254-265): BCF = a
 // BGZF-compressed BCF2 file whose records are encoded and compressed on the device (N1), VCF = uncompressed pVCF text.
 // ---------------------------------------------------------------------------------------------
+#include <array>
 #include <functional>
 namespace glx {
 // ---------------------------------------------------------------------------------------------
@@ -340,6 +341,11 @@ public:
     void close();
     const StreamStats& stats() const { return stats_; }
     glx_ctx* ctx() const { return ctx_; }
+    // Measurement aid: with tracing on, every retired batch adds one row of times in ms since set_trace(true):
+    // device {upload begins, upload done, genotyping kernels done, encoder done, download done}, host {submit entered,
+    // submit returned, download queued}
+    void set_trace(bool on);
+    const std::vector<std::array<float, 8>>& trace() const { return trace_; }
 
 private:
     struct Slot;
@@ -353,6 +359,10 @@ private:
     uint64_t n_submitted_ = 0, n_retired_ = 0;
     StreamStats stats_;
     Status failed_;
+    bool tracing_ = false;
+    void* trace_base_ = nullptr;
+    double trace_t0_ = 0;
+    std::vector<std::array<float, 8>> trace_;
 };
 
 struct ServiceStats {

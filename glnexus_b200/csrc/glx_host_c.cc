@@ -558,6 +558,15 @@ int glxh_stream_output(const glxh_stream* h, const char** bytes, uint64_t* n_byt
 }
 
 void glxh_stream_close(glxh_stream* h) { delete h; }
+void glxh_stream_trace(glxh_stream* h, int on) {
+    if (h) h->rs.set_trace(on != 0);
+}
+uint32_t glxh_stream_trace_rows(const glxh_stream* h, float* rows, uint32_t cap) {
+    if (!h) return 0;
+    const auto& t = h->rs.trace();
+    for (uint32_t i = 0; i < t.size() && i < cap && rows; i++) memcpy(rows + 8 * i, t[i].data(), 8 * sizeof(float));
+    return (uint32_t)t.size();
+}
 
 int glxh_preset_text(const char* name, char** text) {
     glx::genotyper_config cfg;

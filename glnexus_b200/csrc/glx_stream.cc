@@ -41,7 +41,24 @@ struct RangeStream::Slot {
     // column output (mode COLUMNS): pinned arrays sized for the largest batch seen
     glx_out cols{};
     size_t cap_cells = 0, cap_sites = 0, cap_fld[GLX_MAX_FIELDS] = {};
+    void* mark[5] = {};  // tracing
+    float host_ms[3] = {};
 };
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void RangeStream::set_trace(bool on) {
+    tracing_ = on && ctx_;
+    trace_.clear();
+    if (trace_base_) glx_mark_free(ctx_, trace_base_);
+    trace_base_ = nullptr;
+    if (tracing_) {
+        glx_synchronize(ctx_);
+        trace_base_ = glx_mark(ctx_, nullptr);
+        glx_synchronize(ctx_);
+        trace_t0_ = now_ms();
+    }
+}
 
 RangeStream::RangeStream() = default;
 
@@ -80,8 +97,13 @@ void RangeStream::close() {
         if (sl.cols.site_flags) glx_pinned_free(sl.cols.site_flags);
         for (auto& f : sl.cols.fld)
             if (f) glx_pinned_free(f);
+        for (auto& m : sl.mark)
+            if (m) glx_mark_free(ctx_, m);
     }
     slots_.clear();
+    if (trace_base_) glx_mark_free(ctx_, trace_base_);
+    trace_base_ = nullptr;
+    tracing_ = false;
     glx_destroy(ctx_);
     ctx_ = nullptr;
 }
@@ -128,6 +150,10 @@ Status RangeStream::start_download(Slot& sl) {
     sl.n_records = glx_bcf_records(sl.dev);
     s = status_of_rc(glx_download_bcf_on(ctx_, sl.dev, sl.pinned, sl.pinned_cap, sl.stream, 0), ctx_);
     if (s.ok()) sl.state = 2;
+    if (tracing_) {
+        sl.mark[4] = glx_mark(ctx_, sl.stream);
+        sl.host_ms[2] = (float)(now_ms() - trace_t0_);
+    }
     return s;
 }
 
@@ -152,6 +178,16 @@ Status RangeStream::retire(Slot& sl) {
         }
         s = sink_(r);
     }
+    if (tracing_ && sl.mark[0]) {
+        std::array<float, 8> row{};
+        for (int k = 0; k < 5; k++) row[k] = sl.mark[k] ? glx_mark_ms(ctx_, trace_base_, sl.mark[k]) : -1.f;
+        for (int k = 0; k < 3; k++) row[5 + k] = sl.host_ms[k];
+        trace_.push_back(row);
+    }
+    for (auto& m : sl.mark) {
+        if (m) glx_mark_free(ctx_, m);
+        m = nullptr;
+    }
     if (s.ok() && failed_.ok()) {
         stats_.batches_retired++;
         stats_.d2h_bytes += mode_ == Mode::COLUMNS ? glx_out_bytes(sl.dev) : sl.n_out;
@@ -172,22 +208,31 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     if (failed_.bad()) return failed_;
     const size_t depth = slots_.size();
     Slot& sl = *slots_[n_submitted_ % depth];
+    const double t_enter = tracing_ ? now_ms() - trace_t0_ : 0;
     Status s = retire(sl);  // the batch submitted `depth` steps ago
     if (s.bad()) return s;
+    if (tracing_) {
+        sl.host_ms[0] = (float)t_enter;
+        sl.mark[0] = glx_mark(ctx_, sl.stream);
+    }
     sl.batch = b;
     sl.owned = std::move(owned);
     s = status_of_rc(wire ? glx_upload_wire_on(ctx_, &b->cfg, wire, &b->sites, sl.stream, 0, &sl.dev)
                           : glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev),
                      ctx_);
+    if (tracing_ && s.ok()) sl.mark[1] = glx_mark(ctx_, sl.stream);
     if (s.ok()) s = status_of_rc(glx_launch(ctx_, sl.dev, sl.stream), ctx_);
+    if (tracing_ && s.ok()) sl.mark[2] = glx_mark(ctx_, sl.stream);
     if (s.ok()) {
         if (mode_ == Mode::COLUMNS) {
             s = ensure_cols(sl, *b);
             if (s.ok()) s = status_of_rc(glx_download_on(ctx_, sl.dev, &sl.cols, sl.stream, 0), ctx_);
+            if (tracing_ && s.ok()) sl.mark[4] = glx_mark(ctx_, sl.stream);
         } else {
             const glx_bcf_meta& meta = build_bcf_meta(*b);
             s = status_of_rc(glx_bcf_attach(ctx_, sl.dev, &b->sites, &meta, &b->cfg, sl.stream), ctx_);
             if (s.ok()) s = status_of_rc(glx_encode_bcf_on(ctx_, sl.dev, mode_ == Mode::BGZF ? 1 : 0, sl.stream), ctx_);
+            if (tracing_ && s.ok()) sl.mark[3] = glx_mark(ctx_, sl.stream);
         }
     }
     if (s.bad()) {
@@ -215,6 +260,7 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
         s = start_download(prev);
         if (s.bad() && failed_.ok()) failed_ = s;
     }
+    if (tracing_) sl.host_ms[1] = (float)(now_ms() - trace_t0_);
     return s;
 }
 

@@ -311,6 +311,11 @@ int glx_narrow_finish(glx_ctx* ctx, glx_dev_batch* dev, glx_out16* out);
 void* glx_stream_create(glx_ctx* ctx);
 void glx_stream_destroy(glx_ctx* ctx, void* stream);
 int glx_stream_sync(glx_ctx* ctx, void* stream);
+/* Timing marks (cudaEvent_t): glx_mark records a new event on `stream`; glx_mark_ms waits for `b` and returns the device
+ * time from `a` to `b` in ms (negative on error); marks are freed with glx_mark_free. */
+void* glx_mark(glx_ctx* ctx, void* stream);
+float glx_mark_ms(glx_ctx* ctx, void* a, void* b);
+void glx_mark_free(glx_ctx* ctx, void* mark);
 int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
 void glx_host_unregister(void* p);
 /* ---- N1: BCF2 records (and BGZF blocks) encoded on the device. After glx_launch, on the same stream:

@@ -114,6 +114,11 @@ int glxh_stream_submit(glxh_stream* s, glxh_batch* b, char* err, size_t errlen);
 void glxh_stream_use_wire(glxh_stream* s, int on);
 int glxh_stream_drain(glxh_stream* s, char* err, size_t errlen);
 void glxh_stream_stats(const glxh_stream* s, uint64_t stats[8]);
+/* Measurement aid: glxh_stream_trace(s, 1) starts a timeline; every batch retired afterwards adds a row of 8 times in ms:
+ * device {upload begins, upload done, genotyping kernels done, encoder done, download done}, host {submit entered, submit
+ * returned, download queued}. glxh_stream_trace_rows copies up to `cap` rows and returns how many there are. */
+void glxh_stream_trace(glxh_stream* s, int on);
+uint32_t glxh_stream_trace_rows(const glxh_stream* s, float* rows, uint32_t cap);
 int glxh_stream_output(const glxh_stream* s, const char** bytes, uint64_t* n_bytes);
 void glxh_stream_close(glxh_stream* s);
 
