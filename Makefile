@@ -27,3 +27,12 @@ oracle/libglx_oracle.so: oracle/glx_oracle.cc oracle/glx_bcf_oracle.cc include/g
 
 clean:
 	rm -f $(CSRC)/*.o glnexus_b200/libglx.so oracle/libglx_oracle.so $(CSRC)/*.ptxas.log
+
+# A/B builds of the same sources with extra defines (ablations, experiments): make alt NAME=nopf DEFS=-DGLX_ABLATE_ROW_PREFETCH
+# -> build_alt/libglx_$(NAME).so, loaded with GLX_LIB_PATH=build_alt/libglx_$(NAME).so
+alt: $(HOST_OBJS)
+	mkdir -p build_alt
+	$(NVCC) $(NVCCFLAGS) $(DEFS) -c $(CSRC)/glx_device.cu -o build_alt/glx_device_$(NAME).o 2> build_alt/glx_device_$(NAME).ptxas.log
+	$(NVCC) $(NVCCFLAGS) $(DEFS) -c $(CSRC)/glx_bcf.cu -o build_alt/glx_bcf_$(NAME).o 2> build_alt/glx_bcf_$(NAME).ptxas.log
+	$(NVCC) -shared $(GENCODE) -o build_alt/libglx_$(NAME).so $(HOST_OBJS) build_alt/glx_device_$(NAME).o build_alt/glx_bcf_$(NAME).o -cudart static -lpthread
+	rm -f build_alt/*.o

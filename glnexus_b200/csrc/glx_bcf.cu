@@ -6,6 +6,12 @@
 #include <cstring>
 #include <vector>
 
+// Phase clock of the BGZF kernel (thread 0 of every block; a dozen clock reads and atomics per 64 KB block): where a block's
+// time goes, for profiles/ — glx_debug_bgzf_phases. [0, 10): the kernel's phases; [10, 16): parts of the gather (builds with
+// -DGLX_FILL_PROFILE).
+__device__ unsigned long long glx_bgzf_phase_cycles[16];
+#define GLX_FILL_PROFILE_HERE 1
+
 #include "glx_bgzf.cuh"
 #include "glx_dev_state.cuh"
 
@@ -136,9 +142,6 @@ __global__ void __launch_bounds__(GLX_BCF_SPAN_THREADS, 3) glx_bcf_span_raw_kern
     for (uint32_t i = n16 + threadIdx.x; i < n; i += blockDim.x) out[lo + i] = M.buf[i];  // tail of the stream's last span
 }
 
-// Phase clock of the BGZF kernel (thread 0 of every block; a dozen clock reads and atomics per 64 KB block): where a block's
-// time goes, for profiles/ — glx_debug_bgzf_phases.
-__device__ unsigned long long glx_bgzf_phase_cycles[16];
 #define GLX_PHASE(i)                                                                    \
     do {                                                                                \
         if (tid == 0) {                                                                 \
@@ -149,13 +152,6 @@ __device__ unsigned long long glx_bgzf_phase_cycles[16];
     } while (0)
 
 #define GLX_BGZF_THREADS 1024
-#define GLX_BGZF_OUT_PAD ((GLX_BGZF_OUT + 15u) & ~15u)
-struct BgzfSmem {
-    uint8_t in[(GLX_BGZF_IN_PAD + 15u) & ~15u];  // BcfPadded layout
-    uint8_t out[GLX_BGZF_OUT_PAD];
-    BgzfShared sh;
-    BcfSpanTab tab;
-};
 struct BgzfSampleSmem {
     uint8_t in[(GLX_BGZF_IN_PAD + 15u) & ~15u];
     BgzfShared sh;
@@ -189,13 +185,22 @@ __global__ void __launch_bounds__(320) glx_bgzf_table_kernel(const uint32_t* __r
     for (uint32_t i = threadIdx.x; i < sizeof(BgzfTable) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tab)[i] = reinterpret_cast<const uint32_t*>(&s_tab)[i];
 }
 
-// One CTA per span: gather the span, CRC-32, DEFLATE under the batch's code and BGZF framing in shared memory, one bulk store
-// into the block's slot.
-__global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_span_kernel(BcfEnc E, const uint32_t* __restrict__ span_site, const BgzfTable* __restrict__ gtab,
+// One CTA per span: gather the span into shared memory, CRC-32 and DEFLATE under the batch's code there, and write the codes
+// straight into the block's slot in global memory (interior words of a worker's bit range with plain stores, the boundary
+// words it shares with its neighbours with atomic ORs onto zeroed words), then the BGZF framing around them. Without an
+// output stage the CTA needs ~112 KB of shared memory and 512 threads x 64 registers, so two spans are resident per SM:
+// one's gather (waiting on HBM) and barriers overlap the other's tokenizer and emitter (ALU and shared memory).
+#define GLX_BGZF_SPAN_THREADS 512
+struct BgzfSpanSmem {
+    uint8_t in[(GLX_BGZF_IN_PAD + 15u) & ~15u];  // BcfPadded layout
+    BgzfShared sh;
+    BcfSpanTab tab;
+};
+__global__ void __launch_bounds__(GLX_BGZF_SPAN_THREADS, 2) glx_bgzf_span_kernel(BcfEnc E, const uint32_t* __restrict__ span_site, const BgzfTable* __restrict__ gtab,
                                                                          const uint32_t* __restrict__ crc_pw, uint8_t* __restrict__ slots,
                                                                          uint32_t* __restrict__ sizes) {
     extern __shared__ __align__(128) uint8_t s_raw[];
-    BgzfSmem& M = *reinterpret_cast<BgzfSmem*>(s_raw);
+    BgzfSpanSmem& M = *reinterpret_cast<BgzfSpanSmem*>(s_raw);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const unsigned long long total = E.rec_off[E.n_sites];
     const unsigned long long lo = (unsigned long long)blockIdx.x * GLX_BCF_SPAN;
@@ -205,23 +210,29 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_span_kernel(BcfE
     }
     const unsigned long long hi = min(total, lo + GLX_BCF_SPAN);
     const uint32_t n = (uint32_t)(hi - lo);
-    uint32_t* out_words = reinterpret_cast<uint32_t*>(M.out + GLX_BGZF_LEAD + 18);
+    uint8_t* const slot = slots + (size_t)blockIdx.x * GLX_BGZF_SLOT;
+    uint32_t* const out_words = reinterpret_cast<uint32_t*>(slot + GLX_BGZF_LEAD + 18);  // 32 bytes into the (aligned) slot
     long long t_phase = clock64();
-    for (uint32_t i = tid; i < GLX_BGZF_OUT_PAD / 4; i += nt) reinterpret_cast<uint32_t*>(M.out)[i] = 0;
     for (uint32_t i = tid; i < sizeof(BgzfTable) / 4; i += nt) reinterpret_cast<uint32_t*>(&M.sh.tab)[i] = reinterpret_cast<const uint32_t*>(gtab)[i];
     if (tid == 0) M.sh.n_in = n;
     bgzf_crc_setup(M.sh, tid, nt);
     bcf_fill_span<BcfPadded>(E, lo, hi, span_site[blockIdx.x], M.in, M.tab, tid, nt);  // ends with a barrier
     GLX_PHASE(0);
-    bgzf_put_header(M.sh, out_words, tid, nt);
     bgzf_tokenize<false, true>(M.sh, M.tab, M.in, n, crc_pw, tid, nt);
     __syncthreads();
     GLX_PHASE(4);
     if (tid == 0) bgzf_crc_finish(M.sh, crc_pw);
-    {  // exclusive scan of the 1024 bit counts (+ header bits): warp scans, then the 32 warp totals
+    {  // exclusive scan of the GLX_BGZF_WORKERS bit counts (+ header bits): K consecutive workers per thread, warp scans, warp totals
+        constexpr uint32_t K = GLX_BGZF_WORKERS / GLX_BGZF_SPAN_THREADS;
+        static_assert(K * GLX_BGZF_SPAN_THREADS == GLX_BGZF_WORKERS && GLX_BGZF_SPAN_THREADS / 32 <= 32, "scan shape");
         __shared__ uint32_t s_wsum[32];
-        const uint32_t mine = M.sh.wbits[tid];
-        uint32_t incl = mine;
+        uint32_t mine[K], sum = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++) {
+            mine[k] = M.sh.wbits[tid * K + k];
+            sum += mine[k];
+        }
+        uint32_t incl = sum;
         for (uint32_t d = 1; d < 32; d <<= 1) {
             const uint32_t a = __shfl_up_sync(0xffffffffu, incl, d);
             if ((tid & 31) >= d) incl += a;
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_span_kernel(BcfE
         if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
         __syncthreads();
         if (tid < 32) {
-            uint32_t v = s_wsum[tid];
+            uint32_t v = tid < GLX_BGZF_SPAN_THREADS / 32 ? s_wsum[tid] : 0u;
             for (uint32_t d = 1; d < 32; d <<= 1) {
                 const uint32_t a = __shfl_up_sync(0xffffffffu, v, d);
                 if (tid >= d) v += a;
@@ -237,31 +248,33 @@ __global__ void __launch_bounds__(GLX_BGZF_THREADS, 1) glx_bgzf_span_kernel(BcfE
             s_wsum[tid] = v;
         }
         __syncthreads();
-        const uint32_t base = (tid >> 5) ? s_wsum[(tid >> 5) - 1] : 0u;
-        M.sh.wbits[tid] = base + incl - mine + M.sh.tab.hdr_bits;
-        if (tid == GLX_BGZF_WORKERS - 1) M.sh.data_bits = base + incl + M.sh.tab.hdr_bits;
+        uint32_t acc = ((tid >> 5) ? s_wsum[(tid >> 5) - 1] : 0u) + incl - sum + M.sh.tab.hdr_bits;
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++) {
+            M.sh.wbits[tid * K + k] = acc;
+            acc += mine[k];
+        }
+        if (tid == GLX_BGZF_SPAN_THREADS - 1) M.sh.data_bits = acc;
+    }
+    __syncthreads();
+    {  // zero the words the codes (and the end-of-block code) will be OR-ed into
+        const uint32_t nz = ((M.sh.data_bits + 15u + 31u) >> 5) + 1u;
+        for (uint32_t i = tid; i < nz; i += nt) out_words[i] = 0u;
     }
     __syncthreads();
     GLX_PHASE(7);
+    bgzf_put_header(M.sh, out_words, tid, nt);
     bgzf_emit(M.sh, M.tab, M.in, n, out_words, tid, nt);
     __syncthreads();
     GLX_PHASE(8);
     if (tid == 0) bgzf_finish_deflate(M.sh, out_words);
     __syncthreads();
     if (M.sh.stored) {
-        bgzf_store_raw(M.sh, M.in, M.out, tid, nt);
+        bgzf_store_raw(M.sh, M.in, slot, tid, nt);
         __syncthreads();
     }
-    if (tid == 0) bgzf_frame(M.sh, M.out);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
     if (tid == 0) {
-        const uint32_t bytes = (GLX_BGZF_LEAD + M.sh.block_len + 15u) & ~15u;
-        const uint32_t src = (uint32_t)__cvta_generic_to_shared(M.out);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(slots + (size_t)blockIdx.x * GLX_BGZF_SLOT), "r"(src), "r"(bytes)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        bgzf_frame(M.sh, slot);
         sizes[blockIdx.x] = M.sh.block_len;
     }
     GLX_PHASE(9);
@@ -326,14 +339,15 @@ __global__ void __launch_bounds__(256) glx_bgzf_pack_kernel(const uint8_t* __res
 
 static int glx_bgzf_launch(glx_ctx* ctx, const BcfEnc& E, const uint32_t* span_site, GlxBcfState& B, uint32_t n_spans, cudaStream_t st) {
     if (!(ctx->func_attrs & 1)) {  // per device: a process may drive several
-        CU(cudaFuncSetAttribute(glx_bgzf_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSmem)));
+        CU(cudaFuncSetAttribute(glx_bgzf_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSpanSmem)));
+        CU(cudaFuncSetAttribute(glx_bgzf_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU(cudaFuncSetAttribute(glx_bgzf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSampleSmem)));
         ctx->func_attrs |= 1;
     }
     CU(cudaMemsetAsync(B.hist, 0, GLX_BGZF_HIST * 4, st));
     glx_bgzf_sample_kernel<<<std::min<uint32_t>(n_spans, GLX_BGZF_SAMPLES), GLX_BGZF_THREADS, sizeof(BgzfSampleSmem), st>>>(E, span_site, B.hist);
     glx_bgzf_table_kernel<<<1, 320, 0, st>>>(B.hist, B.table);
-    glx_bgzf_span_kernel<<<n_spans, GLX_BGZF_THREADS, sizeof(BgzfSmem), st>>>(E, span_site, B.table, ctx->crc_pw, B.stream, B.blk_sizes);
+    glx_bgzf_span_kernel<<<n_spans, GLX_BGZF_SPAN_THREADS, sizeof(BgzfSpanSmem), st>>>(E, span_site, B.table, ctx->crc_pw, B.stream, B.blk_sizes);
     glx_bgzf_offsets_kernel<<<1, 1024, 0, st>>>(B.blk_sizes, n_spans, B.blk_offsets, B.totals);
     glx_bgzf_pack_kernel<<<n_spans, 256, 0, st>>>(B.stream, B.blk_sizes, B.blk_offsets, B.packed);
     CU(cudaGetLastError());

@@ -545,7 +545,25 @@ struct BcfPadded {
 // each FORMAT block's key/descriptor bytes, each FORMAT block's data — with where its bytes come from. Built by the whole
 // block (one thread per piece, so the plan loads of all pieces are in flight together), then the span is filled word by
 // word: a thread finds its word's piece by binary search and converts the source values, 16 independent words per thread.
+// profiling builds (-DGLX_FILL_PROFILE, glx_bcf.cu): thread 0's cycles per part of the gather into glx_bgzf_phase_cycles[10..]
+#if defined(GLX_FILL_PROFILE) && defined(GLX_FILL_PROFILE_HERE) && defined(__CUDA_ARCH__)
+#define GLX_FILL_MARK(i)                                                                               \
+    do {                                                                                               \
+        if (tid == 0) {                                                                                \
+            const long long now_ = clock64();                                                          \
+            atomicAdd(&::glx_bgzf_phase_cycles[10 + (i)], (unsigned long long)(now_ - glx_fill_mark_t)); \
+            glx_fill_mark_t = now_;                                                                    \
+        }                                                                                              \
+    } while (0)
+#define GLX_FILL_MARK_INIT() long long glx_fill_mark_t = clock64()
+#else
+#define GLX_FILL_MARK(i) ((void)0)
+#define GLX_FILL_MARK_INIT() ((void)0)
+#endif
 #define GLX_BCF_FILL_UNROLL 4
+#ifndef GLX_BCF_ITEM_SHIFT
+#define GLX_BCF_ITEM_SHIFT 8  // log2 of the bytes of one fill item
+#endif
 #define GLX_BCF_TAB_MAX 256
 #define GLX_BCF_REC_MAX 24
 enum { BCF_PK_BYTES = 0, BCF_PK_GT = 1, BCF_PK_INT = 2, BCF_PK_RAW4 = 3, BCF_PK_TRIM = 4, BCF_PK_STR = 5 };
@@ -563,6 +581,7 @@ struct BcfSpanTab {
     unsigned long long foff[GLX_BCF_REC_MAX][GLX_MAX_FIELDS];
     uint16_t fcnt[GLX_BCF_REC_MAX][GLX_MAX_FIELDS];
     uint32_t n, n_rec, site0, site_next, complete;  // complete: the table holds every piece of the span (one round)
+    uint32_t next_item;                             // bcf_tab_fill: the next 1 KB item nobody has taken yet
     long long cov_lo, cov_hi;                       // span-relative byte range the table covers
 };
 
@@ -589,6 +608,7 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
                                               uint32_t nt) {
     const uint32_t F = E.n_fields, slots = 1 + 2 * (F + 2);  // pieces per record
     const uint32_t max_rec = GLX_BCF_TAB_MAX / slots < GLX_BCF_REC_MAX ? GLX_BCF_TAB_MAX / slots : GLX_BCF_REC_MAX;
+    GLX_FILL_MARK_INIT();
     // ---- stage: offsets, plans and field layouts of sites s_begin - 1 .. s_begin + max_rec (every load independent) ----
     for (uint32_t j = tid; j <= max_rec + 1; j += nt) {
         const long long s = (long long)s_begin - 1 + j;
@@ -610,10 +630,12 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
         T.foff[j][k] = s < E.n_sites ? E.fld_off[k][s] : 0ull;
     }
     GLX_BLOCK_SYNC();
+    GLX_FILL_MARK(0);
     if (tid == 0) {
         uint32_t nr = 0;
         while (nr < max_rec && s_begin + nr < E.n_sites && T.roff[1 + nr] < hi) nr++;
         T.n_rec = nr;
+        T.next_item = 0;
         T.site0 = s_begin;
         T.site_next = s_begin + nr;
         T.n = nr * slots;
@@ -623,6 +645,7 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
         T.start[nr * slots] = (int32_t)(long long)(end - lo);
     }
     GLX_BLOCK_SYNC();
+    GLX_FILL_MARK(1);
     const uint32_t N = E.n_samples;
     for (uint32_t idx = tid; idx < T.n; idx += nt) {
         const uint32_t j = idx / slots, p = idx - j * slots, s = s_begin + j;
@@ -688,6 +711,7 @@ __host__ __device__ inline void bcf_tab_build(const BcfEnc& E, BcfSpanTab& T, un
         T.fld[idx] = (uint8_t)fld;
     }
     GLX_BLOCK_SYNC();
+    GLX_FILL_MARK(2);
 }
 
 // piece holding span byte x (x inside the table's coverage): last piece with start <= x
@@ -793,15 +817,28 @@ __host__ __device__ __forceinline__ void bcf_put_word(uint8_t* buf, long long x0
 #endif
 }
 
-// Fill the covered bytes of the span from the table. The span is cut into 1 KB items; a warp takes an item, walks the pieces
-// that overlap it and converts their words lane by lane, two independent words per lane in flight — 32 warps on 32 items.
+// Fill the covered bytes of the span from the table. The span is cut into items of 2^GLX_BCF_ITEM_SHIFT bytes; a warp takes the next untaken item (items
+// cost up to 4x one another: 1 KB of 1-byte values reads 4 KB of int32 columns, 1 KB of GT reads 1 KB), walks the pieces that
+// overlap it and converts their words lane by lane, GLX_BCF_FILL_UNROLL independent words per lane in flight.
 template <class Addr>
-__host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, const BcfSpanTab& T, uint8_t* buf, uint32_t tid, uint32_t nt) {
+__host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, BcfSpanTab& T, uint8_t* buf, uint32_t tid, uint32_t nt) {
     if (T.cov_hi <= T.cov_lo) return;
-    const uint32_t n_lanes = nt < 32 ? nt : 32, lane = tid % n_lanes, warp = tid / n_lanes, n_warps = nt / n_lanes;
-    const long long it0 = T.cov_lo >> 10, it1 = (T.cov_hi + 1023) >> 10;
-    for (long long it = it0 + warp; it < it1; it += n_warps) {
-        const long long a_it = (it << 10) < T.cov_lo ? T.cov_lo : (it << 10), e_it = ((it + 1) << 10) > T.cov_hi ? T.cov_hi : ((it + 1) << 10);
+    const uint32_t n_lanes = nt < 32 ? nt : 32, lane = tid % n_lanes;
+    constexpr int IS = GLX_BCF_ITEM_SHIFT;
+    const long long it0 = T.cov_lo >> IS, it1 = (T.cov_hi + (1ll << IS) - 1) >> IS;
+    for (;;) {
+        long long it;
+#if defined(__CUDA_ARCH__)
+        {
+            uint32_t k = 0;
+            if (lane == 0) k = atomicAdd(&T.next_item, 1u);
+            it = it0 + (long long)__shfl_sync(0xffffffffu, k, 0);
+        }
+#else
+        it = it0 + (long long)T.next_item++;
+#endif
+        if (it >= it1) break;
+        const long long a_it = (it << IS) < T.cov_lo ? T.cov_lo : (it << IS), e_it = ((it + 1) << IS) > T.cov_hi ? T.cov_hi : ((it + 1) << IS);
         for (uint32_t p = bcf_tab_find(T, a_it); p < T.n && T.start[p] < e_it; p++) {
             const long long base = T.start[p];
             const long long ps = base < a_it ? a_it : base, pe = T.start[p + 1] > e_it ? e_it : T.start[p + 1];
@@ -857,13 +894,17 @@ template <class Addr>
 __host__ __device__ inline void bcf_fill_span(const BcfEnc& E, unsigned long long lo, unsigned long long hi, uint32_t s_first, uint8_t* buf, BcfSpanTab& T,
                                               uint32_t tid, uint32_t nt) {
     uint32_t s = s_first, rounds = 0;
+    GLX_FILL_MARK_INIT();
     for (;;) {
         bcf_tab_build(E, T, lo, hi, s, tid, nt);
+        GLX_FILL_MARK(3);
         bcf_tab_fill<Addr>(E, T, buf, tid, nt);
+        GLX_FILL_MARK(4);
         const uint32_t next = T.site_next;
         const bool more = next < E.n_sites && T.n_rec > 0 && T.roff[1 + T.n_rec] < hi;
         rounds++;
         GLX_BLOCK_SYNC();  // the table is rebuilt (or read by the caller) after everyone has finished with it
+        GLX_FILL_MARK(5);
         if (!more) break;
         s = next;
     }

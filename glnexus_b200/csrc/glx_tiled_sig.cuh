@@ -5,6 +5,7 @@
 // glx_cell_fast.cuh (same blobs, same classification, same patterns); configs whose signature has no instantiation
 // run the dynamic kernel there. Reference lines: see glx_cell_fast.cuh.
 #pragma once
+#include <type_traits>
 #include "glx_cell_fast.cuh"
 #include "glx_cell_variant.cuh"
 
@@ -210,6 +211,110 @@ __device__ __forceinline__ int4 ldg_blob(const int4* p) {
 #endif
 }
 
+// The lane's NEXT blob row, fetched ahead of need. A lane walks its sample's rows in order and, without this, waits a full
+// L2 / HBM round trip at every cursor step (the profile's top stall: profiles/r1_ncu_full.md). BlobPrefetch keeps one
+// 64-byte row per lane in flight: a TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> the lane's shared-memory slot,
+// completion counted on the lane's own mbarrier, issued when the current row is taken and consumed — usually many sites
+// later — with a shared-memory read. NoPrefetch is the plain form (host emulation, dynamic kernel).
+#ifndef GLX_ROW_PREFETCH
+#define GLX_ROW_PREFETCH 2  // 1: TMA bulk copies + per-lane mbarriers, 2: per-thread cp.async
+#endif
+struct NoPrefetch {
+    template <uint32_t W>
+    __host__ __device__ __forceinline__ bool take(uint32_t, int32_t (&)[W]) { return false; }
+    __host__ __device__ __forceinline__ void issue(const int32_t*, uint32_t, int) {}
+    __host__ __device__ __forceinline__ void drain() {}
+};
+#if defined(__CUDACC__)
+template <uint32_t W>
+struct BlobPrefetch {
+    static constexpr uint32_t NONE = 0xffffffffu;
+    uint32_t slot, bar;  // shared-space addresses: the lane's row slot (W words, 16-byte aligned) and its mbarrier
+    uint32_t row;        // row index (within the sample) in flight or landed in the slot, NONE if nothing is
+    uint32_t phase;
+    int qmax;            // largest qbeg of the tile: a row whose maxend exceeds it is the lane's last in this tile
+    __device__ __forceinline__ void init(void* slot_p, void* bar_p, int qmax_) {
+        slot = (uint32_t)__cvta_generic_to_shared(slot_p);
+        bar = (uint32_t)__cvta_generic_to_shared(bar_p);
+        row = NONE;
+        phase = 0;
+        qmax = qmax_;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "GLX_PF_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra GLX_PF_DONE;\n"
+            "bra GLX_PF_WAIT;\n"
+            "GLX_PF_DONE:\n"
+            "}" ::"r"(bar),
+            "r"(phase)
+            : "memory");
+        phase ^= 1u;
+    }
+    __device__ __forceinline__ bool take(uint32_t want, int32_t (&w)[W]) {
+        if (row == NONE) return false;
+        wait();
+        const bool hit = row == want;
+        row = NONE;
+        if (!hit) return false;
+#pragma unroll
+        for (uint32_t q = 0; q < W / 4; q++)
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * q]), "=r"(w[4 * q + 1]), "=r"(w[4 * q + 2]), "=r"(w[4 * q + 3]) : "r"(slot + 16u * q) : "memory");
+        return true;
+    }
+    // fetch row r (at src) unless the row just taken already reaches past the tile
+    __device__ __forceinline__ void issue(const int32_t* src, uint32_t r, int maxend) {
+        if (maxend > qmax) return;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(W * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot), "l"(src), "n"(W * 4), "r"(bar) : "memory");
+        row = r;
+    }
+    __device__ __forceinline__ void drain() {  // nothing may be in flight when the CTA's shared memory goes away
+        if (row != NONE) wait();
+        row = NONE;
+    }
+};
+// the same with per-thread cp.async (LDGSTS) copies: no mbarrier, no per-lane serialisation of the issue
+template <uint32_t W>
+struct BlobPrefetchLdgsts {
+    static constexpr uint32_t NONE = 0xffffffffu;
+    uint32_t slot, row;
+    int qmax;
+    __device__ __forceinline__ void init(void* slot_p, void*, int qmax_) {
+        slot = (uint32_t)__cvta_generic_to_shared(slot_p);
+        row = NONE;
+        qmax = qmax_;
+    }
+    __device__ __forceinline__ bool take(uint32_t want, int32_t (&w)[W]) {
+        if (row == NONE) return false;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        const bool hit = row == want;
+        row = NONE;
+        if (!hit) return false;
+#pragma unroll
+        for (uint32_t q = 0; q < W / 4; q++)
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * q]), "=r"(w[4 * q + 1]), "=r"(w[4 * q + 2]), "=r"(w[4 * q + 3]) : "r"(slot + 16u * q) : "memory");
+        return true;
+    }
+    __device__ __forceinline__ void issue(const int32_t* src, uint32_t r, int maxend) {
+        if (maxend > qmax) return;
+#pragma unroll
+        for (uint32_t q = 0; q < W / 4; q++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + 16u * q), "l"(src + 4 * q) : "memory");
+        row = r;
+    }
+    __device__ __forceinline__ void drain() {
+        if (row != NONE) asm volatile("cp.async.wait_all;" ::: "memory");
+        row = NONE;
+    }
+};
+#endif
+
 template <class Sig>
 struct TiledLane {
     uint64_t base;
@@ -220,18 +325,27 @@ struct TiledLane {
     int32_t rv[Sig::NRV_ARR];
 
     // load record c's blob straight into registers (four 128-bit loads for the preset signatures)
-    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs) {
+    template <class PF>
+    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs, PF& pf) {
         if (c < n) {
             const int4* b = reinterpret_cast<const int4*>(blobs + (base + c) * Sig::W);
             int32_t w[Sig::W];
+            if (!pf.take(c, w)) {
 #pragma unroll
-            for (uint32_t q = 0; q < Sig::W / 4; q++) {
-                const int4 v = ldg_blob(b + q);
-                w[4 * q] = v.x;
-                w[4 * q + 1] = v.y;
-                w[4 * q + 2] = v.z;
-                w[4 * q + 3] = v.w;
+                for (uint32_t q = 0; q < Sig::W / 4; q++) {
+                    const int4 v = ldg_blob(b + q);
+                    w[4 * q] = v.x;
+                    w[4 * q + 1] = v.y;
+                    w[4 * q + 2] = v.z;
+                    w[4 * q + 3] = v.w;
+                }
+#if defined(__CUDA_ARCH__) && defined(GLX_L2_AHEAD)
+                if (c + GLX_L2_AHEAD < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (Sig::W / 4) * GLX_L2_AHEAD));
+#endif
             }
+            // (skipping a prefetch is always allowed: the test on the row's last words only makes the copy into the slot wait
+            // until every shared-memory read of the row taken from that slot has returned)
+            if (c + 1 < n && (w[Sig::W / 4 + 3] ^ w[Sig::W / 2 + 3] ^ w[Sig::W - 1]) != (int32_t)0x5a17c3e9) pf.issue(blobs + (base + c + 1) * Sig::W, c + 1, w[2]);
             beg_c = w[0];
             end_c = w[1];
             maxend_c = w[2];
@@ -246,12 +360,21 @@ struct TiledLane {
             mrd = -1;
         }
     }
-    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t sample, uint32_t tile_cursor) {
+    __device__ __forceinline__ void load(const int32_t* __restrict__ blobs) {
+        NoPrefetch pf;
+        load(blobs, pf);
+    }
+    template <class PF>
+    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t sample, uint32_t tile_cursor, PF& pf) {
         base = R.ds_rec_off[sample];
         const uint64_t hi = R.ds_rec_off[sample + 1];
         n = (uint32_t)(hi - base);
         c = tile_cursor < n ? tile_cursor : n;  // tile cursor table (fill_tile_cursors)
-        load(blobs);
+        load(blobs, pf);
+    }
+    __device__ __forceinline__ void init(const DRecs& R, const int32_t* __restrict__ blobs, uint32_t sample, uint32_t tile_cursor) {
+        NoPrefetch pf;
+        init(R, blobs, sample, tile_cursor, pf);
     }
     __device__ __forceinline__ void idle() {
         base = 0;
@@ -262,25 +385,32 @@ struct TiledLane {
 #pragma unroll
         for (uint32_t j = 0; j < Sig::NRV_ARR; j++) rv[j] = 0;
     }
-    __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int qbeg, bool back) {
+    template <class PF>
+    __device__ __forceinline__ void seek(const int32_t* __restrict__ blobs, int qbeg, bool back, PF& pf) {
         if (back) {
             bool moved = false;
             while (c > 0 && blobs[(base + c - 1) * Sig::W + 2] > qbeg) {
                 c--;
                 moved = true;
             }
-            if (moved) load(blobs);
+            if (moved) load(blobs, pf);
         }
         while (c < n && maxend_c <= qbeg) {
             c++;
-            load(blobs);
+            load(blobs, pf);
         }
     }
     // same decision table as fast_classify, written without early exits (a handful of predicate ops instead of a
     // branch ladder that the warp would walk divergently)
     __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int sbeg, int send, int qbeg, int qend, bool slow_site, bool back,
                                             bool& called, int& rnc) {
-        seek(blobs, qbeg, back);
+        NoPrefetch pf;
+        return classify(cfg, blobs, sbeg, send, qbeg, qend, slow_site, back, called, rnc, pf);
+    }
+    template <class PF>
+    __device__ __forceinline__ int classify(const DCfg& cfg, const int32_t* __restrict__ blobs, int sbeg, int send, int qbeg, int qend, bool slow_site, bool back,
+                                            bool& called, int& rnc, PF& pf) {
+        seek(blobs, qbeg, back, pf);
         const bool none = beg_c >= qend;  // also true past the sample's last record (sentinel)
         const bool slow = slow_site | (!none & ((beg_n < qend) | ((bits & RB_SLOW) != 0)));
         const bool overl = (end_c > sbeg) & (beg_c < send);
@@ -420,12 +550,21 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS 
                                                                                uint2* __restrict__ worklist,
                                                                                uint32_t* __restrict__ n_work, uint32_t n_sample_blocks, uint32_t cta0) {
     static_assert(TS <= 64, "per-lane site masks are 64-bit");
-    __shared__ int4 s_pos[TS];       // beg, end, qbeg, qend
-    __shared__ uint32_t s_meta[TS];  // bits 0-7 n_allele, bit 8 general path only, bit 9 qbeg below the previous site's
-    __shared__ unsigned long long s_off[Sig::nf ? Sig::nf : 1][TS];
+    // per site of the tile, one record: {beg, end, qbeg, qend | meta | - | fld_off of the allele/genotype-numbered fields}; meta: bits 0-7
+    // n_allele, bit 8 general path only, bit 9 qbeg below the previous site's. The walk reads it through one running
+    // 32-bit shared address (explicit ld.shared: the compiler's uniform-datapath addressing recomputed the window base every site).
+    constexpr uint32_t SITE_W = (6u + 2u * (Sig::nf ? Sig::nf : 1) + 3u) & ~3u;  // words, a multiple of 16 bytes
+    __shared__ __align__(16) uint32_t s_site[TS][SITE_W];
     __shared__ uint32_t s_red[4][GLX_TILE_THREADS / 32];  // per-warp called/lost site masks (lo, hi words)
     __shared__ uint32_t s_nslow;  // cells this CTA handed to the worklist kernels (its worklist region is CTA-private)
     __shared__ int32_t s_stage[GLX_TILE_THREADS / 32][32 * GLX_STAGE_MAX];  // per-warp transposition buffer for narrow vectors
+#ifndef GLX_ABLATE_ROW_PREFETCH
+    __shared__ __align__(16) int32_t s_next[GLX_TILE_THREADS][Sig::W];  // per lane: its next blob row (BlobPrefetch)
+    __shared__ __align__(8) unsigned long long s_bar[GLX_ROW_PREFETCH == 1 ? GLX_TILE_THREADS : 1];
+    __shared__ int s_qmax;
+    if (threadIdx.x == 0) s_qmax = (int)0x80000000;
+    __syncthreads();
+#endif
 
     const uint32_t cta = blockIdx.x + cta0;  // launches cover chunks of the tile grid so that the worklist kernels of one chunk overlap the next
     const uint32_t sb = cta % n_sample_blocks, tile = cta / n_sample_blocks;
@@ -443,56 +582,79 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS 
     for (uint32_t i = tid; i < nsite; i += GLX_TILE_THREADS) {
         const uint32_t s = site0 + i;
         const int qb = S.qbeg[s];
-        s_pos[i] = make_int4(S.beg[s], S.end[s], qb, S.qend[s]);
-        s_meta[i] = (uint32_t)S.n_allele[s] | (S.monoallelic[s] ? 256u : 0u) | ((i > 0 && qb < S.qbeg[s - 1]) ? 512u : 0u);
+        *reinterpret_cast<int4*>(&s_site[i][0]) = make_int4(S.beg[s], S.end[s], qb, S.qend[s]);
+#ifndef GLX_ABLATE_ROW_PREFETCH
+        atomicMax(&s_qmax, qb);
+#endif
+        s_site[i][4] = (uint32_t)S.n_allele[s] | (S.monoallelic[s] ? 256u : 0u) | ((i > 0 && qb < S.qbeg[s - 1]) ? 512u : 0u);
 #pragma unroll
         for (uint32_t k = 0; k < Sig::nf; k++)
-            if (Sig::mode(k) != FM_VEC) s_off[k][i] = S.fld_off[k][s];
+            if (Sig::mode(k) != FM_VEC) *reinterpret_cast<unsigned long long*>(&s_site[i][6 + 2 * k]) = S.fld_off[k][s];
     }
     __syncthreads();
+    uint32_t site_a = (uint32_t)__cvta_generic_to_shared(&s_site[0][0]);
 
     TiledLane<Sig> L;
-    if (active) L.init(R, blobs, sample, tile_cursors[(size_t)tile * N + sample]);
+#ifndef GLX_ABLATE_ROW_PREFETCH
+#if GLX_ROW_PREFETCH == 1
+    BlobPrefetch<Sig::W> pf;
+    pf.init(&s_next[tid][0], &s_bar[tid], s_qmax);
+#else
+    BlobPrefetchLdgsts<Sig::W> pf;
+    pf.init(&s_next[tid][0], nullptr, s_qmax);
+#endif
+#else
+    NoPrefetch pf;
+#endif
+    if (active) L.init(R, blobs, sample, tile_cursors[(size_t)tile * N + sample], pf);
     else L.idle();
     // sites (bit i of the tile) where this lane called 0/0, resp. produced a "lost call" RNC; reduced once per tile
-    unsigned long long called_bits = 0, lost_bits = 0;
+    typedef typename std::conditional<(TS <= 32), uint32_t, unsigned long long>::type site_mask_t;
+    site_mask_t called_bits = 0, lost_bits = 0;
     char2* __restrict__ gt_p = reinterpret_cast<char2*>(O.gt) + ((size_t)site0 * N + sample);
     uchar2* __restrict__ rnc_p = reinterpret_cast<uchar2*>(O.rnc) + ((size_t)site0 * N + sample);
 
-    for (uint32_t i = 0; i < nsite; i++, gt_p += N, rnc_p += N) {
+    for (uint32_t i = 0; i < nsite; i++, gt_p += N, rnc_p += N, site_a += SITE_W * 4u) {
         const uint32_t s = site0 + i;
-        const int4 pos = s_pos[i];
-        const uint32_t meta = s_meta[i];
+        int4 pos;
+        uint32_t meta;
+        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pos.x), "=r"(pos.y), "=r"(pos.z), "=r"(pos.w) : "r"(site_a));
+        asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(meta) : "r"(site_a));
         int type = CT_MISSING, rnc = RNC_M;
         bool called = false;
-        if (active) type = L.classify(cfg, blobs, pos.x, pos.y, pos.z, pos.w, meta & 256u, meta & 512u, called, rnc);
+        if (active) type = L.classify(cfg, blobs, pos.x, pos.y, pos.z, pos.w, meta & 256u, meta & 512u, called, rnc, pf);
         const bool slow = active && type == CT_SLOW;
-        const uint32_t slow_mask = __ballot_sync(0xffffffffu, slow);
-        if (slow_mask) {
-            uint32_t wbase = 0;
-            const int leader = __ffs(slow_mask) - 1;
-            if ((int)lane == leader) wbase = atomicAdd(&s_nslow, (uint32_t)__popc(slow_mask));
-            wbase = __shfl_sync(0xffffffffu, wbase, leader);
-            if (slow)
-                my_work[wbase + __popc(slow_mask & ((1u << lane) - 1))] =
-                    make_uint2(s * N + sample, L.c | ((!(meta & 256u) && L.c < L.n && L.beg_c < pos.w && L.beg_n >= pos.w) ? GLX_WORK_SINGLE : 0u));
-        }
+        // worklist entry: each slow lane takes its own slot of the CTA's region (order within the region is immaterial)
+        if (slow)
+            my_work[atomicAdd(&s_nslow, 1u)] =
+                make_uint2(s * N + sample, L.c | ((!(meta & 256u) && L.c < L.n && L.beg_c < pos.w && L.beg_n >= pos.w) ? GLX_WORK_SINGLE : 0u));
         const bool done = active && !slow;
         if (done) {
-            called_bits |= (unsigned long long)called << i;
-            lost_bits |= (unsigned long long)(rnc == RNC_I) << i;
+            called_bits |= (site_mask_t)called << i;
+            lost_bits |= (site_mask_t)(rnc == RNC_I) << i;
             const signed char a = called ? 0 : -1;
             const unsigned char rc = (unsigned char)kRncChar[rnc];
             *gt_p = make_char2(a, a);
             *rnc_p = make_uchar2(rc, rc);
         }
-        L.emit(plan, O, done, type == CT_REF, s, N, sample, meta & 255u, [&](uint32_t k) { return s_off[k][i]; }, s_stage[tid >> 5], lane, nvalid);
+        L.emit(plan, O, done, type == CT_REF, s, N, sample, meta & 255u,
+               [&](uint32_t k) {
+                   unsigned long long off;
+                   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(off) : "r"(site_a + 24u + 8u * k));
+                   return off;
+               },
+               s_stage[tid >> 5], lane, nvalid);
     }
+    pf.drain();
     // ---- per-site reductions for the whole tile: allele 0 used / some call lost ----
     {
         const uint32_t w = tid >> 5;
-        const uint32_t c_lo = __reduce_or_sync(0xffffffffu, (uint32_t)called_bits), c_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(called_bits >> 32));
-        const uint32_t l_lo = __reduce_or_sync(0xffffffffu, (uint32_t)lost_bits), l_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(lost_bits >> 32));
+        const uint32_t c_lo = __reduce_or_sync(0xffffffffu, (uint32_t)called_bits), l_lo = __reduce_or_sync(0xffffffffu, (uint32_t)lost_bits);
+        uint32_t c_hi = 0, l_hi = 0;
+        if constexpr (TS > 32) {
+            c_hi = __reduce_or_sync(0xffffffffu, (uint32_t)((unsigned long long)called_bits >> 32));
+            l_hi = __reduce_or_sync(0xffffffffu, (uint32_t)((unsigned long long)lost_bits >> 32));
+        }
         if (lane == 0) {
             s_red[0][w] = c_lo;
             s_red[1][w] = c_hi;

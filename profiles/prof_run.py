@@ -38,8 +38,12 @@ def main():
             cyc = ctx.bgzf_phase_cycles()
             names = ["gather", "segments", "setup", "crc parts", "tokenize", "crc tree", "codes+header", "count+scan", "emit", "finish+store"]
             tot = sum(cyc) or 1
+            tot = sum(cyc[:10]) or 1
             print("BGZF kernel, thread-0 cycles per phase:", ", ".join(f"{nm} {100 * c / tot:.1f}%" for nm, c in zip(names, cyc)),
                   f"; {tot / max(1, n * dev.bcf_length()[2]):.0f} cycles per block")
+            if any(cyc[10:]):  # -DGLX_FILL_PROFILE builds: parts of the gather (these also count the sampling kernel's blocks)
+                sub = ["stage loads", "serial part", "piece table", "(build total)", "fill", "closing barrier"]
+                print("  gather parts, % of the same total:", ", ".join(f"{nm} {100 * c / tot:.1f}%" for nm, c in zip(sub, cyc[10:])))
     print(f"{w}: {b.n_sites} sites x {b.n_samples} samples, {b.n_records} records, {dev.launch_count} kernels per launch")
     dev.close()
     ctx.close()
