@@ -278,7 +278,8 @@ def main():
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--segments", type=int, default=0, help="segments (range batches) of the streamed cohort; default 6 per GPU (weak scaling)")
-    ap.add_argument("--passes", type=int, default=1, help="times the rank's batches are streamed in the timed end-to-end region")
+    ap.add_argument("--passes", type=int, default=4, help="times the rank's batches are streamed in the timed end-to-end region (4 x 6 range batches per GPU: the "
+                    "pipeline's fill and drain, ~1 batch time, are then ~4 % of the run instead of ~15 %; a chromosome is hundreds of batches)")
     ap.add_argument("--e2e-modes", default="bgzf+wire,bgzf,bcf,columns")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -467,6 +468,14 @@ def main():
                     break
             except Exception:
                 pass
+        if traffic is None:  # other BASELINE shapes: the per-kernel DRAM bytes of profiles/r2_traffic_c345.json (same shape and sizes only)
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic_c345.json")))["dram_bytes"].get(args.workload, {})
+                if (n_samples, n_sites) == WORKLOADS[args.workload][1:3]:
+                    key = "tiled_sig" if dom_i == 1 else ("resolve" if dom_i == 0 else None)
+                    traffic = next((v for k, v in tr.items() if key and key in k), None)
+            except Exception:
+                pass
         n_b = max(1, head["batches"])
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -482,7 +491,7 @@ def main():
                         "value_excludes": "the two upload-side kernels (glx_prepare_inputs_kernel %.3f ms, glx_block_hints_kernel %.3f ms per upload) and three O(records)/O(sites) "
                                           "host loops of glx_upload_on; e2e includes them" % (up_ms[0], up_ms[1])},
             "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(head["h2d"] / n_b), "d2h_bytes_per_step": int(head["d2h"] / n_b),
-                    "steps": int(n_b), "cells": head["cells"], "seconds": head["s"],
+                    "steps": int(n_b), "cells": head["cells"], "seconds": head["s"], "passes_over_the_cohort": args.passes,
                     "mode": "glxh_stream_* (C++ range-batch driver, 3 batches in flight): per range batch H2D of the record store in its compact wire form (glx_wire) + sites "
                             "from pinned host memory, expansion + all genotyping kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF "
                             "blocks into pinned host memory; every rank streams its own contiguous site range of one cohort",

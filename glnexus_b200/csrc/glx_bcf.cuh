@@ -562,7 +562,7 @@ struct BcfPadded {
 #endif
 #define GLX_BCF_FILL_UNROLL 4
 #ifndef GLX_BCF_ITEM_SHIFT
-#define GLX_BCF_ITEM_SHIFT 8  // log2 of the bytes of one fill item
+#define GLX_BCF_ITEM_SHIFT 11  // log2 of the bytes of one fill item (measured on configs[1]: 256 B items 10 % slower than 1 KB — the per-item piece search — 2 KB 1.6 % faster)
 #endif
 #define GLX_BCF_TAB_MAX 256
 #define GLX_BCF_REC_MAX 24
