@@ -536,9 +536,11 @@ __host__ __device__ __forceinline__ uint32_t bcf_conv(int32_t v, uint32_t width)
 // (BGZF stage: its workers walk 64-byte chunks, and a 68-byte stride spreads them over the shared-memory banks)
 struct BcfLinear {
     static __host__ __device__ __forceinline__ size_t phys(unsigned long long i) { return (size_t)i; }
+    static __host__ __device__ __forceinline__ uint32_t phys32(uint32_t i) { return i; }
 };
 struct BcfPadded {
     static __host__ __device__ __forceinline__ size_t phys(unsigned long long i) { return (size_t)(i + ((i >> 6) << 2)); }
+    static __host__ __device__ __forceinline__ uint32_t phys32(uint32_t i) { return i + ((i >> 6) << 2); }
 };
 
 // The span's piece table (shared memory): every run of bytes of the records overlapping the span — header + shared part,
@@ -759,7 +761,7 @@ __host__ __device__ inline uint8_t bcf_piece_byte(const BcfEnc& E, const BcfSpan
 }
 
 // byte `off` of a plainly typed piece (INT / RAW4 / GT / BYTES), no divisions: w is 1, 2 or 4
-__host__ __device__ __forceinline__ uint32_t bcf_fast_byte(const void* src, uint32_t kind, uint32_t w, uint32_t km, unsigned long long off) {
+__host__ __device__ __forceinline__ uint32_t bcf_fast_byte(const void* src, uint32_t kind, uint32_t w, uint32_t km, uint32_t off) {
     if (kind == BCF_PK_BYTES) return static_cast<const uint8_t*>(src)[off];
     if (kind == BCF_PK_GT) {
         const int a = static_cast<const int8_t*>(src)[off];
@@ -769,7 +771,7 @@ __host__ __device__ __forceinline__ uint32_t bcf_fast_byte(const void* src, uint
     return (bcf_conv(static_cast<const int32_t*>(src)[off >> sh], w) >> (8 * (uint32_t)(off & (w - 1)))) & 0xffu;
 }
 // One aligned 4-byte word of the span taken wholly from a plainly typed piece: byte offset `off` of the piece's data.
-__host__ __device__ __forceinline__ uint32_t bcf_piece_word(const void* src, uint32_t kind, uint32_t w, uint32_t km, unsigned long long off) {
+__host__ __device__ __forceinline__ uint32_t bcf_piece_word(const void* src, uint32_t kind, uint32_t w, uint32_t km, uint32_t off) {
     if (kind == BCF_PK_INT && w == 1) {
         const int32_t* v = static_cast<const int32_t*>(src) + off;
         int32_t a, b, c, d;
@@ -809,11 +811,11 @@ __host__ __device__ __forceinline__ uint32_t bcf_piece_word(const void* src, uin
     return c[0] | c[1] << 8 | c[2] << 16 | (uint32_t)c[3] << 24;
 }
 template <class Addr>
-__host__ __device__ __forceinline__ void bcf_put_word(uint8_t* buf, long long x0, uint32_t word) {  // both layouts keep an aligned word contiguous
+__host__ __device__ __forceinline__ void bcf_put_word(uint8_t* buf, uint32_t x0, uint32_t word) {  // both layouts keep an aligned word contiguous
 #if defined(__CUDA_ARCH__)
-    *reinterpret_cast<uint32_t*>(buf + Addr::phys((unsigned long long)x0)) = word;
+    *reinterpret_cast<uint32_t*>(buf + Addr::phys32(x0)) = word;
 #else
-    memcpy(buf + Addr::phys((unsigned long long)x0), &word, 4);  // the host build also runs odd span sizes
+    memcpy(buf + Addr::phys32(x0), &word, 4);  // the host build also runs odd span sizes
 #endif
 }
 
@@ -825,63 +827,65 @@ __host__ __device__ inline void bcf_tab_fill(const BcfEnc& E, BcfSpanTab& T, uin
     if (T.cov_hi <= T.cov_lo) return;
     const uint32_t n_lanes = nt < 32 ? nt : 32, lane = tid % n_lanes;
     constexpr int IS = GLX_BCF_ITEM_SHIFT;
-    const long long it0 = T.cov_lo >> IS, it1 = (T.cov_hi + (1ll << IS) - 1) >> IS;
+    // span-relative positions fit 32 bits (the span is 64 KB; a piece may begin up to its own length before the span)
+    const int32_t cov_lo = (int32_t)T.cov_lo, cov_hi = (int32_t)T.cov_hi;
+    const int32_t it0 = cov_lo >> IS, it1 = (cov_hi + (1 << IS) - 1) >> IS;
     for (;;) {
-        long long it;
+        int32_t it;
 #if defined(__CUDA_ARCH__)
         {
             uint32_t k = 0;
             if (lane == 0) k = atomicAdd(&T.next_item, 1u);
-            it = it0 + (long long)__shfl_sync(0xffffffffu, k, 0);
+            it = it0 + (int32_t)__shfl_sync(0xffffffffu, k, 0);
         }
 #else
-        it = it0 + (long long)T.next_item++;
+        it = it0 + (int32_t)T.next_item++;
 #endif
         if (it >= it1) break;
-        const long long a_it = (it << IS) < T.cov_lo ? T.cov_lo : (it << IS), e_it = ((it + 1) << IS) > T.cov_hi ? T.cov_hi : ((it + 1) << IS);
+        const int32_t a_it = (it << IS) < cov_lo ? cov_lo : (it << IS), e_it = ((it + 1) << IS) > cov_hi ? cov_hi : ((it + 1) << IS);
         for (uint32_t p = bcf_tab_find(T, a_it); p < T.n && T.start[p] < e_it; p++) {
-            const long long base = T.start[p];
-            const long long ps = base < a_it ? a_it : base, pe = T.start[p + 1] > e_it ? e_it : T.start[p + 1];
+            const int32_t base = T.start[p];
+            const int32_t ps = base < a_it ? a_it : base, pe = T.start[p + 1] > e_it ? e_it : T.start[p + 1];
             if (pe <= ps) continue;
             const uint32_t info = T.info[p], kind = info & 15u, w = info >> 4 & 15u, km = T.km[p];
             const void* src = T.src[p];
             if (kind == BCF_PK_TRIM || kind == BCF_PK_STR) {  // rewritten vectors and strings: byte by byte
-                for (long long x = ps + lane; x < pe; x += n_lanes) buf[Addr::phys((unsigned long long)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(x - base));
+                for (int32_t x = ps + (int32_t)lane; x < pe; x += (int32_t)n_lanes) buf[Addr::phys32((uint32_t)x)] = bcf_piece_byte(E, T, p, (unsigned long long)(uint32_t)(x - base));
                 continue;
             }
-            long long wa = (ps + 3) & ~3ll, we = pe & ~3ll;
+            int32_t wa = (ps + 3) & ~3, we = pe & ~3;
             if (wa > we) wa = we = pe;
             // the up to 3 + 3 bytes around the aligned words, in one go
             {
-                const long long nh = wa - ps, ntl = pe - we;
-                if ((long long)lane < nh + ntl) {
-                    const long long x = (long long)lane < nh ? ps + lane : we + (lane - nh);
-                    buf[Addr::phys((unsigned long long)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (unsigned long long)(x - base));
+                const int32_t nh = wa - ps, ntl = pe - we;
+                if ((int32_t)lane < nh + ntl) {
+                    const int32_t x = (int32_t)lane < nh ? ps + (int32_t)lane : we + ((int32_t)lane - nh);
+                    buf[Addr::phys32((uint32_t)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (uint32_t)(x - base));
                 }
                 if (n_lanes < 6)  // the host build's single lane
-                    for (long long i = n_lanes; i < nh + ntl; i++) {
-                        const long long x = i < nh ? ps + i : we + (i - nh);
-                        if (lane == 0) buf[Addr::phys((unsigned long long)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (unsigned long long)(x - base));
+                    for (int32_t i = (int32_t)n_lanes; i < nh + ntl; i++) {
+                        const int32_t x = i < nh ? ps + i : we + (i - nh);
+                        if (lane == 0) buf[Addr::phys32((uint32_t)x)] = (uint8_t)bcf_fast_byte(src, kind, w, km, (uint32_t)(x - base));
                     }
             }
             // aligned words, lane-strided; each lane keeps GLX_BCF_FILL_UNROLL independent loads in flight (the fill is bound by
             // memory latency, not by instructions: one dependent round trip per piece part otherwise)
-            const long long step = 4ll * n_lanes;
-            for (long long xb = wa + 4ll * lane; xb < we; xb += GLX_BCF_FILL_UNROLL * step) {
+            const int32_t step = 4 * (int32_t)n_lanes;
+            for (int32_t xb = wa + 4 * (int32_t)lane; xb < we; xb += GLX_BCF_FILL_UNROLL * step) {
                 uint32_t v[GLX_BCF_FILL_UNROLL];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
                 for (int u = 0; u < GLX_BCF_FILL_UNROLL; u++) {
-                    const long long x0 = xb + u * step;
-                    v[u] = x0 < we ? bcf_piece_word(src, kind, w, km, (unsigned long long)(x0 - base)) : 0u;
+                    const int32_t x0 = xb + u * step;
+                    v[u] = x0 < we ? bcf_piece_word(src, kind, w, km, (uint32_t)(x0 - base)) : 0u;
                 }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
                 for (int u = 0; u < GLX_BCF_FILL_UNROLL; u++) {
-                    const long long x0 = xb + u * step;
-                    if (x0 < we) bcf_put_word<Addr>(buf, x0, v[u]);
+                    const int32_t x0 = xb + u * step;
+                    if (x0 < we) bcf_put_word<Addr>(buf, (uint32_t)x0, v[u]);
                 }
             }
         }

@@ -242,39 +242,6 @@ __host__ __device__ __forceinline__ uint32_t bgzf_low32(uint32_t m) {  // index 
     return (uint32_t)__builtin_ffs((int)m) - 1;
 #endif
 }
-// the recorded tokens of worker w, in order: emit(is_match, literal byte | match length, distance). The start mask is walked
-// as two 32-bit halves, one token behind (a token ends where the next one starts).
-template <class F>
-__host__ __device__ inline void bgzf_replay(const BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t w, F&& emit) {
-    const uint32_t c0 = w * GLX_BGZF_CHUNK;
-    if (c0 >= n) return;
-    const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
-    const unsigned long long t = sh.tok[w], useD = sh.useD[w];
-    BgzfChunkCtx C;
-    if (useD) bgzf_chunk_ctx(T, c0, L, C);
-    const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));
-    uint32_t prev = 0;  // bit 0 of tok is always set: the chunk's first token starts at 0
-    auto token = [&](uint32_t p, uint32_t q) {
-        if (q - p < 3) emit(false, (W[p >> 2] >> (8 * (p & 3))) & 0xffu, 0u);
-        else emit(true, q - p, (useD >> p & 1ull) ? bgzf_D_at(C, p) : 1u);
-    };
-    uint32_t m = (uint32_t)t & ~1u;
-    while (m) {
-        const uint32_t q = bgzf_low32(m);
-        m &= m - 1;
-        token(prev, q);
-        prev = q;
-    }
-    m = (uint32_t)(t >> 32);
-    while (m) {
-        const uint32_t q = 32 + bgzf_low32(m);
-        m &= m - 1;
-        token(prev, q);
-        prev = q;
-    }
-    token(prev, L);
-}
-
 // Worker w owns bytes [64w, 64w+64) of the span (in = the BcfPadded staging buffer). It finds, per byte, whether the byte
 // repeats the one before it (distance 1) and whether it repeats the byte at the structural distance D of its piece, as two
 // 64-bit masks (word-wise compares), then walks them greedily — a D-match of >= 4 bytes that is longer than the distance-1
@@ -653,16 +620,21 @@ __host__ __device__ inline void bgzf_put_header(const BgzfShared& sh, uint32_t* 
     const uint32_t nw = (sh.tab.hdr_bits + 31) >> 5;
     for (uint32_t i = tid; i < nw; i += nt) bgzf_or(&out_words[i], sh.tab.hdr_words[i]);
 }
-// each worker writes its codes at its bit offset: interior words are its own (plain stores), the two boundary words are shared
+// Each worker writes the codes of its recorded tokens at its bit offset: interior words are its own (plain stores), the two
+// boundary words are shared (ORs). A token starts at every set bit of the worker's start mask and ends where the next one
+// starts; a token of one byte is a literal. Literal-heavy chunks set the pace of their warp, so four literals out of one
+// aligned word go out as two double codes (<= 30 bits each).
 __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const BcfSpanTab& T, const uint8_t* in, uint32_t n, uint32_t* out_words, uint32_t tid, uint32_t nt) {
     for (uint32_t w = tid; w < GLX_BGZF_WORKERS; w += nt) {
-        if (w * GLX_BGZF_CHUNK >= n) continue;
+        const uint32_t c0 = w * GLX_BGZF_CHUNK;
+        if (c0 >= n) continue;
+        const uint32_t L = n - c0 < GLX_BGZF_CHUNK ? n - c0 : GLX_BGZF_CHUNK;
         const uint32_t pos = sh.wbits[w];
         uint32_t word = pos >> 5;
         unsigned long long acc = 0;
         uint32_t fill = pos & 31;  // the low `fill` bits of the first word belong to the previous worker
         bool first = true;
-        auto put = [&](uint32_t v, uint32_t nb) {
+        auto put = [&](uint32_t v, uint32_t nb) {  // nb <= 32
             acc |= (unsigned long long)v << fill;
             fill += nb;
             if (fill >= 32) {
@@ -674,21 +646,40 @@ __host__ __device__ inline void bgzf_emit(BgzfShared& sh, const BcfSpanTab& T, c
                 fill -= 32;
             }
         };
-        bgzf_replay(sh, T, in, n, w, [&](bool match, uint32_t v, uint32_t d) {
-            if (!match) {
-                const uint32_t cl = sh.tab.lit_cl[v];
+        const unsigned long long useD = sh.useD[w];
+        BgzfChunkCtx C;
+        if (useD) bgzf_chunk_ctx(T, c0, L, C);
+        const uint32_t* W = reinterpret_cast<const uint32_t*>(in + BcfPadded::phys(c0));
+        unsigned long long rest = sh.tok[w];  // the start mask shifted down to the current token: bit 0 is set
+        uint32_t p = 0;
+        while (p < L) {
+            if (!(p & 3u) && p + 4 <= L && ((uint32_t)rest & 0xFu) == 0xFu && (p + 4 == L || ((uint32_t)rest >> 4 & 1u))) {
+                const uint32_t x = W[p >> 2];
+                const uint32_t a = sh.tab.lit_cl[x & 0xffu], b = sh.tab.lit_cl[x >> 8 & 0xffu], c = sh.tab.lit_cl[x >> 16 & 0xffu], d = sh.tab.lit_cl[x >> 24];
+                put((a & 0xffffu) | (b & 0xffffu) << (a >> 16), (a >> 16) + (b >> 16));
+                put((c & 0xffffu) | (d & 0xffffu) << (c >> 16), (c >> 16) + (d >> 16));
+                rest >>= 4;
+                p += 4;
+                continue;
+            }
+            const unsigned long long nx = rest >> 1;
+            const uint32_t len = nx ? 1u + bgzf_lowbit(nx) : L - p;  // start bits lie below L
+            if (len < 3) {
+                const uint32_t cl = sh.tab.lit_cl[(W[p >> 2] >> (8 * (p & 3))) & 0xffu];
                 put(cl & 0xffffu, cl >> 16);
             } else {
                 uint32_t s, eb, ev;
-                bgzf_len_sym(v, s, eb, ev);
+                bgzf_len_sym(len, s, eb, ev);
                 uint32_t cl = sh.tab.lit_cl[s];
                 put((cl & 0xffffu) | ev << (cl >> 16), (cl >> 16) + eb);  // code (<= 15 bits) and its extra bits (<= 5) in one go
-                bgzf_dist_sym(d, s, eb, ev);
+                bgzf_dist_sym((useD >> p & 1ull) ? bgzf_D_at(C, p) : 1u, s, eb, ev);
                 cl = sh.tab.dist_cl[s];
                 put(cl & 0xffffu, cl >> 16);
                 put(ev, eb);
             }
-        });
+            rest = len < 64 ? rest >> len : 0ull;
+            p += len;
+        }
         if (fill) bgzf_or(&out_words[word], (uint32_t)acc);
     }
 }
