@@ -470,8 +470,8 @@ int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* d, const glx_sites* sites, const
     B.span_site = wa.take<uint32_t>(n_spans_b);
     B.hist = wa.take<uint32_t>(GLX_BGZF_HIST);
     B.table = wa.take<BgzfTable>(1);
-    if (!ctx->crc_pw) {  // the 1,025 CRC powers, once per context
-        std::vector<uint32_t> pw(GLX_BGZF_WORKERS + 1);
+    if (!ctx->crc_pw) {  // the 1,025 CRC powers and their multiplication tables, once per context
+        std::vector<uint32_t> pw(GLX_BGZF_CRC_WORDS);
         bgzf_crc_powers(pw.data());
         CU(cudaMalloc((void**)&ctx->crc_pw, pw.size() * 4));
         CU(cudaMemcpy(ctx->crc_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));

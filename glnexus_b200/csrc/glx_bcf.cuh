@@ -562,7 +562,9 @@ struct BcfPadded {
 #define GLX_FILL_MARK(i) ((void)0)
 #define GLX_FILL_MARK_INIT() ((void)0)
 #endif
+#ifndef GLX_BCF_FILL_UNROLL
 #define GLX_BCF_FILL_UNROLL 4
+#endif
 #ifndef GLX_BCF_ITEM_SHIFT
 #define GLX_BCF_ITEM_SHIFT 11  // log2 of the bytes of one fill item (measured on configs[1]: 256 B items 10 % slower than 1 KB — the per-item piece search — 2 KB 1.6 % faster)
 #endif

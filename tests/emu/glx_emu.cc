@@ -397,8 +397,11 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
     std::vector<uint8_t> all;
     std::vector<uint8_t> in(GLX_BGZF_IN_PAD + 64);
     std::vector<uint32_t> stage_w((GLX_BGZF_OUT + 64) / 4);
-    std::vector<uint32_t> pw(GLX_BGZF_WORKERS + 1);
-    bgzf_crc_powers(pw.data());
+    static std::vector<uint32_t> pw;  // powers + multiplication tables, once per process
+    if (pw.empty()) {
+        pw.resize(GLX_BGZF_CRC_WORDS);
+        bgzf_crc_powers(pw.data());
+    }
     auto sh = std::make_unique<BgzfShared>();
     auto tab = std::make_unique<BcfSpanTab>();
     *n_stored = 0;
