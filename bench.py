@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--passes", type=int, default=4, help="times the rank's batches are streamed in the timed end-to-end region (4 x 6 range batches per GPU: the "
                     "pipeline's fill and drain, ~1 batch time, are then ~4 % of the run instead of ~15 %; a chromosome is hundreds of batches)")
     ap.add_argument("--e2e-modes", default="bgzf+wire,bgzf,bcf,columns")
+    ap.add_argument("--depth", type=int, default=3, help="range batches in flight in the streamed end-to-end driver")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -396,7 +397,7 @@ def main():
 
     def run_mode(m):
         base, _, opt = m.partition("+")
-        return stream_pass(glnexus_b200, local_rank, base, batches, args.passes, wire=opt == "wire")
+        return stream_pass(glnexus_b200, local_rank, base, batches, args.passes, depth=args.depth, wire=opt == "wire")
 
     e2e = {}
     solo = None
@@ -492,9 +493,9 @@ def main():
                                           "host loops of glx_upload_on; e2e includes them" % (up_ms[0], up_ms[1])},
             "e2e": {"value": e2e_v, "unit": "cells/s", "h2d_bytes_per_step": int(head["h2d"] / n_b), "d2h_bytes_per_step": int(head["d2h"] / n_b),
                     "steps": int(n_b), "cells": head["cells"], "seconds": head["s"], "passes_over_the_cohort": args.passes,
-                    "mode": "glxh_stream_* (C++ range-batch driver, 3 batches in flight): per range batch H2D of the record store in its compact wire form (glx_wire) + sites "
-                            "from pinned host memory, expansion + all genotyping kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF "
-                            "blocks into pinned host memory; every rank streams its own contiguous site range of one cohort",
+                    "mode": ("glxh_stream_* (C++ range-batch driver, %d batches in flight): per range batch H2D of the record store in its compact wire form (glx_wire) + sites "
+                             "from pinned host memory, expansion + all genotyping kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF "
+                             "blocks into pinned host memory; every rank streams its own contiguous site range of one cohort") % args.depth,
                     "wire_build_s_untimed": wire_s, "wire_bytes_per_record": wire_bytes / max(1, sum(b.n_records for b in batches)),
                     "d2h_bytes_per_cell": head["d2h"] / max(1, head["cells"]), "h2d_bytes_per_cell": head["h2d"] / max(1, head["cells"]),
                     "uncompressed_bcf_bytes_per_cell": head["raw"] / max(1, head["cells"]),

@@ -337,6 +337,11 @@ __global__ void __launch_bounds__(256) glx_bgzf_pack_kernel(const uint8_t* __res
     for (uint32_t i = head + nw * 4 + threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
 }
 
+__global__ void glx_publish_words_kernel(unsigned long long* __restrict__ host_words, const unsigned long long* __restrict__ src, uint32_t n) {
+    if (threadIdx.x < n) host_words[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
 static int glx_bgzf_launch(glx_ctx* ctx, const BcfEnc& E, const uint32_t* span_site, GlxBcfState& B, uint32_t n_spans, cudaStream_t st) {
     if (!(ctx->func_attrs & 1)) {  // per device: a process may drive several
         CU(cudaFuncSetAttribute(glx_bgzf_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSpanSmem)));
@@ -550,8 +555,11 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
         }
         CU(cudaGetLastError());
     }
-    // lengths -> the batch's pinned words {., raw stream bytes, BGZF bytes, BGZF blocks}
-    CU(cudaMemcpyAsync(d->host_err + 1, B.totals, 40, cudaMemcpyDeviceToHost, st));
+    // lengths -> the batch's pinned words {., raw stream bytes, BGZF bytes, BGZF blocks}, stored by a kernel (the words are mapped
+    // pinned memory): a copy-engine D2H here would queue the stream's next operation behind whatever download that engine is
+    // busy with — the stream stays on the compute engine from its first kernel to this event
+    glx_publish_words_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long*>(d->host_err + 1), B.totals, 5);
+    CU(cudaGetLastError());
     CU(cudaEventRecord(B.len_ev, st));
     return GLX_OK;
 }
@@ -564,6 +572,15 @@ int glx_bcf_length(glx_ctx* ctx, glx_dev_batch* d, uint64_t* n_bytes, uint64_t* 
     if (n_bytes) *n_bytes = d->bcf.mode == 0 ? d->host_err[1] : d->host_err[3];
     if (n_blocks) *n_blocks = d->bcf.mode == 0 ? 0u : (uint32_t)d->host_err[4];
     return GLX_OK;
+}
+
+int glx_bcf_ready(glx_ctx* ctx, glx_dev_batch* d) {
+    if (!ctx || !d || !d->bcf.attached || d->bcf.mode < 0) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaEventQuery(d->bcf.len_ev);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    return cuda_fail(ctx, e, "cudaEventQuery");
 }
 
 // records in the encoded batch (sites that survived allele trimming); valid after glx_bcf_length
@@ -580,6 +597,7 @@ int glx_download_bcf_on(glx_ctx* ctx, glx_dev_batch* d, void* dst, uint64_t capa
     }
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     d->dl_stream = st;
+    CU(cudaStreamWaitEvent(st, d->bcf.len_ev, 0));  // `stream` may be another one than the encoder's (a download-only stream)
     const uint8_t* src = d->bcf.mode == 0 ? d->bcf.stream : d->bcf.packed;
     if (n) CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(d->host_err, d->O.error, 8, cudaMemcpyDeviceToHost, st));

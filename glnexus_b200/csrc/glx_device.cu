@@ -1258,6 +1258,12 @@ float glx_mark_ms(glx_ctx* ctx, void* a, void* b) {
     if (cudaEventSynchronize((cudaEvent_t)b) != cudaSuccess || cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) return -1.f;
     return ms;
 }
+int glx_mark_wait(glx_ctx* ctx, void* m) {
+    if (!ctx || !m) return GLX_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize((cudaEvent_t)m));
+    return GLX_OK;
+}
 void glx_mark_free(glx_ctx* ctx, void* m) {
     if (ctx && m) {
         cudaSetDevice(ctx->device);

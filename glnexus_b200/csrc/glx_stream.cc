@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "glx_host.hpp"
@@ -41,7 +42,8 @@ struct RangeStream::Slot {
     // column output (mode COLUMNS): pinned arrays sized for the largest batch seen
     glx_out cols{};
     size_t cap_cells = 0, cap_sites = 0, cap_fld[GLX_MAX_FIELDS] = {};
-    void* mark[5] = {};  // tracing
+    void* dl_mark = nullptr;  // BCF modes: the download stream has finished this slot's copy
+    void* mark[5] = {};       // tracing
     float host_ms[3] = {};
 };
 
@@ -77,6 +79,11 @@ Status RangeStream::open(int device, Mode mode, int depth, Sink sink) {
         slots_.back()->stream = glx_stream_create(ctx_);
         if (!slots_.back()->stream) return Status::Failure("RangeStream: cudaStreamCreate");
     }
+    // Encoded results leave on a stream of their own. A slot's stream that ended on a D2H copy would hand its next operation
+    // (the next batch's upload) to the copy engine's queue behind whatever download is running there; kept apart, a slot's
+    // stream only ever uploads and computes and the download stream only ever downloads.
+    dl_stream_ = glx_stream_create(ctx_);
+    if (!dl_stream_) return Status::Failure("RangeStream: cudaStreamCreate");
     n_submitted_ = n_retired_ = 0;
     stats_ = StreamStats();
     failed_ = Status::OK();
@@ -88,6 +95,9 @@ void RangeStream::close() {
     for (auto& sp : slots_) {
         Slot& sl = *sp;
         if (sl.stream) glx_stream_sync(ctx_, sl.stream);
+        if (dl_stream_) glx_stream_sync(ctx_, dl_stream_);
+        if (sl.dl_mark) glx_mark_free(ctx_, sl.dl_mark);
+        sl.dl_mark = nullptr;
         if (sl.dev) glx_free_batch(ctx_, sl.dev);
         if (sl.stream) glx_stream_destroy(ctx_, sl.stream);
         if (sl.pinned) glx_pinned_free(sl.pinned);
@@ -101,6 +111,8 @@ void RangeStream::close() {
             if (m) glx_mark_free(ctx_, m);
     }
     slots_.clear();
+    if (dl_stream_) glx_stream_destroy(ctx_, dl_stream_);
+    dl_stream_ = nullptr;
     if (trace_base_) glx_mark_free(ctx_, trace_base_);
     trace_base_ = nullptr;
     tracing_ = false;
@@ -148,10 +160,14 @@ Status RangeStream::start_download(Slot& sl) {
     sl.n_raw = raw;
     sl.n_blocks = blocks;
     sl.n_records = glx_bcf_records(sl.dev);
-    s = status_of_rc(glx_download_bcf_on(ctx_, sl.dev, sl.pinned, sl.pinned_cap, sl.stream, 0), ctx_);
-    if (s.ok()) sl.state = 2;
+    s = status_of_rc(glx_download_bcf_on(ctx_, sl.dev, sl.pinned, sl.pinned_cap, dl_stream_, 0), ctx_);
+    if (s.ok()) {
+        sl.state = 2;
+        sl.dl_mark = glx_mark(ctx_, dl_stream_);
+        if (!sl.dl_mark) s = Status::Failure("RangeStream: cudaEventRecord");
+    }
     if (tracing_) {
-        sl.mark[4] = glx_mark(ctx_, sl.stream);
+        sl.mark[4] = glx_mark(ctx_, dl_stream_);
         sl.host_ms[2] = (float)(now_ms() - trace_t0_);
     }
     return s;
@@ -161,8 +177,14 @@ Status RangeStream::start_download(Slot& sl) {
 Status RangeStream::retire(Slot& sl) {
     if (sl.state == 0) return Status::OK();
     Status s = start_download(sl);
-    if (s.ok()) s = status_of_rc(glx_stream_sync(ctx_, sl.stream), ctx_);
-    else glx_stream_sync(ctx_, sl.stream);
+    if (s.ok() && sl.dl_mark) s = status_of_rc(glx_mark_wait(ctx_, sl.dl_mark), ctx_);  // (its stream's work ended before the copy began)
+    else if (s.ok()) s = status_of_rc(glx_stream_sync(ctx_, sl.stream), ctx_);
+    else {
+        glx_stream_sync(ctx_, sl.stream);
+        glx_stream_sync(ctx_, dl_stream_);
+    }
+    if (sl.dl_mark) glx_mark_free(ctx_, sl.dl_mark);
+    sl.dl_mark = nullptr;
     if (s.ok()) s = status_of_rc(glx_status(ctx_, sl.dev), ctx_);
     if (s.ok() && failed_.ok() && sink_) {
         Result r;
@@ -209,8 +231,11 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     const size_t depth = slots_.size();
     Slot& sl = *slots_[n_submitted_ % depth];
     const double t_enter = tracing_ ? now_ms() - trace_t0_ : 0;
+    static const bool dbg = getenv("GLX_STREAM_DEBUG") != nullptr;
+    double t_dbg[6] = {};
     Status s = retire(sl);  // the batch submitted `depth` steps ago
     if (s.bad()) return s;
+    if (dbg) t_dbg[0] = now_ms() - trace_t0_;
     if (tracing_) {
         sl.host_ms[0] = (float)t_enter;
         sl.mark[0] = glx_mark(ctx_, sl.stream);
@@ -220,8 +245,10 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     s = status_of_rc(wire ? glx_upload_wire_on(ctx_, &b->cfg, wire, &b->sites, sl.stream, 0, &sl.dev)
                           : glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev),
                      ctx_);
+    if (dbg) t_dbg[1] = now_ms() - trace_t0_;
     if (tracing_ && s.ok()) sl.mark[1] = glx_mark(ctx_, sl.stream);
     if (s.ok()) s = status_of_rc(glx_launch(ctx_, sl.dev, sl.stream), ctx_);
+    if (dbg) t_dbg[2] = now_ms() - trace_t0_;
     if (tracing_ && s.ok()) sl.mark[2] = glx_mark(ctx_, sl.stream);
     if (s.ok()) {
         if (mode_ == Mode::COLUMNS) {
@@ -235,6 +262,7 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
             if (tracing_ && s.ok()) sl.mark[3] = glx_mark(ctx_, sl.stream);
         }
     }
+    if (dbg) t_dbg[3] = now_ms() - trace_t0_;
     if (s.bad()) {
         if (sl.dev) {
             glx_stream_sync(ctx_, sl.stream);
@@ -253,14 +281,27 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     stats_.records += b->recs.n_records;
     stats_.h2d_bytes += glx_in_bytes(sl.dev);
     n_submitted_++;
-    // the batch before this one has had time to reach its size event: queue its download behind its encoder now, so that it
-    // overlaps this batch's upload and kernels
-    if (n_submitted_ >= 2) {
-        Slot& prev = *slots_[(n_submitted_ - 2) % depth];
-        s = start_download(prev);
-        if (s.bad() && failed_.ok()) failed_ = s;
+    // Queue the downloads of the batches whose encoders have finished, oldest first, without waiting for any: the host runs
+    // `depth` batches ahead of the device (it only ever blocks in retire(), on the oldest batch), so the device always has the
+    // next batches' uploads and kernels queued behind the encoder it is running.
+    if (mode_ != Mode::COLUMNS) {
+        const uint64_t oldest = n_submitted_ > depth ? n_submitted_ - depth : 0;
+        for (uint64_t b = oldest; b < n_submitted_; b++) {
+            Slot& o = *slots_[b % depth];
+            if (o.state != 1) continue;
+            const int ready = glx_bcf_ready(ctx_, o.dev);
+            if (ready <= 0) break;  // keep the downloads in submission order
+            s = start_download(o);
+            if (s.bad()) {
+                if (failed_.ok()) failed_ = s;
+                break;
+            }
+        }
     }
     if (tracing_) sl.host_ms[1] = (float)(now_ms() - trace_t0_);
+    if (dbg)
+        fprintf(stderr, "[stream] submit %llu: enter %.2f retired %.2f uploaded %.2f launched %.2f encoded %.2f returned %.2f\n", (unsigned long long)n_submitted_ - 1, t_enter,
+                t_dbg[0], t_dbg[1], t_dbg[2], t_dbg[3], now_ms() - trace_t0_);
     return s;
 }
 

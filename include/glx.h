@@ -315,6 +315,7 @@ int glx_stream_sync(glx_ctx* ctx, void* stream);
  * time from `a` to `b` in ms (negative on error); marks are freed with glx_mark_free. */
 void* glx_mark(glx_ctx* ctx, void* stream);
 float glx_mark_ms(glx_ctx* ctx, void* a, void* b);
+int glx_mark_wait(glx_ctx* ctx, void* mark); /* host waits until the stream has reached the mark */
 void glx_mark_free(glx_ctx* ctx, void* mark);
 int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
 void glx_host_unregister(void* p);
@@ -325,11 +326,14 @@ void glx_host_unregister(void* p);
  *                      (sites dropped after allele trimming have no record); mode 1: that stream cut into 65,280-byte BGZF
  *                      blocks (DEFLATE + CRC-32 on the device), contiguous, ready to append to the output file
  *   glx_bcf_length     waits until the encoder's sizes are known (an event early in the encode, not the whole stream)
- *   glx_download_bcf_on copies exactly the encoded bytes to `dst` (and the batch's status word, see glx_status)
+ *   glx_download_bcf_on copies exactly the encoded bytes to `dst` (and the batch's status word, see glx_status); its stream may
+ *                      be a different one (it waits for the encoder's end): a stream that only ever downloads keeps the
+ *                      next upload on the encoder's stream from queueing behind this copy
  * glx_bcf_bound = bytes `dst` must hold in the worst case. */
 int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* dev, const glx_sites* sites, const glx_bcf_meta* meta, const glx_config* cfg, void* stream);
 int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, int mode, void* stream);
 int glx_bcf_length(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* n_bytes, uint64_t* n_raw_bytes, uint32_t* n_blocks);
+int glx_bcf_ready(glx_ctx* ctx, glx_dev_batch* dev); /* 1: the encoder has finished and glx_bcf_length will not block; 0: not yet; < 0: error */
 int glx_download_bcf_on(glx_ctx* ctx, glx_dev_batch* dev, void* dst, uint64_t capacity, void* stream, int sync);
 int glx_bcf_record_offsets(glx_ctx* ctx, glx_dev_batch* dev, uint64_t* rec_off /* [n_sites + 1] */);
 int glx_debug_bgzf_phases(glx_ctx* ctx, uint64_t cycles[16]); /* profiling aid: cycles per phase of the BGZF kernel since the last call */
