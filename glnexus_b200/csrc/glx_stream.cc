@@ -231,11 +231,8 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     const size_t depth = slots_.size();
     Slot& sl = *slots_[n_submitted_ % depth];
     const double t_enter = tracing_ ? now_ms() - trace_t0_ : 0;
-    static const bool dbg = getenv("GLX_STREAM_DEBUG") != nullptr;
-    double t_dbg[6] = {};
     Status s = retire(sl);  // the batch submitted `depth` steps ago
     if (s.bad()) return s;
-    if (dbg) t_dbg[0] = now_ms() - trace_t0_;
     if (tracing_) {
         sl.host_ms[0] = (float)t_enter;
         sl.mark[0] = glx_mark(ctx_, sl.stream);
@@ -245,10 +242,8 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     s = status_of_rc(wire ? glx_upload_wire_on(ctx_, &b->cfg, wire, &b->sites, sl.stream, 0, &sl.dev)
                           : glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev),
                      ctx_);
-    if (dbg) t_dbg[1] = now_ms() - trace_t0_;
     if (tracing_ && s.ok()) sl.mark[1] = glx_mark(ctx_, sl.stream);
     if (s.ok()) s = status_of_rc(glx_launch(ctx_, sl.dev, sl.stream), ctx_);
-    if (dbg) t_dbg[2] = now_ms() - trace_t0_;
     if (tracing_ && s.ok()) sl.mark[2] = glx_mark(ctx_, sl.stream);
     if (s.ok()) {
         if (mode_ == Mode::COLUMNS) {
@@ -262,7 +257,6 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
             if (tracing_ && s.ok()) sl.mark[3] = glx_mark(ctx_, sl.stream);
         }
     }
-    if (dbg) t_dbg[3] = now_ms() - trace_t0_;
     if (s.bad()) {
         if (sl.dev) {
             glx_stream_sync(ctx_, sl.stream);
@@ -286,8 +280,8 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     // next batches' uploads and kernels queued behind the encoder it is running.
     if (mode_ != Mode::COLUMNS) {
         const uint64_t oldest = n_submitted_ > depth ? n_submitted_ - depth : 0;
-        for (uint64_t b = oldest; b < n_submitted_; b++) {
-            Slot& o = *slots_[b % depth];
+        for (uint64_t k = oldest; k < n_submitted_; k++) {
+            Slot& o = *slots_[k % depth];
             if (o.state != 1) continue;
             const int ready = glx_bcf_ready(ctx_, o.dev);
             if (ready <= 0) break;  // keep the downloads in submission order
@@ -299,9 +293,6 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
         }
     }
     if (tracing_) sl.host_ms[1] = (float)(now_ms() - trace_t0_);
-    if (dbg)
-        fprintf(stderr, "[stream] submit %llu: enter %.2f retired %.2f uploaded %.2f launched %.2f encoded %.2f returned %.2f\n", (unsigned long long)n_submitted_ - 1, t_enter,
-                t_dbg[0], t_dbg[1], t_dbg[2], t_dbg[3], now_ms() - trace_t0_);
     return s;
 }
 
