@@ -495,6 +495,8 @@ int glx_bcf_attach(glx_ctx* ctx, glx_dev_batch* d, const glx_sites* sites, const
     E.rnc = d->O.rnc;
     E.allele_used = d->O.allele_used;
     if (!B.len_ev) CU(cudaEventCreateWithFlags(&B.len_ev, cudaEventDisableTiming));
+    if (!B.meta_ev) CU(cudaEventCreateWithFlags(&B.meta_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(B.meta_ev, st));  // the encoder's stream waits for this: the attach may ride a copy-only stream
     if (glx_take_err_slot(ctx, d) != GLX_OK) return cuda_fail(ctx, cudaErrorMemoryAllocation, "pinned status word");
     B.attached = true;
     return GLX_OK;
@@ -508,6 +510,7 @@ int glx_encode_bcf_on(glx_ctx* ctx, glx_dev_batch* d, int mode, void* stream_) {
     const BcfEnc& E = B.E;
     const uint32_t S = d->n_sites, N = d->n_samples;
     B.mode = mode;
+    CU(cudaStreamWaitEvent(st, B.meta_ev, 0));
     const uint32_t n_spans = (uint32_t)((B.stream_bound + GLX_BCF_SPAN - 1) / GLX_BCF_SPAN);
     const size_t need = mode == 0 ? B.stream_bound + 256 : (size_t)n_spans * GLX_BGZF_SLOT + 256;
     if (!B.stream || B.stream_bytes < need) {

@@ -134,6 +134,7 @@ struct GlxBcfState {
     uint64_t stream_bound = 0, hdr_bound = 0;
     BcfEnc E;
     cudaEvent_t len_ev = nullptr;  // recorded when the lengths have landed in the batch's pinned words
+    cudaEvent_t meta_ev = nullptr; // recorded behind glx_bcf_attach's copies (which may be on a stream of their own)
     int mode = -1;                 // last glx_encode_bcf_on: 0 raw records, 1 BGZF blocks
 };
 
@@ -164,7 +165,6 @@ struct glx_dev_batch {
     uint32_t n_cols = 0;  // source columns of the record store
     uint32_t tile_sites = GLX_TILE_SITES;  // sites per tile of the tiled kernel in use
     bool fused_variant = false;  // the tiled kernel finishes its own lone-variant cells
-    std::vector<int32_t> tq_host;
     unsigned long long* host_err = nullptr;  // pinned copy of the device error word (asynchronous download)
     int err_slot = -1;                       // slot of the context's pinned pools, or -1: host_err / host_overflow are the batch's own allocation
     cudaStream_t last_stream = nullptr;      // stream of the last glx_launch (glx_check waits on it)

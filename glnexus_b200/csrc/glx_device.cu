@@ -116,6 +116,23 @@ __global__ void __launch_bounds__(GLX_RESOLVE_THREADS) glx_resolve_records_kerne
 // Once per upload: for every block of GLX_RESOLVE_THREADS records, the sample of its first record and that record's
 // t_hi (first tile whose tq >= its maxend); entry n_blocks closes the table with (last sample, n_tiles). The resolve
 // kernel's per-record searches then run inside [hint[b], hint[b + 1]] instead of over all samples / all tiles.
+// suffix minimum of the tiles' first query positions (one block; tiles are few: sites / 32..64)
+__global__ void __launch_bounds__(1024) glx_tile_q_kernel(const int32_t* __restrict__ qbeg, uint32_t n_tiles, uint32_t tile_sites, int32_t* __restrict__ tile_q) {
+    __shared__ int32_t s_min[1024];
+    const uint32_t t = threadIdx.x, chunk = (n_tiles + 1023u) / 1024u;
+    const uint32_t lo = min(n_tiles, t * chunk), hi = min(n_tiles, lo + chunk);
+    int32_t run = INT32_MAX;
+    for (uint32_t i = hi; i-- > lo;) {
+        run = min(run, qbeg[(size_t)i * tile_sites]);
+        tile_q[i] = run;
+    }
+    s_min[t] = run;
+    __syncthreads();
+    int32_t later = INT32_MAX;
+    for (uint32_t u = t + 1; u < 1024; u++) later = min(later, s_min[u]);
+    for (uint32_t i = lo; i < hi; i++) tile_q[i] = min(tile_q[i], later);
+}
+
 __global__ void __launch_bounds__(256) glx_block_hints_kernel(const DRecs R, uint32_t n_datasets, const int32_t* __restrict__ tile_q, uint32_t n_tiles,
                                                               uint2* __restrict__ hints, uint32_t n_blocks) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,6 +555,7 @@ void glx_free_batch(glx_ctx* ctx, glx_dev_batch* d) {
     }
 
     if (d->bcf.len_ev) cudaEventDestroy(d->bcf.len_ev);
+    if (d->bcf.meta_ev) cudaEventDestroy(d->bcf.meta_ev);
     if (ctx) {
         ctx->give(d->bcf.meta_base, d->bcf.meta_bytes);
         ctx->give(d->bcf.work_base, d->bcf.work_bytes);
@@ -899,15 +917,12 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         if (e != cudaSuccess) return bail(e, "cudaMalloc(record blobs)");
         d->tile_cursors = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part);
         d->tile_q = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part);
-        std::vector<int32_t>& tq = d->tq_host;
-        tq.assign(d->n_site_tiles, 0);
-        int32_t run = INT32_MAX;
-        for (uint32_t tile = d->n_site_tiles; tile-- > 0;) {  // suffix minimum: non-decreasing, never later than any later tile's start
-            run = std::min(run, sites->qbeg[(size_t)tile * d->tile_sites]);
-            tq[tile] = run;
-        }
-        e = cudaMemcpyAsync(d->tile_q, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice, up);
-        if (e != cudaSuccess) return bail(e, "upload(tile_q)");
+        // tile_q[t] = the smallest qbeg of any site from tile t on (non-decreasing, never later than a later tile's start), on the
+        // device: a host-built array would be a pageable copy in the middle of the batch's stream (the host would wait for the
+        // stream, and the copy would queue behind other batches' uploads)
+        glx_tile_q_kernel<<<1, 1024, 0, up>>>(d->S.qbeg, d->n_site_tiles, d->tile_sites, d->tile_q);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return bail(e, "glx_tile_q_kernel");
         d->block_hints = reinterpret_cast<uint2*>(reinterpret_cast<char*>(d->blobs) + blob_part + cur_part + tq_part);
         if (ctx->opt.profile_upload) {
             for (int i = 2; i < 4; i++) cudaEventCreate(&d->up_ev[i]);

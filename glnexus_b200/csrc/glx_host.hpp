@@ -353,7 +353,8 @@ private:
     Status start_download(Slot& sl);
     Status retire(Slot& sl);
     glx_ctx* ctx_ = nullptr;
-    void* dl_stream_ = nullptr;  // downloads of encoded results (modes BCF / BGZF)
+    void* dl_stream_ = nullptr;    // downloads of encoded results (modes BCF / BGZF)
+    void* meta_stream_ = nullptr;  // uploads of the encoder's site metadata
     Mode mode_ = Mode::COLUMNS;
     Sink sink_;
     std::vector<std::unique_ptr<Slot>> slots_;

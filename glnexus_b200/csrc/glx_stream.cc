@@ -83,7 +83,8 @@ Status RangeStream::open(int device, Mode mode, int depth, Sink sink) {
     // (the next batch's upload) to the copy engine's queue behind whatever download is running there; kept apart, a slot's
     // stream only ever uploads and computes and the download stream only ever downloads.
     dl_stream_ = glx_stream_create(ctx_);
-    if (!dl_stream_) return Status::Failure("RangeStream: cudaStreamCreate");
+    meta_stream_ = glx_stream_create(ctx_);
+    if (!dl_stream_ || !meta_stream_) return Status::Failure("RangeStream: cudaStreamCreate");
     n_submitted_ = n_retired_ = 0;
     stats_ = StreamStats();
     failed_ = Status::OK();
@@ -96,6 +97,7 @@ void RangeStream::close() {
         Slot& sl = *sp;
         if (sl.stream) glx_stream_sync(ctx_, sl.stream);
         if (dl_stream_) glx_stream_sync(ctx_, dl_stream_);
+        if (meta_stream_) glx_stream_sync(ctx_, meta_stream_);
         if (sl.dl_mark) glx_mark_free(ctx_, sl.dl_mark);
         sl.dl_mark = nullptr;
         if (sl.dev) glx_free_batch(ctx_, sl.dev);
@@ -112,7 +114,8 @@ void RangeStream::close() {
     }
     slots_.clear();
     if (dl_stream_) glx_stream_destroy(ctx_, dl_stream_);
-    dl_stream_ = nullptr;
+    if (meta_stream_) glx_stream_destroy(ctx_, meta_stream_);
+    dl_stream_ = meta_stream_ = nullptr;
     if (trace_base_) glx_mark_free(ctx_, trace_base_);
     trace_base_ = nullptr;
     tracing_ = false;
@@ -242,6 +245,13 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
     s = status_of_rc(wire ? glx_upload_wire_on(ctx_, &b->cfg, wire, &b->sites, sl.stream, 0, &sl.dev)
                           : glx_upload_on(ctx_, &b->cfg, &b->recs, &b->sites, sl.stream, 0, &sl.dev),
                      ctx_);
+    // The encoder's site metadata goes up right behind the batch, on a copy-only stream: on the slot's stream these small
+    // copies would wait for the upload's expansion kernels first and then sit in the copy engine's queue behind the NEXT
+    // batch's upload (the host is that far ahead), and the encoder with them.
+    if (s.ok() && mode_ != Mode::COLUMNS) {
+        const glx_bcf_meta& meta = build_bcf_meta(*b);
+        s = status_of_rc(glx_bcf_attach(ctx_, sl.dev, &b->sites, &meta, &b->cfg, meta_stream_), ctx_);
+    }
     if (tracing_ && s.ok()) sl.mark[1] = glx_mark(ctx_, sl.stream);
     if (s.ok()) s = status_of_rc(glx_launch(ctx_, sl.dev, sl.stream), ctx_);
     if (tracing_ && s.ok()) sl.mark[2] = glx_mark(ctx_, sl.stream);
@@ -251,15 +261,14 @@ Status RangeStream::submit(PackedBatch* b, std::unique_ptr<PackedBatch> owned, c
             if (s.ok()) s = status_of_rc(glx_download_on(ctx_, sl.dev, &sl.cols, sl.stream, 0), ctx_);
             if (tracing_ && s.ok()) sl.mark[4] = glx_mark(ctx_, sl.stream);
         } else {
-            const glx_bcf_meta& meta = build_bcf_meta(*b);
-            s = status_of_rc(glx_bcf_attach(ctx_, sl.dev, &b->sites, &meta, &b->cfg, sl.stream), ctx_);
-            if (s.ok()) s = status_of_rc(glx_encode_bcf_on(ctx_, sl.dev, mode_ == Mode::BGZF ? 1 : 0, sl.stream), ctx_);
+            s = status_of_rc(glx_encode_bcf_on(ctx_, sl.dev, mode_ == Mode::BGZF ? 1 : 0, sl.stream), ctx_);
             if (tracing_ && s.ok()) sl.mark[3] = glx_mark(ctx_, sl.stream);
         }
     }
     if (s.bad()) {
         if (sl.dev) {
             glx_stream_sync(ctx_, sl.stream);
+            glx_stream_sync(ctx_, meta_stream_);
             glx_free_batch(ctx_, sl.dev);
             sl.dev = nullptr;
         }

@@ -319,7 +319,10 @@ int glx_mark_wait(glx_ctx* ctx, void* mark); /* host waits until the stream has 
 void glx_mark_free(glx_ctx* ctx, void* mark);
 int glx_host_register(void* p, size_t bytes); /* cudaHostRegister: page-lock caller-owned arrays */
 void glx_host_unregister(void* p);
-/* ---- N1: BCF2 records (and BGZF blocks) encoded on the device. After glx_launch, on the same stream:
+/* ---- N1: BCF2 records (and BGZF blocks) encoded on the device. glx_bcf_attach any time after the upload, on any stream
+ * (the encoder waits for it): in a pipeline of several batches give it a stream that only ever copies host-to-device and
+ * call it right after the upload, so that its small copies sit in the copy engine's queue behind this batch's upload and not
+ * behind the next one's. glx_encode_bcf_on after glx_launch, on the stream of the launch:
  *   glx_bcf_attach     once per batch: uploads glx_bcf_meta (+ allele_af of `sites`, the glx_sites the batch was uploaded
  *                      with) and sizes the encoder's buffers; host arrays must stay valid until the stream reaches it
  *   glx_encode_bcf_on  mode 0: the batch's records as one uncompressed stream, exactly what bcf_write would hand to bgzf
