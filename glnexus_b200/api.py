@@ -480,6 +480,13 @@ class DeviceBatch:
         """mode 0: uncompressed record stream; mode 1: BGZF blocks."""
         self.ctx._check(lib().glx_encode_bcf_on(self.ctx.handle, self.handle, int(mode), C.c_void_p(stream or 0)))
 
+    def bcf_ready(self):
+        """True once the encoder has finished (bcf_length will not block)."""
+        rc = lib().glx_bcf_ready(self.ctx.handle, self.handle)
+        if rc < 0:
+            self.ctx._check(rc)
+        return rc == 1
+
     def bcf_length(self):
         """(encoded bytes, uncompressed stream bytes, BGZF blocks); waits for the encoder's size event."""
         n, r, b = C.c_uint64(), C.c_uint64(), C.c_uint32()
@@ -622,6 +629,24 @@ class Context:
         if not s:
             raise GlxError(-100, "glx_stream_create")
         return s
+
+    def mark(self, stream=None):
+        """a timing / ordering mark (CUDA event) recorded on the stream"""
+        lib().glx_mark.restype = C.c_void_p
+        m = lib().glx_mark(self.handle, C.c_void_p(stream or 0))
+        if not m:
+            raise GlxError(-100, "glx_mark")
+        return m
+
+    def mark_ms(self, a, b):
+        lib().glx_mark_ms.restype = C.c_float
+        return float(lib().glx_mark_ms(self.handle, C.c_void_p(a), C.c_void_p(b)))
+
+    def mark_wait(self, m):
+        self._check(lib().glx_mark_wait(self.handle, C.c_void_p(m)))
+
+    def mark_free(self, m):
+        lib().glx_mark_free(self.handle, C.c_void_p(m))
 
     def stream_destroy(self, s):
         lib().glx_stream_destroy(self.handle, C.c_void_p(s))

@@ -115,3 +115,41 @@ def test_gpu_bcf_file(ctx, tmp_path):
     got = bcfdec.bcf_file_to_vcf_text(whole)
     want = b.assemble_vcf(ref)
     assert [l for l in got.split("\n") if not l.startswith("##")] == [l for l in want.split("\n") if not l.startswith("##")]
+
+
+def test_gpu_bcf_three_streams(ctx):
+    """The pipelined call pattern of glx::RangeStream: attach on a copy-only stream, launch + encode on the batch's stream,
+    download on a download-only stream, sizes polled with glx_bcf_ready, completion through a mark — same bytes as the oracle."""
+    import glnexus_b200
+    b = synth_cases.make("c2", n_samples=257, n_sites=900, region_len=900)
+    b.pin()
+    ref = b.alloc_out()
+    oracle_lib.genotype_batch(b, ref, threads=8)
+    want, _ = oracle_lib.bcf_records(b, ref)
+    s_main, s_copy, s_dl = ctx.stream_create(), ctx.stream_create(), ctx.stream_create()
+    try:
+        for mode in (0, 1):
+            dev = ctx.upload_async(b, s_main)
+            dev.bcf_attach(b, stream=s_copy)
+            t0 = ctx.mark(s_main)
+            dev.launch(stream=s_main)
+            dev.encode_bcf(mode, stream=s_main)
+            while not dev.bcf_ready():
+                pass
+            n, raw_n, blocks = dev.bcf_length()
+            buf = glnexus_b200.PinnedBuffer(n + 64)
+            dev.download_bcf(buf, stream=s_dl, sync=False)
+            t1 = ctx.mark(s_dl)
+            ctx.mark_wait(t1)
+            assert ctx.mark_ms(t0, t1) > 0
+            ctx.mark_free(t0)
+            ctx.mark_free(t1)
+            dev.check()
+            got = buf.bytes(n)
+            assert raw_n == len(want)
+            assert (got if mode == 0 else bcfdec.bgzf_decompress(got)[0]) == want
+            buf.close()
+            dev.close()
+    finally:
+        for s_ in (s_main, s_copy, s_dl):
+            ctx.stream_destroy(s_)
