@@ -51,6 +51,11 @@ struct FastPlan {
     uint8_t vview, n_vc;
     int16_t vc[GLX_VIEW_COLS];        // cached columns
     int8_t vc_slot[GLX_MAX_COLS];     // column -> slot in vc, -1 not cached
+    // declined list of the fused tiled kernel (set per launch, null otherwise): worklist entries its biallelic closed form
+    // declined, as (region, index in the region); decl_n counts the entries offered, decl_cap bounds the list
+    uint2* decl_list;
+    uint32_t* decl_n;
+    uint32_t decl_cap;
 };
 
 inline FastPlan make_fast_plan(const DCfg& c) {

@@ -531,4 +531,317 @@ __device__ inline bool genotype_cell_variant(const DCfg& cfg, const FastPlan& pl
     return true;
 }
 
+// The same closed form for the commonest such cell by far: a biallelic site and a record REF, ALT[, <symbolic>] whose ALT is the
+// site's ALT and whose called alleles are REF / ALT, fields lifted (the record kept and spanning the site), nothing malformed.
+// Everything above that is a loop over alleles or genotypes is written out for A = 2, na = 2 or 3 and the identity allele map
+// (the symbolic allele unmapped), the field table is unrolled over the config's signature, PL / AD stay in registers (no
+// shared-memory columns). Any other shape — and every error — is DECLINED (false):
+// the caller hands the cell to genotype_cell_variant, which computes or reports it. As there, a declined cell may already
+// have had some vectors stored; every later stage rewrites the whole cell. Supported fields: PL2, and numeric kinds numbered
+// BASIC with one value or by ALLELES; a signature with anything else always declines.
+template <class Sig>
+__device__ inline bool genotype_cell_biallelic(const DCfg& cfg, const FastPlan& plan, const DRecs& R, const DSites& S, const DOut& O,
+                                               const int32_t* __restrict__ blobs, uint32_t s, uint32_t sample, uint64_t first) {
+    if (!plan.vview) return false;
+    // ---- loads: site rows, the record's view, the first two unification rows ----
+    const int4 sr0 = __ldg(S.site_rows + 2 * (size_t)s), sr1 = __ldg(S.site_rows + 2 * (size_t)s + 1);
+    const int4* bp = reinterpret_cast<const int4*>(blobs + first * Sig::W);
+    const int4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+    const int sbeg = sr0.x, send = sr0.y;
+    const uint32_t al0 = (uint32_t)sr1.y, u0 = (uint32_t)sr1.z, nU = (uint32_t)sr1.w - u0;
+    const size_t ur1 = nU > 1 ? u0 + 1 : u0;
+    const int4 ua0 = __ldg(S.unif_rows + 2 * (size_t)u0), ub0 = __ldg(S.unif_rows + 2 * (size_t)u0 + 1);
+    const int4 ua1 = __ldg(S.unif_rows + 2 * ur1), ub1 = __ldg(S.unif_rows + 2 * ur1 + 1);
+    if ((sr1.x & 256) || (sr1.x & 255) != 2) return false;
+    if (!((uint32_t)b0.w & RB_VIEW)) return false;
+    const int rbeg = b0.x, rend = b0.y;
+    const uint32_t gtw = (uint32_t)b1.x, a0 = (uint32_t)b1.z;
+    const uint32_t pk0 = (uint32_t)b1.w, pk1 = (uint32_t)b2.x, pk2 = (uint32_t)b2.y;
+    const uint8_t flags = (uint8_t)(pk0 & 0x7f);
+    const int na = (int)((pk0 >> 8) & 0xff);
+    if (!(na == 2 || (na == 3 && (flags & GLX_RF_SYMBOLIC_LAST))) || (flags & GLX_RF_NO_GT)) return false;
+    const int nGT = na == 2 ? 3 : 6;
+    const uint32_t afl1 = __ldg(R.al_flags + a0 + 1), aln1 = __ldg(R.al_len + a0 + 1), afl2 = __ldg(R.al_flags + a0 + na - 1);
+    const uint64_t apx1 = __ldg(R.al_prefix + a0 + 1);
+    const int32_t clen[GLX_VIEW_COLS] = {(int32_t)view_len_of((pk0 >> 16) & 0xFFF), (int32_t)view_len_of(((pk0 >> 28) | (pk1 << 4)) & 0xFFF),
+                                         (int32_t)view_len_of((pk1 >> 8) & 0xFFF),  (int32_t)view_len_of((pk1 >> 20) & 0xFFF),
+                                         (int32_t)view_len_of(pk2 & 0xFFF),         (int32_t)view_len_of((pk2 >> 12) & 0xFFF)};
+    const int32_t cval[GLX_VIEW_COLS] = {b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+    auto column = [&](int col, int& rv, int32_t& val) -> bool {
+        rv = -1;
+        val = 0;
+        if (col < 0) return true;
+        const int j = plan.vc_slot[col];
+        if (j < 0) return false;
+        rv = view_rv((uint32_t)pick(clen, j));
+        val = pick(cval, j);
+        return true;
+    };
+    int pl_rv, ad_rv;
+    int32_t pl_val, ad_val;
+    if (!column(cfg.col_pl, pl_rv, pl_val) || !column(cfg.col_allele_dp, ad_rv, ad_val)) return false;
+    if (pl_rv > 0 && pl_rv != nGT) return false;  // a PL of another length: for the general form to judge
+    const bool ad_zero = ad_rv == -1 || ad_rv == -3;
+    if (!ad_zero && ad_rv != na) return false;    // "allele depth vector of the wrong length": general form reports it
+    int32_t pl[6] = {0, 0, 0, 0, 0, 0}, ad[3] = {0, 0, 0};
+    {
+        const bool hp = pl_rv == nGT, ha = ad_rv == na;
+        const int32_t* psrc = hp ? R.pool + pl_val : blobs;
+        const int32_t* asrc = ha ? R.pool + ad_val : blobs;
+        int32_t t[9];
+#pragma unroll
+        for (int i = 0; i < 6; i++) t[i] = __ldg(psrc + (i < nGT ? i : 0));
+#pragma unroll
+        for (int i = 0; i < 3; i++) t[6 + i] = __ldg(asrc + (i < na ? i : 0));
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (hp) pl[i] = t[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (ha) ad[i] = t[6 + i];
+    }
+    // ---- the ALT allele must be the site's ALT (unified allele 1); a third allele must be the symbolic one (unmapped) ----
+    if (!(afl1 & GLX_AF_IS_DNA)) return false;
+    if (na == 3 && (afl2 & GLX_AF_IS_DNA)) return false;
+    {
+        int m = -1;
+#pragma unroll 1
+        for (uint32_t j = 0; j < nU && m < 0; j++) {
+            int4 ua, ub;
+            if (j == 0) {
+                ua = ua0; ub = ub0;
+            } else if (j == 1) {
+                ua = ua1; ub = ub1;
+            } else {
+                ua = __ldg(S.unif_rows + 2 * (size_t)(u0 + j));
+                ub = __ldg(S.unif_rows + 2 * (size_t)(u0 + j) + 1);
+            }
+            const uint64_t upx = (uint64_t)(uint32_t)ub.x | (uint64_t)(uint32_t)ub.y << 32;
+            if (ua.x != rbeg || ua.y != rend || (uint32_t)ua.z != aln1 || upx != apx1) continue;
+            bool eq = true;
+            if (aln1 > 8) {
+                const char* x = R.al_pool + R.al_str[a0 + 1];
+                const char* y = S.unif_pool + (uint32_t)ub.z;
+                for (uint32_t c = 8; c < aln1; c++)
+                    if (x[c] != y[c]) {
+                        eq = false;
+                        break;
+                    }
+            }
+            if (eq) m = ua.w & 255;
+        }
+        if (m != 1) return false;  // lost allele (or a unification the closed form does not take)
+    }
+    // kept (an allele maps); the fields are lifted only if the record spans the site
+    if (!cfg.allow_partial && !(rbeg <= sbeg && rend >= send)) return false;
+    int g0, g1;
+    decode_gt(gtw, flags, g0, g1);
+    // (a called allele >= 2 is malformed or the unmapped symbolic allele: lost-allele accounting and its rescoring are the general form's)
+    if ((!gt_is_missing(g0) && (g0 == GLXD_INT_VEND || gt_allele(g0) >= 2)) || (!gt_is_missing(g1) && (g1 == GLXD_INT_VEND || gt_allele(g1) >= 2))) return false;
+    // ---- revise_genotypes: the called alleles map, so only a homozygous-ALT call is rescored (three or six genotypes) ----
+    int gq_value = 0;
+    bool gq_revised = false;
+    if (cfg.revise && !gt_is_missing(g0) && !gt_is_missing(g1) && gt_allele(g0) > 0 && gt_allele(g0) == gt_allele(g1)) {
+        if (pl_rv != nGT) return false;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (k < nGT && pl[k] != GLXD_INT_MISSING && pl[k] != GLXD_INT_VEND && pl[k] < 0) return false;
+        int gq_rv;
+        int32_t gq_val;
+        if (!column(cfg.col_gq, gq_rv, gq_val) || gq_rv != 1) return false;
+        const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+        double map_gll = ninf, silver_gll = ninf;
+        int map_i = -1, map_j = -1, map_gt = -1, silver_i = -1, silver_j = -1, silver_gt = -1;
+        const double lost_prior = (double)S.lost_log_prior[s];
+#pragma unroll
+        for (int g = 0; g < 6; g++) {  // (i, j) = (0,0), (0,1), (1,1), (0,2), (1,2), (2,2); allele 2 is the unmapped symbolic one
+            if (g >= nGT) break;
+            const int i = g == 2 || g == 4 ? 1 : (g == 5 ? 2 : 0), j = g == 0 ? 0 : (g < 3 ? 1 : 2);
+            double prior = 0.0;
+            if (j == 2) prior = lost_prior;
+            else if (g == 2) prior = (double)S.hom_log_prior[al0 + 1];
+            if (cfg.calibration && prior != 0.0) {
+                const bool has_indel = (g == 2 || g == 4) && S.allele_is_indel[al0 + 1];  // a mapped non-reference allele that is an indel
+                const double x = __dmul_rn((double)(has_indel ? cfg.indel_cal : cfg.snv_cal), prior);
+                prior = (x < 0.0) ? x : 0.0;
+            }
+            const int32_t x = pl[g];
+            const double gll = (x == GLXD_INT_MISSING || x == GLXD_INT_VEND) ? ninf : __ddiv_rn((double)x, cfg.neg10_log10e);
+            const double v = __dadd_rn(gll, prior);
+            if (v > map_gll) {
+                silver_gll = map_gll; silver_gt = map_gt; silver_i = map_i; silver_j = map_j;
+                map_gll = v; map_gt = g; map_i = i; map_j = j;
+            } else if (v > silver_gll) {
+                silver_gll = v; silver_gt = g; silver_i = i; silver_j = j;
+            }
+        }
+        if (map_gt < 0 || silver_gt < 0) return false;
+        if (map_gt == 0) {  // (homalt)
+            map_i = silver_i;
+            map_j = silver_j;
+        }
+        if (map_j >= 2) return false;  // rescored onto the unmapped symbolic allele: a lost call, the general form's
+        g0 = gt_unphased(map_i);
+        g1 = gt_unphased(map_j);
+        const double q = round(__ddiv_rn(__dmul_rn(10.0, __dsub_rn(map_gll, silver_gll)), cfg.ln10));
+        const int qi = to_int_x86(q);
+        gq_value = qi < 99 ? qi : 99;
+        gq_revised = true;
+    }
+    // ---- depth gate, allele slots ----
+    auto depth = [&](int allele) -> unsigned { return (ad_zero || allele < 0 || allele >= na) ? 0u : (unsigned)(allele == 0 ? ad[0] : (allele == 1 ? ad[1] : ad[2])); };
+    int rnc0, rnc1, al_0 = 0, al_1 = 0;
+    if (!(gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0)) {
+        const int mrd = (int)depth(0);
+        if ((unsigned long long)(long long)mrd >= (unsigned long long)cfg.required_dp) {
+            al_0 = al_1 = gt_unphased(0);
+            rnc0 = rnc1 = RNC_NA;
+        } else
+            rnc0 = rnc1 = RNC_D;
+    } else {
+        auto slot = [&](int g, int& al, int& rnc) {
+            rnc = RNC_I;
+            al = 0;
+            if (!gt_is_missing(g)) {
+                const int a = gt_allele(g);
+                if (depth(a) >= cfg.required_dp) {
+                    al = gt_unphased(a);  // identity map
+                    rnc = RNC_NA;
+                } else
+                    rnc = RNC_D;
+            }
+        };
+        slot(g0, al_0, rnc0);
+        slot(g1, al_1, rnc1);
+    }
+    // ---- fields ----
+    const uint32_t N = S.n_samples;
+    bool ok = true;
+    glx_static_for<Sig::nf>([&](auto kc) {
+        constexpr uint32_t k = decltype(kc)::value;
+        if (!ok) return;
+        const DFld& f = cfg.f[k];
+        const int32_t missing = f.type == GLX_TYPE_FLOAT ? (int32_t)GLX_FLOAT_MISSING_BITS : GLXD_INT_MISSING;
+        if (f.kind == GLX_FK_PL2) {
+            if (Sig::num(k) != GLX_NUM_GENOTYPE || __ldg(S.fld_cnt[k] + s) != 3) {
+                ok = false;
+                return;
+            }
+            int32_t* __restrict__ out = O.fld[k] + __ldg(S.fld_off[k] + s) + (uint64_t)sample * 3;
+            const bool have = pl_rv > 0;  // (its length was checked above; the record's genotypes of REF / ALT are its first three)
+            bool zero = false, other = false;
+#pragma unroll
+            for (int o = 0; o < 3; o++) {
+                const int32_t x = have ? pl[o] : GLXD_INT_MISSING;
+                if (x == 0) zero = true;
+                else if (x != GLXD_INT_MISSING) other = true;
+            }
+            const bool censor = !(zero && other);
+#pragma unroll
+            for (int o = 0; o < 3; o++) {
+                const int32_t x = have ? pl[o] : GLXD_INT_MISSING;
+                out[o] = censor ? 0 : (x == GLXD_INT_MISSING ? 990 : x);
+            }
+            return;
+        }
+        if (f.kind == GLX_FK_PL || f.kind == GLX_FK_FT || f.kind == GLX_FK_STRING || (Sig::num(k) != GLX_NUM_BASIC && Sig::num(k) != GLX_NUM_ALLELES) ||
+            (Sig::num(k) == GLX_NUM_BASIC && f.count != 1)) {
+            ok = false;
+            return;
+        }
+        // numeric kinds: the source column (first orig_name present; AD falls back to the reference depth)
+        int n_val = Sig::num(k) == GLX_NUM_BASIC ? 1 : na;
+        int src_col = -1;
+        int32_t src_val = 0;
+        bool found = false, fallback = false;
+        for (int ci = 0; ci < f.n_cols && !found; ci++) {
+            int rv;
+            int32_t val;
+            if (gq_revised && f.cols[ci] == cfg.col_gq) {
+                rv = 1;
+                val = gq_value;
+            } else if (!column(f.cols[ci], rv, val)) {
+                ok = false;
+                return;
+            }
+            if (rv == -2 || (rv >= 0 && rv != n_val)) {
+                ok = false;  // err = 2
+                return;
+            }
+            if (rv >= 0) {
+                found = true;
+                src_col = f.cols[ci];
+                src_val = val;
+            }
+        }
+        if (!found && f.kind == GLX_FK_AD) {
+            int rv;
+            int32_t val;
+            if (gq_revised && cfg.col_ref_dp == cfg.col_gq) {
+                rv = 1;
+                val = gq_value;
+            } else if (!column(cfg.col_ref_dp, rv, val)) {
+                ok = false;
+                return;
+            }
+            if (rv == -2 || (rv >= 0 && rv != 1)) {
+                ok = false;
+                return;
+            }
+            if (rv >= 0) {
+                found = fallback = true;
+                n_val = 1;
+                src_val = val;
+            }
+        }
+        const int32_t dflt = f.default_zero ? 0 : missing;
+        if (Sig::num(k) == GLX_NUM_BASIC) {
+            O.fld[k][((uint64_t)s * N + sample)] = found ? src_val : dflt;
+            return;
+        }
+        if (__ldg(S.fld_cnt[k] + s) != 2) {
+            ok = false;
+            return;
+        }
+        int32_t* __restrict__ out = O.fld[k] + __ldg(S.fld_off[k] + s) + (uint64_t)sample * 2;
+        int32_t x0 = dflt, x1 = dflt;
+        if (found) {
+            if (n_val == 1) {
+                x0 = src_val;  // the scalar (AD's reference-depth fallback: slot 0 only; a 1-value source under shape "alleles" cannot pass the length check)
+                if (!fallback) x1 = dflt;
+            } else if (src_col == cfg.col_pl) {
+                x0 = pl[0];
+                x1 = pl[1];
+            } else if (src_col == cfg.col_allele_dp) {
+                x0 = ad[0];
+                x1 = ad[1];
+            } else {
+                x0 = __ldg(R.pool + src_val);
+                x1 = __ldg(R.pool + src_val + 1);
+            }
+        }
+        if (f.type == GLX_TYPE_INT && x0 == GLXD_INT_MISSING && x1 == GLXD_INT_MISSING) x1 = GLXD_INT_VEND;
+        out[0] = x0;
+        out[1] = x1;
+    });
+    if (!ok) return false;
+    if ((al_0 != 0 && al_1 == 0) || al_0 > al_1) {
+        int tmp = al_0; al_0 = al_1; al_1 = tmp;
+        tmp = rnc0; rnc0 = rnc1; rnc1 = tmp;
+    }
+    const int o0 = gt_is_missing(al_0) ? -1 : gt_allele(al_0), o1 = gt_is_missing(al_1) ? -1 : gt_allele(al_1);
+    const size_t cell = ((size_t)s * N + sample) * 2;
+    *reinterpret_cast<char2*>(O.gt + cell) = make_char2((signed char)o0, (signed char)o1);
+    *reinterpret_cast<uchar2*>(O.rnc + cell) = make_uchar2((unsigned char)kRncChar[rnc0], (unsigned char)kRncChar[rnc1]);
+    uint32_t used = 0;
+    if (o0 >= 0) used |= 1u << o0;
+    if (o1 >= 0) used |= 1u << o1;
+    if (used) atomicOr(O.allele_used + s, used);
+    if (rnc0 == RNC_I || rnc1 == RNC_I) {  // the only "lost call" codes this form produces
+        uint32_t* w = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(O.site_flags + s) & ~(uintptr_t)3);
+        atomicOr(w, 1u << (8 * (reinterpret_cast<uintptr_t>(O.site_flags + s) & 3)));
+    }
+    return true;
+}
+
 }  // namespace glxd

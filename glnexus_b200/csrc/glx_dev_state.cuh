@@ -178,6 +178,9 @@ struct glx_dev_batch {
     FastPlan plan;
     uint2* worklist = nullptr;     // [n_cells] (cell id, record cursor) for the general kernel
     uint32_t* n_work = nullptr;
+    uint2* decl_list = nullptr;  // declined list of the fused tiled kernel (FastPlan::decl_list), inside the worklist arena
+    uint32_t* decl_n = nullptr;  // [GLX_MAX_CHUNKS]
+    uint32_t decl_cap = 0;
     size_t worklist_bytes = 0;
     uint32_t n_sample_blocks = 0, n_site_tiles = 0;
     uint32_t samples_per_cta = GLX_TILE_THREADS;  // one sample per lane

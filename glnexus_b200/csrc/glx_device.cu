@@ -352,6 +352,30 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
     }
 }
 
+// Worklist, pass 0 for the fused tiled kernel's declined list: one thread per listed entry (region, index), any region, the
+// general closed form. A finished entry gets GLX_WORK_DONE and is added to its region's finished count (high half of n_work),
+// so that the region passes skip regions with nothing left.
+template <int CAPA>
+__global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant_list_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
+                                                                uint2* __restrict__ worklist, uint32_t* __restrict__ n_work, uint32_t region_cells,
+                                                                const int32_t* __restrict__ blobs) {
+    extern __shared__ int32_t s_cols[];
+    const uint32_t N = S.n_samples;
+    const uint32_t offered = *plan.decl_n, n = offered < plan.decl_cap ? offered : plan.decl_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 at = plan.decl_list[i];
+        uint2* w = worklist + (size_t)at.x * region_cells + at.y;
+        const uint2 e = *w;
+        if ((e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) != GLX_WORK_SINGLE) continue;
+        const uint32_t s = e.x / N, sample = e.x % N;
+        const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
+        if (genotype_cell_variant<CAPA>(cfg, plan, R, S, O, blobs, s, sample, first, s_cols + threadIdx.x, blockDim.x)) {
+            w->y = e.y | GLX_WORK_DONE;
+            atomicAdd(n_work + at.x, 1u << 16);
+        }
+    }
+}
+
 // Worklist, pass 2: the unflagged cells (several records in the query range) try the closed form for a run of
 // reference bands (genotype_cell_bands, computed from the record blobs); finished cells get GLX_WORK_DONE.
 __global__ void __launch_bounds__(128) glx_cells_bands_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
@@ -904,10 +928,16 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     if (d->plan.enabled && d->n_cells) {
         const size_t n_regions = (size_t)d->n_sample_blocks * d->n_site_tiles;
         const size_t region_cells = (size_t)d->tile_sites * d->samples_per_cta;
-        d->worklist_bytes = n_regions * region_cells * 8 + (n_regions + 64) * 4;
+        // declined list of the fused tiled kernel: per chunk a counter and a share of room for 1/8 of the batch's cells
+        d->decl_cap = d->fused_variant ? (uint32_t)std::min<uint64_t>(d->n_cells / 8 + 4096, 1u << 28) : 0u;
+        const size_t decl_bytes = d->fused_variant ? (size_t)d->decl_cap * 8 + GLX_MAX_CHUNKS * 4 + 64 : 0;
+        const size_t nwork_bytes = ((n_regions + 64) * 4 + 7) & ~(size_t)7;
+        d->worklist_bytes = n_regions * region_cells * 8 + nwork_bytes + decl_bytes;
         e = ctx->take((void**)&d->worklist, &d->worklist_bytes);
         if (e != cudaSuccess) return bail(e, "cudaMalloc(worklist)");
         d->n_work = reinterpret_cast<uint32_t*>(d->worklist + n_regions * region_cells);
+        d->decl_list = d->fused_variant ? reinterpret_cast<uint2*>(reinterpret_cast<char*>(d->n_work) + nwork_bytes) : nullptr;
+        d->decl_n = d->fused_variant ? reinterpret_cast<uint32_t*>(d->decl_list + d->decl_cap) : nullptr;
         const size_t blob_part = ((Rn + 1) * blob_words(d->plan.n_rv) * 4 + 255) & ~(size_t)255;
         const size_t cur_part = (((size_t)d->n_site_tiles * N + 1) * 4 + 255) & ~(size_t)255;
         const size_t tq_part = (((size_t)d->n_site_tiles + 1) * 4 + 255) & ~(size_t)255;
@@ -1048,10 +1078,18 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
         const uint32_t n_regions = d->n_sample_blocks * d->n_site_tiles;
         uint32_t n_chunks = st == ctx->stream ? d->n_chunks : 1u;  // the aux stream and its events belong to the context stream
         if (n_chunks > n_regions) n_chunks = n_regions;
+        if (d->decl_list) CU(cudaMemsetAsync(d->decl_n, 0, GLX_MAX_CHUNKS * 4, st));
         for (uint32_t j = 0; j < n_chunks; j++) {
             const uint32_t c0 = (uint32_t)((uint64_t)n_regions * j / n_chunks), c1 = (uint32_t)((uint64_t)n_regions * (j + 1) / n_chunks);
             if (c1 == c0) continue;
-            d->tiled_kernel<<<c1 - c0, GLX_TILE_THREADS, d->tiled_smem, st>>>(d->cfg, d->plan, d->R, d->S, d->O, d->blobs, d->tile_cursors, d->worklist, d->n_work,
+            FastPlan plan_j = d->plan;
+            if (d->decl_list) {  // this chunk's share of the declined list
+                const uint32_t share = d->decl_cap / n_chunks;
+                plan_j.decl_list = d->decl_list + (size_t)j * share;
+                plan_j.decl_n = d->decl_n + j;
+                plan_j.decl_cap = share;
+            }
+            d->tiled_kernel<<<c1 - c0, GLX_TILE_THREADS, d->tiled_smem, st>>>(d->cfg, plan_j, d->R, d->S, d->O, d->blobs, d->tile_cursors, d->worklist, d->n_work,
                                                                             d->n_sample_blocks, c0);
             d->launches_per_call++;
             CU(cudaGetLastError());
@@ -1064,6 +1102,11 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[2], st));
             const uint32_t region_cells = d->tile_sites * d->samples_per_cta;
+            if (d->decl_list) {
+                glx_cells_variant_list_kernel<4><<<ctx->sm_count * GLX_VARIANT_MIN_BLOCKS, 128, VariantSmem<4>::SLOTS * 128 * 4, ws>>>(d->cfg, plan_j, d->R, d->S, d->O, d->worklist,
+                                                                                                                                 d->n_work, region_cells, d->blobs);
+                d->launches_per_call++;
+            }
             glx_cells_bands_kernel<<<g1, 128, 0, ws>>>(d->cfg, d->plan, d->R, d->S, d->O, d->worklist, d->n_work, c0, c1, region_cells, d->blobs);
             d->launches_per_call++;
             if (d->plan.vview && (!d->fused_variant || d->max_site_alleles > 4)) {  // small sites keep the per-thread shared-memory columns short

@@ -669,17 +669,22 @@ __global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS 
         if (tid == 0) s_ndone = 0;
         __syncthreads();
         uint32_t my_done = 0;
-        static_assert(VariantSmem<(FUSE > 0 ? FUSE : 1)>::SLOTS * GLX_TILE_THREADS <= (GLX_TILE_THREADS / 32) * 32 * GLX_STAGE_MAX, "columns live in s_stage");
         const uint32_t n_items = s_nslow;
-        int32_t* cols = &s_stage[0][0] + tid;
         for (uint32_t it = tid; it < n_items; it += GLX_TILE_THREADS) {
             const uint2 e = my_work[it];
             if (!(e.y & GLX_WORK_SINGLE)) continue;
             const uint32_t ws = e.x / N, wsample = e.x - ws * N;
             const uint64_t first = R.ds_rec_off[wsample] + (e.y & GLX_WORK_CURSOR);
-            if (genotype_cell_variant<(FUSE > 0 ? FUSE : 1)>(cfg, plan, R, S, O, blobs, ws, wsample, first, cols, GLX_TILE_THREADS)) {
+            // The CTA itself only runs the biallelic closed form (straight-line, registers only): nine cells in ten. A cell it
+            // declines would cost the whole warp the general closed form (2 k instructions) for a lane or two, so it goes to the
+            // launch's declined list, which glx_cells_variant_list_kernel works off with every lane busy (a full list: the entry
+            // stays in the region for glx_cells_single_kernel).
+            if (genotype_cell_biallelic<Sig>(cfg, plan, R, S, O, blobs, ws, wsample, first)) {
                 my_work[it].y = e.y | GLX_WORK_DONE;
                 my_done++;
+            } else if (plan.decl_list) {
+                const uint32_t pos = atomicAdd(plan.decl_n, 1u);
+                if (pos < plan.decl_cap) plan.decl_list[pos] = make_uint2(cta, it);
             }
         }
         if (my_done) atomicAdd(&s_ndone, my_done);

@@ -73,8 +73,9 @@ extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* r
 // composition of the cells the fast path declines: [0] finished by the single-record closed form, [1] general path,
 // [2] finished by the all-bands closed form, [3] all-band cells that nevertheless went to the general path
 static int32_t vsm[64];  // the shared-memory column of genotype_cell_variant, stride 1
-static uint64_t g_emu_stats[8];  // [0] single-record closed form [1] general [2] all-band closed form [3] bands declined [4] of [0]: through the record view; [5..7] see note_general
-extern "C" void glx_emu_stats(uint64_t out[8]) { memcpy(out, g_emu_stats, sizeof g_emu_stats); }
+static uint64_t g_emu_stats[9];  // [8] of [4]: finished by the biallelic form; [0] single-record closed form [1] general [2] all-band closed form [3] bands declined [4] of [0]: through the record view; [5..7] see note_general
+extern "C" void glx_emu_stats(uint64_t out[8]) { memcpy(out, g_emu_stats, 8 * sizeof(uint64_t)); }
+extern "C" uint64_t glx_emu_biallelic_cells() { return g_emu_stats[8]; }
 static void note_general(const DRecs& R, const DSites& S, uint32_t s, uint64_t first, uint64_t hi) {
     g_emu_stats[1]++;
     int n = 0;
@@ -113,6 +114,12 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
                 if (type == CT_SLOW) {
                     n_slow++;
                     const bool single = !S.monoallelic[s] && L.c < L.n && L.beg_c < S.qend[s] && L.beg_n >= S.qend[s];
+                    if (single && genotype_cell_biallelic<Sig>(C, plan, R, S, O, blobs, s, n, R.ds_rec_off[n] + L.c)) {  // the fused kernel's form
+                        g_emu_stats[0]++;
+                        g_emu_stats[4]++;
+                        g_emu_stats[8]++;
+                        continue;
+                    }
                     if (single && genotype_cell_variant<8, Sig>(C, plan, R, S, O, blobs, s, n, R.ds_rec_off[n] + L.c, vsm, 1)) {
                         g_emu_stats[0]++;
                         g_emu_stats[4]++;
