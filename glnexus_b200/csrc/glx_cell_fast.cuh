@@ -27,6 +27,7 @@ namespace glxd {
 #ifndef GLX_TILE_SITES
 #define GLX_TILE_SITES 64   // sites walked by one CTA (at most 64: per-lane site masks are 64-bit)
 #endif
+#define GLX_MAX_CHUNKS 8      // a launch covers the tile grid in at most this many chunks (glx_launch)
 #define GLX_TILE_THREADS 128
 #define GLX_STAGE_MAX 32     // per-sample vectors of 3..32 ints are transposed through shared memory before being stored
 #define GLX_WORK_SINGLE 0x80000000u  // worklist cursor flag: the query range holds exactly one record (not a monoallelic site)

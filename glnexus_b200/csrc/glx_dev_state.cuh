@@ -13,7 +13,6 @@
 
 using namespace glxd;
 
-#define GLX_MAX_CHUNKS 8
 #define GLX_ARENA_CACHE 64  // a batch owns up to ten arenas and a range-batch driver keeps two or three batches in flight: no cudaFree in steady state
 struct glx_ctx {
     int device = 0;

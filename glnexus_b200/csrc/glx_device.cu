@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
         if (genotype_cell_variant<CAPA>(cfg, plan, R, S, O, blobs, s, sample, first, s_cols + threadIdx.x, blockDim.x)) {
             w->y = e.y | GLX_WORK_DONE;
             atomicAdd(n_work + at.x, 1u << 16);
+            atomicAdd(plan.decl_n + GLX_MAX_CHUNKS, 1u);  // cells this kernel finished (glx_fused_count leaves them out)
         }
     }
 }
@@ -930,7 +931,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         const size_t region_cells = (size_t)d->tile_sites * d->samples_per_cta;
         // declined list of the fused tiled kernel: per chunk a counter and a share of room for 1/8 of the batch's cells
         d->decl_cap = d->fused_variant ? (uint32_t)std::min<uint64_t>(d->n_cells / 8 + 4096, 1u << 28) : 0u;
-        const size_t decl_bytes = d->fused_variant ? (size_t)d->decl_cap * 8 + GLX_MAX_CHUNKS * 4 + 64 : 0;
+        const size_t decl_bytes = d->fused_variant ? (size_t)d->decl_cap * 8 + 2 * GLX_MAX_CHUNKS * 4 + 64 : 0;
         const size_t nwork_bytes = ((n_regions + 64) * 4 + 7) & ~(size_t)7;
         d->worklist_bytes = n_regions * region_cells * 8 + nwork_bytes + decl_bytes;
         e = ctx->take((void**)&d->worklist, &d->worklist_bytes);
@@ -1078,7 +1079,7 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
         const uint32_t n_regions = d->n_sample_blocks * d->n_site_tiles;
         uint32_t n_chunks = st == ctx->stream ? d->n_chunks : 1u;  // the aux stream and its events belong to the context stream
         if (n_chunks > n_regions) n_chunks = n_regions;
-        if (d->decl_list) CU(cudaMemsetAsync(d->decl_n, 0, GLX_MAX_CHUNKS * 4, st));
+        if (d->decl_list) CU(cudaMemsetAsync(d->decl_n, 0, 2 * GLX_MAX_CHUNKS * 4, st));  // [j]: entries offered by chunk j; [GLX_MAX_CHUNKS + j]: finished by the list kernel
         for (uint32_t j = 0; j < n_chunks; j++) {
             const uint32_t c0 = (uint32_t)((uint64_t)n_regions * j / n_chunks), c1 = (uint32_t)((uint64_t)n_regions * (j + 1) / n_chunks);
             if (c1 == c0) continue;
@@ -1422,6 +1423,11 @@ int glx_fused_count(glx_ctx* ctx, glx_dev_batch* d, uint64_t* n) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h.data(), d->n_work, n_regions * 4, cudaMemcpyDeviceToHost));
     for (uint32_t v : h) *n += v >> 16;
+    if (d->decl_n) {  // the high halves also count what glx_cells_variant_list_kernel finished
+        uint32_t c[2 * GLX_MAX_CHUNKS];
+        CU(cudaMemcpy(c, d->decl_n, sizeof c, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < GLX_MAX_CHUNKS; j++) *n -= c[GLX_MAX_CHUNKS + j];
+    }
     return GLX_OK;
 }
 

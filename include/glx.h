@@ -346,7 +346,8 @@ uint64_t glx_bcf_records(const glx_dev_batch* dev); /* records in the encoded ba
 /* Measurement aids: record CUDA events around the stages of glx_launch on the launching stream; glx_kernel_ms waits
  * for the last launch and returns the durations of {record resolve kernel, tiled fast-path kernel (incl. the fused
  * lone-variant closed form), closed-form worklist kernels (bands, variant, single-record), general worklist kernel}; glx_work_count = cells the tiled kernel put on its worklist, glx_fused_count = those of them it then
- * finished itself (lone-variant-record cells, when that closed form is fused into the tiled kernel). */
+ * finished itself (lone-variant-record cells its fused biallelic closed form took; the ones it declined are finished by
+ * glx_cells_variant_list_kernel and are not counted). */
 int glx_set_profile(glx_ctx* ctx, glx_dev_batch* dev, int on);
 /* Kernel-path switches used by the parity tests and ablations (all 0 by default; they apply to batches uploaded afterwards):
  * "force_general" (the general kernel alone computes every cell), "force_dynamic_tiled", "no_resolve_sig", "no_fuse",
