@@ -96,6 +96,15 @@ __device__ inline bool genotype_cell_variant(const DCfg& cfg, const FastPlan& pl
     int32_t pl_val, ad_val;
     if (!column(cfg.col_pl, pl_rv, pl_val) || !column(cfg.col_allele_dp, ad_rv, ad_val)) return false;
     if ((pl_rv > CAPG && pl_rv != 0x7fffffff) || (ad_rv > CAPA && ad_rv != 0x7fffffff)) return false;
+#if defined(__CUDACC__) && !defined(GLX_ABLATE_POOL_PREFETCH)
+    // every other vector column of the view (SB's four counts, ...) is read from the value pool by the field that lifts it, behind
+    // everything above: ask for its line now, with this round's loads (ncu: that first dependent load was 10 % of the stall samples)
+#pragma unroll
+    for (int j = 0; j < GLX_VIEW_COLS; j++) {
+        const uint32_t len = (uint32_t)clen[j];
+        if (len > 1 && len < 0xFFF0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.pool + cval[j]));
+    }
+#endif
     int32_t* const s_pl = sm;
     int32_t* const s_ad = sm + (size_t)CAPG * sms;
     {
@@ -445,6 +454,76 @@ __device__ inline bool genotype_cell_variant(const DCfg& cfg, const FastPlan& pl
             return o < n_val ? src(o) : dflt;
         };
         bool wipe = false, all_missing = false;
+#ifndef GLX_ABLATE_GENOTYPE_SCATTER
+        if (shape == 0 && found && count == GA) {
+            // A genotype-numbered vector through the allele map, walked from the RECORD's side: its n_genotypes(na) entries (6 or 10
+            // for a record with one or two ALT alleles) instead of the site's n_genotypes(A) slots (28 at seven alleles) twice over.
+            // The allele map is injective here (checked above), so record genotype (i, j) with both alleles mapped is the one source of
+            // slot (map[i], map[j]); every other slot holds the default.
+            int zeroes = 0, nonzeroes = 0, k_mapped = 0;
+            bool none = true;
+            {
+                int g = 0;
+#pragma unroll 1
+                for (int j = 0; j < na; j++) {
+                    const int mj = nib_get(mapw, j);
+                    if (mj >= 0 && mj < A) k_mapped++;
+#pragma unroll 1
+                    for (int i = 0; i <= j; i++, g++) {
+                        const int mi = nib_get(mapw, i);
+                        if (mi < 0 || mj < 0 || mi >= A || mj >= A) continue;
+                        const int32_t x = src(g);
+                        if (x != GLXD_INT_MISSING) none = false;
+                        if (x == 0) zeroes++;
+                        else nonzeroes++;
+                    }
+                }
+            }
+            if (dflt != GLXD_INT_MISSING && (int)n_genotypes((unsigned)k_mapped) < count) none = false;
+            if (f.kind == GLX_FK_PL || vec_rule) all_missing = none;
+            if (f.kind == GLX_FK_PL && (zeroes == 0 || (zeroes == 1 && nonzeroes == 0))) wipe = all_missing = true;
+            const int32_t fillv = wipe ? GLXD_INT_MISSING : dflt;
+            if ((count & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+                const int4 f4 = make_int4(fillv, fillv, fillv, fillv);
+#pragma unroll 1
+                for (int o = 0; o < count; o += 4) *reinterpret_cast<int4*>(out + o) = f4;
+            } else {
+#pragma unroll 1
+                for (int o = 0; o < count; o++) out[o] = fillv;
+            }
+            if (!wipe) {
+                int g = 0;
+#pragma unroll 1
+                for (int j = 0; j < na; j++) {
+                    const int mj = nib_get(mapw, j);
+#pragma unroll 1
+                    for (int i = 0; i <= j; i++, g++) {
+                        const int mi = nib_get(mapw, i);
+                        if (mi < 0 || mj < 0 || mi >= A || mj >= A) continue;
+                        out[alleles_gt(mi, mj)] = src(g);
+                    }
+                }
+            }
+            if (vec_rule && all_missing) out[1] = GLXD_INT_VEND;
+            return true;
+        }
+        if (f.kind != GLX_FK_PL) {  // one pass: the only whole-vector rule is "all missing -> vector end in slot 1", patched afterwards
+            bool none = true;
+            int a = 0, b = 0;
+#pragma unroll 1
+            for (int o = 0; o < count; o++) {
+                const int32_t x = value(o, a, b);
+                if (x != GLXD_INT_MISSING) none = false;
+                out[o] = x;
+                if (++b > a) {
+                    a++;
+                    b = 0;
+                }
+            }
+            if (vec_rule && none) out[1] = GLXD_INT_VEND;
+            return true;
+        }
+#endif
         if (f.kind == GLX_FK_PL || vec_rule) {  // pass 1: the censoring rules look at the whole vector
             int zeroes = 0, nonzeroes = 0;
             all_missing = true;

@@ -342,8 +342,10 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
         const uint32_t n_items = nw & GLX_NWORK_MASK;
         if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
+        uint2 e_next = threadIdx.x < n_items ? w[threadIdx.x] : make_uint2(0u, 0u);
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
-            const uint2 e = w[it];
+            const uint2 e = e_next;
+            if (it + blockDim.x < n_items) e_next = w[it + blockDim.x];  // the next entry travels while this cell is worked on
             if ((e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) != GLX_WORK_SINGLE) continue;
             const uint32_t s = e.x / N, sample = e.x % N;
             const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
