@@ -95,6 +95,8 @@ def lib():
     L.glxh_n_fields.restype = C.c_uint32
     L.glxh_device_supported.argtypes = [vp]
     L.glxh_device_supported.restype = C.c_int
+    L.glxh_has_fast_path.argtypes = [vp]
+    L.glxh_has_fast_path.restype = C.c_int
     L.glxh_out_alloc.argtypes = [vp, C.c_int]
     L.glxh_out_alloc.restype = vp
     L.glxh_out_free.argtypes = [vp]
@@ -389,6 +391,11 @@ class Batch:
     @property
     def device_supported(self):
         return bool(lib().glxh_device_supported(self.handle))
+
+    @property
+    def has_fast_path(self):
+        """single-sample datasets in output order: tiled kernels and a wire form (else the multi-sample kernel, full-width upload)"""
+        return bool(lib().glxh_has_fast_path(self.handle))
 
     def alloc_out(self, pinned=False):
         return Out(self, pinned)

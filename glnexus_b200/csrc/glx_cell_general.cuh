@@ -64,6 +64,42 @@ __device__ __forceinline__ int col_get(const DRecs& R, int col, uint64_t r, cons
     return (int)len;
 }
 
+// One sample of a MULTI-sample dataset, presented as if its records were single-sample: `si` of the dataset's `ns` samples.
+// The per-sample logic (allele depths, likelihood rescoring, FORMAT lifting) runs unchanged on this view; what the reference
+// decides per DATASET across its samples (src/genotyper.cc:95-115, 335-347, 380-392, 474-476) is restated in
+// genotype_cell_general's MULTI branches. Values of a column sit sample-major in the pool (bcf_get_format_*'s layout), the GT
+// pairs in gt_pool.
+struct MRecs : DRecs {
+    const int32_t* gt_pool;
+    uint32_t ns, si;
+};
+__device__ __forceinline__ int col_get(const MRecs& R, int col, uint64_t r, const int32_t*& p) {
+    if (R.ns == 1) return col_get(static_cast<const DRecs&>(R), col, r, p);
+    if (col < 0) return -1;
+    const size_t idx = (size_t)col * R.n_records + r;
+    const uint16_t len = R.col_len[idx];
+    if (len == GLX_LEN_ABSENT) return -3;
+    if (len == 0xFFFE) return -2;
+    if (len == 0xFFFD) {
+        p = nullptr;
+        return 0x7fffffff;
+    }
+    p = R.pool + R.col_val[idx] + (size_t)R.si * len;
+    return (int)len;
+}
+// the record's GT pair as preprocess_record sees it (htslib GT ints, phase bit cleared)
+__device__ __forceinline__ void rec_gt(const DRecs& R, uint64_t r, uint8_t flags, int& g0, int& g1) { decode_gt(R.gt[r], flags, g0, g1); }
+__device__ __forceinline__ void rec_gt_of(const MRecs& R, uint64_t r, uint8_t flags, uint32_t k, int& g0, int& g1) {
+    if (R.ns == 1) {
+        decode_gt(R.gt[r], flags, g0, g1);
+        return;
+    }
+    const int32_t* gp = R.gt_pool + R.gt[r] + 2 * (size_t)k;
+    g0 = gp[0];
+    g1 = gp[1];
+}
+__device__ __forceinline__ void rec_gt(const MRecs& R, uint64_t r, uint8_t flags, int& g0, int& g1) { rec_gt_of(R, r, flags, R.si, g0, g1); }
+
 // site.unification.find(allele(record range, dna)) — src/genotyper.cc:65-72
 template <class RT, class ST>
 __device__ inline int unif_lookup(const RT& R, const ST& S, uint32_t u0, uint32_t u1, int rbeg, int rend, uint32_t a) {
@@ -148,13 +184,20 @@ __device__ __forceinline__ int to_int_x86(double x) {
 // revise_genotypes for one single-sample variant record. Returns 0 ok / positive error code.
 // g0,g1 in/out (htslib GT ints), gq out (valid when revised).
 template <class RT, class ST>
+// `forced`: -1 the record's own GT decides whether it is rescored (single-sample dataset); 0 no; 1 yes; 2 yes, as a homozygous-ALT
+// call (multi-sample dataset: the first sample with a reason decides for all of them, genotyper.cc:97-115 — revise_forced).
 __device__ inline int revise_record(const DCfg& cfg, const RT& R, const ST& S, const SiteCtx& st, uint64_t r, int na, const int8_t* map, int& g0,
-                                    int& g1, int& gq, bool& revised) {
+                                    int& g1, int& gq, bool& revised, int forced = -1) {
     revised = false;
     bool needs = false, homalt = false;
-    if (!gt_is_missing(g0) && map[gt_allele(g0)] == -1 && !st.mono) needs = true;
-    else if (!gt_is_missing(g1) && map[gt_allele(g1)] == -1 && !st.mono) needs = true;
-    else if (!gt_is_missing(g0) && !gt_is_missing(g1) && gt_allele(g0) > 0 && gt_allele(g0) == gt_allele(g1)) needs = homalt = true;
+    if (forced < 0) {
+        if (!gt_is_missing(g0) && map[gt_allele(g0)] == -1 && !st.mono) needs = true;
+        else if (!gt_is_missing(g1) && map[gt_allele(g1)] == -1 && !st.mono) needs = true;
+        else if (!gt_is_missing(g0) && !gt_is_missing(g1) && gt_allele(g0) > 0 && gt_allele(g0) == gt_allele(g1)) needs = homalt = true;
+    } else {
+        needs = forced > 0;
+        homalt = forced == 2;
+    }
     if (!needs) return 0;
     const int nGT = (int)n_genotypes(na);
     const int32_t* pl = nullptr;
@@ -218,6 +261,59 @@ __device__ inline int revise_record(const DCfg& cfg, const RT& R, const ST& S, c
     return 0;
 }
 
+// Who decides the rescoring of record r: its own GT (-1), or — multi-sample dataset — the dataset's samples in order, the first
+// one with a reason (a called allele that is not unified; a homozygous-ALT call) deciding for all (genotyper.cc:97-115).
+__device__ __forceinline__ int revise_forced(const DRecs&, const SiteCtx&, uint64_t, int, uint8_t, const int8_t*) { return -1; }
+__device__ inline int revise_forced(const MRecs& R, const SiteCtx& st, uint64_t r, int na, uint8_t flags, const int8_t* map) {
+    if (R.ns == 1) return -1;
+    for (uint32_t k = 0; k < R.ns; k++) {
+        int g0, g1;
+        rec_gt_of(R, r, flags, k, g0, g1);
+        const bool v0 = !gt_is_missing(g0) && g0 != GLXD_INT_VEND && gt_allele(g0) < na, v1 = !gt_is_missing(g1) && g1 != GLXD_INT_VEND && gt_allele(g1) < na;
+        if (v0 && map[gt_allele(g0)] == -1 && !st.mono) return 1;
+        if (v1 && map[gt_allele(g1)] == -1 && !st.mono) return 1;
+        if (v0 && v1 && gt_allele(g0) > 0 && gt_allele(g0) == gt_allele(g1)) return 2;
+    }
+    return 0;
+}
+// the view's own GT pair of variant record r after revise_genotypes (when configured); 0 or an error code
+template <class RT, class ST>
+__device__ inline int rec_gt_revised(const DCfg& cfg, const RT& R, const ST& S, const SiteCtx& st, uint64_t r, int na, uint8_t flags, const int8_t* map, int& g0,
+                                     int& g1, int& gq, bool& revised) {
+    rec_gt(R, r, flags, g0, g1);
+    revised = false;
+    if (!cfg.revise) return 0;
+    return revise_record(cfg, R, S, st, r, na, map, g0, g1, gq, revised, revise_forced(R, st, r, na, flags, map));
+}
+// Is variant record r "non-0/0" for its dataset: some sample's (revised) GT entry missing or not REF (genotyper.cc:380-392).
+// With `first_only` the answer's GT pair is sample 0's, the one the half-call rules read (genotyper.cc:474-476).
+template <class ST>
+__device__ inline bool rec_non00_any(const DCfg& cfg, const MRecs& R, const ST& S, const SiteCtx& st, uint64_t r, int na, uint8_t flags, const int8_t* map,
+                                     int& g0_first, int& g1_first) {
+    const int forced = cfg.revise ? revise_forced(R, st, r, na, flags, map) : 0;
+    bool non00 = false;
+    MRecs Rk = R;
+    for (uint32_t k = 0; k < R.ns; k++) {
+        Rk.si = k;
+        int g0, g1, gq;
+        bool revised;
+        rec_gt(Rk, r, flags, g0, g1);
+        if (forced > 0) {
+            int h0 = g0, h1 = g1;
+            if (revise_record(cfg, Rk, S, st, r, na, map, h0, h1, gq, revised, forced) == 0) {  // (a failing sample fails the site from its own cell)
+                g0 = h0;
+                g1 = h1;
+            }
+        }
+        if (k == 0) {
+            g0_first = g0;
+            g1_first = g1;
+        }
+        if (gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0) non00 = true;
+    }
+    return non00;
+}
+
 // AlleleDepthHelper::Load + get (genotyper_utils.h:982-1114) for a single-sample record.
 // Returns 0 ok / error code 2 (Invalid). depth out as the reference's `unsigned`.
 template <class RT>
@@ -279,7 +375,8 @@ __device__ __forceinline__ void push_value(const DFld& f, int32_t* out, uint8_t*
 
 // NumericFormatFieldHelper::add_record_data for one record (genotyper_utils.h:285-355, 87-135).
 // rv: 0 found, -3 not found, >0 error code
-__device__ inline int numeric_add(const DFld& f, const DRecs& R, uint64_t r, int na, const int8_t* map, int count, const int16_t* cols, int ncols,
+template <class RT>
+__device__ inline int numeric_add(const DFld& f, const RT& R, uint64_t r, int na, const int8_t* map, int count, const int16_t* cols, int ncols,
                                   int n_val_forced, int32_t* out, uint8_t* cnt, uint32_t stride, bool squeeze_dp, bool gq_revised, int gq_value,
                                   int col_gq) {
     int n_val = n_val_forced;
@@ -393,7 +490,8 @@ struct RecBasic {
 };
 
 // FORMAT lifting of one record into every field that takes it (update_format_fields inner loop)
-__device__ inline int lift_record(const DCfg& cfg, const DRecs& R, const DSites& S, const DOut& O, const SiteCtx& st, uint32_t sample, uint64_t r,
+template <class RT>
+__device__ inline int lift_record(const DCfg& cfg, const RT& R, const DSites& S, const DOut& O, const SiteCtx& st, uint32_t sample, uint64_t r,
                                   bool from_used_set, bool have_used, bool squeeze_mode, const int* slot_base, uint8_t* cnt, uint32_t stride,
                                   uint32_t& self_censor_mask) {
     const int na = R.n_allele[r];
@@ -415,8 +513,7 @@ __device__ inline int lift_record(const DCfg& cfg, const DRecs& R, const DSites&
     int gq_value = 0;
     if (!is_ref && cfg.revise) {
         int g0, g1;
-        decode_gt(R.gt[r], flags, g0, g1);
-        const int e = revise_record(cfg, R, S, st, r, na, map, g0, g1, gq_value, gq_revised);
+        const int e = rec_gt_revised(cfg, R, S, st, r, na, flags, map, g0, g1, gq_value, gq_revised);
         if (e) return e;
     }
     for (uint32_t k = 0; k < cfg.n_fields; k++) {
@@ -459,10 +556,16 @@ __device__ inline int lift_record(const DCfg& cfg, const DRecs& R, const DSites&
 }
 
 // The whole cell. `first` = index of the sample's first record with maxend > site.qbeg; `hi` = end of the sample's records.
-__device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, const DSites& S, const DOut& O, uint32_t s, uint32_t sample, uint64_t first,
-                                             uint64_t hi, uint8_t* cnt, uint32_t stride) {
+// RT = DRecs: the sample's own single-sample dataset. RT = MRecs: output sample `sample` is sample R.si of a dataset of R.ns
+// samples whose records are [first.., hi); the decisions the reference takes per dataset across its samples are the MULTI branches;
+// errors are keyed by `err_cell` (site-major, datasets in order within the site: the first failing dataset's status wins).
+template <class RT>
+__device__ inline void genotype_cell_general(const DCfg& cfg, const RT& R, const DSites& S, const DOut& O, uint32_t s, uint32_t sample, uint64_t first,
+                                             uint64_t hi, uint8_t* cnt, uint32_t stride, unsigned long long err_cell = ~0ull) {
+    constexpr bool MULTI = std::is_same<RT, MRecs>::value;
     const SiteCtx st = load_site(S, s);
     const uint32_t N = S.n_samples;
+    if (err_cell == ~0ull) err_cell = (unsigned long long)s * N + sample;
 
     // ---- pass 0: kept records, span test (types.h:174-215 on a beg-sorted stream) ----
     int n_kept = 0;
@@ -524,7 +627,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                 break;
             }
             int g0, g1;
-            decode_gt(R.gt[r], flags, g0, g1);
+            rec_gt(R, r, flags, g0, g1);
             // GT entries index the record's alleles (ingest-time invariant, src/BCF_utils.cc:126-140); the reference
             // would throw from vector::at on anything else
             if ((!gt_is_missing(g0) && (g0 == GLXD_INT_VEND || gt_allele(g0) >= na)) || (!gt_is_missing(g1) && (g1 == GLXD_INT_VEND || gt_allele(g1) >= na))) {
@@ -542,6 +645,13 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                 }
                 mrd = (mrd < 0) ? (int)d : min(mrd, (int)d);
                 if (!(flags & GLX_RF_HAPLOID) && (gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0)) ref_noncalled = true;
+                if constexpr (MULTI) {  // any sample of the dataset, genotyper.cc:335-347
+                    for (uint32_t k = 0; k < R.ns && !ref_noncalled; k++) {
+                        int h0, h1;
+                        rec_gt_of(R, r, flags, k, h0, h1);
+                        if (!(flags & GLX_RF_HAPLOID) && (gt_is_missing(h0) || gt_allele(h0) != 0 || gt_is_missing(h1) || gt_allele(h1) != 0)) ref_noncalled = true;
+                    }
+                }
                 continue;
             }
             n_var++;
@@ -551,7 +661,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
             if (cfg.revise) {
                 int gq;
                 bool revised;
-                err = revise_record(cfg, R, S, st, r, na, map, g0, g1, gq, revised);
+                err = revise_record(cfg, R, S, st, r, na, map, g0, g1, gq, revised, revise_forced(R, st, r, na, flags, map));
                 if (err) break;
             }
             for (int a = 1; a < na; a++)
@@ -559,7 +669,11 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                     if (mono_rec == ~0ull) mono_rec = r;
                     else mono_multi = true;
                 }
-            const bool non00 = gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0;
+            bool non00 = gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0;
+            if constexpr (MULTI) {
+                // the record is sorted by the whole dataset's calls, and the half-call rules below read sample 0's pair
+                if (R.ns > 1) non00 = rec_non00_any(cfg, R, S, st, r, na, flags, map, g0, g1);
+            }
             if (!non00) {
                 n_00++;
                 continue;
@@ -583,7 +697,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                     const float nq = -1.0f * R.qual[r];
                     for (int w = 0; w < 2; w++) {
                         const int a = w ? a1 : a0;
-                        if (!(a > 0 && map[a] > 0)) continue;
+                        if (!(a > 0 && a < na && map[a] > 0)) continue;
                         const int idx = n_usable++;
                         // keep the two smallest (−QUAL, insertion index) tuples (std::sort of genotyper.cc:497)
                         const bool lt1 = b1r == ~0ull || nq < b1q || (!(b1q < nq) && idx < b1i);
@@ -613,15 +727,25 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                         const uint8_t flags = R.flags[r];
                         const int na = R.n_allele[r];
                         int g0, g1;
-                        decode_gt(R.gt[r], flags, g0, g1);
-                        if (cfg.revise) {
+                        rec_gt(R, r, flags, g0, g1);
+                        bool multi_ds = false;
+                        if constexpr (MULTI) multi_ds = R.ns > 1;
+                        if (cfg.revise || multi_ds) {
                             int8_t map[GLX_MAX_ALLELES];
                             uint32_t del_mask;
                             compute_allele_map(R, S, st, r, na, false, map, del_mask);
-                            int gq;
-                            bool revised;
-                            err = revise_record(cfg, R, S, st, r, na, map, g0, g1, gq, revised);
-                            if (err) break;
+                            if (cfg.revise) {
+                                int gq;
+                                bool revised;
+                                err = revise_record(cfg, R, S, st, r, na, map, g0, g1, gq, revised, revise_forced(R, st, r, na, flags, map));
+                                if (err) break;
+                            }
+                            if constexpr (MULTI) {
+                                if (multi_ds) {
+                                    int f0, f1;
+                                    if (rec_non00_any(cfg, R, S, st, r, na, flags, map, f0, f1)) continue;
+                                }
+                            }
                         }
                         if (gt_is_missing(g0) || gt_allele(g0) != 0 || gt_is_missing(g1) || gt_allele(g1) != 0) continue;
                         unsigned d;
@@ -668,11 +792,10 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                         uint32_t del_mask;
                         compute_allele_map(R, S, st, r, na, false, map, del_mask);
                         int g[2];
-                        decode_gt(R.gt[r], flags, g[0], g[1]);
-                        if (cfg.revise) {
+                        {
                             int gq;
                             bool revised;
-                            err = revise_record(cfg, R, S, st, r, na, map, g[0], g[1], gq, revised);
+                            err = rec_gt_revised(cfg, R, S, st, r, na, flags, map, g[0], g[1], gq, revised);
                             if (err) break;
                         }
                         unsigned dchk;
@@ -735,11 +858,10 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
                     uint32_t del_mask;
                     compute_allele_map(R, S, st, r, na, false, map, del_mask);
                     int g[2];
-                    decode_gt(R.gt[r], flags, g[0], g[1]);
-                    if (cfg.revise) {
+                    {
                         int gq;
                         bool revised;
-                        err = revise_record(cfg, R, S, st, r, na, map, g[0], g[1], gq, revised);
+                        err = rec_gt_revised(cfg, R, S, st, r, na, flags, map, g[0], g[1], gq, revised);
                     }
                     unsigned dchk;
                     if (!err) err = depth_get(cfg, R, r, na, false, 0, dchk);
@@ -802,7 +924,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
         if (!err && used2 != ~0ull) err = lift_record(cfg, R, S, O, st, sample, used2, true, true, squeeze_mode, slot_base, cnt, stride, self_censor);
     }
     if (err) {
-        report_error(O, (unsigned long long)s * N + sample, err);
+        report_error(O, err_cell, err);
         return;
     }
 
@@ -857,7 +979,7 @@ __device__ inline void genotype_cell_general(const DCfg& cfg, const DRecs& R, co
             else if (n_uniq == 1 || f.combi == GLX_COMBI_SEMICOLON) v = (int32_t)uniq;
             else if (f.combi == GLX_COMBI_MISSING) v = 0;
             else {
-                report_error(O, (unsigned long long)s * N + sample, 2);
+                report_error(O, err_cell, 2);
                 return;
             }
             if (cz) v = 0;

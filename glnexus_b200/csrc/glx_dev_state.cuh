@@ -195,5 +195,10 @@ struct glx_dev_batch {
     int32_t* tile_q = nullptr;         // [n_site_tiles] suffix-min of each tile's first qbeg
     uint2* block_hints = nullptr;      // [resolve blocks + 1] (sample, t_hi) of each block's first record (glx_block_hints_kernel)
     uint32_t n_datasets = 0;
+    // multi-sample (or reordered) datasets: every cell goes through glx_cells_multi_kernel
+    bool multi = false;
+    const int32_t* gt_pool = nullptr;   // device copy of glx_records.gt_pool
+    const uint2* out_map = nullptr;     // device [n_samples]: x = dataset (0xFFFFFFFF: the sample has none), y = sample within it | samples of it << 16
+    std::vector<uint2> out_map_host;    // source of that copy (lives as long as the batch)
 };
 

@@ -342,10 +342,16 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
         const uint32_t n_items = nw & GLX_NWORK_MASK;
         if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
+#ifndef GLX_ABLATE_ENTRY_PIPELINE
         uint2 e_next = threadIdx.x < n_items ? w[threadIdx.x] : make_uint2(0u, 0u);
+#endif
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
+#ifndef GLX_ABLATE_ENTRY_PIPELINE
             const uint2 e = e_next;
             if (it + blockDim.x < n_items) e_next = w[it + blockDim.x];  // the next entry travels while this cell is worked on
+#else
+            const uint2 e = w[it];
+#endif
             if ((e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) != GLX_WORK_SINGLE) continue;
             const uint32_t s = e.x / N, sample = e.x % N;
             const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
@@ -443,6 +449,38 @@ __global__ void __launch_bounds__(128) glx_cells_general_kernel(const DCfg cfg, 
         const uint32_t s = (uint32_t)(cell / N), sample = (uint32_t)(cell % N);
         const uint64_t lo = R.ds_rec_off[sample], hi = R.ds_rec_off[sample + 1];
         genotype_cell_general(cfg, R, S, O, s, sample, first_candidate(R.maxend, lo, hi, S.qbeg[s]), hi, cnt, stride);
+    }
+}
+
+// Batches with a multi-sample dataset (or datasets out of output order): one thread per (site, output sample); the thread
+// presents its sample of the dataset as a single-sample view (MRecs) to the general cell logic, whose MULTI branches restate what
+// the reference decides per dataset across its samples. Rare inputs (the reference itself calls its multi-sample handling
+// incomplete, src/genotyper.cc:362,595), so no fast path: correctness only.
+__global__ void __launch_bounds__(128) glx_cells_multi_kernel(const DCfg cfg, const DRecs R0, const int32_t* __restrict__ gt_pool, const uint2* __restrict__ out_map,
+                                                              const DSites S, const DOut O, uint64_t n_all, uint8_t* __restrict__ cnt_scratch) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t* cnt = cnt_scratch + tid;
+    const uint32_t N = S.n_samples;
+    MRecs R;
+    static_cast<DRecs&>(R) = R0;
+    R.gt_pool = gt_pool;
+    for (uint64_t cell = tid; cell < n_all; cell += stride) {
+        const uint32_t s = (uint32_t)(cell / N), sample = (uint32_t)(cell % N);
+        const uint2 m = out_map[sample];
+        uint64_t lo = 0, hi = 0;
+        R.ns = 1;
+        R.si = 0;
+        uint32_t ds = sample;
+        if (m.x != 0xFFFFFFFFu) {
+            ds = m.x;
+            lo = R.ds_rec_off[m.x];
+            hi = R.ds_rec_off[m.x + 1];
+            R.si = m.y & 0xFFFFu;
+            R.ns = m.y >> 16;
+        }
+        const unsigned long long err_cell = (unsigned long long)s * N + (ds < N ? ds : N - 1);
+        genotype_cell_general(cfg, R, S, O, s, sample, lo < hi ? first_candidate(R.maxend, lo, hi, S.qbeg[s]) : lo, hi, cnt, stride, err_cell);
     }
 }
 
@@ -646,14 +684,36 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         return GLX_E_INVALID;
     }
     // preconditions of the device path: single-sample datasets in output-sample order
-    if (recs->n_datasets != sites->n_samples || recs->n_samples_out != sites->n_samples) {
-        ctx->err = "glx_upload: device path needs one single-sample dataset per output sample";
+    if (recs->n_samples_out != sites->n_samples || (wire && recs->n_datasets != sites->n_samples)) {
+        ctx->err = "glx_upload: the record store's output samples are not the sites' samples";
         return GLX_E_UNSUPPORTED;
     }
-    for (uint32_t d = 0; !wire && d < recs->n_datasets; d++) {  // (the wire builder has checked this)
-        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) {
-            ctx->err = "glx_upload: multi-sample or out-of-order dataset is outside the device path";
-            return GLX_E_UNSUPPORTED;
+    // The fast paths want one single-sample dataset per output sample, in output order. Anything else (multi-sample datasets,
+    // reordered or absent samples) takes the general multi-sample kernel, provided every sample of every dataset is in the sample
+    // set (the reference's FORMAT helpers throw on a partly selected dataset, src/genotyper_utils.h:75) and none is there twice.
+    bool multi = false;
+    std::vector<uint2> out_map;
+    if (!wire) {
+        multi = recs->n_datasets != sites->n_samples;
+        for (uint32_t d = 0; !multi && d < recs->n_datasets; d++)
+            multi = recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d;
+    }
+    if (multi) {
+        out_map.assign(sites->n_samples, make_uint2(0xFFFFFFFFu, 0u));
+        for (uint32_t d = 0; d < recs->n_datasets; d++) {
+            const uint32_t ns = recs->ds_n_sample[d];
+            if (ns == 0 || ns > 0xFFFFu || recs->ds_sample_off[d + 1] - recs->ds_sample_off[d] != ns) {
+                ctx->err = "glx_upload: malformed dataset sample table";
+                return GLX_E_INVALID;
+            }
+            for (uint32_t k = 0; k < ns; k++) {
+                const int32_t o = recs->sample_out[recs->ds_sample_off[d] + k];
+                if (o < 0 || (uint32_t)o >= sites->n_samples || out_map[o].x != 0xFFFFFFFFu) {
+                    ctx->err = "glx_upload: a dataset sample outside the sample set (or selected twice) is outside the device path";
+                    return GLX_E_UNSUPPORTED;
+                }
+                out_map[o] = make_uint2(d, k | ns << 16);
+            }
         }
     }
     const uint64_t S = sites->n_sites, N = sites->n_samples;
@@ -674,7 +734,9 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     d->n_fields = cfg->n_fields;
     d->n_cols = cfg->n_cols;
     d->n_cells = S * N;
-    d->force_general = ctx->opt.force_general != 0;
+    d->force_general = ctx->opt.force_general != 0 || multi;
+    d->multi = multi;
+    d->out_map_host.swap(out_map);
     // chunked launches share the context's aux stream and events: only for batches on the context's own stream
     d->n_chunks = (stream_ && (cudaStream_t)stream_ != ctx->stream) ? 1u : (uint32_t)ctx->opt.chunks;
 
@@ -719,6 +781,10 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     add(recs->al_prefix, recs->n_al * 8, &R.al_prefix);
     add(recs->al_str, recs->n_al * 4, &R.al_str);
     add(recs->al_pool, recs->n_al_pool, &R.al_pool);
+    if (multi) {
+        add(recs->gt_pool, recs->n_gt_pool * 4, &d->gt_pool);
+        add(d->out_map_host.data(), N * sizeof(uint2), &d->out_map);
+    }
     Sx.n_sites = (uint32_t)S;
     Sx.n_samples = (uint32_t)N;
     add(sites->beg, S * 4, &Sx.beg);
@@ -1143,7 +1209,11 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
             CU(cudaEventRecord(d->ev[2], st));
             CU(cudaEventRecord(d->ev[3], st));
         }
-        if (d->n_cells) {
+        if (d->n_cells && d->multi) {
+            glx_cells_multi_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->gt_pool, d->out_map, d->S, d->O, d->n_cells, d->cnt_scratch);
+            d->launches_per_call++;
+            CU(cudaGetLastError());
+        } else if (d->n_cells) {
             glx_cells_general_kernel<<<d->general_blocks, 128, 0, st>>>(d->cfg, d->R, d->S, d->O, nullptr, d->n_work, 0, 0, 0, d->n_cells, d->cnt_scratch, d->max_slots,
                                                                         d->n_cols);
             d->launches_per_call++;

@@ -257,6 +257,21 @@ const glx_sites* glxh_sites(const glxh_batch* b) { return &b->b.sites; }
 uint32_t glxh_n_fields(const glxh_batch* b) { return b->b.cfg.n_fields; }
 
 int glxh_device_supported(const glxh_batch* b) {
+    // glx_upload_on's preconditions: every sample of every dataset is in the sample set, once (multi-sample datasets are fine:
+    // they take the general multi-sample kernel; only single-sample datasets in output order have the fast paths and a wire form)
+    const glx_records& r = b->b.recs;
+    std::vector<char> seen(r.n_samples_out, 0);
+    for (uint32_t d = 0; d < r.n_datasets; d++) {
+        if (r.ds_n_sample[d] == 0 || r.ds_n_sample[d] > 0xFFFFu) return 0;
+        for (uint32_t k = 0; k < r.ds_n_sample[d]; k++) {
+            const int32_t o = r.sample_out[r.ds_sample_off[d] + k];
+            if (o < 0 || (uint32_t)o >= r.n_samples_out || seen[o]) return 0;
+            seen[o] = 1;
+        }
+    }
+    return 1;
+}
+int glxh_has_fast_path(const glxh_batch* b) {
     const glx_records& r = b->b.recs;
     if (r.n_datasets != r.n_samples_out) return 0;
     for (uint32_t d = 0; d < r.n_datasets; d++)

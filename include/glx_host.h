@@ -48,6 +48,7 @@ const glx_records* glxh_records(const glxh_batch* b);
 const glx_sites* glxh_sites(const glxh_batch* b);
 uint32_t glxh_n_fields(const glxh_batch* b);
 int glxh_device_supported(const glxh_batch* b); /* 1 if the batch meets the device path's preconditions */
+int glxh_has_fast_path(const glxh_batch* b);    /* 1 if it is single-sample datasets in output order (tiled kernels, wire form); else the multi-sample kernel */
 /* st[0..5] = n_sites, n_samples, n_records, n_datasets, bytes of all input arrays, #variant (non-reference) records */
 void glxh_batch_stats(const glxh_batch* b, uint64_t st[8]);
 

@@ -40,10 +40,64 @@ static void bind(const glx_config* cfg, const glx_records* r, const glx_sites* s
     for (int k = 0; k < GLX_MAX_FIELDS; k++) O.fld[k] = o->fld[k];
 }
 
+// multi-sample (or reordered) datasets: the loop of glx_cells_multi_kernel, the validation of glx_upload_on
+static int emu_multi_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out) {
+    const uint32_t Sn = sites->n_sites, N = sites->n_samples;
+    if (recs->n_samples_out != N) return GLX_E_UNSUPPORTED;
+    std::vector<uint2> out_map(N, uint2{0xFFFFFFFFu, 0u});
+    for (uint32_t d = 0; d < recs->n_datasets; d++) {
+        const uint32_t ns = recs->ds_n_sample[d];
+        if (ns == 0 || ns > 0xFFFFu) return GLX_E_INVALID;
+        for (uint32_t k = 0; k < ns; k++) {
+            const int32_t o = recs->sample_out[recs->ds_sample_off[d] + k];
+            if (o < 0 || (uint32_t)o >= N || out_map[o].x != 0xFFFFFFFFu) return GLX_E_UNSUPPORTED;
+            out_map[o] = uint2{d, k | ns << 16};
+        }
+    }
+    DCfg C; DRecs R0; DSites S; DOut O;
+    unsigned long long err = ~0ull;
+    bind(cfg, recs, sites, out, &err, C, R0, S, O);
+    std::vector<uint8_t> flags(Sn + 8, 0);
+    O.site_flags = flags.data();
+    uint32_t max_slots = 1;
+    for (uint32_t s = 0; s < Sn; s++) {
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < cfg->n_fields; k++) t += sites->fld_cnt[k][s];
+        max_slots = std::max(max_slots, t);
+        out->allele_used[s] = 0;
+    }
+    std::vector<uint8_t> cnt(max_slots);
+    MRecs R;
+    static_cast<DRecs&>(R) = R0;
+    R.gt_pool = recs->gt_pool;
+    for (uint32_t s = 0; s < Sn; s++)
+        for (uint32_t n = 0; n < N; n++) {
+            const uint2 m = out_map[n];
+            uint64_t lo = 0, hi = 0;
+            R.ns = 1;
+            R.si = 0;
+            uint32_t ds = n;
+            if (m.x != 0xFFFFFFFFu) {
+                ds = m.x;
+                lo = R.ds_rec_off[m.x];
+                hi = R.ds_rec_off[m.x + 1];
+                R.si = m.y & 0xFFFFu;
+                R.ns = m.y >> 16;
+            }
+            const unsigned long long err_cell = (unsigned long long)s * N + (ds < N ? ds : N - 1);
+            genotype_cell_general(C, R, S, O, s, n, lo < hi ? first_candidate(R.maxend, lo, hi, S.qbeg[s]) : lo, hi, cnt.data(), 1, err_cell);
+        }
+    memcpy(out->site_flags, flags.data(), Sn);
+    if (err == ~0ull) return GLX_OK;
+    const int code = (int)(err & 0xff);
+    return code == 101 ? GLX_E_UNSUPPORTED : -code;
+}
+
 extern "C" int glx_emu_general_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out) {
-    if (recs->n_datasets != sites->n_samples) return GLX_E_UNSUPPORTED;
-    for (uint32_t d = 0; d < recs->n_datasets; d++)
-        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) return GLX_E_UNSUPPORTED;
+    bool multi = recs->n_datasets != sites->n_samples;
+    for (uint32_t d = 0; !multi && d < recs->n_datasets; d++)
+        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) multi = true;
+    if (multi) return emu_multi_batch(cfg, recs, sites, out);
     DCfg C; DRecs R; DSites S; DOut O;
     unsigned long long err = ~0ull;
     bind(cfg, recs, sites, out, &err, C, R, S, O);
@@ -153,9 +207,15 @@ static void run_tiled_sig(const DCfg& C, const FastPlan& plan, const DRecs& R, c
 // the worklist hand-off are CUDA-only and are covered by the GPU tests.)
 extern "C" void glx_emu_stats_reset() { memset(g_emu_stats, 0, sizeof g_emu_stats); }
 extern "C" int glx_emu_tiled_batch(const glx_config* cfg, const glx_records* recs, const glx_sites* sites, glx_out* out, uint64_t* n_slow_out, int dynamic_only) {
-    if (recs->n_datasets != sites->n_samples) return GLX_E_UNSUPPORTED;
-    for (uint32_t d = 0; d < recs->n_datasets; d++)
-        if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) return GLX_E_UNSUPPORTED;
+    {  // a batch with multi-sample datasets has no tiled path: the device runs glx_cells_multi_kernel whatever the options
+        bool multi = recs->n_datasets != sites->n_samples;
+        for (uint32_t d = 0; !multi && d < recs->n_datasets; d++)
+            if (recs->ds_n_sample[d] != 1 || recs->sample_out[recs->ds_sample_off[d]] != (int32_t)d) multi = true;
+        if (multi) {
+            if (n_slow_out) *n_slow_out = 0;
+            return emu_multi_batch(cfg, recs, sites, out);
+        }
+    }
     DCfg C; DRecs R; DSites S; DOut O;
     unsigned long long err = ~0ull;
     bind(cfg, recs, sites, out, &err, C, R, S, O);

@@ -27,9 +27,11 @@ def _seq(rng, n):
     return "".join(rng.choice(BASES) for _ in range(n))
 
 
-def make_case(seed, preset=None):
+def make_case(seed, preset=None, multi=False):
+    """multi: datasets of one to three samples each (multi-sample gVCFs): every record carries all of its dataset's samples, each
+    with its own GT / GQ / DP / AD / PL / SB values under the record's shared alleles and FORMAT keys."""
     rng = random.Random(seed)
-    n_samples = rng.randint(1, 9)
+    n_samples = rng.randint(1, 9) if not multi else rng.randint(1, 5)
     region = (1000, 1000 + rng.randint(40, 160))
     ref_genome = _seq(rng, region[1] - region[0] + 64)
 
@@ -81,6 +83,7 @@ def make_case(seed, preset=None):
     datasets = []
     for n in range(n_samples):
         name = f"S{n:02d}"
+        ns = rng.randint(1, 3) if multi else 1
         rows = []
         pos = region[0]
         gatk = rng.random() < 0.5
@@ -94,13 +97,14 @@ def make_case(seed, preset=None):
                 for p2 in (s["beg"], s["beg"] + rng.randint(1, s["end"] - s["beg"] - 1)):
                     rb = refseq(p2, p2 + 1)
                     alt = rng.choice([b for b in BASES if b != rb])
-                    rows.append((p2, "\t".join(["chrF", str(p2 + 1), ".", rb, alt + "," + sym, "30", ".", ".", "GT:GQ:DP:AD:PL",
-                                                 f"0/1:{rng.randint(0, 99)}:{rng.randint(1, 60)}:{rng.randint(0, 30)},{rng.randint(0, 30)},0:30,0,300,99,300,990"])))
+                    rows.append((p2, "\t".join(["chrF", str(p2 + 1), ".", rb, alt + "," + sym, "30", ".", ".", "GT:GQ:DP:AD:PL"] +
+                                                [f"{'0/1' if k == 0 or rng.random() < 0.7 else rng.choice(['0/0', '1/1', './.'])}:{rng.randint(0, 99)}:{rng.randint(1, 60)}:"
+                                                 f"{rng.randint(0, 30)},{rng.randint(0, 30)},0:30,0,300,99,300,990" for k in range(ns)])))
                 pos = s["end"]
                 continue
             if site_here and r < 0.55:
                 s = site_here[0]
-                variants = rng.randint(1, 2) if rng.random() < 0.12 else 1
+                variants = rng.randint(1, 2) if rng.random() < (0.4 if multi else 0.12) else 1
                 for _ in range(variants):
                     rep = rng.random()
                     beg, ref = s["beg"], s["ref"]
@@ -117,33 +121,41 @@ def make_case(seed, preset=None):
                     has_sym = rng.random() < 0.8
                     als = [ref] + alts + ([sym] if has_sym else [])
                     na = len(als)
-                    g = rng.random()
-                    if g < 0.08:
-                        gt = str(rng.randint(0, na - 1 - (1 if has_sym else 0)))  # haploid
-                    else:
-                        a0 = rng.randint(0, len(alts))
-                        a1 = rng.randint(0, len(alts))
-                        sep = "|" if rng.random() < 0.1 else "/"
-                        gt = f"{'.' if rng.random() < 0.06 else a0}{sep}{'.' if rng.random() < 0.06 else a1}"
                     nG = na * (na + 1) // 2
-                    pl = [rng.choice([0, 0, 3, 10, 20, 50, 99, 300, 990]) for _ in range(nG)]
-                    if rng.random() < 0.1:
-                        pl[rng.randrange(nG)] = "."
-                    ad = [rng.randint(0, 40) for _ in range(na)]
-                    fmt, vals = ["GT"], [gt]
+                    fmt = ["GT"]
                     if rng.random() < 0.995:
-                        fmt.append("GQ"); vals.append(str(rng.randint(0, 99)))
+                        fmt.append("GQ")
                     if rng.random() < 0.9:
-                        fmt.append("DP"); vals.append(str(rng.randint(0, 80)))
+                        fmt.append("DP")
                     if rng.random() < 0.9:
-                        fmt.append("AD"); vals.append(",".join(map(str, ad)))
+                        fmt.append("AD")
                     if rng.random() < 0.99:
-                        fmt.append("PL"); vals.append(",".join(map(str, pl)))
+                        fmt.append("PL")
                     if gatk and rng.random() < 0.7:
-                        fmt.append("SB"); vals.append(",".join(str(rng.randint(0, 30)) for _ in range(4)))
+                        fmt.append("SB")
+                    hap_rec = ns == 1 and rng.random() < 0.08  # (a multi-sample record keeps one ploidy)
+                    all00 = multi and rng.random() < 0.25          # a variant record nobody in the dataset carries
+                    cols = []
+                    for k in range(ns):
+                        if hap_rec:
+                            gt = str(rng.randint(0, na - 1 - (1 if has_sym else 0)))  # haploid
+                        else:
+                            a0 = rng.randint(0, len(alts))
+                            a1 = rng.randint(0, len(alts))
+                            if all00 or (k > 0 and rng.random() < 0.35):
+                                a0 = a1 = 0  # other samples of the dataset are often hom-ref at the site
+                            sep = "|" if rng.random() < 0.1 else "/"
+                            gt = f"{'.' if rng.random() < 0.06 else a0}{sep}{'.' if rng.random() < 0.06 else a1}"
+                        pl = [rng.choice([0, 0, 3, 10, 20, 50, 99, 300, 990]) for _ in range(nG)]
+                        if rng.random() < 0.1:
+                            pl[rng.randrange(nG)] = "."
+                        ad = [rng.randint(0, 40) for _ in range(na)]
+                        vals = {"GT": gt, "GQ": str(rng.randint(0, 99)), "DP": str(rng.randint(0, 80)), "AD": ",".join(map(str, ad)),
+                                "PL": ",".join(map(str, pl)), "SB": ",".join(str(rng.randint(0, 30)) for _ in range(4))}
+                        cols.append(":".join(vals[f] for f in fmt))
                     qual = rng.choice([".", "0", "12.5", "50", "50", "468.22"])
                     flt = rng.choice([".", "PASS", "PASS", "LowQual", "RefCall"])
-                    rows.append((beg, "\t".join(["chrF", str(beg + 1), ".", ref, ",".join(als[1:]), qual, flt, ".", ":".join(fmt), ":".join(vals)])))
+                    rows.append((beg, "\t".join(["chrF", str(beg + 1), ".", ref, ",".join(als[1:]), qual, flt, ".", ":".join(fmt)] + cols)))
                 pos = s["end"] if rng.random() < 0.8 else s["beg"] + 1
                 continue
             if r < 0.93:
@@ -151,23 +163,29 @@ def make_case(seed, preset=None):
                 nxt = [s["beg"] for s in sites if pos < s["beg"] < pos + ln]
                 if nxt and rng.random() < 0.6:
                     ln = nxt[0] - pos
-                gt = rng.choice(["0/0", "0/0", "0/0", "0/0", "./.", "0", "0|0"])
-                fmt, vals = ["GT"], [gt]
+                fmt = ["GT"]
                 if rng.random() < 0.95:
-                    fmt.append("GQ"); vals.append(str(rng.randint(0, 60)))
+                    fmt.append("GQ")
                 if rng.random() < 0.998:
-                    fmt.append("MIN_DP"); vals.append(str(rng.randint(0, 50)))
+                    fmt.append("MIN_DP")
                 if rng.random() < 0.5:
-                    fmt.append("DP"); vals.append(str(rng.randint(0, 60)))
+                    fmt.append("DP")
                 if rng.random() < 0.9:
-                    fmt.append("PL"); vals.append(rng.choice(["0,30,300", "0,0,0", "0,9,90", "20,0,50", "0,.,."]))
+                    fmt.append("PL")
+                cols = []
+                for k in range(ns):
+                    gt = rng.choice(["0/0", "0/0", "0/0", "0/0", "./.", "0", "0|0"] if ns == 1 else ["0/0"] * 12 + ["./.", "0|0"])
+                    vals = {"GT": gt, "GQ": str(rng.randint(0, 60)), "MIN_DP": str(rng.randint(0, 50)), "DP": str(rng.randint(0, 60)),
+                            "PL": rng.choice(["0,30,300", "0,0,0", "0,9,90", "20,0,50", "0,.,."])}
+                    cols.append(":".join(vals[f] for f in fmt))
                 alt = sym if rng.random() < 0.95 else "."
-                rows.append((pos, "\t".join(["chrF", str(pos + 1), ".", refseq(pos, pos + 1), alt, ".", ".", f"END={pos + ln}", ":".join(fmt), ":".join(vals)])))
+                rows.append((pos, "\t".join(["chrF", str(pos + 1), ".", refseq(pos, pos + 1), alt, ".", ".", f"END={pos + ln}", ":".join(fmt)] + cols)))
                 pos += ln
             else:
                 pos += rng.randint(1, 20)  # coverage gap
         rows.sort(key=lambda x: x[0])
-        body = HEADER + "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + name + "\n" + "\n".join(r[1] for r in rows) + "\n"
+        names = [name] if ns == 1 else [f"{name}_{k}" for k in range(ns)]
+        body = HEADER + "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n" + "\n".join(r[1] for r in rows) + "\n"
         datasets.append((name, body))
 
     preset = preset or rng.choice(["DeepVariant", "gatk", "DeepVariant_unfiltered", "gatk_unfiltered", "weCall"])
@@ -183,10 +201,10 @@ def make_case(seed, preset=None):
     return sites_text, datasets, preset, toggles
 
 
-def build_batch(seed, preset=None):
+def build_batch(seed, preset=None, multi=False):
     """-> glnexus_b200.Batch for the seed (config = preset text with the toggles applied)."""
     from glnexus_b200 import Batch, preset_text
-    sites_text, datasets, preset, toggles = make_case(seed, preset)
+    sites_text, datasets, preset, toggles = make_case(seed, preset, multi)
     cfg_lines = []
     for line in preset_text(preset).split("\n"):
         key = line.split(" ")[0]

@@ -59,3 +59,51 @@ def test_fuzz_gpu(built, path):
             n_ok += 1
     ctx.close()
     assert n_ok >= 100
+
+
+# ---- multi-sample datasets (one to three samples per gVCF): glx_cells_multi_kernel's logic vs the oracle ----
+def _multi_cases(seeds):
+    n_multi = 0
+    for seed in seeds:
+        b = fuzz_cases.build_batch(seed, multi=True)
+        assert b.device_supported
+        n_multi += not b.has_fast_path
+        yield seed, b
+    assert n_multi >= len(seeds) // 2  # most cases must really hold a multi-sample dataset
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_fuzz_multi_sample_emu(built, chunk):
+    n_ok = 0
+    for seed, b in _multi_cases(range(5000 + chunk * 60, 5000 + chunk * 60 + 60)):
+        orc, ref = _oracle(b)
+        got = b.alloc_out()
+        rc = emu_lib.general_batch(b, got)
+        assert rc == orc, f"seed {seed}: status {rc} vs oracle {orc}"
+        if orc == 0:
+            d = compare_outs(got, ref, b.n_fields)
+            assert not d, f"seed {seed}:\n" + "\n".join(d)
+            n_ok += 1
+    assert n_ok >= 20
+
+
+@pytest.mark.gpu
+def test_fuzz_multi_sample_gpu(built):
+    from glnexus_b200 import Context, GlxError
+    ctx = Context(0)
+    n_ok = 0
+    for seed, b in _multi_cases(range(6000, 6200)):
+        orc, ref = _oracle(b)
+        got = b.alloc_out(pinned=False)
+        try:
+            ctx.genotype_batch(b, got)
+            rc = 0
+        except GlxError as e:
+            rc = e.code
+        assert rc == orc, f"seed {seed}: status {rc} vs oracle {orc}"
+        if orc == 0:
+            d = compare_outs(got, ref, b.n_fields)
+            assert not d, f"seed {seed}:\n" + "\n".join(d)
+            n_ok += 1
+    ctx.close()
+    assert n_ok >= 60
