@@ -141,6 +141,7 @@ struct glx_dev_batch {
     GlxBcfState bcf;
     void* wire_sums = nullptr;     // wire upload: block sums of the record scan / of the allele-length scan (inside the input arena)
     void* wire_al_sums = nullptr;
+    void* wire_shape_scratch = nullptr;  // GLX_WF_SHAPES: expanded GT pairs [2R] + column lengths [C][R] (inside the input arena)
     DCfg cfg;
     DRecs R;
     DSites S;

@@ -821,6 +821,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         const size_t nab = (recs->n_al + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS) + 1;
         add((const void*)nullptr, nb * sizeof(uint3x), &d->wire_sums);
         add((const void*)nullptr, nab * sizeof(uint3x), &d->wire_al_sums);
+        if (wire->flags & GLX_WF_SHAPES) add((const void*)nullptr, (size_t)Rn * (2 + C), &d->wire_shape_scratch);  // GT pairs + column lengths, expanded
     }
     size_t total = 0;
     size_t copied = 0;
@@ -863,8 +864,24 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
         // columns that travel as they are
         R.ds_rec_off = reinterpret_cast<const uint64_t*>(wire_dev + wire->off[GLX_WS_DS_REC_OFF]);
         R.beg = reinterpret_cast<const int32_t*>(wire_dev + wire->off[GLX_WS_BEG]);
-        R.flags = reinterpret_cast<const uint8_t*>(wire_dev + wire->off[GLX_WS_FLAGS]);
-        R.n_allele = reinterpret_cast<const uint8_t*>(wire_dev + wire->off[GLX_WS_NALLELE]);
+        if (wire->flags & GLX_WF_SHAPES) {
+            // (flags, n_allele, GT pair, column lengths) come as one shape code per record: expand them first — flags and n_allele into
+            // the arrays the arena holds for them anyway, the GT pairs and column lengths into scratch the record pass reads from
+            if (!(wire->flags & GLX_WF_GT8) || !(wire->flags & GLX_WF_COLLEN8) || wire->n_shapes > 255) return bail(cudaErrorInvalidValue, "glx_upload_wire: malformed shape sections");
+            uint8_t* scratch = reinterpret_cast<uint8_t*>(d->wire_shape_scratch);
+            W.x_flags = R.flags;
+            W.x_nal = R.n_allele;
+            W.x_gt8 = scratch;
+            W.x_collen8 = scratch + 2 * Rn;
+            W.n_shapes = wire->n_shapes;
+            W.n_shape_exc = wire->n_shape_exc;
+            if (Rn)
+                glx_wire_shapes_kernel<<<(unsigned)std::min<uint64_t>((Rn + 255) / 256, (uint64_t)ctx->sm_count * 8), 256, 0, up>>>(
+                    W, const_cast<uint8_t*>(R.flags), const_cast<uint8_t*>(R.n_allele), scratch, scratch + 2 * Rn);
+        } else {
+            R.flags = reinterpret_cast<const uint8_t*>(wire_dev + wire->off[GLX_WS_FLAGS]);
+            R.n_allele = reinterpret_cast<const uint8_t*>(wire_dev + wire->off[GLX_WS_NALLELE]);
+        }
         R.al_pool = wire_dev + wire->off[GLX_WS_AL_POOL];
         const unsigned nb = (unsigned)((Rn + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS));
         const unsigned nab = (unsigned)((recs->n_al + GLX_WIRE_BLOCK * GLX_WIRE_ITEMS - 1) / (GLX_WIRE_BLOCK * GLX_WIRE_ITEMS));

@@ -13,6 +13,14 @@ struct DWire {
     const uint8_t* base;  // device copy of the whole wire buffer
     uint64_t off[GLX_WS_COUNT];
     uint64_t col_val_off[GLX_MAX_COLS];  // byte offset of column c's scalar values
+    // GLX_WF_SHAPES: the four per-record sections below are not on the wire; glx_wire_shapes_kernel writes them here first
+    const uint8_t *x_flags, *x_nal, *x_gt8, *x_collen8;
+    uint32_t n_shapes;
+    uint64_t n_shape_exc;
+    __host__ __device__ const uint8_t* sec_flags() const { return x_flags ? x_flags : base + off[GLX_WS_FLAGS]; }
+    __host__ __device__ const uint8_t* sec_nal() const { return x_nal ? x_nal : base + off[GLX_WS_NALLELE]; }
+    __host__ __device__ const uint8_t* sec_gt() const { return x_gt8 ? x_gt8 : base + off[GLX_WS_GT]; }
+    __host__ __device__ const uint8_t* sec_collen() const { return x_collen8 ? x_collen8 : base + off[GLX_WS_COL_LEN]; }
 };
 
 #define GLX_WIRE_BLOCK 256
@@ -25,21 +33,56 @@ __device__ __forceinline__ uint3x add3(uint3x x, uint3x y) { return uint3x{x.a +
 
 __device__ __forceinline__ uint32_t wire_col_len(const DWire& W, uint64_t c, uint64_t r) {
     if (W.flags & GLX_WF_COLLEN8) {
-        const uint8_t v = (W.base + W.off[GLX_WS_COL_LEN])[c * W.n_records + r];
+        const uint8_t v = W.sec_collen()[c * W.n_records + r];
         return v >= 0xFD ? 0xFF00u | v : v;
     }
-    return reinterpret_cast<const uint16_t*>(W.base + W.off[GLX_WS_COL_LEN])[c * W.n_records + r];
+    return reinterpret_cast<const uint16_t*>(W.sec_collen())[c * W.n_records + r];
 }
 // what record r adds to the three running sums
 __device__ __forceinline__ uint3x wire_record_units(const DWire& W, uint64_t r) {
-    const uint8_t fl = (W.base + W.off[GLX_WS_FLAGS])[r];
+    const uint8_t fl = W.sec_flags()[r];
     const bool var = !(fl & GLX_RF_IS_REF);
     uint32_t pool = 0;
     for (uint32_t c = 0; c < W.n_cols; c++) {
         const uint32_t len = wire_col_len(W, c, r);
         if (len < 0xFFF0 && len != 1) pool += len;
     }
-    return uint3x{var ? 1u : 0u, var ? (uint32_t)(W.base + W.off[GLX_WS_NALLELE])[r] : 0u, pool};
+    return uint3x{var ? 1u : 0u, var ? (uint32_t)W.sec_nal()[r] : 0u, pool};
+}
+
+// GLX_WF_SHAPES, pass 0: a record's shape code -> its (flags, n_allele, GT pair, column lengths) in the layout the sections have
+// without shapes (uint8 columns), so that everything after reads them as if they had travelled. The table (<= 255 rows of
+// 4 + n_cols bytes) sits in shared memory; a record with code 0xFF finds its own row by its index in the sorted exception list.
+__global__ void __launch_bounds__(256) glx_wire_shapes_kernel(const DWire W, uint8_t* __restrict__ flags, uint8_t* __restrict__ nal, uint8_t* __restrict__ gt8,
+                                                              uint8_t* __restrict__ collen8) {
+    __shared__ uint8_t s_table[255 * (4 + GLX_MAX_COLS)];
+    const uint32_t row = 4 + W.n_cols;
+    const uint8_t* table = W.base + W.off[GLX_WS_SHAPE_TABLE];
+    for (uint32_t i = threadIdx.x; i < W.n_shapes * row; i += blockDim.x) s_table[i] = table[i];
+    __syncthreads();
+    const uint8_t* code = W.base + W.off[GLX_WS_SHAPE];
+    const uint32_t* exc_idx = reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_SHAPE_EXC_IDX]);
+    const uint8_t* exc_rows = W.base + W.off[GLX_WS_SHAPE_EXC];
+    const uint64_t R = W.n_records;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = code[r];
+        const uint8_t* p;
+        if (k != 0xFF) p = s_table + k * row;
+        else {
+            uint64_t lo = 0, hi = W.n_shape_exc;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (exc_idx[mid] < (uint32_t)r) lo = mid + 1;
+                else hi = mid;
+            }
+            p = exc_rows + lo * row;
+        }
+        flags[r] = p[0];
+        nal[r] = p[1];
+        gt8[2 * r] = p[2];
+        gt8[2 * r + 1] = p[3];
+        for (uint32_t c = 0; c < W.n_cols; c++) collen8[(size_t)c * R + r] = p[4 + c];
+    }
 }
 
 // block-wide exclusive scan of one uint3x per thread (256 threads); returns the thread's exclusive prefix, total in *tot
@@ -148,8 +191,8 @@ __global__ void __launch_bounds__(GLX_WIRE_BLOCK) glx_wire_records_kernel(const 
     uint3x tot;
     uint3x run = add3(block_scan3(t, &tot), block_sums[blockIdx.x]);
     const int32_t* beg = reinterpret_cast<const int32_t*>(W.base + W.off[GLX_WS_BEG]);
-    const uint8_t* flags = W.base + W.off[GLX_WS_FLAGS];
-    const uint8_t* nal = W.base + W.off[GLX_WS_NALLELE];
+    const uint8_t* flags = W.sec_flags();
+    const uint8_t* nal = W.sec_nal();
     const uint64_t R = W.n_records;
     for (uint32_t i = 0; i < GLX_WIRE_ITEMS; i++, run = add3(run, u[i - 1])) {
         const uint64_t r = r0 + i;
@@ -160,12 +203,12 @@ __global__ void __launch_bounds__(GLX_WIRE_BLOCK) glx_wire_records_kernel(const 
         O.end[r] = e;
         O.maxend[r] = e;  // the listed exceptions are patched afterwards
         if (W.flags & GLX_WF_GT8) {
-            const uint8_t* g = W.base + W.off[GLX_WS_GT] + 2 * r;
+            const uint8_t* g = W.sec_gt() + 2 * r;
             const uint32_t a = g[0] == 0xFF ? (uint32_t)(uint16_t)GLX_GT16_VECTOR_END : (uint32_t)g[0] << 1;
             const uint32_t b = g[1] == 0xFF ? (uint32_t)(uint16_t)GLX_GT16_VECTOR_END : (uint32_t)g[1] << 1;
             O.gt[r] = a | b << 16;
         } else
-            O.gt[r] = reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_GT])[r];
+            O.gt[r] = reinterpret_cast<const uint32_t*>(W.sec_gt())[r];
         const bool var = !(flags[r] & GLX_RF_IS_REF);
         O.qual[r] = var ? reinterpret_cast<const float*>(W.base + W.off[GLX_WS_QUAL])[run.a] : 0.0f;
         O.filt[r] = (W.flags & GLX_WF_FILT_VARIANT) ? (var ? reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_FILT])[run.a] : 0u)

@@ -1,7 +1,10 @@
 // glx_wire_host.cc — builds the compact wire form of a packed batch's record store (glx_wire, include/glx.h): what crosses
 // PCIe instead of the kernel-facing columns. SURVEY.md §8f N2 (start): the packer's output at the width the data needs.
+#include <algorithm>
 #include <cstring>
+#include <string>
 #include <thread>
+#include <unordered_map>
 
 #include "glx_host.hpp"
 
@@ -125,6 +128,81 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
     h.n_maxend_exc = exc.size() / 2;
     h.flags = (len16 ? GLX_WF_LEN16 : 0) | (gt8 ? GLX_WF_GT8 : 0) | (collen8 ? GLX_WF_COLLEN8 : 0) | (pool16 ? GLX_WF_POOL16 : 0) |
               (filt_variant ? GLX_WF_FILT_VARIANT : 0) | (allen16 ? GLX_WF_ALLEN16 : 0);
+    // ---- record shapes: (flags, n_allele, GT pair, column lengths) as one byte per record (GLX_WF_SHAPES) ----
+    const size_t row_bytes = 4 + C;
+    std::vector<uint8_t> shape_code, shape_table, shape_exc;
+    std::vector<uint32_t> shape_exc_idx;
+    const bool shapes = gt8 && collen8 && R > 0;
+    auto shape_row = [&](uint64_t i, uint8_t* row) {
+        row[0] = r.flags[i];
+        row[1] = r.n_allele[i];
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
+            row[2 + hlf] = g == GLX_GT16_VECTOR_END ? (uint8_t)0xFF : (uint8_t)(g >> 1);
+        }
+        for (uint64_t c = 0; c < C; c++) {
+            const uint16_t cl = r.col_len[c * R + i];
+            row[4 + c] = cl >= 0xFFF0 ? (uint8_t)(cl & 0xFF) : (uint8_t)cl;
+        }
+    };
+    if (shapes) {
+        // pass 1: how often each shape occurs (runs of equal shapes — consecutive reference bands — cost one comparison each)
+        std::vector<std::unordered_map<std::string, uint64_t>> counts(T);
+        parallel_chunks(R, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
+            std::string prev(row_bytes, '\0'), cur(row_bytes, '\0');
+            uint64_t* slot = nullptr;
+            for (uint64_t i = lo; i < hi; i++) {
+                shape_row(i, reinterpret_cast<uint8_t*>(&cur[0]));
+                if (!slot || cur != prev) {
+                    slot = &counts[t][cur];
+                    prev = cur;
+                }
+                ++*slot;
+            }
+        });
+        std::unordered_map<std::string, uint64_t> all;
+        for (auto& m : counts)
+            for (auto& kv : m) all[kv.first] += kv.second;
+        std::vector<std::pair<uint64_t, std::string>> order;
+        order.reserve(all.size());
+        for (auto& kv : all) order.emplace_back(kv.second, kv.first);
+        std::sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+        const size_t n_shapes = std::min<size_t>(order.size(), 255);
+        std::unordered_map<std::string, uint8_t> code_of;
+        shape_table.resize(n_shapes * row_bytes);
+        for (size_t k = 0; k < n_shapes; k++) {
+            code_of[order[k].second] = (uint8_t)k;
+            memcpy(&shape_table[k * row_bytes], order[k].second.data(), row_bytes);
+        }
+        // pass 2: the codes; records of rarer shapes keep their row (in record order)
+        shape_code.resize(R);
+        std::vector<std::vector<uint32_t>> exc_idx(T);
+        std::vector<std::vector<uint8_t>> exc_rows(T);
+        parallel_chunks(R, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
+            std::string prev(row_bytes, '\0'), cur(row_bytes, '\0');
+            int code = -2;
+            for (uint64_t i = lo; i < hi; i++) {
+                shape_row(i, reinterpret_cast<uint8_t*>(&cur[0]));
+                if (code == -2 || cur != prev) {
+                    auto it = code_of.find(cur);
+                    code = it == code_of.end() ? 0xFF : it->second;
+                    prev = cur;
+                }
+                shape_code[i] = (uint8_t)code;
+                if (code == 0xFF) {
+                    exc_idx[t].push_back((uint32_t)i);
+                    exc_rows[t].insert(exc_rows[t].end(), cur.begin(), cur.end());
+                }
+            }
+        });
+        for (unsigned t = 0; t < T; t++) {  // (chunks are ascending record ranges: the concatenation stays sorted)
+            shape_exc_idx.insert(shape_exc_idx.end(), exc_idx[t].begin(), exc_idx[t].end());
+            shape_exc.insert(shape_exc.end(), exc_rows[t].begin(), exc_rows[t].end());
+        }
+        h.flags |= GLX_WF_SHAPES;
+        h.n_shapes = (uint32_t)n_shapes;
+        h.n_shape_exc = shape_exc_idx.size();
+    }
     // ---- layout ----
     size_t off = align16(sizeof(glx_wire));
     auto place = [&](int sec, size_t bytes) {
@@ -136,25 +214,38 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
     place(GLX_WS_DS_REC_OFF, (D + 1) * 8);
     place(GLX_WS_BEG, R * 4);
     place(GLX_WS_LEN, R * (len16 ? 2 : 4));
-    place(GLX_WS_FLAGS, R);
-    place(GLX_WS_NALLELE, R);
-    place(GLX_WS_GT, R * (gt8 ? 2 : 4));
+    place(GLX_WS_FLAGS, shapes ? 0 : R);
+    place(GLX_WS_NALLELE, shapes ? 0 : R);
+    place(GLX_WS_GT, shapes ? 0 : R * (gt8 ? 2 : 4));
     place(GLX_WS_QUAL, n_variant * 4);
     place(GLX_WS_FILT, (filt_variant ? n_variant : R) * 4);
-    place(GLX_WS_COL_LEN, C * R * (collen8 ? 1 : 2));
+    place(GLX_WS_COL_LEN, shapes ? 0 : C * R * (collen8 ? 1 : 2));
     place(GLX_WS_COL_VAL, colval_bytes);
     place(GLX_WS_POOL, r.n_pool * (pool16 ? 2 : 4));
     place(GLX_WS_AL_LEN, r.n_al * (allen16 ? 2 : 4));
     place(GLX_WS_AL_POOL, r.n_al_pool);
     place(GLX_WS_MAXEND_EXC, exc.size() * 4);
+    place(GLX_WS_SHAPE, shape_code.size());
+    place(GLX_WS_SHAPE_TABLE, shape_table.size());
+    place(GLX_WS_SHAPE_EXC_IDX, shape_exc_idx.size() * 4);
+    place(GLX_WS_SHAPE_EXC, shape_exc.size());
     h.n_bytes = off;
     w.assign(off, 0);
     memcpy(w.data(), &h, sizeof h);
     uint8_t* p = w.data();
     memcpy(p + h.off[GLX_WS_DS_REC_OFF], r.ds_rec_off, (D + 1) * 8);
     memcpy(p + h.off[GLX_WS_BEG], r.beg, R * 4);
-    memcpy(p + h.off[GLX_WS_FLAGS], r.flags, R);
-    memcpy(p + h.off[GLX_WS_NALLELE], r.n_allele, R);
+    if (!shapes) {
+        memcpy(p + h.off[GLX_WS_FLAGS], r.flags, R);
+        memcpy(p + h.off[GLX_WS_NALLELE], r.n_allele, R);
+    } else {
+        memcpy(p + h.off[GLX_WS_SHAPE], shape_code.data(), shape_code.size());
+        memcpy(p + h.off[GLX_WS_SHAPE_TABLE], shape_table.data(), shape_table.size());
+        if (!shape_exc_idx.empty()) {
+            memcpy(p + h.off[GLX_WS_SHAPE_EXC_IDX], shape_exc_idx.data(), shape_exc_idx.size() * 4);
+            memcpy(p + h.off[GLX_WS_SHAPE_EXC], shape_exc.data(), shape_exc.size());
+        }
+    }
     {
         uint16_t* l16 = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_LEN]);
         uint32_t* l32 = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_LEN]);
@@ -172,7 +263,8 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
                 const uint32_t len = (uint32_t)(r.end[i] - r.beg[i]);
                 if (len16) l16[i] = (uint16_t)len;
                 else l32[i] = len;
-                if (gt8) {
+                if (shapes) {
+                } else if (gt8) {
                     for (int hlf = 0; hlf < 2; hlf++) {
                         const int16_t g = (int16_t)(r.gt[i] >> (16 * hlf));
                         g8[2 * i + hlf] = g == GLX_GT16_VECTOR_END ? (uint8_t)0xFF : (uint8_t)(g >> 1);
@@ -191,7 +283,8 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
                 int32_t* d32 = reinterpret_cast<int32_t*>(p + col_off[c]);
                 for (uint64_t i = lo; i < hi; i++) {
                     const uint16_t cl = r.col_len[c * R + i];
-                    if (collen8) c8[c * R + i] = cl >= 0xFFF0 ? (uint8_t)(cl & 0xFF) : (uint8_t)cl;  // 0xFFFF -> 0xFF, 0xFFFE -> 0xFE, 0xFFFD -> 0xFD
+                    if (shapes) {
+                    } else if (collen8) c8[c * R + i] = cl >= 0xFFF0 ? (uint8_t)(cl & 0xFF) : (uint8_t)cl;  // 0xFFFF -> 0xFF, 0xFFFE -> 0xFE, 0xFFFD -> 0xFD
                     else c16[c * R + i] = cl;
                     if (h.col_w[c] == 2) d16[i] = cl == 1 ? to16(r.col_val[c * R + i]) : (int16_t)0;
                     else if (h.col_w[c] == 4) d32[i] = cl == 1 ? r.col_val[c * R + i] : 0;

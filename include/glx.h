@@ -42,7 +42,7 @@ enum {
     GLX_E_NOT_IMPLEMENTED = -6,
     GLX_E_ABORTED = -7,
     GLX_E_CUDA = -100,       /* CUDA runtime error (message in glx_last_error) */
-    GLX_E_UNSUPPORTED = -101 /* input outside what the device path accepts (e.g. multi-sample dataset) */
+    GLX_E_UNSUPPORTED = -101 /* input outside what the device path accepts (a dataset only partly in the sample set, > 2^32 cells) */
 };
 
 /* ---- sentinels, exactly htslib's (htslib/vcf.h) ---- */
@@ -108,7 +108,8 @@ typedef struct glx_config {
 
 /* Columnar record store: every gVCF record of one contig range, decoded once.
  * Records of dataset d are [ds_rec_off[d], ds_rec_off[d+1]), sorted by (beg,end) (range::operator<).
- * The device path requires single-sample datasets with sample_out[d]==d. */
+ * Single-sample datasets with sample_out[d]==d take the fast kernels (and have a wire form); a store with multi-sample or
+ * reordered datasets takes the general multi-sample kernel (every sample of every dataset must be in the sample set, once). */
 typedef struct glx_records {
     uint32_t n_datasets, n_samples_out, n_cols, _pad;
     uint64_t n_records;
@@ -152,20 +153,28 @@ typedef struct glx_records {
  * builds it from a packed batch; glx_upload_wire_on expands it on the device into exactly the arrays glx_upload_on would copy.
  * One contiguous buffer: this header, then the sections at off[GLX_WS_*] (each 16-byte aligned). */
 enum { GLX_WS_DS_REC_OFF = 0, GLX_WS_BEG, GLX_WS_LEN, GLX_WS_FLAGS, GLX_WS_NALLELE, GLX_WS_GT, GLX_WS_QUAL, GLX_WS_FILT, GLX_WS_COL_LEN, GLX_WS_COL_VAL,
-       GLX_WS_POOL, GLX_WS_AL_LEN, GLX_WS_AL_POOL, GLX_WS_MAXEND_EXC, GLX_WS_COUNT };
+       GLX_WS_POOL, GLX_WS_AL_LEN, GLX_WS_AL_POOL, GLX_WS_MAXEND_EXC, GLX_WS_SHAPE, GLX_WS_SHAPE_TABLE, GLX_WS_SHAPE_EXC_IDX, GLX_WS_SHAPE_EXC, GLX_WS_COUNT };
 enum {
     GLX_WF_LEN16 = 1,          /* end - beg as uint16 (else uint32) */
     GLX_WF_GT8 = 2,            /* GT pair as two uint8: htslib GT int / 2, 0xFF = vector end (else the uint32 of glx_records.gt) */
     GLX_WF_COLLEN8 = 4,        /* col_len as uint8: 0xFF absent, 0xFE type clash, 0xFD length error (else uint16) */
     GLX_WF_POOL16 = 8,         /* value pool as int16 with BCF's 16-bit sentinels (else int32) */
     GLX_WF_FILT_VARIANT = 16,  /* FILTER masks only for non-reference records (no lifted field reads FILTER) */
-    GLX_WF_ALLEN16 = 32        /* allele lengths as uint16 (else uint32) */
+    GLX_WF_ALLEN16 = 32,       /* allele lengths as uint16 (else uint32) */
+    GLX_WF_SHAPES = 64         /* a record's (flags, n_allele, GT pair, column lengths) travel as ONE byte: its row of the batch's shape
+                                  table (GLX_WS_SHAPE_TABLE: n_shapes <= 255 rows of 4 + n_cols bytes {flags, n_allele, gt0, gt1, col_len8[]},
+                                  the batch's commonest shapes), 0xFF = the record's own row is in GLX_WS_SHAPE_EXC, found by its index in
+                                  the sorted GLX_WS_SHAPE_EXC_IDX. The FLAGS / NALLELE / GT / COL_LEN sections are then absent (needs
+                                  GLX_WF_GT8 and GLX_WF_COLLEN8): reference bands and the few genotype patterns of a cohort are a few
+                                  dozen shapes, so this takes 3 + n_cols bytes off every record */
 };
 #define GLX_WIRE_MAGIC 0x57584c47u /* "GLXW" */
 typedef struct glx_wire {
     uint32_t magic, flags;
     uint64_t n_bytes; /* the whole buffer, header included */
     uint64_t n_records, n_variant, n_al, n_al_pool, n_pool, n_maxend_exc;
+    uint64_t n_shape_exc; /* GLX_WF_SHAPES: records with code 0xFF */
+    uint32_t n_shapes, _pad;
     uint32_t n_datasets, n_cols;
     uint8_t col_w[GLX_MAX_COLS]; /* bytes per scalar value of column c on the wire: 0 (the column has no scalar entry), 2 or 4 */
     uint64_t off[GLX_WS_COUNT];

@@ -514,3 +514,48 @@ extern "C" int glx_emu_bgzf(const glx_config* cfg, const glx_sites* sites, const
     *n_bytes = all.size();
     return 0;
 }
+
+// GLX_WF_SHAPES (include/glx.h): decode every record's shape code the way glx_wire_shapes_kernel does and compare with the record
+// store the wire form was built from. Returns the number of records that differ, or -1 when the wire form carries no shapes;
+// *n_exc / *n_shapes report how the batch was coded.
+extern "C" long long glx_emu_wire_shapes_check(const glx_wire* w, const glx_records* recs, uint64_t* n_shapes, uint64_t* n_exc) {
+    if (!(w->flags & GLX_WF_SHAPES)) return -1;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(w);
+    const uint64_t R = w->n_records, C = w->n_cols, row = 4 + C;
+    if (R != recs->n_records || C != recs->n_cols) return R + 1;
+    const uint8_t* code = base + w->off[GLX_WS_SHAPE];
+    const uint8_t* table = base + w->off[GLX_WS_SHAPE_TABLE];
+    const uint32_t* exc_idx = reinterpret_cast<const uint32_t*>(base + w->off[GLX_WS_SHAPE_EXC_IDX]);
+    const uint8_t* exc_rows = base + w->off[GLX_WS_SHAPE_EXC];
+    if (n_shapes) *n_shapes = w->n_shapes;
+    if (n_exc) *n_exc = w->n_shape_exc;
+    long long bad = 0;
+    for (uint64_t r = 0; r < R; r++) {
+        const uint8_t* p;
+        if (code[r] != 0xFF) {
+            if (code[r] >= w->n_shapes) {
+                bad++;
+                continue;
+            }
+            p = table + code[r] * row;
+        } else {
+            const uint32_t* it = std::lower_bound(exc_idx, exc_idx + w->n_shape_exc, (uint32_t)r);
+            if (it == exc_idx + w->n_shape_exc || *it != (uint32_t)r) {
+                bad++;
+                continue;
+            }
+            p = exc_rows + (it - exc_idx) * row;
+        }
+        bool ok = p[0] == recs->flags[r] && p[1] == recs->n_allele[r];
+        for (int h = 0; h < 2; h++) {
+            const int16_t g = (int16_t)(recs->gt[r] >> (16 * h));
+            ok = ok && p[2 + h] == (g == GLX_GT16_VECTOR_END ? (uint8_t)0xFF : (uint8_t)(g >> 1));
+        }
+        for (uint64_t c = 0; c < C; c++) {
+            const uint16_t cl = recs->col_len[c * R + r];
+            ok = ok && p[4 + c] == (cl >= 0xFFF0 ? (uint8_t)(cl & 0xFF) : (uint8_t)cl);
+        }
+        bad += !ok;
+    }
+    return bad;
+}

@@ -37,8 +37,19 @@ def lib():
         L.glx_emu_bcf_records.restype = C.c_int
         L.glx_emu_bgzf.argtypes = [vp, vp, vp, vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.glx_emu_bgzf.restype = C.c_int
+        L.glx_emu_wire_shapes_check.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.glx_emu_wire_shapes_check.restype = C.c_longlong
         _lib = L
     return _lib
+
+
+def wire_shapes_check(batch):
+    """(records whose decoded shape differs from the record store, shapes in the table, records coded as exceptions); the first is -1
+    when the batch's wire form carries no shape codes."""
+    ptr, _ = batch.wire()
+    ns, ne = C.c_uint64(), C.c_uint64()
+    bad = lib().glx_emu_wire_shapes_check(ptr, batch.records_ptr, C.byref(ns), C.byref(ne))
+    return bad, ns.value, ne.value
 
 
 def general_batch(batch, out):

@@ -1,0 +1,35 @@
+"""The wire form's record-shape coding (GLX_WF_SHAPES, include/glx.h) on the host: every record's one-byte code must decode —
+table row or its own exception row — to the flags, allele count, GT pair and column lengths of the record store it was built from.
+(The device-side expansion of the whole wire form is compared array by array in test_gpu_wire.py.)"""
+import pytest
+
+import emu_lib
+import fuzz_cases
+import golden_util as gu
+import synth_cases
+
+
+@pytest.mark.parametrize("shape,ns,nsites,region", [("c2", 300, 3000, 3000), ("c3", 200, 1500, 96000), ("c5", 200, 1500, 45000)])
+def test_wire_shapes_synth(built, shape, ns, nsites, region):
+    b = synth_cases.make(shape, n_samples=ns, n_sites=nsites, region_len=region)
+    bad, n_shapes, n_exc = emu_lib.wire_shapes_check(b)
+    assert bad == 0 and 0 < n_shapes <= 255
+    assert n_exc * 100 <= b.n_records  # a cohort's records are a few dozen shapes: next to none may need its own row
+    _, n_bytes = b.wire()
+    print(f"{shape}: {n_shapes} shapes, {n_exc} exceptions, {n_bytes / b.n_records:.1f} wire bytes per record")
+
+
+def test_wire_shapes_fuzz_and_golden(built):
+    n = 0
+    for seed in range(300, 360):
+        b = fuzz_cases.build_batch(seed)
+        bad, _, _ = emu_lib.wire_shapes_check(b)
+        assert bad in (0, -1), f"seed {seed}: {bad} records decode to another shape"
+        n += bad == 0
+    for name in gu.case_names():
+        for b in gu.batches_of_case(gu.load_case(name)):
+            if b.has_fast_path and b.n_records:
+                bad, _, _ = emu_lib.wire_shapes_check(b)
+                assert bad in (0, -1), f"{name}: {bad}"
+                n += bad == 0
+    assert n >= 60
