@@ -96,15 +96,6 @@ __device__ inline bool genotype_cell_variant(const DCfg& cfg, const FastPlan& pl
     int32_t pl_val, ad_val;
     if (!column(cfg.col_pl, pl_rv, pl_val) || !column(cfg.col_allele_dp, ad_rv, ad_val)) return false;
     if ((pl_rv > CAPG && pl_rv != 0x7fffffff) || (ad_rv > CAPA && ad_rv != 0x7fffffff)) return false;
-#if defined(__CUDACC__) && !defined(GLX_ABLATE_POOL_PREFETCH)
-    // every other vector column of the view (SB's four counts, ...) is read from the value pool by the field that lifts it, behind
-    // everything above: ask for its line now, with this round's loads (ncu: that first dependent load was 10 % of the stall samples)
-#pragma unroll
-    for (int j = 0; j < GLX_VIEW_COLS; j++) {
-        const uint32_t len = (uint32_t)clen[j];
-        if (len > 1 && len < 0xFFF0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.pool + cval[j]));
-    }
-#endif
     int32_t* const s_pl = sm;
     int32_t* const s_ad = sm + (size_t)CAPG * sms;
     {

@@ -342,16 +342,8 @@ __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant
         const uint32_t n_items = nw & GLX_NWORK_MASK;
         if ((nw >> 16) == n_items) continue;  // nothing left: the tiled kernel finished every entry of this region itself
         uint2* __restrict__ w = worklist + (size_t)reg * region_cells;
-#ifndef GLX_ABLATE_ENTRY_PIPELINE
-        uint2 e_next = threadIdx.x < n_items ? w[threadIdx.x] : make_uint2(0u, 0u);
-#endif
         for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
-#ifndef GLX_ABLATE_ENTRY_PIPELINE
-            const uint2 e = e_next;
-            if (it + blockDim.x < n_items) e_next = w[it + blockDim.x];  // the next entry travels while this cell is worked on
-#else
             const uint2 e = w[it];
-#endif
             if ((e.y & (GLX_WORK_SINGLE | GLX_WORK_DONE)) != GLX_WORK_SINGLE) continue;
             const uint32_t s = e.x / N, sample = e.x % N;
             const uint64_t first = R.ds_rec_off[sample] + (e.y & GLX_WORK_CURSOR);
@@ -963,7 +955,13 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     // ---- general-path scratch ----
     const int threads = 128;
     uint64_t want_blocks = (d->n_cells + threads - 1) / threads;
-    const uint64_t cap = (uint64_t)ctx->sm_count * 16;
+#ifndef GLX_GENERAL_BLOCKS_PER_SM
+#define GLX_GENERAL_BLOCKS_PER_SM 16
+#endif
+    // (the worklist pass walks regions block by block: with as many blocks as regions every region's few cells start at once instead
+    // of queueing behind the block's other regions — the kernel is a chain of dependent loads per cell; the scratch bound keeps it small)
+    uint64_t cap = (uint64_t)ctx->sm_count * GLX_GENERAL_BLOCKS_PER_SM;
+    while (cap > (uint64_t)ctx->sm_count * 16 && cap * threads * max_slots > (128ull << 20)) cap /= 2;
     d->general_blocks = (int)(want_blocks < cap ? (want_blocks ? want_blocks : 1) : cap);
     d->cnt_scratch_bytes = (size_t)d->general_blocks * threads * max_slots;
     e = ctx->take((void**)&d->cnt_scratch, &d->cnt_scratch_bytes);

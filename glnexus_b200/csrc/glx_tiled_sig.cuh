@@ -544,11 +544,8 @@ struct TiledLane {
 #ifndef GLX_FUSED_MIN_BLOCKS
 #define GLX_FUSED_MIN_BLOCKS 7  // 72 registers: the walk over the tile wants the occupancy more than the fused closed form wants registers
 #endif
-#ifndef GLX_UNFUSED_MIN_BLOCKS
-#define GLX_UNFUSED_MIN_BLOCKS 1
-#endif
 template <class Sig, int FUSE, int TS>
-__global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS : GLX_UNFUSED_MIN_BLOCKS) glx_cells_tiled_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
+__global__ void __launch_bounds__(GLX_TILE_THREADS, FUSE ? GLX_FUSED_MIN_BLOCKS : 1) glx_cells_tiled_sig_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
                                                                                const int32_t* __restrict__ blobs, const uint32_t* __restrict__ tile_cursors,
                                                                                uint2* __restrict__ worklist,
                                                                                uint32_t* __restrict__ n_work, uint32_t n_sample_blocks, uint32_t cta0) {
