@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(128) glx_cells_single_kernel(const DCfg cfg, c
 // Worklist, pass 0: the same cells as pass 1, through the record's view (glx_cell_variant.cuh): all loads of the closed
 // form issued up front. Finished cells get GLX_WORK_DONE; a record without a view is left to pass 1.
 #ifndef GLX_VARIANT_MIN_BLOCKS
-#define GLX_VARIANT_MIN_BLOCKS 6  // 80 registers; measured best for the 8-allele instantiation
+#define GLX_VARIANT_MIN_BLOCKS 5  // 96 registers, no spills (6: 80 registers with 72 B of spills, measured 2 % slower on the 8-allele instantiation)
 #endif
 template <int CAPA>
 __global__ void __launch_bounds__(128, GLX_VARIANT_MIN_BLOCKS) glx_cells_variant_kernel(const DCfg cfg, const FastPlan plan, const DRecs R, const DSites S, const DOut O,
@@ -956,7 +956,7 @@ static int upload_impl(glx_ctx* ctx, const glx_config* cfg, const glx_records* r
     const int threads = 128;
     uint64_t want_blocks = (d->n_cells + threads - 1) / threads;
 #ifndef GLX_GENERAL_BLOCKS_PER_SM
-#define GLX_GENERAL_BLOCKS_PER_SM 16
+#define GLX_GENERAL_BLOCKS_PER_SM 96
 #endif
     // (the worklist pass walks regions block by block: with as many blocks as regions every region's few cells start at once instead
     // of queueing behind the block's other regions — the kernel is a chain of dependent loads per cell; the scratch bound keeps it small)
@@ -1183,7 +1183,10 @@ int glx_launch(glx_ctx* ctx, glx_dev_batch* d, void* stream_) {
                 CU(cudaStreamWaitEvent(ws, ctx->chunk_ev[j], 0));
             }
             const uint32_t nreg = c1 - c0;
-            const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * 32 ? nreg : (uint32_t)ctx->sm_count * 32;
+#ifndef GLX_WORKLIST_BLOCKS_PER_SM
+#define GLX_WORKLIST_BLOCKS_PER_SM 96
+#endif
+            const uint32_t g1 = nreg < (uint32_t)ctx->sm_count * GLX_WORKLIST_BLOCKS_PER_SM ? nreg : (uint32_t)ctx->sm_count * GLX_WORKLIST_BLOCKS_PER_SM;
             if (d->profile && n_chunks == 1) CU(cudaEventRecord(d->ev[2], st));
             const uint32_t region_cells = d->tile_sites * d->samples_per_cta;
             if (d->decl_list) {
