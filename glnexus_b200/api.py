@@ -121,6 +121,8 @@ def lib():
     L.glxh_bgzf_eof.restype = C.c_int
     L.glxh_batch_wire.argtypes = [vp, C.POINTER(vp)]
     L.glxh_batch_wire.restype = C.c_int
+    L.glxh_debug_wire_shape_cap.argtypes = [C.c_uint32]
+    L.glxh_debug_wire_shape_cap.restype = None
     L.glx_upload_wire_on.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.glx_upload_wire_on.restype = C.c_int
     L.glx_debug_compare_records.argtypes = [vp, vp, vp, C.POINTER(C.c_uint32)]
@@ -813,3 +815,8 @@ def preset_text(name):
         return C.string_at(t.value).decode()
     finally:
         lib().glxh_free_text(t)
+
+
+def wire_shape_cap(cap=255):
+    """Test aid: rows of the shape table of wire forms built from now on (default and maximum 255)."""
+    lib().glxh_debug_wire_shape_cap(cap)

@@ -289,6 +289,7 @@ std::string bgzf_eof_block();
 
 // N2 (start): the compact wire form of the batch's record store (glx_wire, include/glx.h) — glx_wire_host.cc
 Status build_wire(const PackedBatch& b, std::vector<uint8_t>& wire);
+void set_wire_shape_cap(uint32_t cap);  // test aid: rows of the wire form's shape table (default and maximum 255)
 
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
 // [site_lo, site_hi) with every record its sites can touch.

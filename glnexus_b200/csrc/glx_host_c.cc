@@ -182,6 +182,8 @@ int glxh_batch_pin(glxh_batch* hb) {
     return rc;
 }
 
+void glxh_debug_wire_shape_cap(uint32_t cap) { glx::set_wire_shape_cap(cap); }
+
 int glxh_batch_wire(glxh_batch* hb, const glx_wire** wire) {
     if (!hb || !wire) return GLX_E_INVALID;
     if (hb->wire.empty()) {

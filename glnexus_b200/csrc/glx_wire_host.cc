@@ -1,6 +1,7 @@
 // glx_wire_host.cc — builds the compact wire form of a packed batch's record store (glx_wire, include/glx.h): what crosses
 // PCIe instead of the kernel-facing columns. SURVEY.md §8f N2 (start): the packer's output at the width the data needs.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -26,6 +27,11 @@ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 bool fits16(int32_t v) { return v == GLX_INT_MISSING || v == GLX_INT_VECTOR_END || (v >= -32760 && v <= 32767); }
 int16_t to16(int32_t v) { return v == GLX_INT_MISSING ? (int16_t)0x8000 : (v == GLX_INT_VECTOR_END ? (int16_t)0x8001 : (int16_t)v); }
 }  // namespace
+
+// rows of the shape table (GLX_WF_SHAPES): 255 = as many as a code byte can name; tests lower it so that records of rarer shapes
+// take the exception path on small inputs
+static std::atomic<uint32_t> g_shape_cap{255};
+void set_wire_shape_cap(uint32_t cap) { g_shape_cap = cap > 255 ? 255 : cap; }
 
 Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
     const glx_records& r = b.recs;
@@ -167,7 +173,7 @@ Status build_wire(const PackedBatch& b, std::vector<uint8_t>& w) {
         order.reserve(all.size());
         for (auto& kv : all) order.emplace_back(kv.second, kv.first);
         std::sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
-        const size_t n_shapes = std::min<size_t>(order.size(), 255);
+        const size_t n_shapes = std::min<size_t>(order.size(), g_shape_cap.load());
         std::unordered_map<std::string, uint8_t> code_of;
         shape_table.resize(n_shapes * row_bytes);
         for (size_t k = 0; k < n_shapes; k++) {

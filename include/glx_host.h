@@ -42,6 +42,9 @@ int glxh_batch_pin(glxh_batch* b);
  * batch is pinned; owned by the batch. Pass it to glx_upload_wire_on. GLX_E_NOT_IMPLEMENTED when the batch has no wire form
  * (multi-sample datasets). */
 int glxh_batch_wire(glxh_batch* b, const glx_wire** wire);
+/* test aid: rows of the shape table of wire forms built from now on (GLX_WF_SHAPES; default and maximum 255) — a small cap sends
+ * the records of rarer shapes through the exception list */
+void glxh_debug_wire_shape_cap(uint32_t cap);
 void glxh_batch_free(glxh_batch* b);
 const glx_config* glxh_config(const glxh_batch* b);
 const glx_records* glxh_records(const glxh_batch* b);

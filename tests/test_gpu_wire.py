@@ -107,3 +107,19 @@ def test_wire_empty(ctx):
     dev.close()
     b = synth_cases.make("c2", n_samples=7, n_sites=40, region_len=40, frac_uncovered=1.0)  # sites but (almost) no records
     check(ctx, b)
+
+
+@pytest.mark.parametrize("cap", [0, 2])
+def test_wire_shape_exceptions(ctx, cap):
+    """GLX_WF_SHAPES with a shape table too small for the cohort: most records take the exception path of glx_wire_shapes_kernel
+    (code 0xFF, own row found by binary search). The expanded store must still equal the full-width one, outputs the oracle's."""
+    import glnexus_b200
+    glnexus_b200.wire_shape_cap(cap)
+    try:
+        check(ctx, synth_cases.make("c5", n_samples=300, n_sites=1500, region_len=45000))
+        for seed in (7, 8, 9, 10):
+            b = fuzz_cases.build_batch(seed)
+            if b.has_fast_path:
+                check(ctx, b)
+    finally:
+        glnexus_b200.wire_shape_cap(255)

@@ -33,3 +33,21 @@ def test_wire_shapes_fuzz_and_golden(built):
                 assert bad in (0, -1), f"{name}: {bad}"
                 n += bad == 0
     assert n >= 60
+
+
+@pytest.mark.parametrize("cap", [0, 1, 3])
+def test_wire_shapes_exception_list(built, cap):
+    """A cohort with more shapes than the table holds: the records of the rarer shapes carry code 0xFF and find their own row by
+    binary search in the sorted exception list (forced here by capping the table at `cap` rows)."""
+    import glnexus_b200
+    glnexus_b200.wire_shape_cap(cap)
+    try:
+        b = synth_cases.make("c5", n_samples=60, n_sites=800, region_len=24000)
+        bad, n_shapes, n_exc = emu_lib.wire_shapes_check(b)
+        assert bad == 0 and n_shapes == cap and n_exc > 0
+        for seed in range(400, 420):
+            fb = fuzz_cases.build_batch(seed)
+            bad, _, _ = emu_lib.wire_shapes_check(fb)
+            assert bad in (0, -1)
+    finally:
+        glnexus_b200.wire_shape_cap(255)
