@@ -288,7 +288,21 @@ std::string bgzf_block_stored(const uint8_t* p, size_t n);
 std::string bgzf_eof_block();
 
 // N2 (start): the compact wire form of the batch's record store (glx_wire, include/glx.h) — glx_wire_host.cc
-Status build_wire(const PackedBatch& b, std::vector<uint8_t>& wire);
+// bytes whose resize() leaves them uninitialised: the wire buffer's pages are first touched by the threads that fill them
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = default_init_allocator<U>;
+    };
+    template <class U, class... A>
+    void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U;
+        else ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+using WireBytes = std::vector<uint8_t, default_init_allocator<uint8_t>>;
+Status build_wire(const PackedBatch& b, WireBytes& wire);
 void set_wire_shape_cap(uint32_t cap);  // test aid: rows of the wire form's shape table (default and maximum 255)
 
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard
@@ -382,6 +396,6 @@ struct glxh_batch {
     glx::PackedBatch b;
     bool pinned = false;
     std::vector<void*> pinned_ptrs;
-    std::vector<uint8_t> wire;  // built on demand (glxh_batch_wire)
+    glx::WireBytes wire;  // built on demand (glxh_batch_wire)
     bool wire_pinned = false;
 };

@@ -51,3 +51,20 @@ def test_wire_shapes_exception_list(built, cap):
             assert bad in (0, -1)
     finally:
         glnexus_b200.wire_shape_cap(255)
+
+
+def test_wire_bytes_are_reproducible(built):
+    """The wire buffer is allocated uninitialised and filled by several threads: every byte — section padding included — must be
+    written. Two builds of the same cohort (fresh allocations, other buffers freed in between) must be identical, and rebuilding with
+    a poisoned allocator state must not change them."""
+    import ctypes as C
+
+    def image(seed_fill):
+        junk = bytearray([seed_fill]) * (64 << 20)  # dirty the heap the next allocation is likely to reuse
+        del junk
+        b = synth_cases.make("c2", n_samples=400, n_sites=4000, region_len=4000)  # > 65,536 records: the multi-threaded path
+        ptr, n = b.wire()
+        return C.string_at(ptr, n)
+
+    a, b2 = image(0xAA), image(0x55)
+    assert a == b2
