@@ -497,6 +497,10 @@ def main():
                              "from pinned host memory, expansion + all genotyping kernels, the on-device BCF2 record encoder + BGZF (DEFLATE, CRC-32), D2H of the finished BGZF "
                              "blocks into pinned host memory; every rank streams its own contiguous site range of one cohort") % args.depth,
                     "wire_build_s_untimed": wire_s, "wire_bytes_per_record": wire_bytes / max(1, sum(b.n_records for b in batches)),
+                    "host_packing": {"wire_build_ms_per_batch": wire_s / max(1, len(batches)) * 1e3, "threads": min(16, os.cpu_count() or 1),
+                                     "what": "full-width record store -> wire form (glx::build_wire) + cudaHostRegister of the buffer, once per range batch, "
+                                             "outside the timed region (a production caller builds batch i+1 while batch i is on the device; at this rate the "
+                                             "host side, not the GPU, bounds a single stream)"},
                     "d2h_bytes_per_cell": head["d2h"] / max(1, head["cells"]), "h2d_bytes_per_cell": head["h2d"] / max(1, head["cells"]),
                     "uncompressed_bcf_bytes_per_cell": head["raw"] / max(1, head["cells"]),
                     "other_modes": {m: {"cells_per_s": e2e_red[m]["cells"] / e2e_red[m]["s"], "d2h_bytes_per_cell": e2e_red[m]["d2h"] / max(1, e2e_red[m]["cells"])}
