@@ -107,3 +107,28 @@ def test_fuzz_multi_sample_gpu(built):
             n_ok += 1
     ctx.close()
     assert n_ok >= 60
+
+
+def test_multi_sample_slices_concatenate(built):
+    """Range sharding of a cohort with multi-sample gVCFs (glxh_batch_slice carries the datasets' GT and value pools): the two halves'
+    columns, computed separately, concatenate to the whole batch's (site-major arrays)."""
+    n = 0
+    for seed in range(7000, 7060):
+        b = fuzz_cases.build_batch(seed, multi=True)
+        if b.has_fast_path or b.n_sites < 3:
+            continue
+        orc, ref = _oracle(b)
+        if orc != 0:
+            continue
+        want = {k: v.copy() for k, v in ref.arrays().items()}
+        cut = b.n_sites // 2
+        got = {k: [] for k in want}
+        for part in (b.slice(0, cut), b.slice(cut, b.n_sites)):
+            o = part.alloc_out()
+            assert emu_lib.general_batch(part, o) == 0
+            for k, v in o.arrays().items():
+                got[k].append(v.copy())
+        for k in want:
+            assert np.array_equal(np.concatenate(got[k]), want[k]), f"seed {seed}: column {k} of the halves differs from the whole"
+        n += 1
+    assert n >= 30
