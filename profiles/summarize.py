@@ -13,6 +13,7 @@ KEYS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak (this ncu's name in --set full)"),
     ("FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak, dram__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("FBSP.TriageCompute.dram__read_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM read throughput % of peak"),
     ("FBSP.TriageCompute.dram__write_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM write throughput % of peak"),
