@@ -123,6 +123,8 @@ def lib():
     L.glxh_batch_wire.restype = C.c_int
     L.glxh_debug_wire_shape_cap.argtypes = [C.c_uint32]
     L.glxh_debug_wire_shape_cap.restype = None
+    L.glxh_debug_pack_threads.argtypes = [C.c_int]
+    L.glxh_debug_pack_threads.restype = None
     L.glx_upload_wire_on.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.glx_upload_wire_on.restype = C.c_int
     L.glx_debug_compare_records.argtypes = [vp, vp, vp, C.POINTER(C.c_uint32)]
@@ -820,3 +822,8 @@ def preset_text(name):
 def wire_shape_cap(cap=255):
     """Test aid: rows of the shape table of wire forms built from now on (default and maximum 255)."""
     lib().glxh_debug_wire_shape_cap(cap)
+
+
+def pack_threads(n=0):
+    """Test aid: threads of the record packer for batches built from now on (0 = chosen from the input's size)."""
+    lib().glxh_debug_pack_threads(n)

@@ -3,10 +3,12 @@
 #include "glx_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace glx {
 
@@ -704,6 +706,10 @@ static bool is_deletion(const std::string& ref, const std::string& alt) {
     return true;
 }
 
+// threads of pack_records: 0 = by the size of the input (tests force 1 and several to compare the two)
+static std::atomic<int> g_pack_threads{0};
+void set_pack_threads(int n) { g_pack_threads = n < 0 ? 0 : n; }
+
 Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInfo& hdr, const std::vector<std::string>& samples,
                     PackedBatch& b) {
     const glx_config& c = b.cfg;
@@ -738,31 +744,45 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
     }
     b.filter_names.assign(filt.begin(), filt.end());
 
-    size_t R = 0;
-    for (const auto& o : order) R += o.second->records.size();
-    b.ds_rec_off.assign(1, 0);
+    // Datasets are independent: each is packed by one of T threads into the per-record arrays (at its record base, known up front) and
+    // into pools of its own (values, GT pairs, allele descriptors, allele strings); the pools are then laid end to end in dataset order
+    // and the offsets that point into them shifted by the dataset's base — the same bytes a serial pass writes.
+    const size_t nD = order.size();
+    std::vector<size_t> rec_base(nD + 1, 0);
+    for (size_t d = 0; d < nD; d++) rec_base[d + 1] = rec_base[d] + order[d].second->records.size();
+    const size_t R = rec_base[nD];
+    b.ds_rec_off.assign(rec_base.begin(), rec_base.end());
     b.ds_n_sample.clear();
     b.ds_sample_off.assign(1, 0);
     b.sample_out.clear();
-    b.r_beg.clear(); b.r_end.clear(); b.r_maxend.clear(); b.r_qual.clear(); b.r_n_allele.clear(); b.r_flags.clear();
-    b.r_filt.clear(); b.r_gt.clear(); b.r_allele_off.clear();
-    b.col_val.assign((size_t)c.n_cols * R, 0);
-    b.col_len.assign((size_t)c.n_cols * R, GLX_LEN_ABSENT);
-    b.pool.clear(); b.gt_pool.clear();
-    b.al_len.clear(); b.al_str.clear(); b.al_flags.clear(); b.al_prefix.clear(); b.al_pool.clear();
-
-    size_t r_idx = 0;
     for (const auto& o : order) {
-        const GvcfDataset& ds = *o.second;
-        const uint32_t ns = (uint32_t)ds.samples.size();
-        b.ds_n_sample.push_back(ns);
-        for (const auto& sm : ds.samples) {
+        b.ds_n_sample.push_back((uint32_t)o.second->samples.size());
+        for (const auto& sm : o.second->samples) {
             auto it = samples_index.find(sm);
             b.sample_out.push_back(it == samples_index.end() ? -1 : it->second);
         }
         b.ds_sample_off.push_back((uint32_t)b.sample_out.size());
+    }
+    b.r_beg.assign(R, 0); b.r_end.assign(R, 0); b.r_maxend.assign(R, 0); b.r_qual.assign(R, 0.0f); b.r_n_allele.assign(R, 0); b.r_flags.assign(R, 0);
+    b.r_filt.assign(R, 0); b.r_gt.assign(R, 0); b.r_allele_off.assign(R, 0);
+    b.col_val.assign((size_t)c.n_cols * R, 0);
+    b.col_len.assign((size_t)c.n_cols * R, GLX_LEN_ABSENT);
+    struct Local {
+        std::vector<int32_t> pool, gt_pool;
+        std::vector<uint32_t> al_len, al_str;
+        std::vector<uint8_t> al_flags;
+        std::vector<uint64_t> al_prefix;
+        std::vector<char> al_pool;
+        Status st;
+    };
+    std::vector<Local> loc(nD);
+    auto pack_one = [&](size_t d) -> Status {
+        const GvcfDataset& ds = *order[d].second;
+        Local& L = loc[d];
+        const uint32_t ns = (uint32_t)ds.samples.size();
         int32_t maxend = INT32_MIN;
         int prev_rid = -1, prev_beg = -1;
+        size_t r_idx = rec_base[d];
         for (const auto& r : ds.records) {
             if (r.n_sample != (int)ns) return Status::Invalid("gVCF record doesn't have expected # of samples", ds.name);
             if (r.alleles.size() > GLX_MAX_ALLELES) return Status::NotImplemented("pack_records: more record alleles than GLX_MAX_ALLELES", ds.name);
@@ -771,12 +791,12 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
             prev_rid = r.rid;
             prev_beg = r.pos;
             maxend = std::max(maxend, r.pos + r.rlen);
-            b.r_beg.push_back(r.pos);
-            b.r_end.push_back(r.pos + r.rlen);
-            b.r_maxend.push_back(maxend);
-            b.r_qual.push_back(r.qual);
+            b.r_beg[r_idx] = r.pos;
+            b.r_end[r_idx] = r.pos + r.rlen;
+            b.r_maxend[r_idx] = maxend;
+            b.r_qual[r_idx] = r.qual;
             const size_t na = r.alleles.size();
-            b.r_n_allele.push_back((uint8_t)na);
+            b.r_n_allele[r_idx] = (uint8_t)na;
             // is_gvcf_ref_record, src/types.cc:978-980
             const bool is_ref = na == 1 || (na == 2 && is_symbolic_allele(r.alleles[1]));
             uint8_t fl = is_ref ? GLX_RF_IS_REF : 0;
@@ -786,7 +806,7 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
                 auto it = std::lower_bound(b.filter_names.begin(), b.filter_names.end(), f);
                 if (it != b.filter_names.end() && *it == f) fm |= 1u << (it - b.filter_names.begin());
             }
-            b.r_filt.push_back(fm);
+            b.r_filt[r_idx] = fm;
             // GT (preprocess_record's view of bcf_get_genotypes, src/genotyper.cc:44-57)
             uint32_t gtv = 0;
             if (ns == 1) {
@@ -800,15 +820,15 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
                     fl |= GLX_RF_NO_GT;
             } else {
                 if (r.n_gt == 2) {
-                    gtv = (uint32_t)b.gt_pool.size();
-                    for (auto v : r.gt) b.gt_pool.push_back(v == GLX_INT_VECTOR_END ? v : (v & ~1));
+                    gtv = (uint32_t)L.gt_pool.size();  // (dataset-local: shifted below)
+                    for (auto v : r.gt) L.gt_pool.push_back(v == GLX_INT_VECTOR_END ? v : (v & ~1));
                 } else
                     fl |= GLX_RF_NO_GT;
             }
-            b.r_gt.push_back(gtv);
-            b.r_flags.push_back(fl);
+            b.r_gt[r_idx] = gtv;
+            b.r_flags[r_idx] = fl;
             // allele descriptors (preprocess_record's is_dna / deletion_allele inputs, src/genotyper.cc:59-77)
-            b.r_allele_off.push_back((uint32_t)b.al_len.size());
+            b.r_allele_off[r_idx] = (uint32_t)L.al_len.size();  // (dataset-local)
             if (!is_ref) {
                 const std::string& ref = r.alleles[0];
                 for (size_t i = 0; i < na; i++) {
@@ -817,11 +837,11 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
                     if (is_dna(al)) af |= GLX_AF_IS_DNA;
                     if (is_symbolic_allele(al)) af |= GLX_AF_SYMBOLIC;
                     if (i > 0 && al.size() < (size_t)r.rlen && (size_t)r.rlen == ref.size() && is_deletion(ref, al)) af |= GLX_AF_DELETION;
-                    b.al_len.push_back((uint32_t)al.size());
-                    b.al_flags.push_back(af);
-                    b.al_prefix.push_back(prefix8(al));
-                    b.al_str.push_back((uint32_t)b.al_pool.size());
-                    b.al_pool.insert(b.al_pool.end(), al.begin(), al.end());
+                    L.al_len.push_back((uint32_t)al.size());
+                    L.al_flags.push_back(af);
+                    L.al_prefix.push_back(prefix8(al));
+                    L.al_str.push_back((uint32_t)L.al_pool.size());  // (dataset-local)
+                    L.al_pool.insert(L.al_pool.end(), al.begin(), al.end());
                 }
             }
             // source columns
@@ -848,14 +868,66 @@ Status pack_records(const std::vector<GvcfDataset>& datasets, const VcfHeaderInf
                 b.col_len[(size_t)ci * R + r_idx] = (uint16_t)len;
                 if (ns == 1 && len == 1) b.col_val[(size_t)ci * R + r_idx] = fv->v[0];
                 else {
-                    b.col_val[(size_t)ci * R + r_idx] = (int32_t)b.pool.size();
-                    b.pool.insert(b.pool.end(), fv->v.begin(), fv->v.end());
+                    b.col_val[(size_t)ci * R + r_idx] = (int32_t)L.pool.size();  // (dataset-local)
+                    L.pool.insert(L.pool.end(), fv->v.begin(), fv->v.end());
                 }
             }
             r_idx++;
         }
-        b.ds_rec_off.push_back(r_idx);
+        return Status::OK();
+    };
+    unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), nD, R / 4096 + 1}));
+    if (g_pack_threads.load() > 0) T = (unsigned)std::min<size_t>((size_t)g_pack_threads.load(), std::max<size_t>(nD, 1));
+    auto over_datasets = [&](auto&& fn) {  // fn(d) for every dataset, dynamically shared among T threads
+        if (T <= 1) {
+            for (size_t d = 0; d < nD; d++) fn(d);
+            return;
+        }
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < T; t++)
+            pool.emplace_back([&]() {
+                for (size_t d = next++; d < nD; d = next++) fn(d);
+            });
+        for (auto& th : pool) th.join();
+    };
+    over_datasets([&](size_t d) { loc[d].st = pack_one(d); });
+    for (size_t d = 0; d < nD; d++)
+        if (loc[d].st.bad()) return loc[d].st;  // the first failing dataset, as a serial pass would report
+    std::vector<size_t> pool_base(nD + 1, 0), gt_base(nD + 1, 0), al_base(nD + 1, 0), str_base(nD + 1, 0);
+    for (size_t d = 0; d < nD; d++) {
+        pool_base[d + 1] = pool_base[d] + loc[d].pool.size();
+        gt_base[d + 1] = gt_base[d] + loc[d].gt_pool.size();
+        al_base[d + 1] = al_base[d] + loc[d].al_len.size();
+        str_base[d + 1] = str_base[d] + loc[d].al_pool.size();
     }
+    if (pool_base[nD] > (size_t)INT32_MAX || gt_base[nD] > UINT32_MAX || al_base[nD] > UINT32_MAX || str_base[nD] > UINT32_MAX)
+        return Status::NotImplemented("pack_records: the range's pools exceed 32-bit offsets; use smaller range batches");
+    b.pool.resize(pool_base[nD]);
+    b.gt_pool.resize(gt_base[nD]);
+    b.al_len.resize(al_base[nD]); b.al_str.resize(al_base[nD]); b.al_flags.resize(al_base[nD]); b.al_prefix.resize(al_base[nD]);
+    b.al_pool.resize(str_base[nD]);
+    over_datasets([&](size_t d) {
+        Local& L = loc[d];
+        const uint32_t ns = b.ds_n_sample[d];
+        std::copy(L.pool.begin(), L.pool.end(), b.pool.begin() + pool_base[d]);
+        std::copy(L.gt_pool.begin(), L.gt_pool.end(), b.gt_pool.begin() + gt_base[d]);
+        std::copy(L.al_len.begin(), L.al_len.end(), b.al_len.begin() + al_base[d]);
+        std::copy(L.al_flags.begin(), L.al_flags.end(), b.al_flags.begin() + al_base[d]);
+        std::copy(L.al_prefix.begin(), L.al_prefix.end(), b.al_prefix.begin() + al_base[d]);
+        std::copy(L.al_pool.begin(), L.al_pool.end(), b.al_pool.begin() + str_base[d]);
+        for (size_t a = 0; a < L.al_str.size(); a++) b.al_str[al_base[d] + a] = L.al_str[a] + (uint32_t)str_base[d];
+        for (size_t r = rec_base[d]; r < rec_base[d + 1]; r++) {
+            b.r_allele_off[r] += (uint32_t)al_base[d];
+            if (ns != 1 && !(b.r_flags[r] & GLX_RF_NO_GT)) b.r_gt[r] += (uint32_t)gt_base[d];
+            for (uint32_t ci = 0; ci < c.n_cols; ci++) {
+                const uint16_t len = b.col_len[(size_t)ci * R + r];
+                if (len >= 0xFFF0 || (ns == 1 && len == 1)) continue;
+                b.col_val[(size_t)ci * R + r] += (int32_t)pool_base[d];
+            }
+        }
+        L = Local();
+    });
     b.recs.n_datasets = (uint32_t)order.size();
     b.recs.n_samples_out = (uint32_t)samples.size();
     b.recs.n_cols = c.n_cols;

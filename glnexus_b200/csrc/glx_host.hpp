@@ -303,6 +303,7 @@ struct default_init_allocator : std::allocator<T> {
 };
 using WireBytes = std::vector<uint8_t, default_init_allocator<uint8_t>>;
 Status build_wire(const PackedBatch& b, WireBytes& wire);
+void set_pack_threads(int n);  // test aid: threads of pack_records (0 = chosen from the input's size)
 void set_wire_shape_cap(uint32_t cap);  // test aid: rows of the wire form's shape table (default and maximum 255)
 
 // Multi-GPU sharding by contiguous site range (no collective): cut points of equal output weight, and the shard

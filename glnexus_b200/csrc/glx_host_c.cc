@@ -1,4 +1,6 @@
 // glx_host_c.cc — C entry points of include/glx_host.h over the C++ host pipeline.
+#include <thread>
+#include <atomic>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +45,29 @@ void out_release(void* p, bool pinned) {
 
 extern "C" {
 
+// read every dataset's gVCF text (independent: one of up to 16 threads each); statuses come back in dataset order
+static void read_datasets(int n_datasets, const char* const* dataset_names, const char* const* vcf_texts, bool ingest_rules, std::vector<glx::GvcfDataset>& datasets,
+                          std::vector<glx::VcfHeaderInfo>& headers, std::vector<glx::Status>& status) {
+    datasets.assign(n_datasets, glx::GvcfDataset());
+    headers.assign(n_datasets, glx::VcfHeaderInfo());
+    status.assign(n_datasets, glx::Status::OK());
+    size_t bytes = 0;
+    for (int i = 0; i < n_datasets; i++) bytes += vcf_texts[i] ? strlen(vcf_texts[i]) : 0;
+    const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), (size_t)n_datasets, bytes / (1u << 20) + 1}));
+    auto one = [&](int i) { status[i] = glx::read_vcf_text(vcf_texts[i], dataset_names[i], ingest_rules, headers[i], datasets[i]); };
+    if (T <= 1) {
+        for (int i = 0; i < n_datasets; i++) one(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; t++)
+        pool.emplace_back([&]() {
+            for (int i = next++; i < n_datasets; i = next++) one(i);
+        });
+    for (auto& th : pool) th.join();
+}
+
 int glxh_batch_from_text(const char* preset, const char* config_text, const char* sites_text, int n_datasets, const char* const* dataset_names,
                          const char* const* vcf_texts, const char* contig, int test_ingest_rules, glxh_batch** ans, char* err, size_t errlen) {
     using namespace glx;
@@ -58,11 +83,14 @@ int glxh_batch_from_text(const char* preset, const char* config_text, const char
         s = genotyper_config::of_text(config_text, cfg);
         if (s.bad()) return fail(s, err, errlen);
     }
-    std::vector<GvcfDataset> datasets(n_datasets);
+    std::vector<GvcfDataset> datasets;
+    std::vector<VcfHeaderInfo> headers;
+    std::vector<Status> read_status;
+    read_datasets(n_datasets, dataset_names, vcf_texts, test_ingest_rules != 0, datasets, headers, read_status);
     VcfHeaderInfo hdr0, hdr_all;
     for (int i = 0; i < n_datasets; i++) {
-        VcfHeaderInfo h;
-        s = read_vcf_text(vcf_texts[i], dataset_names[i], test_ingest_rules != 0, h, datasets[i]);
+        VcfHeaderInfo& h = headers[i];
+        s = read_status[i];
         if (s.bad()) return fail(s, err, errlen);
         if (i == 0) hdr0 = h;  // VCFData::contigs serves the first dataset's contigs (test/utils.cc:128-131)
         else {
@@ -183,6 +211,7 @@ int glxh_batch_pin(glxh_batch* hb) {
 }
 
 void glxh_debug_wire_shape_cap(uint32_t cap) { glx::set_wire_shape_cap(cap); }
+void glxh_debug_pack_threads(int n) { glx::set_pack_threads(n); }
 
 int glxh_batch_wire(glxh_batch* hb, const glx_wire** wire) {
     if (!hb || !wire) return GLX_E_INVALID;
@@ -217,11 +246,14 @@ int glxh_genotype_sites(const char* preset, const char* config_text, const char*
         s = genotyper_config::of_text(config_text, cfg);
         if (s.bad()) return fail(s, err, errlen);
     }
-    std::vector<GvcfDataset> datasets(n_datasets);
+    std::vector<GvcfDataset> datasets;
+    std::vector<VcfHeaderInfo> headers;
+    std::vector<Status> read_status;
+    read_datasets(n_datasets, dataset_names, vcf_texts, test_ingest_rules != 0, datasets, headers, read_status);
     VcfHeaderInfo hdr_all;
     for (int i = 0; i < n_datasets; i++) {
-        VcfHeaderInfo h;
-        s = read_vcf_text(vcf_texts[i], dataset_names[i], test_ingest_rules != 0, h, datasets[i]);
+        VcfHeaderInfo& h = headers[i];
+        s = read_status[i];
         if (s.bad()) return fail(s, err, errlen);
         if (i == 0) {
             hdr_all.contigs = h.contigs;

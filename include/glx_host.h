@@ -45,6 +45,9 @@ int glxh_batch_wire(glxh_batch* b, const glx_wire** wire);
 /* test aid: rows of the shape table of wire forms built from now on (GLX_WF_SHAPES; default and maximum 255) — a small cap sends
  * the records of rarer shapes through the exception list */
 void glxh_debug_wire_shape_cap(uint32_t cap);
+/* test aid: threads pack_records uses for the batches built from now on (0 = chosen from the input's size: datasets are packed
+ * independently and their pools laid end to end) */
+void glxh_debug_pack_threads(int n);
 void glxh_batch_free(glxh_batch* b);
 const glx_config* glxh_config(const glxh_batch* b);
 const glx_records* glxh_records(const glxh_batch* b);
