@@ -31,6 +31,15 @@ struct uint3x {
 };
 __device__ __forceinline__ uint3x add3(uint3x x, uint3x y) { return uint3x{x.a + y.a, x.b + y.b, x.c + y.c}; }
 
+__device__ __forceinline__ uint32_t wire_al_len(const DWire& W, uint64_t a) {
+    const uint8_t* p = W.base + W.off[GLX_WS_AL_LEN];
+    if (W.flags & GLX_WF_ALLEN8) return p[a];
+    return (W.flags & GLX_WF_ALLEN16) ? reinterpret_cast<const uint16_t*>(p)[a] : reinterpret_cast<const uint32_t*>(p)[a];
+}
+__device__ __forceinline__ uint32_t wire_filt(const DWire& W, uint64_t i) {
+    const uint8_t* p = W.base + W.off[GLX_WS_FILT];
+    return (W.flags & GLX_WF_FILT8) ? (uint32_t)p[i] : reinterpret_cast<const uint32_t*>(p)[i];
+}
 __device__ __forceinline__ uint32_t wire_col_len(const DWire& W, uint64_t c, uint64_t r) {
     if (W.flags & GLX_WF_COLLEN8) {
         const uint8_t v = W.sec_collen()[c * W.n_records + r];
@@ -139,8 +148,7 @@ __global__ void __launch_bounds__(GLX_WIRE_BLOCK) glx_wire_al_sums_kernel(const 
     uint3x t{0, 0, 0};
     for (uint32_t i = 0; i < GLX_WIRE_ITEMS; i++)
         if (a0 + i < W.n_al)
-            t.a += (W.flags & GLX_WF_ALLEN16) ? reinterpret_cast<const uint16_t*>(W.base + W.off[GLX_WS_AL_LEN])[a0 + i]
-                                              : reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_AL_LEN])[a0 + i];
+            t.a += wire_al_len(W, a0 + i);
     uint3x tot;
     block_scan3(t, &tot);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
@@ -153,8 +161,7 @@ __global__ void __launch_bounds__(GLX_WIRE_BLOCK) glx_wire_alleles_kernel(const 
     for (uint32_t i = 0; i < GLX_WIRE_ITEMS; i++) {
         len[i] = 0;
         if (a0 + i < W.n_al)
-            len[i] = (W.flags & GLX_WF_ALLEN16) ? reinterpret_cast<const uint16_t*>(W.base + W.off[GLX_WS_AL_LEN])[a0 + i]
-                                                : reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_AL_LEN])[a0 + i];
+            len[i] = wire_al_len(W, a0 + i);
         t.a += len[i];
     }
     uint3x tot;
@@ -211,8 +218,7 @@ __global__ void __launch_bounds__(GLX_WIRE_BLOCK) glx_wire_records_kernel(const 
             O.gt[r] = reinterpret_cast<const uint32_t*>(W.sec_gt())[r];
         const bool var = !(flags[r] & GLX_RF_IS_REF);
         O.qual[r] = var ? reinterpret_cast<const float*>(W.base + W.off[GLX_WS_QUAL])[run.a] : 0.0f;
-        O.filt[r] = (W.flags & GLX_WF_FILT_VARIANT) ? (var ? reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_FILT])[run.a] : 0u)
-                                                    : reinterpret_cast<const uint32_t*>(W.base + W.off[GLX_WS_FILT])[r];
+        O.filt[r] = (W.flags & GLX_WF_FILT_VARIANT) ? (var ? wire_filt(W, run.a) : 0u) : wire_filt(W, r);
         O.allele_off[r] = run.b;
         uint32_t po = run.c;
         for (uint32_t c = 0; c < W.n_cols; c++) {

@@ -52,7 +52,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
     // ---- what fits (one pass over the records on T threads; per-chunk results merged below) ----
     const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     struct Part {
-        bool len16 = true, gt8 = true, collen8 = true, pool16 = true, pool_order = true;
+        bool len16 = true, gt8 = true, collen8 = true, pool16 = true, pool_order = true, filt8 = true;
         uint64_t n_variant = 0, pool_units = 0, al_units = 0;
         bool al_order = true;
         std::vector<uint32_t> exc;
@@ -67,6 +67,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
         for (uint64_t i = lo; i < hi; i++) {
             const int64_t len = (int64_t)r.end[i] - r.beg[i];
             if (len < 0 || len > 65535) P.len16 = false;
+            if (r.filt[i] > 255u) P.filt8 = false;
             if (!(r.flags[i] & GLX_RF_IS_REF)) {
                 P.n_variant++;
                 P.al_units += r.n_allele[i];
@@ -90,7 +91,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
             }
         }
     });
-    bool len16 = true, gt8 = true, collen8 = true, pool16 = true, allen16 = true;
+    bool len16 = true, gt8 = true, collen8 = true, pool16 = true, allen16 = true, allen8 = true, filt8 = true;
     uint64_t n_variant = 0;
     std::vector<uint32_t> exc;  // (record, maxend) pairs where maxend != end
     std::vector<uint64_t> pool_base(T + 1, 0), var_base(T + 1, 0), al_base(T + 1, 0);
@@ -99,6 +100,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
         len16 = len16 && P.len16;
         gt8 = gt8 && P.gt8;
         collen8 = collen8 && P.collen8;
+        filt8 = filt8 && P.filt8;
         exc.insert(exc.end(), P.exc.begin(), P.exc.end());
         pool_base[t + 1] = pool_base[t] + P.pool_units;
         var_base[t + 1] = var_base[t] + P.n_variant;
@@ -143,12 +145,13 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
     // allele strings must be laid out in allele order for their offsets to be prefix sums (checked chunk by chunk: the lengths' sums first)
     {
         std::vector<uint64_t> len_base(T + 1, 0);
-        std::vector<char> ok16(T, 1), okstr(T, 1);
+        std::vector<char> ok16(T, 1), ok8(T, 1), okstr(T, 1);
         parallel_chunks(r.n_al, T, [&](unsigned t, uint64_t lo, uint64_t hi) {
             uint64_t sum = 0;
             for (uint64_t a = lo; a < hi; a++) {
                 sum += r.al_len[a];
                 if (r.al_len[a] > 65535) ok16[t] = 0;
+                if (r.al_len[a] > 255) ok8[t] = 0;
             }
             len_base[t + 1] = sum;
         });
@@ -162,6 +165,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
         });
         for (unsigned t = 0; t < T; t++) {
             allen16 = allen16 && ok16[t];
+            allen8 = allen8 && ok8[t];
             if (!okstr[t]) return Status::NotImplemented("build_wire: allele strings are not in allele order");
         }
         if (len_base[T] != r.n_al_pool) return Status::NotImplemented("build_wire: allele string pool has bytes no allele refers to");
@@ -172,7 +176,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
     h.n_variant = n_variant;
     h.n_maxend_exc = exc.size() / 2;
     h.flags = (len16 ? GLX_WF_LEN16 : 0) | (gt8 ? GLX_WF_GT8 : 0) | (collen8 ? GLX_WF_COLLEN8 : 0) | (pool16 ? GLX_WF_POOL16 : 0) |
-              (filt_variant ? GLX_WF_FILT_VARIANT : 0) | (allen16 ? GLX_WF_ALLEN16 : 0);
+              (filt_variant ? GLX_WF_FILT_VARIANT : 0) | (allen16 ? GLX_WF_ALLEN16 : 0) | (allen8 ? GLX_WF_ALLEN8 : 0) | (filt8 ? GLX_WF_FILT8 : 0);
     // ---- record shapes: (flags, n_allele, GT pair, column lengths) as one byte per record (GLX_WF_SHAPES) ----
     // A row is 4 + n_cols <= 16 bytes (more columns: no shapes), handled as two 64-bit words. Runs of equal shapes (consecutive
     // reference bands) cost one comparison; the rest goes through a small open-addressing table per thread.
@@ -327,11 +331,11 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
     place(GLX_WS_NALLELE, shapes ? 0 : R);
     place(GLX_WS_GT, shapes ? 0 : R * (gt8 ? 2 : 4));
     place(GLX_WS_QUAL, n_variant * 4);
-    place(GLX_WS_FILT, (filt_variant ? n_variant : R) * 4);
+    place(GLX_WS_FILT, (filt_variant ? n_variant : R) * (filt8 ? 1 : 4));
     place(GLX_WS_COL_LEN, shapes ? 0 : C * R * (collen8 ? 1 : 2));
     place(GLX_WS_COL_VAL, colval_bytes);
     place(GLX_WS_POOL, r.n_pool * (pool16 ? 2 : 4));
-    place(GLX_WS_AL_LEN, r.n_al * (allen16 ? 2 : 4));
+    place(GLX_WS_AL_LEN, r.n_al * (allen8 ? 1 : (allen16 ? 2 : 4)));
     place(GLX_WS_AL_POOL, r.n_al_pool);
     place(GLX_WS_MAXEND_EXC, exc.size() * 4);
     place(GLX_WS_SHAPE, shape_code.size());
@@ -366,6 +370,7 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
         uint32_t* g32 = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_GT]);
         float* q = reinterpret_cast<float*>(p + h.off[GLX_WS_QUAL]);
         uint32_t* f = reinterpret_cast<uint32_t*>(p + h.off[GLX_WS_FILT]);
+        uint8_t* f8 = p + h.off[GLX_WS_FILT];
         uint8_t* c8 = p + h.off[GLX_WS_COL_LEN];
         uint16_t* c16 = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_COL_LEN]);
         std::vector<size_t> col_off(C + 1, h.off[GLX_WS_COL_VAL]);
@@ -392,10 +397,16 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
                     g32[i] = r.gt[i];
                 if (!(r.flags[i] & GLX_RF_IS_REF)) {
                     q[v] = r.qual[i];
-                    if (filt_variant) f[v] = r.filt[i];
+                    if (filt_variant) {
+                        if (filt8) f8[v] = (uint8_t)r.filt[i];
+                        else f[v] = r.filt[i];
+                    }
                     v++;
                 }
-                if (!filt_variant) f[i] = r.filt[i];
+                if (!filt_variant) {
+                    if (filt8) f8[i] = (uint8_t)r.filt[i];
+                    else f[i] = r.filt[i];
+                }
             }
             for (uint64_t c = 0; c < C; c++) {
                 int16_t* d16 = reinterpret_cast<int16_t*>(p + col_off[c]);
@@ -418,7 +429,12 @@ Status build_wire(const PackedBatch& b, WireBytes& w) {
         });
     } else
         memcpy(p + h.off[GLX_WS_POOL], r.pool, r.n_pool * 4);
-    if (allen16) {
+    if (allen8) {
+        uint8_t* d = p + h.off[GLX_WS_AL_LEN];
+        parallel_chunks(r.n_al, T, [&](unsigned, uint64_t lo, uint64_t hi) {
+            for (uint64_t a = lo; a < hi; a++) d[a] = (uint8_t)r.al_len[a];
+        });
+    } else if (allen16) {
         uint16_t* d = reinterpret_cast<uint16_t*>(p + h.off[GLX_WS_AL_LEN]);
         parallel_chunks(r.n_al, T, [&](unsigned, uint64_t lo, uint64_t hi) {
             for (uint64_t a = lo; a < hi; a++) d[a] = (uint16_t)r.al_len[a];

@@ -161,6 +161,8 @@ enum {
     GLX_WF_POOL16 = 8,         /* value pool as int16 with BCF's 16-bit sentinels (else int32) */
     GLX_WF_FILT_VARIANT = 16,  /* FILTER masks only for non-reference records (no lifted field reads FILTER) */
     GLX_WF_ALLEN16 = 32,       /* allele lengths as uint16 (else uint32) */
+    GLX_WF_ALLEN8 = 128,       /* allele lengths as uint8 (every allele of the batch is shorter than 256) */
+    GLX_WF_FILT8 = 256,        /* FILTER masks as uint8 (the batch's FILTER dictionary has at most 8 ids) */
     GLX_WF_SHAPES = 64         /* a record's (flags, n_allele, GT pair, column lengths) travel as ONE byte: its row of the batch's shape
                                   table (GLX_WS_SHAPE_TABLE: n_shapes <= 255 rows of 4 + n_cols bytes {flags, n_allele, gt0, gt1, col_len8[]},
                                   the batch's commonest shapes), 0xFF = the record's own row is in GLX_WS_SHAPE_EXC, found by its index in
